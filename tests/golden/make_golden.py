@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Regenerates the fixtures under tests/golden/ from the read-only reference checkout.
+
+Run in the build container only (needs /root/reference). The GPU box never reads /root/reference:
+tests use the committed copies.
+
+  * verbatim copies of reference DATA files (no source code): CAMB transfer tables, paramfiles,
+    tipsy / text goldens of test_13, test_05a, test_02k, test_02m
+  * test_01a_basic_grid/reference_output (9.4 MB, 64^3 tipsy) -> every 61st particle, as .npz
+  * test_19_rounding_errors/reference_grid/grid-0.npy (2 MB float64 64^3) -> [::4, ::4, ::4] subsample
+"""
+import os
+import shutil
+import struct
+import numpy as np
+
+REF = "/root/reference/genetIC/tests"
+EX = "/root/reference/example"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def cp(src, dst):
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    shutil.copyfile(src, dst)
+    os.chmod(dst, 0o644)
+
+
+def read_tipsy(fn):
+    raw = open(fn, "rb").read()
+    a, n, ndim, ngas, ndark, nstar = struct.unpack("<diiiii", raw[:28])
+    return np.frombuffer(raw, dtype=np.float32, count=ndark * 9, offset=32).reshape(ndark, 9)
+
+
+for f in ("camb_transfer_kmax40_z0.dat", "camb_transfer_kmax40_z500.dat"):
+    cp(f"{REF}/{f}", f"{HERE}/{f}")
+cp(f"{EX}/planck_2018_transfer_out.dat", f"{HERE}/planck_2018_transfer_out.dat")
+cp(f"{EX}/paramfile.txt", f"{HERE}/example_paramfile.txt")
+for t, files in {
+    "test_13_parallel_seed": ("paramfile.txt", "reference_output"),
+    "test_05a_seed_old": ("paramfile.txt", "reference_output"),
+    "test_02k_chisquare_onelevel": ("paramfile.txt", "reference.txt"),
+    "test_02m_chisquare_twolevels": ("paramfile.txt", "reference.txt"),
+    "test_01a_basic_grid": ("paramfile.txt",),
+    "test_19_rounding_errors": ("paramfile.txt",),
+}.items():
+    for f in files:
+        cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
+
+d = read_tipsy(f"{REF}/test_01a_basic_grid/reference_output")
+idx = np.arange(0, d.shape[0], 61)
+np.savez_compressed(f"{HERE}/test_01a_basic_grid/particles_every61.npz", index=idx, particles=d[idx])
+g = np.load(f"{REF}/test_19_rounding_errors/reference_grid/grid-0.npy")
+np.savez_compressed(f"{HERE}/test_19_rounding_errors/grid0_every4.npz", grid=g[::4, ::4, ::4])
+print("ok")
