@@ -1,0 +1,125 @@
+// C-ABI: library, memory, host<->device layout copies, FFT entry points.
+#include "../../include/genetic_b200.h"
+#include "fft.cuh"
+
+namespace gx {
+const char *last_error_cstr();
+template <typename T> int mirror(T *field, int n, cudaStream_t st);
+}
+
+using namespace gx;
+
+static int check_n(int n) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  return 0;
+}
+static size_t esize(int dtype) { return dtype == GX_F64 ? 8 : 4; }
+
+extern "C" {
+
+const char *gx_last_error(void) { return gx::last_error_cstr(); }
+int gx_version(void) { return 100; }
+
+int gx_device_count(int *count) {
+  GX_CUDA_CHECK(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int gx_set_device(int device) {
+  GX_CUDA_CHECK(cudaSetDevice(device));
+  return gx::fft::ensure_twiddles();
+}
+
+int gx_synchronize(void *stream) {
+  GX_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) stream));
+  return 0;
+}
+
+unsigned long long gx_launch_count(void) { return gx::g_launch_count; }
+
+size_t gx_field_bytes(int n, int dtype) { return (size_t) 2 * n * n * (n / 2 + 1) * esize(dtype); }
+
+int gx_malloc(void **ptr, size_t bytes) {
+  GX_CUDA_CHECK(cudaMalloc(ptr, bytes));
+  return 0;
+}
+int gx_free(void *ptr) {
+  GX_CUDA_CHECK(cudaFree(ptr));
+  return 0;
+}
+int gx_memset_zero(void *ptr, size_t bytes, void *stream) {
+  GX_CUDA_CHECK(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t) stream));
+  return 0;
+}
+int gx_host_alloc_pinned(void **ptr, size_t bytes) {
+  GX_CUDA_CHECK(cudaMallocHost(ptr, bytes));
+  return 0;
+}
+int gx_host_free_pinned(void *ptr) {
+  GX_CUDA_CHECK(cudaFreeHost(ptr));
+  return 0;
+}
+int gx_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+  GX_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+  return 0;
+}
+int gx_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  GX_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+  return 0;
+}
+int gx_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+  GX_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+  return 0;
+}
+
+int gx_field_upload(void *dev_field, const void *host, int n, int dtype, int layout, void *stream) {
+  if (check_n(n)) return 1;
+  const size_t es = esize(dtype);
+  if (layout == GX_LAYOUT_FOURIER) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(dev_field, host, gx_field_bytes(n, dtype), cudaMemcpyHostToDevice, (cudaStream_t) stream));
+  } else if (layout == GX_LAYOUT_REAL) {
+    // rows of n reals on the host -> rows of n+2 reals on the device
+    GX_CUDA_CHECK(cudaMemcpy2DAsync(dev_field, (size_t) (n + 2) * es, host, (size_t) n * es, (size_t) n * es,
+                                    (size_t) n * n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+  } else {
+    return gx::fail("bad layout");
+  }
+  return 0;
+}
+
+int gx_field_download(void *host, const void *dev_field, int n, int dtype, int layout, void *stream) {
+  if (check_n(n)) return 1;
+  const size_t es = esize(dtype);
+  if (layout == GX_LAYOUT_FOURIER) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(host, dev_field, gx_field_bytes(n, dtype), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+  } else if (layout == GX_LAYOUT_REAL) {
+    GX_CUDA_CHECK(cudaMemcpy2DAsync(host, (size_t) n * es, dev_field, (size_t) (n + 2) * es, (size_t) n * es,
+                                    (size_t) n * n, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+  } else {
+    return gx::fail("bad layout");
+  }
+  return 0;
+}
+
+int gx_fft_forward(void *field, int n, int dtype, void *stream) {
+  if (check_n(n)) return 1;
+  if (dtype == GX_F64) return gx::fft::fft3d<double>((double *) field, n, -1, (cudaStream_t) stream);
+  if (dtype == GX_F32) return gx::fft::fft3d<float>((float *) field, n, -1, (cudaStream_t) stream);
+  return gx::fail("bad dtype");
+}
+
+int gx_fft_inverse(void *field, int n, int dtype, void *stream) {
+  if (check_n(n)) return 1;
+  int rc;
+  if (dtype == GX_F64) {
+    rc = gx::mirror<double>((double *) field, n, (cudaStream_t) stream);
+    return rc ? rc : gx::fft::fft3d<double>((double *) field, n, 1, (cudaStream_t) stream);
+  }
+  if (dtype == GX_F32) {
+    rc = gx::mirror<float>((float *) field, n, (cudaStream_t) stream);
+    return rc ? rc : gx::fft::fft3d<float>((float *) field, n, 1, (cudaStream_t) stream);
+  }
+  return gx::fail("bad dtype");
+}
+
+}  // extern "C"

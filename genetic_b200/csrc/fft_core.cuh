@@ -1,0 +1,244 @@
+// In-register / shared-memory 1-D complex FFT building block (power-of-two lengths 2..4096).
+//
+// Replaces the FFTW plans of the reference (tools/numerics/fourier.hpp:521-563,
+// fftw_plan_dft_r2c_3d / c2r_3d) as the line transform inside each of the three 1-D passes.
+//
+// Structure: mixed-radix decimation-in-frequency, radices from {2,4,8,16}. A line of NC points is
+// owned by P = NC/E threads, each holding E points in registers (E = first radix). Stage 0 works on
+// the registers as loaded (thread t holds x[t + i*P]); later stages exchange through one shared-memory
+// copy of the line (in place: a butterfly reads and writes the same R positions), with one
+// __syncthreads between stages. The last stage hands each output to an `emit(k, value)` callback with
+// its natural frequency index k (mixed-radix digit reversal is resolved in index arithmetic, not by a
+// data pass). Everything here is __host__ __device__ so the index math is unit-tested on the CPU
+// (tests/host/fft_core_host_test.cu) -- there is no GPU in the build container.
+#pragma once
+#include "gx_common.cuh"
+
+namespace gx {
+namespace fft {
+
+// DIR = -1: forward, kernel exp(-2 pi i nk/N) (FFTW_FORWARD); DIR = +1: backward.
+template <int DIR, typename C> GX_HD C mul_i_dir(C a) {  // a * (DIR * i)
+  C r;
+  if (DIR < 0) { r.x = a.y; r.y = -a.x; } else { r.x = -a.y; r.y = a.x; }
+  return r;
+}
+
+template <typename T> struct K {
+  static constexpr T rs2 = (T) 0.70710678118654752440084436210485L;  // 1/sqrt(2)
+  static constexpr T c16 = (T) 0.92387953251128675612818318939679L;  // cos(pi/8)
+  static constexpr T s16 = (T) 0.38268343236508977172845998403040L;  // sin(pi/8)
+};
+
+// a * W8^k, W8 = exp(DIR * 2 pi i / 8)
+template <int DIR, int k, typename T> GX_HD cplx<T> mul_w8(cplx<T> a) {
+  constexpr T h = K<T>::rs2;
+  cplx<T> r;
+  if (k == 0) return a;
+  if (k == 2) return mul_i_dir<DIR>(a);
+  if (k == 1) {
+    if (DIR < 0) { r.x = (a.x + a.y) * h; r.y = (a.y - a.x) * h; }
+    else { r.x = (a.x - a.y) * h; r.y = (a.x + a.y) * h; }
+    return r;
+  }
+  // k == 3
+  if (DIR < 0) { r.x = (a.y - a.x) * h; r.y = -(a.x + a.y) * h; }
+  else { r.x = -(a.x + a.y) * h; r.y = (a.x - a.y) * h; }
+  return r;
+}
+
+// a * W16^k for k in {1,3,9} (the others reduce to W8 powers)
+template <int DIR, int k, typename T> GX_HD cplx<T> mul_w16(cplx<T> a) {
+  constexpr T c = K<T>::c16, s = K<T>::s16;
+  // W16^1 = (c, DIR*s); W16^3 = (s, DIR*c); W16^9 = -(W16^1)
+  T wr = (k == 3) ? s : c, wi = (k == 3) ? c : s;
+  if (DIR < 0) wi = -wi;
+  cplx<T> r;
+  r.x = a.x * wr - a.y * wi;
+  r.y = a.x * wi + a.y * wr;
+  if (k == 9) { r.x = -r.x; r.y = -r.y; }
+  return r;
+}
+
+template <int DIR, typename C> GX_HD void r2(C &a0, C &a1) {
+  C t = a0;
+  a0 = cadd(t, a1);
+  a1 = csub(t, a1);
+}
+
+// natural-order radix-4: (a0..a3) <- DFT4
+template <int DIR, typename C> GX_HD void r4(C &a0, C &a1, C &a2, C &a3) {
+  C t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_i_dir<DIR>(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a1 = cadd(t1, t3);
+  a2 = csub(t0, t2);
+  a3 = csub(t1, t3);
+}
+
+template <int DIR, typename T> GX_HD void r8(cplx<T> *a) {
+  using C = cplx<T>;
+  r4<DIR>(a[0], a[2], a[4], a[6]);  // E0..E3 in a0,a2,a4,a6
+  r4<DIR>(a[1], a[3], a[5], a[7]);  // O0..O3 in a1,a3,a5,a7
+  C o0 = a[1], o1 = mul_w8<DIR, 1, T>(a[3]), o2 = mul_w8<DIR, 2, T>(a[5]), o3 = mul_w8<DIR, 3, T>(a[7]);
+  C e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+  a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+  a[1] = cadd(e1, o1); a[5] = csub(e1, o1);
+  a[2] = cadd(e2, o2); a[6] = csub(e2, o2);
+  a[3] = cadd(e3, o3); a[7] = csub(e3, o3);
+}
+
+template <int DIR, typename T> GX_HD void r16(cplx<T> *a) {
+  using C = cplx<T>;
+  // four DFT4 over a[j + 4r] (r = 0..3): a[j + 4q] <- B_j[q]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r4<DIR>(a[j], a[j + 4], a[j + 8], a[j + 12]);
+  // twiddle B_j[q] *= W16^(j q)
+  a[5] = mul_w16<DIR, 1, T>(a[5]);    // j=1,q=1
+  a[9] = mul_w8<DIR, 1, T>(a[9]);     // j=1,q=2 -> W16^2
+  a[13] = mul_w16<DIR, 3, T>(a[13]);  // j=1,q=3
+  a[6] = mul_w8<DIR, 1, T>(a[6]);     // j=2,q=1 -> W16^2
+  a[10] = mul_w8<DIR, 2, T>(a[10]);   // j=2,q=2 -> W16^4
+  a[14] = mul_w8<DIR, 3, T>(a[14]);   // j=2,q=3 -> W16^6
+  a[7] = mul_w16<DIR, 3, T>(a[7]);    // j=3,q=1
+  a[11] = mul_w8<DIR, 3, T>(a[11]);   // j=3,q=2 -> W16^6
+  a[15] = mul_w16<DIR, 9, T>(a[15]);  // j=3,q=3
+  // DFT4 across j for each q: a[4q + p] <- y[q + 4p]
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r4<DIR>(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+  // transpose to natural order: out[q + 4p] = a[4q + p]
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int p = q + 1; p < 4; ++p) { C t = a[4 * q + p]; a[4 * q + p] = a[4 * p + q]; a[4 * p + q] = t; }
+}
+
+template <int R, int DIR, typename T> GX_HD void butterfly(cplx<T> *a) {
+  if (R == 2) r2<DIR>(a[0], a[1]);
+  else if (R == 4) r4<DIR>(a[0], a[1], a[2], a[3]);
+  else if (R == 8) r8<DIR, T>(a);
+  else r16<DIR, T>(a);
+}
+
+// ---- per-length plan: radices (largest first), E = radices[0]
+template <int NC> struct Plan;
+#define GX_PLAN(N_, S_, R0, R1, R2)                                  \
+  template <> struct Plan<N_> {                                      \
+    static constexpr int S = S_;                                     \
+    GX_HD static constexpr int radix(int s) { return s == 0 ? R0 : (s == 1 ? R1 : R2); } \
+  };
+GX_PLAN(2, 1, 2, 1, 1)
+GX_PLAN(4, 1, 4, 1, 1)
+GX_PLAN(8, 1, 8, 1, 1)
+GX_PLAN(16, 1, 16, 1, 1)
+GX_PLAN(32, 2, 8, 4, 1)
+GX_PLAN(64, 2, 8, 8, 1)
+GX_PLAN(128, 2, 16, 8, 1)
+GX_PLAN(256, 2, 16, 16, 1)
+GX_PLAN(512, 3, 8, 8, 8)
+GX_PLAN(1024, 3, 16, 8, 8)
+GX_PLAN(2048, 3, 16, 16, 8)
+GX_PLAN(4096, 3, 16, 16, 16)
+#undef GX_PLAN
+
+// shared-memory index skew: one pad element every SKEW elements keeps power-of-two strides off the
+// same banks (SKEW elements == 128 bytes == one full bank row)
+template <typename T> GX_HD constexpr int skew_of() { return 128 / (int) sizeof(cplx<T>); }
+template <typename T> GX_HD int sidx(int p) { return p + p / skew_of<T>(); }
+template <typename T> GX_HD constexpr int line_pitch(int nc) { return nc + nc / skew_of<T>() + 1; }
+
+template <typename T, int NC, int DIR> struct BlockFFT {
+  using C = cplx<T>;
+  using PL = Plan<NC>;
+  static constexpr int S = PL::S;
+  static constexpr int E = PL::radix(0);
+  static constexpr int P = NC / E;
+
+  GX_HD static constexpr int L(int s) {  // sub-transform length entering stage s
+    int l = NC;
+    for (int i = 0; i < s; ++i) l /= PL::radix(i);
+    return l;
+  }
+  GX_HD static constexpr int D(int s) { return L(s) / PL::radix(s); }
+
+  // natural frequency index of final in-place position p
+  GX_HD static int freq_of_pos(int p) {
+    int k = 0, mult = 1;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int d = D(s), r = PL::radix(s);
+      int q = (p / d) % r;
+      k += q * mult;
+      mult *= r;
+    }
+    return k;
+  }
+
+  GX_HD static C twiddle(const C *__restrict__ tw, int j) {
+    // tw[j] = exp(-2 pi i j / NC)
+#ifdef __CUDA_ARCH__
+    C w = __ldg(tw + j);
+#else
+    C w = tw[j];
+#endif
+    if (DIR > 0) w.y = -w.y;
+    return w;
+  }
+
+  // stage 0 on the registers as loaded: v[i] = x[t + i*P]
+  template <class Emit> GX_HD static void stage0(C (&v)[E], int t, C *line, const C *__restrict__ tw, Emit &&emit) {
+    butterfly<E, DIR, T>(v);
+    if (S == 1) {
+#pragma unroll
+      for (int q = 0; q < E; ++q) emit(q, v[q]);  // NC == E, P == 1, t == 0
+      return;
+    }
+#pragma unroll
+    for (int q = 1; q < E; ++q) v[q] = cmul(v[q], twiddle(tw, t * q));
+#pragma unroll
+    for (int q = 0; q < E; ++q) line[sidx<T>(t + q * P)] = v[q];
+  }
+
+  template <int s, class Emit> GX_HD static void stage(int t, C *line, const C *__restrict__ tw, Emit &&emit) {
+    constexpr int R = PL::radix(s);
+    constexpr int Ls = L(s), Ds = D(s);
+    constexpr bool last = (s == S - 1);
+#pragma unroll
+    for (int j = 0; j < E / R; ++j) {
+      const int b = t + j * P;
+      const int g = b / Ds, m = b % Ds;
+      const int base = g * Ls + m;
+      C a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = line[sidx<T>(base + r * Ds)];
+      butterfly<R, DIR, T>(a);
+      if (last) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) emit(freq_of_pos(base + q * Ds), a[q]);
+      } else {
+#pragma unroll
+        for (int q = 1; q < R; ++q) a[q] = cmul(a[q], twiddle(tw, m * q * (NC / Ls)));
+#pragma unroll
+        for (int q = 0; q < R; ++q) line[sidx<T>(base + q * Ds)] = a[q];
+      }
+    }
+  }
+
+#ifdef __CUDACC__
+  // Device driver. All threads of the CTA must call it (it contains __syncthreads).
+  template <class Emit> __device__ __forceinline__ static void run(C (&v)[E], int t, C *line, const C *__restrict__ tw,
+                                                                   Emit &&emit) {
+    stage0(v, t, line, tw, emit);
+    if constexpr (S >= 2) {
+      __syncthreads();
+      stage<1>(t, line, tw, emit);
+    }
+    if constexpr (S >= 3) {
+      __syncthreads();
+      stage<2>(t, line, tw, emit);
+    }
+  }
+#endif
+};
+
+}  // namespace fft
+}  // namespace gx

@@ -1,0 +1,66 @@
+// Particle emit for a unigrid: ZeldovichParticleEvaluator::getParticle (zeldovich.hpp:87-119,
+// generator.hpp:49-53), Grid::getCentroidFromCoordinate / wrapPoint (grid.hpp:519-531,656-669).
+#include "../../include/genetic_b200.h"
+#include "gx_common.cuh"
+
+namespace gx {
+
+template <typename T, typename O>
+__global__ void __launch_bounds__(256)
+emit_component_kernel(const T *__restrict__ psi, int n, int axis, T dx, T lower, T domain, T ratio,
+                      O *__restrict__ out_pos, O *__restrict__ out_vel, long stride, long long id0, long long count) {
+  const long long n2 = (long long) n * n;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long) gridDim.x * blockDim.x) {
+    const long long id = id0 + i;
+    const int x = (int) (id / n2);
+    const long long rem = id - (long long) x * n2;
+    const int y = (int) (rem / n);
+    const int z = (int) (rem - (long long) y * n);
+    const T p = psi[((size_t) x * n + y) * (size_t) (n + 2) + z];
+    const int c = axis == 0 ? x : (axis == 1 ? y : z);
+    // result = coord*cellSize; += offsetLower; += cellSize/2   (three separately rounded operations)
+    T cen = (T) c * dx;
+    cen = cen + lower;
+    cen = cen + dx / (T) 2;
+    T q = p + cen;
+    q = fmod(q, domain);
+    if (q < 0) q += domain;
+    if (out_pos) out_pos[i * stride] = (O) q;
+    if (out_vel) out_vel[i * stride] = (O) (p * ratio);
+  }
+}
+
+template <typename T, typename O>
+static int emit_t(const void *psi, int n, int axis, double dx, double lower, double domain, double ratio, void *pos,
+                  void *vel, long stride, long long id0, long long count, cudaStream_t st) {
+  if (count <= 0) return 0;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  emit_component_kernel<T, O><<<(unsigned) blocks, 256, 0, st>>>((const T *) psi, n, axis, (T) dx, (T) lower, (T) domain,
+                                                                (T) ratio, (O *) pos, (O *) vel, stride, id0, count);
+  count_launch();
+  GX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace gx
+
+extern "C" int gx_emit_component(const void *psi, int n, int dtype, int axis, double cell_size, double offset_lower,
+                                 double domain_size, double vel_ratio, void *out_pos, void *out_vel, int out_dtype,
+                                 long stride_elems, long long id0, long long count, void *stream) {
+  using namespace gx;
+  if (axis < 0 || axis > 2) return fail("axis must be 0, 1 or 2");
+  const long long n3 = (long long) n * n * n;
+  if (id0 < 0 || id0 + count > n3) return fail("gx_emit_component: id range outside the grid");
+  cudaStream_t st = (cudaStream_t) stream;
+  if (dtype == GX_F64 && out_dtype == GX_F64)
+    return emit_t<double, double>(psi, n, axis, cell_size, offset_lower, domain_size, vel_ratio, out_pos, out_vel, stride_elems, id0, count, st);
+  if (dtype == GX_F64 && out_dtype == GX_F32)
+    return emit_t<double, float>(psi, n, axis, cell_size, offset_lower, domain_size, vel_ratio, out_pos, out_vel, stride_elems, id0, count, st);
+  if (dtype == GX_F32 && out_dtype == GX_F32)
+    return emit_t<float, float>(psi, n, axis, cell_size, offset_lower, domain_size, vel_ratio, out_pos, out_vel, stride_elems, id0, count, st);
+  if (dtype == GX_F32 && out_dtype == GX_F64)
+    return emit_t<float, double>(psi, n, axis, cell_size, offset_lower, domain_size, vel_ratio, out_pos, out_vel, stride_elems, id0, count, st);
+  return fail("bad dtype");
+}

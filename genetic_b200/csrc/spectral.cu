@@ -1,0 +1,273 @@
+// Spectral element-wise kernels + their C-ABI entry points.
+#include "../../include/genetic_b200.h"
+#include "spectral.cuh"
+#include "spectrum_host.h"
+#include <vector>
+
+namespace gx {
+
+struct NoInit { __device__ __forceinline__ void init() const {} };
+
+// ---- ensureFourierModesAreMirrored (fourier.hpp:331-357) ---------------------------------------------
+// One thread per (plane in {kz=0, kz=n/2}, kx in [0, n/2], ky in [0, n)).
+template <typename T> __global__ void mirror_kernel(cplx<T> *f, int n, int nc) {
+  const int h = n >> 1;
+  const int total = 2 * (h + 1) * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ky = i % n;
+    const int kx = (i / n) % (h + 1);
+    const int iz = (i / (n * (h + 1))) ? h : 0;
+    const size_t src = ((size_t) kx * n + ky) * nc + iz;
+    if (kx == 0 || kx == h) {
+      // within-row: +ky -> -ky for 0 < ky < h; the self-conjugate entries get their imaginary part negated,
+      // exactly as the reference's sequential descending-ky loop leaves them
+      if (ky == 0 || ky == h) { f[src].y = -f[src].y; }
+      else if (ky < h) { cplx<T> v = f[src]; v.y = -v.y; f[((size_t) kx * n + (n - ky)) * nc + iz] = v; }
+    } else {
+      cplx<T> v = f[src];
+      v.y = -v.y;
+      f[((size_t) (n - kx) * n + ((n - ky) % n)) * nc + iz] = v;
+    }
+  }
+}
+
+template <typename T> int mirror(T *field, int n, cudaStream_t st) {
+  const int nc = n / 2 + 1;
+  const int total = 2 * (n / 2 + 1) * n;
+  mirror_kernel<T><<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<cplx<T> *>(field), n, nc);
+  count_launch();
+  GX_LAUNCH_CHECK();
+  return 0;
+}
+template int mirror<float>(float *, int, cudaStream_t);
+template int mirror<double>(double *, int, cudaStream_t);
+
+// ---- spectrum table staging ------------------------------------------------------------------------
+struct SpecInit {
+  SpecDev sp;
+  __device__ __forceinline__ void init() const {
+    extern __shared__ double s_tab[];
+    for (int i = threadIdx.x; i < 3 * sp.m; i += blockDim.x) s_tab[i] = sp.tab[i];
+    __syncthreads();
+  }
+  __device__ __forceinline__ const double *lx() const { extern __shared__ double s_tab[]; return s_tab; }
+};
+
+// ---- getPowerSpectrumForGridUncached (camb.hpp:101-119) ------------------------------------------------
+template <typename T> struct CovarianceF : SpecInit {
+  cplx<T> *out; int n; T kmin, norm;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    cplx<T> v = mk<T>(0, 0);
+    if (slot_is_independent(n, ix, iy, iz)) {
+      T kx, ky, kz, k2;
+      slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+      const double *t = lx();
+      v.x = mul_rn(spectrum_power<T>(sp, t, t + sp.m, t + 2 * sp.m, sqrt_rn(k2)), norm);
+    }
+    out[s] = v;
+  }
+};
+
+// ---- Field::applyTransferFunction with the covariance evaluated on the fly (field.hpp:394-412) ------------
+template <typename T> struct ApplyTransferF : SpecInit {
+  cplx<T> *f; int n; T kmin, norm; double power;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    T kx, ky, kz, k2;
+    slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+    const double *t = lx();
+    T spec = mul_rn(spectrum_power<T>(sp, t, t + sp.m, t + 2 * sp.m, sqrt_rn(k2)), norm);
+    spec = spec_pow<T>(spec, power);
+    cplx<T> v = f[s];
+    f[s] = mk<T>(mul_rn(v.x, spec), mul_rn(v.y, spec));
+  }
+};
+
+template <typename T> struct ApplyTransferFieldF : NoInit {
+  cplx<T> *f; const cplx<T> *cov; int n; double power;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    T spec = spec_pow<T>(cov[s].x, power);
+    cplx<T> v = f[s];
+    f[s] = mk<T>(mul_rn(v.x, spec), mul_rn(v.y, spec));
+  }
+};
+
+// ---- filters (filter.hpp) ---------------------------------------------------------------------------
+struct FilterDesc { int nf; gx_filter_factor f[8]; };
+
+template <typename T> __device__ __forceinline__ T filter_eval(const FilterDesc &d, T k) {
+  T r = (T) 1;
+  for (int i = 0; i < d.nf; ++i) {
+    const gx_filter_factor &q = d.f[i];
+    T v;
+    if (q.kind == GX_FILTER_CONST) v = (T) q.kcut;
+    else {
+      // LowPassFermiFilter::operator() : 1./(1.+exp((k-kcut)/temperature)) in T
+      const T kc = (T) q.kcut, tp = (T) q.temperature;
+      const T lp = (T) 1. / ((T) 1. + (T) exp((double) ((k - kc) / tp)));
+      if (q.kind == GX_FILTER_FERMI_LP) v = lp;
+      else if (q.kind == GX_FILTER_FERMI_HP_COV) v = sqrt_rn((T) 1. - lp * lp);
+      else v = (T) 1. - lp;
+    }
+    for (int p = 0; p < q.power; ++p) r *= v;
+  }
+  return r;
+}
+
+template <typename T> struct ApplyFilterF : NoInit {
+  cplx<T> *f; int n; T kmin; FilterDesc d;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    T kx, ky, kz, k2;
+    slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+    // field.hpp:743: k = sqrt(double(kx*kx+ky*ky+kz*kz)) -> CoordinateType
+    const T k = (T) sqrt((double) k2);
+    const T w = filter_eval<T>(d, k);
+    cplx<T> v = f[s];
+    f[s] = mk<T>(mul_rn(v.x, w), mul_rn(v.y, w));
+  }
+};
+
+// ---- enforceUnitVariance (multilevelfield.hpp:498-510) ---------------------------------------------------
+template <typename T> struct UnitVarianceF : NoInit {
+  cplx<T> *f; int n;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    cplx<T> v = f[s];
+    const T a = (T) hypot((double) v.x, (double) v.y);
+    if (a == (T) 0) f[s] = mk<T>(0, 0);
+    else f[s] = mk<T>(div_rn(v.x, a), div_rn(v.y, a));
+  }
+};
+
+// ---- Zeldovich operator, unfused form (zeldovich.hpp:156-181 through fourier.hpp:253-274) ---------------
+template <typename T> struct ZeldovichF : NoInit {
+  const cplx<T> *delta; cplx<T> *psi; int n, axis; T kmin;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    cplx<T> r = mk<T>(0, 0);
+    if (slot_is_independent(n, ix, iy, iz)) {
+      T kx, ky, kz, k2;
+      slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+      const int h = n >> 1;
+      const int ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+      const T ka = axis == 0 ? kx : (axis == 1 ? ky : kz);
+      if (ia != h && k2 != (T) 0) {
+        const cplx<T> d = delta[s];
+        r.x = mul_rn(div_rn(-d.y, k2), ka);
+        r.y = mul_rn(div_rn(d.x, k2), ka);
+      }
+    }
+    psi[s] = r;
+  }
+};
+
+template <typename T> static T kmin_of(double grid_length) { return (T) (2. * M_PI / (double) (T) grid_length); }
+
+}  // namespace gx
+
+using namespace gx;
+
+#define GX_DISPATCH(dtype, CALL)                                      \
+  do {                                                                \
+    if ((dtype) == GX_F64) { using T = double; return CALL; }         \
+    if ((dtype) == GX_F32) { using T = float; return CALL; }          \
+    return gx::fail("bad dtype");                                     \
+  } while (0)
+
+static int check_n(int n) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  return 0;
+}
+
+template <typename T> static SpecInit make_spec_init(const gx_spectrum *s) {
+  SpecInit si;
+  si.sp = gx_spectrum_device_view(s);
+  return si;
+}
+
+template <typename T> static int covariance_field_t(void *out, int n, double L, const gx_spectrum *s, cudaStream_t st) {
+  CovarianceF<T> f;
+  f.sp = gx_spectrum_device_view(s);
+  f.out = (cplx<T> *) out; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n);
+  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double));
+}
+
+template <typename T>
+static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, double power, cudaStream_t st) {
+  ApplyTransferF<T> f;
+  f.sp = gx_spectrum_device_view(s);
+  f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n); f.power = power;
+  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double));
+}
+
+template <typename T> static int apply_transfer_field_t(void *field, const void *cov, int n, double power, cudaStream_t st) {
+  ApplyTransferFieldF<T> f;
+  f.f = (cplx<T> *) field; f.cov = (const cplx<T> *) cov; f.n = n; f.power = power;
+  return launch_slot_sweep(n, f, st);
+}
+
+template <typename T>
+static int apply_filter_t(void *field, int n, double L, const gx_filter_factor *fac, int nf, cudaStream_t st) {
+  if (nf < 0 || nf > 8) return gx::fail("gx_apply_filter: at most 8 factors");
+  ApplyFilterF<T> f;
+  f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.d.nf = nf;
+  for (int i = 0; i < nf; ++i) f.d.f[i] = fac[i];
+  return launch_slot_sweep(n, f, st);
+}
+
+template <typename T> static int unit_variance_t(void *field, int n, cudaStream_t st) {
+  UnitVarianceF<T> f;
+  f.f = (cplx<T> *) field; f.n = n;
+  return launch_slot_sweep(n, f, st);
+}
+
+template <typename T>
+static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, int axis, cudaStream_t st) {
+  ZeldovichF<T> f;
+  f.delta = (const cplx<T> *) delta; f.psi = (cplx<T> *) psi; f.n = n; f.axis = axis; f.kmin = kmin_of<T>(L);
+  return launch_slot_sweep(n, f, st);
+}
+
+extern "C" {
+
+int gx_mirror(void *field, int n, int dtype, void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, gx::mirror<T>((T *) field, n, (cudaStream_t) stream));
+}
+
+int gx_covariance_field(void *out_field, int n, int dtype, double grid_length, const gx_spectrum *s, void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, covariance_field_t<T>(out_field, n, grid_length, s, (cudaStream_t) stream));
+}
+
+int gx_apply_transfer(void *field, int n, int dtype, double grid_length, const gx_spectrum *s, double power,
+                      void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, apply_transfer_t<T>(field, n, grid_length, s, power, (cudaStream_t) stream));
+}
+
+int gx_apply_transfer_field(void *field, const void *cov_field, int n, int dtype, double power, void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, apply_transfer_field_t<T>(field, cov_field, n, power, (cudaStream_t) stream));
+}
+
+int gx_apply_filter(void *field, int n, int dtype, double grid_length, const gx_filter_factor *factors, int nfactors,
+                    void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, apply_filter_t<T>(field, n, grid_length, factors, nfactors, (cudaStream_t) stream));
+}
+
+int gx_unit_variance(void *field, int n, int dtype, void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, unit_variance_t<T>(field, n, (cudaStream_t) stream));
+}
+
+int gx_zeldovich_fourier(const void *delta_k, void *psi_k, int n, int dtype, double grid_length, int axis,
+                         void *stream) {
+  if (check_n(n)) return 1;
+  if (axis < 0 || axis > 2) return gx::fail("axis must be 0, 1 or 2");
+  GX_DISPATCH(dtype, zeldovich_fourier_t<T>(delta_k, psi_k, n, grid_length, axis, (cudaStream_t) stream));
+}
+
+}  // extern "C"

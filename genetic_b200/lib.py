@@ -1,0 +1,110 @@
+"""ctypes binding of libgenetic_b200.so -- one prototype per function declared in include/genetic_b200.h."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libgenetic_b200.so")
+F32, F64 = 0, 1
+LAYOUT_REAL, LAYOUT_FOURIER = 0, 1
+NOISE_REAL, NOISE_FOURIER_SERIAL, NOISE_FOURIER_PARALLEL = 0, 1, 2
+FILTER_CONST, FILTER_FERMI_LP, FILTER_FERMI_HP_COV, FILTER_FERMI_HP = 0, 1, 2, 3
+
+
+class GxError(RuntimeError):
+    pass
+
+
+class FilterFactor(C.Structure):
+    _fields_ = [("kind", C.c_int), ("kcut", C.c_double), ("temperature", C.c_double), ("power", C.c_int)]
+
+
+vp, ci, cd, cl, cll, csz = C.c_void_p, C.c_int, C.c_double, C.c_long, C.c_longlong, C.c_size_t
+cul, cull = C.c_ulong, C.c_ulonglong
+P = C.POINTER
+
+# name -> (restype, argtypes); int-returning functions are status codes
+PROTOTYPES = {
+    "gx_last_error": (C.c_char_p, []),
+    "gx_version": (ci, []),
+    "gx_device_count": (ci, [P(ci)]),
+    "gx_set_device": (ci, [ci]),
+    "gx_synchronize": (ci, [vp]),
+    "gx_launch_count": (cull, []),
+    "gx_field_bytes": (csz, [ci, ci]),
+    "gx_malloc": (ci, [P(vp), csz]),
+    "gx_free": (ci, [vp]),
+    "gx_memset_zero": (ci, [vp, csz, vp]),
+    "gx_host_alloc_pinned": (ci, [P(vp), csz]),
+    "gx_host_free_pinned": (ci, [vp]),
+    "gx_memcpy_d2d": (ci, [vp, vp, csz, vp]),
+    "gx_memcpy_h2d": (ci, [vp, vp, csz, vp]),
+    "gx_memcpy_d2h": (ci, [vp, vp, csz, vp]),
+    "gx_field_upload": (ci, [vp, vp, ci, ci, ci, vp]),
+    "gx_field_download": (ci, [vp, vp, ci, ci, ci, vp]),
+    "gx_fft_forward": (ci, [vp, ci, ci, vp]),
+    "gx_fft_inverse": (ci, [vp, ci, ci, vp]),
+    "gx_mirror": (ci, [vp, ci, ci, vp]),
+    "gx_noise_draw": (ci, [vp, ci, ci, cul, ci, ci, P(cull), vp]),
+    "gx_rng_raw": (ci, [cul, cull, cl, vp]),
+    "gx_rng_gaussians": (ci, [cul, cl, vp, P(cull)]),
+    "gx_spectrum_create_camb": (ci, [vp, vp, vp, ci, cd, cd, cd, cd, cd, ci, P(vp)]),
+    "gx_spectrum_create_powerlaw": (ci, [cd, cd, ci, P(vp)]),
+    "gx_spectrum_destroy": (ci, [vp]),
+    "gx_spectrum_amplitude": (cd, [vp]),
+    "gx_spectrum_eval": (cd, [vp, cd]),
+    "gx_covariance_field": (ci, [vp, ci, ci, cd, vp, vp]),
+    "gx_apply_transfer": (ci, [vp, ci, ci, cd, vp, cd, vp]),
+    "gx_apply_transfer_field": (ci, [vp, vp, ci, ci, cd, vp]),
+    "gx_apply_filter": (ci, [vp, ci, ci, cd, P(FilterFactor), ci, vp]),
+    "gx_unit_variance": (ci, [vp, ci, ci, vp]),
+    "gx_scale": (ci, [vp, ci, ci, cd, vp]),
+    "gx_axpy": (ci, [vp, vp, ci, ci, cd, vp]),
+    "gx_axpy_fourier": (ci, [vp, vp, ci, ci, cd, vp]),
+    "gx_mul_mask": (ci, [vp, vp, ci, ci, vp]),
+    "gx_dot_fourier": (ci, [vp, vp, ci, ci, P(cd), vp]),
+    "gx_dot_real": (ci, [vp, vp, ci, ci, P(cd), vp]),
+    "gx_get_mode": (ci, [vp, ci, ci, ci, ci, ci, P(cd), P(cd)]),
+    "gx_set_mode": (ci, [vp, ci, ci, ci, ci, ci, cd, cd]),
+    "gx_zeldovich_fourier": (ci, [vp, vp, ci, ci, cd, ci, vp]),
+    "gx_zeldovich_offset": (ci, [vp, vp, ci, ci, cd, ci, vp]),
+    "gx_emit_component": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, vp, ci, cl, cll, cll, vp]),
+}
+NOT_STATUS = {"gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_spectrum_amplitude",
+              "gx_spectrum_eval"}
+
+_lib = None
+
+
+class _Checked:
+    """Wraps a status-returning entry point: non-zero -> GxError(gx_last_error()), the reference's
+    std::runtime_error behaviour (tools/parser.hpp:202-207)."""
+
+    def __init__(self, lib, name, fn):
+        self._lib, self._name, self._fn = lib, name, fn
+
+    def __call__(self, *args):
+        rc = self._fn(*args)
+        if rc != 0:
+            raise GxError("%s: %s" % (self._name, self._lib.gx_last_error().decode()))
+        return rc
+
+
+class _Lib:
+    def __init__(self, cdll):
+        self.cdll = cdll
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(cdll, name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn if name in NOT_STATUS else _Checked(self, name, fn))
+
+
+def load():
+    """Loads the CUDA library. Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise GxError("genetic_b200: %s is missing -- run `python -m genetic_b200.build` "
+                          "(there is no CPU fallback)" % LIBPATH)
+        _lib = _Lib(C.CDLL(LIBPATH))
+    return _lib

@@ -1,0 +1,153 @@
+/* genetic_b200 -- C ABI of the B200-native genetIC hot path (Gaussian random field generation +
+ * Zeldovich displacement).  extern "C", plain pointers and sizes, no C++/torch types.
+ *
+ * The reference (pynbody/genetIC) has no FFI: its seam is the C++ class API of fields::Field /
+ * tools::numerics::fourier::FieldFourierManager / fields::RandomFieldGenerator / cosmology::CAMB /
+ * particle::ZeldovichParticleGenerator.  Each entry point below names the reference member function(s)
+ * it replaces (paths relative to genetIC/src/).  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - every function returns 0 on success; otherwise non-zero and gx_last_error() describes the failure
+ *    (the C++ host layer turns that into std::runtime_error, the reference's error behaviour,
+ *    tools/parser.hpp:202-207).
+ *  - `dtype`: GX_F32 (the reference's `-f` build, main.cpp:14-20) or GX_F64.
+ *  - a *field* is a device buffer of gx_field_bytes(n, dtype) bytes: n*n rows of (n/2+1) complex =
+ *    n+2 reals, z fastest (grid.hpp:610-626, fourier.hpp:300-319, 471-476).  Fourier space uses every
+ *    slot; real space uses the first n reals of each row (the device keeps the padded pitch; the
+ *    reference's unpadded N^3 real-space layout exists only on the host side of gx_field_upload /
+ *    gx_field_download).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ *    asynchronous with respect to the host unless documented otherwise.
+ *  - n must be a power of two in [4, 4096].
+ */
+#ifndef GENETIC_B200_H
+#define GENETIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GX_F32 0
+#define GX_F64 1
+
+/* host layouts for upload/download */
+#define GX_LAYOUT_REAL 0    /* n^3 reals, unpadded, C order [x][y][z]      (Field::getDataVector() in real space) */
+#define GX_LAYOUT_FOURIER 1 /* 2*n*n*(n/2+1) reals, the padded half-complex (Field::getDataVector() in Fourier space) */
+
+/* white-noise draw orders (randomfieldgenerator.hpp) */
+#define GX_NOISE_REAL 0             /* drawRandomForSpecifiedGrid :181-197 (+ r2c, Re(DC)=0) */
+#define GX_NOISE_FOURIER_SERIAL 1   /* drawRandomForSpecifiedGridFourier :246-256 */
+#define GX_NOISE_FOURIER_PARALLEL 2 /* drawRandomForSpecifiedGridFourier :226-243 (stream per shell, seed+ks) */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char *gx_last_error(void);
+int gx_version(void);
+int gx_device_count(int *count);
+int gx_set_device(int device);           /* fourier::initialise() analogue, fourier.hpp:36-81 */
+int gx_synchronize(void *stream);
+unsigned long long gx_launch_count(void); /* kernels launched by this library so far (bench bookkeeping) */
+
+/* ---- memory ----------------------------------------------------------------------------------- */
+size_t gx_field_bytes(int n, int dtype); /* FieldFourierManager::getRequiredDataSize, fourier.hpp:471-476 */
+int gx_malloc(void **ptr, size_t bytes);
+int gx_free(void *ptr);
+int gx_memset_zero(void *ptr, size_t bytes, void *stream);
+int gx_host_alloc_pinned(void **ptr, size_t bytes);
+int gx_host_free_pinned(void *ptr);
+int gx_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int gx_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int gx_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+/* Field(grid, dataVector, fourier) construction / getDataVector() read-back (field.hpp:230-249,271-278).
+   GX_LAYOUT_REAL repacks between the host's unpadded n^3 and the device's padded pitch
+   (replaces padForFFTWRealTransform / unpadAfterFFTWRealTransform, fourier.hpp:368-405). */
+int gx_field_upload(void *dev_field, const void *host, int n, int dtype, int layout, void *stream);
+int gx_field_download(void *host, const void *dev_field, int n, int dtype, int layout, void *stream);
+
+/* ---- FFT (FieldFourierManager<T,T>::performTransform, fourier.hpp:479-518) ----------------------- */
+int gx_fft_forward(void *field, int n, int dtype, void *stream); /* toFourier: r2c, / n^1.5 */
+int gx_fft_inverse(void *field, int n, int dtype, void *stream); /* toReal: mirror, c2r, / n^1.5 */
+int gx_mirror(void *field, int n, int dtype, void *stream);      /* ensureFourierModesAreMirrored :331-357 */
+
+/* ---- white noise (RandomFieldGenerator::draw, randomfieldgenerator.hpp:122-139) ------------------ */
+/* Draws one level. `stream_offset_io` (may be NULL): for the two serial modes the reference draws all
+   levels from ONE gsl stream; pass the number of raw 24-bit outputs already consumed (0 for the first
+   level) and receive the updated count. The result is in Fourier space for every mode. */
+int gx_noise_draw(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
+                  unsigned long long *stream_offset_io, void *stream);
+/* Test hooks for the generator: n raw 24-bit outputs / n gaussians of gsl_rng_ranlxs2 seeded with `seed`,
+   starting at raw offset `offset`, computed on the device and written to host arrays. */
+int gx_rng_raw(unsigned long seed, unsigned long long offset, long n, uint32_t *host_out);
+int gx_rng_gaussians(unsigned long seed, long n, double *host_out, unsigned long long *raw_consumed);
+
+/* ---- power spectrum (cosmology::CAMB, camb.hpp:173-332; PowerLawPowerSpectrum :150-168) ---------- */
+typedef struct gx_spectrum gx_spectrum;
+/* k[nk] > 0 and T[nk] = one CAMB column already divided by the file's first CDM entry (camb.hpp:254-262);
+   calculates the spline (interpolation.hpp:46-54,88-103) and the sigma8/growth normalisation (:289-328)
+   with T_norm[nk] = the `total` column (species::all), and uploads the tables. */
+int gx_spectrum_create_camb(const double *k, const double *T, const double *T_norm, int nk, double OmegaM0,
+                            double OmegaLambda0, double sigma8, double ns, double scalefactor, int dtype,
+                            gx_spectrum **out);
+int gx_spectrum_create_powerlaw(double amplitude, double ns, int dtype, gx_spectrum **out);
+int gx_spectrum_destroy(gx_spectrum *s);
+double gx_spectrum_amplitude(const gx_spectrum *s);
+double gx_spectrum_eval(const gx_spectrum *s, double k); /* CAMB::operator()(k), host evaluation */
+/* getPowerSpectrumForGridUncached (camb.hpp:101-119): materialise C(k) = P(k) * n^3 / L^3 as a Fourier field */
+int gx_covariance_field(void *out_field, int n, int dtype, double grid_length, const gx_spectrum *s, void *stream);
+/* Field::applyTransferFunction (field.hpp:394-412) with the covariance evaluated in-kernel (nothing materialised) */
+int gx_apply_transfer(void *field, int n, int dtype, double grid_length, const gx_spectrum *s, double power,
+                      void *stream);
+/* Field::applyTransferFunction with an explicit covariance field */
+int gx_apply_transfer_field(void *field, const void *cov_field, int n, int dtype, double power, void *stream);
+
+/* ---- filters (filters::*, filter.hpp:107-317; Field::applyFilter, field.hpp:741-746) -------------- */
+#define GX_FILTER_CONST 0          /* value                                       (filter.hpp:60-105)  */
+#define GX_FILTER_FERMI_LP 1       /* 1/(1+exp((k-kcut)/T)), T = kcut*param       (filter.hpp:209-239) */
+#define GX_FILTER_FERMI_HP_COV 2   /* sqrt(1 - lp^2)                              (filter.hpp:246-275) */
+#define GX_FILTER_FERMI_HP 3       /* 1 - lp                                      (filter.hpp:282-317) */
+typedef struct {
+  int kind;
+  double kcut;  /* or the constant */
+  double temperature;
+  int power;    /* factor raised to this integer power (>=1); f*f products fold to power 2 */
+} gx_filter_factor;
+int gx_apply_filter(void *field, int n, int dtype, double grid_length, const gx_filter_factor *factors,
+                    int nfactors, void *stream);
+
+/* ---- element-wise and reductions ------------------------------------------------------------------- */
+int gx_unit_variance(void *field, int n, int dtype, void *stream); /* enforceUnitVariance, multilevelfield.hpp:498-510 */
+int gx_scale(void *field, int n, int dtype, double a, void *stream);                   /* Field::operator*=(value) */
+int gx_axpy(void *y, const void *x, int n, int dtype, double a, void *stream);         /* Field::addScaled :355-362 */
+int gx_axpy_fourier(void *y, const void *x, int n, int dtype, double a, void *stream); /* MultiLevelField::addScaled :194-212 */
+int gx_mul_mask(void *field, const unsigned char *mask_n3, int n, int dtype, void *stream); /* operator*=(Field<char>) :306-318 */
+/* MultiLevelField::innerProduct for one level (:248-294): sum_modes w Re(conj(a) b), weights fourier.hpp:116-147 */
+int gx_dot_fourier(const void *a, const void *b, int n, int dtype, double *host_out, void *stream);
+/* Field::innerProduct in real space over the n^3 cells (field.hpp:365-377; the stale-padding quirk is dropped) */
+int gx_dot_real(const void *a, const void *b, int n, int dtype, double *host_out, void *stream);
+int gx_get_mode(const void *field, int n, int dtype, int kx, int ky, int kz, double *re, double *im); /* getFourierCoefficient */
+int gx_set_mode(void *field, int n, int dtype, int kx, int ky, int kz, double re, double im);         /* setFourierCoefficient */
+
+/* ---- Zeldovich (ZeldovichParticleGenerator::calculateOffsetFields, zeldovich.hpp:152-181,248-251) ------- */
+/* psi_axis(k) = i k_axis delta_k / k^2 (0 at k=0 and where k_axis is the Nyquist mode), independent slots
+   only, into a separate field (generateNewFourierFields, fourier.hpp:253-274). axis: 0,1,2. */
+int gx_zeldovich_fourier(const void *delta_k, void *psi_k, int n, int dtype, double grid_length, int axis,
+                         void *stream);
+/* The same followed by toReal() (mirror + c2r + 1/n^1.5) with the operator, the mirror and the scaling fused
+   into the FFT passes: psi = real-space displacement component `axis`. delta_k is not modified. */
+int gx_zeldovich_offset(const void *delta_k, void *psi, int n, int dtype, double grid_length, int axis,
+                        void *stream);
+/* ZeldovichParticleEvaluator::getParticle for a unigrid (zeldovich.hpp:87-119, generator.hpp:49-53,
+   grid.hpp:519-531,656-669): for cell id = (x*n+y)*n+z,
+     pos[axis] = wrap(centroid_axis + psi), vel[axis] = psi * vel_ratio.
+   Output arrays are strided so that one call fills one component of an interleaved particle array:
+   out[(id)*stride_elems]. out_dtype GX_F32/GX_F64. `id0`/`count` select a range of cells. */
+int gx_emit_component(const void *psi, int n, int dtype, int axis, double cell_size, double offset_lower,
+                      double domain_size, double vel_ratio, void *out_pos, void *out_vel, int out_dtype,
+                      long stride_elems, long long id0, long long count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

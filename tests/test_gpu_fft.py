@@ -1,0 +1,159 @@
+"""GPU parity: the hand-written 3-D FFT and the spectral operators against the CPU oracle (oracle/model.py).
+All calls go through the C ABI (genetic_b200.lib). Tolerances: f64 1e-10 relative (north star), f32 1e-5."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import genetic_b200 as gb
+from oracle import model as M
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _tol(dtype):
+    return 1e-10 if np.dtype(dtype) == np.float64 else 1e-5
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256])
+def test_fft_forward_inverse_vs_oracle(n, dtype):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, n, n)).astype(dtype)
+    g = gb.Grid(100.0, n, dtype=dtype)
+    f = gb.Field(g, x, fourier=False)
+    f.toFourier()
+    F = f.getDataVector()
+    Fo = M.to_fourier(x.astype(np.float64))
+    assert _rel(F, Fo) < _tol(dtype)
+    # the transform is unitary: Parseval through the reference's mode weights
+    assert abs(np.sum(M.mode_weights(n) * np.abs(F) ** 2) / np.sum(x.astype(np.float64) ** 2) - 1) < 10 * _tol(dtype)
+    f.toReal()
+    y = f.getDataVector()
+    assert _rel(y, x) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_inverse_of_unmirrored_spectrum(dtype):
+    """toReal mirrors first (fourier.hpp:497): fill only independent slots, redundant ones hold garbage."""
+    n = 16
+    rng = np.random.default_rng(5)
+    ct = np.complex128 if dtype == np.float64 else np.complex64
+    F = (rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))).astype(ct)
+    g = gb.Grid(100.0, n, dtype=dtype)
+    f = gb.Field(g, F, fourier=True)
+    f.ensureFourierModesAreMirrored()
+    Fm = f.getDataVector()
+    assert np.array_equal(Fm, M.mirror(F.copy()))  # bit-exact storage, including the self-conjugate sign flips
+    f2 = gb.Field(g, F, fourier=True)
+    f2.toReal()
+    assert _rel(f2.getDataVector(), M.to_real(F.astype(np.complex128))) < _tol(dtype)
+
+
+@pytest.mark.parametrize("n", [512])
+def test_fft_roundtrip_large(n):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, n, n))
+    g = gb.Grid(100.0, n)
+    f = gb.Field(g, x, fourier=False)
+    f.toFourier()
+    F = f.getDataVector()
+    # spot-check a few modes against a direct DFT sum (size-independent property: linearity + known modes)
+    for (kx, ky, kz) in [(0, 0, 0), (1, 2, 3), (n // 2, 0, 5), (n - 1, n - 2, n // 2)]:
+        ph = np.exp(-2j * np.pi * (kx * np.arange(n)[:, None, None] + ky * np.arange(n)[None, :, None]
+                                   + kz * np.arange(n)[None, None, :]) / n)
+        ref = (x * ph).sum() / n ** 1.5
+        assert abs(F[kx, ky, kz] - ref) < 1e-10 * np.sqrt(n ** 3)
+    f.toReal()
+    assert _rel(f.getDataVector(), x) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_transfer_zeldovich_emit_vs_oracle(dtype):
+    """White noise from the oracle (device noise is tested separately) -> sqrt(P) -> psi_xyz -> particles."""
+    n, box = 32, 50.0
+    cos_o = M.Cosmology(0.279, 0.721, 0.817, 99)
+    camb_file = os.path.join(GOLD, "camb_transfer_kmax40_z0.dat")
+    r = M.unigrid_ic(n, box, 8896131, "fourier_parallel", camb_file, cos_o, dtype=dtype, return_intermediate=True)
+    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99)
+    g = gb.Grid(box, n, dtype=dtype)
+    spec = gb.CAMB(cos, camb_file, "all", dtype)
+    assert abs(spec.amplitude / r["camb"].amplitude - 1) < (1e-13 if dtype == np.float64 else 1e-5)
+    cov = spec.getPowerSpectrumForGrid(g).getDataVector()
+    assert _rel(cov.real, r["cov"]) < 100 * _tol(dtype) and np.all(cov.imag == 0)
+    f = gb.Field(g, r["white"], fourier=True)
+    f.applyTransferFunction(spec, 0.5)
+    D = f.getDataVector()
+    assert _rel(D, r["delta_k"]) < _tol(dtype) * 10
+    # the Zeldovich operator itself is pure IEEE arithmetic: bit-exact given identical delta_k
+    f2 = gb.Field(g, r["delta_k"], fourier=True)
+    for axis in range(3):
+        psi = gb.Field(g, fourier=True)
+        f2.lib.gx_zeldovich_fourier(f2.ptr, psi.ptr, n, f2.dt, float(g.thisGridSize), axis, None)
+        assert np.array_equal(psi.getDataVector(), r["psi_k"][axis])
+    gen = gb.ZeldovichParticleGenerator(f2)
+    for axis in range(3):
+        assert _rel(gen.getGeneratedFields()[axis].getDataVector(), r["psi"][axis]) < _tol(dtype) * 10
+    from genetic_b200.host import emit_particles
+    pos, vel = emit_particles(gen.getGeneratedFields(), g, cos, out_dtype=dtype)
+    assert np.abs(vel - r["vel"]).max() < _tol(dtype) * 10 * np.abs(r["vel"]).max()
+    d = np.abs(pos - r["pos"])
+    d = np.minimum(d, box - d)  # a particle within rounding of the box edge may wrap differently
+    assert d.max() < _tol(dtype) * 10 * box
+
+
+def test_reductions_and_axpy():
+    n = 32
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))
+    B = rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))
+    g = gb.Grid(10.0, n)
+    fa, fb = gb.Field(g, A), gb.Field(g, B)
+    ref = np.sum(M.mode_weights(n) * (np.conj(A) * B).real)
+    assert abs(fa.innerProduct(fb) - ref) < 1e-12 * abs(ref) + 1e-9
+    fa.addScaledFourier(fb, 0.25)
+    ind = M.independent_mask(n)
+    out = fa.getDataVector()
+    assert np.allclose(out[ind], (A + 0.25 * B)[ind], rtol=1e-15, atol=0) and np.array_equal(out[~ind], A[~ind])
+    x = rng.standard_normal((n, n, n))
+    y = rng.standard_normal((n, n, n))
+    fx, fy = gb.Field(g, x, fourier=False), gb.Field(g, y, fourier=False)
+    assert abs(fx.innerProduct(fy) - np.sum(x * y)) < 1e-10
+    fx *= 3.0
+    assert np.array_equal(fx.getDataVector(), x * 3.0)
+
+
+def test_filters_and_unit_variance():
+    n, box = 16, 20.0
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))
+    g = gb.Grid(box, n)
+    kmin = 2 * np.pi / box
+    ks = M.signed_modes(n) * kmin
+    k = np.sqrt(ks[:, None, None] ** 2 + ks[None, :, None] ** 2 + (np.arange(n // 2 + 1) * kmin)[None, None, :] ** 2)
+    kcut = 0.3 * n * kmin
+    lp = 1.0 / (1.0 + np.exp((k - kcut) / (0.1 * kcut)))
+    ind = M.independent_mask(n)
+    f = gb.Field(g, A)
+    f.applyFilter(gb.LowPassFermiFilter(kcut))
+    assert np.allclose(f.getDataVector()[ind], (A * lp)[ind], rtol=1e-13)
+    from genetic_b200.host import ComplementaryCovarianceFilter
+    f = gb.Field(g, A)
+    f.applyFilter(ComplementaryCovarianceFilter(kcut))
+    assert np.allclose(f.getDataVector()[ind], (A * np.sqrt(1 - lp * lp))[ind], rtol=1e-12, atol=1e-15)
+    f = gb.Field(g, A)
+    f.enforceUnitVariance()
+    assert np.allclose(np.abs(f.getDataVector()[ind]), 1.0, rtol=1e-14)
+
+
+def test_errors_are_raised():
+    g = gb.Grid(10.0, 12)
+    with pytest.raises(gb.GxError):
+        f = gb.Field(g, fourier=False)
+        f.toFourier()
