@@ -4,6 +4,8 @@ import sys
 import time
 
 import numpy as np
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import genetic_b200 as gb
 from genetic_b200 import lib as L
