@@ -21,7 +21,6 @@ FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 def _deps():
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "genetic_b200.h"))
-    hdrs.append(os.path.join(os.path.dirname(HERE), "oracle", "zig_tables.h"))  # constant data only
     return max(os.path.getmtime(h) for h in hdrs if os.path.exists(h))
 
 

@@ -1,0 +1,566 @@
+// White noise on the device, draw-for-draw identical to the reference's GSL stream.
+//
+// Replaces fields::RandomFieldGenerator::draw (randomfieldgenerator.hpp:122-139):
+//   drawRandomForSpecifiedGrid        :181-197  N^3 gaussians in cell order, then r2c and Re(DC) = 0
+//   drawRandomForSpecifiedGridFourier :203-260  square k-shells, serial (one stream) or per-shell streams
+//   drawOneFourierMode                :144-171  two consecutive gaussians per mode, the "also write -k" quirk,
+//                                               later writes overwrite earlier ones
+//
+// Parallelisation (rng_core.cuh has the arithmetic):
+//   1. every stream (one per shell in parallel mode, one in total otherwise) is cut into chunks of kBc
+//      increments (kBc*24 raw outputs); a thread jumps to its chunk with the LCG skip-ahead;
+//   2. pass A: the thread generates its chunk and computes the chunk's *transfer function*: for each of the
+//      four possible positions at which the first ziggurat attempt of the chunk can start, where the parse
+//      leaves the chunk and how many gaussians it accepted (attempts consume 2-4 outputs; the four parses
+//      merge after a few attempts, so this costs ~1.1 parses);
+//   3. a 64-ary tree scan composes the transfer functions (associative) and hands every chunk its true entry
+//      position and the index of its first gaussian;
+//   4. pass B regenerates the chunk, parses it once and delivers gaussian g of the stream straight to its
+//      storage slot -- for the Fourier orders as a gather-free scatter in which a draw is written only if it
+//      is the last writer of its slot (a mode and its conjugate partner can both be drawn in a shell);
+//   5. accepted tail draws (~6e-4 of all) depend on log(): their raw integers are listed and the values are
+//      recomputed on the HOST with the C library's log() -- exactly the call GSL makes -- and patched in, so
+//      the field is bit-identical to what the reference produces on the same machine.
+#include "../../include/genetic_b200.h"
+#include "rng_core.cuh"
+#include "zig_tables.h"  // generated constant tables (GSL's published 128-level ziggurat)
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+namespace gx {
+template <typename T> int mirror(T *field, int n, cudaStream_t st);
+namespace fft { template <typename T> int fft3d(T *data, int n, int dir, cudaStream_t st); }
+
+namespace rng {
+
+constexpr int kBc = 64;                 // increments per chunk
+constexpr int kChunkLen = kBc * 24;     // raw outputs per chunk
+constexpr int kThreads = 128;
+constexpr int kJumpBits = 40;
+
+__device__ unsigned int d_zig_ktab[128];
+__device__ double d_zig_wtab[128];
+__device__ double d_zig_ytab[128];
+
+struct StreamDesc {
+  State s0;              // seed state (used when the stream starts at block 0)
+  Big xs;                // X at block b0 (start block of the stream's first chunk)
+  long long b0;          // first block index of the stream's first chunk
+  int entry0;            // position of the first attempt inside the first chunk
+  int first_chunk;       // index of the stream's first chunk in the global chunk list
+  long long n_gauss;     // gaussians wanted from this stream
+  int shell;             // ks for per-shell streams, 0 otherwise
+};
+
+struct ChunkFn {
+  long long count[4];
+  unsigned char exit[4];
+  unsigned char reset;
+};
+
+struct ScanState {
+  long long base;
+  int entry;
+};
+
+struct TailEvent {
+  long long g;       // stream-local gaussian index
+  int stream;
+  unsigned int u1;   // raw integer behind U1
+  int positive;      // sign of the draw
+};
+
+enum { MODE_REAL = 0, MODE_FOURIER_SERIAL = 1, MODE_FOURIER_PARALLEL = 2, MODE_LIST = 3 };
+
+template <typename T> struct Dest {
+  int mode;
+  int n;
+  int reverse;
+  double sigma;      // FloatType sigma = 1.0 / sqrt(2.0) (randomfieldgenerator.hpp:213), widened to double
+  T *field;          // padded field (real or Fourier layout)
+  double *list;      // MODE_LIST: plain gaussian list (test hook)
+};
+
+__device__ __forceinline__ ChunkFn compose(const ChunkFn &f, const ChunkFn &g) {  // f first, then g
+  if (g.reset) return g;
+  ChunkFn h;
+  h.reset = f.reset;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h.exit[e] = g.exit[f.exit[e]];
+    h.count[e] = f.count[e] + g.count[f.exit[e]];
+  }
+  return h;
+}
+
+__device__ __forceinline__ ScanState apply_fn(const ChunkFn &f, const ScanState &s) {
+  ScanState o;
+  if (f.reset) { o.entry = f.exit[0]; o.base = f.count[0]; }
+  else { o.entry = f.exit[s.entry]; o.base = s.base + f.count[s.entry]; }
+  return o;
+}
+
+// ---- delivery of gaussian g of a stream to its destination ---------------------------------------------------
+// calls before shell ks in the serial order: sum_{j<ks} 3 (2j)^2 = 2 (ks-1) ks (2ks-1)
+__device__ __forceinline__ long long calls_before_shell(long long ks) { return 2 * (ks - 1) * ks * (2 * ks - 1); }
+
+// index of the drawOneFourierMode call that draws mode (k1,k2,k3) inside its shell, or -1 if it is never drawn
+__device__ __forceinline__ long long call_index_in_shell(int ks, int a, int b, int c) {
+  // drawn iff exactly one coordinate equals +ks and the other two lie in [-ks, ks-1]
+  const int np = (a == ks) + (b == ks) + (c == ks);
+  if (np != 1) return -1;
+  int face, p, q;
+  if (a == ks) { face = 0; p = b; q = c; }
+  else if (b == ks) { face = 1; p = a; q = c; }
+  else { face = 2; p = a; q = b; }
+  if (p < -ks || p >= ks || q < -ks || q >= ks) return -1;
+  return ((long long) (p + ks) * (2 * ks) + (q + ks)) * 3 + face;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_part(T *field, int n, int kx, int ky, int kz, int part, T v) {
+  // kz >= 0 here
+  if (ky < 0) ky += n;
+  if (kx < 0) kx += n;
+  const size_t slot = (size_t) kz + (size_t) (n / 2 + 1) * ((size_t) ky + (size_t) n * kx);
+  field[2 * slot + part] = v;
+}
+
+template <typename T>
+__device__ void deliver(const Dest<T> &d, const StreamDesc &sd, long long g, double value) {
+  if (d.mode == MODE_LIST) { d.list[g] = value; return; }
+  const int n = d.n;
+  if (d.mode == MODE_REAL) {
+    const long long row = g / n;
+    const int z = (int) (g - row * n);
+    d.field[row * (n + 2) + z] = (T) value;
+    return;
+  }
+  // Fourier orders: gaussian g -> call c = g/2, component g&1
+  long long c = g >> 1;
+  const int comp = (int) (g & 1);
+  int ks;
+  if (d.mode == MODE_FOURIER_PARALLEL) ks = sd.shell;
+  else {
+    ks = (int) cbrt((double) c / 4.0) + 1;
+    while (ks > 1 && calls_before_shell(ks) > c) --ks;
+    while (calls_before_shell(ks + 1) <= c) ++ks;
+    c -= calls_before_shell(ks);
+  }
+  const int face = (int) (c % 3);
+  const long long t = c / 3;
+  const int p = (int) (t / (2 * ks)) - ks, q = (int) (t % (2 * ks)) - ks;
+  int k1, k2, k3;
+  if (face == 0) { k1 = ks; k2 = p; k3 = q; }
+  else if (face == 1) { k1 = p; k2 = ks; k3 = q; }
+  else { k1 = p; k2 = q; k3 = ks; }
+  // last-writer-wins: the conjugate partner -k may be drawn in the same shell
+  const long long cp = call_index_in_shell(ks, -k1, -k2, -k3);
+  if (cp > c) return;
+  // value of this component in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2))
+  const T v = (T) GX_DMUL(d.sigma, value);
+  // normal order: (a, b) -> (re, im); reverse: (b, a)
+  const int part = d.reverse ? (1 - comp) : comp;
+  // setFourierCoefficient(k, val): stored at the kz >= 0 representative, imaginary part negated if conjugated
+  if (k3 < 0) store_part<T>(d.field, n, -k1, -k2, -k3, part, part == 1 ? -v : v);
+  else store_part<T>(d.field, n, k1, k2, k3, part, v);
+  // the explicit second write, setFourierCoefficient(-k, conj(val)), lands on a different slot only when k3 == 0
+  if (k3 == 0) store_part<T>(d.field, n, -k1, -k2, 0, part, part == 1 ? -v : v);
+}
+
+// ---- chunk kernels -------------------------------------------------------------------------------------------
+struct ChunkParams {
+  const StreamDesc *streams;
+  const int *chunk_stream;
+  int n_chunks;
+  const Big *jump;            // jump[j] = a^(397 * kBc * 2^j)
+  ChunkFn *fn;                // pass A output
+  const ScanState *scan;      // pass B input
+  unsigned long long *stream_end;  // pass B: raw position after the last wanted gaussian (per stream)
+  TailEvent *tails;
+  unsigned int *tail_count;
+  unsigned int tail_capacity;
+};
+
+__device__ __forceinline__ State chunk_start_state(const StreamDesc &sd, int q, const Big *jump) {
+  if (sd.b0 == 0 && q == 0) return sd.s0;
+  Big X = sd.xs;
+  for (int j = 0; j < kJumpBits; ++j)
+    if ((q >> j) & 1) X = modmul(X, jump[j]);
+  return big_to_state(X);
+}
+
+template <int PASS, typename T>
+__global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest<T> dest) {
+  __shared__ unsigned int s_k[128];
+  __shared__ double s_w[128], s_y[128];
+  __shared__ uint32_t ring[48][kThreads];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_k[i] = d_zig_ktab[i]; s_w[i] = d_zig_wtab[i]; s_y[i] = d_zig_ytab[i]; }
+  __syncthreads();
+  const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= P.n_chunks) return;
+  const int sid = P.chunk_stream[chunk];
+  const StreamDesc &sd = P.streams[sid];
+  const int q = chunk - sd.first_chunk;
+  const bool first = (q == 0);
+  const int tx = threadIdx.x;
+
+  int pos[4];
+  long long cnt[4];
+  int rep[4];          // representative cursor after a merge (-1: own)
+  long long delta[4];  // cnt[e] - cnt[rep[e]] at merge time
+  int ncur;
+  long long g = 0;
+  if (PASS == 0) {
+    if (first) { ncur = 1; pos[0] = sd.entry0; }
+    else { ncur = 4; for (int e = 0; e < 4; ++e) pos[e] = e; }
+    for (int e = 0; e < 4; ++e) { cnt[e] = 0; rep[e] = -1; delta[e] = 0; }
+  } else {
+    const ScanState ss = P.scan[chunk];
+    ncur = 1;
+    pos[0] = first ? sd.entry0 : ss.entry;
+    g = first ? 0 : ss.base;
+    if (g >= sd.n_gauss) return;  // nothing wanted from this chunk
+  }
+
+  State st = chunk_start_state(sd, q, P.jump);
+
+  for (int bi = 0; bi <= kBc; ++bi) {
+    advance_block(st);
+    const int half = (bi & 1) * 24;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) ring[half + j][tx] = block_output(st, j);
+    const int avail = 24 * (bi + 1);
+    const int limit = min(avail - 3, kChunkLen);
+    for (int e = 0; e < ncur; ++e) {
+      if (PASS == 0 && rep[e] >= 0) continue;
+      int p = pos[e];
+      while (p < limit) {
+        const Attempt a = zig_attempt(ring[p % 48][tx], ring[(p + 1) % 48][tx], ring[(p + 2) % 48][tx],
+                                      ring[(p + 3) % 48][tx], s_k, s_w, s_y);
+        p += a.consumed;
+        if (a.accepted) {
+          if (PASS == 0) cnt[e]++;
+          else {
+            if (g < sd.n_gauss) {
+              deliver<T>(dest, sd, g, a.value);
+              if (a.tail) {
+                const unsigned int slot = atomicAdd(P.tail_count, 1u);
+                if (slot < P.tail_capacity) {
+                  TailEvent ev; ev.g = g; ev.stream = sid; ev.u1 = a.tail_u1; ev.positive = a.value > 0;
+                  P.tails[slot] = ev;
+                }
+              }
+              if (g == sd.n_gauss - 1)
+                P.stream_end[sid] = (unsigned long long) (sd.b0 + (long long) q * kBc) * 24ull + (unsigned long long) p;
+            }
+            ++g;
+          }
+        }
+      }
+      pos[e] = p;
+    }
+    if (PASS == 0 && ncur == 4) {
+      // merge cursors that have reached the same position
+      for (int e = 1; e < 4; ++e) {
+        if (rep[e] >= 0) continue;
+        for (int r = 0; r < e; ++r) {
+          if (rep[r] < 0 && pos[r] == pos[e]) { rep[e] = r; delta[e] = cnt[e] - cnt[r]; break; }
+        }
+      }
+    }
+    if (PASS == 1 && g >= sd.n_gauss) break;
+  }
+
+  if (PASS == 0) {
+    ChunkFn f;
+    f.reset = first ? 1 : 0;
+    for (int e = 0; e < 4; ++e) {
+      const int src = first ? 0 : e;
+      const int r = rep[src] >= 0 ? rep[src] : src;
+      f.exit[e] = (unsigned char) (pos[r] - kChunkLen);
+      f.count[e] = cnt[r] + (rep[src] >= 0 ? delta[src] : 0);
+    }
+    P.fn[chunk] = f;
+  }
+}
+
+// ---- scan over chunk functions -----------------------------------------------------------------------------------
+__global__ void scan_up_kernel(const ChunkFn *in, int n_in, ChunkFn *out, int n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  ChunkFn h = in[(size_t) 64 * i];
+  for (int k = 1; k < 64; ++k) {
+    const size_t idx = (size_t) 64 * i + k;
+    if (idx >= (size_t) n_in) break;
+    h = compose(h, in[idx]);
+  }
+  out[i] = h;
+}
+
+__global__ void scan_top_kernel(const ChunkFn *fn, int n, ScanState *st) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  ScanState s; s.base = 0; s.entry = 0;
+  for (int i = 0; i < n; ++i) { st[i] = s; s = apply_fn(fn[i], s); }
+}
+
+__global__ void scan_down_kernel(const ChunkFn *child_fn, int n_child, const ScanState *parent, int n_parent,
+                                 ScanState *child) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_parent) return;
+  ScanState s = parent[i];
+  for (int k = 0; k < 64; ++k) {
+    const size_t idx = (size_t) 64 * i + k;
+    if (idx >= (size_t) n_child) break;
+    child[idx] = s;
+    s = apply_fn(child_fn[idx], s);
+  }
+}
+
+// ---- patch kernel: re-deliver tail draws with host-computed values -------------------------------------------------
+template <typename T>
+__global__ void tail_patch_kernel(const TailEvent *ev, const double *values, unsigned int n, const StreamDesc *streams,
+                                  Dest<T> dest) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  deliver<T>(dest, streams[ev[i].stream], ev[i].g, values[i]);
+}
+
+// test hook: plain raw outputs of whole chunks
+__global__ void raw_chunks_kernel(StreamDesc sd, const Big *jump, long long q0, int nch, uint32_t *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nch) return;
+  State st = chunk_start_state(sd, (int) (q0 + i), jump);
+  for (int bi = 0; bi < kBc; ++bi) {
+    advance_block(st);
+    for (int j = 0; j < 24; ++j) out[((size_t) i * kBc + bi) * 24 + j] = block_output(st, j);
+  }
+}
+
+template <typename T> __global__ void zero_dc_real_kernel(T *field) { field[0] = (T) 0; }
+
+// ---- host driver ------------------------------------------------------------------------------------------------------
+static Big *g_jump = nullptr;
+static int ensure_jump_table() {
+  if (g_jump) return 0;
+  std::vector<Big> h(kJumpBits);
+  Big base = modpow(big_a(), 397ull * kBc);
+  for (int j = 0; j < kJumpBits; ++j) { h[j] = base; base = modmul(base, base); }
+  GX_CUDA_CHECK(cudaMemcpyToSymbol(d_zig_ktab, gx_zig_ktab, sizeof(gx_zig_ktab)));
+  GX_CUDA_CHECK(cudaMemcpyToSymbol(d_zig_wtab, gx_zig_wtab, sizeof(gx_zig_wtab)));
+  GX_CUDA_CHECK(cudaMemcpyToSymbol(d_zig_ytab, gx_zig_ytab, sizeof(gx_zig_ytab)));
+  GX_CUDA_CHECK(cudaMalloc(&g_jump, sizeof(Big) * kJumpBits));
+  GX_CUDA_CHECK(cudaMemcpy(g_jump, h.data(), sizeof(Big) * kJumpBits, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static long long calls_before_shell_host(long long ks) { return 2 * (ks - 1) * ks * (2 * ks - 1); }
+
+static long long raw_budget(long long n_gauss) {
+  // mean 2.0247 raw outputs per gaussian, sd ~0.16 per gaussian; generous margin, verified after the fact
+  return (long long) (2.03 * (double) n_gauss + 8.0 * sqrt((double) n_gauss) + 128.0);
+}
+
+struct StreamReq { unsigned long seed; unsigned long long start_raw; long long n_gauss; int shell; };
+
+template <typename T>
+static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::vector<unsigned long long> *end_raw,
+                       cudaStream_t cs) {
+  if (ensure_jump_table()) return 1;
+  const int ns = (int) reqs.size();
+  std::vector<StreamDesc> sd(ns);
+  std::vector<int> chunk_stream;
+  const Big a = big_a();
+  for (int s = 0; s < ns; ++s) {
+    StreamDesc &d = sd[s];
+    d.s0 = seed_state(reqs[s].seed);
+    d.b0 = (long long) (reqs[s].start_raw / 24ull);
+    d.entry0 = (int) (reqs[s].start_raw % 24ull);
+    d.n_gauss = reqs[s].n_gauss;
+    d.shell = reqs[s].shell;
+    d.xs = state_to_big(d.s0);
+    if (d.b0 > 0) d.xs = modmul(d.xs, modpow(a, 397ull * (unsigned long long) d.b0));
+    d.first_chunk = (int) chunk_stream.size();
+    const long long raws = d.entry0 + raw_budget(d.n_gauss);
+    const long long nch = (raws + kChunkLen - 1) / kChunkLen;
+    if ((long long) chunk_stream.size() + nch > 2000000000ll) return fail("gx_noise_draw: too many chunks");
+    chunk_stream.insert(chunk_stream.end(), (size_t) nch, s);
+  }
+  const int n0 = (int) chunk_stream.size();
+  if (n0 == 0) return 0;
+
+  StreamDesc *d_streams = nullptr; int *d_chunk_stream = nullptr; unsigned long long *d_end = nullptr;
+  unsigned int *d_tail_count = nullptr; TailEvent *d_tails = nullptr;
+  long long total_gauss = 0;
+  for (auto &r : reqs) total_gauss += r.n_gauss;
+  const unsigned int tail_cap = (unsigned int) std::min<long long>((long long) (total_gauss * 8e-4) + 4096, 400000000ll);
+  GX_CUDA_CHECK(cudaMalloc(&d_streams, sizeof(StreamDesc) * ns));
+  GX_CUDA_CHECK(cudaMalloc(&d_chunk_stream, sizeof(int) * (size_t) n0));
+  GX_CUDA_CHECK(cudaMalloc(&d_end, sizeof(unsigned long long) * ns));
+  GX_CUDA_CHECK(cudaMalloc(&d_tail_count, sizeof(unsigned int)));
+  GX_CUDA_CHECK(cudaMalloc(&d_tails, sizeof(TailEvent) * (size_t) tail_cap));
+  GX_CUDA_CHECK(cudaMemcpyAsync(d_streams, sd.data(), sizeof(StreamDesc) * ns, cudaMemcpyHostToDevice, cs));
+  GX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_stream, chunk_stream.data(), sizeof(int) * (size_t) n0, cudaMemcpyHostToDevice, cs));
+  GX_CUDA_CHECK(cudaMemsetAsync(d_end, 0xFF, sizeof(unsigned long long) * ns, cs));
+  GX_CUDA_CHECK(cudaMemsetAsync(d_tail_count, 0, sizeof(unsigned int), cs));
+
+  // scan levels
+  std::vector<int> level_n;
+  level_n.push_back(n0);
+  while (level_n.back() > 4096) level_n.push_back((level_n.back() + 63) / 64);
+  const int nl = (int) level_n.size();
+  std::vector<ChunkFn *> d_fn(nl, nullptr);
+  std::vector<ScanState *> d_st(nl, nullptr);
+  for (int l = 0; l < nl; ++l) {
+    GX_CUDA_CHECK(cudaMalloc(&d_fn[l], sizeof(ChunkFn) * (size_t) level_n[l]));
+    GX_CUDA_CHECK(cudaMalloc(&d_st[l], sizeof(ScanState) * (size_t) level_n[l]));
+  }
+
+  ChunkParams P;
+  P.streams = d_streams; P.chunk_stream = d_chunk_stream; P.n_chunks = n0; P.jump = g_jump; P.fn = d_fn[0];
+  P.scan = d_st[0]; P.stream_end = d_end; P.tails = d_tails; P.tail_count = d_tail_count; P.tail_capacity = tail_cap;
+  const int grid = (n0 + kThreads - 1) / kThreads;
+  rng_chunk_kernel<0, T><<<grid, kThreads, 0, cs>>>(P, dest);
+  count_launch();
+  GX_LAUNCH_CHECK();
+  for (int l = 1; l < nl; ++l) {
+    scan_up_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_fn[l], level_n[l]);
+    count_launch();
+  }
+  scan_top_kernel<<<1, 32, 0, cs>>>(d_fn[nl - 1], level_n[nl - 1], d_st[nl - 1]);
+  count_launch();
+  for (int l = nl - 1; l >= 1; --l) {
+    scan_down_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_st[l], level_n[l], d_st[l - 1]);
+    count_launch();
+  }
+  GX_LAUNCH_CHECK();
+  rng_chunk_kernel<1, T><<<grid, kThreads, 0, cs>>>(P, dest);
+  count_launch();
+  GX_LAUNCH_CHECK();
+
+  // tails: host libm recomputation (the reference's own arithmetic for these draws)
+  unsigned int ntail = 0;
+  std::vector<unsigned long long> h_end(ns);
+  GX_CUDA_CHECK(cudaMemcpyAsync(&ntail, d_tail_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h_end.data(), d_end, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToHost, cs));
+  GX_CUDA_CHECK(cudaStreamSynchronize(cs));
+  int rc = 0;
+  if (ntail > tail_cap) rc = fail("gx_noise_draw: tail list overflow");
+  for (int s = 0; s < ns && !rc; ++s)
+    if (reqs[s].n_gauss > 0 && h_end[s] == ~0ull) rc = fail("gx_noise_draw: raw budget too small for a stream (internal)");
+  if (!rc && ntail > 0) {
+    std::vector<TailEvent> ev(ntail);
+    std::vector<double> val(ntail);
+    rc = cudaMemcpy(ev.data(), d_tails, sizeof(TailEvent) * ntail, cudaMemcpyDeviceToHost) != cudaSuccess;
+    const double R = GX_ZIG_R;
+    for (unsigned int i = 0; i < ntail; ++i) {
+      const double U1 = 1.0 - (double) ev[i].u1 / 16777216.0;
+      const double x = R - std::log(U1) / R;
+      val[i] = ev[i].positive ? x : -x;
+    }
+    double *d_val = nullptr;
+    if (!rc) rc = cudaMalloc(&d_val, sizeof(double) * ntail) != cudaSuccess;
+    if (!rc) rc = cudaMemcpyAsync(d_val, val.data(), sizeof(double) * ntail, cudaMemcpyHostToDevice, cs) != cudaSuccess;
+    if (!rc) {
+      tail_patch_kernel<T><<<(ntail + 127) / 128, 128, 0, cs>>>(d_tails, d_val, ntail, d_streams, dest);
+      count_launch();
+      rc = cudaStreamSynchronize(cs) != cudaSuccess;
+    }
+    if (d_val) cudaFree(d_val);
+    if (rc) fail("gx_noise_draw: tail patch failed");
+  }
+  if (end_raw) *end_raw = h_end;
+  for (int l = 0; l < nl; ++l) { cudaFree(d_fn[l]); cudaFree(d_st[l]); }
+  cudaFree(d_streams); cudaFree(d_chunk_stream); cudaFree(d_end); cudaFree(d_tail_count); cudaFree(d_tails);
+  return rc;
+}
+
+template <typename T>
+static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int reverse, unsigned long long *offset_io,
+                        cudaStream_t cs) {
+  const size_t bytes = (size_t) 2 * n * n * (n / 2 + 1) * sizeof(T);
+  GX_CUDA_CHECK(cudaMemsetAsync(field, 0, bytes, cs));
+  Dest<T> dest;
+  dest.n = n; dest.reverse = reverse; dest.field = (T *) field; dest.list = nullptr;
+  dest.sigma = (double) (T) (1.0 / sqrt(2.0));
+  const long long n3 = (long long) n * n * n;
+  const unsigned long long start = offset_io ? *offset_io : 0ull;
+  std::vector<StreamReq> reqs;
+  std::vector<unsigned long long> ends;
+  if (mode == GX_NOISE_REAL) {
+    dest.mode = MODE_REAL;
+    reqs.push_back({seed, start, n3, 0});
+  } else if (mode == GX_NOISE_FOURIER_SERIAL) {
+    dest.mode = MODE_FOURIER_SERIAL;
+    const long long h = n / 2;
+    reqs.push_back({seed, start, 2 * calls_before_shell_host(h), 0});
+  } else if (mode == GX_NOISE_FOURIER_PARALLEL) {
+    dest.mode = MODE_FOURIER_PARALLEL;
+    for (int ks = 1; ks < n / 2; ++ks) reqs.push_back({seed + (unsigned long) ks, 0ull, 24ll * ks * ks, ks});
+  } else {
+    return fail("gx_noise_draw: unknown mode");
+  }
+  int rc = run_streams<T>(reqs, dest, &ends, cs);
+  if (rc) return rc;
+  if (mode == GX_NOISE_REAL) {
+    rc = fft::fft3d<T>((T *) field, n, -1, cs);
+    if (rc) return rc;
+    zero_dc_real_kernel<T><<<1, 1, 0, cs>>>((T *) field);  // tools::set_zero(fieldData[0]) :195
+    count_launch();
+    GX_LAUNCH_CHECK();
+  }
+  if (offset_io && mode != GX_NOISE_FOURIER_PARALLEL && !ends.empty()) *offset_io = ends[0];
+  return 0;
+}
+
+}  // namespace rng
+}  // namespace gx
+
+using namespace gx;
+using namespace gx::rng;
+
+extern "C" {
+
+int gx_noise_draw(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
+                  unsigned long long *stream_offset_io, void *stream) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (dtype == GX_F64) return noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
+  if (dtype == GX_F32) return noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
+  return gx::fail("bad dtype");
+}
+
+int gx_rng_raw(unsigned long seed, unsigned long long offset, long n, uint32_t *host_out) {
+  if (ensure_jump_table()) return 1;
+  StreamDesc sd;
+  sd.s0 = seed_state(seed); sd.xs = state_to_big(sd.s0); sd.b0 = 0; sd.entry0 = 0; sd.first_chunk = 0; sd.n_gauss = 0; sd.shell = 0;
+  const long long q0 = (long long) (offset / kChunkLen);
+  const long long q1 = (long long) ((offset + (unsigned long long) n + kChunkLen - 1) / kChunkLen);
+  const int nch = (int) (q1 - q0);
+  uint32_t *d = nullptr;
+  GX_CUDA_CHECK(cudaMalloc(&d, sizeof(uint32_t) * (size_t) nch * kChunkLen));
+  raw_chunks_kernel<<<(nch + 63) / 64, 64>>>(sd, g_jump, q0, nch, d);
+  count_launch();
+  GX_LAUNCH_CHECK();
+  int rc = cudaMemcpy(host_out, d + (offset - (unsigned long long) q0 * kChunkLen), sizeof(uint32_t) * (size_t) n,
+                      cudaMemcpyDeviceToHost) != cudaSuccess;
+  cudaFree(d);
+  return rc ? gx::fail("gx_rng_raw: copy failed") : 0;
+}
+
+int gx_rng_gaussians(unsigned long seed, long n, double *host_out, unsigned long long *raw_consumed) {
+  double *d = nullptr;
+  GX_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * (size_t) n));
+  Dest<double> dest;
+  dest.mode = MODE_LIST; dest.n = 0; dest.reverse = 0; dest.field = nullptr; dest.list = d; dest.sigma = 1.0;
+  std::vector<StreamReq> reqs;
+  reqs.push_back({seed, raw_consumed ? *raw_consumed : 0ull, (long long) n, 0});
+  std::vector<unsigned long long> ends;
+  int rc = run_streams<double>(reqs, dest, &ends, 0);
+  if (!rc) rc = cudaMemcpy(host_out, d, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost) != cudaSuccess;
+  cudaFree(d);
+  if (!rc && raw_consumed) *raw_consumed = ends[0];
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""GPU parity: device white noise (ranlxs2 + ziggurat with skip-ahead and scan) is bit-exact against the oracle's
+sequential GSL restatement, for every draw order of the reference; and the whole unigrid chain reproduces the
+reference's golden particle files."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import genetic_b200 as gb
+from genetic_b200 import lib as L
+from oracle import crng, model as M
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("seed,offset,n", [(42, 0, 5000), (42, 1536 * 3 + 7, 4000), (8896131, 1536 * 64 * 5 + 1535, 3000),
+                                           (13842314, 987654321, 2000)])
+def test_device_raw_stream(seed, offset, n):
+    lib = L.load()
+    out = np.empty(n, dtype=np.uint32)
+    lib.gx_rng_raw(seed, offset, n, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, crng.raw_stream(seed, offset + n)[offset:])
+
+
+@pytest.mark.parametrize("seed,n", [(42, 10), (43, 1000), (13842314, 64 ** 3), (7, 1_000_000)])
+def test_device_gaussians_bit_exact(seed, n):
+    lib = L.load()
+    out = np.empty(n, dtype=np.float64)
+    used = C.c_ulonglong(0)
+    lib.gx_rng_gaussians(seed, n, out.ctypes.data_as(C.c_void_p), C.byref(used))
+    s = crng.Stream(seed)
+    ref = s.gaussians(n)
+    assert np.array_equal(out, ref)
+    # the stream position after n gaussians: the next raw output must be what the sequential stream gives next
+    nxt = np.empty(1, dtype=np.uint32)
+    lib.gx_rng_raw(seed, used.value, 1, nxt.ctypes.data_as(C.c_void_p))
+    assert nxt[0] == int(s.uniform() * 16777216.0)
+
+
+def _draw(n, seed, mode, dtype, reverse=False):
+    g = gb.Grid(100.0, n, dtype=dtype)
+    f = gb.Field(g, fourier=True)
+    r = gb.RandomFieldGenerator(f)
+    r.seed(seed)
+    r.setDrawInFourierSpace(mode != "real")
+    r.setParallel(mode == "fourier_parallel")
+    r.setReverseRandomDrawOrder(reverse)
+    r.draw()
+    return f
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+@pytest.mark.parametrize("mode,reverse", [("fourier_parallel", False), ("fourier_serial", False),
+                                          ("fourier_serial", True)])
+def test_fourier_draws_bit_exact(n, mode, reverse, dtype):
+    seed = 8896131
+    f = _draw(n, seed, mode, dtype, reverse)
+    W = f.getDataVector()
+    omode = "fourier_reverse" if reverse else mode
+    Wo = M.draw_white_noise(n, seed, omode, dtype)
+    assert np.array_equal(W, Wo.astype(W.dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_real_space_draw_and_chi2_golden(dtype):
+    n, seed = 64, 13842314
+    f = _draw(n, seed, "real", dtype)
+    W = f.getDataVector()
+    Wo = M.draw_white_noise(n, seed, "real", dtype)
+    tol = 1e-10 if dtype == np.float64 else 1e-5
+    assert np.abs(W - Wo).max() < tol * np.abs(Wo).max()
+    assert W[0, 0, 0].real == 0
+    if dtype == np.float64:
+        # tests/test_02k_chisquare_onelevel/reference.txt through the device reduction
+        chi2 = f.innerProduct(f)
+        ref = open(os.path.join(GOLD, "test_02k_chisquare_onelevel", "reference.txt")).read().strip()
+        assert "Calculated chi^2 = %.10g (dof = %d)" % (chi2, n ** 3) == ref
+
+
+def test_serial_streams_continue_across_levels():
+    """randomfieldgenerator.hpp:125-138: all levels are drawn from one stream in the serial modes."""
+    seed = 1512351
+    g1, g2 = gb.Grid(50.0, 16), gb.Grid(25.0, 32)
+    f1, f2 = gb.Field(g1), gb.Field(g2)
+    r = gb.RandomFieldGenerator([f1, f2])
+    r.seed(seed)
+    r.setDrawInFourierSpace(True)
+    r.draw()
+    st = crng.Stream(seed)
+    assert np.array_equal(f1.getDataVector(), M.draw_white_noise(16, seed, "fourier_serial", stream=st))
+    assert np.array_equal(f2.getDataVector(), M.draw_white_noise(32, seed, "fourier_serial", stream=st))
+
+
+@pytest.mark.parametrize("test,box,seed,mode", [
+    ("test_13_parallel_seed", 10.0, 42, "fourier_parallel"),
+    ("test_05a_seed_old", 50.0, 8896131, "fourier_reverse"),
+])
+def test_reference_goldens_end_to_end(test, box, seed, mode):
+    """The reference's own golden tipsy files, reproduced by the device path (float32 file precision)."""
+    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99)
+    camb = os.path.join(GOLD, "camb_transfer_kmax40_z0.dat")
+    pos, vel, mass, eps = gb.generate_unigrid_ic(8, box, seed, cos, camb, mode=mode, out_dtype=np.float64)
+    ocos = M.Cosmology(0.279, 0.721, 0.817, 99)
+    t = M.to_tipsy_units(pos, vel, mass, eps, box, ocos, 8 ** 3)
+    g = M.read_tipsy(os.path.join(GOLD, test, "reference_output"))
+    ulp_p = np.abs(t["pos"] - g["pos"]) / np.spacing(np.abs(g["pos"]))
+    ulp_v = np.abs(t["vel"] - g["vel"]) / np.spacing(np.abs(g["vel"]))
+    assert ulp_p.max() <= 1 and ulp_v.max() <= 1
+    assert (ulp_p == 0).mean() > 0.99 and (ulp_v == 0).mean() > 0.99
+    assert np.all(g["mass"] == t["mass"]) and np.all(g["eps"] == t["eps"])
+
+
+def test_unigrid_128_vs_oracle():
+    """Whole chain at 128^3 against the oracle on the same seed: 1e-10 relative (north-star tolerance, f64)."""
+    n, box, seed = 128, 100.0, 8896131
+    camb = os.path.join(GOLD, "planck_2018_transfer_out.dat")
+    cos = gb.CosmologicalParameters(0.3158, 0.6842, 0.8117, 200, ns=0.9660, hubble=0.6732)
+    pos, vel, mass, eps = gb.generate_unigrid_ic(n, box, seed, cos, camb, out_dtype=np.float64)
+    ocos = M.Cosmology(0.3158, 0.6842, 0.8117, 200, ns=0.9660, hubble=0.6732)
+    opos, ovel, omass, oeps = M.unigrid_ic(n, box, seed, "fourier_parallel", camb, ocos)
+    assert np.abs(vel - ovel).max() < 1e-10 * np.abs(ovel).max()
+    d = np.abs(pos - opos)
+    d = np.minimum(d, box - d)
+    assert d.max() < 1e-10 * box
+    assert mass == omass and eps == oeps
