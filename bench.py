@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- IC particles/sec for a Zeldovich unigrid IC generated from a seed (BASELINE.json metric).
+
+One "step" = the whole hot path for one IC: draw white noise from the seed (GSL-exact, parallel Fourier order)
+-> delta_k = sqrt(C(k)) * noise -> psi_xyz = c2r(i k_j delta_k / k^2) -> particle positions and velocities.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n GRID] [--impl ours|reference]
+
+  value : N^3 / step time, device timed (CUDA events), results left in HBM (staging buffer)
+  e2e   : the same through the C-ABI call with HOST buffers: the transfer table is uploaded and the particles are
+          copied to pinned host memory inside the timed region
+  roofline     : the dominant kernel's algorithmic GB/s (2*B per FFT pass) against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle port (oracle/) timed on this box's host cores on a bounded sample
+`--impl reference` times the CPU port alone (the reference cannot be compiled in this image: FFTW3, GSL and HDF5 are
+absent) with the same metric/config keys.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+CAMB_FILE = os.path.join(GOLD, "planck_2018_transfer_out.dat")
+SEED = 8896131
+COSMO = dict(Om=0.3158, Ol=0.6842, s8=0.8117, z=200.0, ns=0.9660, hubble=0.6732)  # example/paramfile.txt:4-10
+
+
+def box_for(n):
+    return 200.0 * n / 512.0  # 512^3 -> L=200, 2048^3 -> L=1000 (k_Nyq stays inside the CAMB table)
+
+
+def workload_name(n, dtype):
+    return "%d^3 unigrid %s, L=%g Mpc/h, Planck-2018 CAMB transfer, random_seed %d (parallel Fourier), " \
+           "Zeldovich displacement+velocity" % (n, dtype, box_for(n), SEED)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_port_step(n, threads):
+    """One IC through the CPU oracle port (the reference's algorithm on the host cores). Returns seconds.
+    C/OpenMP: per-shell ranlxs2+ziggurat draw (randomfieldgenerator.hpp:226-243), covariance field and transfer
+    (camb.hpp:101-119, field.hpp:394-412). numpy/scipy(pocketfft, `threads` workers): ik/k^2 and the three c2r."""
+    import numpy as np
+    import scipy.fft
+    from oracle import model as M, crng
+    box = box_for(n)
+    cos = M.Cosmology(COSMO["Om"], COSMO["Ol"], COSMO["s8"], COSMO["z"], ns=COSMO["ns"], hubble=COSMO["hubble"])
+    t0 = time.perf_counter()
+    buf = crng.draw_fourier_parallel_shells(SEED, n, 0, n // 2)
+    W = buf.view(np.complex128).reshape(n, n, n // 2 + 1)
+    camb = M.CAMB(CAMB_FILE, cos)
+    cov = camb.covariance(box, n, "all")
+    D = M.apply_transfer(W, cov, 0.5)
+    psis_k = M.zeldovich_offsets_fourier(D, box)
+    psis = []
+    for p in psis_k:
+        M.mirror_fast(p)
+        psis.append(scipy.fft.irfftn(p, s=(n, n, n), axes=(0, 1, 2), workers=threads) * (float(n) ** 1.5))
+    pos, vel, mass, eps = M.particles_unigrid(psis, box, cos)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n = args.cpu_n
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_step(min(n, 128), threads)
+    times = [cpu_port_step(n, threads) for _ in range(max(1, min(args.steps, 3)))]
+    t = statistics.mean(times)
+    v = n ** 3 / t
+    sample = "%d^3 unigrid (the %d^3 workload does not fit the CPU time budget); CPU oracle port: C/OpenMP draw + " \
+             "covariance, numpy/pocketfft FFTs with %d workers (FFTW/GSL absent, reference not compilable here)" % (
+                 n, args.n, threads)
+    line = {"impl": "reference", "metric": "IC particles/sec (Zeldovich %d^3)" % args.n, "value": v,
+            "unit": "particles/s", "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.n, "f64"), "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "particles/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from genetic_b200 import lib as L
+    import genetic_b200 as gb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    lib = L.load()
+    lib.gx_set_device(local_rank)
+    if world > 1:
+        from genetic_b200 import slab
+        return slab.bench_main(args, lib, world, rank, local_rank)
+
+    n = args.n
+    dtype = np.float64
+    dt = L.F64
+    box = box_for(n)
+    cos = gb.CosmologicalParameters(COSMO["Om"], COSMO["Ol"], COSMO["s8"], COSMO["z"], ns=COSMO["ns"],
+                                    hubble=COSMO["hubble"])
+    grid = gb.Grid(box, n, dtype=dtype)
+    spectrum = gb.CAMB(cos, CAMB_FILE, "all", dtype)
+    fbytes = lib.gx_field_bytes(n, dt)
+    delta, psi, stage = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    lib.gx_malloc(C.byref(delta), fbytes)
+    lib.gx_malloc(C.byref(psi), fbytes)
+    osz = 4  # the reference's writers store float32 (ic.hpp:1294-1305)
+    n3 = n ** 3
+    stage_bytes = min(2 * 2 * n3 * osz, 2 << 30)
+    stage_bytes = max(stage_bytes, 2 * 2 * n * n * osz)
+    lib.gx_malloc(C.byref(stage), stage_bytes)
+    # host arrays: full component-major arrays if they fit 24 GiB, else a ring
+    cap = n3 if 6 * n3 * osz <= (24 << 30) else (8 << 30) // (3 * osz)
+    hpos, hvel = C.c_void_p(), C.c_void_p()
+    lib.gx_host_alloc_pinned(C.byref(hpos), 3 * cap * osz)
+    lib.gx_host_alloc_pinned(C.byref(hvel), 3 * cap * osz)
+
+    prm = L.IcParams()
+    prm.n, prm.dtype, prm.out_dtype = n, dt, L.F32
+    prm.noise_mode, prm.reverse_order, prm.fix_power = L.NOISE_FOURIER_PARALLEL, 0, 0
+    prm.seed = SEED
+    prm.grid_length, prm.cell_size, prm.domain_size = float(grid.thisGridSize), float(grid.cellSize), float(
+        grid.periodicDomainSize)
+    prm.offset_lower[0] = prm.offset_lower[1] = prm.offset_lower[2] = 0.0
+    prm.vel_ratio = cos.zeldovichVelocityToOffsetRatio(dtype)
+
+    def device_step():
+        lib.gx_unigrid_ic(C.byref(prm), spectrum.handle, delta, psi, stage, stage_bytes, None, None, 0, None)
+
+    def e2e_step():
+        sp = gb.CAMB(cos, CAMB_FILE, "all", dtype)  # host spline + normalisation, table upload (H2D)
+        lib.gx_unigrid_ic(C.byref(prm), sp.handle, delta, psi, stage, stage_bytes, hpos, hvel, cap, None)
+        return sp
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.gx_timing_enable(1)
+    l0 = lib.gx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = lib.gx_launch_count() - l0
+    buf = C.create_string_buffer(1 << 16)
+    lib.gx_timing_report(buf, len(buf))
+    lib.gx_timing_enable(0)
+    clocks = sampler.stop()
+    classes = {}
+    for line in buf.value.decode().strip().split("\n"):
+        if line:
+            nm, cnt, tot = line.split()
+            classes[nm] = (int(cnt), float(tot))
+
+    # e2e: host buffers, copies inside the timed region (wall clock around synchronous calls + device sync)
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    tab_bytes = 3 * 8 * 213
+
+    # roofline of the dominant kernel class
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    fft_classes = {k: v for k, v in classes.items() if k.startswith("fft_")}
+    dom = max(fft_classes, key=lambda k: fft_classes[k][1]) if fft_classes else None
+    roof = None
+    if dom:
+        cnt, tot = classes[dom]
+        avg_ms = tot / cnt
+        achieved = 2 * fbytes / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 2 * fbytes, "avg_launch_ms": avg_ms,
+                "per_class_ms_per_step": {k: v[1] / args.steps for k, v in sorted(classes.items())},
+                "share_of_step": tot / args.steps / ms}
+
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cpu_port_step(64, threads)
+        tcpu = cpu_port_step(args.cpu_n, threads)
+        cpu = {"value": args.cpu_n ** 3 / tcpu, "unit": "particles/s", "cores": threads, "kind": "port",
+               "sample": "one %d^3 IC (%.1f s) through the CPU oracle port: C/OpenMP draw+covariance, pocketfft with "
+                         "%d workers; FFTW/GSL absent so the reference itself cannot be built here" % (
+                             args.cpu_n, tcpu, threads)}
+
+    line = {"metric": "IC particles/sec (Zeldovich %d^3)" % n, "value": n3 / (ms * 1e-3), "unit": "particles/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n, "f64"), "output": "float32 pos+vel, component-major",
+                       "l2": "inputs larger than L2 (each field %.2f GB)" % (fbytes / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": tab_bytes,
+                    "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "512")))
+    ap.add_argument("--cpu-n", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -98,6 +98,8 @@ int launch_cols(const cplx<T> *src, cplx<T> *dst, int n, LoadOp lop, StoreOp sop
   if (Cfg::smem > 48 * 1024) {
     GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
   }
+  const char *tname = std::is_same<Pass, PassY>::value ? "fft_cols_y" : "fft_cols_x";
+  GX_TIMED(tname, st);
   kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(src, dst, n, nc, ncols, line_stride, batch_stride,
                                                         tiles_per_batch, twiddle_table<T>(N), lop, sop);
   count_launch();
@@ -212,6 +214,7 @@ template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream
   if (Cfg::smem > 48 * 1024)
     GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
   const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
+  GX_TIMED("fft_rows_r2c", st);
   kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N));
   count_launch();
   GX_LAUNCH_CHECK();
@@ -224,6 +227,7 @@ template <typename T, int N> int launch_rows_c2r(T *data, long nrows, T scale, c
   if (Cfg::smem > 48 * 1024)
     GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
   const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
+  GX_TIMED("fft_rows_c2r", st);
   kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, nrows, scale, twiddle_table<T>(N / 2),
                                                         twiddle_table<T>(N));
   count_launch();

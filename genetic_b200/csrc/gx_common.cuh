@@ -50,6 +50,16 @@ GX_HD bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long) n; }
 
+// Optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py for the
+// roofline line: gx_timing_enable(1); ...; gx_timing_report(). Off by default (no events recorded).
+struct TimedScope {
+  int idx;
+  cudaStream_t st;
+  TimedScope(const char *name, cudaStream_t s);
+  ~TimedScope();
+};
+#define GX_TIMED(name, stream) ::gx::TimedScope _gx_timed_scope(name, stream)
+
 // field geometry: padded half-complex layout, N x N x (N/2+1) complex == N x N x (N+2) reals
 struct Geo {
   int n;        // grid side

@@ -37,6 +37,7 @@ static int emit_t(const void *psi, int n, int axis, double dx, double lower, dou
   if (count <= 0) return 0;
   long long blocks = (count + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
+  GX_TIMED("emit", st);
   emit_component_kernel<T, O><<<(unsigned) blocks, 256, 0, st>>>((const T *) psi, n, axis, (T) dx, (T) lower, (T) domain,
                                                                 (T) ratio, (O *) pos, (O *) vel, stride, id0, count);
   count_launch();

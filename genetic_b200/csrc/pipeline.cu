@@ -1,0 +1,83 @@
+// Whole unigrid path behind one C-ABI call: ICGenerator::done -> write (ic.hpp:1633-1648, 1275-1331)
+//   draw white noise -> [fix_power] -> delta_k = sqrt(C(k)) * noise -> psi_j = c2r(i k_j delta_k / k^2), j = x,y,z
+//   -> particles (pos = wrap(centroid + psi), vel = psi * ratio), streamed in x-slabs through a bounded staging
+//   buffer, optionally copied to HOST arrays (component-major: out[axis][particle id]).
+// The reference pulls particles one at a time through virtual evaluators into an mmapped file
+// (mapperiterator.hpp:151-156, tipsy.hpp:120-146); here a slab of a component is emitted per kernel and the
+// device->host copy of slab s overlaps the emit of slab s+1.
+#include "../../include/genetic_b200.h"
+#include "gx_common.cuh"
+#include <algorithm>
+
+extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field,
+                             void *stage, size_t stage_bytes, void *host_pos, void *host_vel,
+                             size_t host_capacity_particles, void *stream) {
+  using namespace gx;
+  if (!p || !spectrum || !delta_field || !psi_field || !stage) return fail("gx_unigrid_ic: null argument");
+  const int n = p->n, dt = p->dtype, odt = p->out_dtype;
+  cudaStream_t st = (cudaStream_t) stream;
+  int rc;
+  unsigned long long off = 0;
+  if ((rc = gx_noise_draw(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, stream))) return rc;
+  if (p->fix_power && (rc = gx_unit_variance(delta_field, n, dt, stream))) return rc;
+  if ((rc = gx_apply_transfer(delta_field, n, dt, p->grid_length, spectrum, 0.5, stream))) return rc;
+
+  const size_t osz = odt == GX_F64 ? 8 : 4;
+  const long long n3 = (long long) n * n * n, n2 = (long long) n * n;
+  // staging: two halves, each holding pos+vel of `slab` particles (whole x-planes)
+  long long planes = (long long) (stage_bytes / 2 / (2 * osz)) / n2;
+  if (planes < 1) return fail("gx_unigrid_ic: staging buffer smaller than one x-plane of pos+vel");
+  if (planes > n) planes = n;
+  const long long slab = planes * n2;
+  const bool to_host = host_pos != nullptr || host_vel != nullptr;
+  if (to_host && host_capacity_particles == 0) return fail("gx_unigrid_ic: host_capacity_particles == 0");
+  static cudaStream_t copy_stream = nullptr;
+  static cudaEvent_t ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  if (to_host && !copy_stream) {
+    GX_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_emit[i], cudaEventDisableTiming));
+      GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
+    }
+  }
+  bool copy_pending[2] = {false, false};
+  int buf = 0;
+  for (int axis = 0; axis < 3; ++axis) {
+    if ((rc = gx_zeldovich_offset(delta_field, psi_field, n, dt, p->grid_length, axis, stream))) return rc;
+    for (long long id0 = 0; id0 < n3; id0 += slab) {
+      const long long cnt = std::min(slab, n3 - id0);
+      char *half = (char *) stage + (size_t) buf * (stage_bytes / 2);
+      void *dpos = half, *dvel = half + (size_t) slab * osz;
+      if (to_host && copy_pending[buf]) GX_CUDA_CHECK(cudaStreamWaitEvent(st, ev_copy[buf], 0));
+      if ((rc = gx_emit_component(psi_field, n, dt, axis, p->cell_size, p->offset_lower[axis], p->domain_size,
+                                  p->vel_ratio, dpos, dvel, odt, 1, id0, cnt, stream)))
+        return rc;
+      if (to_host) {
+        GX_CUDA_CHECK(cudaEventRecord(ev_emit[buf], st));
+        GX_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_emit[buf], 0));
+        // component-major host arrays; a capacity below n^3 makes the host side a ring (the consumer is a writer thread)
+        const size_t cap = host_capacity_particles;
+        const size_t hoff = (size_t) (((unsigned long long) axis * (unsigned long long) n3 + (unsigned long long) id0) % (3ull * cap));
+        const size_t room = 3 * cap - hoff;
+        const size_t c1 = std::min<size_t>((size_t) cnt, room);
+        if (host_pos) {
+          GX_CUDA_CHECK(cudaMemcpyAsync((char *) host_pos + hoff * osz, dpos, c1 * osz, cudaMemcpyDeviceToHost, copy_stream));
+          if (c1 < (size_t) cnt)
+            GX_CUDA_CHECK(cudaMemcpyAsync(host_pos, (char *) dpos + c1 * osz, ((size_t) cnt - c1) * osz, cudaMemcpyDeviceToHost, copy_stream));
+        }
+        if (host_vel) {
+          GX_CUDA_CHECK(cudaMemcpyAsync((char *) host_vel + hoff * osz, dvel, c1 * osz, cudaMemcpyDeviceToHost, copy_stream));
+          if (c1 < (size_t) cnt)
+            GX_CUDA_CHECK(cudaMemcpyAsync(host_vel, (char *) dvel + c1 * osz, ((size_t) cnt - c1) * osz, cudaMemcpyDeviceToHost, copy_stream));
+        }
+        GX_CUDA_CHECK(cudaEventRecord(ev_copy[buf], copy_stream));
+        copy_pending[buf] = true;
+      }
+      buf ^= 1;
+    }
+  }
+  if (to_host) {
+    GX_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+  }
+  return 0;
+}

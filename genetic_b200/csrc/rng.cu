@@ -422,9 +422,14 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   P.streams = d_streams; P.chunk_stream = d_chunk_stream; P.n_chunks = n0; P.jump = g_jump; P.fn = d_fn[0];
   P.scan = d_st[0]; P.stream_end = d_end; P.tails = d_tails; P.tail_count = d_tail_count; P.tail_capacity = tail_cap;
   const int grid = (n0 + kThreads - 1) / kThreads;
-  rng_chunk_kernel<0, T><<<grid, kThreads, 0, cs>>>(P, dest);
+  {
+    GX_TIMED("rng_pass_a", cs);
+    rng_chunk_kernel<0, T><<<grid, kThreads, 0, cs>>>(P, dest);
+  }
   count_launch();
   GX_LAUNCH_CHECK();
+  {
+  GX_TIMED("rng_scan", cs);
   for (int l = 1; l < nl; ++l) {
     scan_up_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_fn[l], level_n[l]);
     count_launch();
@@ -435,8 +440,12 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     scan_down_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_st[l], level_n[l], d_st[l - 1]);
     count_launch();
   }
+  }
   GX_LAUNCH_CHECK();
-  rng_chunk_kernel<1, T><<<grid, kThreads, 0, cs>>>(P, dest);
+  {
+    GX_TIMED("rng_pass_b", cs);
+    rng_chunk_kernel<1, T><<<grid, kThreads, 0, cs>>>(P, dest);
+  }
   count_launch();
   GX_LAUNCH_CHECK();
 

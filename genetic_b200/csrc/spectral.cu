@@ -34,6 +34,7 @@ template <typename T> __global__ void mirror_kernel(cplx<T> *f, int n, int nc) {
 template <typename T> int mirror(T *field, int n, cudaStream_t st) {
   const int nc = n / 2 + 1;
   const int total = 2 * (n / 2 + 1) * n;
+  GX_TIMED("mirror", st);
   mirror_kernel<T><<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<cplx<T> *>(field), n, nc);
   count_launch();
   GX_LAUNCH_CHECK();
@@ -190,7 +191,7 @@ template <typename T> static int covariance_field_t(void *out, int n, double L, 
   CovarianceF<T> f;
   f.sp = gx_spectrum_device_view(s);
   f.out = (cplx<T> *) out; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n);
-  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double));
+  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double), "covariance_field");
 }
 
 template <typename T>
@@ -198,7 +199,7 @@ static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, 
   ApplyTransferF<T> f;
   f.sp = gx_spectrum_device_view(s);
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n); f.power = power;
-  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double));
+  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double), "apply_transfer");
 }
 
 template <typename T> static int apply_transfer_field_t(void *field, const void *cov, int n, double power, cudaStream_t st) {
@@ -226,7 +227,7 @@ template <typename T>
 static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, int axis, cudaStream_t st) {
   ZeldovichF<T> f;
   f.delta = (const cplx<T> *) delta; f.psi = (cplx<T> *) psi; f.n = n; f.axis = axis; f.kmin = kmin_of<T>(L);
-  return launch_slot_sweep(n, f, st);
+  return launch_slot_sweep(n, f, st, 0, "zeldovich_op");
 }
 
 extern "C" {

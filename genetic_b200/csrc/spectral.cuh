@@ -101,7 +101,8 @@ template <class F> __global__ void __launch_bounds__(256) slot_sweep_kernel(int 
   }
 }
 
-template <class F> int launch_slot_sweep(int n, F f, cudaStream_t st, size_t smem = 0) {
+template <class F> int launch_slot_sweep(int n, F f, cudaStream_t st, size_t smem = 0, const char *name = "slot_sweep") {
+  GX_TIMED(name, st);
   const int nc = n / 2 + 1;
   const int plane = n * nc;
   int bx = (plane + 255) / 256;

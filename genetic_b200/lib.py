@@ -14,6 +14,13 @@ class GxError(RuntimeError):
     pass
 
 
+class IcParams(C.Structure):
+    _fields_ = [("n", C.c_int), ("dtype", C.c_int), ("out_dtype", C.c_int), ("noise_mode", C.c_int),
+                ("reverse_order", C.c_int), ("fix_power", C.c_int), ("seed", C.c_ulong), ("grid_length", C.c_double),
+                ("cell_size", C.c_double), ("domain_size", C.c_double), ("offset_lower", C.c_double * 3),
+                ("vel_ratio", C.c_double)]
+
+
 class FilterFactor(C.Structure):
     _fields_ = [("kind", C.c_int), ("kcut", C.c_double), ("temperature", C.c_double), ("power", C.c_int)]
 
@@ -68,8 +75,11 @@ PROTOTYPES = {
     "gx_zeldovich_fourier": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_zeldovich_offset": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_emit_component": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, vp, ci, cl, cll, cll, vp]),
+    "gx_unigrid_ic": (ci, [P(IcParams), vp, vp, vp, vp, csz, vp, vp, csz, vp]),
+    "gx_timing_enable": (ci, [ci]),
+    "gx_timing_report": (ci, [C.c_char_p, ci]),
 }
-NOT_STATUS = {"gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_spectrum_amplitude",
+NOT_STATUS = {"gx_timing_report", "gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_spectrum_amplitude",
               "gx_spectrum_eval"}
 
 _lib = None

@@ -147,6 +147,34 @@ int gx_emit_component(const void *psi, int n, int dtype, int axis, double cell_s
                       double domain_size, double vel_ratio, void *out_pos, void *out_vel, int out_dtype,
                       long stride_elems, long long id0, long long count, void *stream);
 
+/* ---- whole unigrid path (ICGenerator::done -> write, ic.hpp:1633-1648,1275-1331) ------------------------------ */
+typedef struct {
+  int n;                   /* base_grid n */
+  int dtype;               /* GX_F64, or GX_F32 for the reference's -f mode */
+  int out_dtype;           /* particle output type (the reference's writers store float32) */
+  int noise_mode;          /* GX_NOISE_* */
+  int reverse_order;       /* seedfourier_reverse */
+  int fix_power;           /* fix_power */
+  unsigned long seed;
+  double grid_length;      /* Grid::thisGridSize */
+  double cell_size;        /* Grid::cellSize */
+  double domain_size;      /* Grid::periodicDomainSize */
+  double offset_lower[3];  /* Grid::offsetLower */
+  double vel_ratio;        /* zeldovichVelocityToOffsetRatio, parameters.hpp:83-106 */
+} gx_ic_params;
+/* delta_field, psi_field: two device fields of gx_field_bytes(n,dtype). stage: device buffer of stage_bytes used as
+   two halves, each holding pos+vel of a whole number of x-planes of one component.
+   host_pos/host_vel (may be NULL: results stay in the staging buffer, nothing is copied): component-major arrays
+   out[axis][id] of out_dtype; if host_capacity_particles < n^3 they are used as a ring of 3*capacity elements.
+   Synchronous with respect to the device->host copies; kernels run on `stream`. On return delta_field holds
+   delta_k and psi_field the z displacement in real space. */
+int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field, void *stage,
+                  size_t stage_bytes, void *host_pos, void *host_vel, size_t host_capacity_particles, void *stream);
+
+/* ---- per-kernel-class device timing for the roofline report (off by default) ---------------------------------- */
+int gx_timing_enable(int on);
+int gx_timing_report(char *buf, int buflen); /* lines "name count total_ms" */
+
 #ifdef __cplusplus
 }
 #endif
