@@ -76,18 +76,21 @@ template <typename T, int N> static int fft3d_n(T *data, int dir, cudaStream_t s
   using C = cplx<T>;
   const T scale = (T) (1.0 / pow((double) N, 1.5));
   C *cdata = reinterpret_cast<C *>(data);
+  const int nc = N / 2 + 1;
   if (dir < 0) {
     int rc = launch_rows_r2c<T, N>(data, (long) N * N, st);
     if (rc) return rc;
-    rc = launch_cols<T, N, -1, PassY>(cdata, cdata, N, OpIdentity<T>(), OpIdentity<T>(), st);
+    rc = launch_cols<T, N, -1, PassY>(cdata, cdata, N, N, nc, OpIdentity<T>(), OpIdentity<T>(), st);
     if (rc) return rc;
-    return launch_cols<T, N, -1, PassX>(cdata, cdata, N, OpIdentity<T>(), OpScale<T>(scale), st);
+    return launch_cols<T, N, -1, PassX>(cdata, cdata, N, N, nc, OpIdentity<T>(), OpScale<T>(scale), st);
   } else {
-    int rc = launch_cols<T, N, 1, PassX>(cdata, cdata, N, OpIdentity<T>(), OpIdentity<T>(), st);
+    int rc = launch_cols<T, N, 1, PassX>(cdata, cdata, N, N, nc, OpIdentity<T>(), OpIdentity<T>(), st);
     if (rc) return rc;
-    rc = launch_cols<T, N, 1, PassY>(cdata, cdata, N, OpIdentity<T>(), OpIdentity<T>(), st);
+    rc = launch_cols<T, N, 1, PassY>(cdata, cdata, N, N, nc, OpIdentity<T>(), OpIdentity<T>(), st);
     if (rc) return rc;
-    return launch_rows_c2r<T, N>(data, (long) N * N, scale, st);
+    StoreRealScaled<T> store;
+    store.data = data; store.scale = scale; store.n = N;
+    return launch_rows_c2r<T, N>(data, 0, (long) N * N, store, st);
   }
 }
 

@@ -1,8 +1,27 @@
-// Pass kernels of the 3-D FFT (templates; instantiated from fft.cu and the fused Zeldovich path).
+// Pass kernels of the 3-D FFT (templates; instantiated from fft.cu and the fused Zeldovich path in pipeline.cu).
+//
+// Column passes (the two strided axes) -- fft_cols_kernel
+//   A tile is TC adjacent columns (TC * sizeof(complex) = 256 contiguous bytes) x the whole line of N points.
+//   profiles/r1_segbench2048.txt: with a 33 MB line stride, 32-byte segments reach 1.5 TB/s, 64 B 3.0 TB/s,
+//   128 B 5.7 TB/s and 256 B 6.5 TB/s, but only when several 64 KB tiles are resident per SM. A 2048-point f64
+//   line of 16 columns is 512 KB, so the line is split over a thread-block CLUSTER of CL CTAs, decimation in time:
+//   CTA q loads the rows j = q + CL j1 (R = N / CL of them; each row is its own 256-byte segment, so the stride is
+//   free), transforms them locally and leaves W_N^(q k1) Y_q[k1] in its shared memory; after one cluster barrier
+//   every CTA pulls the positions k1 in its 1/CL slice from all CL CTAs through distributed shared memory, does the
+//   final radix-CL butterflies and stores X[k1 + R k2] straight to HBM. DSMEM moves (CL-1)/CL of a tile once
+//   (B300_MICROARCH: ~20 B/cycle/SM, so it must stay below the HBM time of the tile). Shared memory is
+//   [row][column] with the column fastest: every warp access is a run of whole 256-byte rows -- no padding, no
+//   bank conflicts.
+//
+// Row passes (z axis, contiguous) -- fft_rows_r2c_kernel / fft_rows_c2r_kernel
+//   r2c and c2r through a half-length complex transform with the split/merge step done in shared memory; one
+//   buffer per row; the c2r results leave through a store functor so the particle emit can be fused into it.
 #pragma once
 #include <vector>
 #include <cmath>
 #include <type_traits>
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include "gx_common.cuh"
 #include "fft_core.cuh"
 
@@ -14,6 +33,7 @@ template <typename T> const cplx<T> *twiddle_table(int n);
 template <typename T> int fft3d(T *data, int n, int dir, cudaStream_t st);
 
 // ---- element operators fused into the load or store side of a column pass -----------------------
+// Called as op(value, i0, i1, i2) with the storage indices of the element in the [n0][n1][nc] array.
 template <typename T> struct OpIdentity {
   __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int, int) const { return v; }
 };
@@ -24,87 +44,259 @@ template <typename T> struct OpScale {
 };
 
 // ---- which axis a column pass transforms ---------------------------------------------------------
-// PassY: batch = ix, line index = iy, column = iz            (line stride nc,   batch stride n*nc)
-// PassX: one batch, line index = ix, column = iy*nc + iz     (line stride n*nc)
+// PassY: batch = i0, line index = i1, column = i2            (line stride nc,   batch stride n1*nc)
+// PassX: one batch, line index = i0, column = i1*nc + i2     (line stride n1*nc)
 struct PassY {};
 struct PassX {};
 
-template <typename T, int N> struct ColsCfg {
-  using B = BlockFFT<T, N, -1>;
-  static constexpr int P = B::P;
-  static constexpr int minTC = (sizeof(T) == 8) ? (N >= 2048 ? 2 : 4) : (N >= 2048 ? 4 : 8);
-  static constexpr int byThreads = 256 / P;
-  static constexpr int TC = byThreads > minTC ? byThreads : minTC;
-  static constexpr int threads = TC * P;
-  static constexpr int pitch = line_pitch<T>(N);
-  static constexpr size_t smem = (size_t) TC * pitch * sizeof(cplx<T>);
+struct ColGeo {
+  long ncols;          // columns per batch
+  long line_stride;    // elements between consecutive line positions
+  long batch_stride;   // elements between batches
+  int tiles_per_batch;
+  int nc;              // fastest extent (n/2+1)
 };
 
-// One CTA transforms TC adjacent columns (contiguous in memory) of length N.
-template <typename T, int N, int DIR, class Pass, class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(ColsCfg<T, N>::threads)
-fft_cols_kernel(const cplx<T> *__restrict__ src, cplx<T> *__restrict__ dst, int n, int nc, long ncols,
-                long line_stride, long batch_stride, int tiles_per_batch, const cplx<T> *__restrict__ tw,
-                LoadOp lop, StoreOp sop) {
+// default cluster size / tile width / residency target per (type, N); see profiles/ for the variant sweep
+template <typename T, int N> struct ColsPlan {
+  // 128-byte row segments and 256 rows per CTA: 32 KB tiles, double buffered, 3 CTAs per SM; 4096-point lines keep the
+  // portable cluster size 8 with 512 rows per CTA
+  static constexpr int TC = 128 / (int) sizeof(cplx<T>);
+  static constexpr int Rmax = (N >= 4096) ? 512 : 256;
+  static constexpr int CL = (N > Rmax) ? N / Rmax : 1;  // 512 -> 2, 1024 -> 4, 2048 -> 8, 4096 -> 8
+  static constexpr int MINB = (N >= 4096) ? 1 : 3;      // register cap so that three 64 KB CTAs fit an SM
+};
+
+template <typename T, int N, int CL_, int TC_> struct ColsCfg {
+  static constexpr int TC = TC_;
+  static constexpr int CL = CL_;
+  static constexpr int R = N / CL;
+  using B = BlockFFT<T, R, -1, TC>;
+  static constexpr int E = B::E, P = B::P;
+  static constexpr int threads = P * TC;
+  static constexpr int IPT = (CL > 1) ? E / CL : 1;  // cross-cluster butterflies per thread
+  static_assert(CL == 1 || (E % CL == 0 && E >= CL), "first local radix must be a multiple of the cluster size");
+  static_assert(threads <= 1024, "too many threads per CTA");
+  static constexpr size_t tile_bytes = (size_t) R * TC * sizeof(cplx<T>);
+  // two tile buffers + the local twiddles W_R^j and (clusters) this CTA's cross twiddles W_N^(q j)
+  static constexpr size_t smem = 2 * tile_bytes + (size_t) (CL > 1 ? 2 : 1) * R * sizeof(cplx<T>);
+};
+
+__device__ __forceinline__ unsigned smem_addr_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+// one element global -> shared without passing through registers (LDGSTS); !pred zero-fills
+template <typename C> __device__ __forceinline__ void cp_async_elem(C *sdst, const C *gsrc, bool pred) {
+  if constexpr (sizeof(C) == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr_u32(sdst)), "l"(gsrc), "r"(pred ? 16 : 0)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr_u32(sdst)), "l"(gsrc), "r"(pred ? 8 : 0)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NG> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NG) : "memory"); }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// relaxed arrive that cannot be issued before `dep` has been computed (i.e. before the loads feeding it returned)
+__device__ __forceinline__ void cluster_arrive_relaxed_after(double dep) {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::"d"(dep) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed_after(float dep) {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::"f"(dep) : "memory");
+}
+
+// Persistent: cluster `cid` of `nclusters` walks the tiles cid, cid + nclusters, ...; the loads of the next tile are in
+// flight (cp.async into the other half of shared memory) while the current one is transformed.
+template <typename T, int N, int CL, int TC, int MINB, int DIR, class Pass, class LoadOp, class StoreOp>
+__global__ void __launch_bounds__(ColsCfg<T, N, CL, TC>::threads, MINB)
+fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int nclusters, const cplx<T> *__restrict__ twR,
+                const cplx<T> *__restrict__ twN, LoadOp lop, StoreOp sop) {
   using C = cplx<T>;
-  using B = BlockFFT<T, N, DIR>;
-  using Cfg = ColsCfg<T, N>;
-  constexpr int TC = Cfg::TC, E = B::E, P = B::P;
+  using Cfg = ColsCfg<T, N, CL, TC>;
+  using B = BlockFFT<T, Cfg::R, DIR, TC>;
+  constexpr int R = Cfg::R, E = B::E, P = B::P;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
 
   const int c = threadIdx.x % TC;
   const int t = threadIdx.x / TC;
-  const long tile = blockIdx.x;
-  const int batch = (int) (tile / tiles_per_batch);
-  const long col = (tile % tiles_per_batch) * TC + c;
-  const bool active = col < ncols;
-  int cx, cy, cz;  // slot coordinates that do not depend on the line index
-  if (std::is_same<Pass, PassY>::value) { cx = batch; cy = 0; cz = (int) col; }
-  else { cx = 0; cy = (int) (col / nc); cz = (int) (col % nc); }
+  int q = 0;
+  if constexpr (CL > 1) q = (int) cooperative_groups::this_cluster().block_rank();
+  const long cid = blockIdx.x / CL;
+  C *twl = smem + 2 * (R * TC);  // W_R^j
+  C *twc = twl + R;              // W_N^(q j)
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    twl[i] = twR[i];
+    if constexpr (CL > 1) twc[i] = twN[q * i];
+  }
+  __syncthreads();
 
-  const long base = (long) batch * batch_stride + col;
-  C v[E];
+  auto issue = [&](long tile, C *buf) {
+    const int batch = (int) (tile / g.tiles_per_batch);
+    const long col = (tile % g.tiles_per_batch) * TC + c;
+    const bool active = col < g.ncols;
+    const C *p = src + ((long) batch * g.batch_stride + (active ? col : 0));
 #pragma unroll
-  for (int i = 0; i < E; ++i) {
-    const int row = t + i * P;
-    if (active) {
-      C x = src[base + (long) row * line_stride];
-      v[i] = std::is_same<Pass, PassY>::value ? lop(x, cx, row, cz) : lop(x, row, cy, cz);
+    for (int i = 0; i < E; ++i) {
+      const int row = (CL > 1) ? q + CL * (t + i * P) : t + i * P;
+      cp_async_elem<C>(buf + (t + i * P) * TC + c, p + (long) row * g.line_stride, active);
+    }
+    cp_async_commit();
+  };
+
+  long tile = cid;
+  if (tile < ntiles) issue(tile, smem);
+  for (int it = 0; tile < ntiles; tile += nclusters, ++it) {
+    C *buf = smem + (size_t) (it & 1) * (R * TC);
+    const long next = tile + nclusters;
+    if (next < ntiles) { issue(next, smem + (size_t) ((it + 1) & 1) * (R * TC)); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+
+    const int batch = (int) (tile / g.tiles_per_batch);
+    const long col = (tile % g.tiles_per_batch) * TC + c;
+    const bool active = col < g.ncols;
+    int c1 = 0, c2;  // storage indices that do not depend on the line position
+    if (std::is_same<Pass, PassY>::value) { c2 = (int) col; }
+    else { c1 = (int) (col / g.nc); c2 = (int) (col - (long) c1 * g.nc); }
+    const long base = (long) batch * g.batch_stride + col;
+    auto load_op = [&](C x, int row) -> C {
+      return std::is_same<Pass, PassY>::value ? lop(x, batch, row, c2) : lop(x, row, c1, c2);
+    };
+    auto store = [&](int row, C val) {
+      if (active) {
+        C y = std::is_same<Pass, PassY>::value ? sop(val, batch, row, c2) : sop(val, row, c1, c2);
+        dst[base + (long) row * g.line_stride] = y;
+      }
+    };
+
+    // every thread consumes exactly the elements it copied itself, and stage 0 rewrites the same positions:
+    // no barrier between the copy and the first butterflies
+    C v[E];
+    if constexpr (CL == 1) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) v[i] = active ? load_op(buf[(t + i * P) * TC + c], t + i * P) : mk<T>(0, 0);
+      B::run(v, t, buf + c, twl, [&](int k, C val) { store(k, val); });
+      if constexpr (B::S > 1) __syncthreads();  // the buffer is the target of the copy issued two tiles later
     } else {
-      v[i] = mk<T>(0, 0);
+      // decimation in time across the cluster: CTA q owns the rows j = q + CL j1, transforms them locally and leaves
+      // W_N^(q k1) Y_q[k1] in shared memory
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const int row = q + CL * (t + i * P);
+        v[i] = active ? load_op(buf[(t + i * P) * TC + c], row) : mk<T>(0, 0);
+      }
+      B::run_synced_emit(v, t, buf + c, twl, [&](int k1, C val) {
+        buf[k1 * TC + c] = (q == 0) ? val : cmul(val, B::twiddle(twc, k1));
+      });
+      // A release-arrive would also wait for the cp.async prefetch of the next tile (it is a full memory barrier):
+      // the CTA barrier makes this CTA's shared-memory writes complete, then the cluster barrier is execution-only.
+      __syncthreads();
+      cluster_arrive_relaxed();
+      cluster_wait();
+      // final radix-CL stage: this CTA combines the positions k1 in [q R/CL, (q+1) R/CL) of all CL sub-transforms
+      // (one pull through distributed shared memory) and stores X[k1 + R k2], k2 = 0..CL-1
+      constexpr int IPT = Cfg::IPT;
+      C y[IPT][CL];
+      cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+#pragma unroll
+      for (int m = 0; m < IPT; ++m) {
+        const int k1 = q * (R / CL) + t + m * P;
+#pragma unroll
+        for (int q2 = 0; q2 < CL; ++q2) y[m][q2] = cluster.map_shared_rank(buf, q2)[k1 * TC + c];
+      }
+      T dep = (T) 0;
+#pragma unroll
+      for (int m = 0; m < IPT; ++m) {
+        butterfly<CL, DIR, T>(y[m]);
+        dep += y[m][0].x;  // output 0 is the sum of all CL pulled values
+      }
+      // Nobody may overwrite (next prefetch) or retire (exit) a buffer its peers are still pulling from: arrive only
+      // once this thread's pulls have returned -- enforced by the data dependence, not by a memory barrier -- and
+      // defer the wait past the stores.
+      cluster_arrive_relaxed_after(dep);
+#pragma unroll
+      for (int m = 0; m < IPT; ++m) {
+        const int k1 = q * (R / CL) + t + m * P;
+#pragma unroll
+        for (int k2 = 0; k2 < CL; ++k2) store(k1 + R * k2, y[m][k2]);
+      }
+      cluster_wait();
     }
   }
-  C *line = smem + c * Cfg::pitch;
-  B::run(v, t, line, tw, [&](int k, C val) {
-    if (active) {
-      C y = std::is_same<Pass, PassY>::value ? sop(val, cx, k, cz) : sop(val, k, cy, cz);
-      dst[base + (long) k * line_stride] = y;
-    }
-  });
 }
 
-template <typename T, int N, int DIR, class Pass, class LoadOp, class StoreOp>
-int launch_cols(const cplx<T> *src, cplx<T> *dst, int n, LoadOp lop, StoreOp sop, cudaStream_t st) {
-  using Cfg = ColsCfg<T, N>;
-  const int nc = n / 2 + 1;
-  long ncols, line_stride, batch_stride;
-  int nbatch;
-  if (std::is_same<Pass, PassY>::value) { ncols = nc; line_stride = nc; batch_stride = (long) n * nc; nbatch = n; }
-  else { ncols = (long) n * nc; line_stride = (long) n * nc; batch_stride = 0; nbatch = 1; }
-  const int tiles_per_batch = (int) ((ncols + Cfg::TC - 1) / Cfg::TC);
-  const long grid = (long) tiles_per_batch * nbatch;
-  auto kern = fft_cols_kernel<T, N, DIR, Pass, LoadOp, StoreOp>;
-  if (Cfg::smem > 48 * 1024) {
-    GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
+template <typename T, int N, int CL, int TC, int MINB, int DIR, class Pass, class LoadOp, class StoreOp>
+int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, LoadOp lop, StoreOp sop, cudaStream_t st) {
+  using Cfg = ColsCfg<T, N, CL, TC>;
+  g.tiles_per_batch = (int) ((g.ncols + TC - 1) / TC);
+  const long ntiles = (long) g.tiles_per_batch * nbatch;
+  if (ntiles <= 0) return 0;
+  auto kern = fft_cols_kernel<T, N, CL, TC, MINB, DIR, Pass, LoadOp, StoreOp>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(Cfg::threads);
+  cfg.dynamicSmemBytes = Cfg::smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // how many clusters can be resident at once (queried once per kernel and device)
+  static int max_clusters = 0, max_clusters_dev = -1;
+  int dev = 0;
+  GX_CUDA_CHECK(cudaGetDevice(&dev));
+  if (max_clusters_dev != dev) {
+    if (Cfg::smem > 48 * 1024)
+      GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
+    // ask for the largest shared-memory carveout: residency is decided by how many double-buffered tiles fit
+    GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (CL > 8) GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (CL > 1) {
+      cfg.gridDim = dim3(CL * 1024);
+      GX_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    } else {
+      int per_sm = 0, sms = 0;
+      GX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::threads, Cfg::smem));
+      GX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      max_clusters = per_sm * sms;
+    }
+    if (max_clusters < 1) return fail("fft_cols: kernel cannot be resident (cluster occupancy query returned 0)");
+    max_clusters_dev = dev;
+    if (getenv("GX_DEBUG"))
+      fprintf(stderr, "[gx] fft_cols<N=%d,CL=%d,TC=%d,%zu-byte elems>: %d resident clusters, %zu KB smem/CTA, %d threads\n", N, CL,
+              TC, sizeof(cplx<T>), max_clusters, Cfg::smem / 1024, Cfg::threads);
   }
+  const int nclusters = (int) (ntiles < max_clusters ? ntiles : max_clusters);
+  cfg.gridDim = dim3((unsigned) nclusters * CL);
   const char *tname = std::is_same<Pass, PassY>::value ? "fft_cols_y" : "fft_cols_x";
   GX_TIMED(tname, st);
-  kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(src, dst, n, nc, ncols, line_stride, batch_stride,
-                                                        tiles_per_batch, twiddle_table<T>(N), lop, sop);
+  const cplx<T> *twR = twiddle_table<T>(Cfg::R), *twN = twiddle_table<T>(N);
+  GX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, src, dst, g, ntiles, nclusters, twR, twN, lop, sop));
   count_launch();
   GX_LAUNCH_CHECK();
   return 0;
+}
+
+template <class Pass> inline ColGeo make_col_geo(int n0, int n1, int nc, int &nbatch) {
+  ColGeo g;
+  g.nc = nc;
+  g.tiles_per_batch = 0;
+  if (std::is_same<Pass, PassY>::value) { g.ncols = nc; g.line_stride = nc; g.batch_stride = (long) n1 * nc; nbatch = n0; }
+  else { g.ncols = (long) n1 * nc; g.line_stride = (long) n1 * nc; g.batch_stride = 0; nbatch = 1; }
+  return g;
+}
+
+// Column pass over an [n0][n1][nc] array: PassX transforms i0 (n0 == N), PassY transforms i1 (n1 == N).
+template <typename T, int N, int DIR, class Pass, class LoadOp, class StoreOp>
+int launch_cols(const cplx<T> *src, cplx<T> *dst, int n0, int n1, int nc, LoadOp lop, StoreOp sop, cudaStream_t st) {
+  using PL = ColsPlan<T, N>;
+  int nbatch;
+  ColGeo g = make_col_geo<Pass>(n0, n1, nc, nbatch);
+  return launch_cols_cfg<T, N, PL::CL, PL::TC, PL::MINB, DIR, Pass, LoadOp, StoreOp>(src, dst, g, nbatch, lop, sop, st);
 }
 
 // ---- row passes (z axis, contiguous): r2c and c2r through a half-length complex FFT ---------------
@@ -112,11 +304,10 @@ template <typename T, int N> struct RowsCfg {
   static constexpr int M = N / 2;
   using B = BlockFFT<T, M, -1>;
   static constexpr int P = B::P;
-  static constexpr int pitch = line_pitch<T>(M);
-  static constexpr int zpitch = M + 2;
-  static constexpr size_t per_row = (size_t) (pitch + zpitch) * sizeof(cplx<T>);
+  static constexpr int pitch = line_pitch<T>(M) + 1;  // >= M + 1 entries (the c2r input has M + 1)
+  static constexpr size_t per_row = (size_t) pitch * sizeof(cplx<T>);
   static constexpr int byThreads = (256 / P) > 0 ? (256 / P) : 1;
-  static constexpr int bySmem = (int) ((96 * 1024) / per_row) > 0 ? (int) ((96 * 1024) / per_row) : 1;
+  static constexpr int bySmem = (int) ((72 * 1024) / per_row) > 0 ? (int) ((72 * 1024) / per_row) : 1;
   static constexpr int LR = byThreads < bySmem ? byThreads : bySmem;
   static constexpr int threads = LR * P;
   static constexpr size_t smem = (size_t) LR * per_row;
@@ -126,8 +317,7 @@ template <typename T, int N> struct RowsCfg {
 //   X[k] = 1/2 (Z[k] + conj Z[M-k]) - i/2 W_N^k (Z[k] - conj Z[M-k]),  k = 0..M,  Z[M] == Z[0]
 template <typename T, int N>
 __global__ void __launch_bounds__(RowsCfg<T, N>::threads)
-fft_rows_r2c_kernel(T *__restrict__ data, long nrows, const cplx<T> *__restrict__ twM,
-                    const cplx<T> *__restrict__ twN) {
+fft_rows_r2c_kernel(T *data, long nrows, const cplx<T> *__restrict__ twM, const cplx<T> *__restrict__ twN) {
   using C = cplx<T>;
   using Cfg = RowsCfg<T, N>;
   using B = BlockFFT<T, Cfg::M, -1>;
@@ -138,20 +328,20 @@ fft_rows_r2c_kernel(T *__restrict__ data, long nrows, const cplx<T> *__restrict_
   const long row = (long) blockIdx.x * Cfg::LR + l;
   const bool active = row < nrows;
   C *rowp = reinterpret_cast<C *>(data + row * (long) (N + 2));
-  C *line = smem + (size_t) l * (Cfg::pitch + Cfg::zpitch);
-  C *zbuf = line + Cfg::pitch;
+  C *line = smem + (size_t) l * Cfg::pitch;
   C v[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) v[i] = active ? rowp[t + i * P] : mk<T>(0, 0);
-  B::run(v, t, line, twM, [&](int k, C val) { zbuf[k] = val; });
+  // the spectrum Z lands in natural order in the same buffer the stages exchanged through
+  B::run_synced_emit(v, t, line, twM, [&](int k, C val) { line[k] = val; });
   __syncthreads();
   if (!active) return;
   const T half = (T) 0.5;
 #pragma unroll
   for (int i = 0; i < E; ++i) {
     const int k = t + i * P;
-    const C zk = zbuf[k];
-    const C zm = cconj(zbuf[(M - k) & (M - 1)]);
+    const C zk = line[k];
+    const C zm = cconj(line[(M - k) & (M - 1)]);
     const C xe = mk<T>((zk.x + zm.x) * half, (zk.y + zm.y) * half);
     const C d = csub(zk, zm);
     const C xo = mk<T>(d.y * half, -d.x * half);  // -i/2 * d
@@ -161,13 +351,23 @@ fft_rows_r2c_kernel(T *__restrict__ data, long nrows, const cplx<T> *__restrict_
   }
 }
 
-// Inverse: N/2+1 complex -> N reals in place (unnormalised c2r, times `scale`).
+// c2r store functors: called with the row index, the complex index k and z = (x[2k], x[2k+1]) unscaled.
+template <typename T> struct StoreRealScaled {
+  T *data;
+  T scale;
+  int n;
+  __device__ __forceinline__ void operator()(long row, int k, cplx<T> z) const {
+    reinterpret_cast<cplx<T> *>(data + row * (long) (n + 2))[k] = mk<T>(z.x * scale, z.y * scale);
+  }
+};
+
+// Inverse: N/2+1 complex -> N reals (unnormalised c2r; the store functor scales).
 //   Zt[k] = (X[k] + conj X[M-k]) + i W_N^{-k} (X[k] - conj X[M-k]),  z = IFFT_M(Zt),  x[2m] = Re z[m], x[2m+1] = Im z[m]
 // The imaginary parts of X[0] and X[M] are ignored, as FFTW's c2r does.
-template <typename T, int N>
+template <typename T, int N, class Store>
 __global__ void __launch_bounds__(RowsCfg<T, N>::threads)
-fft_rows_c2r_kernel(T *__restrict__ data, long nrows, T scale, const cplx<T> *__restrict__ twM,
-                    const cplx<T> *__restrict__ twN) {
+fft_rows_c2r_kernel(const T *data, long row0, long nrows, const cplx<T> *__restrict__ twM,
+                    const cplx<T> *__restrict__ twN, Store store) {
   using C = cplx<T>;
   using Cfg = RowsCfg<T, N>;
   using B = BlockFFT<T, Cfg::M, 1>;
@@ -175,21 +375,20 @@ fft_rows_c2r_kernel(T *__restrict__ data, long nrows, T scale, const cplx<T> *__
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
   const int l = threadIdx.x / P, t = threadIdx.x % P;
-  const long row = (long) blockIdx.x * Cfg::LR + l;
-  const bool active = row < nrows;
-  C *rowp = reinterpret_cast<C *>(data + row * (long) (N + 2));
-  C *line = smem + (size_t) l * (Cfg::pitch + Cfg::zpitch);
-  C *zbuf = line + Cfg::pitch;
+  const long row = row0 + (long) blockIdx.x * Cfg::LR + l;
+  const bool active = row < row0 + nrows;
+  const C *rowp = reinterpret_cast<const C *>(data + row * (long) (N + 2));
+  C *line = smem + (size_t) l * Cfg::pitch;
 #pragma unroll
-  for (int i = 0; i < E; ++i) zbuf[t + i * P] = active ? rowp[t + i * P] : mk<T>(0, 0);
-  if (t == 0) zbuf[M] = active ? rowp[M] : mk<T>(0, 0);
+  for (int i = 0; i < E; ++i) line[t + i * P] = active ? rowp[t + i * P] : mk<T>(0, 0);
+  if (t == 0) line[M] = active ? rowp[M] : mk<T>(0, 0);
   __syncthreads();
   C v[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
     const int k = t + i * P;
-    C xk = zbuf[k];
-    C xm = cconj(zbuf[M - k]);
+    C xk = line[k];
+    C xm = cconj(line[M - k]);
     if (k == 0) { xk.y = 0; xm.y = 0; }
     const C s = cadd(xk, xm);
     const C d = csub(xk, xm);
@@ -197,15 +396,8 @@ fft_rows_c2r_kernel(T *__restrict__ data, long nrows, T scale, const cplx<T> *__
     const C wd = cmul(w, d);
     v[i] = mk<T>(s.x - wd.y, s.y + wd.x);  // s + i*wd
   }
-  __syncthreads();  // everyone has consumed zbuf before it is reused for the outputs
-  B::run(v, t, line, twM, [&](int k, C val) { zbuf[k] = val; });
-  __syncthreads();
-  if (!active) return;
-#pragma unroll
-  for (int i = 0; i < E; ++i) {
-    const C z = zbuf[t + i * P];
-    rowp[t + i * P] = mk<T>(z.x * scale, z.y * scale);
-  }
+  __syncthreads();  // everyone has consumed the inputs before the buffer is reused for the stage exchanges
+  B::run(v, t, line, twM, [&](int k, C val) { if (active) store(row, k, val); });
 }
 
 template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream_t st) {
@@ -214,6 +406,7 @@ template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream
   if (Cfg::smem > 48 * 1024)
     GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
   const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
+  if (grid <= 0) return 0;
   GX_TIMED("fft_rows_r2c", st);
   kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N));
   count_launch();
@@ -221,15 +414,18 @@ template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream
   return 0;
 }
 
-template <typename T, int N> int launch_rows_c2r(T *data, long nrows, T scale, cudaStream_t st) {
+// rows [row0, row0 + nrows) of `data` (pitch N+2 reals) -> store functor
+template <typename T, int N, class Store>
+int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStream_t st) {
   using Cfg = RowsCfg<T, N>;
-  auto kern = fft_rows_c2r_kernel<T, N>;
+  auto kern = fft_rows_c2r_kernel<T, N, Store>;
   if (Cfg::smem > 48 * 1024)
     GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
   const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
+  if (grid <= 0) return 0;
   GX_TIMED("fft_rows_c2r", st);
-  kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, nrows, scale, twiddle_table<T>(N / 2),
-                                                        twiddle_table<T>(N));
+  kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2),
+                                                        twiddle_table<T>(N), store);
   count_launch();
   GX_LAUNCH_CHECK();
   return 0;

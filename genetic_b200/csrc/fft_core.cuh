@@ -146,12 +146,17 @@ template <typename T> GX_HD constexpr int skew_of() { return 128 / (int) sizeof(
 template <typename T> GX_HD int sidx(int p) { return p + p / skew_of<T>(); }
 template <typename T> GX_HD constexpr int line_pitch(int nc) { return nc + nc / skew_of<T>() + 1; }
 
-template <typename T, int NC, int DIR> struct BlockFFT {
+// LS = 0: the line is contiguous in shared memory with the bank skew above (row passes).
+// LS > 0: element p of the line lives at line[p * LS] (column passes: LS adjacent columns are interleaved,
+//         so a warp touches LS * sizeof(C) contiguous bytes per line position and no skew is needed).
+template <typename T, int NC, int DIR, int LS = 0> struct BlockFFT {
   using C = cplx<T>;
   using PL = Plan<NC>;
   static constexpr int S = PL::S;
   static constexpr int E = PL::radix(0);
   static constexpr int P = NC / E;
+
+  GX_HD static int lidx(int p) { return LS > 0 ? p * LS : sidx<T>(p); }
 
   GX_HD static constexpr int L(int s) {  // sub-transform length entering stage s
     int l = NC;
@@ -174,12 +179,9 @@ template <typename T, int NC, int DIR> struct BlockFFT {
   }
 
   GX_HD static C twiddle(const C *__restrict__ tw, int j) {
-    // tw[j] = exp(-2 pi i j / NC)
-#ifdef __CUDA_ARCH__
-    C w = __ldg(tw + j);
-#else
+    // tw[j] = exp(-2 pi i j / NC); the table may live in global memory (const __restrict__ -> LDG.CONSTANT) or in
+    // shared memory (column passes: the cluster barrier's acquire invalidates L1, so they keep a private copy)
     C w = tw[j];
-#endif
     if (DIR > 0) w.y = -w.y;
     return w;
   }
@@ -195,7 +197,7 @@ template <typename T, int NC, int DIR> struct BlockFFT {
 #pragma unroll
     for (int q = 1; q < E; ++q) v[q] = cmul(v[q], twiddle(tw, t * q));
 #pragma unroll
-    for (int q = 0; q < E; ++q) line[sidx<T>(t + q * P)] = v[q];
+    for (int q = 0; q < E; ++q) line[lidx(t + q * P)] = v[q];
   }
 
   template <int s, class Emit> GX_HD static void stage(int t, C *line, const C *__restrict__ tw, Emit &&emit) {
@@ -209,7 +211,7 @@ template <typename T, int NC, int DIR> struct BlockFFT {
       const int base = g * Ls + m;
       C a[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) a[r] = line[sidx<T>(base + r * Ds)];
+      for (int r = 0; r < R; ++r) a[r] = line[lidx(base + r * Ds)];
       butterfly<R, DIR, T>(a);
       if (last) {
 #pragma unroll
@@ -218,12 +220,57 @@ template <typename T, int NC, int DIR> struct BlockFFT {
 #pragma unroll
         for (int q = 1; q < R; ++q) a[q] = cmul(a[q], twiddle(tw, m * q * (NC / Ls)));
 #pragma unroll
-        for (int q = 0; q < R; ++q) line[sidx<T>(base + q * Ds)] = a[q];
+        for (int q = 0; q < R; ++q) line[lidx(base + q * Ds)] = a[q];
       }
     }
   }
 
 #ifdef __CUDACC__
+  // Last stage with every output held in registers until the whole CTA has finished reading the line, so that
+  // emit() may overwrite the line buffer itself (used by the r2c row pass, which needs the spectrum in natural
+  // order in shared memory and has no second buffer).
+  template <int s, class Emit> __device__ __forceinline__ static void stage_last_synced(int t, C *line, Emit &&emit) {
+    constexpr int R = PL::radix(s);
+    constexpr int Ls = L(s), Ds = D(s);
+    C out[E];
+#pragma unroll
+    for (int j = 0; j < E / R; ++j) {
+      const int b = t + j * P;
+      const int base = (b / Ds) * Ls + (b % Ds);
+      C a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = line[lidx(base + r * Ds)];
+      butterfly<R, DIR, T>(a);
+#pragma unroll
+      for (int q = 0; q < R; ++q) out[j * R + q] = a[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < E / R; ++j) {
+      const int b = t + j * P;
+      const int base = (b / Ds) * Ls + (b % Ds);
+#pragma unroll
+      for (int q = 0; q < R; ++q) emit(freq_of_pos(base + q * Ds), out[j * R + q]);
+    }
+  }
+
+  template <class Emit> __device__ __forceinline__ static void run_synced_emit(C (&v)[E], int t, C *line,
+                                                                              const C *__restrict__ tw, Emit &&emit) {
+    if constexpr (S == 1) {
+      stage0(v, t, line, tw, emit);
+    } else if constexpr (S == 2) {
+      stage0(v, t, line, tw, emit);
+      __syncthreads();
+      stage_last_synced<1>(t, line, emit);
+    } else {
+      stage0(v, t, line, tw, emit);
+      __syncthreads();
+      stage<1>(t, line, tw, emit);
+      __syncthreads();
+      stage_last_synced<2>(t, line, emit);
+    }
+  }
+
   // Device driver. All threads of the CTA must call it (it contains __syncthreads).
   template <class Emit> __device__ __forceinline__ static void run(C (&v)[E], int t, C *line, const C *__restrict__ tw,
                                                                    Emit &&emit) {

@@ -1,0 +1,45 @@
+// Development entry point: one column pass of the 3-D FFT with an explicit (cluster size, tile width, residency)
+// configuration, so tools/fft_variant_bench.py can sweep them on the GPU. Not part of the product path.
+#include "../../include/genetic_b200.h"
+#include "fft.cuh"
+
+using namespace gx;
+using namespace gx::fft;
+
+template <int N, int CL, int TC, int MINB> static int run_variant(void *field, int pass, cudaStream_t st) {
+  using T = double;
+  using C = cplx<T>;
+  if (int rc = ensure_twiddles()) return rc;
+  C *d = (C *) field;
+  int nbatch;
+  if (pass == 0) {
+    ColGeo g = make_col_geo<PassX>(N, N, N / 2 + 1, nbatch);
+    return launch_cols_cfg<T, N, CL, TC, MINB, 1, PassX>(d, d, g, nbatch, OpIdentity<T>(), OpIdentity<T>(), st);
+  }
+  ColGeo g = make_col_geo<PassY>(N, N, N / 2 + 1, nbatch);
+  return launch_cols_cfg<T, N, CL, TC, MINB, 1, PassY>(d, d, g, nbatch, OpIdentity<T>(), OpIdentity<T>(), st);
+}
+
+extern "C" int gx_dev_fft_cols_variant(void *field, int n, int pass, int variant, void *stream) {
+  cudaStream_t st = (cudaStream_t) stream;
+  if (n == 2048) {
+    switch (variant) {
+      case 0: return run_variant<2048, 8, 8, 3>(field, pass, st);
+      case 1: return run_variant<2048, 8, 8, 2>(field, pass, st);
+      case 2: return run_variant<2048, 8, 16, 1>(field, pass, st);
+      case 3: return run_variant<2048, 8, 4, 6>(field, pass, st);
+      case 4: return run_variant<2048, 16, 8, 3>(field, pass, st);
+      case 5: return run_variant<2048, 16, 16, 3>(field, pass, st);
+    }
+  } else if (n == 1024) {
+    switch (variant) {
+      case 0: return run_variant<1024, 4, 8, 3>(field, pass, st);
+      case 1: return run_variant<1024, 4, 8, 2>(field, pass, st);
+      case 2: return run_variant<1024, 4, 16, 1>(field, pass, st);
+      case 3: return run_variant<1024, 4, 4, 6>(field, pass, st);
+      case 4: return run_variant<1024, 8, 8, 3>(field, pass, st);
+      case 5: return run_variant<1024, 8, 16, 3>(field, pass, st);
+    }
+  }
+  return gx::fail("gx_dev_fft_cols_variant: unknown variant");
+}

@@ -1,7 +1,7 @@
 // Particle emit for a unigrid: ZeldovichParticleEvaluator::getParticle (zeldovich.hpp:87-119,
 // generator.hpp:49-53), Grid::getCentroidFromCoordinate / wrapPoint (grid.hpp:519-531,656-669).
 #include "../../include/genetic_b200.h"
-#include "gx_common.cuh"
+#include "spectral.cuh"
 
 namespace gx {
 
@@ -20,14 +20,12 @@ emit_component_kernel(const T *__restrict__ psi, int n, int axis, T dx, T lower,
     const T p = psi[((size_t) x * n + y) * (size_t) (n + 2) + z];
     const int c = axis == 0 ? x : (axis == 1 ? y : z);
     // result = coord*cellSize; += offsetLower; += cellSize/2   (three separately rounded operations)
-    T cen = (T) c * dx;
-    cen = cen + lower;
-    cen = cen + dx / (T) 2;
-    T q = p + cen;
-    q = fmod(q, domain);
-    if (q < 0) q += domain;
+    T cen = mul_rn((T) c, dx);
+    cen = add_rn(cen, lower);
+    cen = add_rn(cen, dx / (T) 2);
+    const T q = wrap_coordinate<T>(add_rn(p, cen), domain);
     if (out_pos) out_pos[i * stride] = (O) q;
-    if (out_vel) out_vel[i * stride] = (O) (p * ratio);
+    if (out_vel) out_vel[i * stride] = (O) mul_rn(p, ratio);
   }
 }
 

@@ -7,6 +7,7 @@
 // device->host copy of slab s overlaps the emit of slab s+1.
 #include "../../include/genetic_b200.h"
 #include "gx_common.cuh"
+#include "zeldovich.cuh"
 #include <algorithm>
 
 extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field,
@@ -20,7 +21,8 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
   unsigned long long off = 0;
   if ((rc = gx_noise_draw(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, stream))) return rc;
   if (p->fix_power && (rc = gx_unit_variance(delta_field, n, dt, stream))) return rc;
-  if ((rc = gx_apply_transfer(delta_field, n, dt, p->grid_length, spectrum, 0.5, stream))) return rc;
+  // delta_k = sqrt(C(k)) * noise, left divided by k^2: the quotient all three displacement components start from
+  if ((rc = apply_transfer_ex(delta_field, n, dt, p->grid_length, spectrum, 0.5, 1, st))) return rc;
 
   const size_t osz = odt == GX_F64 ? 8 : 4;
   const long long n3 = (long long) n * n * n, n2 = (long long) n * n;
@@ -43,14 +45,18 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
   bool copy_pending[2] = {false, false};
   int buf = 0;
   for (int axis = 0; axis < 3; ++axis) {
-    if ((rc = gx_zeldovich_offset(delta_field, psi_field, n, dt, p->grid_length, axis, stream))) return rc;
+    // x- and y-pass with the ik/k^2 operator and the Hermitian mirror fused into the first load
+    if ((rc = zeldovich_xy(delta_field, psi_field, n, dt, p->grid_length, axis, 1, st))) return rc;
+    EmitGeo eg;
+    eg.cell_size = p->cell_size; eg.offset_lower = p->offset_lower[axis]; eg.domain_size = p->domain_size;
+    eg.vel_ratio = p->vel_ratio;
     for (long long id0 = 0; id0 < n3; id0 += slab) {
       const long long cnt = std::min(slab, n3 - id0);
       char *half = (char *) stage + (size_t) buf * (stage_bytes / 2);
       void *dpos = half, *dvel = half + (size_t) slab * osz;
       if (to_host && copy_pending[buf]) GX_CUDA_CHECK(cudaStreamWaitEvent(st, ev_copy[buf], 0));
-      if ((rc = gx_emit_component(psi_field, n, dt, axis, p->cell_size, p->offset_lower[axis], p->domain_size,
-                                  p->vel_ratio, dpos, dvel, odt, 1, id0, cnt, stream)))
+      // z-pass (c2r) of this slab of x-planes with the particle evaluation fused into its store
+      if ((rc = zeldovich_z_emit(psi_field, n, dt, axis, eg, (long) (id0 / n), (long) (cnt / n), dpos, dvel, odt, st)))
         return rc;
       if (to_host) {
         GX_CUDA_CHECK(cudaEventRecord(ev_emit[buf], st));

@@ -127,19 +127,25 @@ __device__ __forceinline__ void store_part(T *field, int n, int kx, int ky, int 
   field[2 * slot + part] = v;
 }
 
+// Position of a gaussian in its draw order. Initialised once per chunk from the gaussian index (divisions), then
+// advanced incrementally: the draw loops of the reference are plain nested counters.
+struct Cursor {
+  int ks, p, q, face, comp;  // Fourier orders: shell, (k1, k2) loop counters, which of the 3 modes, re/im draw
+  long long row;             // real order: row = x*n + y, z
+  int z;
+};
+
 template <typename T>
-__device__ void deliver(const Dest<T> &d, const StreamDesc &sd, long long g, double value) {
-  if (d.mode == MODE_LIST) { d.list[g] = value; return; }
-  const int n = d.n;
+__device__ __forceinline__ void cursor_init(const Dest<T> &d, const StreamDesc &sd, long long g, Cursor &cu) {
+  cu.ks = cu.p = cu.q = cu.face = cu.comp = 0; cu.row = 0; cu.z = 0;
+  if (d.mode == MODE_LIST) return;
   if (d.mode == MODE_REAL) {
-    const long long row = g / n;
-    const int z = (int) (g - row * n);
-    d.field[row * (n + 2) + z] = (T) value;
+    cu.row = g / d.n;
+    cu.z = (int) (g - cu.row * d.n);
     return;
   }
-  // Fourier orders: gaussian g -> call c = g/2, component g&1
   long long c = g >> 1;
-  const int comp = (int) (g & 1);
+  cu.comp = (int) (g & 1);
   int ks;
   if (d.mode == MODE_FOURIER_PARALLEL) ks = sd.shell;
   else {
@@ -148,14 +154,45 @@ __device__ void deliver(const Dest<T> &d, const StreamDesc &sd, long long g, dou
     while (calls_before_shell(ks + 1) <= c) ++ks;
     c -= calls_before_shell(ks);
   }
-  const int face = (int) (c % 3);
+  cu.ks = ks;
+  cu.face = (int) (c % 3);
   const long long t = c / 3;
-  const int p = (int) (t / (2 * ks)) - ks, q = (int) (t % (2 * ks)) - ks;
+  cu.p = (int) (t / (2 * ks)) - ks;
+  cu.q = (int) (t % (2 * ks)) - ks;
+}
+
+template <typename T> __device__ __forceinline__ void cursor_advance(const Dest<T> &d, Cursor &cu) {
+  if (d.mode == MODE_LIST) return;
+  if (d.mode == MODE_REAL) {
+    if (++cu.z == d.n) { cu.z = 0; ++cu.row; }
+    return;
+  }
+  cu.comp ^= 1;
+  if (cu.comp) return;
+  if (++cu.face < 3) return;
+  cu.face = 0;
+  if (++cu.q < cu.ks) return;
+  cu.q = -cu.ks;
+  if (++cu.p < cu.ks) return;
+  ++cu.ks;  // serial order: on to the next shell (a per-shell stream ends here)
+  cu.p = cu.q = -cu.ks;
+}
+
+template <typename T>
+__device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, long long g, double value) {
+  if (d.mode == MODE_LIST) { d.list[g] = value; return; }
+  const int n = d.n;
+  if (d.mode == MODE_REAL) {
+    d.field[cu.row * (n + 2) + cu.z] = (T) value;
+    return;
+  }
+  const int ks = cu.ks, p = cu.p, q = cu.q, face = cu.face, comp = cu.comp;
   int k1, k2, k3;
   if (face == 0) { k1 = ks; k2 = p; k3 = q; }
   else if (face == 1) { k1 = p; k2 = ks; k3 = q; }
   else { k1 = p; k2 = q; k3 = ks; }
   // last-writer-wins: the conjugate partner -k may be drawn in the same shell
+  const long long c = ((long long) (p + ks) * (2 * ks) + (q + ks)) * 3 + face;
   const long long cp = call_index_in_shell(ks, -k1, -k2, -k3);
   if (cp > c) return;
   // value of this component in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2))
@@ -169,10 +206,17 @@ __device__ void deliver(const Dest<T> &d, const StreamDesc &sd, long long g, dou
   if (k3 == 0) store_part<T>(d.field, n, -k1, -k2, 0, part, part == 1 ? -v : v);
 }
 
+template <typename T>
+__device__ void deliver(const Dest<T> &d, const StreamDesc &sd, long long g, double value) {
+  Cursor cu;
+  cursor_init<T>(d, sd, g, cu);
+  deliver_at<T>(d, cu, g, value);
+}
+
 // ---- chunk kernels -------------------------------------------------------------------------------------------
 struct ChunkParams {
   const StreamDesc *streams;
-  const int *chunk_stream;
+  int n_streams;
   int n_chunks;
   const Big *jump;            // jump[j] = a^(397 * kBc * 2^j)
   ChunkFn *fn;                // pass A output
@@ -200,7 +244,15 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
   __syncthreads();
   const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
   if (chunk >= P.n_chunks) return;
-  const int sid = P.chunk_stream[chunk];
+  int sid = 0;
+  {  // the stream this chunk belongs to: last stream with first_chunk <= chunk
+    int lo = 0, hi = P.n_streams - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (P.streams[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+    }
+    sid = lo;
+  }
   const StreamDesc &sd = P.streams[sid];
   const int q = chunk - sd.first_chunk;
   const bool first = (q == 0);
@@ -224,6 +276,9 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
     if (g >= sd.n_gauss) return;  // nothing wanted from this chunk
   }
 
+  Cursor cu;
+  if (PASS == 1) cursor_init<T>(dest, sd, g, cu);
+
   State st = chunk_start_state(sd, q, P.jump);
 
   for (int bi = 0; bi <= kBc; ++bi) {
@@ -244,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
           if (PASS == 0) cnt[e]++;
           else {
             if (g < sd.n_gauss) {
-              deliver<T>(dest, sd, g, a.value);
+              deliver_at<T>(dest, cu, g, a.value);
               if (a.tail) {
                 const unsigned int slot = atomicAdd(P.tail_count, 1u);
                 if (slot < P.tail_capacity) {
@@ -256,6 +311,7 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
                 P.stream_end[sid] = (unsigned long long) (sd.b0 + (long long) q * kBc) * 24ull + (unsigned long long) p;
             }
             ++g;
+            cursor_advance<T>(dest, cu);
           }
         }
       }
@@ -365,14 +421,68 @@ static long long raw_budget(long long n_gauss) {
 
 struct StreamReq { unsigned long seed; unsigned long long start_raw; long long n_gauss; int shell; };
 
+// Grow-only device/pinned workspace: a draw needs ~50 bytes per 1536 raw outputs (chunk functions and scan
+// states) plus the tail list; allocating and freeing that per call cost more than the kernels at 512^3.
+struct Workspace {
+  void *dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t dev_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void *pin[3] = {nullptr, nullptr, nullptr};
+  size_t pin_cap[3] = {0, 0, 0};
+  int device = -1;
+};
+static Workspace g_ws;
+
+static void ws_release() {
+  for (int i = 0; i < 8; ++i) { if (g_ws.dev[i]) cudaFree(g_ws.dev[i]); g_ws.dev[i] = nullptr; g_ws.dev_cap[i] = 0; }
+  for (int i = 0; i < 3; ++i) { if (g_ws.pin[i]) cudaFreeHost(g_ws.pin[i]); g_ws.pin[i] = nullptr; g_ws.pin_cap[i] = 0; }
+}
+
+static int ws_bind_device() {  // call before the first ws_dev / ws_pin of a draw
+  int dev = 0;
+  GX_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev != g_ws.device) { ws_release(); g_ws.device = dev; }
+  return 0;
+}
+
+static int ws_dev(int slot, size_t bytes, void **out) {
+  if (g_ws.dev_cap[slot] < bytes) {
+    if (g_ws.dev[slot]) GX_CUDA_CHECK(cudaFree(g_ws.dev[slot]));
+    g_ws.dev[slot] = nullptr; g_ws.dev_cap[slot] = 0;
+    const size_t cap = bytes + bytes / 8 + 4096;
+    GX_CUDA_CHECK(cudaMalloc(&g_ws.dev[slot], cap));
+    g_ws.dev_cap[slot] = cap;
+  }
+  *out = g_ws.dev[slot];
+  return 0;
+}
+
+static int ws_pin(int slot, size_t bytes, void **out) {
+  if (g_ws.pin_cap[slot] < bytes) {
+    if (g_ws.pin[slot]) GX_CUDA_CHECK(cudaFreeHost(g_ws.pin[slot]));
+    g_ws.pin[slot] = nullptr; g_ws.pin_cap[slot] = 0;
+    const size_t cap = bytes + bytes / 8 + 4096;
+    GX_CUDA_CHECK(cudaMallocHost(&g_ws.pin[slot], cap));
+    g_ws.pin_cap[slot] = cap;
+  }
+  *out = g_ws.pin[slot];
+  return 0;
+}
+
 template <typename T>
 static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::vector<unsigned long long> *end_raw,
                        cudaStream_t cs) {
   if (ensure_jump_table()) return 1;
   const int ns = (int) reqs.size();
-  std::vector<StreamDesc> sd(ns);
-  std::vector<int> chunk_stream;
+  if (ns == 0) return 0;
+  if (ws_bind_device()) return 1;
+  // stream descriptors are staged in pinned memory (slot 0) followed by the per-stream end positions
+  void *pin0 = nullptr;
+  if (ws_pin(0, sizeof(StreamDesc) * ns + sizeof(unsigned long long) * ns + 64, &pin0)) return 1;
+  StreamDesc *sd = (StreamDesc *) pin0;
+  unsigned long long *h_end = (unsigned long long *) ((char *) pin0 + sizeof(StreamDesc) * ns);
+  unsigned int *h_ntail = (unsigned int *) (h_end + ns);
   const Big a = big_a();
+  long long n_chunks = 0, total_gauss = 0;
   for (int s = 0; s < ns; ++s) {
     StreamDesc &d = sd[s];
     d.s0 = seed_state(reqs[s].seed);
@@ -382,44 +492,46 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     d.shell = reqs[s].shell;
     d.xs = state_to_big(d.s0);
     if (d.b0 > 0) d.xs = modmul(d.xs, modpow(a, 397ull * (unsigned long long) d.b0));
-    d.first_chunk = (int) chunk_stream.size();
+    d.first_chunk = (int) n_chunks;
     const long long raws = d.entry0 + raw_budget(d.n_gauss);
-    const long long nch = (raws + kChunkLen - 1) / kChunkLen;
-    if ((long long) chunk_stream.size() + nch > 2000000000ll) return fail("gx_noise_draw: too many chunks");
-    chunk_stream.insert(chunk_stream.end(), (size_t) nch, s);
+    n_chunks += (raws + kChunkLen - 1) / kChunkLen;
+    if (n_chunks > 2000000000ll) return fail("gx_noise_draw: too many chunks");
+    total_gauss += d.n_gauss;
   }
-  const int n0 = (int) chunk_stream.size();
+  const int n0 = (int) n_chunks;
   if (n0 == 0) return 0;
-
-  StreamDesc *d_streams = nullptr; int *d_chunk_stream = nullptr; unsigned long long *d_end = nullptr;
-  unsigned int *d_tail_count = nullptr; TailEvent *d_tails = nullptr;
-  long long total_gauss = 0;
-  for (auto &r : reqs) total_gauss += r.n_gauss;
-  const unsigned int tail_cap = (unsigned int) std::min<long long>((long long) (total_gauss * 8e-4) + 4096, 400000000ll);
-  GX_CUDA_CHECK(cudaMalloc(&d_streams, sizeof(StreamDesc) * ns));
-  GX_CUDA_CHECK(cudaMalloc(&d_chunk_stream, sizeof(int) * (size_t) n0));
-  GX_CUDA_CHECK(cudaMalloc(&d_end, sizeof(unsigned long long) * ns));
-  GX_CUDA_CHECK(cudaMalloc(&d_tail_count, sizeof(unsigned int)));
-  GX_CUDA_CHECK(cudaMalloc(&d_tails, sizeof(TailEvent) * (size_t) tail_cap));
-  GX_CUDA_CHECK(cudaMemcpyAsync(d_streams, sd.data(), sizeof(StreamDesc) * ns, cudaMemcpyHostToDevice, cs));
-  GX_CUDA_CHECK(cudaMemcpyAsync(d_chunk_stream, chunk_stream.data(), sizeof(int) * (size_t) n0, cudaMemcpyHostToDevice, cs));
-  GX_CUDA_CHECK(cudaMemsetAsync(d_end, 0xFF, sizeof(unsigned long long) * ns, cs));
-  GX_CUDA_CHECK(cudaMemsetAsync(d_tail_count, 0, sizeof(unsigned int), cs));
 
   // scan levels
   std::vector<int> level_n;
   level_n.push_back(n0);
   while (level_n.back() > 4096) level_n.push_back((level_n.back() + 63) / 64);
   const int nl = (int) level_n.size();
-  std::vector<ChunkFn *> d_fn(nl, nullptr);
-  std::vector<ScanState *> d_st(nl, nullptr);
-  for (int l = 0; l < nl; ++l) {
-    GX_CUDA_CHECK(cudaMalloc(&d_fn[l], sizeof(ChunkFn) * (size_t) level_n[l]));
-    GX_CUDA_CHECK(cudaMalloc(&d_st[l], sizeof(ScanState) * (size_t) level_n[l]));
+  size_t fn_total = 0;
+  for (int l = 0; l < nl; ++l) fn_total += (size_t) level_n[l];
+
+  const unsigned int tail_cap = (unsigned int) std::min<long long>((long long) (total_gauss * 8e-4) + 4096, 400000000ll);
+  void *p_streams, *p_misc, *p_tails, *p_fn, *p_st;
+  if (ws_dev(0, sizeof(StreamDesc) * ns, &p_streams)) return 1;
+  if (ws_dev(1, sizeof(unsigned long long) * ns + 64, &p_misc)) return 1;
+  if (ws_dev(2, sizeof(TailEvent) * (size_t) tail_cap, &p_tails)) return 1;
+  if (ws_dev(3, sizeof(ChunkFn) * fn_total, &p_fn)) return 1;
+  if (ws_dev(4, sizeof(ScanState) * fn_total, &p_st)) return 1;
+  StreamDesc *d_streams = (StreamDesc *) p_streams;
+  unsigned long long *d_end = (unsigned long long *) p_misc;
+  unsigned int *d_tail_count = (unsigned int *) (d_end + ns);
+  TailEvent *d_tails = (TailEvent *) p_tails;
+  std::vector<ChunkFn *> d_fn(nl);
+  std::vector<ScanState *> d_st(nl);
+  {
+    size_t off = 0;
+    for (int l = 0; l < nl; ++l) { d_fn[l] = (ChunkFn *) p_fn + off; d_st[l] = (ScanState *) p_st + off; off += (size_t) level_n[l]; }
   }
+  GX_CUDA_CHECK(cudaMemcpyAsync(d_streams, sd, sizeof(StreamDesc) * ns, cudaMemcpyHostToDevice, cs));
+  GX_CUDA_CHECK(cudaMemsetAsync(d_end, 0xFF, sizeof(unsigned long long) * ns, cs));
+  GX_CUDA_CHECK(cudaMemsetAsync(d_tail_count, 0, sizeof(unsigned int), cs));
 
   ChunkParams P;
-  P.streams = d_streams; P.chunk_stream = d_chunk_stream; P.n_chunks = n0; P.jump = g_jump; P.fn = d_fn[0];
+  P.streams = d_streams; P.n_streams = ns; P.n_chunks = n0; P.jump = g_jump; P.fn = d_fn[0];
   P.scan = d_st[0]; P.stream_end = d_end; P.tails = d_tails; P.tail_count = d_tail_count; P.tail_capacity = tail_cap;
   const int grid = (n0 + kThreads - 1) / kThreads;
   {
@@ -429,17 +541,17 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   count_launch();
   GX_LAUNCH_CHECK();
   {
-  GX_TIMED("rng_scan", cs);
-  for (int l = 1; l < nl; ++l) {
-    scan_up_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_fn[l], level_n[l]);
+    GX_TIMED("rng_scan", cs);
+    for (int l = 1; l < nl; ++l) {
+      scan_up_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_fn[l], level_n[l]);
+      count_launch();
+    }
+    scan_top_kernel<<<1, 32, 0, cs>>>(d_fn[nl - 1], level_n[nl - 1], d_st[nl - 1]);
     count_launch();
-  }
-  scan_top_kernel<<<1, 32, 0, cs>>>(d_fn[nl - 1], level_n[nl - 1], d_st[nl - 1]);
-  count_launch();
-  for (int l = nl - 1; l >= 1; --l) {
-    scan_down_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_st[l], level_n[l], d_st[l - 1]);
-    count_launch();
-  }
+    for (int l = nl - 1; l >= 1; --l) {
+      scan_down_kernel<<<(level_n[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], level_n[l - 1], d_st[l], level_n[l], d_st[l - 1]);
+      count_launch();
+    }
   }
   GX_LAUNCH_CHECK();
   {
@@ -450,40 +562,38 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   GX_LAUNCH_CHECK();
 
   // tails: host libm recomputation (the reference's own arithmetic for these draws)
-  unsigned int ntail = 0;
-  std::vector<unsigned long long> h_end(ns);
-  GX_CUDA_CHECK(cudaMemcpyAsync(&ntail, d_tail_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
-  GX_CUDA_CHECK(cudaMemcpyAsync(h_end.data(), d_end, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToHost, cs));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h_ntail, d_tail_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h_end, d_end, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToHost, cs));
   GX_CUDA_CHECK(cudaStreamSynchronize(cs));
-  int rc = 0;
-  if (ntail > tail_cap) rc = fail("gx_noise_draw: tail list overflow");
-  for (int s = 0; s < ns && !rc; ++s)
-    if (reqs[s].n_gauss > 0 && h_end[s] == ~0ull) rc = fail("gx_noise_draw: raw budget too small for a stream (internal)");
-  if (!rc && ntail > 0) {
-    std::vector<TailEvent> ev(ntail);
-    std::vector<double> val(ntail);
-    rc = cudaMemcpy(ev.data(), d_tails, sizeof(TailEvent) * ntail, cudaMemcpyDeviceToHost) != cudaSuccess;
+  const unsigned int ntail = *h_ntail;
+  if (ntail > tail_cap) return fail("gx_noise_draw: tail list overflow");
+  for (int s = 0; s < ns; ++s)
+    if (reqs[s].n_gauss > 0 && h_end[s] == ~0ull) return fail("gx_noise_draw: raw budget too small for a stream (internal)");
+  if (end_raw) end_raw->assign(h_end, h_end + ns);
+  if (ntail > 0) {
+    void *pin_ev = nullptr, *pin_val = nullptr, *p_val = nullptr;
+    if (ws_pin(1, sizeof(TailEvent) * (size_t) ntail, &pin_ev)) return 1;
+    if (ws_pin(2, sizeof(double) * (size_t) ntail, &pin_val)) return 1;
+    if (ws_dev(5, sizeof(double) * (size_t) ntail, &p_val)) return 1;
+    TailEvent *ev = (TailEvent *) pin_ev;
+    double *val = (double *) pin_val;
+    GX_CUDA_CHECK(cudaMemcpyAsync(ev, d_tails, sizeof(TailEvent) * ntail, cudaMemcpyDeviceToHost, cs));
+    GX_CUDA_CHECK(cudaStreamSynchronize(cs));
     const double R = GX_ZIG_R;
     for (unsigned int i = 0; i < ntail; ++i) {
       const double U1 = 1.0 - (double) ev[i].u1 / 16777216.0;
       const double x = R - std::log(U1) / R;
       val[i] = ev[i].positive ? x : -x;
     }
-    double *d_val = nullptr;
-    if (!rc) rc = cudaMalloc(&d_val, sizeof(double) * ntail) != cudaSuccess;
-    if (!rc) rc = cudaMemcpyAsync(d_val, val.data(), sizeof(double) * ntail, cudaMemcpyHostToDevice, cs) != cudaSuccess;
-    if (!rc) {
-      tail_patch_kernel<T><<<(ntail + 127) / 128, 128, 0, cs>>>(d_tails, d_val, ntail, d_streams, dest);
-      count_launch();
-      rc = cudaStreamSynchronize(cs) != cudaSuccess;
-    }
-    if (d_val) cudaFree(d_val);
-    if (rc) fail("gx_noise_draw: tail patch failed");
+    GX_CUDA_CHECK(cudaMemcpyAsync(p_val, val, sizeof(double) * ntail, cudaMemcpyHostToDevice, cs));
+    GX_TIMED("rng_tail_patch", cs);
+    tail_patch_kernel<T><<<(ntail + 127) / 128, 128, 0, cs>>>(d_tails, (const double *) p_val, ntail, d_streams, dest);
+    count_launch();
+    GX_LAUNCH_CHECK();
+    // the pinned staging buffers are reused by the next draw: wait for the upload
+    GX_CUDA_CHECK(cudaStreamSynchronize(cs));
   }
-  if (end_raw) *end_raw = h_end;
-  for (int l = 0; l < nl; ++l) { cudaFree(d_fn[l]); cudaFree(d_st[l]); }
-  cudaFree(d_streams); cudaFree(d_chunk_stream); cudaFree(d_end); cudaFree(d_tail_count); cudaFree(d_tails);
-  return rc;
+  return 0;
 }
 
 template <typename T>
@@ -538,6 +648,11 @@ int gx_noise_draw(void *field, int n, int dtype, unsigned long seed, int mode, i
   if (dtype == GX_F64) return noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
   if (dtype == GX_F32) return noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
   return gx::fail("bad dtype");
+}
+
+int gx_workspace_release(void) {
+  gx::rng::ws_release();
+  return 0;
 }
 
 int gx_rng_raw(unsigned long seed, unsigned long long offset, long n, uint32_t *host_out) {

@@ -70,8 +70,11 @@ template <typename T> struct CovarianceF : SpecInit {
 };
 
 // ---- Field::applyTransferFunction with the covariance evaluated on the fly (field.hpp:394-412) ------------
+// divide_k2: additionally leave delta_k / k^2 (0 at k = 0) -- the quotient every Zeldovich component starts from
+// (zeldovich.hpp:170-176 divides per component; the rounded quotient is the same number, so it is formed once here
+// instead of three times inside the FFT passes).
 template <typename T> struct ApplyTransferF : SpecInit {
-  cplx<T> *f; int n; T kmin, norm; double power;
+  cplx<T> *f; int n; T kmin, norm; double power; int divide_k2;
   __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
     if (!slot_is_independent(n, ix, iy, iz)) return;
     T kx, ky, kz, k2;
@@ -80,7 +83,9 @@ template <typename T> struct ApplyTransferF : SpecInit {
     T spec = mul_rn(spectrum_power<T>(sp, t, t + sp.m, t + 2 * sp.m, sqrt_rn(k2)), norm);
     spec = spec_pow<T>(spec, power);
     cplx<T> v = f[s];
-    f[s] = mk<T>(mul_rn(v.x, spec), mul_rn(v.y, spec));
+    v = mk<T>(mul_rn(v.x, spec), mul_rn(v.y, spec));
+    if (divide_k2) v = (k2 != (T) 0) ? mk<T>(div_rn(v.x, k2), div_rn(v.y, k2)) : mk<T>(0, 0);
+    f[s] = v;
   }
 };
 
@@ -195,10 +200,12 @@ template <typename T> static int covariance_field_t(void *out, int n, double L, 
 }
 
 template <typename T>
-static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, double power, cudaStream_t st) {
+static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, double power, cudaStream_t st,
+                            int divide_k2 = 0) {
   ApplyTransferF<T> f;
   f.sp = gx_spectrum_device_view(s);
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n); f.power = power;
+  f.divide_k2 = divide_k2;
   return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double), "apply_transfer");
 }
 
@@ -229,6 +236,16 @@ static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, in
   f.delta = (const cplx<T> *) delta; f.psi = (cplx<T> *) psi; f.n = n; f.axis = axis; f.kmin = kmin_of<T>(L);
   return launch_slot_sweep(n, f, st, 0, "zeldovich_op");
 }
+
+namespace gx {
+int apply_transfer_ex(void *field, int n, int dtype, double L, const gx_spectrum *s, double power, int divide_k2,
+                      cudaStream_t st) {
+  if (check_n(n)) return 1;
+  if (dtype == GX_F64) return apply_transfer_t<double>(field, n, L, s, power, st, divide_k2);
+  if (dtype == GX_F32) return apply_transfer_t<float>(field, n, L, s, power, st, divide_k2);
+  return fail("bad dtype");
+}
+}  // namespace gx
 
 extern "C" {
 

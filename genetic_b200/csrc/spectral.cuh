@@ -26,6 +26,15 @@ __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, 
 __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 
+// Grid::wrapIndividualCoordinate (grid.hpp:527-531): x = fmod(x, L); if (x < 0) x += L.  fmod is exact, and for
+// L <= x < 2L it equals x - L, which is itself exact (Sterbenz), so the common cases never enter the slow routine.
+template <typename T> __device__ __forceinline__ T wrap_coordinate(T x, T L) {
+  if (x >= L) x = (x < L + L) ? x - L : fmod(x, L);
+  else if (x <= -L) x = fmod(x, L);
+  if (x < 0) x = add_rn(x, L);
+  return x;
+}
+
 // k^2 and |k| of a storage slot exactly as the reference forms them:
 //   kx = int * kMin (CoordinateType), k2 = kx*kx + ky*ky + kz*kz, k = sqrt(k2)
 template <typename T> __device__ __forceinline__ void slot_k(int n, int ix, int iy, int iz, T kmin, T &kx, T &ky, T &kz,

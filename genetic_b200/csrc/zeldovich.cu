@@ -1,0 +1,182 @@
+// Zeldovich displacement with everything fused into the three inverse-FFT passes.
+//
+// Reference: ZeldovichParticleGenerator::calculateOffsetFields (zeldovich.hpp:152-181,248-251) builds three new
+// Fourier fields through generateNewFourierFields (fourier.hpp:253-274), then each toReal() runs
+// ensureFourierModesAreMirrored (:331-357), the c2r plan, unpadAfterFFTWRealTransform (:389-405) and the
+// divide-by-N^1.5 sweep (:512-513); ZeldovichParticleEvaluator::getParticle (zeldovich.hpp:87-119) later reads the
+// three real fields cell by cell. Here, per component:
+//   x-pass : reads delta_k ONCE, applies i k_j / k^2 (Nyquist/DC zeroing) and the mirror on load, writes the
+//            half-transformed field                                                                   (2 B)
+//   y-pass : in place                                                                              (2 B)
+//   z-pass : c2r + 1/N^1.5 and either the real field or directly pos = wrap(centroid + psi), vel = psi * ratio
+//            in the output type                                                                     (<= 2 B)
+// The arithmetic of each element is the unfused path's (spectral.cu ZeldovichF, mirror_kernel, particles.cu), so both
+// paths give bit-identical results.
+#include "../../include/genetic_b200.h"
+#include "spectral.cuh"
+#include "fft.cuh"
+#include "zeldovich.cuh"
+
+namespace gx {
+
+template <typename T, bool PREDIV> struct OpZeldovichMirror {
+  const cplx<T> *delta;
+  int n, nc, axis;
+  T kmin;
+  __device__ __forceinline__ cplx<T> operator()(cplx<T> d, int ix, int iy, int iz) const {
+    const int h = n >> 1;
+    bool conj = false;
+    if ((iz == 0 || iz == h) && !slot_is_independent(n, ix, iy, iz)) {
+      // ensureFourierModesAreMirrored: this slot is the conjugate of (-kx, -ky) on the same kz plane
+      ix = (n - ix) & (n - 1);
+      iy = (n - iy) & (n - 1);
+      d = delta[((size_t) ix * n + iy) * nc + iz];
+      conj = true;
+    }
+    T kx, ky, kz, k2;
+    slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+    const int ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+    const T ka = axis == 0 ? kx : (axis == 1 ? ky : kz);
+    cplx<T> r = mk<T>(0, 0);
+    if (ia != h && k2 != (T) 0) {
+      if (PREDIV) { r.x = mul_rn(-d.y, ka); r.y = mul_rn(d.x, ka); }
+      else { r.x = mul_rn(div_rn(-d.y, k2), ka); r.y = mul_rn(div_rn(d.x, k2), ka); }
+    }
+    // the mirror leaves conj(value) in dependent slots and a negated imaginary part in self-conjugate ones
+    const bool self = (iz == 0 || iz == h) && (ix == 0 || ix == h) && (iy == 0 || iy == h);
+    if (conj || self) r.y = -r.y;
+    return r;
+  }
+};
+
+template <typename O> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<double> { using type = double2; };
+
+template <typename T, typename O> struct StoreEmit {
+  O *pos, *vel;
+  long long id0;
+  int n, axis;
+  T scale, dx, lower, half_dx, domain, ratio;
+  __device__ __forceinline__ T wrap(T psi, int c) const {
+    // getCentroidFromCoordinate: coord*cellSize; += offsetLower; += cellSize/2 (three separately rounded operations)
+    T cen = add_rn(add_rn(mul_rn((T) c, dx), lower), half_dx);
+    return wrap_coordinate<T>(add_rn(psi, cen), domain);
+  }
+  __device__ __forceinline__ void operator()(long row, int k, cplx<T> z) const {
+    const T p0 = z.x * scale, p1 = z.y * scale;
+    const long long i = (long long) row * n + 2 * k - id0;
+    using P2 = typename Pair<O>::type;
+    if (pos) {
+      int c0, c1;
+      if (axis == 2) { c0 = 2 * k; c1 = 2 * k + 1; }
+      else {
+        const int x = (int) (row / n);
+        c0 = c1 = (axis == 0) ? x : (int) (row - (long) x * n);
+      }
+      P2 o; o.x = (O) wrap(p0, c0); o.y = (O) wrap(p1, c1);
+      *reinterpret_cast<P2 *>(pos + i) = o;
+    }
+    if (vel) {
+      P2 o; o.x = (O) mul_rn(p0, ratio); o.y = (O) mul_rn(p1, ratio);
+      *reinterpret_cast<P2 *>(vel + i) = o;
+    }
+  }
+};
+
+template <typename T, int N, bool PREDIV>
+static int zeldovich_xy_n(const void *delta_k, void *work, double L, int axis, cudaStream_t st) {
+  using namespace fft;
+  using C = cplx<T>;
+  const int nc = N / 2 + 1;
+  OpZeldovichMirror<T, PREDIV> op;
+  op.delta = (const C *) delta_k; op.n = N; op.nc = nc; op.axis = axis;
+  op.kmin = (T) (2. * M_PI / (double) (T) L);
+  int rc = launch_cols<T, N, 1, PassX>((const C *) delta_k, (C *) work, N, N, nc, op, OpIdentity<T>(), st);
+  if (rc) return rc;
+  return launch_cols<T, N, 1, PassY>((const C *) work, (C *) work, N, N, nc, OpIdentity<T>(), OpIdentity<T>(), st);
+}
+
+template <typename T, int N> static int z_real_n(void *work, long row0, long nrows, cudaStream_t st) {
+  fft::StoreRealScaled<T> s;
+  s.data = (T *) work; s.scale = (T) (1.0 / pow((double) N, 1.5)); s.n = N;
+  return fft::launch_rows_c2r<T, N>((const T *) work, row0, nrows, s, st);
+}
+
+template <typename T, typename O, int N>
+static int z_emit_n(const void *work, int axis, const EmitGeo &g, long row0, long nrows, void *pos, void *vel, cudaStream_t st) {
+  StoreEmit<T, O> s;
+  s.pos = (O *) pos; s.vel = (O *) vel; s.id0 = (long long) row0 * N; s.n = N; s.axis = axis;
+  s.scale = (T) (1.0 / pow((double) N, 1.5));
+  s.dx = (T) g.cell_size; s.lower = (T) g.offset_lower; s.half_dx = (T) g.cell_size / (T) 2;
+  s.domain = (T) g.domain_size; s.ratio = (T) g.vel_ratio;
+  return fft::launch_rows_c2r<T, N>((const T *) work, row0, nrows, s, st);
+}
+
+#define GX_N_SWITCH(n, CALL)                                                                                     \
+  switch (n) {                                                                                                   \
+    case 4: { constexpr int N = 4; return CALL; }                                                                \
+    case 8: { constexpr int N = 8; return CALL; }                                                                \
+    case 16: { constexpr int N = 16; return CALL; }                                                              \
+    case 32: { constexpr int N = 32; return CALL; }                                                              \
+    case 64: { constexpr int N = 64; return CALL; }                                                              \
+    case 128: { constexpr int N = 128; return CALL; }                                                            \
+    case 256: { constexpr int N = 256; return CALL; }                                                            \
+    case 512: { constexpr int N = 512; return CALL; }                                                            \
+    case 1024: { constexpr int N = 1024; return CALL; }                                                          \
+    case 2048: { constexpr int N = 2048; return CALL; }                                                          \
+    case 4096: { constexpr int N = 4096; return CALL; }                                                          \
+    default: return fail("grid size must be a power of two in [4,4096]");                                        \
+  }
+
+template <typename T, bool PREDIV>
+static int zeldovich_xy_t(const void *d, void *w, int n, double L, int axis, cudaStream_t st) {
+  GX_N_SWITCH(n, (zeldovich_xy_n<T, N, PREDIV>(d, w, L, axis, st)));
+}
+template <typename T> static int z_real_t(void *w, int n, long row0, long nrows, cudaStream_t st) {
+  GX_N_SWITCH(n, (z_real_n<T, N>(w, row0, nrows, st)));
+}
+template <typename T, typename O>
+static int z_emit_t(const void *w, int n, int axis, const EmitGeo &g, long row0, long nrows, void *pos, void *vel,
+                    cudaStream_t st) {
+  GX_N_SWITCH(n, (z_emit_n<T, O, N>(w, axis, g, row0, nrows, pos, vel, st)));
+}
+
+int zeldovich_xy(const void *delta_k, void *work, int n, int dtype, double grid_length, int axis, int prediv,
+                 cudaStream_t st) {
+  if (axis < 0 || axis > 2) return fail("axis must be 0, 1 or 2");
+  if (delta_k == work) return fail("zeldovich: the work field must not alias delta_k");
+  if (int rc = fft::ensure_twiddles()) return rc;
+  if (dtype == GX_F64)
+    return prediv ? zeldovich_xy_t<double, true>(delta_k, work, n, grid_length, axis, st)
+                  : zeldovich_xy_t<double, false>(delta_k, work, n, grid_length, axis, st);
+  if (dtype == GX_F32)
+    return prediv ? zeldovich_xy_t<float, true>(delta_k, work, n, grid_length, axis, st)
+                  : zeldovich_xy_t<float, false>(delta_k, work, n, grid_length, axis, st);
+  return fail("bad dtype");
+}
+
+int zeldovich_z_real(void *work, int n, int dtype, long row0, long nrows, cudaStream_t st) {
+  if (dtype == GX_F64) return z_real_t<double>(work, n, row0, nrows, st);
+  if (dtype == GX_F32) return z_real_t<float>(work, n, row0, nrows, st);
+  return fail("bad dtype");
+}
+
+int zeldovich_z_emit(const void *work, int n, int dtype, int axis, const EmitGeo &geo, long row0, long nrows,
+                     void *out_pos, void *out_vel, int out_dtype, cudaStream_t st) {
+  if (dtype == GX_F64 && out_dtype == GX_F32) return z_emit_t<double, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  if (dtype == GX_F64 && out_dtype == GX_F64) return z_emit_t<double, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  if (dtype == GX_F32 && out_dtype == GX_F32) return z_emit_t<float, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  if (dtype == GX_F32 && out_dtype == GX_F64) return z_emit_t<float, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  return fail("bad dtype");
+}
+
+}  // namespace gx
+
+extern "C" int gx_zeldovich_offset(const void *delta_k, void *psi, int n, int dtype, double grid_length, int axis,
+                                   void *stream) {
+  cudaStream_t st = (cudaStream_t) stream;
+  int rc = gx::zeldovich_xy(delta_k, psi, n, dtype, grid_length, axis, 0, st);
+  if (rc) return rc;
+  return gx::zeldovich_z_real(psi, n, dtype, 0, (long) n * n, st);
+}

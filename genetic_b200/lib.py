@@ -36,6 +36,7 @@ PROTOTYPES = {
     "gx_device_count": (ci, [P(ci)]),
     "gx_set_device": (ci, [ci]),
     "gx_synchronize": (ci, [vp]),
+    "gx_workspace_release": (ci, []),
     "gx_launch_count": (cull, []),
     "gx_field_bytes": (csz, [ci, ci]),
     "gx_malloc": (ci, [P(vp), csz]),

@@ -48,6 +48,7 @@ int gx_version(void);
 int gx_device_count(int *count);
 int gx_set_device(int device);           /* fourier::initialise() analogue, fourier.hpp:36-81 */
 int gx_synchronize(void *stream);
+int gx_workspace_release(void);          /* frees the grow-only scratch buffers the noise generator keeps between calls */
 unsigned long long gx_launch_count(void); /* kernels launched by this library so far (bench bookkeeping) */
 
 /* ---- memory ----------------------------------------------------------------------------------- */
@@ -167,7 +168,8 @@ typedef struct {
    host_pos/host_vel (may be NULL: results stay in the staging buffer, nothing is copied): component-major arrays
    out[axis][id] of out_dtype; if host_capacity_particles < n^3 they are used as a ring of 3*capacity elements.
    Synchronous with respect to the device->host copies; kernels run on `stream`. On return delta_field holds
-   delta_k and psi_field the z displacement in real space. */
+   delta_k / k^2 (the common factor of the three displacement components, formed once); psi_field is scratch (the half-transformed z component: the last FFT pass writes particles, not the
+   real-space field). */
 int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field, void *stage,
                   size_t stage_bytes, void *host_pos, void *host_vel, size_t host_capacity_particles, void *stream);
 
