@@ -57,21 +57,28 @@ struct ColGeo {
   int nc;              // fastest extent (n/2+1)
 };
 
-// default cluster size / tile width / residency target per (type, N); see profiles/ for the variant sweep
+// default cluster size / tile width / residency target per (type, N); profiles/r1_fft_variants.txt keeps the sweep
 template <typename T, int N> struct ColsPlan {
-  // 128-byte row segments and 256 rows per CTA: 32 KB tiles, double buffered, 3 CTAs per SM; 4096-point lines keep the
-  // portable cluster size 8 with 512 rows per CTA
+  // 128-byte row segments x 256 rows per CTA = 32 KB tiles, single buffer, one tile per cluster, five CTAs per SM
+  // (register cap 102): on B200 the phase diversity of many small CTAs beat both the persistent double-buffered
+  // form and wider tiles. 4096-point lines keep the portable cluster size 8 with 512 rows per CTA.
   static constexpr int TC = 128 / (int) sizeof(cplx<T>);
   static constexpr int Rmax = (N >= 4096) ? 512 : 256;
   static constexpr int CL = (N > Rmax) ? N / Rmax : 1;  // 512 -> 2, 1024 -> 4, 2048 -> 8, 4096 -> 8
-  static constexpr int MINB = (N >= 4096) ? 1 : 3;      // register cap so that three 64 KB CTAs fit an SM
+  static constexpr int MINB = (N >= 4096) ? 1 : (sizeof(T) == 8 ? 5 : 4);
+  static constexpr int SEL = 4;  // single buffer, non-persistent (see ColsCfg)
 };
 
-template <typename T, int N, int CL_, int TC_> struct ColsCfg {
+template <typename T, int N, int CL_, int TC_, int SEL_ = 0> struct ColsCfg {
   static constexpr int TC = TC_;
   static constexpr int CL = CL_;
   static constexpr int R = N / CL;
-  using B = BlockFFT<T, R, -1, TC>;
+  // SEL_ bit 0: 8-points-per-thread plan (exists for 256-point local transforms); bit 2: single buffer, one tile per
+  // cluster (non-persistent); bit 1: timing experiment only (wrong results): no DSMEM traffic
+  static constexpr int SEL = (R == 256 && (SEL_ & 1)) ? 1 : 0;
+  static constexpr bool kExperimentLocalPull = (SEL_ & 2) != 0;
+  static constexpr int NBUF = (SEL_ & 4) ? 1 : 2;
+  using B = BlockFFT<T, R, -1, TC, SEL>;
   static constexpr int E = B::E, P = B::P;
   static constexpr int threads = P * TC;
   static constexpr int IPT = (CL > 1) ? E / CL : 1;  // cross-cluster butterflies per thread
@@ -79,7 +86,7 @@ template <typename T, int N, int CL_, int TC_> struct ColsCfg {
   static_assert(threads <= 1024, "too many threads per CTA");
   static constexpr size_t tile_bytes = (size_t) R * TC * sizeof(cplx<T>);
   // two tile buffers + the local twiddles W_R^j and (clusters) this CTA's cross twiddles W_N^(q j)
-  static constexpr size_t smem = 2 * tile_bytes + (size_t) (CL > 1 ? 2 : 1) * R * sizeof(cplx<T>);
+  static constexpr size_t smem = NBUF * tile_bytes + (size_t) (CL > 1 ? 2 : 1) * R * sizeof(cplx<T>);
 };
 
 __device__ __forceinline__ unsigned smem_addr_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -109,13 +116,13 @@ __device__ __forceinline__ void cluster_arrive_relaxed_after(float dep) {
 
 // Persistent: cluster `cid` of `nclusters` walks the tiles cid, cid + nclusters, ...; the loads of the next tile are in
 // flight (cp.async into the other half of shared memory) while the current one is transformed.
-template <typename T, int N, int CL, int TC, int MINB, int DIR, class Pass, class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(ColsCfg<T, N, CL, TC>::threads, MINB)
+template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
+__global__ void __launch_bounds__(ColsCfg<T, N, CL, TC, SEL>::threads, MINB)
 fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int nclusters, const cplx<T> *__restrict__ twR,
                 const cplx<T> *__restrict__ twN, LoadOp lop, StoreOp sop) {
   using C = cplx<T>;
-  using Cfg = ColsCfg<T, N, CL, TC>;
-  using B = BlockFFT<T, Cfg::R, DIR, TC>;
+  using Cfg = ColsCfg<T, N, CL, TC, SEL>;
+  using B = BlockFFT<T, Cfg::R, DIR, TC, Cfg::SEL>;
   constexpr int R = Cfg::R, E = B::E, P = B::P;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
@@ -125,7 +132,7 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
   int q = 0;
   if constexpr (CL > 1) q = (int) cooperative_groups::this_cluster().block_rank();
   const long cid = blockIdx.x / CL;
-  C *twl = smem + 2 * (R * TC);  // W_R^j
+  C *twl = smem + Cfg::NBUF * (R * TC);  // W_R^j
   C *twc = twl + R;              // W_N^(q j)
   for (int i = threadIdx.x; i < R; i += blockDim.x) {
     twl[i] = twR[i];
@@ -147,12 +154,17 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
   };
 
   long tile = cid;
-  if (tile < ntiles) issue(tile, smem);
+  if (Cfg::NBUF == 2 && tile < ntiles) issue(tile, smem);
   for (int it = 0; tile < ntiles; tile += nclusters, ++it) {
-    C *buf = smem + (size_t) (it & 1) * (R * TC);
-    const long next = tile + nclusters;
-    if (next < ntiles) { issue(next, smem + (size_t) ((it + 1) & 1) * (R * TC)); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
+    C *buf = smem + (size_t) (Cfg::NBUF == 2 ? (it & 1) : 0) * (R * TC);
+    if constexpr (Cfg::NBUF == 2) {
+      const long next = tile + nclusters;
+      if (next < ntiles) { issue(next, smem + (size_t) ((it + 1) & 1) * (R * TC)); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+    } else {
+      issue(tile, buf);
+      cp_async_wait<0>();
+    }
 
     const int batch = (int) (tile / g.tiles_per_batch);
     const long col = (tile % g.tiles_per_batch) * TC + c;
@@ -190,10 +202,10 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
       B::run_synced_emit(v, t, buf + c, twl, [&](int k1, C val) {
         buf[k1 * TC + c] = (q == 0) ? val : cmul(val, B::twiddle(twc, k1));
       });
-      // A release-arrive would also wait for the cp.async prefetch of the next tile (it is a full memory barrier):
-      // the CTA barrier makes this CTA's shared-memory writes complete, then the cluster barrier is execution-only.
-      __syncthreads();
-      cluster_arrive_relaxed();
+      // release/acquire: the peers' DSMEM reads must see these shared-memory writes (a relaxed arrive after a CTA
+      // barrier is NOT enough -- remote reads can overtake stores still queued in this SM; measured as sparse wrong
+      // tiles). With a single buffer no global access is outstanding here, so the fence is cheap.
+      cluster_arrive_release();
       cluster_wait();
       // final radix-CL stage: this CTA combines the positions k1 in [q R/CL, (q+1) R/CL) of all CL sub-transforms
       // (one pull through distributed shared memory) and stores X[k1 + R k2], k2 = 0..CL-1
@@ -204,7 +216,8 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
       for (int m = 0; m < IPT; ++m) {
         const int k1 = q * (R / CL) + t + m * P;
 #pragma unroll
-        for (int q2 = 0; q2 < CL; ++q2) y[m][q2] = cluster.map_shared_rank(buf, q2)[k1 * TC + c];
+        for (int q2 = 0; q2 < CL; ++q2)
+          y[m][q2] = cluster.map_shared_rank(buf, Cfg::kExperimentLocalPull ? q : q2)[((k1 + (Cfg::kExperimentLocalPull ? q2 * 7 : 0)) % R) * TC + c];
       }
       T dep = (T) 0;
 #pragma unroll
@@ -227,13 +240,13 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
   }
 }
 
-template <typename T, int N, int CL, int TC, int MINB, int DIR, class Pass, class LoadOp, class StoreOp>
+template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
 int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, LoadOp lop, StoreOp sop, cudaStream_t st) {
-  using Cfg = ColsCfg<T, N, CL, TC>;
+  using Cfg = ColsCfg<T, N, CL, TC, SEL>;
   g.tiles_per_batch = (int) ((g.ncols + TC - 1) / TC);
   const long ntiles = (long) g.tiles_per_batch * nbatch;
   if (ntiles <= 0) return 0;
-  auto kern = fft_cols_kernel<T, N, CL, TC, MINB, DIR, Pass, LoadOp, StoreOp>;
+  auto kern = fft_cols_kernel<T, N, CL, TC, MINB, SEL, DIR, Pass, LoadOp, StoreOp>;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(Cfg::threads);
   cfg.dynamicSmemBytes = Cfg::smem;
@@ -270,7 +283,7 @@ int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, Load
       fprintf(stderr, "[gx] fft_cols<N=%d,CL=%d,TC=%d,%zu-byte elems>: %d resident clusters, %zu KB smem/CTA, %d threads\n", N, CL,
               TC, sizeof(cplx<T>), max_clusters, Cfg::smem / 1024, Cfg::threads);
   }
-  const int nclusters = (int) (ntiles < max_clusters ? ntiles : max_clusters);
+  const int nclusters = (int) ((ntiles < max_clusters || Cfg::NBUF == 1) ? ntiles : max_clusters);
   cfg.gridDim = dim3((unsigned) nclusters * CL);
   const char *tname = std::is_same<Pass, PassY>::value ? "fft_cols_y" : "fft_cols_x";
   GX_TIMED(tname, st);
@@ -296,7 +309,7 @@ int launch_cols(const cplx<T> *src, cplx<T> *dst, int n0, int n1, int nc, LoadOp
   using PL = ColsPlan<T, N>;
   int nbatch;
   ColGeo g = make_col_geo<Pass>(n0, n1, nc, nbatch);
-  return launch_cols_cfg<T, N, PL::CL, PL::TC, PL::MINB, DIR, Pass, LoadOp, StoreOp>(src, dst, g, nbatch, lop, sop, st);
+  return launch_cols_cfg<T, N, PL::CL, PL::TC, PL::MINB, PL::SEL, DIR, Pass, LoadOp, StoreOp>(src, dst, g, nbatch, lop, sop, st);
 }
 
 // ---- row passes (z axis, contiguous): r2c and c2r through a half-length complex FFT ---------------
@@ -306,17 +319,19 @@ template <typename T, int N> struct RowsCfg {
   static constexpr int P = B::P;
   static constexpr int pitch = line_pitch<T>(M) + 1;  // >= M + 1 entries (the c2r input has M + 1)
   static constexpr size_t per_row = (size_t) pitch * sizeof(cplx<T>);
-  static constexpr int byThreads = (256 / P) > 0 ? (256 / P) : 1;
-  static constexpr int bySmem = (int) ((72 * 1024) / per_row) > 0 ? (int) ((72 * 1024) / per_row) : 1;
+  // 128-thread CTAs (<= 37 KB of shared memory each) so that five are resident per SM in different phases
+  static constexpr int byThreads = (128 / P) > 0 ? (128 / P) : 1;
+  static constexpr int bySmem = (int) ((40 * 1024) / per_row) > 0 ? (int) ((40 * 1024) / per_row) : 1;
   static constexpr int LR = byThreads < bySmem ? byThreads : bySmem;
   static constexpr int threads = LR * P;
+  static constexpr int MINB = (threads <= 128 && sizeof(T) == 8) ? 5 : 1;
   static constexpr size_t smem = (size_t) LR * per_row;
 };
 
 // Forward: each row of N reals (viewed as M = N/2 complex z[m] = x[2m] + i x[2m+1]) -> N/2+1 complex, in place.
 //   X[k] = 1/2 (Z[k] + conj Z[M-k]) - i/2 W_N^k (Z[k] - conj Z[M-k]),  k = 0..M,  Z[M] == Z[0]
 template <typename T, int N>
-__global__ void __launch_bounds__(RowsCfg<T, N>::threads)
+__global__ void __launch_bounds__(RowsCfg<T, N>::threads, RowsCfg<T, N>::MINB)
 fft_rows_r2c_kernel(T *data, long nrows, const cplx<T> *__restrict__ twM, const cplx<T> *__restrict__ twN) {
   using C = cplx<T>;
   using Cfg = RowsCfg<T, N>;
@@ -365,7 +380,7 @@ template <typename T> struct StoreRealScaled {
 //   Zt[k] = (X[k] + conj X[M-k]) + i W_N^{-k} (X[k] - conj X[M-k]),  z = IFFT_M(Zt),  x[2m] = Re z[m], x[2m+1] = Im z[m]
 // The imaginary parts of X[0] and X[M] are ignored, as FFTW's c2r does.
 template <typename T, int N, class Store>
-__global__ void __launch_bounds__(RowsCfg<T, N>::threads)
+__global__ void __launch_bounds__(RowsCfg<T, N>::threads, RowsCfg<T, N>::MINB)
 fft_rows_c2r_kernel(const T *data, long row0, long nrows, const cplx<T> *__restrict__ twM,
                     const cplx<T> *__restrict__ twN, Store store) {
   using C = cplx<T>;

@@ -120,9 +120,11 @@ template <int R, int DIR, typename T> GX_HD void butterfly(cplx<T> *a) {
 }
 
 // ---- per-length plan: radices (largest first), E = radices[0]
-template <int NC> struct Plan;
+// SEL = 0: fewest stages (16 points per thread where possible). SEL = 1: 8 points per thread -- half the registers and
+// twice the threads per line, for kernels that need more warps in flight (the f64 column passes).
+template <int NC, int SEL = 0> struct Plan : Plan<NC, 0> {};
 #define GX_PLAN(N_, S_, R0, R1, R2)                                  \
-  template <> struct Plan<N_> {                                      \
+  template <> struct Plan<N_, 0> {                                   \
     static constexpr int S = S_;                                     \
     GX_HD static constexpr int radix(int s) { return s == 0 ? R0 : (s == 1 ? R1 : R2); } \
   };
@@ -139,6 +141,11 @@ GX_PLAN(1024, 3, 16, 8, 8)
 GX_PLAN(2048, 3, 16, 16, 8)
 GX_PLAN(4096, 3, 16, 16, 16)
 #undef GX_PLAN
+template <> struct Plan<256, 1> {
+  static constexpr int S = 3;
+  GX_HD static constexpr int radix(int s) { return s == 0 ? 8 : (s == 1 ? 8 : 4); }
+};
+
 
 // shared-memory index skew: one pad element every SKEW elements keeps power-of-two strides off the
 // same banks (SKEW elements == 128 bytes == one full bank row)
@@ -149,9 +156,9 @@ template <typename T> GX_HD constexpr int line_pitch(int nc) { return nc + nc / 
 // LS = 0: the line is contiguous in shared memory with the bank skew above (row passes).
 // LS > 0: element p of the line lives at line[p * LS] (column passes: LS adjacent columns are interleaved,
 //         so a warp touches LS * sizeof(C) contiguous bytes per line position and no skew is needed).
-template <typename T, int NC, int DIR, int LS = 0> struct BlockFFT {
+template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT {
   using C = cplx<T>;
-  using PL = Plan<NC>;
+  using PL = Plan<NC, SEL>;
   static constexpr int S = PL::S;
   static constexpr int E = PL::radix(0);
   static constexpr int P = NC / E;

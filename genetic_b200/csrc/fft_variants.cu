@@ -6,7 +6,7 @@
 using namespace gx;
 using namespace gx::fft;
 
-template <int N, int CL, int TC, int MINB> static int run_variant(void *field, int pass, cudaStream_t st) {
+template <int N, int CL, int TC, int MINB, int SEL = 0> static int run_variant(void *field, int pass, cudaStream_t st) {
   using T = double;
   using C = cplx<T>;
   if (int rc = ensure_twiddles()) return rc;
@@ -14,31 +14,31 @@ template <int N, int CL, int TC, int MINB> static int run_variant(void *field, i
   int nbatch;
   if (pass == 0) {
     ColGeo g = make_col_geo<PassX>(N, N, N / 2 + 1, nbatch);
-    return launch_cols_cfg<T, N, CL, TC, MINB, 1, PassX>(d, d, g, nbatch, OpIdentity<T>(), OpIdentity<T>(), st);
+    return launch_cols_cfg<T, N, CL, TC, MINB, SEL, 1, PassX>(d, d, g, nbatch, OpIdentity<T>(), OpIdentity<T>(), st);
   }
   ColGeo g = make_col_geo<PassY>(N, N, N / 2 + 1, nbatch);
-  return launch_cols_cfg<T, N, CL, TC, MINB, 1, PassY>(d, d, g, nbatch, OpIdentity<T>(), OpIdentity<T>(), st);
+  return launch_cols_cfg<T, N, CL, TC, MINB, SEL, 1, PassY>(d, d, g, nbatch, OpIdentity<T>(), OpIdentity<T>(), st);
 }
 
 extern "C" int gx_dev_fft_cols_variant(void *field, int n, int pass, int variant, void *stream) {
   cudaStream_t st = (cudaStream_t) stream;
   if (n == 2048) {
     switch (variant) {
-      case 0: return run_variant<2048, 8, 8, 3>(field, pass, st);
-      case 1: return run_variant<2048, 8, 8, 2>(field, pass, st);
-      case 2: return run_variant<2048, 8, 16, 1>(field, pass, st);
-      case 3: return run_variant<2048, 8, 4, 6>(field, pass, st);
-      case 4: return run_variant<2048, 16, 8, 3>(field, pass, st);
-      case 5: return run_variant<2048, 16, 16, 3>(field, pass, st);
+      case 0: return run_variant<2048, 8, 8, 4, 4>(field, pass, st);
+      case 1: return run_variant<2048, 8, 8, 5, 4>(field, pass, st);
+      case 2: return run_variant<2048, 8, 8, 6, 4>(field, pass, st);
+      case 3: return run_variant<2048, 16, 8, 8, 4>(field, pass, st);
+      case 4: return run_variant<2048, 16, 8, 10, 4>(field, pass, st);
+      case 5: return run_variant<2048, 16, 16, 4, 4>(field, pass, st);
     }
   } else if (n == 1024) {
     switch (variant) {
-      case 0: return run_variant<1024, 4, 8, 3>(field, pass, st);
-      case 1: return run_variant<1024, 4, 8, 2>(field, pass, st);
-      case 2: return run_variant<1024, 4, 16, 1>(field, pass, st);
-      case 3: return run_variant<1024, 4, 4, 6>(field, pass, st);
-      case 4: return run_variant<1024, 8, 8, 3>(field, pass, st);
-      case 5: return run_variant<1024, 8, 16, 3>(field, pass, st);
+      case 0: return run_variant<1024, 4, 8, 4, 4>(field, pass, st);
+      case 1: return run_variant<1024, 4, 8, 5, 4>(field, pass, st);
+      case 2: return run_variant<1024, 4, 8, 6, 4>(field, pass, st);
+      case 3: return run_variant<1024, 8, 8, 8, 4>(field, pass, st);
+      case 4: return run_variant<1024, 8, 8, 10, 4>(field, pass, st);
+      case 5: return run_variant<1024, 8, 16, 4, 4>(field, pass, st);
     }
   }
   return gx::fail("gx_dev_fft_cols_variant: unknown variant");

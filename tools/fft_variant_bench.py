@@ -7,8 +7,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from genetic_b200 import lib as L
 
-NAMES = {2048: ["CL8 TC8 minb3", "CL8 TC8 minb2", "CL8 TC16 minb1", "CL8 TC4 minb6", "CL16 TC8 minb3", "CL16 TC16 minb3"],
-         1024: ["CL4 TC8 minb3", "CL4 TC8 minb2", "CL4 TC16 minb1", "CL4 TC4 minb6", "CL8 TC8 minb3", "CL8 TC16 minb3"]}
+NAMES = {2048: ["CL8 TC8 minb4 1buf", "CL8 TC8 minb5 1buf", "CL8 TC8 minb6 1buf", "CL16 TC8 minb8 1buf", "CL16 TC8 minb10 1buf", "CL16 TC16 minb4 1buf"],
+         1024: ["CL4 TC8 minb4 1buf", "CL4 TC8 minb5 1buf", "CL4 TC8 minb6 1buf", "CL8 TC8 minb8 1buf", "CL8 TC8 minb10 1buf", "CL8 TC16 minb4 1buf"]}
 
 
 def main():
@@ -36,12 +36,12 @@ def main():
             for ps, pname in ((0, "x"), (1, "y")):
                 rc = fn(p, n, ps, v, None)
                 if rc != 0:
-                    print("n=%d %-16s pass %s: FAILED %s" % (n, name, pname, lib.gx_last_error().decode()), flush=True)
+                    print("n=%d %-30s pass %s: FAILED %s" % (n, name, pname, lib.gx_last_error().decode()), flush=True)
                     continue
                 try:
                     lib.gx_synchronize(None)
                 except Exception as e:
-                    print("n=%d %-16s pass %s: FAILED %s" % (n, name, pname, e), flush=True)
+                    print("n=%d %-30s pass %s: FAILED %s" % (n, name, pname, e), flush=True)
                     continue
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 reps = 5
@@ -51,7 +51,7 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / reps
-                print("n=%d %-16s pass %s: %8.3f ms  %7.1f GB/s" % (n, name, pname, ms, 2 * nbytes / ms / 1e6), flush=True)
+                print("n=%d %-30s pass %s: %8.3f ms  %7.1f GB/s" % (n, name, pname, ms, 2 * nbytes / ms / 1e6), flush=True)
         lib.gx_free(p)
 
 
