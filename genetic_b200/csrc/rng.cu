@@ -164,20 +164,30 @@ __device__ __forceinline__ void cursor_init(const Dest<T> &d, const StreamDesc &
 template <typename T> __device__ __forceinline__ void cursor_advance(const Dest<T> &d, Cursor &cu) {
   if (d.mode == MODE_LIST) return;
   if (d.mode == MODE_REAL) {
-    if (++cu.z == d.n) { cu.z = 0; ++cu.row; }
+    const bool wrap = (cu.z + 1 == d.n);
+    cu.z = wrap ? 0 : cu.z + 1;
+    cu.row += wrap ? 1 : 0;
     return;
   }
+  // nested counters (comp fastest, then face, q, p, shell) as carries instead of branches
+  const int c0 = cu.comp;                       // carry out of comp
   cu.comp ^= 1;
-  if (cu.comp) return;
-  if (++cu.face < 3) return;
-  cu.face = 0;
-  if (++cu.q < cu.ks) return;
-  cu.q = -cu.ks;
-  if (++cu.p < cu.ks) return;
-  ++cu.ks;  // serial order: on to the next shell (a per-shell stream ends here)
-  cu.p = cu.q = -cu.ks;
+  const int face1 = cu.face + c0;
+  const int c1 = (face1 == 3);
+  cu.face = c1 ? 0 : face1;
+  const int q1 = cu.q + c1;
+  const int c2 = (q1 == cu.ks);
+  cu.q = c2 ? -cu.ks : q1;
+  const int p1 = cu.p + c2;
+  const int c3 = (p1 == cu.ks);
+  // serial order: on to the next shell (a per-shell stream simply ends here)
+  cu.ks += c3;
+  cu.p = c3 ? -cu.ks : p1;
+  cu.q = c3 ? -cu.ks : cu.q;
 }
 
+// Branch-free on purpose: neighbouring lanes sit at different (face, re/im, sign of kz) phases of the draw loops, so
+// every branch here used to be executed serially for 6+ lane groups (ncu: 9 of 32 threads active on average).
 template <typename T>
 __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, long long g, double value) {
   if (d.mode == MODE_LIST) { d.list[g] = value; return; }
@@ -187,23 +197,39 @@ __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, l
     return;
   }
   const int ks = cu.ks, p = cu.p, q = cu.q, face = cu.face, comp = cu.comp;
-  int k1, k2, k3;
-  if (face == 0) { k1 = ks; k2 = p; k3 = q; }
-  else if (face == 1) { k1 = p; k2 = ks; k3 = q; }
-  else { k1 = p; k2 = q; k3 = ks; }
-  // last-writer-wins: the conjugate partner -k may be drawn in the same shell
-  const long long c = ((long long) (p + ks) * (2 * ks) + (q + ks)) * 3 + face;
-  const long long cp = call_index_in_shell(ks, -k1, -k2, -k3);
-  if (cp > c) return;
+  // drawOneFourierMode is called for (ks,p,q), (p,ks,q), (p,q,ks) in turn
+  const int k1 = (face == 0) ? ks : p;
+  const int k2 = (face == 0) ? p : ((face == 1) ? ks : q);
+  const int k3 = (face == 2) ? ks : q;
+  // last-writer-wins: the conjugate partner -k is drawn in the same shell iff exactly one of its coordinates equals
+  // +ks (i.e. one of ours equals -ks) and the other two lie in [-ks, ks-1] (ours in [-ks+1, ks])
+  const int a = -k1, b = -k2, c3 = -k3;
+  const int np = (a == ks) + (b == ks) + (c3 == ks);
+  const int pface = (a == ks) ? 0 : ((b == ks) ? 1 : 2);
+  const int pp = (pface == 0) ? b : a;
+  const int pq = (pface == 2) ? b : c3;
+  const bool partner_drawn = (np == 1) && (pp >= -ks) && (pp < ks) && (pq >= -ks) && (pq < ks);
+  const int twoks = 2 * ks;
+  const int c_self = ((p + ks) * twoks + (q + ks)) * 3 + face;      // < 3 * 4096^2: fits an int
+  const int c_partner = ((pp + ks) * twoks + (pq + ks)) * 3 + pface;
+  const bool write = !(partner_drawn && c_partner > c_self);
   // value of this component in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2))
-  const T v = (T) GX_DMUL(d.sigma, value);
+  T v = (T) GX_DMUL(d.sigma, value);
   // normal order: (a, b) -> (re, im); reverse: (b, a)
   const int part = d.reverse ? (1 - comp) : comp;
-  // setFourierCoefficient(k, val): stored at the kz >= 0 representative, imaginary part negated if conjugated
-  if (k3 < 0) store_part<T>(d.field, n, -k1, -k2, -k3, part, part == 1 ? -v : v);
-  else store_part<T>(d.field, n, k1, k2, k3, part, v);
+  // setFourierCoefficient(k, val): stored at the kz >= 0 representative, imaginary part negated if conjugated;
   // the explicit second write, setFourierCoefficient(-k, conj(val)), lands on a different slot only when k3 == 0
-  if (k3 == 0) store_part<T>(d.field, n, -k1, -k2, 0, part, part == 1 ? -v : v);
+  const bool neg = k3 < 0;
+  const int s1 = neg ? -k1 : k1, s2 = neg ? -k2 : k2, s3 = neg ? -k3 : k3;
+  const T vconj = (part == 1) ? -v : v;
+  const int nc = n / 2 + 1;
+  const size_t slot = (size_t) s3 + (size_t) nc * ((size_t) (s2 < 0 ? s2 + n : s2) + (size_t) n * (size_t) (s1 < 0 ? s1 + n : s1));
+  if (write) d.field[2 * slot + part] = neg ? vconj : v;
+  if (write && k3 == 0) {
+    const int t1 = -k1, t2 = -k2;
+    const size_t slot2 = (size_t) nc * ((size_t) (t2 < 0 ? t2 + n : t2) + (size_t) n * (size_t) (t1 < 0 ? t1 + n : t1));
+    d.field[2 * slot2 + part] = vconj;
+  }
 }
 
 template <typename T>
@@ -242,8 +268,13 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
   __shared__ uint32_t ring[48][kThreads];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_k[i] = d_zig_ktab[i]; s_w[i] = d_zig_wtab[i]; s_y[i] = d_zig_ytab[i]; }
   __syncthreads();
-  const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chunk >= P.n_chunks) return;
+  // No lane leaves before the end: every increment starts with a __syncwarp so that the 397-step generator advance
+  // runs with the whole warp converged (lanes that had left early or sat in different parse branches used to run it
+  // in 5-lane groups -- 70% of all issued instructions of pass B, ncu r1p).
+  const int chunk_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = chunk_raw < P.n_chunks;
+  const int chunk = in_range ? chunk_raw : P.n_chunks - 1;
+  bool live = in_range;
   int sid = 0;
   {  // the stream this chunk belongs to: last stream with first_chunk <= chunk
     int lo = 0, hi = P.n_streams - 1;
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
     ncur = 1;
     pos[0] = first ? sd.entry0 : ss.entry;
     g = first ? 0 : ss.base;
-    if (g >= sd.n_gauss) return;  // nothing wanted from this chunk
+    if (g >= sd.n_gauss) live = false;  // nothing wanted from this chunk
   }
 
   Cursor cu;
@@ -282,6 +313,7 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
   State st = chunk_start_state(sd, q, P.jump);
 
   for (int bi = 0; bi <= kBc; ++bi) {
+    __syncwarp();
     advance_block(st);
     const int half = (bi & 1) * 24;
 #pragma unroll
@@ -291,7 +323,7 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
     for (int e = 0; e < ncur; ++e) {
       if (PASS == 0 && rep[e] >= 0) continue;
       int p = pos[e];
-      while (p < limit) {
+      while (live && p < limit) {
         const Attempt a = zig_attempt(ring[p % 48][tx], ring[(p + 1) % 48][tx], ring[(p + 2) % 48][tx],
                                       ring[(p + 3) % 48][tx], s_k, s_w, s_y);
         p += a.consumed;
@@ -326,10 +358,10 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
         }
       }
     }
-    if (PASS == 1 && g >= sd.n_gauss) break;
+    if (PASS == 1 && g >= sd.n_gauss) live = false;
   }
 
-  if (PASS == 0) {
+  if (PASS == 0 && in_range) {
     ChunkFn f;
     f.reset = first ? 1 : 0;
     for (int e = 0; e < 4; ++e) {
