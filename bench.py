@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "512")))
+    ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "2048")))
     ap.add_argument("--cpu-n", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

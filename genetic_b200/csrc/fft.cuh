@@ -49,10 +49,32 @@ template <typename T> struct OpScale {
 struct PassY {};
 struct PassX {};
 
+// Where line position `row` of a batch lives: (row >> blk_shift) * blk_stride + (row & blk_mask) * line_stride.
+// The plain layouts use one block (blk_shift = 30). The slab-decomposed y-pass reads (inverse) or writes (forward) the
+// all-to-all exchange buffer directly -- [peer][x_local][ky_local][kz] -- so no pack/unpack sweep exists.
+struct LineMap {
+  long line_stride;    // elements between consecutive line positions inside a block
+  long batch_stride;   // elements between batches
+  long blk_stride;     // elements between blocks of line positions
+  int blk_shift, blk_mask;
+  __host__ __device__ __forceinline__ long off(int row) const {
+    return (long) (row >> blk_shift) * blk_stride + (long) (row & blk_mask) * line_stride;
+  }
+};
+inline LineMap plain_map(long line_stride, long batch_stride) {
+  LineMap m; m.line_stride = line_stride; m.batch_stride = batch_stride; m.blk_stride = 0; m.blk_shift = 30; m.blk_mask = 0x3fffffff;
+  return m;
+}
+inline LineMap blocked_map(long line_stride, long batch_stride, int rows_per_block, long blk_stride) {
+  LineMap m; m.line_stride = line_stride; m.batch_stride = batch_stride; m.blk_stride = blk_stride;
+  m.blk_shift = 0; while ((1 << m.blk_shift) < rows_per_block) ++m.blk_shift;
+  m.blk_mask = rows_per_block - 1;
+  return m;
+}
+
 struct ColGeo {
   long ncols;          // columns per batch
-  long line_stride;    // elements between consecutive line positions
-  long batch_stride;   // elements between batches
+  LineMap src, dst;
   int tiles_per_batch;
   int nc;              // fastest extent (n/2+1)
 };
@@ -144,11 +166,11 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
     const int batch = (int) (tile / g.tiles_per_batch);
     const long col = (tile % g.tiles_per_batch) * TC + c;
     const bool active = col < g.ncols;
-    const C *p = src + ((long) batch * g.batch_stride + (active ? col : 0));
+    const C *p = src + ((long) batch * g.src.batch_stride + (active ? col : 0));
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       const int row = (CL > 1) ? q + CL * (t + i * P) : t + i * P;
-      cp_async_elem<C>(buf + (t + i * P) * TC + c, p + (long) row * g.line_stride, active);
+      cp_async_elem<C>(buf + (t + i * P) * TC + c, p + g.src.off(row), active);
     }
     cp_async_commit();
   };
@@ -172,14 +194,14 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
     int c1 = 0, c2;  // storage indices that do not depend on the line position
     if (std::is_same<Pass, PassY>::value) { c2 = (int) col; }
     else { c1 = (int) (col / g.nc); c2 = (int) (col - (long) c1 * g.nc); }
-    const long base = (long) batch * g.batch_stride + col;
+    const long base = (long) batch * g.dst.batch_stride + col;
     auto load_op = [&](C x, int row) -> C {
       return std::is_same<Pass, PassY>::value ? lop(x, batch, row, c2) : lop(x, row, c1, c2);
     };
     auto store = [&](int row, C val) {
       if (active) {
         C y = std::is_same<Pass, PassY>::value ? sop(val, batch, row, c2) : sop(val, row, c1, c2);
-        dst[base + (long) row * g.line_stride] = y;
+        dst[base + g.dst.off(row)] = y;
       }
     };
 
@@ -298,8 +320,9 @@ template <class Pass> inline ColGeo make_col_geo(int n0, int n1, int nc, int &nb
   ColGeo g;
   g.nc = nc;
   g.tiles_per_batch = 0;
-  if (std::is_same<Pass, PassY>::value) { g.ncols = nc; g.line_stride = nc; g.batch_stride = (long) n1 * nc; nbatch = n0; }
-  else { g.ncols = (long) n1 * nc; g.line_stride = (long) n1 * nc; g.batch_stride = 0; nbatch = 1; }
+  if (std::is_same<Pass, PassY>::value) { g.ncols = nc; g.src = plain_map(nc, (long) n1 * nc); nbatch = n0; }
+  else { g.ncols = (long) n1 * nc; g.src = plain_map((long) n1 * nc, 0); nbatch = 1; }
+  g.dst = g.src;
   return g;
 }
 
@@ -448,3 +471,20 @@ int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStrea
 
 }  // namespace fft
 }  // namespace gx
+
+#define GX_N_SWITCH(n, CALL)                                                                                     \
+  switch (n) {                                                                                                   \
+    case 4: { constexpr int N = 4; return CALL; }                                                                \
+    case 8: { constexpr int N = 8; return CALL; }                                                                \
+    case 16: { constexpr int N = 16; return CALL; }                                                              \
+    case 32: { constexpr int N = 32; return CALL; }                                                              \
+    case 64: { constexpr int N = 64; return CALL; }                                                              \
+    case 128: { constexpr int N = 128; return CALL; }                                                            \
+    case 256: { constexpr int N = 256; return CALL; }                                                            \
+    case 512: { constexpr int N = 512; return CALL; }                                                            \
+    case 1024: { constexpr int N = 1024; return CALL; }                                                          \
+    case 2048: { constexpr int N = 2048; return CALL; }                                                          \
+    case 4096: { constexpr int N = 4096; return CALL; }                                                          \
+    default: return fail("grid size must be a power of two in [4,4096]");                                        \
+  }
+

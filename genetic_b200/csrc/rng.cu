@@ -78,8 +78,12 @@ template <typename T> struct Dest {
   int n;
   int reverse;
   double sigma;      // FloatType sigma = 1.0 / sqrt(2.0) (randomfieldgenerator.hpp:213), widened to double
-  T *field;          // padded field (real or Fourier layout)
+  T *field;          // padded field (real or Fourier layout), or this rank's slab of it
   double *list;      // MODE_LIST: plain gaussian list (test hook)
+  // slab ownership (multi-GPU): Fourier orders keep the modes with storage index iy in [iy0, iy0 + ny) in a
+  // [n][ny][n/2+1] array; the real order keeps rows (x*n + y) in [row0, row0 + nrows). Whole field: 0, n / 0, n*n.
+  int iy0, ny;
+  long long row0, nrows;
 };
 
 __device__ __forceinline__ ChunkFn compose(const ChunkFn &f, const ChunkFn &g) {  // f first, then g
@@ -193,7 +197,8 @@ __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, l
   if (d.mode == MODE_LIST) { d.list[g] = value; return; }
   const int n = d.n;
   if (d.mode == MODE_REAL) {
-    d.field[cu.row * (n + 2) + cu.z] = (T) value;
+    const long long r = cu.row - d.row0;
+    if (r >= 0 && r < d.nrows) d.field[r * (n + 2) + cu.z] = (T) value;
     return;
   }
   const int ks = cu.ks, p = cu.p, q = cu.q, face = cu.face, comp = cu.comp;
@@ -223,12 +228,14 @@ __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, l
   const int s1 = neg ? -k1 : k1, s2 = neg ? -k2 : k2, s3 = neg ? -k3 : k3;
   const T vconj = (part == 1) ? -v : v;
   const int nc = n / 2 + 1;
-  const size_t slot = (size_t) s3 + (size_t) nc * ((size_t) (s2 < 0 ? s2 + n : s2) + (size_t) n * (size_t) (s1 < 0 ? s1 + n : s1));
-  if (write) d.field[2 * slot + part] = neg ? vconj : v;
+  const int j2 = (s2 < 0 ? s2 + n : s2) - d.iy0;
+  const size_t slot = (size_t) s3 + (size_t) nc * ((size_t) j2 + (size_t) d.ny * (size_t) (s1 < 0 ? s1 + n : s1));
+  if (write && j2 >= 0 && j2 < d.ny) d.field[2 * slot + part] = neg ? vconj : v;
   if (write && k3 == 0) {
     const int t1 = -k1, t2 = -k2;
-    const size_t slot2 = (size_t) nc * ((size_t) (t2 < 0 ? t2 + n : t2) + (size_t) n * (size_t) (t1 < 0 ? t1 + n : t1));
-    d.field[2 * slot2 + part] = vconj;
+    const int u2 = (t2 < 0 ? t2 + n : t2) - d.iy0;
+    const size_t slot2 = (size_t) nc * ((size_t) u2 + (size_t) d.ny * (size_t) (t1 < 0 ? t1 + n : t1));
+    if (u2 >= 0 && u2 < d.ny) d.field[2 * slot2 + part] = vconj;
   }
 }
 
@@ -628,13 +635,18 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   return 0;
 }
 
+// world == 1: the whole field. world > 1: rank's slab only -- Fourier orders fill the ky-slab [n][n/world][nc] (every
+// rank walks every stream and keeps the draws it owns), the real order fills the x-slab and stays in real space (the
+// caller runs the slab-decomposed r2c and zeroes Re(DC)).
 template <typename T>
 static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int reverse, unsigned long long *offset_io,
-                        cudaStream_t cs) {
-  const size_t bytes = (size_t) 2 * n * n * (n / 2 + 1) * sizeof(T);
+                        cudaStream_t cs, int world = 1, int rank = 0) {
+  const size_t bytes = (size_t) 2 * n * n * (n / 2 + 1) * sizeof(T) / (size_t) world;
   GX_CUDA_CHECK(cudaMemsetAsync(field, 0, bytes, cs));
   Dest<T> dest;
   dest.n = n; dest.reverse = reverse; dest.field = (T *) field; dest.list = nullptr;
+  dest.ny = n / world; dest.iy0 = rank * dest.ny;
+  dest.nrows = (long long) n * n / world; dest.row0 = rank * dest.nrows;
   dest.sigma = (double) (T) (1.0 / sqrt(2.0));
   const long long n3 = (long long) n * n * n;
   const unsigned long long start = offset_io ? *offset_io : 0ull;
@@ -655,7 +667,7 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
   }
   int rc = run_streams<T>(reqs, dest, &ends, cs);
   if (rc) return rc;
-  if (mode == GX_NOISE_REAL) {
+  if (mode == GX_NOISE_REAL && world == 1) {
     rc = fft::fft3d<T>((T *) field, n, -1, cs);
     if (rc) return rc;
     zero_dc_real_kernel<T><<<1, 1, 0, cs>>>((T *) field);  // tools::set_zero(fieldData[0]) :195
@@ -679,6 +691,15 @@ int gx_noise_draw(void *field, int n, int dtype, unsigned long seed, int mode, i
   if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
   if (dtype == GX_F64) return noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
   if (dtype == GX_F32) return noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
+  return gx::fail("bad dtype");
+}
+
+int gx_slab_noise_draw(void *slab, int n, int dtype, int world, int rank, unsigned long seed, int mode,
+                       int reverse_order, unsigned long long *stream_offset_io, void *stream) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (world < 1 || n % world != 0 || rank < 0 || rank >= world) return gx::fail("gx_slab_noise_draw: bad world/rank");
+  if (dtype == GX_F64) return noise_draw_t<double>(slab, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream, world, rank);
+  if (dtype == GX_F32) return noise_draw_t<float>(slab, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream, world, rank);
   return gx::fail("bad dtype");
 }
 
@@ -710,6 +731,7 @@ int gx_rng_gaussians(unsigned long seed, long n, double *host_out, unsigned long
   GX_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * (size_t) n));
   Dest<double> dest;
   dest.mode = MODE_LIST; dest.n = 0; dest.reverse = 0; dest.field = nullptr; dest.list = d; dest.sigma = 1.0;
+  dest.iy0 = 0; dest.ny = 0; dest.row0 = 0; dest.nrows = 0;
   std::vector<StreamReq> reqs;
   reqs.push_back({seed, raw_consumed ? *raw_consumed : 0ull, (long long) n, 0});
   std::vector<unsigned long long> ends;

@@ -201,12 +201,12 @@ template <typename T> static int covariance_field_t(void *out, int n, double L, 
 
 template <typename T>
 static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, double power, cudaStream_t st,
-                            int divide_k2 = 0) {
+                            int divide_k2 = 0, int iy0 = 0, int ny = -1) {
   ApplyTransferF<T> f;
   f.sp = gx_spectrum_device_view(s);
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n); f.power = power;
   f.divide_k2 = divide_k2;
-  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double), "apply_transfer");
+  return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double), "apply_transfer", iy0, ny);
 }
 
 template <typename T> static int apply_transfer_field_t(void *field, const void *cov, int n, double power, cudaStream_t st) {
@@ -239,10 +239,20 @@ static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, in
 
 namespace gx {
 int apply_transfer_ex(void *field, int n, int dtype, double L, const gx_spectrum *s, double power, int divide_k2,
-                      cudaStream_t st) {
+                      cudaStream_t st, int iy0, int ny) {
   if (check_n(n)) return 1;
-  if (dtype == GX_F64) return apply_transfer_t<double>(field, n, L, s, power, st, divide_k2);
-  if (dtype == GX_F32) return apply_transfer_t<float>(field, n, L, s, power, st, divide_k2);
+  if (dtype == GX_F64) return apply_transfer_t<double>(field, n, L, s, power, st, divide_k2, iy0, ny);
+  if (dtype == GX_F32) return apply_transfer_t<float>(field, n, L, s, power, st, divide_k2, iy0, ny);
+  return fail("bad dtype");
+}
+template <typename T> static int unit_variance_slab_t(void *field, int n, int iy0, int ny, cudaStream_t st) {
+  UnitVarianceF<T> f;
+  f.f = (cplx<T> *) field; f.n = n;
+  return launch_slot_sweep(n, f, st, 0, "unit_variance", iy0, ny);
+}
+int unit_variance_slab(void *field, int n, int dtype, int iy0, int ny, cudaStream_t st) {
+  if (dtype == GX_F64) return unit_variance_slab_t<double>(field, n, iy0, ny, st);
+  if (dtype == GX_F32) return unit_variance_slab_t<float>(field, n, iy0, ny, st);
   return fail("bad dtype");
 }
 }  // namespace gx

@@ -98,26 +98,31 @@ template <typename T> __device__ __forceinline__ T spec_pow(T spec, double power
   return spec;
 }
 
-// ---- slot sweep: grid.y = ix, grid.x * blockDim.x covers the n*nc slots of one x-plane ---------------
-template <class F> __global__ void __launch_bounds__(256) slot_sweep_kernel(int n, int nc, F f) {
+// ---- slot sweep: grid.y = ix, grid.x * blockDim.x covers the ny*nc slots of one x-plane ---------------
+// The functor sees the global storage indices (ix, iy, iz) and the element offset s in the array it was given: the
+// whole field [n][n][nc] (iy0 = 0, ny = n) or one rank's ky-slab [n][ny][nc] holding iy in [iy0, iy0 + ny).
+template <class F> __global__ void __launch_bounds__(256) slot_sweep_kernel(int n, int nc, int iy0, int ny, F f) {
   const int ix = blockIdx.y;
-  const int plane = n * nc;
+  const int plane = ny * nc;
   f.init();  // optional per-CTA prologue (e.g. stage a table in shared memory); must be called by all threads
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += gridDim.x * blockDim.x) {
-    const int iy = i / nc;
-    const int iz = i - iy * nc;
-    f(ix, iy, iz, (size_t) ix * plane + i);
+    const int iyl = i / nc;
+    const int iz = i - iyl * nc;
+    f(ix, iy0 + iyl, iz, (size_t) ix * plane + i);
   }
 }
 
-template <class F> int launch_slot_sweep(int n, F f, cudaStream_t st, size_t smem = 0, const char *name = "slot_sweep") {
+template <class F>
+int launch_slot_sweep(int n, F f, cudaStream_t st, size_t smem = 0, const char *name = "slot_sweep", int iy0 = 0,
+                      int ny = -1) {
   GX_TIMED(name, st);
   const int nc = n / 2 + 1;
-  const int plane = n * nc;
+  if (ny < 0) ny = n;
+  const int plane = ny * nc;
   int bx = (plane + 255) / 256;
   if (bx > 64) bx = 64;  // 64 x n CTAs: >= 4 waves of 148 SMs from n = 16 upward
   dim3 grid(bx, n);
-  slot_sweep_kernel<F><<<grid, 256, smem, st>>>(n, nc, f);
+  slot_sweep_kernel<F><<<grid, 256, smem, st>>>(n, nc, iy0, ny, f);
   count_launch();
   GX_LAUNCH_CHECK();
   return 0;

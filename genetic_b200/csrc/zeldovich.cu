@@ -84,14 +84,23 @@ template <typename T, typename O> struct StoreEmit {
   }
 };
 
+// order 0: x-pass (fused load, out of place) then y-pass in place.
+// order 1: y-pass (fused load, out of place) then x-pass in place. The two 1-D transforms commute; which one carries the
+// out-of-place operator matters for HBM: a 2048^3 x-line visits 2048 distinct 2 MB pages, and reading delta_k while
+// writing the work field doubles that footprint, whereas a y-pass tile spans 16 pages.
 template <typename T, int N, bool PREDIV>
-static int zeldovich_xy_n(const void *delta_k, void *work, double L, int axis, cudaStream_t st) {
+static int zeldovich_xy_n(const void *delta_k, void *work, double L, int axis, int order, cudaStream_t st) {
   using namespace fft;
   using C = cplx<T>;
   const int nc = N / 2 + 1;
   OpZeldovichMirror<T, PREDIV> op;
   op.delta = (const C *) delta_k; op.n = N; op.nc = nc; op.axis = axis;
   op.kmin = (T) (2. * M_PI / (double) (T) L);
+  if (order == 1) {
+    int rc = launch_cols<T, N, 1, PassY>((const C *) delta_k, (C *) work, N, N, nc, op, OpIdentity<T>(), st);
+    if (rc) return rc;
+    return launch_cols<T, N, 1, PassX>((const C *) work, (C *) work, N, N, nc, OpIdentity<T>(), OpIdentity<T>(), st);
+  }
   int rc = launch_cols<T, N, 1, PassX>((const C *) delta_k, (C *) work, N, N, nc, op, OpIdentity<T>(), st);
   if (rc) return rc;
   return launch_cols<T, N, 1, PassY>((const C *) work, (C *) work, N, N, nc, OpIdentity<T>(), OpIdentity<T>(), st);
@@ -113,25 +122,9 @@ static int z_emit_n(const void *work, int axis, const EmitGeo &g, long row0, lon
   return fft::launch_rows_c2r<T, N>((const T *) work, row0, nrows, s, st);
 }
 
-#define GX_N_SWITCH(n, CALL)                                                                                     \
-  switch (n) {                                                                                                   \
-    case 4: { constexpr int N = 4; return CALL; }                                                                \
-    case 8: { constexpr int N = 8; return CALL; }                                                                \
-    case 16: { constexpr int N = 16; return CALL; }                                                              \
-    case 32: { constexpr int N = 32; return CALL; }                                                              \
-    case 64: { constexpr int N = 64; return CALL; }                                                              \
-    case 128: { constexpr int N = 128; return CALL; }                                                            \
-    case 256: { constexpr int N = 256; return CALL; }                                                            \
-    case 512: { constexpr int N = 512; return CALL; }                                                            \
-    case 1024: { constexpr int N = 1024; return CALL; }                                                          \
-    case 2048: { constexpr int N = 2048; return CALL; }                                                          \
-    case 4096: { constexpr int N = 4096; return CALL; }                                                          \
-    default: return fail("grid size must be a power of two in [4,4096]");                                        \
-  }
-
 template <typename T, bool PREDIV>
-static int zeldovich_xy_t(const void *d, void *w, int n, double L, int axis, cudaStream_t st) {
-  GX_N_SWITCH(n, (zeldovich_xy_n<T, N, PREDIV>(d, w, L, axis, st)));
+static int zeldovich_xy_t(const void *d, void *w, int n, double L, int axis, int order, cudaStream_t st) {
+  GX_N_SWITCH(n, (zeldovich_xy_n<T, N, PREDIV>(d, w, L, axis, order, st)));
 }
 template <typename T> static int z_real_t(void *w, int n, long row0, long nrows, cudaStream_t st) {
   GX_N_SWITCH(n, (z_real_n<T, N>(w, row0, nrows, st)));
@@ -147,12 +140,17 @@ int zeldovich_xy(const void *delta_k, void *work, int n, int dtype, double grid_
   if (axis < 0 || axis > 2) return fail("axis must be 0, 1 or 2");
   if (delta_k == work) return fail("zeldovich: the work field must not alias delta_k");
   if (int rc = fft::ensure_twiddles()) return rc;
+  static int order = -1;
+  if (order < 0) {
+    const char *e = getenv("GX_ZELDOVICH_ORDER");  // development switch: "xy" or "yx"
+    order = (e && e[0] == 'x') ? 0 : 1;
+  }
   if (dtype == GX_F64)
-    return prediv ? zeldovich_xy_t<double, true>(delta_k, work, n, grid_length, axis, st)
-                  : zeldovich_xy_t<double, false>(delta_k, work, n, grid_length, axis, st);
+    return prediv ? zeldovich_xy_t<double, true>(delta_k, work, n, grid_length, axis, order, st)
+                  : zeldovich_xy_t<double, false>(delta_k, work, n, grid_length, axis, order, st);
   if (dtype == GX_F32)
-    return prediv ? zeldovich_xy_t<float, true>(delta_k, work, n, grid_length, axis, st)
-                  : zeldovich_xy_t<float, false>(delta_k, work, n, grid_length, axis, st);
+    return prediv ? zeldovich_xy_t<float, true>(delta_k, work, n, grid_length, axis, order, st)
+                  : zeldovich_xy_t<float, false>(delta_k, work, n, grid_length, axis, order, st);
   return fail("bad dtype");
 }
 

@@ -17,7 +17,8 @@ int zeldovich_xy(const void *delta_k, void *work, int n, int dtype, double grid_
 // Field::applyTransferFunction (field.hpp:394-412) with the covariance evaluated in-kernel, optionally followed by
 // the division by k^2 that every Zeldovich component needs
 int apply_transfer_ex(void *field, int n, int dtype, double grid_length, const gx_spectrum *s, double power,
-                      int divide_k2, cudaStream_t st);
+                      int divide_k2, cudaStream_t st, int iy0 = 0, int ny = -1);
+int unit_variance_slab(void *field, int n, int dtype, int iy0, int ny, cudaStream_t st);
 // last pass: c2r along z of rows [row0, row0+nrows) of `work`, scaled by n^-1.5, written back in place (real space)
 int zeldovich_z_real(void *work, int n, int dtype, long row0, long nrows, cudaStream_t st);
 // last pass fused with the particle evaluation: pos/vel of cells id0 = row0*n ... written to out_pos/out_vel

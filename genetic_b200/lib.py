@@ -77,10 +77,22 @@ PROTOTYPES = {
     "gx_zeldovich_offset": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_emit_component": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, vp, ci, cl, cll, cll, vp]),
     "gx_unigrid_ic": (ci, [P(IcParams), vp, vp, vp, vp, csz, vp, vp, csz, vp]),
+    "gx_slab_bytes": (csz, [ci, ci, ci]),
+    "gx_slab_noise_draw": (ci, [vp, ci, ci, ci, ci, cul, ci, ci, P(cull), vp]),
+    "gx_slab_zero_dc": (ci, [vp, ci, vp]),
+    "gx_slab_unit_variance": (ci, [vp, ci, ci, ci, ci, vp]),
+    "gx_slab_apply_transfer": (ci, [vp, ci, ci, ci, ci, cd, vp, cd, ci, vp]),
+    "gx_slab_extract_planes": (ci, [vp, vp, ci, ci, ci, vp]),
+    "gx_slab_fft_x_mirror": (ci, [vp, vp, vp, ci, ci, ci, ci, cd, ci, ci, vp]),
+    "gx_slab_fft_x": (ci, [vp, ci, ci, ci, ci, ci, vp]),
+    "gx_slab_fft_y": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "gx_slab_fft_z_r2c": (ci, [vp, ci, ci, ci, vp]),
+    "gx_slab_fft_z_c2r": (ci, [vp, ci, ci, ci, vp]),
+    "gx_slab_z_emit": (ci, [vp, ci, ci, ci, ci, ci, cd, cd, cd, cd, ci, ci, vp, vp, ci, vp]),
     "gx_timing_enable": (ci, [ci]),
     "gx_timing_report": (ci, [C.c_char_p, ci]),
 }
-NOT_STATUS = {"gx_timing_report", "gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_spectrum_amplitude",
+NOT_STATUS = {"gx_timing_report", "gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_slab_bytes", "gx_spectrum_amplitude",
               "gx_spectrum_eval"}
 
 _lib = None

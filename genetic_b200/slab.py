@@ -1,0 +1,348 @@
+"""Slab-decomposed (multi-GPU) Zeldovich IC and 3-D FFT: one process per GPU, torch.distributed for the exchange.
+
+The reference is a single process; this is the SURVEY 8(e) decomposition of its unigrid path
+(ICGenerator::done, ic.hpp:1633-1648; FieldFourierManager::performTransform, fourier.hpp:479-518):
+
+    Fourier space  rank r holds the ky-slab [kx:n][ky_local:P][kz:n/2+1]     (P = n / world)
+    real space     rank r holds the x-slab  [x_local:P][y:n][z:n+2]          (contiguous particle ids)
+    inverse FFT  = local x-pass | all-to-all | local y-pass | local z-pass   (forward: the reverse)
+
+The exchange buffer is [peer][x_local][ky_local][kz]: the x-pass leaves it in that order and the y-pass reads the
+received blocks in place (csrc/slab.cu), so the only data movement besides the passes is ONE all-to-all per
+transform (NCCL over NVLink) plus one all-gather of the two Hermitian-mirror planes per field.
+
+`SlabPipeline` is written against two small interfaces so that the sequencing and the buffer/layout logic are the
+same objects on a B200 node and in the world_size-2 gloo tests that run on CPU:
+    ops  : the per-rank passes. Product: `CudaSlabOps` (C ABI, raises if the CUDA library is missing).
+           The tests supply a numpy stand-in; nothing in this package computes field data on the CPU.
+    comm : `TorchComm` (torch.distributed all_to_all_single / all_gather_into_tensor; nccl or gloo).
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import lib as L
+
+
+class SlabGeometry:
+    """Sizes and index ranges of one rank's slabs."""
+
+    def __init__(self, n, world, rank, itemsize=8):
+        if n & (n - 1) or world & (world - 1) or n % world:
+            raise L.GxError("slab: n and world must be powers of two with world | n")
+        self.n, self.world, self.rank = n, world, rank
+        self.P = n // world
+        self.nc = n // 2 + 1
+        self.itemsize = itemsize                                  # bytes per real
+        self.slab_complex = n * self.P * self.nc                   # complex elements per slab (either space)
+        self.slab_bytes = 2 * self.slab_complex * itemsize
+        self.block_complex = self.P * self.P * self.nc             # one peer block of the exchange buffer
+        self.planes_local_complex = n * self.P * 2                 # kz = 0 and kz = n/2 of the ky-slab
+        self.iy0 = rank * self.P                                   # first ky storage index owned (Fourier space)
+        self.x0 = rank * self.P                                    # first x plane owned (real space)
+        self.id0 = self.x0 * n * n                                 # first particle id owned
+        self.particles = self.P * n * n
+
+
+class TorchComm:
+    """The two collectives of the slab path, on torch tensors (uint8 views of the slab buffers)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_to_all(self, recv, send):
+        """Equal-split exchange: block s of `send` goes to rank s, block r of `recv` comes from rank r."""
+        if self.world == 1:
+            recv.copy_(send)
+            return
+        self.dist.all_to_all_single(recv, send, group=self.group)
+
+    def all_gather(self, out, inp):
+        if self.world == 1:
+            out.copy_(inp)
+            return
+        self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+
+class CudaSlabOps:
+    """Per-rank passes through the C ABI (include/genetic_b200.h, 'slab decomposition'). Buffers are torch CUDA
+    tensors (so that NCCL can see them); kernels are launched on torch's current stream."""
+
+    def __init__(self, geo, dtype=np.float64, device=None):
+        import torch
+        self.torch = torch
+        self.lib = L.load()  # raises if the CUDA library has not been built: there is no CPU fallback
+        self.geo = geo
+        self.dt = L.F64 if np.dtype(dtype) == np.float64 else L.F32
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def alloc(self, nbytes):
+        return self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+
+    def _st(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr())
+
+    def noise_draw(self, slab, seed, mode, reverse, offset=0):
+        g = self.geo
+        off = C.c_ulonglong(offset)
+        self.lib.gx_slab_noise_draw(self._p(slab), g.n, self.dt, g.world, g.rank, seed, mode, int(reverse),
+                                    C.byref(off), self._st())
+        return off.value
+
+    def unit_variance(self, slab):
+        g = self.geo
+        self.lib.gx_slab_unit_variance(self._p(slab), g.n, self.dt, g.world, g.rank, self._st())
+
+    def apply_transfer(self, slab, grid_length, spectrum, power, divide_k2):
+        g = self.geo
+        self.lib.gx_slab_apply_transfer(self._p(slab), g.n, self.dt, g.world, g.rank, float(grid_length),
+                                        spectrum.handle, float(power), int(divide_k2), self._st())
+
+    def extract_planes(self, slab, planes_local):
+        g = self.geo
+        self.lib.gx_slab_extract_planes(self._p(slab), self._p(planes_local), g.n, self.dt, g.world, self._st())
+
+    def x_inverse_mirror(self, slab, planes_all, out, grid_length, op, axis):
+        g = self.geo
+        self.lib.gx_slab_fft_x_mirror(self._p(slab), self._p(planes_all), self._p(out), g.n, self.dt, g.world, g.rank,
+                                      float(grid_length), op, axis, self._st())
+
+    def x_pass(self, slab, direction, scale):
+        g = self.geo
+        self.lib.gx_slab_fft_x(self._p(slab), g.n, self.dt, g.world, direction, int(scale), self._st())
+
+    def y_pass(self, src, dst, direction, src_exchange, dst_exchange):
+        g = self.geo
+        self.lib.gx_slab_fft_y(self._p(src), self._p(dst), g.n, self.dt, g.world, direction, int(src_exchange),
+                               int(dst_exchange), self._st())
+
+    def z_r2c(self, slab):
+        g = self.geo
+        self.lib.gx_slab_fft_z_r2c(self._p(slab), g.n, self.dt, g.world, self._st())
+
+    def z_c2r(self, slab):
+        g = self.geo
+        self.lib.gx_slab_fft_z_c2r(self._p(slab), g.n, self.dt, g.world, self._st())
+
+    def z_emit(self, slab, axis, cell_size, offset_lower, domain_size, vel_ratio, plane0, nplanes, out_pos, out_vel,
+               out_dtype):
+        g = self.geo
+        odt = L.F64 if np.dtype(out_dtype) == np.float64 else L.F32
+        self.lib.gx_slab_z_emit(self._p(slab), g.n, self.dt, g.world, g.rank, axis, float(cell_size),
+                                float(offset_lower), float(domain_size), float(vel_ratio), plane0, nplanes,
+                                self._p(out_pos) if out_pos is not None else None,
+                                self._p(out_vel) if out_vel is not None else None, odt, self._st())
+
+    def zero_dc(self, slab):
+        self.lib.gx_slab_zero_dc(self._p(slab), self.dt, self._st())
+
+
+class SlabPipeline:
+    """Sequencing of the slab path for one rank. All tensors are flat uint8 buffers of geo.slab_bytes."""
+
+    def __init__(self, geo, ops, comm):
+        self.geo, self.ops, self.comm = geo, ops, comm
+        g = geo
+        self.bufA = ops.alloc(g.slab_bytes)
+        self.bufB = ops.alloc(g.slab_bytes)
+        self.planes_local = ops.alloc(2 * g.planes_local_complex * g.itemsize)
+        self.planes_all = ops.alloc(2 * g.planes_local_complex * g.itemsize * g.world)
+
+    # ---- general transforms (Field::toReal / toFourier on a slab) ---------------------------------------------
+    def gather_mirror_planes(self, slab):
+        self.ops.extract_planes(slab, self.planes_local)
+        self.comm.all_gather(self.planes_all, self.planes_local)
+
+    def inverse_after_x(self, work):
+        """bufA holds the x-transformed ky-slab: exchange, y-pass into `work` ([x_local][y][kz])."""
+        self.comm.all_to_all(self.bufB, self.bufA)
+        self.ops.y_pass(self.bufB, work, +1, True, False)
+
+    def to_real(self, slab):
+        """In: ky-slab (Fourier). Out: x-slab (real, padded rows) in the same buffer."""
+        self.gather_mirror_planes(slab)
+        self.ops.x_inverse_mirror(slab, self.planes_all, self.bufA, 1.0, 0, 0)
+        self.inverse_after_x(slab)
+        self.ops.z_c2r(slab)
+
+    def to_fourier(self, slab):
+        """In: x-slab (real). Out: ky-slab (Fourier) in the same buffer."""
+        self.ops.z_r2c(slab)
+        self.ops.y_pass(slab, self.bufA, -1, False, True)
+        self.comm.all_to_all(slab, self.bufA)
+        self.ops.x_pass(slab, -1, True)
+
+    # ---- the IC path -------------------------------------------------------------------------------------------
+    def draw_delta(self, delta, seed, mode, reverse, fix_power, grid_length, spectrum):
+        self.ops.noise_draw(delta, seed, mode, reverse)
+        if mode == L.NOISE_REAL:
+            self.to_fourier(delta)
+            if self.geo.rank == 0:
+                self.ops.zero_dc(delta)
+        if fix_power:
+            self.ops.unit_variance(delta)
+        self.ops.apply_transfer(delta, grid_length, spectrum, 0.5, 1)  # leaves delta_k / k^2
+
+    def zeldovich(self, delta, grid_length, emit):
+        """delta: ky-slab holding delta_k / k^2. emit(axis, work) consumes the half-transformed x-slab
+        ([x_local][y][kz], y and x already inverse-transformed) of each displacement component."""
+        self.gather_mirror_planes(delta)
+        for axis in range(3):
+            self.ops.x_inverse_mirror(delta, self.planes_all, self.bufA, grid_length, 1, axis)
+            self.inverse_after_x(self.bufA)  # B <- exchange(A); A <- y-pass(B)
+            emit(axis, self.bufA)
+
+
+def unigrid_ic_slab(geo, ops, comm, seed, mode, reverse, fix_power, grid, spectrum, vel_ratio, out_dtype, delta, pipe,
+                    out_pos, out_vel, planes_per_emit=None):
+    """One IC for this rank's x-slab: out_pos/out_vel are [3][particles] (component-major) device tensors."""
+    g = geo
+    pipe.draw_delta(delta, seed, mode, reverse, fix_power, float(grid.thisGridSize), spectrum)
+    osz = np.dtype(out_dtype).itemsize
+
+    def emit(axis, work):
+        ops.z_emit(work, axis, float(grid.cellSize), float(grid.offsetLower[axis]), float(grid.periodicDomainSize),
+                   vel_ratio, 0, g.P, out_pos[axis * g.particles * osz:], out_vel[axis * g.particles * osz:], out_dtype)
+
+    pipe.zeldovich(delta, float(grid.thisGridSize), emit)
+
+
+# ---- bench entry (python bench.py under torchrun, N > 1) ------------------------------------------------------------
+def bench_main(args, lib, world, rank, local_rank):
+    import torch
+    import torch.distributed as dist
+    import genetic_b200 as gb
+    import bench as B
+
+    n = args.n
+    dtype, out_dtype = np.float64, np.float32
+    box = B.box_for(n)
+    cos = gb.CosmologicalParameters(B.COSMO["Om"], B.COSMO["Ol"], B.COSMO["s8"], B.COSMO["z"], ns=B.COSMO["ns"],
+                                    hubble=B.COSMO["hubble"])
+    grid = gb.Grid(box, n, dtype=dtype)
+    spectrum = gb.CAMB(cos, B.CAMB_FILE, "all", dtype)
+    geo = SlabGeometry(n, world, rank, 8)
+    ops = CudaSlabOps(geo, dtype)
+    comm = TorchComm()
+    pipe = SlabPipeline(geo, ops, comm)
+    delta = ops.alloc(geo.slab_bytes)
+    osz = 4
+    out_pos = ops.alloc(3 * geo.particles * osz)
+    out_vel = ops.alloc(3 * geo.particles * osz)
+    vel_ratio = cos.zeldovichVelocityToOffsetRatio(dtype)
+    hpos = torch.empty(3 * geo.particles * osz, dtype=torch.uint8, pin_memory=True)
+    hvel = torch.empty(3 * geo.particles * osz, dtype=torch.uint8, pin_memory=True)
+
+    def device_step():
+        unigrid_ic_slab(geo, ops, comm, B.SEED, L.NOISE_FOURIER_PARALLEL, 0, 0, grid, spectrum, vel_ratio, out_dtype,
+                        delta, pipe, out_pos, out_vel)
+
+    def e2e_step():
+        sp = gb.CAMB(cos, B.CAMB_FILE, "all", dtype)
+        unigrid_ic_slab(geo, ops, comm, B.SEED, L.NOISE_FOURIER_PARALLEL, 0, 0, grid, sp, vel_ratio, out_dtype, delta,
+                        pipe, out_pos, out_vel)
+        hpos.copy_(out_pos, non_blocking=True)
+        hvel.copy_(out_vel, non_blocking=True)
+        torch.cuda.synchronize()
+        return sp
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = B.ClockSampler(local_rank)
+    sampler.start()
+    lib.gx_timing_enable(1)
+    l0 = lib.gx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    ms_local = e0.elapsed_time(e1) / args.steps
+    launches = lib.gx_launch_count() - l0
+    buf = C.create_string_buffer(1 << 16)
+    lib.gx_timing_report(buf, len(buf))
+    lib.gx_timing_enable(0)
+    clocks = sampler.stop()
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_local = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    classes = {}
+    for line in buf.value.decode().strip().split("\n"):
+        if line:
+            nm, cnt, tot = line.split()
+            classes[nm] = (int(cnt), float(tot))
+    n3 = n ** 3
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(B.ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        fft_classes = {k: v for k, v in classes.items() if k.startswith("fft_")}
+        dom = max(fft_classes, key=lambda k: fft_classes[k][1]) if fft_classes else None
+        roof = None
+        if dom:
+            cnt, tot = classes[dom]
+            avg_ms = tot / cnt
+            per_launch = 2 * geo.slab_bytes if dom.startswith("fft_cols") else geo.slab_bytes + 8 * geo.particles
+            achieved = per_launch / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
+                    "per_class_ms_per_step_rank0": {k: v[1] / args.steps for k, v in sorted(classes.items())},
+                    "share_of_step": tot / args.steps / ms}
+        a2a_bytes = 3 * geo.slab_bytes * (world - 1) // world
+        line = {"metric": "IC particles/sec (Zeldovich %d^3)" % n, "value": n3 / (ms * 1e-3), "unit": "particles/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": B.workload_name(n, "f64"), "output": "float32 pos+vel, component-major, x-slab per rank",
+                           "parallelism": "slab%d: ky-slabs in Fourier space, x-slabs in real space, one NCCL all-to-all "
+                                          "per inverse transform" % world,
+                           "l2": "inputs larger than L2 (each slab %.2f GB)" % (geo.slab_bytes / 1e9)},
+                "clocks": clocks,
+                "e2e": {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": 3 * 8 * 213 * world,
+                        "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": int(launches) * world,
+                "nvlink": {"all_to_all_bytes_sent_per_gpu_per_step": a2a_bytes},
+                "roofline": roof, "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

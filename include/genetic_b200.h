@@ -173,6 +173,44 @@ typedef struct {
 int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field, void *stage,
                   size_t stage_bytes, void *host_pos, void *host_vel, size_t host_capacity_particles, void *stream);
 
+/* ---- slab decomposition over G GPUs (one process per GPU) ----------------------------------------------
+   The reference is one process: FieldFourierManager::performTransform (fourier.hpp:479-518) transforms the whole field.
+   Here rank r of `world` (a power of two dividing n, P = n/world) holds
+     Fourier space: the ky-slab [kx:n][ky_local:P][kz:n/2+1], ky = r*P + ky_local
+     real space   : the x-slab  [x_local:P][y:n][z:n+2],       x  = r*P + x_local
+   and a 3-D transform is local x-pass | all-to-all | local y-pass | local z-pass (reverse order for r2c). The exchange
+   buffer is [peer][x_local][ky_local][kz] (each peer block contiguous), which the x-pass produces/consumes in natural
+   order and the y-pass addresses directly, so there is no pack/unpack sweep. The all-to-all and the all-gather of the
+   two mirror planes are issued by the host layer (NCCL). Every function works on this rank's slab only. */
+size_t gx_slab_bytes(int n, int dtype, int world);
+/* RandomFieldGenerator::draw for this rank's slab: Fourier orders fill the ky-slab; GX_NOISE_REAL fills the x-slab in
+   real space (follow with the slab r2c and gx_slab_zero_dc on rank 0). Bit-identical to gx_noise_draw slot for slot. */
+int gx_slab_noise_draw(void *slab, int n, int dtype, int world, int rank, unsigned long seed, int mode,
+                       int reverse_order, unsigned long long *stream_offset_io, void *stream);
+int gx_slab_zero_dc(void *slab, int dtype, void *stream);
+int gx_slab_unit_variance(void *slab, int n, int dtype, int world, int rank, void *stream);
+/* Field::applyTransferFunction on the ky-slab; divide_k2 != 0 leaves delta_k / k^2 (see gx_unigrid_ic) */
+int gx_slab_apply_transfer(void *slab, int n, int dtype, int world, int rank, double grid_length, const gx_spectrum *s,
+                           double power, int divide_k2, void *stream);
+/* planes_local[n][P][2] <- the kz = 0 and kz = n/2 planes of the ky-slab (input of the mirror all-gather) */
+int gx_slab_extract_planes(const void *slab, void *planes_local, int n, int dtype, int world, void *stream);
+/* inverse x-pass of the ky-slab with ensureFourierModesAreMirrored (fourier.hpp:331-357) resolved on load from the
+   all-gathered planes [peer][n][P][2]; op 0: mirror only (toReal of any field), 1: times i k_axis (slab holds
+   delta_k/k^2), 2: times i k_axis / k^2 (zeldovich.hpp:170-176). out may not alias slab. */
+int gx_slab_fft_x_mirror(const void *slab, const void *planes_all, void *out, int n, int dtype, int world, int rank,
+                         double grid_length, int op, int axis, void *stream);
+int gx_slab_fft_x(void *slab, int n, int dtype, int world, int dir, int scale, void *stream); /* plain x-pass, in place; scale: / n^1.5 */
+/* y-pass over the P local x-planes; either side may be the exchange layout instead of [x_local][y][kz] */
+int gx_slab_fft_y(const void *src, void *dst, int n, int dtype, int world, int dir, int src_exchange_layout,
+                  int dst_exchange_layout, void *stream);
+int gx_slab_fft_z_r2c(void *slab, int n, int dtype, int world, void *stream);  /* rows, real -> half-complex, unscaled */
+int gx_slab_fft_z_c2r(void *slab, int n, int dtype, int world, void *stream);  /* rows, half-complex -> real, / n^1.5 */
+/* last inverse pass fused with ZeldovichParticleEvaluator::getParticle for local x-planes [plane0, plane0+nplanes):
+   element i of out_pos/out_vel is particle id (rank*P + plane0)*n*n + i */
+int gx_slab_z_emit(const void *slab, int n, int dtype, int world, int rank, int axis, double cell_size,
+                   double offset_lower, double domain_size, double vel_ratio, int plane0, int nplanes, void *out_pos,
+                   void *out_vel, int out_dtype, void *stream);
+
 /* ---- per-kernel-class device timing for the roofline report (off by default) ---------------------------------- */
 int gx_timing_enable(int on);
 int gx_timing_report(char *buf, int buflen); /* lines "name count total_ms" */
