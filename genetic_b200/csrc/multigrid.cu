@@ -1,0 +1,475 @@
+// Moving real-space fields between grids of different resolution (zoom levels), windows and flagged-cell masks.
+//
+// Reference (paths relative to genetIC/src/):
+//   Field::addFieldFromDifferentGrid             simulation/field/field.hpp:804-812  (through evaluator.hpp:31-57)
+//     coarse -> fine : SuperSampleEvaluator[SectionEvaluator] -> Field::evaluateInterpolated :483-508,
+//                      makeTricubicInterpolator :598-617, LocalUnitTricubicApproximation tools/numerics/tricubic.hpp:54-77
+//     fine -> coarse : SubSampleEvaluator evaluator.hpp:168-205, SubSampleGrid::forEachSubcell virtualgrid.hpp:570-600
+//   Field::deInterpolate                          field.hpp:420-480 in the loop of
+//     MultiLevelGridBase::generateMultilevelCovectorFromHiresCovector multilevelgrid.hpp:283-297
+//   Field::setZeroInsideWindow / setZeroOutsideWindow  field.hpp:774-795, Window<T>::contains window.hpp
+//   FilteredVarianceModification::windowOperator / varianceOperator quadraticmodification.hpp:172-221
+//
+// All three transfers are separable: out[A][B][C] (+)= scale * sum_ijk wx[A][i] wy[B][j] wz[C][k] v[ix[A][i]][iy[B][j]][iz[C][k]].
+// The tricubic polynomial of the reference (64 coefficients from a 4^3 neighbourhood, tricubic.hpp:80-430) is the tensor
+// product of the per-axis Catmull-Rom weights listed at tricubic.hpp:450-549, so interpolation gathers with those
+// weights, "conjugate deinterpolation" gathers with the transposed per-axis tables, and sub-cell averaging gathers with
+// unit weights and divides by the number of sub-cells the fine grid holds. The per-axis tables (a few KB) are built on
+// the host with the reference's own coordinate arithmetic (fmod wrap, floor(x/dx - 1/2)) in the field's CoordinateType;
+// the kernel is one CTA per destination row: the 4x4 (or (4r)^2, r^2) source rows are combined into one row in shared
+// memory with coalesced loads, then every thread finishes one cell along z.
+#include "../../include/genetic_b200.h"
+#include "gx_common.cuh"
+#include "spectral.cuh"
+#include <cmath>
+#include <vector>
+
+namespace gx {
+
+template <typename T> struct AxisTab {
+  const int *cnt;            // [n_dst]
+  const int *idx;            // [n_dst][K] source indices
+  const T *w;                // [n_dst][K]
+  const unsigned char *flag; // [n_dst] bit 0 / bit 1: containment tests
+  int K;
+};
+
+// mode 0: weighted sum, cell contained when bit 0 is set on all three axes
+// mode 1: mean over the gathered cells, contained when bit 0 is set on all axes or bit 1 is set on all axes
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+axis_gather_add_kernel(T *__restrict__ dst, int n_dst, const T *__restrict__ src, int n_src, AxisTab<T> tx, AxisTab<T> ty,
+                       AxisTab<T> tz, T scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *row = reinterpret_cast<T *>(smem_raw);
+  const int A = blockIdx.y, B = blockIdx.x;
+  const int cx = tx.cnt[A], cy = ty.cnt[B];
+  if (cx == 0 || cy == 0) return;
+  const unsigned fxy = tx.flag[A] & ty.flag[B];
+  if (fxy == 0) return;
+  const long ps = n_src + 2, pd = n_dst + 2;
+  const int *ix = tx.idx + (long) A * tx.K, *iy = ty.idx + (long) B * ty.K;
+  const T *wx = tx.w + (long) A * tx.K, *wy = ty.w + (long) B * ty.K;
+  for (int z = threadIdx.x; z < n_src; z += blockDim.x) {
+    T acc = 0;
+    for (int i = 0; i < cx; ++i) {
+      const T *plane = src + (long) ix[i] * n_src * ps + z;
+      T a = 0;
+      for (int j = 0; j < cy; ++j) a += wy[j] * plane[(long) iy[j] * ps];
+      acc += wx[i] * a;
+    }
+    row[z] = acc;
+  }
+  __syncthreads();
+  T *out = dst + ((long) A * n_dst + B) * pd;
+  for (int C = threadIdx.x; C < n_dst; C += blockDim.x) {
+    const int cz = tz.cnt[C];
+    if (cz == 0) continue;
+    const unsigned f = fxy & tz.flag[C];
+    if (MODE == 0 ? !(f & 1u) : f == 0) continue;
+    const int *iz = tz.idx + (long) C * tz.K;
+    const T *wz = tz.w + (long) C * tz.K;
+    T s = 0;
+    for (int k = 0; k < cz; ++k) s += wz[k] * row[iz[k]];
+    if (MODE == 1) s /= (T) (cx * cy * cz);
+    out[C] += scale * s;
+  }
+}
+
+// ---- host-side per-axis tables ---------------------------------------------------------------------------------
+template <typename T> struct HostAxis {
+  int n = 0, K = 0;
+  std::vector<int> cnt, idx;
+  std::vector<T> w;
+  std::vector<unsigned char> flag;
+  void init(int n_, int K_) { n = n_; K = K_; cnt.assign(n, 0); idx.assign((size_t) n * K, 0); w.assign((size_t) n * K, (T) 0); flag.assign(n, 0); }
+};
+
+template <typename T> static inline T wrap_point(T x, T L) {  // Grid::wrapIndividualCoordinate, grid.hpp:527-531
+  x = std::fmod(x, L);
+  if (x < 0) x += L;
+  return x;
+}
+template <typename T> static inline T centroid(const gx_grid_desc &g, int axis, int c) {  // grid.hpp:662-669
+  return ((T) c * (T) g.cell_size + (T) g.offset_lower[axis]) + (T) g.cell_size / 2;
+}
+static inline int sim_equivalent(const gx_grid_desc &g) { return (int) std::lround(g.domain_size / g.cell_size); }  // grid.hpp:111
+
+template <typename T> static inline void catmull_rom(T t, T w[4]) {  // tricubic.hpp:450-549, per axis
+  w[0] = -(t - 1) * (t - 1) * t / 2;
+  w[1] = (2 - 5 * t * t + 3 * t * t * t) / 2;
+  w[2] = -t * (-1 - 4 * t + 3 * t * t) / 2;
+  w[3] = (t - 1) * t * t / 2;
+}
+
+// the four source cells and weights Field::evaluateInterpolated uses for a point at the centroid of dst cell c
+template <typename T>
+static void stencil(const gx_grid_desc &dst, const gx_grid_desc &src, int axis, int c, bool wrap_with_grid, int idx[4], T w[4]) {
+  T loc = centroid<T>(dst, axis, c) - (T) src.offset_lower[axis];
+  loc = wrap_point<T>(loc, (T) src.domain_size);
+  const T u = loc / (T) src.cell_size - (T) 0.5;
+  const int p0 = (int) std::floor(u);
+  catmull_rom<T>(u - (T) p0, w);
+  const int S = sim_equivalent(src);
+  for (int i = 0; i < 4; ++i) {
+    int q = p0 - 1 + i;
+    if (wrap_with_grid) {            // deInterpolate's own wrap (field.hpp:452-462), with >= where the reference has >
+      if (q < 0) q += src.n;
+      if (q >= src.n) q -= src.n;
+    } else if (src.n == S) {         // wrapCoordinate, grid.hpp:566-574
+      if (q > S - 1) q -= S;
+      if (q < 0) q += S;
+    } else {                         // clampCoordinate, grid.hpp:592-600
+      if (q > src.n - 1) q = src.n - 1;
+      if (q < 0) q = 0;
+    }
+    idx[i] = q;
+  }
+}
+
+template <typename T> static int build_interp(const gx_grid_desc &dst, const gx_grid_desc &src, HostAxis<T> t[3]) {
+  const int ratio = (int) std::lround(src.cell_size / dst.cell_size);
+  if (ratio < 1 || std::fabs(src.cell_size / dst.cell_size - ratio) > 1e-6 * ratio)
+    return fail("gx_interp_add: cell sizes are not in an integer ratio");
+  const long S = (long) sim_equivalent(src) * ratio;
+  for (int a = 0; a < 3; ++a) {
+    t[a].init(dst.n, 4);
+    const long rel = std::lround((dst.offset_lower[a] - src.offset_lower[a]) / dst.cell_size);
+    for (int c = 0; c < dst.n; ++c) {
+      int idx[4]; T w[4];
+      stencil<T>(dst, src, a, c, false, idx, w);
+      t[a].cnt[c] = 4;
+      for (int i = 0; i < 4; ++i) { t[a].idx[(size_t) c * 4 + i] = idx[i]; t[a].w[(size_t) c * 4 + i] = w[i]; }
+      long q = c + rel;  // SectionOfGrid / SuperSampleGrid containment, virtualgrid.hpp:199-206,472-480
+      if (q > S - 1) q -= S;
+      if (q < 0) q += S;
+      t[a].flag[c] = (q >= 0 && q / ratio < src.n) ? 1 : 0;
+    }
+  }
+  return 0;
+}
+
+template <typename T> static int build_deinterp(const gx_grid_desc &lo, const gx_grid_desc &hi, HostAxis<T> t[3]) {
+  const int ratio = (int) std::lround(lo.cell_size / hi.cell_size);
+  if (ratio < 1) return fail("gx_deinterp_add: the source must be the finer grid");
+  for (int a = 0; a < 3; ++a) {
+    std::vector<std::vector<std::pair<int, T>>> lists(lo.n);
+    for (int f = 0; f < hi.n; ++f) {
+      int idx[4]; T w[4];
+      stencil<T>(hi, lo, a, f, true, idx, w);
+      for (int i = 0; i < 4; ++i) lists[idx[i]].push_back({f, w[i]});
+    }
+    size_t K = 1;
+    for (auto &l : lists) K = std::max(K, l.size());
+    t[a].init(lo.n, (int) K);
+    for (int p = 0; p < lo.n; ++p) {
+      t[a].cnt[p] = (int) lists[p].size();
+      t[a].flag[p] = 1;
+      for (size_t i = 0; i < lists[p].size(); ++i) {
+        t[a].idx[(size_t) p * K + i] = lists[p][i].first;
+        t[a].w[(size_t) p * K + i] = lists[p][i].second;
+      }
+    }
+  }
+  return 0;
+}
+
+template <typename T> static int build_subsample(const gx_grid_desc &dst, const gx_grid_desc &src, HostAxis<T> t[3]) {
+  const int r = (int) std::lround(dst.cell_size / src.cell_size);
+  if (r < 2) return fail("gx_interp_add: sub-cell averaging needs a finer source");
+  const long S = (long) sim_equivalent(dst) * r;
+  for (int a = 0; a < 3; ++a) {
+    t[a].init(dst.n, r);
+    const long rel = std::lround((dst.offset_lower[a] - src.offset_lower[a]) / src.cell_size);
+    for (int c = 0; c < dst.n; ++c) {
+      int cnt = 0;
+      unsigned char flag = 0;
+      for (int j = 0; j < r; ++j) {
+        long f = (long) c * r + j + rel;
+        if (f > S - 1) f -= S;
+        if (f < 0) f += S;
+        if (f < src.n) {
+          t[a].idx[(size_t) c * r + cnt] = (int) f;
+          t[a].w[(size_t) c * r + cnt] = (T) 1;
+          ++cnt;
+          if (j == 0) flag |= 1;      // first sub-cell held  (virtualgrid.hpp:628-633)
+          if (j == r - 1) flag |= 2;  // last sub-cell held
+        }
+      }
+      t[a].cnt[c] = cnt;
+      t[a].flag[c] = flag;
+    }
+  }
+  return 0;
+}
+
+// device copies of the tables of one call; freed after the kernel has been enqueued (stream-ordered)
+template <typename T> struct DevTabs {
+  void *blob = nullptr;
+  AxisTab<T> tab[3];
+  int upload(const HostAxis<T> h[3], cudaStream_t st) {
+    size_t off[3][4], total = 0;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t) 15; };
+    for (int a = 0; a < 3; ++a) {
+      off[a][0] = total; total += al(h[a].cnt.size() * sizeof(int));
+      off[a][1] = total; total += al(h[a].idx.size() * sizeof(int));
+      off[a][2] = total; total += al(h[a].w.size() * sizeof(T));
+      off[a][3] = total; total += al(h[a].flag.size());
+    }
+    std::vector<unsigned char> stage(total);
+    for (int a = 0; a < 3; ++a) {
+      memcpy(&stage[off[a][0]], h[a].cnt.data(), h[a].cnt.size() * sizeof(int));
+      memcpy(&stage[off[a][1]], h[a].idx.data(), h[a].idx.size() * sizeof(int));
+      memcpy(&stage[off[a][2]], h[a].w.data(), h[a].w.size() * sizeof(T));
+      memcpy(&stage[off[a][3]], h[a].flag.data(), h[a].flag.size());
+    }
+    GX_CUDA_CHECK(cudaMalloc(&blob, total));
+    GX_CUDA_CHECK(cudaMemcpy(blob, stage.data(), total, cudaMemcpyHostToDevice));  // synchronous: `stage` is a local
+    (void) st;
+    unsigned char *b = (unsigned char *) blob;
+    for (int a = 0; a < 3; ++a) {
+      tab[a].cnt = (const int *) (b + off[a][0]);
+      tab[a].idx = (const int *) (b + off[a][1]);
+      tab[a].w = (const T *) (b + off[a][2]);
+      tab[a].flag = b + off[a][3];
+      tab[a].K = h[a].K;
+    }
+    return 0;
+  }
+  int release(cudaStream_t st) {
+    if (blob) { GX_CUDA_CHECK(cudaStreamSynchronize(st)); GX_CUDA_CHECK(cudaFree(blob)); blob = nullptr; }
+    return 0;
+  }
+};
+
+template <typename T, int MODE>
+static int run_gather(void *dst, int n_dst, const void *src, int n_src, const HostAxis<T> h[3], T scale, const char *name,
+                      cudaStream_t st) {
+  DevTabs<T> d;
+  if (d.upload(h, st)) return 1;
+  {
+    GX_TIMED(name, st);
+    axis_gather_add_kernel<T, MODE><<<dim3(n_dst, n_dst), 256, (size_t) n_src * sizeof(T), st>>>(
+        (T *) dst, n_dst, (const T *) src, n_src, d.tab[0], d.tab[1], d.tab[2], scale);
+    count_launch();
+  }
+  GX_LAUNCH_CHECK();
+  return d.release(st);
+}
+
+static int check_desc(const gx_grid_desc *g, const char *who) {
+  if (!g) return fail(std::string(who) + ": null grid descriptor");
+  if (g->n < 4 || g->n > 4096 || !is_pow2(g->n)) return fail(std::string(who) + ": grid size must be a power of two in [4,4096]");
+  if (!(g->cell_size > 0) || !(g->domain_size > 0)) return fail(std::string(who) + ": cell and domain size must be positive");
+  return 0;
+}
+
+template <typename T>
+static int interp_add_t(void *dst, const gx_grid_desc *gd, const void *src, const gx_grid_desc *gs, cudaStream_t st) {
+  HostAxis<T> h[3];
+  if (gs->cell_size > gd->cell_size) {
+    if (build_interp<T>(*gd, *gs, h)) return 1;
+    return run_gather<T, 0>(dst, gd->n, src, gs->n, h, (T) 1, "interp_add", st);
+  }
+  if (gs->cell_size < gd->cell_size) {
+    if (build_subsample<T>(*gd, *gs, h)) return 1;
+    return run_gather<T, 1>(dst, gd->n, src, gs->n, h, (T) 1, "subsample_add", st);
+  }
+  return fail("gx_interp_add: source and destination have the same resolution");
+}
+
+template <typename T>
+static int deinterp_add_t(void *dst, const gx_grid_desc *gc, const void *src, const gx_grid_desc *gf, double scale,
+                          cudaStream_t st) {
+  HostAxis<T> h[3];
+  if (build_deinterp<T>(*gc, *gf, h)) return 1;
+  return run_gather<T, 0>(dst, gc->n, src, gf->n, h, (T) scale, "deinterp_add", st);
+}
+
+// ---- windows -------------------------------------------------------------------------------------------------------
+template <typename T> __global__ void zero_window_kernel(T *f, int n, const unsigned char *in, int inside) {
+  // in[0..n) x, in[n..2n) y, in[2n..3n) z
+  const long nrows = (long) n * n;
+  for (long r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const int x = (int) (r / n), y = (int) (r - (long) x * n);
+    const unsigned char xy = in[x] & in[n + y];
+    T *row = f + r * (n + 2);
+    for (int z = threadIdx.x; z < n; z += blockDim.x) {
+      const int contained = xy & in[2 * n + z];
+      if (contained == inside) row[z] = (T) 0;
+    }
+  }
+}
+
+template <typename T>
+static int zero_window_t(void *field, const gx_grid_desc *g, const gx_grid_desc *win, int inside, cudaStream_t st) {
+  // Grid::getWindow (grid.hpp:502-504) -> Window(L, lower, upper): wrapCorners, then contains() on cell centroids
+  const int n = g->n;
+  std::vector<unsigned char> in(3 * (size_t) n);
+  const T L = (T) win->domain_size;
+  auto wrap = [L](T v) { if (v < 0) v += L; if (v >= L) v -= L; return v; };
+  for (int a = 0; a < 3; ++a) {
+    const T thisGridSize = (T) win->cell_size * (T) win->n;
+    T lo = wrap((T) win->offset_lower[a]);
+    T hi = (T) win->offset_lower[a] + thisGridSize;
+    hi = std::nextafter(wrap(std::nextafter(hi, -std::numeric_limits<T>::infinity())), std::numeric_limits<T>::infinity());
+    for (int c = 0; c < n; ++c) {
+      const T x = centroid<T>(*g, a, c);
+      in[(size_t) a * n + c] = (hi >= lo) ? (x < hi && x >= lo) : (x < hi || x >= lo);
+    }
+  }
+  unsigned char *d = nullptr;
+  GX_CUDA_CHECK(cudaMalloc(&d, in.size()));
+  GX_CUDA_CHECK(cudaMemcpy(d, in.data(), in.size(), cudaMemcpyHostToDevice));
+  const long nrows = (long) n * n;
+  zero_window_kernel<T><<<(int) (nrows < 148 * 16 ? nrows : 148 * 16), 256, 0, st>>>((T *) field, n, d, inside ? 1 : 0);
+  count_launch();
+  GX_LAUNCH_CHECK();
+  GX_CUDA_CHECK(cudaStreamSynchronize(st));
+  GX_CUDA_CHECK(cudaFree(d));
+  return 0;
+}
+
+// ---- flagged-cell masks -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T> __global__ void __launch_bounds__(256)
+masked_sum_kernel(const T *__restrict__ f, const unsigned char *__restrict__ mask, int n, double *partials) {
+  const long nrows = (long) n * n;
+  double acc = 0;
+  for (long r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const T *row = f + r * (n + 2);
+    const unsigned char *m = mask + r * n;
+    for (int z = threadIdx.x; z < n; z += blockDim.x) if (m[z]) acc += (double) row[z];
+  }
+  __shared__ double s[8];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? s[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;
+  }
+}
+
+__global__ void partial_sum_kernel(const double *partials, int n, double *out) {
+  __shared__ double s[32];
+  double v = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+  v = warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) *out = v;
+  }
+}
+
+// x <- mask ? (x - shift) * scale : 0   (windowOperator + the mean/size step of varianceOperator)
+template <typename T> __global__ void masked_shift_scale_kernel(T *f, const unsigned char *mask, int n, T shift, T scale) {
+  const long nrows = (long) n * n;
+  for (long r = blockIdx.x; r < nrows; r += gridDim.x) {
+    T *row = f + r * (n + 2);
+    const unsigned char *m = mask + r * n;
+    for (int z = threadIdx.x; z < n; z += blockDim.x) row[z] = m[z] ? (row[z] - shift) * scale : (T) 0;
+  }
+}
+
+template <typename T> static int masked_sum_t(const void *f, const unsigned char *mask, int n, double *host_out, cudaStream_t st) {
+  const long nrows = (long) n * n;
+  const int grid = (int) (nrows < 148 * 8 ? nrows : 148 * 8);
+  double *part = nullptr;
+  GX_CUDA_CHECK(cudaMalloc(&part, (grid + 1) * sizeof(double)));
+  masked_sum_kernel<T><<<grid, 256, 0, st>>>((const T *) f, mask, n, part);
+  partial_sum_kernel<<<1, 1024, 0, st>>>(part, grid, part + grid);
+  count_launch(2);
+  GX_LAUNCH_CHECK();
+  GX_CUDA_CHECK(cudaMemcpyAsync(host_out, part + grid, sizeof(double), cudaMemcpyDeviceToHost, st));
+  GX_CUDA_CHECK(cudaStreamSynchronize(st));
+  GX_CUDA_CHECK(cudaFree(part));
+  return 0;
+}
+
+template <typename T>
+static int masked_shift_scale_t(void *f, const unsigned char *mask, int n, double shift, double scale, cudaStream_t st) {
+  const long nrows = (long) n * n;
+  masked_shift_scale_kernel<T><<<(int) (nrows < 148 * 16 ? nrows : 148 * 16), 256, 0, st>>>((T *) f, mask, n, (T) shift, (T) scale);
+  count_launch();
+  GX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- F <- scale * F / k^2 on the independent slots, 0 at k = 0 (VelocityModification::computeVelocity real-space-derivative
+// branch, linearmodification.hpp:242-262; cosmology::densityToPotential) -------------------------------------------------
+template <typename T> struct ScaleInvK2F {
+  cplx<T> *f; int n; T kmin, scale;
+  __device__ __forceinline__ void init() const {}
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    T kx, ky, kz, k2;
+    slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+    cplx<T> v = f[s];
+    f[s] = (k2 == (T) 0) ? mk<T>(0, 0) : mk<T>(div_rn(mul_rn(scale, v.x), k2), div_rn(mul_rn(scale, v.y), k2));
+  }
+};
+
+template <typename T> static int scale_inv_k2_t(void *field, int n, double L, double scale, cudaStream_t st) {
+  ScaleInvK2F<T> f;
+  f.f = (cplx<T> *) field; f.n = n; f.kmin = (T) (2. * M_PI / (double) (T) L); f.scale = (T) scale;
+  return launch_slot_sweep(n, f, st, 0, "scale_inv_k2");
+}
+
+}  // namespace gx
+
+using namespace gx;
+
+#define GX_DISPATCH(dtype, CALL)                              \
+  do {                                                        \
+    if ((dtype) == GX_F64) { using T = double; return CALL; } \
+    if ((dtype) == GX_F32) { using T = float; return CALL; }  \
+    return gx::fail("bad dtype");                             \
+  } while (0)
+
+extern "C" {
+
+int gx_interp_add(void *dst, const gx_grid_desc *dst_grid, const void *src, const gx_grid_desc *src_grid, int dtype,
+                  void *stream) {
+  if (check_desc(dst_grid, "gx_interp_add") || check_desc(src_grid, "gx_interp_add")) return 1;
+  if (dst == src) return gx::fail("gx_interp_add: source and destination alias");
+  GX_DISPATCH(dtype, interp_add_t<T>(dst, dst_grid, src, src_grid, (cudaStream_t) stream));
+}
+
+int gx_deinterp_add(void *dst_coarse, const gx_grid_desc *coarse_grid, const void *src_fine, const gx_grid_desc *fine_grid,
+                    int dtype, double scale, void *stream) {
+  if (check_desc(coarse_grid, "gx_deinterp_add") || check_desc(fine_grid, "gx_deinterp_add")) return 1;
+  if (!(fine_grid->cell_size < coarse_grid->cell_size)) return gx::fail("gx_deinterp_add: the source must be the finer grid");
+  GX_DISPATCH(dtype, deinterp_add_t<T>(dst_coarse, coarse_grid, src_fine, fine_grid, scale, (cudaStream_t) stream));
+}
+
+int gx_zero_window(void *field, const gx_grid_desc *grid, int dtype, const gx_grid_desc *window_grid, int inside,
+                   void *stream) {
+  if (check_desc(grid, "gx_zero_window") || check_desc(window_grid, "gx_zero_window")) return 1;
+  GX_DISPATCH(dtype, zero_window_t<T>(field, grid, window_grid, inside, (cudaStream_t) stream));
+}
+
+int gx_masked_sum(const void *field, const unsigned char *mask_n3, int n, int dtype, double *host_out, void *stream) {
+  GX_DISPATCH(dtype, masked_sum_t<T>(field, mask_n3, n, host_out, (cudaStream_t) stream));
+}
+
+int gx_masked_shift_scale(void *field, const unsigned char *mask_n3, int n, int dtype, double shift, double scale,
+                          void *stream) {
+  GX_DISPATCH(dtype, masked_shift_scale_t<T>(field, mask_n3, n, shift, scale, (cudaStream_t) stream));
+}
+
+int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, void *stream) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  GX_DISPATCH(dtype, scale_inv_k2_t<T>(field, n, grid_length, scale, (cudaStream_t) stream));
+}
+
+}  // extern "C"
