@@ -231,14 +231,17 @@ def run_ours(args):
             classes[nm] = (int(cnt), float(tot))
 
     # e2e: host buffers, copies inside the timed region (wall clock around synchronous calls + device sync)
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    if args.no_e2e:   # development switch for kernel A/B runs; the line then carries no e2e number
+        e2e_s = float("nan")
+    else:
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
     tab_bytes = 3 * 8 * 213
 
     # roofline of the dominant kernel class
@@ -293,8 +296,8 @@ def run_ours(args):
             "config": {"workload": workload_name(n, "f64"), "output": "float32 pos+vel, component-major",
                        "l2": "inputs larger than L2 (each field %.2f GB)" % (fbytes / 1e9)},
             "clocks": clocks,
-            "e2e": {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": tab_bytes,
-                    "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
+            "e2e": None if args.no_e2e else {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": tab_bytes,
+                                             "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
@@ -310,6 +313,7 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "2048")))
     ap.add_argument("--cpu-n", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

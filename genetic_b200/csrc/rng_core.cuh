@@ -201,9 +201,53 @@ GX_HD void swb_round(State &st) {
   st.c = (uint32_t) c;
 }
 
+#ifdef __CUDA_ARCH__
+// The same round with the 48-bit borrow kept in the hardware carry flag. A word is held as (hi, lo) = (x >> 16,
+// (x & 0xffff) << 16): subtracting the two halves with sub.cc/subc.cc makes the borrow out of the upper half exactly the
+// borrow of the 48-bit subtraction, and the incoming borrow enters at bit 0 of `lo`, ripples through its 16 zero bits
+// (leaving 0xffff there when it was set) and lands on bit 16 -- the word's own bit 0. One `and` clears those 16 bits.
+// 3 instructions per word step instead of 11 (two 64-bit subtractions, shift, mask, carry extraction); the generator
+// advance is ~70 % of all instructions the noise kernels issue.
+__device__ __forceinline__ void swb_round_cc(uint32_t (&lo)[12], uint32_t (&hi)[12], uint32_t &c) {
+  asm volatile(
+      "{\n\t.reg .u32 t;\n\t"
+      "sub.cc.u32 t, 0, %24;\n\t"  // carry flag <- (c != 0)
+      "subc.cc.u32 %0, %7, %0;\n\t subc.cc.u32 %12, %19, %12;\n\t and.b32 %0, %0, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %1, %8, %1;\n\t subc.cc.u32 %13, %20, %13;\n\t and.b32 %1, %1, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %2, %9, %2;\n\t subc.cc.u32 %14, %21, %14;\n\t and.b32 %2, %2, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %3, %10, %3;\n\t subc.cc.u32 %15, %22, %15;\n\t and.b32 %3, %3, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %4, %11, %4;\n\t subc.cc.u32 %16, %23, %16;\n\t and.b32 %4, %4, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %5, %0, %5;\n\t subc.cc.u32 %17, %12, %17;\n\t and.b32 %5, %5, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %6, %1, %6;\n\t subc.cc.u32 %18, %13, %18;\n\t and.b32 %6, %6, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %7, %2, %7;\n\t subc.cc.u32 %19, %14, %19;\n\t and.b32 %7, %7, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %8, %3, %8;\n\t subc.cc.u32 %20, %15, %20;\n\t and.b32 %8, %8, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %9, %4, %9;\n\t subc.cc.u32 %21, %16, %21;\n\t and.b32 %9, %9, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %10, %5, %10;\n\t subc.cc.u32 %22, %17, %22;\n\t and.b32 %10, %10, 0xFFFF0000;\n\t"
+      "subc.cc.u32 %11, %6, %11;\n\t subc.cc.u32 %23, %18, %23;\n\t and.b32 %11, %11, 0xFFFF0000;\n\t"
+      "subc.u32 %24, 0, 0;\n\t"  // c <- 0 or 0xffffffff
+      "}"
+      : "+r"(lo[0]), "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]), "+r"(lo[4]), "+r"(lo[5]), "+r"(lo[6]), "+r"(lo[7]),
+        "+r"(lo[8]), "+r"(lo[9]), "+r"(lo[10]), "+r"(lo[11]), "+r"(hi[0]), "+r"(hi[1]), "+r"(hi[2]), "+r"(hi[3]),
+        "+r"(hi[4]), "+r"(hi[5]), "+r"(hi[6]), "+r"(hi[7]), "+r"(hi[8]), "+r"(hi[9]), "+r"(hi[10]), "+r"(hi[11]),
+        "+r"(c));
+}
+#endif
+
 // increment_state of ranlxs2: 397 = 33*12 + 1 word steps, then rotate so x[0] is the oldest again.
 GX_HD void advance_block(State &st) {
+#ifdef __CUDA_ARCH__
+  uint32_t lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { lo[i] = (uint32_t) (st.x[i] << 16); hi[i] = (uint32_t) (st.x[i] >> 16); }
+  uint32_t c = st.c;
+#pragma unroll 3
+  for (int r = 0; r < 33; ++r) swb_round_cc(lo, hi, c);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) st.x[i] = ((uint64_t) hi[i] << 16) | (uint64_t) (lo[i] >> 16);
+  st.c = c & 1u;
+#else
   for (int r = 0; r < 33; ++r) swb_round(st);
+#endif
   const uint64_t y = st.x[7] - st.x[0] - (uint64_t) st.c;
   st.c = (uint32_t) (y >> 63);
   const uint64_t newest = y & kMask48;

@@ -3,6 +3,7 @@
 #include "spectral.cuh"
 #include "spectrum_host.h"
 #include <vector>
+#include <cstdlib>
 
 namespace gx {
 
@@ -89,6 +90,40 @@ template <typename T> struct ApplyTransferF : SpecInit {
   }
 };
 
+// ---- the same through a table over the integer |k|^2 ---------------------------------------------------------------
+// C(k) only depends on m = ix^2 + iy^2 + iz^2 (signed mode numbers), at most 3 (n/2)^2 + 1 distinct values (25 MB of
+// doubles at n = 2048: resident in the 126 MB L2). Evaluating log / spline / exp / pow once per m instead of once per
+// mode turns the sweep from FP64-bound (53 % FP64 pipe, 1.4 TB/s at 2048^3, profiles/r1s3_*) into a streaming pass.
+// The table is rebuilt by every call (a few hundred microseconds): nothing is cached between calls.
+// Rounding: the reference forms k^2 from the three rounded products (slot_k); the table uses k^2 = m * kmin^2. The two
+// differ by a few ulp, i.e. ~1e-16 relative in the factor -- the north star's tolerance is 1e-10 (the in-kernel
+// evaluation above already differs from glibc's pow/log/exp by an ulp).
+template <typename T> struct TransferTableF : SpecInit {
+  T *tab; long mcount; T kmin, norm; double power; int divide_k2;
+  __device__ __forceinline__ void build(long m) const {
+    const T k2 = mul_rn((T) m, mul_rn(kmin, kmin));
+    const double *t = lx();
+    T spec = mul_rn(spectrum_power<T>(sp, t, t + sp.m, t + 2 * sp.m, sqrt_rn(k2)), norm);
+    spec = spec_pow<T>(spec, power);
+    if (divide_k2) spec = (m != 0) ? div_rn(spec, k2) : (T) 0;
+    tab[m] = spec;
+  }
+};
+template <typename T> __global__ void __launch_bounds__(256) transfer_table_kernel(TransferTableF<T> f) {
+  f.init();
+  for (long m = (long) blockIdx.x * blockDim.x + threadIdx.x; m < f.mcount; m += (long) gridDim.x * blockDim.x) f.build(m);
+}
+template <typename T> struct ApplyTableF : NoInit {
+  cplx<T> *f; const T *__restrict__ tab; int n;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    const int a = signed_mode(ix, n), b = signed_mode(iy, n);
+    const T w = __ldg(tab + ((long) a * a + (long) b * b + (long) iz * iz));
+    cplx<T> v = f[s];
+    f[s] = mk<T>(mul_rn(v.x, w), mul_rn(v.y, w));
+  }
+};
+
 template <typename T> struct ApplyTransferFieldF : NoInit {
   cplx<T> *f; const cplx<T> *cov; int n; double power;
   __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
@@ -100,7 +135,7 @@ template <typename T> struct ApplyTransferFieldF : NoInit {
 };
 
 // ---- filters (filter.hpp) ---------------------------------------------------------------------------
-struct FilterDesc { int nf; gx_filter_factor f[8]; };
+struct FilterDesc { int nf; gx_filter_factor f[16]; };
 
 template <typename T> __device__ __forceinline__ T filter_eval(const FilterDesc &d, T k) {
   T r = (T) 1;
@@ -199,9 +234,37 @@ template <typename T> static int covariance_field_t(void *out, int n, double L, 
   return launch_slot_sweep(n, f, st, 3 * f.sp.m * sizeof(double), "covariance_field");
 }
 
+static void *g_transfer_tab = nullptr;   // grow-only workspace for the |k|^2 table (values are rebuilt by every call)
+static size_t g_transfer_tab_bytes = 0;
+
 template <typename T>
 static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, double power, cudaStream_t st,
                             int divide_k2 = 0, int iy0 = 0, int ny = -1) {
+  static int use_table = -1;
+  if (use_table < 0) { const char *e = getenv("GX_TRANSFER_TABLE"); use_table = (e && e[0] == '0') ? 0 : 1; }
+  if (use_table) {
+    const long h = n / 2, mcount = 3 * h * h + 1;
+    if (g_transfer_tab_bytes < mcount * sizeof(T)) {
+      if (g_transfer_tab) { GX_CUDA_CHECK(cudaDeviceSynchronize()); GX_CUDA_CHECK(cudaFree(g_transfer_tab)); g_transfer_tab = nullptr; }
+      GX_CUDA_CHECK(cudaMalloc(&g_transfer_tab, mcount * sizeof(T)));
+      g_transfer_tab_bytes = mcount * sizeof(T);
+    }
+    TransferTableF<T> tf;
+    tf.sp = gx_spectrum_device_view(s);
+    tf.tab = (T *) g_transfer_tab; tf.mcount = mcount; tf.kmin = kmin_of<T>(L); tf.norm = (T) gx_spectrum_grid_norm(s, L, n);
+    tf.power = power; tf.divide_k2 = divide_k2;
+    {
+      GX_TIMED("transfer_table", st);
+      long blocks = (mcount + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      transfer_table_kernel<T><<<(unsigned) blocks, 256, 3 * tf.sp.m * sizeof(double), st>>>(tf);
+      count_launch();
+    }
+    GX_LAUNCH_CHECK();
+    ApplyTableF<T> f;
+    f.f = (cplx<T> *) field; f.tab = (const T *) g_transfer_tab; f.n = n;
+    return launch_slot_sweep(n, f, st, 0, "apply_transfer", iy0, ny);
+  }
   ApplyTransferF<T> f;
   f.sp = gx_spectrum_device_view(s);
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.norm = (T) gx_spectrum_grid_norm(s, L, n); f.power = power;
@@ -217,7 +280,7 @@ template <typename T> static int apply_transfer_field_t(void *field, const void 
 
 template <typename T>
 static int apply_filter_t(void *field, int n, double L, const gx_filter_factor *fac, int nf, cudaStream_t st) {
-  if (nf < 0 || nf > 8) return gx::fail("gx_apply_filter: at most 8 factors");
+  if (nf < 0 || nf > 16) return gx::fail("gx_apply_filter: at most 16 factors");
   ApplyFilterF<T> f;
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.d.nf = nf;
   for (int i = 0; i < nf; ++i) f.d.f[i] = fac[i];

@@ -62,8 +62,42 @@ class Grid:
         self.size, self.size2, self.size3 = n, n * n, n * n * n
         self.kMin = T(2. * math.pi / float(self.thisGridSize))  # setKmin, grid.hpp:128-130
 
+        self.simEquivalentSize = int(round(float(simsize) / float(self.cellSize)))  # grid.hpp:111
+        self.flags = np.zeros(0, dtype=np.int64)  # sorted flagged cell indices (Grid::flagCells / getFlaggedCells)
+        self._mask = None
+
     def getFourierKmin(self):
         return self.kMin
+
+    def desc(self):
+        """The const metadata a cross-grid kernel needs (gx_grid_desc)."""
+        d = L.GridDesc()
+        d.n, d.cell_size, d.domain_size = self.size, float(self.cellSize), float(self.periodicDomainSize)
+        for a in range(3):
+            d.offset_lower[a] = float(self.offsetLower[a])
+        return d
+
+    def flagCells(self, indices):
+        self.flags = np.unique(np.asarray(indices, dtype=np.int64).reshape(-1))
+        self._mask = None
+
+    def getFlaggedCells(self):
+        return self.flags
+
+    def flagMask(self, complement=False):
+        """Device byte mask of the flagged cells (n^3 bytes, 1 = flagged), cached until the flags change."""
+        if self._mask is None:
+            self._mask = {}
+        if complement not in self._mask:
+            lib = L.load()
+            m = np.full(self.size3, 1 if complement else 0, dtype=np.uint8)
+            m[self.flags] = 0 if complement else 1
+            p = C.c_void_p()
+            lib.gx_malloc(C.byref(p), m.nbytes)
+            lib.gx_memcpy_h2d(p, m.ctypes.data_as(C.c_void_p), m.nbytes, None)
+            lib.gx_synchronize(None)
+            self._mask[complement] = p
+        return self._mask[complement]
 
     def coversFullSimulation(self):
         return self.periodicDomainSize == self.thisGridSize
@@ -218,6 +252,68 @@ class Field:
 
     def norm(self):
         return math.sqrt(self.innerProduct(self))
+
+    def __iadd__(self, other):
+        """operator+= over the whole storage (tools/numerics/vectormath.hpp)."""
+        self.lib.gx_axpy(self.ptr, other.ptr, self.n, self.dt, 1.0, self.stream)
+        return self
+
+    def __isub__(self, other):
+        self.lib.gx_axpy(self.ptr, other.ptr, self.n, self.dt, -1.0, self.stream)
+        return self
+
+    def __neg__(self):
+        f = self.copy()
+        f *= -1.0
+        return f
+
+    def mulMask(self, mask_dev):
+        """operator*=(Field<char>) (field.hpp:306-318) with the mask as n^3 device bytes."""
+        assert not self.fourier
+        self.lib.gx_mul_mask(self.ptr, mask_dev, self.n, self.dt, self.stream)
+
+    # ---- windows and other grids (field.hpp:752-849) ---------------------------------------------------
+    def setZeroInsideWindow(self, window_grid):
+        self.toReal()
+        self.lib.gx_zero_window(self.ptr, C.byref(self.grid.desc()), self.dt, C.byref(window_grid.desc()), 1, self.stream)
+
+    def setZeroOutsideWindow(self, window_grid):
+        self.toReal()
+        self.lib.gx_zero_window(self.ptr, C.byref(self.grid.desc()), self.dt, C.byref(window_grid.desc()), 0, self.stream)
+
+    def applyFilterInWindow(self, filt, window_grid, windowFirst):
+        """Field::applyFilterInWindow (field.hpp:752-772); the window is window_grid.getWindow()."""
+        inWindow = self.copy()
+        if windowFirst:
+            inWindow.setZeroOutsideWindow(window_grid)
+            inWindow.toFourier()
+            inWindow.applyFilter(filt)
+        else:
+            inWindow.toFourier()
+            inWindow.applyFilter(filt)
+            inWindow.setZeroOutsideWindow(window_grid)
+        self.setZeroInsideWindow(window_grid)
+        if inWindow.fourier:
+            self.toFourier()
+        else:
+            self.toReal()
+        self += inWindow
+
+    def addFieldFromDifferentGrid(self, source):
+        """Field::addFieldFromDifferentGrid (field.hpp:804-812,834-840): tricubic interpolation of a coarser source,
+        sub-cell average of a finer one."""
+        source.toReal()
+        self.toReal()
+        self.lib.gx_interp_add(self.ptr, C.byref(self.grid.desc()), source.ptr, C.byref(source.grid.desc()), self.dt,
+                               self.stream)
+
+    def addFieldFromDifferentGridWithFilter(self, source, filt):
+        """FILTER_ON_COARSE_GRID branch (field.hpp:819-832), the reference's default build."""
+        tmp = source.copy()
+        tmp.applyFilter(filt)
+        tmp.toReal()
+        self.toReal()
+        self.addFieldFromDifferentGrid(tmp)
 
 
 # ---- filters -----------------------------------------------------------------------------------------

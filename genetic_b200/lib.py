@@ -21,6 +21,10 @@ class IcParams(C.Structure):
                 ("vel_ratio", C.c_double)]
 
 
+class GridDesc(C.Structure):
+    _fields_ = [("n", C.c_int), ("cell_size", C.c_double), ("offset_lower", C.c_double * 3), ("domain_size", C.c_double)]
+
+
 class FilterFactor(C.Structure):
     _fields_ = [("kind", C.c_int), ("kcut", C.c_double), ("temperature", C.c_double), ("power", C.c_int)]
 
@@ -73,6 +77,12 @@ PROTOTYPES = {
     "gx_dot_real": (ci, [vp, vp, ci, ci, P(cd), vp]),
     "gx_get_mode": (ci, [vp, ci, ci, ci, ci, ci, P(cd), P(cd)]),
     "gx_set_mode": (ci, [vp, ci, ci, ci, ci, ci, cd, cd]),
+    "gx_interp_add": (ci, [vp, P(GridDesc), vp, P(GridDesc), ci, vp]),
+    "gx_deinterp_add": (ci, [vp, P(GridDesc), vp, P(GridDesc), ci, cd, vp]),
+    "gx_zero_window": (ci, [vp, P(GridDesc), ci, P(GridDesc), ci, vp]),
+    "gx_masked_sum": (ci, [vp, vp, ci, ci, P(cd), vp]),
+    "gx_masked_shift_scale": (ci, [vp, vp, ci, ci, cd, cd, vp]),
+    "gx_scale_inv_k2": (ci, [vp, ci, ci, cd, cd, vp]),
     "gx_zeldovich_fourier": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_zeldovich_offset": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_emit_component": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, vp, ci, cl, cll, cll, vp]),

@@ -130,6 +130,39 @@ int gx_dot_real(const void *a, const void *b, int n, int dtype, double *host_out
 int gx_get_mode(const void *field, int n, int dtype, int kx, int ky, int kz, double *re, double *im); /* getFourierCoefficient */
 int gx_set_mode(void *field, int n, int dtype, int kx, int ky, int kz, double re, double im);         /* setFourierCoefficient */
 
+/* ---- zoom levels: fields on grids of different resolution, windows, flagged-cell masks ----------------------------- */
+typedef struct {
+  int n;                  /* Grid::size */
+  double cell_size;       /* Grid::cellSize */
+  double offset_lower[3]; /* Grid::offsetLower */
+  double domain_size;     /* Grid::periodicDomainSize */
+} gx_grid_desc;           /* the const metadata of grids::Grid<T>, grid.hpp:84-93 */
+/* Field::addFieldFromDifferentGrid (field.hpp:804-812; evaluator.hpp:31-57), both fields in real space:
+   coarser source: every dst cell the source covers += tricubic interpolation of the source at the cell centre
+                   (evaluateInterpolated field.hpp:483-508, makeTricubicInterpolator :598-617 -- wrapped stencil if the source
+                   spans the box, clamped otherwise; LocalUnitTricubicApproximation tricubic.hpp:54-77);
+   finer source  : every dst cell whose first or last sub-cell the source holds += mean of the sub-cells it holds
+                   (SubSampleEvaluator evaluator.hpp:168-205, SubSampleGrid::forEachSubcell virtualgrid.hpp:570-600). */
+int gx_interp_add(void *dst, const gx_grid_desc *dst_grid, const void *src, const gx_grid_desc *src_grid, int dtype,
+                  void *stream);
+/* The deinterpolation loop of generateMultilevelCovectorFromHiresCovector (multilevelgrid.hpp:283-297):
+   dst_coarse += sum over fine cells of Field::deInterpolate(centroid, value * scale) (field.hpp:420-480), i.e. the transpose
+   of the tricubic interpolation (tricubic.hpp:450-549), gathered per coarse cell (deterministic, no atomics). */
+int gx_deinterp_add(void *dst_coarse, const gx_grid_desc *coarse_grid, const void *src_fine, const gx_grid_desc *fine_grid,
+                    int dtype, double scale, void *stream);
+/* Field::setZeroInsideWindow / setZeroOutsideWindow (field.hpp:774-795) for window = window_grid->getWindow()
+   (grid.hpp:502-504): zero the real-space cells whose centroid is inside (inside != 0) / outside the window. */
+int gx_zero_window(void *field, const gx_grid_desc *grid, int dtype, const gx_grid_desc *window_grid, int inside,
+                   void *stream);
+/* flagged cells as a device mask of n^3 bytes (1 = flagged): sum over flagged cells, and
+   x <- flagged ? (x - shift) * scale : 0 (windowOperator / varianceOperator, quadraticmodification.hpp:172-221) */
+int gx_masked_sum(const void *field, const unsigned char *mask_n3, int n, int dtype, double *host_out, void *stream);
+int gx_masked_shift_scale(void *field, const unsigned char *mask_n3, int n, int dtype, double shift, double scale,
+                          void *stream);
+/* F <- scale * F / k^2 on the independent modes, 0 at k = 0 (VelocityModification::computeVelocity, real-space-derivative
+   branch, linearmodification.hpp:242-262; cosmology::densityToPotential) */
+int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, void *stream);
+
 /* ---- Zeldovich (ZeldovichParticleGenerator::calculateOffsetFields, zeldovich.hpp:152-181,248-251) ------- */
 /* psi_axis(k) = i k_axis delta_k / k^2 (0 at k=0 and where k_axis is the Nyquist mode), independent slots
    only, into a separate field (generateNewFourierFields, fourier.hpp:253-274). axis: 0,1,2. */

@@ -1,0 +1,37 @@
+"""CPU tests of the Python HOST LOGIC of the multi-level layer (genetic_b200/multilevel.py): the same test bodies as
+tests/test_gpu_multilevel.py, run with the C ABI replaced by a numpy stand-in (tests/host/mock_device.py, test
+infrastructure). They check the reference's control flow as restated by the host classes (metric, covectors,
+Gram-Schmidt, variance iterations, splice + conjugate gradient) against the oracle's independent restatement and the
+reference's goldens; the kernels themselves are checked on the GPU by the `-m gpu` run of the same bodies."""
+import importlib.util
+import os
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_mock = _load("gx_mock_device", os.path.join(HERE, "host", "mock_device.py"))
+_cases = _load("gx_multilevel_cases", os.path.join(HERE, "test_gpu_multilevel.py"))
+
+
+@pytest.fixture(autouse=True)
+def mock_device(monkeypatch):
+    return _mock.install(monkeypatch)
+
+
+test_chi2_two_levels_golden_02m = _cases.test_chi2_two_levels_golden_02m
+test_metric_vs_oracle_three_levels = _cases.test_metric_vs_oracle_three_levels
+test_zoom_combination_vs_oracle_and_golden_01c = _cases.test_zoom_combination_vs_oracle_and_golden_01c
+test_two_linear_modifications_golden_02c = _cases.test_two_linear_modifications_golden_02c
+test_velocity_covector_vs_oracle = _cases.test_velocity_covector_vs_oracle
+test_variance_values_golden_02f_02g = _cases.test_variance_values_golden_02f_02g
+test_variance_modification_reaches_target_and_matches_oracle = _cases.test_variance_modification_reaches_target_and_matches_oracle
+test_splice_golden_24_and_oracle = _cases.test_splice_golden_24_and_oracle
