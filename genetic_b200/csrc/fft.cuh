@@ -442,71 +442,10 @@ fft_rows_c2r_kernel(const T *data, long row0, long nrows, const cplx<T> *__restr
   B::run(v, t, line, twM, [&](int k, C val) { if (active) store(row, k, val); });
 }
 
-// The same transform as a persistent, double-buffered kernel: while a CTA works on one group of LR rows, the next
-// group's rows are already on their way into the other half of shared memory (cp.async, no registers held), so every
-// resident CTA keeps a full tile of loads in flight all the time instead of only during its load phase. The single-shot
-// kernel above has at most 5 x 32 KB per SM in flight and only while a CTA is loading (~1/3 of its life): by Little's law
-// that caps the pass near 2.4-2.9 TB/s, which is what it measures (profiles/r1s3_*).
-template <typename T, int N> struct RowsPipeCfg {
-  using Base = RowsCfg<T, N>;
-  static constexpr int LR = Base::LR, threads = Base::threads, pitch = Base::pitch;
-  static constexpr size_t smem = 2 * Base::smem;
-  static constexpr int MINB = (sizeof(T) == 8) ? 3 : 3;
-};
-
-template <typename T, int N, class Store>
-__global__ void __launch_bounds__(RowsPipeCfg<T, N>::threads, RowsPipeCfg<T, N>::MINB)
-fft_rows_c2r_pipe_kernel(const T *data, long row0, long nrows, const cplx<T> *__restrict__ twM,
-                         const cplx<T> *__restrict__ twN, Store store) {
-  using C = cplx<T>;
-  using Cfg = RowsPipeCfg<T, N>;
-  using B = BlockFFT<T, N / 2, 1>;
-  constexpr int M = N / 2, E = B::E, P = B::P, LR = Cfg::LR;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  C *smem = reinterpret_cast<C *>(smem_raw);
-  const int l = threadIdx.x / P, t = threadIdx.x % P;
-  const long ngroups = (nrows + LR - 1) / LR;
-
-  auto issue = [&](long group, int b) {
-    const long row = row0 + group * LR + l;
-    const bool active = row < row0 + nrows;
-    const C *rowp = reinterpret_cast<const C *>(data + (active ? row : row0) * (long) (N + 2));
-    C *line = smem + ((size_t) b * LR + l) * Cfg::pitch;
-#pragma unroll
-    for (int i = 0; i < E; ++i) cp_async_elem<C>(line + t + i * P, rowp + t + i * P, active);
-    if (t == 0) cp_async_elem<C>(line + M, rowp + M, active);
-    cp_async_commit();
-  };
-
-  long group = blockIdx.x;
-  if (group < ngroups) issue(group, 0);
-  for (int it = 0; group < ngroups; group += gridDim.x, ++it) {
-    const int b = it & 1;
-    const long next = group + gridDim.x;
-    if (next < ngroups) { issue(next, b ^ 1); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncthreads();  // every thread's copies of the current group have landed
-    const long row = row0 + group * LR + l;
-    const bool active = row < row0 + nrows;
-    C *line = smem + ((size_t) b * LR + l) * Cfg::pitch;
-    C v[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-      const int k = t + i * P;
-      C xk = line[k];
-      C xm = cconj(line[M - k]);
-      if (k == 0) { xk.y = 0; xm.y = 0; }
-      const C s = cadd(xk, xm);
-      const C d = csub(xk, xm);
-      const C w = cconj(__ldg(twN + k));
-      const C wd = cmul(w, d);
-      v[i] = mk<T>(s.x - wd.y, s.y + wd.x);
-    }
-    __syncthreads();  // inputs consumed: the buffer becomes the stage exchange area
-    B::run(v, t, line, twM, [&](int k, C val) { if (active) store(row, k, val); });
-    __syncthreads();  // the next iteration's prefetch targets this buffer
-  }
-}
+// (Also measured and dropped, profiles/r1s5_bench2048_rows_{single,pipelined}.json: a persistent form of this kernel with
+// the next group of rows prefetched by cp.async into a second shared-memory buffer -- 3 CTAs of 128 threads per SM instead
+// of 5 -- took 203 ms per step at 2048^3 against 174 ms: the pass is bound by how many warps an SM has to cover the
+// shared-memory exchange and FP64 latency of the radix stages, not by loads in flight.)
 
 template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream_t st) {
   using Cfg = RowsCfg<T, N>;
@@ -526,39 +465,14 @@ template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream
 template <typename T, int N, class Store>
 int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStream_t st) {
   using Cfg = RowsCfg<T, N>;
-  static int pipe = -1;
-  if (pipe < 0) { const char *e = getenv("GX_ROWS_PIPE"); pipe = (e && e[0] == '0') ? 0 : 1; }
-  const long groups = (nrows + Cfg::LR - 1) / Cfg::LR;
-  if (groups <= 0) return 0;
-  if (pipe && N >= 256) {
-    using PC = RowsPipeCfg<T, N>;
-    auto kern = fft_rows_c2r_pipe_kernel<T, N, Store>;
-    static int resident = 0, resident_dev = -1;
-    int dev = 0;
-    GX_CUDA_CHECK(cudaGetDevice(&dev));
-    if (resident_dev != dev) {
-      GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PC::smem));
-      GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      int per_sm = 0, sms = 0;
-      GX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PC::threads, PC::smem));
-      GX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      resident = per_sm * sms;
-      resident_dev = dev;
-      if (resident < 1) return fail("fft_rows_c2r_pipe: kernel cannot be resident");
-    }
-    const long grid = groups < resident ? groups : resident;
-    GX_TIMED("fft_rows_c2r", st);
-    kern<<<(unsigned) grid, PC::threads, PC::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store);
-    count_launch();
-    GX_LAUNCH_CHECK();
-    return 0;
-  }
   auto kern = fft_rows_c2r_kernel<T, N, Store>;
   if (Cfg::smem > 48 * 1024)
     GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
+  const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
+  if (grid <= 0) return 0;
   GX_TIMED("fft_rows_c2r", st);
-  kern<<<(unsigned) groups, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2),
-                                                          twiddle_table<T>(N), store);
+  kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2),
+                                                        twiddle_table<T>(N), store);
   count_launch();
   GX_LAUNCH_CHECK();
   return 0;

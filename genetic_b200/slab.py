@@ -207,18 +207,79 @@ class SlabPipeline:
             emit(axis, self.bufA)
 
 
+class EmitStager:
+    """Bounded staging for the particles of one rank: the z-pass emits `planes` x-planes of one component at a time into
+    one of two device halves; with `to_host` each half is copied to pinned host memory on a copy stream while the next
+    emit runs (the host side is a two-slot ring: a writer thread is its consumer in an application). Keeps a 2048^3 run
+    inside 180 GB at any world size -- whole-slab pos+vel arrays would need 24 bytes x n^3 / world per rank on top of
+    the three slab buffers."""
+
+    def __init__(self, ops, geo, out_dtype, stage_bytes=1 << 30):
+        import torch
+        self.torch, self.ops, self.geo = torch, ops, geo
+        self.osz = np.dtype(out_dtype).itemsize
+        n2 = geo.n * geo.n
+        self.planes = int(max(1, min(geo.P, stage_bytes // (4 * n2 * self.osz))))
+        half = self.planes * n2 * self.osz
+        self.dev = [(ops.alloc(half), ops.alloc(half)) for _ in range(2)]
+        self.host = None
+        self.copy_stream = torch.cuda.Stream()
+        self.ev_copy = [None, None]
+        self.turn = 0
+        self.d2h_bytes = 0
+
+    def enable_host(self):
+        if self.host is None:
+            half = self.dev[0][0].numel()
+            self.host = [(self.torch.empty(half, dtype=self.torch.uint8, pin_memory=True),
+                          self.torch.empty(half, dtype=self.torch.uint8, pin_memory=True)) for _ in range(2)]
+
+    def emit(self, work, axis, grid, vel_ratio, out_dtype, to_host):
+        torch, g = self.torch, self.geo
+        cur = torch.cuda.current_stream()
+        for plane0 in range(0, g.P, self.planes):
+            npl = min(self.planes, g.P - plane0)
+            b = self.turn
+            self.turn ^= 1
+            if to_host and self.ev_copy[b] is not None:
+                cur.wait_event(self.ev_copy[b])          # the half is free once its previous copy has finished
+            dpos, dvel = self.dev[b]
+            self.ops.z_emit(work, axis, float(grid.cellSize), float(grid.offsetLower[axis]),
+                            float(grid.periodicDomainSize), vel_ratio, plane0, npl, dpos, dvel, out_dtype)
+            if to_host:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.copy_stream.wait_event(ev)
+                nb = npl * g.n * g.n * self.osz
+                with torch.cuda.stream(self.copy_stream):
+                    self.host[b][0][:nb].copy_(dpos[:nb], non_blocking=True)
+                    self.host[b][1][:nb].copy_(dvel[:nb], non_blocking=True)
+                    self.ev_copy[b] = torch.cuda.Event()
+                    self.ev_copy[b].record(self.copy_stream)
+                self.d2h_bytes += 2 * nb
+
+    def finish(self):
+        self.copy_stream.synchronize()
+
+
 def unigrid_ic_slab(geo, ops, comm, seed, mode, reverse, fix_power, grid, spectrum, vel_ratio, out_dtype, delta, pipe,
-                    out_pos, out_vel, planes_per_emit=None):
-    """One IC for this rank's x-slab: out_pos/out_vel are [3][particles] (component-major) device tensors."""
+                    out_pos, out_vel, planes_per_emit=None, stager=None, to_host=False):
+    """One IC for this rank's x-slab. Either out_pos/out_vel are [3][particles] (component-major) device tensors that
+    receive every particle, or `stager` streams them through bounded staging (and to pinned host memory if to_host)."""
     g = geo
     pipe.draw_delta(delta, seed, mode, reverse, fix_power, float(grid.thisGridSize), spectrum)
     osz = np.dtype(out_dtype).itemsize
 
     def emit(axis, work):
+        if stager is not None:
+            stager.emit(work, axis, grid, vel_ratio, out_dtype, to_host)
+            return
         ops.z_emit(work, axis, float(grid.cellSize), float(grid.offsetLower[axis]), float(grid.periodicDomainSize),
                    vel_ratio, 0, g.P, out_pos[axis * g.particles * osz:], out_vel[axis * g.particles * osz:], out_dtype)
 
     pipe.zeldovich(delta, float(grid.thisGridSize), emit)
+    if stager is not None and to_host:
+        stager.finish()
 
 
 # ---- bench entry (python bench.py under torchrun, N > 1) ------------------------------------------------------------
@@ -241,22 +302,18 @@ def bench_main(args, lib, world, rank, local_rank):
     pipe = SlabPipeline(geo, ops, comm)
     delta = ops.alloc(geo.slab_bytes)
     osz = 4
-    out_pos = ops.alloc(3 * geo.particles * osz)
-    out_vel = ops.alloc(3 * geo.particles * osz)
     vel_ratio = cos.zeldovichVelocityToOffsetRatio(dtype)
-    hpos = torch.empty(3 * geo.particles * osz, dtype=torch.uint8, pin_memory=True)
-    hvel = torch.empty(3 * geo.particles * osz, dtype=torch.uint8, pin_memory=True)
+    stager = EmitStager(ops, geo, out_dtype)   # particles leave through bounded staging, as in gx_unigrid_ic
+    stager.enable_host()
 
     def device_step():
         unigrid_ic_slab(geo, ops, comm, B.SEED, L.NOISE_FOURIER_PARALLEL, 0, 0, grid, spectrum, vel_ratio, out_dtype,
-                        delta, pipe, out_pos, out_vel)
+                        delta, pipe, None, None, stager=stager, to_host=False)
 
     def e2e_step():
         sp = gb.CAMB(cos, B.CAMB_FILE, "all", dtype)
         unigrid_ic_slab(geo, ops, comm, B.SEED, L.NOISE_FOURIER_PARALLEL, 0, 0, grid, sp, vel_ratio, out_dtype, delta,
-                        pipe, out_pos, out_vel)
-        hpos.copy_(out_pos, non_blocking=True)
-        hvel.copy_(out_vel, non_blocking=True)
+                        pipe, None, None, stager=stager, to_host=True)
         torch.cuda.synchronize()
         return sp
 
@@ -318,16 +375,22 @@ def bench_main(args, lib, world, rank, local_rank):
         dom = max(fft_classes, key=lambda k: fft_classes[k][1]) if fft_classes else None
         roof = None
         if dom:
+            # class bytes per step on this rank; a class may be several launches per step
+            class_bytes = {"fft_cols_x": 3 * 2 * geo.slab_bytes, "fft_cols_y": 3 * 2 * geo.slab_bytes,
+                           "fft_rows_c2r": 3 * (geo.slab_bytes + 2 * osz * geo.particles)}
             cnt, tot = classes[dom]
             avg_ms = tot / cnt
-            per_launch = 2 * geo.slab_bytes if dom.startswith("fft_cols") else geo.slab_bytes + 8 * geo.particles
+            per_launch = class_bytes[dom] * args.steps / cnt
             achieved = per_launch / (avg_ms * 1e-3) / 1e9
+            passes = {k: {"GB/s": class_bytes[k] / (classes[k][1] / args.steps * 1e-3) / 1e9,
+                          "frac": class_bytes[k] / (classes[k][1] / args.steps * 1e-3) / 1e9 / peak}
+                      for k in class_bytes if k in classes and classes[k][1] > 0}
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None,
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                     "per_class_ms_per_step_rank0": {k: v[1] / args.steps for k, v in sorted(classes.items())},
-                    "share_of_step": tot / args.steps / ms}
+                    "passes": passes, "share_of_step": tot / args.steps / ms}
         a2a_bytes = 3 * geo.slab_bytes * (world - 1) // world
         line = {"metric": "IC particles/sec (Zeldovich %d^3)" % n, "value": n3 / (ms * 1e-3), "unit": "particles/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,

@@ -1,0 +1,185 @@
+"""Host logic around the zoom levels: cell selection and zoom-window placement (pure index arithmetic, no field data).
+
+Reference (paths relative to genetIC/src/):
+  ICGenerator::select / selectSphere / selectCube / selectNearest     ic.hpp:1447-1524
+  ICGenerator::initZoomGrid                                            ic.hpp:398-479
+  ICGenerator::initZoomGridWithLowLeftCornerAt (flag transfer)         ic.hpp:502-598
+  Window<int>                                                          simulation/window.hpp
+"""
+import math
+
+import numpy as np
+
+from . import lib as L
+
+
+def _centroids(grid, axis):
+    """Grid::getCentroidFromCoordinate (grid.hpp:662-669): coord*cellSize, + offsetLower, + cellSize/2, in the grid's type."""
+    T = grid.dtype.type
+    c = np.arange(grid.size).astype(grid.dtype)
+    return (c * T(grid.cellSize) + T(grid.offsetLower[axis])) + T(grid.cellSize) / T(2)
+
+
+def _wrapped_offset(base, a, b):
+    """Grid::getWrappedOffset with the base grid's period (ICGenerator::get_wrapped_delta, ic.hpp:1368-1370)."""
+    d = np.asarray(b) - np.asarray(a)
+    Lbox = base.periodicDomainSize
+    d = np.where(d < -Lbox / 2, d + Lbox, d)
+    return np.where(d > Lbox / 2, d - Lbox, d)
+
+
+def select(context, centre, inclusion):
+    """ICGenerator::select (ic.hpp:1458-1484): on every level flag the cells whose centroid offset from `centre`
+    satisfies inclusion(dx, dy, dz)."""
+    base = context.getGridForLevel(0)
+    for g in context.grids:
+        d = [_wrapped_offset(base, _centroids(g, a), g.dtype.type(centre[a])) for a in range(3)]
+        m = inclusion(d[0][:, None, None], d[1][None, :, None], d[2][None, None, :])
+        g.flagCells(np.flatnonzero(np.broadcast_to(m, (g.size,) * 3).reshape(-1)))
+
+
+def selectSphere(context, centre, radius):
+    r2 = float(np.float32(radius) * np.float32(radius))   # selectSphere(float radius), ic.hpp:1490-1496
+    select(context, centre, lambda x, y, z: x * x + y * y + z * z < r2)
+
+
+def selectCube(context, centre, side):
+    h = float(np.float32(side) / np.float32(2))           # selectCube(float side), ic.hpp:1519-1524
+    select(context, centre, lambda x, y, z: (np.abs(x) < h) & (np.abs(y) < h) & (np.abs(z) < h))
+
+
+def selectNearest(context, centre):
+    """ICGenerator::selectNearest (ic.hpp:1447-1455): the cell of the deepest level that holds `centre`
+    (Grid::getIndexFromPoint, grid.hpp:672-677)."""
+    for g in context.grids:
+        g.flagCells([])
+    g = context.grids[-1]
+    c = []
+    for a in range(3):
+        x = math.fmod(float(centre[a]) - float(g.offsetLower[a]), float(g.periodicDomainSize))
+        if x < 0:
+            x += float(g.periodicDomainSize)
+        c.append(int(math.floor(x / float(g.cellSize))))
+    g.flagCells([(c[0] * g.size + c[1]) * g.size + c[2]])
+
+
+class _Window:
+    """Window<int> (window.hpp): a periodic cuboid [lower, upper) per axis."""
+
+    def __init__(self, wrap, point):
+        self.wrap, self.lo, self.hi = wrap, list(point), [p + 1 for p in point]
+
+    def _w(self, v):
+        if v < 0:
+            v += self.wrap
+        if v >= self.wrap:
+            v -= self.wrap
+        return v
+
+    @staticmethod
+    def _within(lo, hi, v):
+        return (lo <= v < hi) if hi >= lo else (v < hi or v >= lo)
+
+    def expandToInclude(self, p):
+        for a in range(3):
+            lo, hi, v = self.lo[a], self.hi[a], p[a]
+            if self._within(lo, hi, v):
+                continue
+            sizeLower = self._w(hi - v - 1) + 1
+            sizeUpper = self._w(v - lo) + 1
+            canLower = self._within(v, hi, lo)
+            canUpper = self._within(lo, v + 1, hi - 1)
+            if canLower and (sizeLower < sizeUpper or not canUpper):
+                self.lo[a] = v
+            else:
+                self.hi[a] = v + 1
+
+    def sizes(self):
+        return [self._w(self.hi[a] - self.lo[a] - 1) + 1 for a in range(3)]
+
+    def wrapCorners(self):
+        self.lo = [self._w(v) for v in self.lo]
+        self.hi = [self._w(v - 1) + 1 for v in self.hi]
+
+    def shift(self, d):
+        self.lo = [self.lo[a] + d[a] for a in range(3)]
+        self.hi = [self.hi[a] + d[a] for a in range(3)]
+        self.wrapCorners()
+
+    def expandSymmetricallyToSize(self, new):
+        old = list(self.lo)
+        if new == self.wrap:
+            self.lo, self.hi = [0, 0, 0], [new] * 3
+            return
+        c = [self._w(self.lo[a] + self._w(self.hi[a] - 1 - self.lo[a]) // 2) for a in range(3)]
+        self.lo = [self._w(c[a] - new // 2) for a in range(3)]
+        up = new // 2 - 1 if new % 2 == 0 else new // 2
+        self.hi = [self._w(c[a] + up) + 1 for a in range(3)]
+        # (the reference compares the y corner against the old *z* corner, window.hpp; kept)
+        for a, ref in ((0, old[0]), (1, old[2]), (2, old[2])):
+            if self.lo[a] > ref:
+                self.lo[a] -= 1
+                self.hi[a] -= 1
+
+    def wrappedOffset(self, a, b):
+        d = b - a
+        if d < -(self.wrap // 2):
+            d += self.wrap
+        if d > self.wrap // 2:
+            d -= self.wrap
+        return d
+
+
+def zoomCorner(grid, zoomfac):
+    """ICGenerator::initZoomGrid (ic.hpp:398-479) without stray particles: the lower-left corner, in cells of `grid`, of
+    the zoom window of grid.size / zoomfac cells that holds the flagged cells."""
+    n = grid.size
+    flags = grid.getFlaggedCells()
+    if len(flags) == 0:
+        raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
+    coords = np.stack(np.unravel_index(flags, (n, n, n)), axis=1)
+    wrap = grid.simEquivalentSize
+    w = _Window(wrap, [int(v) for v in coords[0]])
+    for c in coords:
+        w.expandToInclude([int(v) for v in c])
+    n_user = n // zoomfac
+    n_required = max(w.sizes())
+    if n_required > n_user:
+        raise L.GxError("Zoom particles do not fit in specified sub-box. Decrease zoom, or choose different particles")
+    if n_required < n_user:
+        w.expandSymmetricallyToSize(n_user)
+    lo = [int(round(float(grid.offsetLower[a]) / float(grid.cellSize))) for a in range(3)]
+    w.shift(lo)
+    above = _Window(wrap, lo)
+    above.hi = [lo[a] + n for a in range(3)]
+    above.wrapCorners()
+    move = [0, 0, 0]
+    for a in range(3):
+        if not above._within(above.lo[a], above.hi[a], w.lo[a]):
+            move[a] = w.wrappedOffset(w.lo[a], above.lo[a])
+        if not above._within(above.lo[a], above.hi[a], w.hi[a] - 1):
+            move[a] = w.wrappedOffset(w.hi[a], above.hi[a])
+    w.shift(move)
+    w.shift([-v for v in above.lo])
+    return tuple(w.lo)
+
+
+def initZoomGrid(context, zoomfac, n, corner=None):
+    """initZoomGrid / initZoomGridWithLowLeftCornerAt: appends the zoom level and carries the flags of the level above
+    onto it (the SuperSample + Section view of the parent, grid.hpp:195-228, virtualgrid.hpp:161-166,489-498)."""
+    up = context.grids[-1]
+    if corner is None:
+        corner = zoomCorner(up, zoomfac)
+    if min(corner) < 0:
+        raise L.GxError("The newly initialised zoom level is not fully contained within the previous level")
+    g = context.addZoomLevel(zoomfac, n, corner)
+    ratio = int(round(float(up.cellSize) / float(g.cellSize)))
+    pm = np.zeros(up.size3, dtype=bool)
+    pm[up.getFlaggedCells()] = True
+    pm = pm.reshape((up.size,) * 3)
+    idx = [((np.arange(n) // ratio) + corner[a]) % up.simEquivalentSize for a in range(3)]
+    inside = [i < up.size for i in idx]
+    sub = pm[np.ix_(idx[0] % up.size, idx[1] % up.size, idx[2] % up.size)].copy()
+    sub &= inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :]
+    g.flagCells(np.flatnonzero(sub.reshape(-1)))
+    return g

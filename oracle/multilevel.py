@@ -665,12 +665,17 @@ def orthonormalise(grids, alphas, targets):
 
 
 def apply_linear_modifications(grids, field, alphas, targets):
-    """applyLinearModif (modificationmanager.hpp:199-217) after orthonormalisation."""
+    """applyLinearModif (modificationmanager.hpp:199-217) after orthonormalisation. Returns the modified field and the
+    orthonormalised family as VECTORS: the reference converts each covector in place (alpha_i.convertToVector()), and
+    it is these converted objects that performIterations later receives."""
     alphas, targets = orthonormalise(grids, alphas, targets)
     existing = [inner_product(grids, a, field) for a in alphas]
+    vecs = []
     for a, t, e in zip(alphas, targets, existing):
-        field = add_scaled(field, apply_metric(grids, a, False), t - e)
-    return field, alphas
+        v = apply_metric(grids, a, False)
+        vecs.append(v)
+        field = add_scaled(field, v, t - e)
+    return field, vecs
 
 
 def variance_push(grids, covs, field, scale):
@@ -704,22 +709,35 @@ def variance_value(grids, covs, field, scale):
     return inner_product(grids, variance_push(grids, covs, field, scale), field)
 
 
-def variance_iterations(grids, covs, field, alphas, target, scale, n_steps):
-    """ModificationManager::performIterations (modificationmanager.hpp:249-272); alphas orthonormalised."""
+def variance_iterations(grids, covs, field, alpha_vecs, target, scale, n_steps):
+    """ModificationManager::performIterations (modificationmanager.hpp:249-272). alpha_vecs: the orthonormal family as
+    left by applyLinearModif (vectors); addToOrthonormalFamily (:306-319) projects the pushed covector against them."""
     start = variance_value(grids, covs, field, scale)
-    targets = np.linspace(start, target, n_steps + 1)  # tools::linspace(start, end, n) returns n+1 points
+    if n_steps in (0, 1) or start == target:       # tools::linspace (util_functions.hpp:78-92)
+        targets = [target]
+    else:
+        step = (target - start) / n_steps
+        targets = [start + c * step for c in range(n_steps + 1)]
     for i in range(n_steps):
         cur = variance_value(grids, covs, field, scale)
         pushed = variance_push(grids, covs, field, scale)
         norm = math.sqrt(inner_product(grids, pushed, apply_metric(grids, pushed, False)))
-        for a in alphas:
-            r = inner_product(grids, pushed, apply_metric(grids, a, False))
+        for a in alpha_vecs:
+            r = inner_product(grids, pushed, a)
             pushed = add_scaled(pushed, a, -r)
         nrm = math.sqrt(inner_product(grids, pushed, apply_metric(grids, pushed, False)))
         pushed = [x / nrm for x in pushed]
         mult = 0.5 * (targets[i + 1] - cur) / norm
         field = add_scaled(field, apply_metric(grids, pushed, False), mult)
     return field
+
+
+def apply_variance_modification(grids, covs, field, alpha_vecs, target, scale, init_steps=10, precision=0.001):
+    """applyLinQuadModif for one quadratic modification (modificationmanager.hpp:219-247)."""
+    test = variance_iterations(grids, covs, [f.copy() for f in field], alpha_vecs, target, scale, init_steps)
+    achieved = abs(variance_value(grids, covs, test, scale) - target)
+    n_steps = init_steps * int(math.ceil(math.sqrt(achieved / (target * precision))))
+    return variance_iterations(grids, covs, field, alpha_vecs, target, scale, n_steps if n_steps > init_steps else init_steps)
 
 
 # --------------------------------------------------------------------------------------------------------------

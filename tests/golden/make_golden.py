@@ -8,7 +8,8 @@ tests use the committed copies.
     tipsy / text goldens of test_13, test_05a, test_02k, test_02m
   * test_01a_basic_grid/reference_output (9.4 MB, 64^3 tipsy) -> every 61st particle, as .npz
   * test_19_rounding_errors/reference_grid/grid-0.npy (2 MB float64 64^3) -> [::4, ::4, ::4] subsample
-  * multi-level goldens: test_01c (zoom), test_02c (two linear modifications with a zoom) reference_grid/grid-{0,1}.npy
+  * multi-level goldens: test_01c (zoom), test_02c (two linear modifications with a zoom), test_02i
+    (overdensity + variance modification on two levels) reference_grid/grid-{0,1}.npy
     -> [::4, ::4, ::4] subsamples + the id files that flag the zoom region; test_24 (splicing, 16^3) grid-0.npy whole;
     test_02f / test_02g reference.txt (variance / overdensity values)
 """
@@ -50,6 +51,7 @@ for t, files in {
     "test_02f_onelevelvariance": ("paramfile.txt", "reference.txt"),
     "test_02g_multilevelvariance": ("paramfile.txt", "reference.txt"),
     "test_24_splicing": ("paramfile.txt",),
+    "test_02i_multilevel_algorithm": ("paramfile.txt",),
 }.items():
     for f in files:
         cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
@@ -59,7 +61,7 @@ idx = np.arange(0, d.shape[0], 61)
 np.savez_compressed(f"{HERE}/test_01a_basic_grid/particles_every61.npz", index=idx, particles=d[idx])
 g = np.load(f"{REF}/test_19_rounding_errors/reference_grid/grid-0.npy")
 np.savez_compressed(f"{HERE}/test_19_rounding_errors/grid0_every4.npz", grid=g[::4, ::4, ::4])
-for t in ("test_01c_zoom_grid", "test_02c_two_modifs"):
+for t in ("test_01c_zoom_grid", "test_02c_two_modifs", "test_02i_multilevel_algorithm"):
     gs = {"grid%d" % l: np.load(f"{REF}/{t}/reference_grid/grid-{l}.npy")[::4, ::4, ::4] for l in (0, 1)}
     np.savez_compressed(f"{HERE}/{t}/grids_every4.npz", **gs)
 np.savez_compressed(f"{HERE}/test_24_splicing/grid0.npz", grid0=np.load(f"{REF}/test_24_splicing/reference_grid/grid-0.npy"))

@@ -246,6 +246,32 @@ def test_variance_modification_reaches_target_and_matches_oracle(golden_dir):
     assert abs(v0 / ML.variance_value(og, cdm, of, 20.) - 1) < 1e-9
 
 
+def test_overdensity_and_variance_modification_golden_02i(golden_dir):
+    """The reference's test_02i through the host layer: selection, zoom placement, both modifications, level combination."""
+    from genetic_b200 import zoom as Z
+    cos, dev, ocamb = _camb_pair(golden_dir)
+    ctx = GM.MultiLevelGrid()
+    ctx.addLevel(gb.Grid(64.0, 64))
+    for k, v in dev.items():
+        ctx.setPowerspectrumGenerator(k, v)
+    Z.selectSphere(ctx, (32.5, 32.5, 32.5), 5)
+    Z.initZoomGrid(ctx, 4, 64)
+    Z.selectCube(ctx, (32.5, 32.5, 32.5), 6.0)
+    field = GM.draw(ctx, 8896131)
+    mm = GM.ModificationManager(ctx, cos, field)
+    mm.addModificationToList("overdensity", "relative", 1.0)
+    mm.addModificationToList("variance", "relative", 2.0, filterscale=2.0)
+    mm.applyModifications()
+    field.applyPowerSpectrumFor(GM.ALL)
+    GM.MultiLevelParticleGenerator(field)
+    z = np.load(os.path.join(golden_dir, "test_02i_multilevel_algorithm", "grids_every4.npz"))
+    for l in range(2):
+        d = field.getFieldForLevel(l)
+        d.toReal()
+        ref = z["grid%d" % l]
+        assert np.abs(d.getDataVector()[::4, ::4, ::4] - ref).max() < 1e-6 * ref.std()
+
+
 def test_splice_golden_24_and_oracle(golden_dir):
     cos, dev, ocamb = _camb_pair(golden_dir)
     og = ML.Grid(50.0, 16)

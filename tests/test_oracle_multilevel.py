@@ -99,6 +99,31 @@ def test_variance_and_overdensity_values_golden_02f_02g(golden_dir):
     assert "variance: calculated value = %.6g" % ML.variance_value(grids, covs, f, 10000.) in ref
 
 
+def test_overdensity_and_variance_modification_golden_02i(golden_dir):
+    """test_02i: zoom x4, `modify overdensity relative 1` + `modify variance relative 2` with filtering_scale 2 and the
+    default 10 initial steps / 0.1 % precision; grids after `done`. Pins performIterations, addToOrthonormalFamily and
+    the step-count rule (modificationmanager.hpp:219-281) end to end."""
+    camb = _camb(golden_dir)
+    grids = [ML.Grid(64.0, 64)]
+    ML.select_sphere(grids, (32.5, 32.5, 32.5), 5)
+    ML.add_zoom_level(grids, 4, 64)
+    ML.select_cube(grids, (32.5, 32.5, 32.5), 6.0)
+    f = ML.draw_levels(grids, 8896131, "real")
+    cdm = [camb.covariance(g.size, g.n, "dm") for g in grids]
+    call = [camb.covariance(g.size, g.n, "all") for g in grids]
+    a = ML.overdensity_covector(grids, cdm)
+    v = ML.inner_product(grids, a, f)
+    var0 = ML.variance_value(grids, cdm, f, 2.0)
+    f, vecs = ML.apply_linear_modifications(grids, f, [a], [1.0 * v])
+    f = ML.apply_variance_modification(grids, cdm, f, vecs, 2.0 * var0, 2.0)
+    assert abs(ML.variance_value(grids, cdm, f, 2.0) / (2.0 * var0) - 1) < 1e-3
+    out = ML.combine_levels(grids, [M.apply_transfer(x, c, 0.5) for x, c in zip(f, call)])
+    z = np.load(os.path.join(golden_dir, "test_02i_multilevel_algorithm", "grids_every4.npz"))
+    for l in range(2):
+        ref = z["grid%d" % l]
+        assert np.abs(out[l][0][::4, ::4, ::4] - ref).max() < 1e-6 * ref.std()
+
+
 def test_splice_golden_24(golden_dir):
     """test_24: 16^3, select_sphere 10, splice 8896132 -- spliceOneLevel + conjugateGradient (splice.hpp:38-118,
     cg.hpp:14-58). CG stops at rtol 1e-6, so the grid is pinned to a few 1e-6 sigma."""
