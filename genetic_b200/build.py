@@ -48,8 +48,27 @@ def build(force=False, verbose=False):
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"])
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-lpthread"])
+    build_host(force or bool(jobs))
     return LIB
+
+
+HOST_SRC = os.path.join(os.path.dirname(HERE), "host", "genetic_b200_ic.cpp")
+HOST_BIN = os.path.join(os.path.dirname(HERE), "host", "genetic_b200_ic")
+
+
+def build_host(force=False):
+    """The C++ host layer (include/genetic_b200.hpp) and its paramfile driver: plain g++, linked against the C ABI."""
+    hdr = os.path.join(os.path.dirname(HERE), "include", "genetic_b200.hpp")
+    newest = max(os.path.getmtime(p) for p in (HOST_SRC, hdr, os.path.join(os.path.dirname(HERE), "include", "genetic_b200.h")))
+    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= newest:
+        return HOST_BIN
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(os.path.dirname(HERE), "include"), HOST_SRC,
+           "-L", HERE, "-lgenetic_b200", "-Wl,-rpath,$ORIGIN/../genetic_b200", "-o", HOST_BIN]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed: %s\n%s" % (" ".join(cmd), r.stderr))
+    return HOST_BIN
 
 
 if __name__ == "__main__":

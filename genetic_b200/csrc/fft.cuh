@@ -389,14 +389,17 @@ fft_rows_r2c_kernel(T *data, long nrows, const cplx<T> *__restrict__ twM, const 
   }
 }
 
-// c2r store functors: called with the row index, the complex index k and z = (x[2k], x[2k+1]) unscaled.
+// c2r store functors: `begin(row)` is evaluated once per thread and row (everything that depends on the row only: base
+// pointers, the x / y cell centre), `put(ctx, k, z)` once per complex result z = (x[2k], x[2k+1]), unscaled.
 template <typename T> struct StoreRealScaled {
   T *data;
   T scale;
   int n;
-  __device__ __forceinline__ void operator()(long row, int k, cplx<T> z) const {
-    reinterpret_cast<cplx<T> *>(data + row * (long) (n + 2))[k] = mk<T>(z.x * scale, z.y * scale);
+  struct Ctx { cplx<T> *row; };
+  __device__ __forceinline__ Ctx begin(long row) const {
+    Ctx c; c.row = reinterpret_cast<cplx<T> *>(data + row * (long) (n + 2)); return c;
   }
+  __device__ __forceinline__ void put(const Ctx &c, int k, cplx<T> z) const { c.row[k] = mk<T>(z.x * scale, z.y * scale); }
 };
 
 // Inverse: N/2+1 complex -> N reals (unnormalised c2r; the store functor scales).
@@ -439,7 +442,8 @@ fft_rows_c2r_kernel(const T *data, long row0, long nrows, const cplx<T> *__restr
     v[i] = mk<T>(s.x - wd.y, s.y + wd.x);  // s + i*wd
   }
   __syncthreads();  // everyone has consumed the inputs before the buffer is reused for the stage exchanges
-  B::run(v, t, line, twM, [&](int k, C val) { if (active) store(row, k, val); });
+  const auto ctx = store.begin(active ? row : row0);
+  B::run(v, t, line, twM, [&](int k, C val) { if (active) store.put(ctx, k, val); });
 }
 
 // (Also measured and dropped, profiles/r1s5_bench2048_rows_{single,pipelined}.json: a persistent form of this kernel with

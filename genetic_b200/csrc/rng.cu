@@ -27,6 +27,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 namespace gx {
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
@@ -190,18 +191,18 @@ template <typename T> __device__ __forceinline__ void cursor_advance(const Dest<
   cu.q = c3 ? -cu.ks : cu.q;
 }
 
-// Branch-free on purpose: neighbouring lanes sit at different (face, re/im, sign of kz) phases of the draw loops, so
-// every branch here used to be executed serially for 6+ lane groups (ncu: 9 of 32 threads active on average).
-template <typename T>
-__device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, long long g, double value) {
-  if (d.mode == MODE_LIST) { d.list[g] = value; return; }
+// Where the mode drawn at cursor `cu` is stored (Fourier orders). Branch-free on purpose: neighbouring lanes sit at
+// different (face, re/im, sign of kz) phases of the draw loops, so every branch here used to be executed serially for
+// 6+ lane groups (ncu: 9 of 32 threads active on average).
+struct ModeSlot {
+  size_t slot, slot2;   // complex slot of the kz >= 0 representative; slot of -k on the kz = 0 plane
+  bool write, write2;   // last-writer-wins and slab ownership already applied
+  bool neg;             // the representative is the conjugate (k3 < 0)
+};
+
+template <typename T> __device__ __forceinline__ ModeSlot mode_slot(const Dest<T> &d, const Cursor &cu) {
   const int n = d.n;
-  if (d.mode == MODE_REAL) {
-    const long long r = cu.row - d.row0;
-    if (r >= 0 && r < d.nrows) d.field[r * (n + 2) + cu.z] = (T) value;
-    return;
-  }
-  const int ks = cu.ks, p = cu.p, q = cu.q, face = cu.face, comp = cu.comp;
+  const int ks = cu.ks, p = cu.p, q = cu.q, face = cu.face;
   // drawOneFourierMode is called for (ks,p,q), (p,ks,q), (p,q,ks) in turn
   const int k1 = (face == 0) ? ks : p;
   const int k2 = (face == 0) ? p : ((face == 1) ? ks : q);
@@ -218,25 +219,51 @@ __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, l
   const int c_self = ((p + ks) * twoks + (q + ks)) * 3 + face;      // < 3 * 4096^2: fits an int
   const int c_partner = ((pp + ks) * twoks + (pq + ks)) * 3 + pface;
   const bool write = !(partner_drawn && c_partner > c_self);
-  // value of this component in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2))
-  T v = (T) GX_DMUL(d.sigma, value);
-  // normal order: (a, b) -> (re, im); reverse: (b, a)
-  const int part = d.reverse ? (1 - comp) : comp;
   // setFourierCoefficient(k, val): stored at the kz >= 0 representative, imaginary part negated if conjugated;
   // the explicit second write, setFourierCoefficient(-k, conj(val)), lands on a different slot only when k3 == 0
-  const bool neg = k3 < 0;
-  const int s1 = neg ? -k1 : k1, s2 = neg ? -k2 : k2, s3 = neg ? -k3 : k3;
-  const T vconj = (part == 1) ? -v : v;
+  ModeSlot m;
+  m.neg = k3 < 0;
+  const int s1 = m.neg ? -k1 : k1, s2 = m.neg ? -k2 : k2, s3 = m.neg ? -k3 : k3;
   const int nc = n / 2 + 1;
   const int j2 = (s2 < 0 ? s2 + n : s2) - d.iy0;
-  const size_t slot = (size_t) s3 + (size_t) nc * ((size_t) j2 + (size_t) d.ny * (size_t) (s1 < 0 ? s1 + n : s1));
-  if (write && j2 >= 0 && j2 < d.ny) d.field[2 * slot + part] = neg ? vconj : v;
-  if (write && k3 == 0) {
-    const int t1 = -k1, t2 = -k2;
-    const int u2 = (t2 < 0 ? t2 + n : t2) - d.iy0;
-    const size_t slot2 = (size_t) nc * ((size_t) u2 + (size_t) d.ny * (size_t) (t1 < 0 ? t1 + n : t1));
-    if (u2 >= 0 && u2 < d.ny) d.field[2 * slot2 + part] = vconj;
+  m.slot = (size_t) s3 + (size_t) nc * ((size_t) j2 + (size_t) d.ny * (size_t) (s1 < 0 ? s1 + n : s1));
+  m.write = write && j2 >= 0 && j2 < d.ny;
+  const int t1 = -k1, t2 = -k2;
+  const int u2 = (t2 < 0 ? t2 + n : t2) - d.iy0;
+  m.slot2 = (size_t) nc * ((size_t) u2 + (size_t) d.ny * (size_t) (t1 < 0 ? t1 + n : t1));
+  m.write2 = write && k3 == 0 && u2 >= 0 && u2 < d.ny;
+  return m;
+}
+
+template <typename T>
+__device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, long long g, double value) {
+  if (d.mode == MODE_LIST) { d.list[g] = value; return; }
+  const int n = d.n;
+  if (d.mode == MODE_REAL) {
+    const long long r = cu.row - d.row0;
+    if (r >= 0 && r < d.nrows) d.field[r * (n + 2) + cu.z] = (T) value;
+    return;
   }
+  const ModeSlot m = mode_slot<T>(d, cu);
+  // value of this component in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2))
+  const T v = (T) GX_DMUL(d.sigma, value);
+  // normal order: (a, b) -> (re, im); reverse: (b, a)
+  const int part = d.reverse ? (1 - cu.comp) : cu.comp;
+  const T vconj = (part == 1) ? -v : v;
+  if (m.write) d.field[2 * m.slot + part] = m.neg ? vconj : v;
+  if (m.write2) d.field[2 * m.slot2 + part] = vconj;
+}
+
+// Both draws of one drawOneFourierMode call at once (the cursor is the same for the two): one 2-component store per
+// slot instead of two scattered scalar ones, and the index arithmetic once per mode.
+template <typename T>
+__device__ __forceinline__ void deliver_pair(const Dest<T> &d, const Cursor &cu, double first, double second) {
+  const ModeSlot m = mode_slot<T>(d, cu);
+  const T a = (T) GX_DMUL(d.sigma, first), b = (T) GX_DMUL(d.sigma, second);
+  const T re = d.reverse ? b : a, im = d.reverse ? a : b;
+  cplx<T> *f = reinterpret_cast<cplx<T> *>(d.field);
+  if (m.write) f[m.slot] = mk<T>(re, m.neg ? -im : im);
+  if (m.write2) f[m.slot2] = mk<T>(re, -im);
 }
 
 template <typename T>
@@ -316,6 +343,9 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
 
   Cursor cu;
   if (PASS == 1) cursor_init<T>(dest, sd, g, cu);
+  const bool pairs = (PASS == 1) && (dest.mode == MODE_FOURIER_SERIAL || dest.mode == MODE_FOURIER_PARALLEL);
+  bool have_held = false;  // the first draw of a mode waits for the second (same thread unless the chunk ends in between)
+  double held = 0.0;
 
   State st = chunk_start_state(sd, q, P.jump);
 
@@ -338,7 +368,10 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
           if (PASS == 0) cnt[e]++;
           else {
             if (g < sd.n_gauss) {
-              deliver_at<T>(dest, cu, g, a.value);
+              if (!pairs) deliver_at<T>(dest, cu, g, a.value);
+              else if (cu.comp == 0) { held = a.value; have_held = true; }
+              else if (have_held) { deliver_pair<T>(dest, cu, held, a.value); have_held = false; }
+              else deliver_at<T>(dest, cu, g, a.value);  // its partner was the last draw of the previous chunk
               if (a.tail) {
                 const unsigned int slot = atomicAdd(P.tail_count, 1u);
                 if (slot < P.tail_capacity) {
@@ -366,6 +399,12 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
       }
     }
     if (PASS == 1 && g >= sd.n_gauss) live = false;
+  }
+
+  if (PASS == 1 && have_held) {  // the chunk ended between the two draws of a mode: the cursor already points at comp 1
+    Cursor c0 = cu;
+    c0.comp = 0;
+    deliver_at<T>(dest, c0, g - 1, held);
   }
 
   if (PASS == 0 && in_range) {
@@ -618,11 +657,28 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     double *val = (double *) pin_val;
     GX_CUDA_CHECK(cudaMemcpyAsync(ev, d_tails, sizeof(TailEvent) * ntail, cudaMemcpyDeviceToHost, cs));
     GX_CUDA_CHECK(cudaStreamSynchronize(cs));
-    const double R = GX_ZIG_R;
-    for (unsigned int i = 0; i < ntail; ++i) {
-      const double U1 = 1.0 - (double) ev[i].u1 / 16777216.0;
-      const double x = R - std::log(U1) / R;
-      val[i] = ev[i].positive ? x : -x;
+    // ~6e-4 of all draws: 5 million log() calls at 2048^3 -- on one core that was ~60 ms of idle GPU per draw
+    {
+      const double R = GX_ZIG_R;
+      auto work = [&](unsigned int i0, unsigned int i1) {
+        for (unsigned int i = i0; i < i1; ++i) {
+          const double U1 = 1.0 - (double) ev[i].u1 / 16777216.0;
+          const double x = R - std::log(U1) / R;
+          val[i] = ev[i].positive ? x : -x;
+        }
+      };
+      unsigned int nt = std::thread::hardware_concurrency();
+      if (nt > 32) nt = 32;
+      if (nt < 2 || ntail < 65536) work(0, ntail);
+      else {
+        std::vector<std::thread> pool;
+        const unsigned int per = (ntail + nt - 1) / nt;
+        for (unsigned int t = 0; t < nt; ++t) {
+          const unsigned int i0 = t * per, i1 = std::min(ntail, i0 + per);
+          if (i0 < i1) pool.emplace_back(work, i0, i1);
+        }
+        for (auto &th : pool) th.join();
+      }
     }
     GX_CUDA_CHECK(cudaMemcpyAsync(p_val, val, sizeof(double) * ntail, cudaMemcpyHostToDevice, cs));
     GX_TIMED("rng_tail_patch", cs);

@@ -29,10 +29,10 @@ __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 // Grid::wrapIndividualCoordinate (grid.hpp:527-531): x = fmod(x, L); if (x < 0) x += L.  fmod is exact, and for
 // L <= x < 2L it equals x - L, which is itself exact (Sterbenz), so the common cases never enter the slow routine.
 template <typename T> __device__ __forceinline__ T wrap_coordinate(T x, T L) {
-  if (x >= L) x = (x < L + L) ? x - L : fmod(x, L);
-  else if (x <= -L) x = fmod(x, L);
-  if (x < 0) x = add_rn(x, L);
-  return x;
+  // -L < x < 2L (every particle: |psi| << L): selects only, no divergent branches; anything else takes the library fmod
+  T y = (x >= L) ? x - L : x;
+  if (!(x > -L && x < L + L)) y = fmod(x, L);
+  return (y < 0) ? add_rn(y, L) : y;
 }
 
 // k^2 and |k| of a storage slot exactly as the reference forms them:

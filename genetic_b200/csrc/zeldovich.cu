@@ -58,28 +58,31 @@ template <typename T, typename O> struct StoreEmit {
   long long id0;
   int n, axis;
   T scale, dx, lower, half_dx, domain, ratio;
-  __device__ __forceinline__ T wrap(T psi, int c) const {
-    // getCentroidFromCoordinate: coord*cellSize; += offsetLower; += cellSize/2 (three separately rounded operations)
-    T cen = add_rn(add_rn(mul_rn((T) c, dx), lower), half_dx);
-    return wrap_coordinate<T>(add_rn(psi, cen), domain);
+  using P2 = typename Pair<O>::type;
+  struct Ctx { P2 *pos, *vel; T cen; };
+  // getCentroidFromCoordinate: coord*cellSize; += offsetLower; += cellSize/2 (three separately rounded operations)
+  __device__ __forceinline__ T centre(int c) const { return add_rn(add_rn(mul_rn((T) c, dx), lower), half_dx); }
+  __device__ __forceinline__ Ctx begin(long row) const {
+    Ctx c;
+    const long long first = (long long) row * n - id0;  // index of particle (row, z = 0) in the output arrays (even)
+    c.pos = pos ? reinterpret_cast<P2 *>(pos + first) : nullptr;
+    c.vel = vel ? reinterpret_cast<P2 *>(vel + first) : nullptr;
+    const int x = (int) (row / n);
+    c.cen = centre(axis == 0 ? x : (int) (row - (long) x * n));  // unused for axis 2
+    return c;
   }
-  __device__ __forceinline__ void operator()(long row, int k, cplx<T> z) const {
+  __device__ __forceinline__ void put(const Ctx &c, int k, cplx<T> z) const {
     const T p0 = z.x * scale, p1 = z.y * scale;
-    const long long i = (long long) row * n + 2 * k - id0;
-    using P2 = typename Pair<O>::type;
-    if (pos) {
-      int c0, c1;
-      if (axis == 2) { c0 = 2 * k; c1 = 2 * k + 1; }
-      else {
-        const int x = (int) (row / n);
-        c0 = c1 = (axis == 0) ? x : (int) (row - (long) x * n);
-      }
-      P2 o; o.x = (O) wrap(p0, c0); o.y = (O) wrap(p1, c1);
-      *reinterpret_cast<P2 *>(pos + i) = o;
+    if (c.pos) {
+      const T c0 = axis == 2 ? centre(2 * k) : c.cen, c1 = axis == 2 ? centre(2 * k + 1) : c.cen;
+      P2 o;
+      o.x = (O) wrap_coordinate<T>(add_rn(p0, c0), domain);
+      o.y = (O) wrap_coordinate<T>(add_rn(p1, c1), domain);
+      c.pos[k] = o;
     }
-    if (vel) {
+    if (c.vel) {
       P2 o; o.x = (O) mul_rn(p0, ratio); o.y = (O) mul_rn(p1, ratio);
-      *reinterpret_cast<P2 *>(vel + i) = o;
+      c.vel[k] = o;
     }
   }
 };
