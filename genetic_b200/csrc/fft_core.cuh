@@ -185,6 +185,32 @@ template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT 
     return k;
   }
 
+  // Twiddles of one butterfly are the powers w, w^2, .., w^(R-1) of one table entry. In double precision they are
+  // formed by multiplication (w^(h+l) = w^h * w^l with h in {4, 8, 12}, l in {1, 2, 3}: depth <= 5, error a few 1e-16)
+  // instead of R-1 table loads at stride q: those loads hit L1 but each touches up to 32 distinct 128-byte lines per warp,
+  // and the L1 data pipe, not the FP64 pipe, is what the passes run out of (ncu: L1 data pipe 83 %, FP64 26 % in the z-pass).
+  // (Row passes only, LS == 0: the column passes read their twiddles from a private shared-memory copy, their L1 data pipe
+  // is at ~50 %, and the extra live values made them spill under the 96-register cap.)
+  static constexpr bool kPowersByMultiplication = (sizeof(T) == 8) && (LS == 0);
+  // a[q] *= w1^q for q = 1..R-1 with few values live (w1..w3 and w4, w8, w12): w^(h+l) = w^h * w^l
+  template <int R> GX_HD static void apply_twiddle_powers(C w1, C *a) {
+    a[1] = cmul(a[1], w1);
+    if (R == 2) return;
+    const C w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], w3);
+    if (R == 4) return;
+    C wh = cmul(w2, w2);  // w^4
+#pragma unroll
+    for (int h = 4; h < R; h += 4) {
+      a[h] = cmul(a[h], wh);
+      a[h + 1] = cmul(a[h + 1], cmul(wh, w1));
+      a[h + 2] = cmul(a[h + 2], cmul(wh, w2));
+      a[h + 3] = cmul(a[h + 3], cmul(wh, w3));
+      if (h + 4 < R) wh = (h == 4) ? cmul(wh, wh) : cmul(wh, cmul(w2, w2));  // w^8 = (w^4)^2, w^12 = w^8 * w^4
+    }
+  }
+
   GX_HD static C twiddle(const C *__restrict__ tw, int j) {
     // tw[j] = exp(-2 pi i j / NC); the table may live in global memory (const __restrict__ -> LDG.CONSTANT) or in
     // shared memory (column passes: the cluster barrier's acquire invalidates L1, so they keep a private copy)
@@ -201,8 +227,12 @@ template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT 
       for (int q = 0; q < E; ++q) emit(q, v[q]);  // NC == E, P == 1, t == 0
       return;
     }
+    if (kPowersByMultiplication) {
+      apply_twiddle_powers<E>(twiddle(tw, t), v);
+    } else {
 #pragma unroll
-    for (int q = 1; q < E; ++q) v[q] = cmul(v[q], twiddle(tw, t * q));
+      for (int q = 1; q < E; ++q) v[q] = cmul(v[q], twiddle(tw, t * q));
+    }
 #pragma unroll
     for (int q = 0; q < E; ++q) line[lidx(t + q * P)] = v[q];
   }
@@ -224,8 +254,12 @@ template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT 
 #pragma unroll
         for (int q = 0; q < R; ++q) emit(freq_of_pos(base + q * Ds), a[q]);
       } else {
+        if (kPowersByMultiplication) {
+          apply_twiddle_powers<R>(twiddle(tw, m * (NC / Ls)), a);
+        } else {
 #pragma unroll
-        for (int q = 1; q < R; ++q) a[q] = cmul(a[q], twiddle(tw, m * q * (NC / Ls)));
+          for (int q = 1; q < R; ++q) a[q] = cmul(a[q], twiddle(tw, m * q * (NC / Ls)));
+        }
 #pragma unroll
         for (int q = 0; q < R; ++q) line[lidx(base + q * Ds)] = a[q];
       }

@@ -299,7 +299,7 @@ template <int PASS, typename T>
 __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest<T> dest) {
   __shared__ unsigned int s_k[128];
   __shared__ double s_w[128], s_y[128];
-  __shared__ uint32_t ring[48][kThreads];
+  __shared__ uint32_t ring[64][kThreads];  // raw output p of the chunk lives in slot p & 63 (the parse looks back < 28 outputs)
   for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_k[i] = d_zig_ktab[i]; s_w[i] = d_zig_wtab[i]; s_y[i] = d_zig_ytab[i]; }
   __syncthreads();
   // No lane leaves before the end: every increment starts with a __syncwarp so that the 397-step generator advance
@@ -352,17 +352,17 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
   for (int bi = 0; bi <= kBc; ++bi) {
     __syncwarp();
     advance_block(st);
-    const int half = (bi & 1) * 24;
+    const int rbase = 24 * bi;
 #pragma unroll
-    for (int j = 0; j < 24; ++j) ring[half + j][tx] = block_output(st, j);
+    for (int j = 0; j < 24; ++j) ring[(rbase + j) & 63][tx] = block_output(st, j);
     const int avail = 24 * (bi + 1);
     const int limit = min(avail - 3, kChunkLen);
     for (int e = 0; e < ncur; ++e) {
       if (PASS == 0 && rep[e] >= 0) continue;
       int p = pos[e];
       while (live && p < limit) {
-        const Attempt a = zig_attempt(ring[p % 48][tx], ring[(p + 1) % 48][tx], ring[(p + 2) % 48][tx],
-                                      ring[(p + 3) % 48][tx], s_k, s_w, s_y);
+        const Attempt a = zig_attempt(ring[p & 63][tx], ring[(p + 1) & 63][tx], ring[(p + 2) & 63][tx],
+                                      ring[(p + 3) & 63][tx], s_k, s_w, s_y);
         p += a.consumed;
         if (a.accepted) {
           if (PASS == 0) cnt[e]++;

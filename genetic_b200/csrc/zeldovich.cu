@@ -33,14 +33,20 @@ template <typename T, bool PREDIV> struct OpZeldovichMirror {
       d = delta[((size_t) ix * n + iy) * nc + iz];
       conj = true;
     }
-    T kx, ky, kz, k2;
-    slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
     const int ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-    const T ka = axis == 0 ? kx : (axis == 1 ? ky : kz);
     cplx<T> r = mk<T>(0, 0);
-    if (ia != h && k2 != (T) 0) {
-      if (PREDIV) { r.x = mul_rn(-d.y, ka); r.y = mul_rn(d.x, ka); }
-      else { r.x = mul_rn(div_rn(-d.y, k2), ka); r.y = mul_rn(div_rn(d.x, k2), ka); }
+    if (PREDIV) {
+      // delta_k / k^2 was formed by the transfer sweep: only k_axis is needed here, and k^2 != 0 is an integer test
+      // (k = integer * kMin), so the three products and two sums of slot_k drop out of every element of the pass
+      if (ia != h && (ix | iy | iz) != 0) {
+        const T ka = mul_rn((T) (axis == 2 ? iz : signed_mode(ia, n)), kmin);
+        r.x = mul_rn(-d.y, ka); r.y = mul_rn(d.x, ka);
+      }
+    } else {
+      T kx, ky, kz, k2;
+      slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+      const T ka = axis == 0 ? kx : (axis == 1 ? ky : kz);
+      if (ia != h && k2 != (T) 0) { r.x = mul_rn(div_rn(-d.y, k2), ka); r.y = mul_rn(div_rn(d.x, k2), ka); }
     }
     // the mirror leaves conj(value) in dependent slots and a negated imaginary part in self-conjugate ones
     const bool self = (iz == 0 || iz == h) && (ix == 0 || ix == h) && (iy == 0 || iy == h);

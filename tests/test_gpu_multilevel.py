@@ -272,6 +272,38 @@ def test_overdensity_and_variance_modification_golden_02i(golden_dir):
         assert np.abs(d.getDataVector()[::4, ::4, ::4] - ref).max() < 1e-6 * ref.std()
 
 
+def test_example_paramfile_fields_vs_oracle(golden_dir):
+    """BASELINE.json config 1 (example/paramfile.txt as shipped): Planck-2018 transfer, base 128^3 over 50 Mpc/h, zoom x3
+    128^3 around (32.5, 32.5, 32.5), random_seed 8896131 (parallel Fourier). Overdensity and displacement fields of both
+    levels after the level combination against the CPU oracle (the particle mapper and the gadget writer are the
+    `next` rows of SURVEY 8f)."""
+    from genetic_b200 import zoom as Z
+    fn = os.path.join(golden_dir, "planck_2018_transfer_out.dat")
+    kw = dict(ns=0.9660, hubble=0.6732)
+    cos = gb.CosmologicalParameters(0.3158, 0.6842, 0.8117, 200, **kw)
+    ocamb = M.CAMB(fn, M.Cosmology(0.3158, 0.6842, 0.8117, 200, **kw))
+    ctx = GM.MultiLevelGrid()
+    ctx.addLevel(gb.Grid(50.0, 128))
+    ctx.setPowerspectrumGenerator("all", gb.CAMB(cos, fn, "all"))
+    Z.selectSphere(ctx, (32.5, 32.5, 32.5), 6)
+    Z.initZoomGrid(ctx, 3, 128)
+    og = [ML.Grid(50.0, 128)]
+    ML.select_sphere(og, (32.5, 32.5, 32.5), 6)
+    ML.add_zoom_level(og, 3, 128)
+    assert tuple(float(v) for v in ctx.grids[1].offsetLower) == og[1].offset
+    field = GM.draw(ctx, 8896131, drawInFourierSpace=True, parallel=True)
+    field.applyPowerSpectrumFor(GM.ALL)
+    gen = GM.MultiLevelParticleGenerator(field)
+    ofields = ML.draw_levels(og, 8896131, "fourier_parallel")
+    ref = ML.combine_levels(og, [M.apply_transfer(f, ocamb.covariance(g.size, g.n, "all"), 0.5) for f, g in zip(ofields, og)])
+    for l in range(2):
+        d = field.getFieldForLevel(l)
+        d.toReal()
+        assert _rel(d.getDataVector(), ref[l][0]) < TOL
+        for a in range(3):
+            assert _rel(gen.getGeneratorForLevel(l).getGeneratedFields()[a].getDataVector(), ref[l][1][a]) < TOL
+
+
 def test_splice_golden_24_and_oracle(golden_dir):
     cos, dev, ocamb = _camb_pair(golden_dir)
     og = ML.Grid(50.0, 16)
