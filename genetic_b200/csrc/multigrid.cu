@@ -408,20 +408,27 @@ static int masked_shift_scale_t(void *f, const unsigned char *mask, int n, doubl
 // ---- F <- scale * F / k^2 on the independent slots, 0 at k = 0 (VelocityModification::computeVelocity real-space-derivative
 // branch, linearmodification.hpp:242-262; cosmology::densityToPotential) -------------------------------------------------
 template <typename T> struct ScaleInvK2F {
-  cplx<T> *f; int n; T kmin, scale;
+  cplx<T> *f; int n; T kmin, scale; int potential_form;
   __device__ __forceinline__ void init() const {}
   __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
     if (!slot_is_independent(n, ix, iy, iz)) return;
     T kx, ky, kz, k2;
     slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
     cplx<T> v = f[s];
-    f[s] = (k2 == (T) 0) ? mk<T>(0, 0) : mk<T>(div_rn(mul_rn(scale, v.x), k2), div_rn(mul_rn(scale, v.y), k2));
+    if (potential_form) {
+      // densityToPotential (parameters.hpp:208-225): ksq_inv = 1/ksq, set to 0 where the SECOND wavenumber component is
+      // zero (the reference tests its lambda argument `k2`, i.e. ky, not ksq), result = scale * val * ksq_inv
+      const T inv = (ky == (T) 0) ? (T) 0 : div_rn((T) 1, k2);
+      f[s] = mk<T>(mul_rn(mul_rn(scale, v.x), inv), mul_rn(mul_rn(scale, v.y), inv));
+    } else {
+      f[s] = (k2 == (T) 0) ? mk<T>(0, 0) : mk<T>(div_rn(mul_rn(scale, v.x), k2), div_rn(mul_rn(scale, v.y), k2));
+    }
   }
 };
 
-template <typename T> static int scale_inv_k2_t(void *field, int n, double L, double scale, cudaStream_t st) {
+template <typename T> static int scale_inv_k2_t(void *field, int n, double L, double scale, int potential_form, cudaStream_t st) {
   ScaleInvK2F<T> f;
-  f.f = (cplx<T> *) field; f.n = n; f.kmin = (T) (2. * M_PI / (double) (T) L); f.scale = (T) scale;
+  f.f = (cplx<T> *) field; f.n = n; f.kmin = (T) (2. * M_PI / (double) (T) L); f.scale = (T) scale; f.potential_form = potential_form;
   return launch_slot_sweep(n, f, st, 0, "scale_inv_k2");
 }
 
@@ -467,9 +474,9 @@ int gx_masked_shift_scale(void *field, const unsigned char *mask_n3, int n, int 
   GX_DISPATCH(dtype, masked_shift_scale_t<T>(field, mask_n3, n, shift, scale, (cudaStream_t) stream));
 }
 
-int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, void *stream) {
+int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, int potential_form, void *stream) {
   if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
-  GX_DISPATCH(dtype, scale_inv_k2_t<T>(field, n, grid_length, scale, (cudaStream_t) stream));
+  GX_DISPATCH(dtype, scale_inv_k2_t<T>(field, n, grid_length, scale, potential_form, (cudaStream_t) stream));
 }
 
 }  // extern "C"

@@ -285,6 +285,8 @@ struct ChunkParams {
   TailEvent *tails;
   unsigned int *tail_count;
   unsigned int tail_capacity;
+  const int *list;            // pass B on a slab: the chunks that can touch this rank's slots (nullptr: all chunks)
+  int n_list;
 };
 
 __device__ __forceinline__ State chunk_start_state(const StreamDesc &sd, int q, const Big *jump) {
@@ -305,9 +307,9 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
   // No lane leaves before the end: every increment starts with a __syncwarp so that the 397-step generator advance
   // runs with the whole warp converged (lanes that had left early or sat in different parse branches used to run it
   // in 5-lane groups -- 70% of all issued instructions of pass B, ncu r1p).
-  const int chunk_raw = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = chunk_raw < P.n_chunks;
-  const int chunk = in_range ? chunk_raw : P.n_chunks - 1;
+  const int slot_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = slot_raw < (P.list ? P.n_list : P.n_chunks);
+  const int chunk = in_range ? (P.list ? P.list[slot_raw] : slot_raw) : P.n_chunks - 1;
   bool live = in_range;
   int sid = 0;
   {  // the stream this chunk belongs to: last stream with first_chunk <= chunk
@@ -419,6 +421,39 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
     }
     P.fn[chunk] = f;
   }
+}
+
+// ---- slab ownership: which chunks of the per-shell streams can write into ky storage rows [iy0, iy0 + ny) ---------------
+// A draw of shell ks is stored at ky = +-k2 with k2 = p (mode (ks,p,q)), ks (mode (p,ks,q)) or q (mode (p,q,ks)); a chunk
+// holds at most kChunkLen / 2 gaussians, i.e. a short run of the (p, q) loop. The test is conservative (intervals, both
+// signs); chunks it rejects are not generated at all in pass B. The appended order is irrelevant: every chunk is
+// delivered independently and overwrites are resolved analytically (last writer wins by call index).
+__global__ void need_kernel(const StreamDesc *streams, int n_streams, int n_chunks, const ScanState *scan, int n, int iy0,
+                            int ny, int *list, unsigned int *count) {
+  const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= n_chunks) return;
+  int lo = 0, hi = n_streams - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (streams[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+  }
+  const StreamDesc &sd = streams[lo];
+  const long long g0 = (chunk == sd.first_chunk) ? 0 : scan[chunk].base;
+  if (g0 >= sd.n_gauss) return;
+  long long g1 = g0 + kChunkLen / 2 + 3;   // past the last gaussian the chunk can hold (>= 2 outputs each, entry offset <= 3)
+  bool need = false;
+  if (g1 >= sd.n_gauss) { g1 = sd.n_gauss; need = true; }  // the chunk that records the end of the stream always runs
+  // signed ky values of the slab: storage index j <= n/2 is ky = j, above it ky = j - n (ky = n/2 is never drawn)
+  const int s0 = (iy0 + ny <= n / 2) ? iy0 : iy0 - n, s1 = s0 + ny - 1;
+  auto owned = [&](int a, int b) {  // does [a, b] meet [s0, s1] or [-s1, -s0]?
+    return (a <= s1 && b >= s0) || (a <= -s0 && b >= -s1);
+  };
+  const int ks = sd.shell, two = 2 * ks;
+  const long long t0 = (g0 / 2) / 3, t1 = ((g1 - 1) / 2) / 3;
+  const int pa = (int) (t0 / two) - ks, pb = (int) (t1 / two) - ks;
+  const int qa = (int) (t0 % two) - ks, qb = (int) (t1 % two) - ks;
+  need = need || owned(ks, ks) || owned(pa, pb) || (pa == pb ? owned(qa, qb) : owned(-ks, ks - 1));
+  if (need) list[atomicAdd(count, 1u)] = chunk;
 }
 
 // ---- scan over chunk functions -----------------------------------------------------------------------------------
@@ -611,6 +646,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   ChunkParams P;
   P.streams = d_streams; P.n_streams = ns; P.n_chunks = n0; P.jump = g_jump; P.fn = d_fn[0];
   P.scan = d_st[0]; P.stream_end = d_end; P.tails = d_tails; P.tail_count = d_tail_count; P.tail_capacity = tail_cap;
+  P.list = nullptr; P.n_list = 0;
   const int grid = (n0 + kThreads - 1) / kThreads;
   {
     GX_TIMED("rng_pass_a", cs);
@@ -632,9 +668,26 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     }
   }
   GX_LAUNCH_CHECK();
-  {
+  int grid_b = grid;
+  P.list = nullptr; P.n_list = 0;
+  if (dest.mode == MODE_FOURIER_PARALLEL && dest.ny < dest.n) {
+    // this rank's slab: pass B only over the chunks that can reach it
+    void *p_list = nullptr;
+    if (ws_dev(6, sizeof(int) * (size_t) n0 + 64, &p_list)) return 1;
+    int *d_list = (int *) p_list;
+    unsigned int *d_count = (unsigned int *) (d_list + n0);
+    GX_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), cs));
+    need_kernel<<<grid, kThreads, 0, cs>>>(d_streams, ns, n0, d_st[0], dest.n, dest.iy0, dest.ny, d_list, d_count);
+    count_launch();
+    GX_LAUNCH_CHECK();
+    GX_CUDA_CHECK(cudaMemcpyAsync(h_ntail, d_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
+    GX_CUDA_CHECK(cudaStreamSynchronize(cs));
+    P.list = d_list; P.n_list = (int) *h_ntail;
+    grid_b = (P.n_list + kThreads - 1) / kThreads;
+  }
+  if (grid_b > 0) {
     GX_TIMED("rng_pass_b", cs);
-    rng_chunk_kernel<1, T><<<grid, kThreads, 0, cs>>>(P, dest);
+    rng_chunk_kernel<1, T><<<grid_b, kThreads, 0, cs>>>(P, dest);
   }
   count_launch();
   GX_LAUNCH_CHECK();

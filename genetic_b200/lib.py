@@ -82,7 +82,7 @@ PROTOTYPES = {
     "gx_zero_window": (ci, [vp, P(GridDesc), ci, P(GridDesc), ci, vp]),
     "gx_masked_sum": (ci, [vp, vp, ci, ci, P(cd), vp]),
     "gx_masked_shift_scale": (ci, [vp, vp, ci, ci, cd, cd, vp]),
-    "gx_scale_inv_k2": (ci, [vp, ci, ci, cd, cd, vp]),
+    "gx_scale_inv_k2": (ci, [vp, ci, ci, cd, cd, ci, vp]),
     "gx_zeldovich_fourier": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_zeldovich_offset": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_emit_component": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, vp, ci, cl, cll, cll, vp]),

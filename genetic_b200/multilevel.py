@@ -418,7 +418,71 @@ class VelocityModification(OverdensityModification):
         scale = self.cosmology.zeldovichVelocityToOffsetRatio(field.getFieldForLevel(0).dtype)
         for f in field.fieldsOnLevels:
             f.toFourier()
-            f.lib.gx_scale_inv_k2(f.ptr, f.n, f.dt, float(f.grid.thisGridSize), -scale, f.stream)
+            f.lib.gx_scale_inv_k2(f.ptr, f.n, f.dt, float(f.grid.thisGridSize), -scale, 0, f.stream)
+
+
+class PotentialModification(OverdensityModification):
+    """linearmodification.hpp:128-146 with cosmology::densityToPotential (parameters.hpp:208-225)."""
+
+    def turnLocalisationCovectorIntoModificationCovector(self, field):
+        super().turnLocalisationCovectorIntoModificationCovector(field)
+        c = self.cosmology
+        prefac = 3. / 2. * c.OmegaM0 / c.scalefactor * 100. * 100. / 299792. / 299792.
+        for f in field.fieldsOnLevels:
+            f.toFourier()
+            f.lib.gx_scale_inv_k2(f.ptr, f.n, f.dt, float(f.grid.thisGridSize), -prefac, 1, f.stream)
+
+
+class AngMomentumModification(OverdensityModification):
+    """linearmodification.hpp:288-411: specific angular momentum of the flagged Lagrangian patch about its centre,
+    -(q - q_c) x grad(Phi) with the 4th-order real-space stencil."""
+
+    def __init__(self, context, cosmology, direction):
+        super().__init__(context, cosmology)
+        if direction not in (0, 1, 2):
+            raise L.GxError("Angular momentum direction must be 0 (x), 1 (y) or 2 (z)")
+        self.direction = direction
+
+    def calculateLocalisationCovector(self, grid):
+        from . import zoom as Z
+        n, S = grid.size, grid.simEquivalentSize
+        flags = self.flaggedCellsFinestGrid
+        qc = Z.getCentreWrapped(grid, flags)
+        norm = len(flags) * float(grid.cellSize)
+        a, b = 1. / 12. / norm, -2. / 3. / norm
+        d, d1, d2 = self.direction, (self.direction + 1) % 3, (self.direction + 2) % 3
+        c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0)
+        q = [(c[ax].astype(np.float64) * float(grid.cellSize) + float(grid.offsetLower[ax])) + float(grid.cellSize) / 2
+             for ax in range(3)]
+        dq = [Z.getWrappedOffset(grid, qc[ax], q[ax]) for ax in range(3)]
+        coeff = {d: np.zeros(len(flags)), d2: dq[d1], d1: -dq[d2]}
+        data = np.zeros((n, n, n), dtype=grid.dtype)
+
+        def step(cc, ax, s):
+            cc = cc.copy()
+            v = cc[ax] + s
+            v = np.where(v > S - 1, v - S, v)
+            cc[ax] = np.where(v < 0, v + S, v)
+            return cc
+        for ax in range(3):
+            if ax == d:
+                continue
+            m1, p1 = step(c, ax, -1), step(c, ax, 1)
+            m2, p2 = step(m1, ax, -1), step(p1, ax, 1)
+            np.add.at(data, tuple(m2), coeff[ax] * a)
+            np.add.at(data, tuple(m1), coeff[ax] * b)
+            np.add.at(data, tuple(p1), -coeff[ax] * b)
+            np.add.at(data, tuple(p2), -coeff[ax] * a)
+        f = Field(grid, data, fourier=False)
+        f.toFourier()
+        return f
+
+    def turnLocalisationCovectorIntoModificationCovector(self, field):
+        super().turnLocalisationCovectorIntoModificationCovector(field)
+        scale = self.cosmology.zeldovichVelocityToOffsetRatio(field.getFieldForLevel(0).dtype)
+        for f in field.fieldsOnLevels:
+            f.toFourier()
+            f.lib.gx_scale_inv_k2(f.ptr, f.n, f.dt, float(f.grid.thisGridSize), -scale, 0, f.stream)
 
 
 class FilteredVarianceModification:
@@ -490,8 +554,12 @@ class ModificationManager:
         nm = name.lower()
         if nm == "overdensity":
             return OverdensityModification(self.context, self.cosmology)
+        if nm == "potential":
+            return PotentialModification(self.context, self.cosmology)
         if nm in ("vx", "vy", "vz"):
             return VelocityModification(self.context, self.cosmology, "xyz".index(nm[1]))
+        if nm in ("lx", "ly", "lz"):
+            return AngMomentumModification(self.context, self.cosmology, "xyz".index(nm[1]))
         if nm == "variance":
             return FilteredVarianceModification(self.context, self.cosmology, kw.get("filterscale", -1.0),
                                                 kw.get("initNumberSteps", 10), kw.get("precision", 0.001))

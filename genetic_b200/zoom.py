@@ -48,6 +48,37 @@ def selectCube(context, centre, side):
     select(context, centre, lambda x, y, z: (np.abs(x) < h) & (np.abs(y) < h) & (np.abs(z) < h))
 
 
+def selectEllipse(context, centre, a, b, c):
+    a2, b2, c2 = (float(np.float32(v) * np.float32(v)) for v in (a, b, c))   # selectEllipse(float a, b, c), ic.hpp:1503-1513
+    select(context, centre, lambda x, y, z: x * x / a2 + y * y / b2 + z * z / c2 < 1.)
+
+
+def getWrappedOffset(grid, x0, x1):
+    """Grid::getWrappedOffset(x0, x1) = x0 - x1 wrapped into [-L/2, L/2] (grid.hpp:445-454)."""
+    d = np.asarray(x0, dtype=np.float64) - np.asarray(x1, dtype=np.float64)
+    Lbox = float(grid.periodicDomainSize)
+    d = np.where(d > Lbox / 2, d - Lbox, d)
+    return np.where(d < -Lbox / 2, d + Lbox, d)
+
+
+def getCentreWrapped(grid, flags):
+    """Grid::getCentreWrapped (grid.hpp:466-494): the mean of the flagged cells' wrapped offsets from the first one."""
+    if len(flags) == 0:
+        raise L.GxError("Cannot calculate the center of an empty region")
+    n = grid.size
+    c = np.stack(np.unravel_index(np.asarray(flags), (n, n, n)), axis=0)
+    out = []
+    for a in range(3):
+        pos = (c[a].astype(np.float64) * float(grid.cellSize) + float(grid.offsetLower[a])) + float(grid.cellSize) / 2
+        run = 0.0
+        for v in pos[1:]:
+            run += float(getWrappedOffset(grid, v, pos[0]))
+        run /= len(pos)
+        x = math.fmod(run + pos[0], float(grid.periodicDomainSize))
+        out.append(x + float(grid.periodicDomainSize) if x < 0 else x)
+    return out
+
+
 def selectNearest(context, centre):
     """ICGenerator::selectNearest (ic.hpp:1447-1455): the cell of the deepest level that holds `centre`
     (Grid::getIndexFromPoint, grid.hpp:672-677)."""

@@ -159,9 +159,11 @@ int gx_zero_window(void *field, const gx_grid_desc *grid, int dtype, const gx_gr
 int gx_masked_sum(const void *field, const unsigned char *mask_n3, int n, int dtype, double *host_out, void *stream);
 int gx_masked_shift_scale(void *field, const unsigned char *mask_n3, int n, int dtype, double shift, double scale,
                           void *stream);
-/* F <- scale * F / k^2 on the independent modes, 0 at k = 0 (VelocityModification::computeVelocity, real-space-derivative
-   branch, linearmodification.hpp:242-262; cosmology::densityToPotential) */
-int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, void *stream);
+/* potential_form == 0: F <- scale * F / k^2 on the independent modes, 0 at k = 0 (VelocityModification::computeVelocity,
+   real-space-derivative branch, linearmodification.hpp:242-262; AngMomentumModification :386-411).
+   potential_form != 0: cosmology::densityToPotential (parameters.hpp:208-225) as written: F <- scale * F * (1/k^2) with the
+   reciprocal forced to 0 where the ky component is 0 (the reference compares its lambda argument `k2` = ky, not k^2). */
+int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, int potential_form, void *stream);
 
 /* ---- Zeldovich (ZeldovichParticleGenerator::calculateOffsetFields, zeldovich.hpp:152-181,248-251) ------- */
 /* psi_axis(k) = i k_axis delta_k / k^2 (0 at k=0 and where k_axis is the Nyquist mode), independent slots

@@ -45,6 +45,13 @@ class Grid:
         d = np.where(d > L / 2, d - L, d)
         return d
 
+    def get_wrapped_offset(self, x0, x1):
+        """Grid::getWrappedOffset(x0, x1) = x0 - x1 wrapped (grid.hpp:445-454)."""
+        d = np.asarray(x0, dtype=np.float64) - np.asarray(x1, dtype=np.float64)
+        L = self.simsize
+        d = np.where(d > L / 2, d - L, d)
+        return np.where(d < -L / 2, d + L, d)
+
     def index_from_point(self, p):
         """getIndexFromPoint (grid.hpp:672-677)."""
         c = []
@@ -73,6 +80,11 @@ def select_sphere(grids, centre, radius):
 def select_cube(grids, centre, side):
     h = float(np.float32(side) / np.float32(2))   # selectCube(float side), ic.hpp:1519-1524
     select(grids, grids[0], centre, lambda x, y, z: (np.abs(x) < h) & (np.abs(y) < h) & (np.abs(z) < h))
+
+
+def select_ellipse(grids, centre, a, b, c):
+    a2, b2, c2 = (float(np.float32(v) * np.float32(v)) for v in (a, b, c))   # selectEllipse(float a, b, c), ic.hpp:1503-1513
+    select(grids, grids[0], centre, lambda x, y, z: x * x / a2 + y * y / b2 + z * z / c2 < 1.)
 
 
 def select_nearest(grids, centre):
@@ -623,6 +635,84 @@ def velocity_localisation_covector(grid, direction):
     np.add.at(f, tuple(p1), -b)
     np.add.at(f, tuple(p2), -a)
     return f
+
+
+def centre_wrapped(grid):
+    """Grid::getCentreWrapped of the flagged cells (grid.hpp:466-494): mean offset from the first flagged cell."""
+    n = grid.n
+    c = np.stack(np.unravel_index(grid.flags, (n, n, n)), axis=0)
+    out = []
+    for a in range(3):
+        pos = (c[a].astype(np.float64) * grid.cell + grid.offset[a]) + grid.cell / 2
+        run = 0.0
+        for v in pos[1:]:
+            run += float(grid.get_wrapped_offset(v, pos[0]))
+        run /= len(pos)
+        x = math.fmod(run + pos[0], grid.simsize)
+        out.append(x + grid.simsize if x < 0 else x)
+    return out
+
+
+def angular_momentum_localisation_covector(grid, direction):
+    """AngMomentumModification::calculateLocalisationCovector (linearmodification.hpp:331-384)."""
+    n = grid.n
+    qc = centre_wrapped(grid)
+    norm = len(grid.flags) * grid.cell
+    a, b = 1. / 12. / norm, -2. / 3. / norm
+    d1, d2 = (direction + 1) % 3, (direction + 2) % 3
+    f = np.zeros((n, n, n))
+    c = np.stack(np.unravel_index(grid.flags, (n, n, n)), axis=0)
+    q = [(c[ax].astype(np.float64) * grid.cell + grid.offset[ax]) + grid.cell / 2 for ax in range(3)]
+    dq = [grid.get_wrapped_offset(qc[ax], q[ax]) for ax in range(3)]   # qcenter - q
+    coeff = {direction: np.zeros(len(grid.flags)), d2: dq[d1], d1: -dq[d2]}
+    S = grid.sim_equiv
+
+    def step(cc, ax, s):
+        cc = cc.copy()
+        v = cc[ax] + s
+        v = np.where(v > S - 1, v - S, v)
+        cc[ax] = np.where(v < 0, v + S, v)
+        return cc
+    for ax in range(3):
+        if ax == direction:
+            continue
+        m1, p1 = step(c, ax, -1), step(c, ax, 1)
+        m2, p2 = step(m1, ax, -1), step(p1, ax, 1)
+        np.add.at(f, tuple(m2), coeff[ax] * a)
+        np.add.at(f, tuple(m1), coeff[ax] * b)
+        np.add.at(f, tuple(p1), -coeff[ax] * b)
+        np.add.at(f, tuple(p2), -coeff[ax] * a)
+    return f
+
+
+def angular_momentum_covector(grids, covs, direction, vel_ratio):
+    """AngMomentumModification (linearmodification.hpp:288-411): localisation, times C_dm^(1/2), times -scale / k^2."""
+    cov = overdensity_covector(grids, covs, angular_momentum_localisation_covector(grids[-1], direction))
+    return [_scale_inv_k2(g, F, -vel_ratio) for g, F in zip(grids, cov)]
+
+
+def potential_covector(grids, covs, Om, a):
+    """PotentialModification (linearmodification.hpp:128-146) with cosmology::densityToPotential (parameters.hpp:208-225),
+    including its test of the *second wavenumber component* (named k2 there) against zero: the whole ky = 0 plane is
+    zeroed, not just k = 0."""
+    prefac = 3. / 2. * Om / a * 100. * 100. / 299792. / 299792.
+    out = []
+    for g, F in zip(grids, overdensity_covector(grids, covs)):
+        k2 = k_magnitude(g) ** 2
+        ky0 = (np.arange(g.n) == 0)[None, :, None]
+        ind = M.independent_mask(g.n)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v = np.where(ky0, 0.0, -prefac * F * (1.0 / k2))
+        out.append(np.where(ind, v, F))
+    return out
+
+
+def _scale_inv_k2(g, F, scale):
+    k2 = k_magnitude(g) ** 2
+    ind = M.independent_mask(g.n)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v = np.where(k2 == 0, 0.0, scale * F / k2)
+    return np.where(ind, v, F)
 
 
 def overdensity_covector(grids, covs, hires_real=None):

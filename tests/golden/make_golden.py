@@ -11,7 +11,8 @@ tests use the committed copies.
   * multi-level goldens: test_01c (zoom), test_02c (two linear modifications with a zoom), test_02i
     (overdensity + variance modification on two levels) reference_grid/grid-{0,1}.npy
     -> [::4, ::4, ::4] subsamples + the id files that flag the zoom region; test_24 (splicing, 16^3) grid-0.npy whole;
-    test_02f / test_02g reference.txt (variance / overdensity values)
+    test_02f / test_02g reference.txt (variance / overdensity values); test_14 (vx modification, 8^3) and test_22 (Ly
+    modification, 32^3, every 7th particle) gadget3 outputs -> pos/vel arrays
 """
 import os
 import shutil
@@ -65,4 +66,22 @@ for t in ("test_01c_zoom_grid", "test_02c_two_modifs", "test_02i_multilevel_algo
     gs = {"grid%d" % l: np.load(f"{REF}/{t}/reference_grid/grid-{l}.npy")[::4, ::4, ::4] for l in (0, 1)}
     np.savez_compressed(f"{HERE}/{t}/grids_every4.npz", **gs)
 np.savez_compressed(f"{HERE}/test_24_splicing/grid0.npz", grid0=np.load(f"{REF}/test_24_splicing/reference_grid/grid-0.npy"))
+
+
+def read_gadget_pos_vel(fn, npart):
+    """gadget2/3 single file, Fortran record markers (io/gadget.hpp:513-552): header, POS (float32 n x 3), VEL, ID."""
+    raw = open(fn, "rb").read()
+    pos = np.frombuffer(raw, dtype=np.float32, count=3 * npart, offset=4 + 256 + 4 + 4).reshape(-1, 3)
+    vel = np.frombuffer(raw, dtype=np.float32, count=3 * npart, offset=4 + 256 + 4 + 4 + 12 * npart + 4 + 4).reshape(-1, 3)
+    return pos, vel
+
+
+cp(f"{REF}/test_14_velocity_modif/paramfile.txt", f"{HERE}/test_14_velocity_modif/paramfile.txt")
+cp(f"{REF}/test_14_velocity_modif/ids.txt", f"{HERE}/test_14_velocity_modif/ids.txt")
+pos, vel = read_gadget_pos_vel(f"{REF}/test_14_velocity_modif/reference_output", 8 ** 3)
+np.savez_compressed(f"{HERE}/test_14_velocity_modif/particles.npz", pos=pos, vel=vel)
+cp(f"{REF}/test_22_angular_momentum_modif/paramfile.txt", f"{HERE}/test_22_angular_momentum_modif/paramfile.txt")
+pos, vel = read_gadget_pos_vel(f"{REF}/test_22_angular_momentum_modif/reference_output", 32 ** 3)
+idx = np.arange(0, 32 ** 3, 7)
+np.savez_compressed(f"{HERE}/test_22_angular_momentum_modif/particles_every7.npz", index=idx, pos=pos[idx], vel=vel[idx])
 print("ok")

@@ -183,13 +183,17 @@ class MockLib:
         self.F(psi, n)[:] = M.zeldovich_offsets_fourier(self.F(d, n), L)[axis]
         return 0
 
-    def gx_scale_inv_k2(self, p, n, dt, L, scale, st):
+    def gx_scale_inv_k2(self, p, n, dt, L, scale, potential_form, st):
         g = ML.Grid(L, n)
         k2 = ML.k_magnitude(g) ** 2
         ind = M.independent_mask(n)
         F = self.F(p, n)
         with np.errstate(divide="ignore", invalid="ignore"):
-            F[:] = np.where(ind, np.where(k2 == 0, 0.0, scale * F / k2), F)
+            if potential_form:
+                ky0 = (np.arange(n) == 0)[None, :, None]
+                F[:] = np.where(ind, np.where(ky0, 0.0, scale * F * (1.0 / k2)), F)
+            else:
+                F[:] = np.where(ind, np.where(k2 == 0, 0.0, scale * F / k2), F)
         return 0
 
     # ---- cross-grid ----------------------------------------------------------------------------------------------

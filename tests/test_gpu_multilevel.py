@@ -209,6 +209,40 @@ def test_velocity_covector_vs_oracle(golden_dir):
         assert _rel(cov.getFieldForLevel(l).getDataVector()[ind], ref[l][ind]) < 1e-9
 
 
+def test_velocity_angular_momentum_potential_modifications_vs_oracle(golden_dir):
+    """`modify vx absolute 0` (test_14), `modify Ly absolute 100` (test_22) and a potential modification through the
+    ModificationManager against the oracle (which is pinned on the gadget goldens of test_14 / test_22)."""
+    from genetic_b200 import zoom as Z
+    cos, dev, ocamb = _camb_pair(golden_dir)
+    ocos = M.Cosmology(0.279, 0.721, 0.817, 99)
+    ratio = M.velocity_to_offset_ratio(ocos)
+    cases = []
+    og = ML.Grid(50.0, 8)
+    og.flags = np.sort(np.loadtxt(os.path.join(golden_dir, "test_14_velocity_modif", "ids.txt"), dtype=np.int64))
+    cases.append((og, "vx", 0.0, lambda g, c: ML.velocity_covector([g], c, 0, ratio)))
+    og = ML.Grid(50.0, 32)
+    ML.select_ellipse([og], (25, 25, 25), 10, 7.5, 5)
+    cases.append((og, "Ly", 100.0, lambda g, c: ML.angular_momentum_covector([g], c, 1, ratio)))
+    og = ML.Grid(50.0, 32)
+    ML.select_sphere([og], (20, 30, 25), 6)
+    cases.append((og, "potential", 1e-6, lambda g, c: ML.potential_covector([g], c, 0.279, 0.01)))
+    for og, name, target, ocov in cases:
+        ctx = _context([og], dev)
+        field = GM.draw(ctx, 8896131)
+        mm = GM.ModificationManager(ctx, cos, field)
+        cdm = [ocamb.covariance(og.size, og.n, "dm")]
+        of = ML.draw_levels([og], 8896131, "real")
+        a = ocov(og, cdm)
+        v = mm.calculateCurrentValueByName(name)
+        assert abs(v - ML.inner_product([og], a, of)) < 1e-9 * max(abs(v), 1e-30)
+        mm.addModificationToList(name, "absolute", target)
+        mm.applyModifications()
+        of2, _ = ML.apply_linear_modifications([og], of, [a], [target])
+        ind = M.independent_mask(og.n)
+        assert _rel(field.getFieldForLevel(0).getDataVector()[ind], of2[0][ind]) < 1e-9
+        assert abs(mm.calculateCurrentValueByName(name) - target) < 1e-9 * max(abs(target), abs(v))
+
+
 def test_variance_values_golden_02f_02g(golden_dir):
     cos, dev, ocamb = _camb_pair(golden_dir)
     og = [ML.Grid(64.0, 64)]

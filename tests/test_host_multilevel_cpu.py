@@ -36,3 +36,4 @@ test_variance_values_golden_02f_02g = _cases.test_variance_values_golden_02f_02g
 test_variance_modification_reaches_target_and_matches_oracle = _cases.test_variance_modification_reaches_target_and_matches_oracle
 test_splice_golden_24_and_oracle = _cases.test_splice_golden_24_and_oracle
 test_overdensity_and_variance_modification_golden_02i = _cases.test_overdensity_and_variance_modification_golden_02i
+test_velocity_angular_momentum_potential_modifications_vs_oracle = _cases.test_velocity_angular_momentum_potential_modifications_vs_oracle

@@ -124,6 +124,42 @@ def test_overdensity_and_variance_modification_golden_02i(golden_dir):
         assert np.abs(out[l][0][::4, ::4, ::4] - ref).max() < 1e-6 * ref.std()
 
 
+def _unigrid_particles(g, f, camb, cos):
+    D = M.apply_transfer(f, camb.covariance(g.size, g.n, "all"), 0.5)
+    psis = [M.to_real(p) for p in M.zeldovich_offsets_fourier(D, g.size)]
+    return M.particles_unigrid(psis, g.size, cos)
+
+
+def test_velocity_modification_golden_14(golden_dir):
+    """test_14: basegrid 50 8; idfile; modify vx absolute 0 -- VelocityModification with the real-space 4th-order
+    derivative (linearmodification.hpp:186-285); gadget3 golden (float32)."""
+    camb, cos = _camb(golden_dir), _cosmo()
+    g = ML.Grid(50.0, 8)
+    g.flags = np.sort(np.loadtxt(os.path.join(golden_dir, "test_14_velocity_modif", "ids.txt"), dtype=np.int64))
+    f = ML.draw_levels([g], 8896131, "real")
+    cdm = [camb.covariance(g.size, g.n, "dm")]
+    a = ML.velocity_covector([g], cdm, 0, M.velocity_to_offset_ratio(cos))
+    f2, _ = ML.apply_linear_modifications([g], f, [a], [0.0])
+    pos, vel, _, _ = _unigrid_particles(g, f2[0], camb, cos)
+    z = np.load(os.path.join(golden_dir, "test_14_velocity_modif", "particles.npz"))
+    assert np.abs(pos - z["pos"]).max() < 4e-6 and np.abs(vel - z["vel"]).max() < 1e-4
+
+
+def test_angular_momentum_modification_golden_22(golden_dir):
+    """test_22: base_grid 50 32; select_ellipse 10 7.5 5; modify Ly absolute 100 -- AngMomentumModification
+    (linearmodification.hpp:288-411), Grid::getCentreWrapped; gadget3 golden (float32)."""
+    camb, cos = _camb(golden_dir), _cosmo()
+    g = ML.Grid(50.0, 32)
+    ML.select_ellipse([g], (25, 25, 25), 10, 7.5, 5)
+    f = ML.draw_levels([g], 8896131, "real")
+    cdm = [camb.covariance(g.size, g.n, "dm")]
+    a = ML.angular_momentum_covector([g], cdm, 1, M.velocity_to_offset_ratio(cos))
+    f2, _ = ML.apply_linear_modifications([g], f, [a], [100.0])
+    pos, vel, _, _ = _unigrid_particles(g, f2[0], camb, cos)
+    z = np.load(os.path.join(golden_dir, "test_22_angular_momentum_modif", "particles_every7.npz"))
+    assert np.abs(pos[z["index"]] - z["pos"]).max() < 4e-6 and np.abs(vel[z["index"]] - z["vel"]).max() < 1e-4
+
+
 def test_splice_golden_24(golden_dir):
     """test_24: 16^3, select_sphere 10, splice 8896132 -- spliceOneLevel + conjugateGradient (splice.hpp:38-118,
     cg.hpp:14-58). CG stops at rtol 1e-6, so the grid is pinned to a few 1e-6 sigma."""
