@@ -287,6 +287,8 @@ struct ChunkParams {
   unsigned int tail_capacity;
   const int *list;            // pass B on a slab: the chunks that can touch this rank's slots (nullptr: all chunks)
   int n_list;
+  int first, count;           // list == nullptr: the kernel covers chunks [first, first + count)
+  ChunkFn *fn_out;            // pass A writes fn_out[chunk - first]
 };
 
 __device__ __forceinline__ State chunk_start_state(const StreamDesc &sd, int q, const Big *jump) {
@@ -308,8 +310,8 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
   // runs with the whole warp converged (lanes that had left early or sat in different parse branches used to run it
   // in 5-lane groups -- 70% of all issued instructions of pass B, ncu r1p).
   const int slot_raw = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = slot_raw < (P.list ? P.n_list : P.n_chunks);
-  const int chunk = in_range ? (P.list ? P.list[slot_raw] : slot_raw) : P.n_chunks - 1;
+  const bool in_range = slot_raw < (P.list ? P.n_list : P.count);
+  const int chunk = in_range ? (P.list ? P.list[slot_raw] : P.first + slot_raw) : P.n_chunks - 1;
   bool live = in_range;
   int sid = 0;
   {  // the stream this chunk belongs to: last stream with first_chunk <= chunk
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest
       f.exit[e] = (unsigned char) (pos[r] - kChunkLen);
       f.count[e] = cnt[r] + dsum;
     }
-    P.fn[chunk] = f;
+    P.fn_out[chunk - P.first] = f;
   }
 }
 
@@ -445,14 +447,17 @@ __global__ void need_kernel(const StreamDesc *streams, int n_streams, int n_chun
   if (g1 >= sd.n_gauss) { g1 = sd.n_gauss; need = true; }  // the chunk that records the end of the stream always runs
   // signed ky values of the slab: storage index j <= n/2 is ky = j, above it ky = j - n (ky = n/2 is never drawn)
   const int s0 = (iy0 + ny <= n / 2) ? iy0 : iy0 - n, s1 = s0 + ny - 1;
-  auto owned = [&](int a, int b) {  // does [a, b] meet [s0, s1] or [-s1, -s0]?
-    return (a <= s1 && b >= s0) || (a <= -s0 && b >= -s1);
-  };
+  auto owned = [&](int a, int b) { return a <= s1 && b >= s0; };  // does [a, b] meet the slab?
   const int ks = sd.shell, two = 2 * ks;
   const long long t0 = (g0 / 2) / 3, t1 = ((g1 - 1) / 2) / 3;
   const int pa = (int) (t0 / two) - ks, pb = (int) (t1 / two) - ks;
-  const int qa = (int) (t0 % two) - ks, qb = (int) (t1 % two) - ks;
-  need = need || owned(ks, ks) || owned(pa, pb) || (pa == pb ? owned(qa, qb) : owned(-ks, ks - 1));
+  int qa = (int) (t0 % two) - ks, qb = (int) (t1 % two) - ks;
+  if (pa != pb) { qa = -ks; qb = ks - 1; }  // the run wraps into the next p: every q can occur
+  // modes (ks,p,q) and (p,ks,q) have kz = q: stored at ky = k2 for q >= 0, at the conjugate ky = -k2 for q < 0, and at
+  // both for q == 0 (the explicit second write of drawOneFourierMode); mode (p,q,ks) has kz = ks > 0: stored at ky = q.
+  const bool plus = qb >= 0, minus = qa <= 0;
+  need = need || (plus && (owned(pa, pb) || owned(ks, ks))) || (minus && (owned(-pb, -pa) || owned(-ks, -ks))) ||
+         owned(qa, qb);
   if (need) list[atomicAdd(count, 1u)] = chunk;
 }
 
@@ -581,9 +586,13 @@ static int ws_pin(int slot, size_t bytes, void **out) {
   return 0;
 }
 
+// phase 0: everything. phase 1: pass A only, for this rank's share of the chunks, into `fn_io` (device, `fn_stride` records
+// per rank). phase 2: skip pass A, take the chunk functions of all ranks from `fn_io` (all-gathered by the caller).
+struct Phase { int which = 0; int world = 1, rank = 0; void *fn_io = nullptr; };
+
 template <typename T>
 static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::vector<unsigned long long> *end_raw,
-                       cudaStream_t cs) {
+                       cudaStream_t cs, Phase phase = Phase()) {
   if (ensure_jump_table()) return 1;
   const int ns = (int) reqs.size();
   if (ns == 0) return 0;
@@ -613,6 +622,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   }
   const int n0 = (int) n_chunks;
   if (n0 == 0) return 0;
+  const int per_rank = (n0 + phase.world - 1) / phase.world;  // chunk functions per rank in the all-gathered buffer
 
   // scan levels
   std::vector<int> level_n;
@@ -646,14 +656,29 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   ChunkParams P;
   P.streams = d_streams; P.n_streams = ns; P.n_chunks = n0; P.jump = g_jump; P.fn = d_fn[0];
   P.scan = d_st[0]; P.stream_end = d_end; P.tails = d_tails; P.tail_count = d_tail_count; P.tail_capacity = tail_cap;
-  P.list = nullptr; P.n_list = 0;
+  P.list = nullptr; P.n_list = 0; P.first = 0; P.count = n0; P.fn_out = d_fn[0];
   const int grid = (n0 + kThreads - 1) / kThreads;
-  {
+  if (phase.which == 1) {
+    P.first = std::min(n0, phase.rank * per_rank);
+    P.count = std::min(n0, P.first + per_rank) - P.first;
+    P.fn_out = (ChunkFn *) phase.fn_io;
+    if (P.count > 0) {
+      GX_TIMED("rng_pass_a", cs);
+      rng_chunk_kernel<0, T><<<(P.count + kThreads - 1) / kThreads, kThreads, 0, cs>>>(P, dest);
+      count_launch();
+    }
+    GX_LAUNCH_CHECK();
+    return 0;
+  }
+  if (phase.which == 2) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(d_fn[0], phase.fn_io, sizeof(ChunkFn) * (size_t) n0, cudaMemcpyDeviceToDevice, cs));
+  } else {
     GX_TIMED("rng_pass_a", cs);
     rng_chunk_kernel<0, T><<<grid, kThreads, 0, cs>>>(P, dest);
+    count_launch();
   }
-  count_launch();
   GX_LAUNCH_CHECK();
+  P.first = 0; P.count = n0;
   {
     GX_TIMED("rng_scan", cs);
     for (int l = 1; l < nl; ++l) {
@@ -749,9 +774,9 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
 // caller runs the slab-decomposed r2c and zeroes Re(DC)).
 template <typename T>
 static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int reverse, unsigned long long *offset_io,
-                        cudaStream_t cs, int world = 1, int rank = 0) {
+                        cudaStream_t cs, int world = 1, int rank = 0, Phase phase = Phase()) {
   const size_t bytes = (size_t) 2 * n * n * (n / 2 + 1) * sizeof(T) / (size_t) world;
-  GX_CUDA_CHECK(cudaMemsetAsync(field, 0, bytes, cs));
+  if (phase.which != 1) GX_CUDA_CHECK(cudaMemsetAsync(field, 0, bytes, cs));
   Dest<T> dest;
   dest.n = n; dest.reverse = reverse; dest.field = (T *) field; dest.list = nullptr;
   dest.ny = n / world; dest.iy0 = rank * dest.ny;
@@ -774,8 +799,9 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
   } else {
     return fail("gx_noise_draw: unknown mode");
   }
-  int rc = run_streams<T>(reqs, dest, &ends, cs);
+  int rc = run_streams<T>(reqs, dest, &ends, cs, phase);
   if (rc) return rc;
+  if (phase.which == 1) return 0;
   if (mode == GX_NOISE_REAL && world == 1) {
     rc = fft::fft3d<T>((T *) field, n, -1, cs);
     if (rc) return rc;
@@ -809,6 +835,33 @@ int gx_slab_noise_draw(void *slab, int n, int dtype, int world, int rank, unsign
   if (world < 1 || n % world != 0 || rank < 0 || rank >= world) return gx::fail("gx_slab_noise_draw: bad world/rank");
   if (dtype == GX_F64) return noise_draw_t<double>(slab, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream, world, rank);
   if (dtype == GX_F32) return noise_draw_t<float>(slab, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream, world, rank);
+  return gx::fail("bad dtype");
+}
+
+// chunk functions of the per-shell streams: sum over shells of ceil(raw_budget(24 ks^2) / kChunkLen), split between ranks
+size_t gx_slab_noise_fn_bytes(int n, int world) {
+  long long chunks = 0;
+  for (int ks = 1; ks < n / 2; ++ks) chunks += (raw_budget(24ll * ks * ks) + kChunkLen - 1) / kChunkLen;
+  if (world < 1) world = 1;
+  return (size_t) ((chunks + world - 1) / world) * sizeof(ChunkFn);
+}
+
+int gx_slab_noise_pass_a(void *fn_local, int n, int dtype, int world, int rank, unsigned long seed, void *stream) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (world < 1 || n % world != 0 || rank < 0 || rank >= world) return gx::fail("gx_slab_noise_pass_a: bad world/rank");
+  Phase ph; ph.which = 1; ph.world = world; ph.rank = rank; ph.fn_io = fn_local;
+  if (dtype == GX_F64) return noise_draw_t<double>(nullptr, n, seed, GX_NOISE_FOURIER_PARALLEL, 0, nullptr, (cudaStream_t) stream, world, rank, ph);
+  if (dtype == GX_F32) return noise_draw_t<float>(nullptr, n, seed, GX_NOISE_FOURIER_PARALLEL, 0, nullptr, (cudaStream_t) stream, world, rank, ph);
+  return gx::fail("bad dtype");
+}
+
+int gx_slab_noise_finish(void *slab, const void *fn_all, int n, int dtype, int world, int rank, unsigned long seed,
+                         int reverse_order, void *stream) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (world < 1 || n % world != 0 || rank < 0 || rank >= world) return gx::fail("gx_slab_noise_finish: bad world/rank");
+  Phase ph; ph.which = 2; ph.world = world; ph.rank = rank; ph.fn_io = const_cast<void *>(fn_all);
+  if (dtype == GX_F64) return noise_draw_t<double>(slab, n, seed, GX_NOISE_FOURIER_PARALLEL, reverse_order, nullptr, (cudaStream_t) stream, world, rank, ph);
+  if (dtype == GX_F32) return noise_draw_t<float>(slab, n, seed, GX_NOISE_FOURIER_PARALLEL, reverse_order, nullptr, (cudaStream_t) stream, world, rank, ph);
   return gx::fail("bad dtype");
 }
 

@@ -89,6 +89,9 @@ PROTOTYPES = {
     "gx_unigrid_ic": (ci, [P(IcParams), vp, vp, vp, vp, csz, vp, vp, csz, vp]),
     "gx_slab_bytes": (csz, [ci, ci, ci]),
     "gx_slab_noise_draw": (ci, [vp, ci, ci, ci, ci, cul, ci, ci, P(cull), vp]),
+    "gx_slab_noise_fn_bytes": (csz, [ci, ci]),
+    "gx_slab_noise_pass_a": (ci, [vp, ci, ci, ci, ci, cul, vp]),
+    "gx_slab_noise_finish": (ci, [vp, vp, ci, ci, ci, ci, cul, ci, vp]),
     "gx_slab_zero_dc": (ci, [vp, ci, vp]),
     "gx_slab_unit_variance": (ci, [vp, ci, ci, ci, ci, vp]),
     "gx_slab_apply_transfer": (ci, [vp, ci, ci, ci, ci, cd, vp, cd, ci, vp]),
@@ -102,7 +105,7 @@ PROTOTYPES = {
     "gx_timing_enable": (ci, [ci]),
     "gx_timing_report": (ci, [C.c_char_p, ci]),
 }
-NOT_STATUS = {"gx_timing_report", "gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_slab_bytes", "gx_spectrum_amplitude",
+NOT_STATUS = {"gx_timing_report", "gx_last_error", "gx_version", "gx_launch_count", "gx_field_bytes", "gx_slab_bytes", "gx_slab_noise_fn_bytes", "gx_spectrum_amplitude",
               "gx_spectrum_eval"}
 
 _lib = None

@@ -63,6 +63,14 @@ class TorchComm:
             return
         self.dist.all_to_all_single(recv, send, group=self.group)
 
+    def all_to_all_async(self, recv, send):
+        """Starts the exchange and returns a handle with wait(): the collective runs on the backend's own stream, so kernels
+        issued on the current stream after this call overlap with it (the next component's x-pass)."""
+        if self.world == 1:
+            recv.copy_(send)
+            return None
+        return self.dist.all_to_all_single(recv, send, group=self.group, async_op=True)
+
     def all_gather(self, out, inp):
         if self.world == 1:
             out.copy_(inp)
@@ -102,6 +110,19 @@ class CudaSlabOps:
         self.lib.gx_slab_noise_draw(self._p(slab), g.n, self.dt, g.world, g.rank, seed, mode, int(reverse),
                                     C.byref(off), self._st())
         return off.value
+
+    # parallel Fourier order in phases: pass A shared between the ranks (include/genetic_b200.h)
+    def noise_fn_bytes(self):
+        return self.lib.gx_slab_noise_fn_bytes(self.geo.n, self.geo.world)
+
+    def noise_pass_a(self, fn_local, seed):
+        g = self.geo
+        self.lib.gx_slab_noise_pass_a(self._p(fn_local), g.n, self.dt, g.world, g.rank, seed, self._st())
+
+    def noise_finish(self, slab, fn_all, seed, reverse):
+        g = self.geo
+        self.lib.gx_slab_noise_finish(self._p(slab), self._p(fn_all), g.n, self.dt, g.world, g.rank, seed, int(reverse),
+                                      self._st())
 
     def unit_variance(self, slab):
         g = self.geo
@@ -154,13 +175,19 @@ class CudaSlabOps:
 class SlabPipeline:
     """Sequencing of the slab path for one rank. All tensors are flat uint8 buffers of geo.slab_bytes."""
 
-    def __init__(self, geo, ops, comm):
+    def __init__(self, geo, ops, comm, overlap=False):
         self.geo, self.ops, self.comm = geo, ops, comm
         g = geo
         self.bufA = ops.alloc(g.slab_bytes)
         self.bufB = ops.alloc(g.slab_bytes)
+        # overlap: a second pair of buffers so that the all-to-all of one displacement component runs while the next
+        # component's x-pass and the previous component's y/z-passes compute (5 slab-sized buffers in total with delta)
+        self.overlap = bool(overlap) and g.world > 1 and hasattr(comm, "all_to_all_async")
+        self.bufA2 = ops.alloc(g.slab_bytes) if self.overlap else None
+        self.bufB2 = ops.alloc(g.slab_bytes) if self.overlap else None
         self.planes_local = ops.alloc(2 * g.planes_local_complex * g.itemsize)
         self.planes_all = ops.alloc(2 * g.planes_local_complex * g.itemsize * g.world)
+        self.fn_local = self.fn_all = None
 
     # ---- general transforms (Field::toReal / toFourier on a slab) ---------------------------------------------
     def gather_mirror_planes(self, slab):
@@ -187,8 +214,22 @@ class SlabPipeline:
         self.ops.x_pass(slab, -1, True)
 
     # ---- the IC path -------------------------------------------------------------------------------------------
+    def draw_noise(self, delta, seed, mode, reverse):
+        """RandomFieldGenerator::draw for this rank's slab. With per-shell streams and more than one rank, the chunk parse
+        is split between the ranks and its 40-byte-per-chunk results are all-gathered (one small collective)."""
+        ops, g = self.ops, self.geo
+        if g.world > 1 and mode == L.NOISE_FOURIER_PARALLEL and hasattr(ops, "noise_pass_a"):
+            nb = ops.noise_fn_bytes()
+            if self.fn_local is None or self.fn_local.numel() != nb:
+                self.fn_local, self.fn_all = ops.alloc(nb), ops.alloc(nb * g.world)
+            ops.noise_pass_a(self.fn_local, seed)
+            self.comm.all_gather(self.fn_all, self.fn_local)
+            ops.noise_finish(delta, self.fn_all, seed, reverse)
+        else:
+            ops.noise_draw(delta, seed, mode, reverse)
+
     def draw_delta(self, delta, seed, mode, reverse, fix_power, grid_length, spectrum):
-        self.ops.noise_draw(delta, seed, mode, reverse)
+        self.draw_noise(delta, seed, mode, reverse)
         if mode == L.NOISE_REAL:
             self.to_fourier(delta)
             if self.geo.rank == 0:
@@ -201,10 +242,25 @@ class SlabPipeline:
         """delta: ky-slab holding delta_k / k^2. emit(axis, work) consumes the half-transformed x-slab
         ([x_local][y][kz], y and x already inverse-transformed) of each displacement component."""
         self.gather_mirror_planes(delta)
+        if not self.overlap:
+            for axis in range(3):
+                self.ops.x_inverse_mirror(delta, self.planes_all, self.bufA, grid_length, 1, axis)
+                self.inverse_after_x(self.bufA)  # B <- exchange(A); A <- y-pass(B)
+                emit(axis, self.bufA)
+            return
+        A, B = (self.bufA, self.bufA2), (self.bufB, self.bufB2)
+        self.ops.x_inverse_mirror(delta, self.planes_all, A[0], grid_length, 1, 0)
+        work = self.comm.all_to_all_async(B[0], A[0])
         for axis in range(3):
-            self.ops.x_inverse_mirror(delta, self.planes_all, self.bufA, grid_length, 1, axis)
-            self.inverse_after_x(self.bufA)  # B <- exchange(A); A <- y-pass(B)
-            emit(axis, self.bufA)
+            cur, nxt = axis & 1, (axis + 1) & 1
+            if axis + 1 < 3:   # runs while the exchange of `axis` is in flight; A[nxt] was last read by emit(axis - 1)
+                self.ops.x_inverse_mirror(delta, self.planes_all, A[nxt], grid_length, 1, axis + 1)
+            if work is not None:
+                work.wait()
+            if axis + 1 < 3:   # B[nxt] was last read by the y-pass of axis - 1, already enqueued on this stream
+                work = self.comm.all_to_all_async(B[nxt], A[nxt])
+            self.ops.y_pass(B[cur], A[cur], +1, True, False)
+            emit(axis, A[cur])
 
 
 class EmitStager:
@@ -299,7 +355,10 @@ def bench_main(args, lib, world, rank, local_rank):
     geo = SlabGeometry(n, world, rank, 8)
     ops = CudaSlabOps(geo, dtype)
     comm = TorchComm()
-    pipe = SlabPipeline(geo, ops, comm)
+    # the overlapped exchange needs 5 slab-sized buffers (+ staging): use it when they fit
+    free_b, _ = torch.cuda.mem_get_info()
+    overlap = os.environ.get("GX_SLAB_OVERLAP", "1") != "0" and free_b > 5 * geo.slab_bytes + (12 << 30)
+    pipe = SlabPipeline(geo, ops, comm, overlap=overlap)
     delta = ops.alloc(geo.slab_bytes)
     osz = 4
     vel_ratio = cos.zeldovichVelocityToOffsetRatio(dtype)
@@ -397,7 +456,8 @@ def bench_main(args, lib, world, rank, local_rank):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": B.workload_name(n, "f64"), "output": "float32 pos+vel, component-major, x-slab per rank",
                            "parallelism": "slab%d: ky-slabs in Fourier space, x-slabs in real space, one NCCL all-to-all "
-                                          "per inverse transform" % world,
+                                          "per inverse transform%s" % (world, ", overlapped with the neighbouring components' "
+                                                                              "passes" if pipe.overlap else ""),
                            "l2": "inputs larger than L2 (each slab %.2f GB)" % (geo.slab_bytes / 1e9)},
                 "clocks": clocks,
                 "e2e": {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": 3 * 8 * 213 * world,

@@ -222,6 +222,15 @@ size_t gx_slab_bytes(int n, int dtype, int world);
    real space (follow with the slab r2c and gx_slab_zero_dc on rank 0). Bit-identical to gx_noise_draw slot for slot. */
 int gx_slab_noise_draw(void *slab, int n, int dtype, int world, int rank, unsigned long seed, int mode,
                        int reverse_order, unsigned long long *stream_offset_io, void *stream);
+/* The same for GX_NOISE_FOURIER_PARALLEL in phases, so that the chunk parse (pass A of the generator: the per-chunk transfer
+   functions the scan needs, ~40 % of the noise time) is computed once across the ranks instead of once per rank:
+     gx_slab_noise_pass_a  : this rank's share of the chunks -> fn_local (device, gx_slab_noise_fn_bytes(n, world) bytes)
+     (host layer)          : all-gather of fn_local into fn_all (world * that many bytes, rank-major)
+     gx_slab_noise_finish  : scan + delivery of the chunks that can reach this rank's slab. Bit-identical to gx_slab_noise_draw. */
+size_t gx_slab_noise_fn_bytes(int n, int world);
+int gx_slab_noise_pass_a(void *fn_local, int n, int dtype, int world, int rank, unsigned long seed, void *stream);
+int gx_slab_noise_finish(void *slab, const void *fn_all, int n, int dtype, int world, int rank, unsigned long seed,
+                         int reverse_order, void *stream);
 int gx_slab_zero_dc(void *slab, int dtype, void *stream);
 int gx_slab_unit_variance(void *slab, int n, int dtype, int world, int rank, void *stream);
 /* Field::applyTransferFunction on the ky-slab; divide_k2 != 0 leaves delta_k / k^2 (see gx_unigrid_ic) */

@@ -44,6 +44,10 @@ class LocalComm:
         self.torch.cuda.synchronize()
         self.sh.barrier.wait()
 
+    def all_to_all_async(self, recv, send):
+        self.all_to_all(recv, send)   # in-process stand-in: completes before returning
+        return None
+
     def all_gather(self, out, inp):
         self._publish(inp)
         blk = inp.numel()
@@ -96,8 +100,9 @@ def _run_ranks(world, body):
     return results
 
 
-@pytest.mark.parametrize("world,n", [(1, 32), (2, 32), (4, 64), (8, 64), (4, 512)])
-def test_slab_ic_matches_single_gpu(world, n):
+@pytest.mark.parametrize("world,n,overlap", [(1, 32, False), (2, 32, False), (4, 64, False), (8, 64, False), (4, 512, False),
+                                             (4, 64, True), (8, 128, True)])
+def test_slab_ic_matches_single_gpu(world, n, overlap):
     import torch
     import genetic_b200 as gb
     from genetic_b200 import lib as L, slab as SL
@@ -111,7 +116,7 @@ def test_slab_ic_matches_single_gpu(world, n):
     def body(rank, comm):
         geo = SL.SlabGeometry(n, world, rank, 8)
         ops = LockedOps(SL.CudaSlabOps(geo, np.float64))
-        pipe = SL.SlabPipeline(geo, ops, comm)
+        pipe = SL.SlabPipeline(geo, ops, comm, overlap=overlap)
         delta = ops.alloc(geo.slab_bytes)
         out_pos, out_vel = ops.alloc(3 * geo.particles * 8), ops.alloc(3 * geo.particles * 8)
         SL.unigrid_ic_slab(geo, ops, comm, seed, L.NOISE_FOURIER_PARALLEL, 0, 0, grid, spectrum, ratio, np.float64, delta,

@@ -182,7 +182,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, mode, outdir):
+def _worker(rank, world, port, n, mode, outdir, overlap=False):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -197,7 +197,8 @@ def _worker(rank, world, port, n, mode, outdir):
         geo = SL.SlabGeometry(n, world, rank, 8)
         ops = NumpyOps(geo, box, ocos)
         comm = SL.TorchComm()
-        pipe = SL.SlabPipeline(geo, ops, comm)
+        pipe = SL.SlabPipeline(geo, ops, comm, overlap=overlap)
+        assert pipe.overlap == (overlap and world > 1)
         delta = ops.alloc(geo.slab_bytes)
         grid = H.Grid(box, n)
         ratio = M.velocity_to_offset_ratio(ocos)
@@ -218,12 +219,15 @@ def _worker(rank, world, port, n, mode, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,mode", [(2, 16, 2), (4, 16, 2), (2, 8, 0), (2, 8, 1)])
-def test_slab_pipeline_matches_single_process_oracle(tmp_path, world, n, mode):
+@pytest.mark.parametrize("world,n,mode,overlap", [(2, 16, 2, False), (4, 16, 2, False), (2, 8, 0, False), (2, 8, 1, False),
+                                                  (2, 16, 2, True), (4, 16, 2, True)])
+def test_slab_pipeline_matches_single_process_oracle(tmp_path, world, n, mode, overlap):
+    """overlap=True: the double-buffered Zeldovich loop (exchange of one component in flight during the neighbouring
+    components' passes) must give the same particles as the sequential one."""
     import torch.multiprocessing as mp
     from oracle import model as M
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n, mode, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, mode, str(tmp_path), overlap), nprocs=world, join=True)
     box, seed = 50.0, 8896131
     ocos = M.Cosmology(0.279, 0.721, 0.817, 99)
     name = {0: "real", 1: "fourier_serial", 2: "fourier_parallel"}[mode]
