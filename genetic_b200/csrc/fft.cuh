@@ -97,7 +97,8 @@ template <typename T, int N, int CL_, int TC_, int SEL_ = 0> struct ColsCfg {
   static constexpr int R = N / CL;
   // SEL_ bit 0: 8-points-per-thread plan (exists for 256-point local transforms); bit 2: single buffer, one tile per
   // cluster (non-persistent); bit 1: timing experiment only (wrong results): no DSMEM traffic
-  static constexpr int SEL = (R == 256 && (SEL_ & 1)) ? 1 : 0;
+  // SEL_ bit 3: form the butterfly twiddles as powers of one table entry (as the row passes do)
+  static constexpr int SEL = ((R == 256 && (SEL_ & 1)) ? 1 : 0) | ((SEL_ & 8) ? 2 : 0);
   static constexpr bool kExperimentLocalPull = (SEL_ & 2) != 0;
   static constexpr int NBUF = (SEL_ & 4) ? 1 : 2;
   using B = BlockFFT<T, R, -1, TC, SEL>;

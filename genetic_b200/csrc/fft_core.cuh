@@ -122,7 +122,7 @@ template <int R, int DIR, typename T> GX_HD void butterfly(cplx<T> *a) {
 // ---- per-length plan: radices (largest first), E = radices[0]
 // SEL = 0: fewest stages (16 points per thread where possible). SEL = 1: 8 points per thread -- half the registers and
 // twice the threads per line, for kernels that need more warps in flight (the f64 column passes).
-template <int NC, int SEL = 0> struct Plan : Plan<NC, 0> {};
+template <int NC, int SEL = 0> struct Plan : Plan<NC, 0> {};  // SEL != 0 without a specialisation: the default plan
 #define GX_PLAN(N_, S_, R0, R1, R2)                                  \
   template <> struct Plan<N_, 0> {                                   \
     static constexpr int S = S_;                                     \
@@ -158,7 +158,7 @@ template <typename T> GX_HD constexpr int line_pitch(int nc) { return nc + nc / 
 //         so a warp touches LS * sizeof(C) contiguous bytes per line position and no skew is needed).
 template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT {
   using C = cplx<T>;
-  using PL = Plan<NC, SEL>;
+  using PL = Plan<NC, (SEL & 1)>;  // SEL bit 0: alternative plan; bit 1: twiddle powers by multiplication in column passes
   static constexpr int S = PL::S;
   static constexpr int E = PL::radix(0);
   static constexpr int P = NC / E;
@@ -191,7 +191,7 @@ template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT 
   // and the L1 data pipe, not the FP64 pipe, is what the passes run out of (ncu: L1 data pipe 83 %, FP64 26 % in the z-pass).
   // (Row passes only, LS == 0: the column passes read their twiddles from a private shared-memory copy, their L1 data pipe
   // is at ~50 %, and the extra live values made them spill under the 96-register cap.)
-  static constexpr bool kPowersByMultiplication = (sizeof(T) == 8) && (LS == 0);
+  static constexpr bool kPowersByMultiplication = (sizeof(T) == 8) && (LS == 0 || (SEL & 2) != 0);
   // a[q] *= w1^q for q = 1..R-1 with few values live (w1..w3 and w4, w8, w12): w^(h+l) = w^h * w^l
   template <int R> GX_HD static void apply_twiddle_powers(C w1, C *a) {
     a[1] = cmul(a[1], w1);

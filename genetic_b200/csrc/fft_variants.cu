@@ -30,6 +30,13 @@ extern "C" int gx_dev_fft_cols_variant(void *field, int n, int pass, int variant
       case 3: return run_variant<2048, 16, 8, 8, 4>(field, pass, st);
       case 4: return run_variant<2048, 16, 8, 10, 4>(field, pass, st);
       case 5: return run_variant<2048, 16, 16, 4, 4>(field, pass, st);
+      case 6: return run_variant<2048, 8, 8, 2, 5>(field, pass, st);    // 8 points per thread, 256-thread CTAs
+      case 7: return run_variant<2048, 8, 8, 3, 5>(field, pass, st);
+      case 8: return run_variant<2048, 8, 8, 4, 5>(field, pass, st);
+      case 9: return run_variant<2048, 8, 8, 5, 12>(field, pass, st);   // twiddle powers by multiplication
+      case 10: return run_variant<2048, 8, 8, 4, 12>(field, pass, st);
+      case 11: return run_variant<2048, 8, 8, 3, 13>(field, pass, st);  // both
+      case 12: return run_variant<2048, 8, 8, 4, 13>(field, pass, st);
     }
   } else if (n == 1024) {
     switch (variant) {

@@ -7,7 +7,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from genetic_b200 import lib as L
 
-NAMES = {2048: ["CL8 TC8 minb4 1buf", "CL8 TC8 minb5 1buf", "CL8 TC8 minb6 1buf", "CL16 TC8 minb8 1buf", "CL16 TC8 minb10 1buf", "CL16 TC16 minb4 1buf"],
+NAMES = {2048: ["CL8 TC8 minb4 1buf", "CL8 TC8 minb5 1buf", "CL8 TC8 minb6 1buf", "CL16 TC8 minb8 1buf", "CL16 TC8 minb10 1buf", "CL16 TC16 minb4 1buf",
+                "CL8 TC8 8pt minb2", "CL8 TC8 8pt minb3", "CL8 TC8 8pt minb4", "CL8 TC8 powers minb5", "CL8 TC8 powers minb4",
+                "CL8 TC8 8pt+powers minb3", "CL8 TC8 8pt+powers minb4"],
          1024: ["CL4 TC8 minb4 1buf", "CL4 TC8 minb5 1buf", "CL4 TC8 minb6 1buf", "CL8 TC8 minb8 1buf", "CL8 TC8 minb10 1buf", "CL8 TC16 minb4 1buf"]}
 
 
