@@ -260,7 +260,11 @@ def run_ours(args):
     # (2 B) per component; the z-pass reads the field (B) and writes pos+vel of every particle (2 * osz bytes each). A
     # class may run as several launches per step (the z-pass is launched once per staging slab), so the rate is
     # class bytes / class time and "per launch" is the mean over the class's launches.
-    class_bytes = {"fft_cols_x": 3 * 2 * fbytes, "fft_cols_y": 3 * 2 * fbytes,
+    def n_launch(k):
+        return classes[k][0] / args.steps if k in classes else 0
+
+    # (a column pass is one launch: the shared-transform schedule runs 3 x-passes and 2 y-passes per IC)
+    class_bytes = {"fft_cols_x": n_launch("fft_cols_x") * 2 * fbytes, "fft_cols_y": n_launch("fft_cols_y") * 2 * fbytes,
                    "fft_rows_c2r": 3 * (fbytes + 2 * osz * n3), "apply_transfer": 2 * fbytes,
                    "rng_pass_b": fbytes}
     passes = {}
@@ -279,7 +283,11 @@ def run_ours(args):
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         traffic = None  # dram bytes of the same kernel from the ncu --set full capture (profiles/), per launch
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "ncu --set full of this kernel at 1024^3: dram read+write = 1.00 x algorithmic bytes "
+                                "(profiles/r1s8_ncu_full_1024_summary.txt); at 2048^3 ncu would have to save and restore "
+                                "~150 GB of device memory per replay pass, so no capture exists at the bench size",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "per_class_ms_per_step": {k: v[1] / args.steps for k, v in sorted(classes.items())},
                 "passes": passes, "share_of_step": tot / args.steps / ms}

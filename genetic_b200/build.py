@@ -53,22 +53,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
-HOST_SRC = os.path.join(os.path.dirname(HERE), "host", "genetic_b200_ic.cpp")
-HOST_BIN = os.path.join(os.path.dirname(HERE), "host", "genetic_b200_ic")
+HOST_DIR = os.path.join(os.path.dirname(HERE), "host")
+HOST_PROGRAMS = ("genetic_b200_ic", "genetic_b200_chi2")
+HOST_BIN = os.path.join(HOST_DIR, "genetic_b200_ic")
 
 
-def build_host(force=False):
-    """The C++ host layer (include/genetic_b200.hpp) and its paramfile driver: plain g++, linked against the C ABI."""
-    hdr = os.path.join(os.path.dirname(HERE), "include", "genetic_b200.hpp")
-    newest = max(os.path.getmtime(p) for p in (HOST_SRC, hdr, os.path.join(os.path.dirname(HERE), "include", "genetic_b200.h")))
-    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= newest:
-        return HOST_BIN
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(os.path.dirname(HERE), "include"), HOST_SRC,
-           "-L", HERE, "-lgenetic_b200", "-Wl,-rpath,$ORIGIN/../genetic_b200", "-o", HOST_BIN]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed: %s\n%s" % (" ".join(cmd), r.stderr))
-    return HOST_BIN
+def build_host(force=False, program="genetic_b200_ic"):
+    """The C++ host layer (include/genetic_b200.hpp) and its drivers: plain g++, linked against the C ABI."""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    out = None
+    for prog in HOST_PROGRAMS:
+        src, exe = os.path.join(HOST_DIR, prog + ".cpp"), os.path.join(HOST_DIR, prog)
+        newest = max(os.path.getmtime(p) for p in (src, os.path.join(inc, "genetic_b200.hpp"), os.path.join(inc, "genetic_b200.h")))
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < newest:
+            cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I", inc, src, "-L", HERE, "-lgenetic_b200",
+                   "-Wl,-rpath,$ORIGIN/../genetic_b200", "-o", exe]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed: %s\n%s" % (" ".join(cmd), r.stderr))
+        if prog == program:
+            out = exe
+    return out
 
 
 if __name__ == "__main__":

@@ -22,6 +22,8 @@
 #include "gx_common.cuh"
 #include "spectral.cuh"
 #include <cmath>
+#include <cstring>
+#include <limits>
 #include <vector>
 
 namespace gx {
@@ -236,25 +238,63 @@ template <typename T> struct DevTabs {
     }
     return 0;
   }
-  int release(cudaStream_t st) {
-    if (blob) { GX_CUDA_CHECK(cudaStreamSynchronize(st)); GX_CUDA_CHECK(cudaFree(blob)); blob = nullptr; }
-    return 0;
-  }
 };
 
-template <typename T, int MODE>
-static int run_gather(void *dst, int n_dst, const void *src, int n_src, const HostAxis<T> h[3], T scale, const char *name,
-                      cudaStream_t st) {
-  DevTabs<T> d;
-  if (d.upload(h, st)) return 1;
-  {
-    GX_TIMED(name, st);
-    axis_gather_add_kernel<T, MODE><<<dim3(n_dst, n_dst), 256, (size_t) n_src * sizeof(T), st>>>(
-        (T *) dst, n_dst, (const T *) src, n_src, d.tab[0], d.tab[1], d.tab[2], scale);
-    count_launch();
+// The tables depend only on (kind, dtype, the two grid descriptors): the metric, the covector construction and the variance
+// iterations repeat the same few transfers hundreds of times, so the device copies are kept (a few KB each, at most 64
+// entries, dropped oldest-first) instead of being rebuilt, allocated, copied and freed -- with a stream sync -- per call.
+struct TabKey {
+  int kind, dtype, device;
+  gx_grid_desc a, b;
+  bool operator==(const TabKey &o) const {
+    return kind == o.kind && dtype == o.dtype && device == o.device && memcmp(&a, &o.a, sizeof(a)) == 0 && memcmp(&b, &o.b, sizeof(b)) == 0;
   }
+};
+struct TabEntry { TabKey key; void *tabs; };  // tabs: heap DevTabs<T> of the entry's dtype
+static std::vector<TabEntry> g_tab_cache;
+
+static TabKey make_key(int kind, int dtype, const gx_grid_desc &a, const gx_grid_desc &b) {
+  TabKey k;
+  memset(&k, 0, sizeof(k));  // descriptors are compared bytewise: clear the padding
+  k.kind = kind; k.dtype = dtype;
+  cudaGetDevice(&k.device);
+  k.a.n = a.n; k.a.cell_size = a.cell_size; k.a.domain_size = a.domain_size;
+  k.b.n = b.n; k.b.cell_size = b.cell_size; k.b.domain_size = b.domain_size;
+  for (int i = 0; i < 3; ++i) { k.a.offset_lower[i] = a.offset_lower[i]; k.b.offset_lower[i] = b.offset_lower[i]; }
+  return k;
+}
+
+// kind 0: interpolate (coarse -> fine), 1: sub-cell mean (fine -> coarse), 2: deinterpolate. Builds on a miss.
+template <typename T, class Build>
+static int cached_tabs(int kind, const gx_grid_desc &a, const gx_grid_desc &b, Build build, cudaStream_t st, DevTabs<T> **out) {
+  const TabKey key = make_key(kind, sizeof(T) == 8 ? GX_F64 : GX_F32, a, b);
+  for (auto &e : g_tab_cache)
+    if (e.key == key) { *out = (DevTabs<T> *) e.tabs; return 0; }
+  HostAxis<T> h[3];
+  if (build(h)) return 1;
+  DevTabs<T> *d = new DevTabs<T>();
+  if (d->upload(h, st)) { delete d; return 1; }
+  if (g_tab_cache.size() >= 64) {
+    GX_CUDA_CHECK(cudaDeviceSynchronize());  // a kernel may still be reading the oldest entry
+    TabEntry old = g_tab_cache.front();
+    g_tab_cache.erase(g_tab_cache.begin());
+    cudaFree(((DevTabs<T> *) old.tabs)->blob);  // blob is the first member for either T
+    delete (DevTabs<T> *) old.tabs;
+  }
+  g_tab_cache.push_back(TabEntry{key, d});
+  *out = d;
+  return 0;
+}
+
+template <typename T, int MODE>
+static int run_gather(void *dst, int n_dst, const void *src, int n_src, const DevTabs<T> &d, T scale, const char *name,
+                      cudaStream_t st) {
+  GX_TIMED(name, st);
+  axis_gather_add_kernel<T, MODE><<<dim3(n_dst, n_dst), 256, (size_t) n_src * sizeof(T), st>>>(
+      (T *) dst, n_dst, (const T *) src, n_src, d.tab[0], d.tab[1], d.tab[2], scale);
+  count_launch();
   GX_LAUNCH_CHECK();
-  return d.release(st);
+  return 0;
 }
 
 static int check_desc(const gx_grid_desc *g, const char *who) {
@@ -266,14 +306,14 @@ static int check_desc(const gx_grid_desc *g, const char *who) {
 
 template <typename T>
 static int interp_add_t(void *dst, const gx_grid_desc *gd, const void *src, const gx_grid_desc *gs, cudaStream_t st) {
-  HostAxis<T> h[3];
+  DevTabs<T> *d = nullptr;
   if (gs->cell_size > gd->cell_size) {
-    if (build_interp<T>(*gd, *gs, h)) return 1;
-    return run_gather<T, 0>(dst, gd->n, src, gs->n, h, (T) 1, "interp_add", st);
+    if (cached_tabs<T>(0, *gd, *gs, [&](HostAxis<T> *h) { return build_interp<T>(*gd, *gs, h); }, st, &d)) return 1;
+    return run_gather<T, 0>(dst, gd->n, src, gs->n, *d, (T) 1, "interp_add", st);
   }
   if (gs->cell_size < gd->cell_size) {
-    if (build_subsample<T>(*gd, *gs, h)) return 1;
-    return run_gather<T, 1>(dst, gd->n, src, gs->n, h, (T) 1, "subsample_add", st);
+    if (cached_tabs<T>(1, *gd, *gs, [&](HostAxis<T> *h) { return build_subsample<T>(*gd, *gs, h); }, st, &d)) return 1;
+    return run_gather<T, 1>(dst, gd->n, src, gs->n, *d, (T) 1, "subsample_add", st);
   }
   return fail("gx_interp_add: source and destination have the same resolution");
 }
@@ -281,21 +321,30 @@ static int interp_add_t(void *dst, const gx_grid_desc *gd, const void *src, cons
 template <typename T>
 static int deinterp_add_t(void *dst, const gx_grid_desc *gc, const void *src, const gx_grid_desc *gf, double scale,
                           cudaStream_t st) {
-  HostAxis<T> h[3];
-  if (build_deinterp<T>(*gc, *gf, h)) return 1;
-  return run_gather<T, 0>(dst, gc->n, src, gf->n, h, (T) scale, "deinterp_add", st);
+  DevTabs<T> *d = nullptr;
+  if (cached_tabs<T>(2, *gc, *gf, [&](HostAxis<T> *h) { return build_deinterp<T>(*gc, *gf, h); }, st, &d)) return 1;
+  return run_gather<T, 0>(dst, gc->n, src, gf->n, *d, (T) scale, "deinterp_add", st);
 }
 
 // ---- windows -------------------------------------------------------------------------------------------------------
-template <typename T> __global__ void zero_window_kernel(T *f, int n, const unsigned char *in, int inside) {
-  // in[0..n) x, in[n..2n) y, in[2n..3n) z
+// Window<T>::contains on the cell centroids (window.hpp), per axis: [lo, hi) or its wrapped complement form. The centroid
+// is formed as on the host (coord * cellSize, + offsetLower, + cellSize / 2: three separately rounded operations).
+template <typename T> struct WindowGeo {
+  T dx, half_dx, lower[3], lo[3], hi[3];
+};
+
+template <typename T> __global__ void zero_window_kernel(T *f, int n, WindowGeo<T> w, int inside) {
+  auto in_axis = [&](int a, int c) {
+    const T x = add_rn(add_rn(mul_rn((T) c, w.dx), w.lower[a]), w.half_dx);
+    return (w.hi[a] >= w.lo[a]) ? (x < w.hi[a] && x >= w.lo[a]) : (x < w.hi[a] || x >= w.lo[a]);
+  };
   const long nrows = (long) n * n;
   for (long r = blockIdx.x; r < nrows; r += gridDim.x) {
     const int x = (int) (r / n), y = (int) (r - (long) x * n);
-    const unsigned char xy = in[x] & in[n + y];
+    const bool xy = in_axis(0, x) && in_axis(1, y);
     T *row = f + r * (n + 2);
     for (int z = threadIdx.x; z < n; z += blockDim.x) {
-      const int contained = xy & in[2 * n + z];
+      const int contained = (xy && in_axis(2, z)) ? 1 : 0;
       if (contained == inside) row[z] = (T) 0;
     }
   }
@@ -305,28 +354,21 @@ template <typename T>
 static int zero_window_t(void *field, const gx_grid_desc *g, const gx_grid_desc *win, int inside, cudaStream_t st) {
   // Grid::getWindow (grid.hpp:502-504) -> Window(L, lower, upper): wrapCorners, then contains() on cell centroids
   const int n = g->n;
-  std::vector<unsigned char> in(3 * (size_t) n);
+  WindowGeo<T> w;
+  w.dx = (T) g->cell_size; w.half_dx = (T) g->cell_size / 2;
   const T L = (T) win->domain_size;
   auto wrap = [L](T v) { if (v < 0) v += L; if (v >= L) v -= L; return v; };
   for (int a = 0; a < 3; ++a) {
+    w.lower[a] = (T) g->offset_lower[a];
     const T thisGridSize = (T) win->cell_size * (T) win->n;
-    T lo = wrap((T) win->offset_lower[a]);
-    T hi = (T) win->offset_lower[a] + thisGridSize;
-    hi = std::nextafter(wrap(std::nextafter(hi, -std::numeric_limits<T>::infinity())), std::numeric_limits<T>::infinity());
-    for (int c = 0; c < n; ++c) {
-      const T x = centroid<T>(*g, a, c);
-      in[(size_t) a * n + c] = (hi >= lo) ? (x < hi && x >= lo) : (x < hi || x >= lo);
-    }
+    w.lo[a] = wrap((T) win->offset_lower[a]);
+    const T hi = (T) win->offset_lower[a] + thisGridSize;
+    w.hi[a] = std::nextafter(wrap(std::nextafter(hi, -std::numeric_limits<T>::infinity())), std::numeric_limits<T>::infinity());
   }
-  unsigned char *d = nullptr;
-  GX_CUDA_CHECK(cudaMalloc(&d, in.size()));
-  GX_CUDA_CHECK(cudaMemcpy(d, in.data(), in.size(), cudaMemcpyHostToDevice));
   const long nrows = (long) n * n;
-  zero_window_kernel<T><<<(int) (nrows < 148 * 16 ? nrows : 148 * 16), 256, 0, st>>>((T *) field, n, d, inside ? 1 : 0);
+  zero_window_kernel<T><<<(int) (nrows < 148 * 16 ? nrows : 148 * 16), 256, 0, st>>>((T *) field, n, w, inside ? 1 : 0);
   count_launch();
   GX_LAUNCH_CHECK();
-  GX_CUDA_CHECK(cudaStreamSynchronize(st));
-  GX_CUDA_CHECK(cudaFree(d));
   return 0;
 }
 
@@ -384,15 +426,17 @@ template <typename T> __global__ void masked_shift_scale_kernel(T *f, const unsi
 template <typename T> static int masked_sum_t(const void *f, const unsigned char *mask, int n, double *host_out, cudaStream_t st) {
   const long nrows = (long) n * n;
   const int grid = (int) (nrows < 148 * 8 ? nrows : 148 * 8);
-  double *part = nullptr;
-  GX_CUDA_CHECK(cudaMalloc(&part, (grid + 1) * sizeof(double)));
+  static double *part = nullptr;  // 148 * 8 partials + the result; the call returns only after its result has been read
+  static int part_device = -1;
+  int dev = 0;
+  GX_CUDA_CHECK(cudaGetDevice(&dev));
+  if (part_device != dev) { GX_CUDA_CHECK(cudaMalloc(&part, (148 * 8 + 1) * sizeof(double))); part_device = dev; }
   masked_sum_kernel<T><<<grid, 256, 0, st>>>((const T *) f, mask, n, part);
-  partial_sum_kernel<<<1, 1024, 0, st>>>(part, grid, part + grid);
+  partial_sum_kernel<<<1, 1024, 0, st>>>(part, grid, part + 148 * 8);
   count_launch(2);
   GX_LAUNCH_CHECK();
-  GX_CUDA_CHECK(cudaMemcpyAsync(host_out, part + grid, sizeof(double), cudaMemcpyDeviceToHost, st));
+  GX_CUDA_CHECK(cudaMemcpyAsync(host_out, part + 148 * 8, sizeof(double), cudaMemcpyDeviceToHost, st));
   GX_CUDA_CHECK(cudaStreamSynchronize(st));
-  GX_CUDA_CHECK(cudaFree(part));
   return 0;
 }
 

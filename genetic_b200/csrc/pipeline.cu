@@ -9,6 +9,7 @@
 #include "gx_common.cuh"
 #include "zeldovich.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field,
                              void *stage, size_t stage_bytes, void *host_pos, void *host_vel,
@@ -19,10 +20,20 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
   cudaStream_t st = (cudaStream_t) stream;
   int rc;
   unsigned long long off = 0;
-  if ((rc = gx_noise_draw(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, stream))) return rc;
-  if (p->fix_power && (rc = gx_unit_variance(delta_field, n, dt, stream))) return rc;
-  // delta_k = sqrt(C(k)) * noise, left divided by k^2: the quotient all three displacement components start from
-  if ((rc = apply_transfer_ex(delta_field, n, dt, p->grid_length, spectrum, 0.5, 1, st))) return rc;
+  static int fuse_transfer = -1;
+  if (fuse_transfer < 0) { const char *e = getenv("GX_FUSE_TRANSFER"); fuse_transfer = (e && e[0] == '0') ? 0 : 1; }
+  if (fuse_transfer && !p->fix_power && p->noise_mode != GX_NOISE_REAL) {
+    // delta_k / k^2 = noise * sqrt(C(k)) / k^2 formed while the noise is delivered: the factor comes from the |k|^2 table
+    // (L2 resident), the product is the one Field::applyTransferFunction would form, and the transfer sweep (2 B) is gone
+    const void *table = nullptr;
+    if ((rc = build_transfer_table(n, dt, p->grid_length, spectrum, 0.5, 1, st, &table))) return rc;
+    if ((rc = noise_draw_scaled(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, st, table))) return rc;
+  } else {
+    if ((rc = gx_noise_draw(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, stream))) return rc;
+    if (p->fix_power && (rc = gx_unit_variance(delta_field, n, dt, stream))) return rc;
+    // delta_k = sqrt(C(k)) * noise, left divided by k^2: the quotient all three displacement components start from
+    if ((rc = apply_transfer_ex(delta_field, n, dt, p->grid_length, spectrum, 0.5, 1, st))) return rc;
+  }
 
   const size_t osz = odt == GX_F64 ? 8 : 4;
   const long long n3 = (long long) n * n * n, n2 = (long long) n * n;
@@ -44,9 +55,8 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
   }
   bool copy_pending[2] = {false, false};
   int buf = 0;
-  for (int axis = 0; axis < 3; ++axis) {
-    // x- and y-pass with the ik/k^2 operator and the Hermitian mirror fused into the first load
-    if ((rc = zeldovich_xy(delta_field, psi_field, n, dt, p->grid_length, axis, 1, st))) return rc;
+  // z-pass (c2r) of one component, slab of x-planes by slab, with the particle evaluation fused into its store
+  auto emit_component = [&](int axis, const void *field) -> int {
     EmitGeo eg;
     eg.cell_size = p->cell_size; eg.offset_lower = p->offset_lower[axis]; eg.domain_size = p->domain_size;
     eg.vel_ratio = p->vel_ratio;
@@ -55,9 +65,8 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
       char *half = (char *) stage + (size_t) buf * (stage_bytes / 2);
       void *dpos = half, *dvel = half + (size_t) slab * osz;
       if (to_host && copy_pending[buf]) GX_CUDA_CHECK(cudaStreamWaitEvent(st, ev_copy[buf], 0));
-      // z-pass (c2r) of this slab of x-planes with the particle evaluation fused into its store
-      if ((rc = zeldovich_z_emit(psi_field, n, dt, axis, eg, (long) (id0 / n), (long) (cnt / n), dpos, dvel, odt, st)))
-        return rc;
+      if (int rc2 = zeldovich_z_emit(field, n, dt, axis, eg, (long) (id0 / n), (long) (cnt / n), dpos, dvel, odt, st))
+        return rc2;
       if (to_host) {
         GX_CUDA_CHECK(cudaEventRecord(ev_emit[buf], st));
         GX_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_emit[buf], 0));
@@ -80,6 +89,28 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
         copy_pending[buf] = true;
       }
       buf ^= 1;
+    }
+    return 0;
+  };
+  static int shared = -1;
+  if (shared < 0) { const char *e = getenv("GX_ZELDOVICH_SHARED"); shared = (e && e[0] == '0') ? 0 : 1; }
+  if (shared) {
+    // 5 column passes instead of 6: i k_y and i k_z do not depend on kx, so psi_y and psi_z share one x-transform of
+    // G = delta_k / k^2. psi_x goes first (it needs G itself); then G <- x-pass(mirror(G)) in place; psi_y = y-pass(i k_y G)
+    // into the work field; psi_z = y-pass(G) in place with i k_z applied as it is stored. (The first attempt shared the
+    // y-transform instead and needed an out-of-place x-pass: 105 ms against 38 in place, profiles/r1s14_*.)
+    if ((rc = zeldovich_xy(delta_field, psi_field, n, dt, p->grid_length, 0, 1, st))) return rc;
+    if ((rc = emit_component(0, psi_field))) return rc;
+    if ((rc = zeldovich_shared_x(delta_field, n, dt, st))) return rc;
+    if ((rc = zeldovich_shared_y(delta_field, psi_field, n, dt, p->grid_length, 1, st))) return rc;
+    if ((rc = emit_component(1, psi_field))) return rc;
+    if ((rc = zeldovich_shared_y(delta_field, psi_field, n, dt, p->grid_length, 2, st))) return rc;
+    if ((rc = emit_component(2, delta_field))) return rc;
+  } else {
+    for (int axis = 0; axis < 3; ++axis) {
+      // x- and y-pass with the ik/k^2 operator and the Hermitian mirror fused into the first load
+      if ((rc = zeldovich_xy(delta_field, psi_field, n, dt, p->grid_length, axis, 1, st))) return rc;
+      if ((rc = emit_component(axis, psi_field))) return rc;
     }
   }
   if (to_host) {

@@ -85,6 +85,9 @@ template <typename T> struct Dest {
   // [n][ny][n/2+1] array; the real order keeps rows (x*n + y) in [row0, row0 + nrows). Whole field: 0, n / 0, n*n.
   int iy0, ny;
   long long row0, nrows;
+  // optional factor per mode, table[k1^2 + k2^2 + k3^2] (sqrt of the covariance [/ k^2]): Field::applyTransferFunction
+  // folded into the delivery -- the same rounded product per component as the separate sweep, one field sweep less
+  const T *wtab;
 };
 
 __device__ __forceinline__ ChunkFn compose(const ChunkFn &f, const ChunkFn &g) {  // f first, then g
@@ -198,6 +201,7 @@ struct ModeSlot {
   size_t slot, slot2;   // complex slot of the kz >= 0 representative; slot of -k on the kz = 0 plane
   bool write, write2;   // last-writer-wins and slab ownership already applied
   bool neg;             // the representative is the conjugate (k3 < 0)
+  int m;                // k1^2 + k2^2 + k3^2
 };
 
 template <typename T> __device__ __forceinline__ ModeSlot mode_slot(const Dest<T> &d, const Cursor &cu) {
@@ -222,6 +226,7 @@ template <typename T> __device__ __forceinline__ ModeSlot mode_slot(const Dest<T
   // setFourierCoefficient(k, val): stored at the kz >= 0 representative, imaginary part negated if conjugated;
   // the explicit second write, setFourierCoefficient(-k, conj(val)), lands on a different slot only when k3 == 0
   ModeSlot m;
+  m.m = k1 * k1 + k2 * k2 + k3 * k3;
   m.neg = k3 < 0;
   const int s1 = m.neg ? -k1 : k1, s2 = m.neg ? -k2 : k2, s3 = m.neg ? -k3 : k3;
   const int nc = n / 2 + 1;
@@ -246,7 +251,8 @@ __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, l
   }
   const ModeSlot m = mode_slot<T>(d, cu);
   // value of this component in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2))
-  const T v = (T) GX_DMUL(d.sigma, value);
+  T v = (T) GX_DMUL(d.sigma, value);
+  if (d.wtab) v = (T) GX_DMUL(v, __ldg(d.wtab + m.m));
   // normal order: (a, b) -> (re, im); reverse: (b, a)
   const int part = d.reverse ? (1 - cu.comp) : cu.comp;
   const T vconj = (part == 1) ? -v : v;
@@ -259,7 +265,8 @@ __device__ __forceinline__ void deliver_at(const Dest<T> &d, const Cursor &cu, l
 template <typename T>
 __device__ __forceinline__ void deliver_pair(const Dest<T> &d, const Cursor &cu, double first, double second) {
   const ModeSlot m = mode_slot<T>(d, cu);
-  const T a = (T) GX_DMUL(d.sigma, first), b = (T) GX_DMUL(d.sigma, second);
+  T a = (T) GX_DMUL(d.sigma, first), b = (T) GX_DMUL(d.sigma, second);
+  if (d.wtab) { const T w = __ldg(d.wtab + m.m); a = (T) GX_DMUL(a, w); b = (T) GX_DMUL(b, w); }
   const T re = d.reverse ? b : a, im = d.reverse ? a : b;
   cplx<T> *f = reinterpret_cast<cplx<T> *>(d.field);
   if (m.write) f[m.slot] = mk<T>(re, m.neg ? -im : im);
@@ -774,7 +781,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
 // caller runs the slab-decomposed r2c and zeroes Re(DC)).
 template <typename T>
 static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int reverse, unsigned long long *offset_io,
-                        cudaStream_t cs, int world = 1, int rank = 0, Phase phase = Phase()) {
+                        cudaStream_t cs, int world = 1, int rank = 0, Phase phase = Phase(), const void *wtab = nullptr) {
   const size_t bytes = (size_t) 2 * n * n * (n / 2 + 1) * sizeof(T) / (size_t) world;
   if (phase.which != 1) GX_CUDA_CHECK(cudaMemsetAsync(field, 0, bytes, cs));
   Dest<T> dest;
@@ -782,6 +789,8 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
   dest.ny = n / world; dest.iy0 = rank * dest.ny;
   dest.nrows = (long long) n * n / world; dest.row0 = rank * dest.nrows;
   dest.sigma = (double) (T) (1.0 / sqrt(2.0));
+  dest.wtab = (const T *) wtab;
+  if (wtab && mode == GX_NOISE_REAL) return fail("noise_draw_scaled: the real-space order has no per-mode factor");
   const long long n3 = (long long) n * n * n;
   const unsigned long long start = offset_io ? *offset_io : 0ull;
   std::vector<StreamReq> reqs;
@@ -814,6 +823,14 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
 }
 
 }  // namespace rng
+
+int noise_draw_scaled(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
+                      unsigned long long *stream_offset_io, cudaStream_t st, const void *table) {
+  if (!is_pow2(n) || n < 4 || n > 4096) return fail("grid size must be a power of two in [4,4096]");
+  if (dtype == GX_F64) return rng::noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table);
+  if (dtype == GX_F32) return rng::noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table);
+  return fail("bad dtype");
+}
 }  // namespace gx
 
 using namespace gx;
@@ -892,7 +909,7 @@ int gx_rng_gaussians(unsigned long seed, long n, double *host_out, unsigned long
   double *d = nullptr;
   GX_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * (size_t) n));
   Dest<double> dest;
-  dest.mode = MODE_LIST; dest.n = 0; dest.reverse = 0; dest.field = nullptr; dest.list = d; dest.sigma = 1.0;
+  dest.mode = MODE_LIST; dest.n = 0; dest.reverse = 0; dest.field = nullptr; dest.list = d; dest.sigma = 1.0; dest.wtab = nullptr;
   dest.iy0 = 0; dest.ny = 0; dest.row0 = 0; dest.nrows = 0;
   std::vector<StreamReq> reqs;
   reqs.push_back({seed, raw_consumed ? *raw_consumed : 0ull, (long long) n, 0});

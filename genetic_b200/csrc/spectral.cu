@@ -237,30 +237,37 @@ template <typename T> static int covariance_field_t(void *out, int n, double L, 
 static void *g_transfer_tab = nullptr;   // grow-only workspace for the |k|^2 table (values are rebuilt by every call)
 static size_t g_transfer_tab_bytes = 0;
 
+// table[m] = C(k)^power [/ k^2] for m = ix^2 + iy^2 + iz^2; rebuilt by every call, only the allocation is kept
+template <typename T>
+static int build_transfer_table_t(int n, double L, const gx_spectrum *s, double power, int divide_k2, cudaStream_t st) {
+  const long h = n / 2, mcount = 3 * h * h + 1;
+  if (g_transfer_tab_bytes < mcount * sizeof(T)) {
+    if (g_transfer_tab) { GX_CUDA_CHECK(cudaDeviceSynchronize()); GX_CUDA_CHECK(cudaFree(g_transfer_tab)); g_transfer_tab = nullptr; }
+    GX_CUDA_CHECK(cudaMalloc(&g_transfer_tab, mcount * sizeof(T)));
+    g_transfer_tab_bytes = mcount * sizeof(T);
+  }
+  TransferTableF<T> tf;
+  tf.sp = gx_spectrum_device_view(s);
+  tf.tab = (T *) g_transfer_tab; tf.mcount = mcount; tf.kmin = kmin_of<T>(L); tf.norm = (T) gx_spectrum_grid_norm(s, L, n);
+  tf.power = power; tf.divide_k2 = divide_k2;
+  {
+    GX_TIMED("transfer_table", st);
+    long blocks = (mcount + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    transfer_table_kernel<T><<<(unsigned) blocks, 256, 3 * tf.sp.m * sizeof(double), st>>>(tf);
+    count_launch();
+  }
+  GX_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T>
 static int apply_transfer_t(void *field, int n, double L, const gx_spectrum *s, double power, cudaStream_t st,
                             int divide_k2 = 0, int iy0 = 0, int ny = -1) {
   static int use_table = -1;
   if (use_table < 0) { const char *e = getenv("GX_TRANSFER_TABLE"); use_table = (e && e[0] == '0') ? 0 : 1; }
   if (use_table) {
-    const long h = n / 2, mcount = 3 * h * h + 1;
-    if (g_transfer_tab_bytes < mcount * sizeof(T)) {
-      if (g_transfer_tab) { GX_CUDA_CHECK(cudaDeviceSynchronize()); GX_CUDA_CHECK(cudaFree(g_transfer_tab)); g_transfer_tab = nullptr; }
-      GX_CUDA_CHECK(cudaMalloc(&g_transfer_tab, mcount * sizeof(T)));
-      g_transfer_tab_bytes = mcount * sizeof(T);
-    }
-    TransferTableF<T> tf;
-    tf.sp = gx_spectrum_device_view(s);
-    tf.tab = (T *) g_transfer_tab; tf.mcount = mcount; tf.kmin = kmin_of<T>(L); tf.norm = (T) gx_spectrum_grid_norm(s, L, n);
-    tf.power = power; tf.divide_k2 = divide_k2;
-    {
-      GX_TIMED("transfer_table", st);
-      long blocks = (mcount + 255) / 256;
-      if (blocks > 148 * 16) blocks = 148 * 16;
-      transfer_table_kernel<T><<<(unsigned) blocks, 256, 3 * tf.sp.m * sizeof(double), st>>>(tf);
-      count_launch();
-    }
-    GX_LAUNCH_CHECK();
+    if (int rc = build_transfer_table_t<T>(n, L, s, power, divide_k2, st)) return rc;
     ApplyTableF<T> f;
     f.f = (cplx<T> *) field; f.tab = (const T *) g_transfer_tab; f.n = n;
     return launch_slot_sweep(n, f, st, 0, "apply_transfer", iy0, ny);
@@ -301,6 +308,17 @@ static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, in
 }
 
 namespace gx {
+// the |k|^2 table alone, for consumers that multiply while they write (the noise delivery in gx_unigrid_ic)
+int build_transfer_table(int n, int dtype, double L, const gx_spectrum *s, double power, int divide_k2, cudaStream_t st,
+                         const void **table) {
+  if (check_n(n)) return 1;
+  int rc;
+  if (dtype == GX_F64) rc = build_transfer_table_t<double>(n, L, s, power, divide_k2, st);
+  else if (dtype == GX_F32) rc = build_transfer_table_t<float>(n, L, s, power, divide_k2, st);
+  else return fail("bad dtype");
+  *table = g_transfer_tab;
+  return rc;
+}
 int apply_transfer_ex(void *field, int n, int dtype, double L, const gx_spectrum *s, double power, int divide_k2,
                       cudaStream_t st, int iy0, int ny) {
   if (check_n(n)) return 1;

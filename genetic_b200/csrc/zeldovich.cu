@@ -55,6 +55,31 @@ template <typename T, bool PREDIV> struct OpZeldovichMirror {
   }
 };
 
+// ---- pieces of the shared-transform schedule (pipeline.cu): the x-transform of G = delta_k / k^2 is computed once, in
+// place, and serves both psi_y (i k_y does not depend on kx: applied on the load side of its y-pass) and psi_z (i k_z on
+// the store side of its y-pass), so an IC takes 5 column passes instead of 6 -- and every one of them is of the cheap kind
+// (x-passes in place, the out-of-place ones along y). The Hermitian mirror commutes with the diagonal operators on the
+// dependent slots (mirror(i k G) = i k mirror(G)), and the imaginary parts it leaves on self-conjugate entries are dropped
+// by the c2r pass either way, so G's two planes are mirrored once, explicitly, before the shared x-pass.
+template <typename T> struct OpIKy {  // load side of a y-pass: (value, ix, iy, iz)
+  int n;
+  T kmin;
+  __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int iy, int) const {
+    if (iy == (n >> 1)) return mk<T>(0, 0);  // zeldovich.hpp:170-176: zero on the Nyquist plane of the component's axis
+    const T ka = mul_rn((T) signed_mode(iy, n), kmin);
+    return mk<T>(mul_rn(-v.y, ka), mul_rn(v.x, ka));
+  }
+};
+template <typename T> struct OpIKz {  // store side of a y-pass
+  int n;
+  T kmin;
+  __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int, int iz) const {
+    if (iz == (n >> 1)) return mk<T>(0, 0);
+    const T ka = mul_rn((T) iz, kmin);
+    return mk<T>(mul_rn(-v.y, ka), mul_rn(v.x, ka));
+  }
+};
+
 template <typename O> struct Pair;
 template <> struct Pair<float> { using type = float2; };
 template <> struct Pair<double> { using type = double2; };
@@ -131,6 +156,31 @@ static int z_emit_n(const void *work, int axis, const EmitGeo &g, long row0, lon
   return fft::launch_rows_c2r<T, N>((const T *) work, row0, nrows, s, st);
 }
 
+// G <- x-pass(G) in place (after the explicit mirror); then, from the x-transformed G:
+//   axis 1: W <- y-pass(i k_y G) out of place;  axis 2: G <- y-pass(G) in place, times i k_z as it is stored
+template <typename T, int N> static int shared_x_n(void *g, cudaStream_t st) {
+  using namespace fft;
+  using C = cplx<T>;
+  return launch_cols<T, N, 1, PassX>((const C *) g, (C *) g, N, N, N / 2 + 1, OpIdentity<T>(), OpIdentity<T>(), st);
+}
+template <typename T, int N> static int shared_y_n(void *g, void *w, double L, int axis, cudaStream_t st) {
+  using namespace fft;
+  using C = cplx<T>;
+  const T kmin = (T) (2. * M_PI / (double) (T) L);
+  if (axis == 1) {
+    OpIKy<T> op;
+    op.n = N; op.kmin = kmin;
+    return launch_cols<T, N, 1, PassY>((const C *) g, (C *) w, N, N, N / 2 + 1, op, OpIdentity<T>(), st);
+  }
+  OpIKz<T> op;
+  op.n = N; op.kmin = kmin;
+  return launch_cols<T, N, 1, PassY>((const C *) g, (C *) g, N, N, N / 2 + 1, OpIdentity<T>(), op, st);
+}
+template <typename T> static int shared_x_t(void *g, int n, cudaStream_t st) { GX_N_SWITCH(n, (shared_x_n<T, N>(g, st))); }
+template <typename T> static int shared_y_t(void *g, void *w, int n, double L, int axis, cudaStream_t st) {
+  GX_N_SWITCH(n, (shared_y_n<T, N>(g, w, L, axis, st)));
+}
+
 template <typename T, bool PREDIV>
 static int zeldovich_xy_t(const void *d, void *w, int n, double L, int axis, int order, cudaStream_t st) {
   GX_N_SWITCH(n, (zeldovich_xy_n<T, N, PREDIV>(d, w, L, axis, order, st)));
@@ -175,6 +225,23 @@ int zeldovich_z_emit(const void *work, int n, int dtype, int axis, const EmitGeo
   if (dtype == GX_F64 && out_dtype == GX_F64) return z_emit_t<double, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
   if (dtype == GX_F32 && out_dtype == GX_F32) return z_emit_t<float, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
   if (dtype == GX_F32 && out_dtype == GX_F64) return z_emit_t<float, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  return fail("bad dtype");
+}
+
+int zeldovich_shared_x(void *g, int n, int dtype, cudaStream_t st) {
+  if (int rc = fft::ensure_twiddles()) return rc;
+  int rc = gx_mirror(g, n, dtype, st);  // ensureFourierModesAreMirrored on G's kz = 0 and Nyquist planes, in place
+  if (rc) return rc;
+  if (dtype == GX_F64) return shared_x_t<double>(g, n, st);
+  if (dtype == GX_F32) return shared_x_t<float>(g, n, st);
+  return fail("bad dtype");
+}
+
+int zeldovich_shared_y(void *g, void *work, int n, int dtype, double grid_length, int axis, cudaStream_t st) {
+  if (axis != 1 && axis != 2) return fail("zeldovich_shared_y: axis must be 1 or 2");
+  if (g == work) return fail("zeldovich: the work field must not alias delta_k");
+  if (dtype == GX_F64) return shared_y_t<double>(g, work, n, grid_length, axis, st);
+  if (dtype == GX_F32) return shared_y_t<float>(g, work, n, grid_length, axis, st);
   return fail("bad dtype");
 }
 

@@ -18,6 +18,11 @@ int zeldovich_xy(const void *delta_k, void *work, int n, int dtype, double grid_
 // the division by k^2 that every Zeldovich component needs
 int apply_transfer_ex(void *field, int n, int dtype, double grid_length, const gx_spectrum *s, double power,
                       int divide_k2, cudaStream_t st, int iy0 = 0, int ny = -1);
+int build_transfer_table(int n, int dtype, double grid_length, const gx_spectrum *s, double power, int divide_k2,
+                         cudaStream_t st, const void **table);
+// gx_noise_draw with every mode multiplied by table[kx^2 + ky^2 + kz^2] as it is written (Fourier orders only)
+int noise_draw_scaled(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
+                      unsigned long long *stream_offset_io, cudaStream_t st, const void *table);
 int unit_variance_slab(void *field, int n, int dtype, int iy0, int ny, cudaStream_t st);
 // last pass: c2r along z of rows [row0, row0+nrows) of `work`, scaled by n^-1.5, written back in place (real space)
 int zeldovich_z_real(void *work, int n, int dtype, long row0, long nrows, cudaStream_t st);
@@ -25,5 +30,9 @@ int zeldovich_z_real(void *work, int n, int dtype, long row0, long nrows, cudaSt
 // (element i = id - id0, unit stride; either pointer may be NULL)
 int zeldovich_z_emit(const void *work, int n, int dtype, int axis, const EmitGeo &geo, long row0, long nrows,
                      void *out_pos, void *out_vel, int out_dtype, cudaStream_t st);
+// shared-transform schedule, G = delta_k / k^2: G <- x-pass(mirror(G)) in place, then for axis 1 work <- y-pass(i k_y G)
+// (out of place) and for axis 2 G <- i k_z y-pass(G) (in place): both ready for the z-pass
+int zeldovich_shared_x(void *g, int n, int dtype, cudaStream_t st);
+int zeldovich_shared_y(void *g, void *work, int n, int dtype, double grid_length, int axis, cudaStream_t st);
 
 }  // namespace gx

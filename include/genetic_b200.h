@@ -202,9 +202,10 @@ typedef struct {
    two halves, each holding pos+vel of a whole number of x-planes of one component.
    host_pos/host_vel (may be NULL: results stay in the staging buffer, nothing is copied): component-major arrays
    out[axis][id] of out_dtype; if host_capacity_particles < n^3 they are used as a ring of 3*capacity elements.
-   Synchronous with respect to the device->host copies; kernels run on `stream`. On return delta_field holds
-   delta_k / k^2 (the common factor of the three displacement components, formed once); psi_field is scratch (the half-transformed z component: the last FFT pass writes particles, not the
-   real-space field). */
+   Synchronous with respect to the device->host copies; kernels run on `stream`. Both fields are scratch on return: the
+   schedule forms delta_k / k^2 once (the factor sqrt(C(k)) / k^2 is applied while the noise is written), emits psi_y, then
+   shares one x-transform of delta_k / k^2 between psi_y and psi_z (5 column passes per IC instead of 6) and lets the last
+   FFT pass write particles instead of real-space fields. */
 int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum, void *delta_field, void *psi_field, void *stage,
                   size_t stage_bytes, void *host_pos, void *host_vel, size_t host_capacity_particles, void *stream);
 

@@ -13,6 +13,7 @@
 //   gx::cosmology::CAMB<T>                    cosmology/camb.hpp:173-332
 //   gx::fields::RandomFieldGenerator<T>       simulation/field/randomfieldgenerator.hpp:25-263
 //   gx::particle::ZeldovichParticleGenerator<T>  simulation/particles/zeldovich.hpp:132-304
+//   gx::multilevelgrid::MultiLevelGrid<T>, gx::filters::FilterFamily<T>, gx::fields::MultiLevelField<T>   (zoom levels, metric, chi^2)
 //   gx::ic::ICGenerator<T>                    ic.hpp (the unigrid command surface: cosmology, camb, seeds, basegrid, done)
 //   gx::io::tipsy::save                       io/tipsy.hpp:207-271 (dark-matter-only unigrid)
 #pragma once
@@ -330,6 +331,146 @@ private:
   std::vector<std::shared_ptr<Field<T>>> levels;
   unsigned long baseSeed;
   bool drawInFourierSpace = false, parallel = false, reverseRandomDrawOrder = false, seeded = false;
+};
+}  // namespace fields
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Zoom levels: the multi-level context, the filter family that splits the information between levels and the
+// multi-level field with its covector metric (simulation/multilevelgrid/multilevelgrid.hpp:30-330,
+// simulation/filters/filterfamily.hpp:86-143, simulation/field/multilevelfield.hpp:18-606). Pure sequencing over the
+// single-level Field operations above; the modifications and the splice (genetic_b200/multilevel.py) build on the same calls.
+namespace multilevelgrid {
+template <typename T> class MultiLevelGrid {
+public:
+  void addLevel(std::shared_ptr<grids::Grid<T>> g) {  // multilevelgrid.hpp:112-137
+    weights.push_back(pGrids.empty() ? T(1) : T(std::pow((double) (g->cellSize / pGrids[0]->cellSize), 3.0)));
+    pGrids.push_back(g);
+  }
+  void addLevel(T size, size_t nside, T x0 = 0, T y0 = 0, T z0 = 0) {  // :97-110
+    if (pGrids.empty()) simSize = size;
+    addLevel(std::make_shared<grids::Grid<T>>(simSize, nside, size / nside, x0, y0, z0));
+  }
+  size_t getNumLevels() const { return pGrids.size(); }
+  grids::Grid<T> &getGridForLevel(size_t level) { return *pGrids[level]; }
+  const grids::Grid<T> &getGridForLevel(size_t level) const { return *pGrids[level]; }
+  T getWeightForLevel(size_t level) const { return weights[level]; }
+  size_t getNumDof() const {  // :160-172
+    size_t dof = 0;
+    for (size_t i = 0; i < pGrids.size(); ++i) {
+      dof += pGrids[i]->size3;
+      if (i > 0) {
+        size_t f = (size_t) std::llround((double) (pGrids[i - 1]->cellSize / pGrids[i]->cellSize));
+        dof -= pGrids[i]->size3 / (f * f * f);
+      }
+    }
+    return dof;
+  }
+private:
+  std::vector<std::shared_ptr<grids::Grid<T>>> pGrids;
+  std::vector<T> weights;
+  T simSize = 0;
+};
+}  // namespace multilevelgrid
+
+namespace filters {
+template <typename T> class FilterFamily {  // filterfamily.hpp:86-143, levels not yet combined; FRACTIONAL_K_SPLIT = 0.3
+public:
+  explicit FilterFamily(const multilevelgrid::MultiLevelGrid<T> &ctx) {
+    fs.emplace_back(); lp.emplace_back(); hp.emplace_back();
+    for (size_t level = 0; level + 1 < ctx.getNumLevels(); ++level) {
+      const auto &g = ctx.getGridForLevel(level);
+      const T k_cut = T(0.3) * (T(g.size) * g.getFourierKmin());
+      Filter<T> filt = fs.back();
+      fs.pop_back(); lp.pop_back();
+      fs.push_back(filt * LowPassFermiFilter<T>(k_cut));
+      lp.push_back(LowPassFermiFilter<T>(k_cut));
+      fs.push_back(filt * ComplementaryCovarianceFilterAdaptor<T>(k_cut));
+      hp.push_back(ComplementaryCovarianceFilterAdaptor<T>(k_cut));
+      lp.emplace_back();
+    }
+  }
+  const Filter<T> &getFilterForLevel(size_t l) const { return fs[l]; }
+  const Filter<T> &getHighPassFilterForLevel(size_t l) const { return hp[l]; }
+  const Filter<T> &getLowPassFilterForLevel(size_t l) const { return lp[l]; }
+private:
+  std::vector<Filter<T>> fs, lp, hp;
+};
+}  // namespace filters
+
+namespace fields {
+template <typename T> class MultiLevelField {
+public:
+  using Context = multilevelgrid::MultiLevelGrid<T>;
+  explicit MultiLevelField(Context &ctx, bool covector = false) : context(&ctx), isCovector(covector) {
+    for (size_t l = 0; l < ctx.getNumLevels(); ++l) fieldsOnLevels.push_back(std::make_shared<Field<T>>(ctx.getGridForLevel(l), true));
+  }
+  MultiLevelField(const MultiLevelField<T> &o) : context(o.context), isCovector(o.isCovector) {  // deep copy
+    for (auto &f : o.fieldsOnLevels) fieldsOnLevels.push_back(f->copy());
+  }
+  size_t getNumLevels() const { return fieldsOnLevels.size(); }
+  Field<T> &getFieldForLevel(size_t l) { return *fieldsOnLevels[l]; }
+  const Field<T> &getFieldForLevel(size_t l) const { return *fieldsOnLevels[l]; }
+  std::vector<std::shared_ptr<Field<T>>> &getFields() { return fieldsOnLevels; }
+  filters::FilterFamily<T> getFilters() const { return filters::FilterFamily<T>(*context); }
+  void toFourier() { for (auto &f : fieldsOnLevels) f->toFourier(); }
+  void toReal() { for (auto &f : fieldsOnLevels) f->toReal(); }
+  void applyFilters(const filters::FilterFamily<T> &fam) {
+    for (size_t l = 0; l < getNumLevels(); ++l) fieldsOnLevels[l]->applyFilter(fam.getFilterForLevel(l));
+  }
+  void addScaled(const MultiLevelField<T> &other, T scale) {  // multilevelfield.hpp:194-212
+    toFourier();
+    for (size_t l = 0; l < getNumLevels(); ++l) fieldsOnLevels[l]->addScaledFourier(other.getFieldForLevel(l), scale);
+  }
+  void operator/=(T ratio) { for (auto &f : fieldsOnLevels) *f /= ratio; }
+  void convertToCovector() { if (isCovector) throw std::runtime_error("already a covector"); applyMetric(true); isCovector = true; }
+  void convertToVector() { if (!isCovector) throw std::runtime_error("already a vector"); applyMetric(false); isCovector = false; }
+  T innerProduct(const MultiLevelField<T> &other) const {  // :248-294
+    if (!isCovector) throw std::runtime_error("The inner product can only be taken if one of the fields is a covector");
+    if (other.isCovector) {
+      MultiLevelField<T> v(other);
+      v.convertToVector();
+      v.toFourier();
+      return innerProduct(v);
+    }
+    T result = 0;
+    for (size_t l = 0; l < getNumLevels(); ++l) result += fieldsOnLevels[l]->innerProduct(other.getFieldForLevel(l));
+    return result;
+  }
+  T getChi2() {  // :461-487 (the field is white noise)
+    toFourier();
+    MultiLevelField<T> c(*this);
+    c.convertToCovector();
+    return c.innerProduct(*this);
+  }
+private:
+  Context *context;
+  std::vector<std::shared_ptr<Field<T>>> fieldsOnLevels;
+  bool isCovector;
+  void applyMetric(bool toCovector) {  // :346-391
+    auto fam = getFilters();
+    toFourier();
+    const size_t nl = getNumLevels();
+    std::vector<std::shared_ptr<Field<T>>> fresh;
+    for (size_t level = 0; level < nl; ++level) {
+      auto result = fieldsOnLevels[level]->copy();
+      const auto &f = fam.getFilterForLevel(level);
+      if (toCovector && level + 1 < nl) {
+        const auto &window = context->getGridForLevel(level + 1);
+        result->applyFilterInWindow(f, window, true);
+        result->applyFilterInWindow(f, window, false);
+      } else {
+        result->applyFilter(f * f);
+      }
+      for (size_t src = 0; src < nl; ++src) {
+        if (src == level) continue;
+        const T ratio = context->getWeightForLevel(level) / context->getWeightForLevel(src);
+        result->addFieldFromDifferentGridWithFilter(*fieldsOnLevels[src], fam.getFilterForLevel(level) * fam.getFilterForLevel(src) * T(std::sqrt((double) ratio)));
+      }
+      result->toFourier();
+      fresh.push_back(result);
+    }
+    fieldsOnLevels = fresh;
+  }
 };
 }  // namespace fields
 

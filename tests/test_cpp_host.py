@@ -62,3 +62,27 @@ def test_unknown_command_is_an_error(tmp_path):
     p.write_text("Om 0.3\nzoomgrid 2 64\n")
     r = subprocess.run([exe, str(p)], capture_output=True, text=True)
     assert r.returncode == 1 and "Unknown command zoomgrid" in r.stderr
+
+
+@pytest.mark.gpu
+def test_chi2_goldens_through_the_cpp_multilevel_classes(tmp_path, golden_dir):
+    """test_02k (one level) and test_02m (zoom x2) chi^2 through gx::fields::MultiLevelField (C++): the windowed covector
+    metric, tricubic / sub-cell transfers and the weighted mode sums; the zoom window comes from genetic_b200/zoom.py."""
+    import re
+    import genetic_b200 as gb
+    from genetic_b200 import multilevel as GM, zoom as Z
+    exe = gbuild.build_host(program="genetic_b200_chi2")
+    ctx = GM.MultiLevelGrid()
+    ctx.addLevel(gb.Grid(64.0, 64))
+    for test, zoom in (("test_02k_chisquare_onelevel", False), ("test_02m_chisquare_twolevels", True)):
+        if zoom:
+            Z.selectCube(ctx, (25, 32, 24), 16)
+            Z.initZoomGrid(ctx, 2, 64)
+        lv = tmp_path / (test + ".txt")
+        lv.write_text("".join("%r %d %r %r %r %r\n" % (float(g.periodicDomainSize), g.size, float(g.cellSize),
+                                                      *(float(v) for v in g.offsetLower)) for g in ctx.grids))
+        r = subprocess.run([exe, str(lv), "13842314"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        ref = open(os.path.join(golden_dir, test, "reference.txt")).read()
+        want = re.search(r"Calculated chi\^2 = [0-9.]+ \(dof = \d+\)", ref).group(0)
+        assert want in r.stdout, (want, r.stdout)

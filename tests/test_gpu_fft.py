@@ -56,6 +56,25 @@ def test_inverse_of_unmirrored_spectrum(dtype):
     assert _rel(f2.getDataVector(), M.to_real(F.astype(np.complex128))) < _tol(dtype)
 
 
+@pytest.mark.parametrize("n", [128, 512])
+def test_fft_cross_check_against_cufft(n):
+    """In-run cross-check of the hand-written passes against cuFFT (through torch.fft on the same device): the north star
+    allows cuFFT for exactly this. Forward r2c and inverse c2r, f64, unitary scaling n^1.5 (fourier.hpp:490,512-513)."""
+    import torch
+    rng = np.random.default_rng(n + 1)
+    x = rng.standard_normal((n, n, n))
+    g = gb.Grid(100.0, n)
+    f = gb.Field(g, x, fourier=False)
+    f.toFourier()
+    F = f.getDataVector()
+    xt = torch.from_numpy(x).cuda()
+    Ft = (torch.fft.rfftn(xt) / float(n) ** 1.5).cpu().numpy()
+    assert _rel(F, Ft) < 1e-13
+    f.toReal()
+    yt = (torch.fft.irfftn(torch.from_numpy(Ft).cuda(), s=(n, n, n)) * float(n) ** 1.5).cpu().numpy()
+    assert _rel(f.getDataVector(), yt) < 1e-13
+
+
 @pytest.mark.parametrize("n", [512])
 def test_fft_roundtrip_large(n):
     rng = np.random.default_rng(1)
