@@ -264,6 +264,16 @@ static TabKey make_key(int kind, int dtype, const gx_grid_desc &a, const gx_grid
   return k;
 }
 
+void release_multigrid_workspace() {
+  if (g_tab_cache.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto &e : g_tab_cache) {
+    cudaFree(((DevTabs<double> *) e.tabs)->blob);  // blob is the first member for either element type
+    if (e.key.dtype == GX_F64) delete (DevTabs<double> *) e.tabs; else delete (DevTabs<float> *) e.tabs;
+  }
+  g_tab_cache.clear();
+}
+
 // kind 0: interpolate (coarse -> fine), 1: sub-cell mean (fine -> coarse), 2: deinterpolate. Builds on a miss.
 template <typename T, class Build>
 static int cached_tabs(int kind, const gx_grid_desc &a, const gx_grid_desc &b, Build build, cudaStream_t st, DevTabs<T> **out) {
@@ -278,8 +288,8 @@ static int cached_tabs(int kind, const gx_grid_desc &a, const gx_grid_desc &b, B
     GX_CUDA_CHECK(cudaDeviceSynchronize());  // a kernel may still be reading the oldest entry
     TabEntry old = g_tab_cache.front();
     g_tab_cache.erase(g_tab_cache.begin());
-    cudaFree(((DevTabs<T> *) old.tabs)->blob);  // blob is the first member for either T
-    delete (DevTabs<T> *) old.tabs;
+    cudaFree(((DevTabs<double> *) old.tabs)->blob);  // blob is the first member for either element type
+    if (old.key.dtype == GX_F64) delete (DevTabs<double> *) old.tabs; else delete (DevTabs<float> *) old.tabs;
   }
   g_tab_cache.push_back(TabEntry{key, d});
   *out = d;

@@ -27,9 +27,12 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 
 namespace gx {
+void release_spectral_workspace();   // spectral.cu: the |k|^2 table
+void release_multigrid_workspace();  // multigrid.cu: cached cross-grid tables
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
 namespace fft { template <typename T> int fft3d(T *data, int n, int dir, cudaStream_t st); }
 
@@ -306,8 +309,8 @@ __device__ __forceinline__ State chunk_start_state(const StreamDesc &sd, int q, 
   return big_to_state(X);
 }
 
-template <int PASS, typename T>
-__global__ void __launch_bounds__(kThreads) rng_chunk_kernel(ChunkParams P, Dest<T> dest) {
+template <int PASS, typename T, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) rng_chunk_kernel(ChunkParams P, Dest<T> dest) {
   __shared__ unsigned int s_k[128];
   __shared__ double s_w[128], s_y[128];
   __shared__ uint32_t ring[64][kThreads];  // raw output p of the chunk lives in slot p & 63 (the parse looks back < 28 outputs)
@@ -466,6 +469,17 @@ __global__ void need_kernel(const StreamDesc *streams, int n_streams, int n_chun
   need = need || (plus && (owned(pa, pb) || owned(ks, ks))) || (minus && (owned(-pb, -pa) || owned(-ks, -ks))) ||
          owned(qa, qb);
   if (need) list[atomicAdd(count, 1u)] = chunk;
+}
+
+// residency of the chunk kernels: 4 CTAs per SM at 128 registers; GX_RNG_MINB=5|6 caps the registers for more warps
+// (development switch for the A/B in profiles/)
+template <int PASS, typename T>
+static void launch_chunk_kernel(int grid, cudaStream_t cs, const ChunkParams &P, const Dest<T> &dest) {
+  static int minb = -1;
+  if (minb < 0) { const char *e = getenv("GX_RNG_MINB"); minb = e ? atoi(e) : 4; }
+  if (minb == 5) rng_chunk_kernel<PASS, T, 5><<<grid, kThreads, 0, cs>>>(P, dest);
+  else if (minb == 6) rng_chunk_kernel<PASS, T, 6><<<grid, kThreads, 0, cs>>>(P, dest);
+  else rng_chunk_kernel<PASS, T, 4><<<grid, kThreads, 0, cs>>>(P, dest);
 }
 
 // ---- scan over chunk functions -----------------------------------------------------------------------------------
@@ -671,7 +685,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     P.fn_out = (ChunkFn *) phase.fn_io;
     if (P.count > 0) {
       GX_TIMED("rng_pass_a", cs);
-      rng_chunk_kernel<0, T><<<(P.count + kThreads - 1) / kThreads, kThreads, 0, cs>>>(P, dest);
+      launch_chunk_kernel<0, T>((P.count + kThreads - 1) / kThreads, cs, P, dest);
       count_launch();
     }
     GX_LAUNCH_CHECK();
@@ -681,7 +695,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     GX_CUDA_CHECK(cudaMemcpyAsync(d_fn[0], phase.fn_io, sizeof(ChunkFn) * (size_t) n0, cudaMemcpyDeviceToDevice, cs));
   } else {
     GX_TIMED("rng_pass_a", cs);
-    rng_chunk_kernel<0, T><<<grid, kThreads, 0, cs>>>(P, dest);
+    launch_chunk_kernel<0, T>(grid, cs, P, dest);
     count_launch();
   }
   GX_LAUNCH_CHECK();
@@ -719,7 +733,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   }
   if (grid_b > 0) {
     GX_TIMED("rng_pass_b", cs);
-    rng_chunk_kernel<1, T><<<grid_b, kThreads, 0, cs>>>(P, dest);
+    launch_chunk_kernel<1, T>(grid_b, cs, P, dest);
   }
   count_launch();
   GX_LAUNCH_CHECK();
@@ -884,6 +898,8 @@ int gx_slab_noise_finish(void *slab, const void *fn_all, int n, int dtype, int w
 
 int gx_workspace_release(void) {
   gx::rng::ws_release();
+  gx::release_spectral_workspace();
+  gx::release_multigrid_workspace();
   return 0;
 }
 

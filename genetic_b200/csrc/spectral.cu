@@ -308,6 +308,10 @@ static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, in
 }
 
 namespace gx {
+void release_spectral_workspace() {
+  if (g_transfer_tab) { cudaDeviceSynchronize(); cudaFree(g_transfer_tab); }
+  g_transfer_tab = nullptr; g_transfer_tab_bytes = 0;
+}
 // the |k|^2 table alone, for consumers that multiply while they write (the noise delivery in gx_unigrid_ic)
 int build_transfer_table(int n, int dtype, double L, const gx_spectrum *s, double power, int divide_k2, cudaStream_t st,
                          const void **table) {

@@ -48,7 +48,7 @@ int gx_version(void);
 int gx_device_count(int *count);
 int gx_set_device(int device);           /* fourier::initialise() analogue, fourier.hpp:36-81 */
 int gx_synchronize(void *stream);
-int gx_workspace_release(void);          /* frees the grow-only scratch buffers the noise generator keeps between calls */
+int gx_workspace_release(void);          /* frees the grow-only scratch the library keeps between calls (noise workspace, |k|^2 table, cross-grid tables) */
 unsigned long long gx_launch_count(void); /* kernels launched by this library so far (bench bookkeeping) */
 
 /* ---- memory ----------------------------------------------------------------------------------- */
