@@ -471,15 +471,16 @@ __global__ void need_kernel(const StreamDesc *streams, int n_streams, int n_chun
   if (need) list[atomicAdd(count, 1u)] = chunk;
 }
 
-// residency of the chunk kernels: 4 CTAs per SM at 128 registers; GX_RNG_MINB=5|6 caps the registers for more warps
-// (development switch for the A/B in profiles/)
+// residency of the chunk kernels: 5 CTAs per SM (96 registers) by default -- measured at 2048^3: 4 CTAs (128 registers)
+// 99 + 180 ms, 5 CTAs 96 + 168 ms, 6 CTAs (80 registers, more spills) 100 + 196 ms (profiles/r1s17_*). GX_RNG_MINB=4|6
+// selects the others.
 template <int PASS, typename T>
 static void launch_chunk_kernel(int grid, cudaStream_t cs, const ChunkParams &P, const Dest<T> &dest) {
   static int minb = -1;
-  if (minb < 0) { const char *e = getenv("GX_RNG_MINB"); minb = e ? atoi(e) : 4; }
-  if (minb == 5) rng_chunk_kernel<PASS, T, 5><<<grid, kThreads, 0, cs>>>(P, dest);
+  if (minb < 0) { const char *e = getenv("GX_RNG_MINB"); minb = e ? atoi(e) : 5; }
+  if (minb == 4) rng_chunk_kernel<PASS, T, 4><<<grid, kThreads, 0, cs>>>(P, dest);
   else if (minb == 6) rng_chunk_kernel<PASS, T, 6><<<grid, kThreads, 0, cs>>>(P, dest);
-  else rng_chunk_kernel<PASS, T, 4><<<grid, kThreads, 0, cs>>>(P, dest);
+  else rng_chunk_kernel<PASS, T, 5><<<grid, kThreads, 0, cs>>>(P, dest);
 }
 
 // ---- scan over chunk functions -----------------------------------------------------------------------------------
