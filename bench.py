@@ -11,8 +11,9 @@ One "step" = the whole hot path for one IC: draw white noise from the seed (GSL-
           copied to pinned host memory inside the timed region
   roofline     : the dominant kernel's algorithmic GB/s (2*B per FFT pass) against MEASURED_PEAKS.json
   cpu_baseline : the CPU oracle port (oracle/) timed on this box's host cores on a bounded sample
-`--impl reference` times the CPU port alone (the reference cannot be compiled in this image: FFTW3, GSL and HDF5 are
-absent) with the same metric/config keys.
+`--impl reference` times the reference's own CPU implementation: oracle/_ref/genetIC, the unmodified reference sources
+compiled against stand-in FFTW3/GSL/HDF5 headers (oracle/build_ref.sh), or the numpy/C oracle port if that
+binary was not built, with the same metric/config keys.
 """
 import argparse
 import ctypes as C
@@ -116,25 +117,58 @@ def cpu_port_step(n, threads):
     return time.perf_counter() - t0
 
 
+def reference_binary_step(n, workdir=None):
+    """One IC of the same workload through the reference ITSELF (oracle/_ref/genetIC: the unmodified sources compiled
+    against the stand-in FFTW3/GSL/HDF5 headers of oracle/shims/): whole-process wall clock, including the tipsy file it
+    has to write (the reference has no output-less mode). Returns (seconds, threads) or None if the binary is absent."""
+    import shutil
+    import tempfile
+    import oracle
+    if oracle.ref_binary() is None:
+        return None
+    d = tempfile.mkdtemp(prefix="gx_ref_", dir=workdir)
+    try:
+        pf = ("Om %(Om)r\nOl %(Ol)r\ns8 %(s8)r\nns %(ns)r\nhubble %(hubble)r\nz %(z)r\n" % COSMO +
+              "camb %s\nrandom_seed %d\noutname bench\noutdir ./\noutformat tipsy\nbase_grid %r %d\ndone\n"
+              % (os.path.basename(CAMB_FILE), SEED, box_for(n), n))
+        t0 = time.perf_counter()
+        oracle.run_ref(pf, d, [CAMB_FILE])
+        return time.perf_counter() - t0, os.cpu_count() or 1
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+REF_SAMPLE = ("%d^3 unigrid of the same paramfile through the reference binary (unmodified genetIC sources compiled against "
+              "stand-in headers: radix-2 OpenMP FFT instead of FFTW, restated GSL ranlxs2/ziggurat/cspline), %d OpenMP threads, "
+              "whole process including its tipsy file write")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
     n = args.cpu_n
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_port_step(min(n, 128), threads)
-    times = [cpu_port_step(n, threads) for _ in range(max(1, min(args.steps, 3)))]
+    kind = "port"
+    first = reference_binary_step(min(n, 64))  # warm-up (page cache, OpenMP pool) and the availability check
+    if first is not None:
+        kind = "reference"
+        times = [reference_binary_step(n)[0] for _ in range(max(1, min(args.steps, 3)))]
+        sample = REF_SAMPLE % (n, threads) + " (the %d^3 workload does not fit the CPU time budget)" % args.n
+    else:
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_port_step(min(n, 128), threads)
+        times = [cpu_port_step(n, threads) for _ in range(max(1, min(args.steps, 3)))]
+        sample = "%d^3 unigrid (the %d^3 workload does not fit the CPU time budget); CPU oracle port: C/OpenMP draw + " \
+                 "covariance, numpy/pocketfft FFTs with %d workers (reference binary oracle/_ref/genetIC not built)" % (
+                     n, args.n, threads)
     t = statistics.mean(times)
     v = n ** 3 / t
-    sample = "%d^3 unigrid (the %d^3 workload does not fit the CPU time budget); CPU oracle port: C/OpenMP draw + " \
-             "covariance, numpy/pocketfft FFTs with %d workers (FFTW/GSL absent, reference not compilable here)" % (
-                 n, args.n, threads)
     line = {"impl": "reference", "metric": "IC particles/sec (Zeldovich %d^3)" % args.n, "value": v,
             "unit": "particles/s", "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n, "f64"), "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "particles/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "particles/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -295,12 +329,16 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
-        cpu_port_step(64, threads)
-        tcpu = cpu_port_step(args.cpu_n, threads)
-        cpu = {"value": args.cpu_n ** 3 / tcpu, "unit": "particles/s", "cores": threads, "kind": "port",
-               "sample": "one %d^3 IC (%.1f s) through the CPU oracle port: C/OpenMP draw+covariance, pocketfft with "
-                         "%d workers; FFTW/GSL absent so the reference itself cannot be built here" % (
-                             args.cpu_n, tcpu, threads)}
+        ref = reference_binary_step(args.cpu_n)
+        if ref is not None:
+            cpu = {"value": args.cpu_n ** 3 / ref[0], "unit": "particles/s", "cores": threads, "kind": "reference",
+                   "sample": "one IC (%.1f s): " % ref[0] + REF_SAMPLE % (args.cpu_n, threads)}
+        else:
+            cpu_port_step(64, threads)
+            tcpu = cpu_port_step(args.cpu_n, threads)
+            cpu = {"value": args.cpu_n ** 3 / tcpu, "unit": "particles/s", "cores": threads, "kind": "port",
+                   "sample": "one %d^3 IC (%.1f s) through the CPU oracle port: C/OpenMP draw+covariance, pocketfft with "
+                             "%d workers (reference binary oracle/_ref/genetIC not built)" % (args.cpu_n, tcpu, threads)}
 
     line = {"metric": "IC particles/sec (Zeldovich %d^3)" % n, "value": n3 / (ms * 1e-3), "unit": "particles/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,

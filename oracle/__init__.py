@@ -6,8 +6,11 @@ import this package.  The product (genetic_b200) never does; it fails loudly wit
   oracle.crng   -- ctypes binding of gx_oracle.c (ranlxs2 + ziggurat + draw orders)
   oracle.model  -- numpy restatement of the field pipeline (layout, FFT convention, CAMB, Zeldovich, ...)
 
-Parity status: PINNED against the reference's own goldens (tests/test_oracle_golden.py):
-test_02k chi^2 text (10 digits), test_13 + test_05a float32 particles bit-exact.
+  oracle.multilevel -- numpy restatement of the zoom-level machinery, modifications, splicing
+  oracle/_ref/genetIC -- the UNMODIFIED reference compiled from /root/reference against oracle/shims/ (build_ref())
+
+Parity status: PINNED against the reference's own goldens (tests/test_oracle_golden.py, test_oracle_multilevel.py)
+and against the reference itself run here on new inputs (tests/test_oracle_ref.py).
 """
 import ctypes
 import os
@@ -33,6 +36,45 @@ def build(force=False):
     except subprocess.CalledProcessError:
         subprocess.check_call(base, cwd=_HERE)
     return so
+
+
+REF_ROOT = "/root/reference"
+REF_BINARY = os.path.join(_HERE, "_ref", "genetIC")
+
+
+def build_ref(force=False):
+    """Compile the UNMODIFIED reference from /root/reference against oracle/shims/ (FFTW3 / GSL / HDF5 stand-ins, see
+    oracle/shims/README.md) into oracle/_ref/genetIC. Only possible where /root/reference exists (the build container);
+    elsewhere the prebuilt binary is used if it travelled with the snapshot. Returns the path or None."""
+    if os.path.isdir(os.path.join(REF_ROOT, "genetIC", "src")):
+        srcs = [os.path.join(_HERE, "build_ref.sh"), os.path.join(_HERE, "gx_oracle.c")] + \
+               [os.path.join(_HERE, "shims", f) for f in ("fft_shim.cpp", "gsl_shim.cpp", "fftw3.h", "highfive/highfive.hpp")]
+        if force or not os.path.exists(REF_BINARY) or os.path.getmtime(REF_BINARY) < max(os.path.getmtime(f) for f in srcs):
+            subprocess.check_call(["/bin/sh", os.path.join(_HERE, "build_ref.sh"), REF_ROOT], stdout=subprocess.DEVNULL)
+    return ref_binary()
+
+
+def ref_binary():
+    """Path of the compiled reference (oracle/_ref/genetIC) if it exists and is executable, else None."""
+    return REF_BINARY if os.access(REF_BINARY, os.X_OK) else None
+
+
+def run_ref(paramfile_text, workdir, files=(), timeout=3600):
+    """Runs the compiled reference on a paramfile written into `workdir` (extra input files are copied next to it).
+    Returns its combined stdout/stderr. Raises if the binary is missing or exits non-zero."""
+    import shutil
+    exe = ref_binary()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/genetIC has not been built (needs /root/reference: oracle.build_ref())")
+    os.makedirs(workdir, exist_ok=True)
+    for f in files:
+        shutil.copy(f, os.path.join(workdir, os.path.basename(f)))
+    with open(os.path.join(workdir, "paramfile.txt"), "w") as fh:
+        fh.write(paramfile_text)
+    r = subprocess.run([exe, "paramfile.txt"], cwd=workdir, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference binary failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return r.stdout + r.stderr
 
 
 def lib():

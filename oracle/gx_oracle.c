@@ -354,3 +354,9 @@ int orc_slot_is_independent(int N, int ix, int iy, int iz) {
 #include "cosmo_impl.inc"
 #undef REAL
 #undef SFX
+
+/* ---- exported for oracle/shims/gsl_shim.cpp (the reference itself compiled against stand-in headers) ------------------- */
+void orc_cspline_init(const double *xa, const double *ya, int size, double *c) { cspline_init(xa, ya, size, c); }
+double orc_cspline_eval(const double *xa, const double *ya, const double *c, int size, double x) {
+  return cspline_eval(xa, ya, c, size, x);
+}

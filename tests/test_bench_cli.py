@@ -23,7 +23,9 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "particles/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("IC particles/sec") and d["value"] > 0 and d["dtype"] == "f64"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    import oracle
+    assert d["cpu_baseline"]["kind"] == ("reference" if oracle.ref_binary() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None
 

@@ -37,3 +37,9 @@ test_variance_modification_reaches_target_and_matches_oracle = _cases.test_varia
 test_splice_golden_24_and_oracle = _cases.test_splice_golden_24_and_oracle
 test_overdensity_and_variance_modification_golden_02i = _cases.test_overdensity_and_variance_modification_golden_02i
 test_velocity_angular_momentum_potential_modifications_vs_oracle = _cases.test_velocity_angular_momentum_potential_modifications_vs_oracle
+
+
+_ref_cases = _load("gx_reference_cases", os.path.join(HERE, "test_gpu_vs_reference.py"))
+import oracle as _oracle  # noqa: E402
+test_zoom_with_modifications_matches_the_reference_binary = pytest.mark.skipif(
+    _oracle.ref_binary() is None, reason="oracle/_ref/genetIC not built")(_ref_cases.test_zoom_with_modifications_matches_the_reference_binary)
