@@ -77,9 +77,15 @@ class Grid:
             d.offset_lower[a] = float(self.offsetLower[a])
         return d
 
-    def flagCells(self, indices):
-        self.flags = np.unique(np.asarray(indices, dtype=np.int64).reshape(-1))
+    def flagCells(self, indices, append=False):
+        """Sets the flagged cells; append=True is the reference's Grid::flagCells (grid.hpp:269-275: union with the flags
+        already there), the default replaces them (unflagAllCells + flagCells)."""
+        new = np.asarray(indices, dtype=np.int64).reshape(-1)
+        self.flags = np.unique(np.concatenate([self.flags, new]) if append else new)
         self._mask = None
+
+    def unflagAllCells(self):
+        self.flagCells([])
 
     def getFlaggedCells(self):
         return self.flags

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "gx_zeldovich_fourier": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_zeldovich_offset": (ci, [vp, vp, ci, ci, cd, ci, vp]),
     "gx_emit_component": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, vp, ci, cl, cll, cll, vp]),
+    "gx_emit_cells": (ci, [vp, ci, ci, ci, cd, cd, cd, cd, vp, cll, vp, vp, ci, cl, vp]),
     "gx_unigrid_ic": (ci, [P(IcParams), vp, vp, vp, vp, csz, vp, vp, csz, vp]),
     "gx_slab_bytes": (csz, [ci, ci, ci]),
     "gx_slab_noise_draw": (ci, [vp, ci, ci, ci, ci, cul, ci, ci, P(cull), vp]),

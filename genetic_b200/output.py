@@ -1,0 +1,160 @@
+"""Particle file writers fed from mapper.MappedParticles (host arrays in mapper order).
+
+Reference (paths relative to genetIC/src/io/):
+  tipsy::TipsyOutput::operator()     tipsy.hpp:207-271   units, header, dark particle = 9 float32, photogenic.txt, tipsy.param
+  gadget::GadgetOutput::operator()   gadget.hpp:340-556  Fortran records: header (256 B), pos, vel, ids, [mass]; by gadget type
+  createGadget2Header / 3Header      gadget.hpp:116-239
+  tools::MemMapFileWriter            tools/memmap.hpp:169-215  32-bit record markers
+
+Dark matter only (no gas blocks); HDF5/swift/grafic are not written.
+"""
+import os
+import struct
+
+import numpy as np
+
+
+def _sequential_sum(values):
+    """tot_mass += mass in mapper order, in double (tipsy.hpp:217-223): sequential, not pairwise."""
+    return float(np.cumsum(np.asarray(values, dtype=np.float64))[-1])
+
+
+def saveTipsy(filename, boxLength, particles, cosmology, aux_dir=None):
+    """tipsy::save. `particles` must hold positions/velocities in the grid's floating type (the conversions below are
+    done in double before the float32 store, like the reference). Writes tipsy.param and, when masses differ,
+    photogenic.txt next to the file (the reference writes them into its working directory)."""
+    mass = particles.mass.astype(np.float64)
+    min_mass, max_mass = float(mass.min()), float(mass.max())
+    mass_factor = float(cosmology.OmegaM0) / _sequential_sum(mass)
+    pos_factor = 1. / float(boxLength)
+    dKpcUnit = float(boxLength) * 1000 / float(cosmology.hubble)
+    dMsolUnit = 1e10 / float(cosmology.hubble) / mass_factor
+    dKmsUnit = float(np.sqrt(4.3022682e-6 * dMsolUnit / dKpcUnit))
+    vel_factor = float(cosmology.scalefactor) ** -0.5 / dKmsUnit
+    N = len(mass)
+    rec = np.zeros((N, 9), dtype=np.float32)
+    rec[:, 0] = mass * mass_factor
+    rec[:, 1:4] = particles.pos.astype(np.float64) * pos_factor - 0.5
+    rec[:, 4:7] = particles.vel.astype(np.float64) * vel_factor
+    rec[:, 7] = particles.eps.astype(np.float64) * pos_factor
+    aux_dir = aux_dir if aux_dir is not None else (os.path.dirname(filename) or ".")
+    if min_mass != max_mass:
+        with open(os.path.join(aux_dir, "photogenic.txt"), "w") as f:
+            for i in np.flatnonzero(mass == min_mass):
+                f.write("%d\n" % i)
+    with open(os.path.join(aux_dir, "tipsy.param"), "w") as f:
+        f.write("dKpcUnit = %s\ndMsolUnit = %s\ndHubble0 = %s\nbComove = 1 \n"
+                % (_g6(dKpcUnit), _g6(dMsolUnit), _g6(0.1 * float(cosmology.hubble) * dKpcUnit / dKmsUnit)))
+    with open(filename, "wb") as f:
+        f.write(struct.pack("<diiiii4x", float(cosmology.scalefactor), N, 3, 0, N, 0))
+        rec.tofile(f)
+
+
+def _g6(x):
+    """operator<<(ostream, double) with the default precision (6 significant digits, %g)."""
+    return "%g" % x
+
+
+def _fortran(f, payload):
+    n = len(payload)
+    marker = struct.pack("<i", n if n <= 0x7fffffff else 0x7fffffff)
+    f.write(marker)
+    f.write(payload)
+    f.write(marker)
+
+
+def _gadget_header(version, masses, npart, npartTotal, nFiles, boxLength, cosmology, doubleprecision):
+    h = bytearray(256)
+    struct.pack_into("<6i", h, 0, *[int(v) for v in npart])
+    struct.pack_into("<6d", h, 24, *[float(m) for m in masses])
+    struct.pack_into("<dd", h, 72, float(cosmology.scalefactor), float(cosmology.redshift))
+    baryons = 1 if npartTotal[0] > 0 else 0
+    struct.pack_into("<ii", h, 88, baryons, baryons)                              # flag_sfr, flag_feedback
+    struct.pack_into("<6I", h, 96, *[int(v) & 0xffffffff for v in npartTotal])
+    struct.pack_into("<ii", h, 120, baryons, int(nFiles))                         # flag_cooling, num_files
+    struct.pack_into("<4d", h, 128, float(boxLength), float(cosmology.OmegaM0), float(cosmology.OmegaLambda0),
+                     float(cosmology.hubble))
+    struct.pack_into("<ii", h, 160, 0, 0)                                         # flag_stellarage, flag_metals
+    struct.pack_into("<6I", h, 168, *[int(v) >> 32 for v in npartTotal])
+    struct.pack_into("<i", h, 192, 0)                                             # flag_entropy_instead_u
+    if version == 3:
+        struct.pack_into("<iif", h, 196, 1 if doubleprecision else 0, 1, 0.0)     # flag_doubleprecision, flag_ic_info, lpt
+    return bytes(h)
+
+
+def saveGadget(name, boxLength, particles, cosmology, gadgetVersion=3, nFiles=1, out_dtype=np.float32):
+    """gadget::save<float>: files `name + "2"/"3"` (+ ".i" when split). Particles are written by gadget type 0..5, within a
+    type in mapper order; ids are mapper indices (unsigned long)."""
+    if gadgetVersion not in (2, 3):
+        raise ValueError("Unknown gadget format")
+    order = np.argsort(particles.gadgetType, kind="stable")
+    types = particles.gadgetType[order]
+    nPartPerType = [int(np.count_nonzero(types == t)) for t in range(6)]
+    nTotal = len(order)
+    masses = [0.0] * 6
+    variableMass = False
+    for t in range(6):
+        if nPartPerType[t]:
+            m = particles.mass[order][types == t]
+            if m.min() != m.max():
+                variableMass = True
+            masses[t] = float(m.min())
+    if variableMass:
+        masses = [0.0] * 6
+    nPartPerFile = [nTotal // nFiles] * (nFiles - 1) + [nTotal - (nTotal // nFiles) * (nFiles - 1)]
+    pos = particles.pos[order].astype(out_dtype)
+    vel = particles.vel[order].astype(out_dtype)
+    ids = order.astype(np.uint64)
+    mass = particles.mass[order].astype(out_dtype)
+    remainingPerType = list(nPartPerType)
+    start = 0
+    written = []
+    for i in range(nFiles):
+        room = nPartPerFile[i]
+        thisFile = [0] * 6
+        for t in range(6):
+            thisFile[t] = min(remainingPerType[t], room)
+            room -= thisFile[t]
+            remainingPerType[t] -= thisFile[t]
+        fn = name + str(gadgetVersion) + ("" if nFiles == 1 else "." + str(i))
+        sl = slice(start, start + nPartPerFile[i])
+        with open(fn, "wb") as f:
+            _fortran(f, _gadget_header(gadgetVersion, masses, thisFile, nPartPerType, nFiles, boxLength, cosmology,
+                                       np.dtype(out_dtype) == np.float64))
+            _fortran(f, pos[sl].tobytes())
+            _fortran(f, vel[sl].tobytes())
+            _fortran(f, ids[sl].tobytes())
+            if variableMass:
+                _fortran(f, mass[sl].tobytes())
+        start += nPartPerFile[i]
+        written.append(fn)
+    return written
+
+
+def read_gadget(filename):
+    """Reader for the files above (tests): header fields and the blocks present."""
+    with open(filename, "rb") as f:
+        raw = f.read()
+
+    def block(off):
+        n = struct.unpack_from("<i", raw, off)[0]
+        return raw[off + 4:off + 4 + n], off + 8 + n
+
+    h, off = block(0)
+    npart = struct.unpack_from("<6i", h, 0)
+    out = {"npart": npart, "mass_table": struct.unpack_from("<6d", h, 24), "time": struct.unpack_from("<d", h, 72)[0],
+           "redshift": struct.unpack_from("<d", h, 80)[0], "nPartTotal": struct.unpack_from("<6I", h, 96),
+           "num_files": struct.unpack_from("<i", h, 124)[0], "BoxSize": struct.unpack_from("<d", h, 128)[0],
+           "Omega0": struct.unpack_from("<d", h, 136)[0], "OmegaLambda": struct.unpack_from("<d", h, 144)[0],
+           "HubbleParam": struct.unpack_from("<d", h, 152)[0], "header": h}
+    n = sum(npart)
+    b, off = block(off)
+    out["pos"] = np.frombuffer(b, dtype=np.float32).reshape(n, 3)
+    b, off = block(off)
+    out["vel"] = np.frombuffer(b, dtype=np.float32).reshape(n, 3)
+    b, off = block(off)
+    out["ids"] = np.frombuffer(b, dtype=np.uint64)
+    if off < len(raw):
+        b, off = block(off)
+        out["mass"] = np.frombuffer(b, dtype=np.float32)
+    return out

@@ -195,14 +195,57 @@ def zoomCorner(grid, zoomfac):
     return tuple(w.lo)
 
 
+def _trimToZoomWindow(up, flags, corner, nCoarse):
+    """The trimming of initZoomGridWithLowLeftCornerAt (ic.hpp:531-554): flagged cells of the level above whose centroid
+    lies outside the new window [centroid(corner) - eps, centroid(corner + nCoarse - 1) + eps] (Window<T>, periodic) are
+    dropped from the list of cells to replace."""
+    T = up.dtype.type
+    n = up.size
+    hi_cell = [corner[a] + nCoarse for a in range(3)]
+    if up.coversFullSimulation():
+        hi_cell = [(h - 1) % n + 1 for h in hi_cell]
+    elif max(hi_cell) > n:
+        raise L.GxError("The newly initialised zoom level is not fully contained within the previous level")
+    eps = T(up.cellSize * T(1e-6))
+    wrapLength = up.periodicDomainSize
+
+    def wrap(v):
+        if v < 0:
+            v = T(v + wrapLength)
+        if v >= wrapLength:
+            v = T(v - wrapLength)
+        return v
+
+    def centroid(c, a):
+        return T(T(T(T(c) * up.cellSize) + up.offsetLower[a]) + up.cellSize / T(2))
+
+    keep = np.ones(len(flags), dtype=bool)
+    coords = np.unravel_index(np.asarray(flags, dtype=np.int64), (n, n, n))
+    for a in range(3):
+        lo = wrap(T(centroid(corner[a], a) - eps))
+        hi = T(centroid(hi_cell[a] - 1, a) + eps)
+        hi = np.nextafter(wrap(np.nextafter(hi, T(-np.inf))), T(np.inf))
+        cen = (coords[a].astype(up.dtype) * up.cellSize + up.offsetLower[a]) + up.cellSize / T(2)
+        keep &= ((cen < hi) & (cen >= lo)) if hi >= lo else ((cen < hi) | (cen >= lo))
+    return np.asarray(flags, dtype=np.int64)[keep]
+
+
 def initZoomGrid(context, zoomfac, n, corner=None):
-    """initZoomGrid / initZoomGridWithLowLeftCornerAt: appends the zoom level and carries the flags of the level above
-    onto it (the SuperSample + Section view of the parent, grid.hpp:195-228, virtualgrid.hpp:161-166,489-498)."""
+    """initZoomGrid / initZoomGridWithLowLeftCornerAt: appends the zoom level, records the cells of the level above that
+    the particle mapper will replace (context.zoomParticleArray, trimmed to the zoom window: ic.hpp:531-571) and carries
+    the flags of the level above onto the new grid (the SuperSample + Section view of the parent, grid.hpp:195-228,
+    virtualgrid.hpp:161-166,489-498)."""
     up = context.grids[-1]
+    if len(up.getFlaggedCells()) == 0:
+        raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
     if corner is None:
         corner = zoomCorner(up, zoomfac)
     if min(corner) < 0:
         raise L.GxError("The newly initialised zoom level is not fully contained within the previous level")
+    if not hasattr(context, "zoomParticleArray"):
+        context.zoomParticleArray = []
+    del context.zoomParticleArray[len(context.grids) - 1:]
+    context.zoomParticleArray.append(_trimToZoomWindow(up, up.getFlaggedCells(), corner, up.size // zoomfac))
     g = context.addZoomLevel(zoomfac, n, corner)
     ratio = int(round(float(up.cellSize) / float(g.cellSize)))
     pm = np.zeros(up.size3, dtype=bool)

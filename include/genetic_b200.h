@@ -183,6 +183,13 @@ int gx_emit_component(const void *psi, int n, int dtype, int axis, double cell_s
                       double domain_size, double vel_ratio, void *out_pos, void *out_vel, int out_dtype,
                       long stride_elems, long long id0, long long count, void *stream);
 
+/* The device-side gather behind the particle mappers (TwoLevelParticleMapper::dereferenceIterator ->
+   ParticleEvaluator::getParticle, twolevelmapper.hpp:846-852, generator.hpp:49-53): the evaluation of gx_emit_component at
+   a DEVICE list of `count` cell indices of the grid (in mapper order); out[i*stride_elems] receives particle i. */
+int gx_emit_cells(const void *psi, int n, int dtype, int axis, double cell_size, double offset_lower,
+                  double domain_size, double vel_ratio, const long long *cells, long long count, void *out_pos,
+                  void *out_vel, int out_dtype, long stride_elems, void *stream);
+
 /* ---- whole unigrid path (ICGenerator::done -> write, ic.hpp:1633-1648,1275-1331) ------------------------------ */
 typedef struct {
   int n;                   /* base_grid n */

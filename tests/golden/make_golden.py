@@ -13,6 +13,9 @@ tests use the committed copies.
     -> [::4, ::4, ::4] subsamples + the id files that flag the zoom region; test_24 (splicing, 16^3) grid-0.npy whole;
     test_02f / test_02g reference.txt (variance / overdensity values); test_14 (vx modification, 8^3) and test_22 (Ly
     modification, 32^3, every 7th particle) gadget3 outputs -> pos/vel arrays
+  * particle mappers / writers: test_10b (zoom x3, variable-mass gadget3) and test_10c (zoom with gadget particle types
+    1 and 0) reference_output -> header[:208] + every 53rd particle (pos, vel, ids, mass) and the per-type counts;
+    mapper_test_01a_zoom (id file round trip through a two-level mapper) paramfile, zoomtest.txt, reference.txt
 """
 import os
 import shutil
@@ -84,4 +87,31 @@ cp(f"{REF}/test_22_angular_momentum_modif/paramfile.txt", f"{HERE}/test_22_angul
 pos, vel = read_gadget_pos_vel(f"{REF}/test_22_angular_momentum_modif/reference_output", 32 ** 3)
 idx = np.arange(0, 32 ** 3, 7)
 np.savez_compressed(f"{HERE}/test_22_angular_momentum_modif/particles_every7.npz", index=idx, pos=pos[idx], vel=vel[idx])
+
+
+def read_gadget_blocks(fn):
+    raw = open(fn, "rb").read()
+    out, off = [], 0
+    while off < len(raw):
+        n = struct.unpack_from("<i", raw, off)[0]
+        out.append(raw[off + 4:off + 4 + n])
+        off += n + 8
+    return out
+
+
+for t in ("test_10b_gadget_zoom_varimass", "test_10c_gadget_zoom_ptype"):
+    cp(f"{REF}/{t}/paramfile.txt", f"{HERE}/{t}/paramfile.txt")
+    cp(f"{REF}/{t}/zoomtest.txt", f"{HERE}/{t}/zoomtest.txt")
+    blocks = read_gadget_blocks(f"{REF}/{t}/reference_output")
+    n = sum(struct.unpack_from("<6i", blocks[0], 0))
+    idx = np.arange(0, n, 53)
+    arrays = dict(header=np.frombuffer(blocks[0][:208], dtype=np.uint8), index=idx,
+                  pos=np.frombuffer(blocks[1], dtype=np.float32).reshape(n, 3)[idx],
+                  vel=np.frombuffer(blocks[2], dtype=np.float32).reshape(n, 3)[idx],
+                  ids=np.frombuffer(blocks[3], dtype=np.uint64)[idx])
+    if len(blocks) > 4:
+        arrays["mass"] = np.frombuffer(blocks[4], dtype=np.float32)[idx]
+    np.savez_compressed(f"{HERE}/{t}/particles_every53.npz", **arrays)
+for f in ("paramfile.txt", "zoomtest.txt", "reference.txt"):
+    cp(f"{REF}/mapper_test_01a_zoom/{f}", f"{HERE}/mapper_test_01a_zoom/{f}")
 print("ok")

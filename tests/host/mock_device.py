@@ -83,6 +83,43 @@ class MockLib:
         self.mem[_addr(d)][:nbytes] = self.mem[_addr(s)][:nbytes]
         return 0
 
+    def gx_memcpy_d2h(self, h, d, nbytes, st):
+        base, off = self._resolve(d)
+        self._host(h, nbytes)[:] = self.mem[base][off:off + nbytes]
+        return 0
+
+    def _resolve(self, p):
+        """An address inside a mock allocation -> (handle, byte offset)."""
+        a = _addr(p)
+        if a in self.mem:
+            return a, 0
+        base = max(h for h in self.mem if h <= a)
+        assert a - base < len(self.mem[base])
+        return base, a - base
+
+    # ---- particle evaluation (zeldovich.hpp:87-119, generator.hpp:49-53, grid.hpp:519-531,656-669) -------------------
+    def gx_emit_cells(self, psi, n, dt, axis, dx, lower, domain, ratio, cells, count, out_pos, out_vel, odt, stride, st):
+        assert dt == 1
+        ids = self.mem[_addr(cells)][:8 * count].view(np.int64)
+        return self._emit(psi, n, axis, dx, lower, domain, ratio, ids, out_pos, out_vel, odt, stride)
+
+    def gx_emit_component(self, psi, n, dt, axis, dx, lower, domain, ratio, out_pos, out_vel, odt, stride, id0, count, st):
+        assert dt == 1
+        return self._emit(psi, n, axis, dx, lower, domain, ratio, np.arange(id0, id0 + count, dtype=np.int64), out_pos,
+                          out_vel, odt, stride)
+
+    def _emit(self, psi, n, axis, dx, lower, domain, ratio, ids, out_pos, out_vel, odt, stride):
+        p = self.R(psi, n).reshape(-1)[ids]
+        c = np.unravel_index(ids, (n, n, n))[axis].astype(np.float64)
+        q = np.fmod(p + ((c * dx + lower) + dx / 2), domain)
+        q = np.where(q < 0, q + domain, q)
+        O = np.float64 if odt == 1 else np.float32
+        for ptr, val in ((out_pos, q), (out_vel, p * ratio)):
+            if _addr(ptr):
+                base, off = self._resolve(ptr)
+                self.mem[base][off:].view(O)[::stride][:len(ids)] = val.astype(O)
+        return 0
+
     # views of a field buffer (f64 only)
     def F(self, p, n):
         return self.mem[_addr(p)].view(np.complex128).reshape(n, n, n // 2 + 1)

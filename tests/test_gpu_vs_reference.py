@@ -83,3 +83,68 @@ def test_zoom_with_modifications_matches_the_reference_binary(tmp_path, golden_d
         d.toReal()
         ref = np.load(str(tmp_path / ("grid-%d.npy" % l)))
         assert np.abs(d.getDataVector() - ref).max() < 1e-9 * ref.std()
+
+
+@pytest.mark.parametrize("case", ["tipsy_two_levels", "tipsy_three_levels", "gadget2_three_levels",
+                                  "gadget3_types_two_files", "gadget3_trimmed_window"])
+def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, case):
+    """The particle mappers (OneLevel / nested TwoLevel ordering, per-level gadget types, the trimming of the zoom list
+    to a user-placed window) and the tipsy / gadget writers: the files written from the device-evaluated particles are
+    compared byte for byte with the files the reference binary writes for the same paramfile."""
+    from genetic_b200 import mapper as PM, output as OUT
+    fmt = {"tipsy": "tipsy", "gadget2": "gadget2", "gadget3": "gadget3"}[case.split("_")[0]]
+    pf = COSMO + "random_seed_real_space 90210\noutname t\noutdir ./\noutformat %s\n" % fmt
+    types, nfiles, corner, radius = [1, 1, 1], 1, None, 7
+    if case == "gadget3_types_two_files":
+        pf += "gadget_num_files 2\n"
+        nfiles, types = 2, [2, 1]
+    pf += "basegrid 60.0 32\n"
+    if case == "gadget3_types_two_files":
+        pf += "gadget_particle_type 2\n"
+    if case == "gadget3_trimmed_window":
+        corner, radius = (6, 9, 13), 12
+        pf += "centre 20 33 41\nselect_sphere 12\nzoomgrid_with_origin_at 6 9 13 2 32\n"
+    else:
+        pf += "centre 20 33 41\nselect_sphere 7\nzoomgrid 2 32\n"
+    if case == "gadget3_types_two_files":
+        pf += "gadget_particle_type 1\n"
+    three = "three" in case
+    if three:
+        pf += "centre 20 33 41\nselect_sphere 3\nzoomgrid 2 32\n"
+    out = oracle.run_ref(pf + "done\n", str(tmp_path), [_camb_file(golden_dir)])
+    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99)
+    ctx = GM.MultiLevelGrid()
+    ctx.addLevel(gb.Grid(60.0, 32))
+    for s in ("dm", "all"):
+        ctx.setPowerspectrumGenerator(s, gb.CAMB(cos, _camb_file(golden_dir), s))
+    Z.selectSphere(ctx, (20, 33, 41), radius)
+    Z.initZoomGrid(ctx, 2, 32, corner=corner)
+    if case == "gadget3_trimmed_window":
+        assert "have been omitted" in out and len(ctx.zoomParticleArray[0]) < len(ctx.getGridForLevel(0).getFlaggedCells())
+    if three:
+        Z.selectSphere(ctx, (20, 33, 41), 3)
+        Z.initZoomGrid(ctx, 2, 32)
+    field = GM.draw(ctx, 90210)
+    field.applyPowerSpectrumFor(GM.ALL)
+    gen = GM.MultiLevelParticleGenerator(field)
+    mapper = PM.updateParticleMapper(ctx, types)
+    assert mapper.size() == int(re.search(r"number dm particles=(\d+)", out).group(1))
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    if fmt == "tipsy":
+        parts = PM.MappedParticles(mapper, gen, cos, out_dtype=np.float64)
+        OUT.saveTipsy(str(ours / "t.tipsy"), 60.0, parts, cos)
+        a, b = (tmp_path / "t.tipsy").read_bytes(), (ours / "t.tipsy").read_bytes()
+        assert a[:28] == b[:28] and a[32:] == b[32:]        # bytes 28..31 are struct padding
+        assert (tmp_path / "tipsy.param").read_text() == (ours / "tipsy.param").read_text()
+        # (photogenic.txt: the reference lists only the lightest particles its OpenMP thread 0 happened to write,
+        #  tipsy.hpp:129-134; ours lists all of them)
+        light = np.loadtxt(str(ours / "photogenic.txt"), dtype=np.int64)
+        assert set(np.loadtxt(str(tmp_path / "photogenic.txt"), dtype=np.int64).tolist()) <= set(light.tolist())
+        assert len(light) == np.count_nonzero(parts.level == ctx.getNumLevels() - 1)
+    else:
+        parts = PM.MappedParticles(mapper, gen, cos, out_dtype=np.float32)
+        files = OUT.saveGadget(str(ours / "t.gadget"), 60.0, parts, cos, int(fmt[-1]), nfiles)
+        assert len(files) == nfiles
+        for f in files:
+            assert open(f, "rb").read() == (tmp_path / os.path.basename(f)).read_bytes()
