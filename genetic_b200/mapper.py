@@ -12,7 +12,7 @@ Reference (paths relative to genetIC/src/simulation/particles/mapper/):
 The reference walks these with iterators that dereference one particle at a time (mapperiterator.hpp:151-156). Here a
 mapper is resolved once into its *layout* -- two arrays (level, cell index) in output order, pure index arithmetic on the
 host -- and the particles of each level are then evaluated on the device at that level's cell list in one launch per
-component (gx_emit_cells). Not covered: gas splitting (AddGasMapper), sub/supersampling, intermediate-resolution padding,
+component (gx_emit_cells). Gas: AddGasMapper over splitMass (gasmapper.hpp). Not covered: sub/supersampling, intermediate-resolution padding,
 stray particles, the grafic mapper.
 """
 import ctypes as C
@@ -27,8 +27,9 @@ from .host import _dt
 class OneLevelParticleMapper:
     """onelevelmapper.hpp: every cell of one grid, in cell-index order."""
 
-    def __init__(self, grid, level, gadgetParticleType=1):
-        self.grid, self.level, self.gadgetParticleType = grid, level, gadgetParticleType
+    def __init__(self, grid, level, gadgetParticleType=1, massScale=None):
+        # massScale: the MassScaledGrid view of `grid` (virtualgrid.hpp:657-676) that splitMass creates for gas / dark matter
+        self.grid, self.level, self.gadgetParticleType, self.massScale = grid, level, gadgetParticleType, massScale
 
     def size(self):
         return self.grid.size3
@@ -45,11 +46,25 @@ class OneLevelParticleMapper:
     def grids(self):
         return {self.level: self.grid}
 
-    def gadgetTypes(self):
-        return {self.level: self.gadgetParticleType}
-
     def layout(self):
         return (np.full(self.grid.size3, self.level, dtype=np.int32), np.arange(self.grid.size3, dtype=np.int64))
+
+    def attrs(self):
+        """Per particle: the mass scale of its (virtual) grid and its gadget type."""
+        T = self.grid.dtype.type
+        return (np.full(self.grid.size3, T(1) if self.massScale is None else T(self.massScale), dtype=self.grid.dtype),
+                np.full(self.grid.size3, self.gadgetParticleType, dtype=np.int32))
+
+    def size_gas(self):
+        return 0
+
+    def splitMass(self, massRatio, toLevels):
+        """onelevelmapper.hpp:155-173: (gas mapper or None, dark-matter mapper)."""
+        T = self.grid.dtype.type
+        if self.level in toLevels:
+            return (OneLevelParticleMapper(self.grid, self.level, 0, T(massRatio)),
+                    OneLevelParticleMapper(self.grid, self.level, self.gadgetParticleType, T(T(1.0) - T(massRatio))))
+        return None, OneLevelParticleMapper(self.grid, self.level, self.gadgetParticleType, self.massScale)
 
     def unflagAllParticles(self):
         self.grid.unflagAllCells()
@@ -135,6 +150,7 @@ class TwoLevelParticleMapper:
         keep[self.level1ParticlesToReplace] = False
         if skipLevel1:
             keep[:] = False
+        self._keep = keep
         self._layout = (np.concatenate([lev[keep], np.full(len(self.zoomParticleArrayHiresUnsorted), pLevel2.level, np.int32)]),
                         np.concatenate([cell[keep], self.zoomParticleArrayHiresUnsorted]))
 
@@ -155,13 +171,26 @@ class TwoLevelParticleMapper:
         g.update(self.pLevel2.grids())
         return g
 
-    def gadgetTypes(self):
-        g = dict(self.pLevel1.gadgetTypes())
-        g.update(self.pLevel2.gadgetTypes())
-        return g
-
     def layout(self):
         return self._layout
+
+    def attrs(self):
+        a1, a2 = self.pLevel1.attrs(), self.pLevel2.attrs()
+        return tuple(np.concatenate([x[self._keep], y[self.zoomParticleArrayHiresUnsorted]]) for x, y in zip(a1, a2))
+
+    def size_gas(self):
+        return 0
+
+    def splitMass(self, massRatio, toLevels):
+        """twolevelmapper.hpp:519-553: gas exists only where level 2 (and possibly level 1) was asked to carry it; a level
+        1 without gas is kept as the notional (skipped) low-resolution part of the gas mapper."""
+        gas1, dm1 = self.pLevel1.splitMass(massRatio, toLevels)
+        gas2, dm2 = self.pLevel2.splitMass(massRatio, toLevels)
+        newskip = self.skipLevel1
+        if gas1 is None:
+            gas1, newskip = self.pLevel1, True
+        gas = TwoLevelParticleMapper(gas1, gas2, self.level1CellsToReplace, newskip) if gas2 is not None else None
+        return gas, TwoLevelParticleMapper(dm1, dm2, self.level1CellsToReplace, self.skipLevel1)
 
     def unflagAllParticles(self):
         self.pLevel1.unflagAllParticles()
@@ -205,25 +234,102 @@ class TwoLevelParticleMapper:
         return np.sort(np.concatenate(out))
 
 
-def updateParticleMapper(context, gadgetTypesForLevels=None):
-    """ICGenerator::updateParticleMapper (ic.hpp:1129-1176) for dark matter without sub/supersampling: the one-level
-    mapper of the base grid, wrapped once per zoom level with that level's zoomParticleArray (stored on the context by
-    zoom.initZoomGrid)."""
+class AddGasMapper:
+    """gasmapper.hpp: a gas mapper and a dark-matter mapper back to back (gas first for tipsy, last for gadget). Ids
+    refer to the dark-matter part only (flagParticles / getFlaggedParticles, gasmapper.hpp:149-190)."""
+
+    def __init__(self, pFirst, pSecond, gasFirst=True):
+        self.firstMap, self.secondMap, self.gasFirst = pFirst, pSecond, gasFirst
+        self.nFirst, self.nSecond = pFirst.size(), pSecond.size()
+        gas, dm = (pFirst, pSecond) if gasFirst else (pSecond, pFirst)
+        self.gasMap, self.dmMap = gas, dm
+        if (gas.attrs()[1] != 0).any():
+            raise L.GxError("AddGasMapper: the gas mapper holds particles of a gadget type other than 0")
+        if (dm.attrs()[1] == 0).any():
+            raise L.GxError("You have asked for some gadget DM particles to be output with type 0, but have also set "
+                            "non-zero baryon density. Type 0 is reserved for gas particles in hydro simulations, and "
+                            "genetIC particle types refer only to the dark matter part of the output.")
+
+    def size(self):
+        return self.nFirst + self.nSecond
+
+    def size_gas(self):
+        return self.nFirst if self.gasFirst else self.nSecond
+
+    def size_dm(self):
+        return self.nSecond if self.gasFirst else self.nFirst
+
+    def getFinestGrid(self):
+        return self.dmMap.getFinestGrid()
+
+    def getCoarsestGrid(self):
+        return self.dmMap.getCoarsestGrid()
+
+    def grids(self):
+        g = dict(self.firstMap.grids())
+        g.update(self.secondMap.grids())
+        return g
+
+    def layout(self):
+        return tuple(np.concatenate([a, b]) for a, b in zip(self.firstMap.layout(), self.secondMap.layout()))
+
+    def attrs(self):
+        return tuple(np.concatenate([a, b]) for a, b in zip(self.firstMap.attrs(), self.secondMap.attrs()))
+
+    def isGas(self):
+        g = np.zeros(self.size(), dtype=bool)
+        if self.gasFirst:
+            g[:self.nFirst] = True
+        else:
+            g[self.nFirst:] = True
+        return g
+
+    def unflagAllParticles(self):
+        self.firstMap.unflagAllParticles()
+        self.secondMap.unflagAllParticles()
+
+    def flagParticles(self, ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        if self.gasFirst:
+            self.secondMap.flagParticles(ids[ids >= self.nFirst] - self.nFirst)
+        else:
+            self.firstMap.flagParticles(ids[ids < self.nFirst])
+
+    def getFlaggedParticles(self):
+        if self.gasFirst:
+            return self.secondMap.getFlaggedParticles() + self.nFirst
+        return self.firstMap.getFlaggedParticles()
+
+
+def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, baryonsOnAllLevels=False, gasFirst=False):
+    """ICGenerator::updateParticleMapper (ic.hpp:1129-1221) without sub/supersampling and padding: the one-level mapper of
+    the base grid, wrapped once per zoom level with that level's zoomParticleArray (stored on the context by
+    zoom.initZoomGrid); with OmegaBaryons0 > 0 the mass is split into a gas mapper (deepest level only unless
+    baryonsOnAllLevels) and a dark-matter mapper, gas first for tipsy and last for gadget."""
     nl = context.getNumLevels()
     types = list(gadgetTypesForLevels) if gadgetTypesForLevels is not None else [1] * nl
     m = OneLevelParticleMapper(context.getGridForLevel(0), 0, types[0])
     for level in range(1, nl):
         fine = OneLevelParticleMapper(context.getGridForLevel(level), level, types[level])
         m = TwoLevelParticleMapper(m, fine, context.zoomParticleArray[level - 1])
+    if cosmology is not None and cosmology.OmegaBaryons0 > 0:
+        T = context.getGridForLevel(0).dtype.type
+        gas, dm = m.splitMass(T(T(cosmology.OmegaBaryons0) / T(cosmology.OmegaM0)),
+                              list(range(nl)) if baryonsOnAllLevels else [nl - 1])
+        m = AddGasMapper(gas, dm, True) if gasFirst else AddGasMapper(dm, gas, False)
     return m
 
 
-def particle_mass(grid, cosmology):
+def particle_mass(grid, cosmology, massScale=None):
     """ZeldovichParticleEvaluator::getMass (zeldovich.hpp:55-62,108-110): boxMass * cellMassFrac, cellMassFrac =
-    pow(dx / simsize, 3) (grid.hpp:112), in the grid's type."""
+    pow(dx / simsize, 3) (grid.hpp:112), times the mass scale of a MassScaledGrid (virtualgrid.hpp:672), in the grid's type.
+    massScale may be an array (one entry per particle)."""
     T = grid.dtype.type
     boxMass = T(T(27.744948) * T(cosmology.OmegaM0)) * T(math.pow(float(grid.periodicDomainSize), 3.0))
-    return T(boxMass * T(math.pow(float(T(grid.cellSize / grid.periodicDomainSize)), 3.0)))
+    frac = T(math.pow(float(T(grid.cellSize / grid.periodicDomainSize)), 3.0))
+    if massScale is None:
+        return T(boxMass * frac)
+    return boxMass * (np.asarray(massScale, dtype=grid.dtype) * frac)
 
 
 def particle_eps(grid, epsNorm=0.01075):
@@ -239,8 +345,10 @@ class MappedParticles:
     def __init__(self, mapper, particleGenerator, cosmology, out_dtype=np.float32, epsNorm=0.01075):
         lib = L.load()
         lev, cell = mapper.layout()
+        scale, self.gadgetType = mapper.attrs()
         N = len(lev)
         self.level, self.cell = lev, cell
+        self.isGas = mapper.isGas() if hasattr(mapper, "isGas") else np.zeros(N, dtype=bool)
         self.pos = np.empty((N, 3), dtype=out_dtype)
         self.vel = np.empty((N, 3), dtype=out_dtype)
         grids = mapper.grids()
@@ -250,7 +358,7 @@ class MappedParticles:
         odt, esz = _dt(out_dtype), np.dtype(out_dtype).itemsize
         for level, grid in grids.items():
             where = np.flatnonzero(lev == level)
-            self.mass[where] = particle_mass(grid, cosmology)
+            self.mass[where] = particle_mass(grid, cosmology, scale[where])
             self.eps[where] = particle_eps(grid, epsNorm)
             m = len(where)
             if m == 0:
@@ -287,6 +395,3 @@ class MappedParticles:
             else:
                 self.pos[where] = p
                 self.vel[where] = v
-        self.gadgetType = np.empty(N, dtype=np.int32)
-        for level, t in mapper.gadgetTypes().items():
-            self.gadgetType[lev == level] = t

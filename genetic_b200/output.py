@@ -6,7 +6,8 @@ Reference (paths relative to genetIC/src/io/):
   createGadget2Header / 3Header      gadget.hpp:116-239
   tools::MemMapFileWriter            tools/memmap.hpp:169-215  32-bit record markers
 
-Dark matter only (no gas blocks); HDF5/swift/grafic are not written.
+Gas particles (OmegaBaryons0 > 0: mapper.AddGasMapper) are written as tipsy gas records / gadget type 0 with the dummy
+internal-energy block. HDF5/swift/grafic are not written.
 """
 import os
 import struct
@@ -32,11 +33,23 @@ def saveTipsy(filename, boxLength, particles, cosmology, aux_dir=None):
     dKmsUnit = float(np.sqrt(4.3022682e-6 * dMsolUnit / dKpcUnit))
     vel_factor = float(cosmology.scalefactor) ** -0.5 / dKmsUnit
     N = len(mass)
-    rec = np.zeros((N, 9), dtype=np.float32)
-    rec[:, 0] = mass * mass_factor
-    rec[:, 1:4] = particles.pos.astype(np.float64) * pos_factor - 0.5
-    rec[:, 4:7] = particles.vel.astype(np.float64) * vel_factor
-    rec[:, 7] = particles.eps.astype(np.float64) * pos_factor
+    gas = np.asarray(getattr(particles, "isGas", np.zeros(N, dtype=bool)))
+    ngas = int(gas.sum())
+    if ngas and not gas[:ngas].all():
+        raise ValueError("tipsy output needs the gas particles first (AddGasMapper with gasFirst)")
+
+    def records(sl, width, eps_col):
+        rec = np.zeros((sl.stop - sl.start, width), dtype=np.float32)
+        rec[:, 0] = mass[sl] * mass_factor
+        rec[:, 1:4] = particles.pos[sl].astype(np.float64) * pos_factor - 0.5
+        rec[:, 4:7] = particles.vel[sl].astype(np.float64) * vel_factor
+        rec[:, eps_col] = particles.eps[sl].astype(np.float64) * pos_factor
+        return rec
+
+    # gas: mass, x, y, z, vx, vy, vz, rho, temp, eps, metals, phi; dark: mass, x, y, z, vx, vy, vz, eps, phi
+    grec = records(slice(0, ngas), 12, 9)
+    grec[:, 8] = _temperature(cosmology)
+    rec = records(slice(ngas, N), 9, 7)
     aux_dir = aux_dir if aux_dir is not None else (os.path.dirname(filename) or ".")
     if min_mass != max_mass:
         with open(os.path.join(aux_dir, "photogenic.txt"), "w") as f:
@@ -46,8 +59,17 @@ def saveTipsy(filename, boxLength, particles, cosmology, aux_dir=None):
         f.write("dKpcUnit = %s\ndMsolUnit = %s\ndHubble0 = %s\nbComove = 1 \n"
                 % (_g6(dKpcUnit), _g6(dMsolUnit), _g6(0.1 * float(cosmology.hubble) * dKpcUnit / dKmsUnit)))
     with open(filename, "wb") as f:
-        f.write(struct.pack("<diiiii4x", float(cosmology.scalefactor), N, 3, 0, N, 0))
+        f.write(struct.pack("<diiiii4x", float(cosmology.scalefactor), N, 3, ngas, N - ngas, 0))
+        grec.tofile(f)
         rec.tofile(f)
+
+
+def _temperature(cosmology):
+    """cosmology::getTemperature (parameters.hpp:36-42); baryon decoupling at a = 1/150 (ic.hpp:206)."""
+    a, adec = float(cosmology.scalefactor), 1. / 150.
+    if a > adec:
+        return float(cosmology.TCMB) * adec / (a * a)
+    return float(cosmology.TCMB) / a
 
 
 def _g6(x):
@@ -126,6 +148,8 @@ def saveGadget(name, boxLength, particles, cosmology, gadgetVersion=3, nFiles=1,
             _fortran(f, ids[sl].tobytes())
             if variableMass:
                 _fortran(f, mass[sl].tobytes())
+            if float(cosmology.OmegaBaryons0) > 0:
+                _fortran(f, np.zeros(thisFile[0], dtype=out_dtype).tobytes())        # dummy internal energy, gadget.hpp:545-552
         start += nPartPerFile[i]
         written.append(fn)
     return written
@@ -154,7 +178,8 @@ def read_gadget(filename):
     out["vel"] = np.frombuffer(b, dtype=np.float32).reshape(n, 3)
     b, off = block(off)
     out["ids"] = np.frombuffer(b, dtype=np.uint64)
-    if off < len(raw):
-        b, off = block(off)
-        out["mass"] = np.frombuffer(b, dtype=np.float32)
+    for _ in range(2):
+        if off < len(raw):
+            b, off = block(off)
+            out["mass" if len(b) == 4 * n and "mass" not in out else "u"] = np.frombuffer(b, dtype=np.float32)
     return out

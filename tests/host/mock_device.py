@@ -153,11 +153,12 @@ class MockLib:
 
     def gx_noise_draw(self, p, n, dt, seed, mode, reverse, off, st):
         from oracle import crng
-        assert mode == 0, "the mock provides the real-space draw order only"
         o = off._obj if off is not None else None
         if o is None or o.value == 0:           # first level: new gsl stream; later levels continue it
             self._stream = crng.Stream(seed)
-        self.F(p, n)[:] = M.draw_white_noise(n, seed, "real", stream=self._stream)
+        name = {0: "real", 1: "fourier_reverse" if reverse else "fourier_serial", 2: "fourier_parallel"}[mode]
+        # parallel mode: one stream per shell, seeded from the base seed on every level (randomfieldgenerator.hpp:228-229)
+        self.F(p, n)[:] = M.draw_white_noise(n, seed, name, stream=None if mode == 2 else self._stream)
         if o is not None:
             o.value += 1                         # (the device counts raw outputs; any non-zero value continues)
         return 0

@@ -86,14 +86,18 @@ def test_zoom_with_modifications_matches_the_reference_binary(tmp_path, golden_d
 
 
 @pytest.mark.parametrize("case", ["tipsy_two_levels", "tipsy_three_levels", "gadget2_three_levels",
-                                  "gadget3_types_two_files", "gadget3_trimmed_window"])
+                                  "gadget3_types_two_files", "gadget3_trimmed_window", "tipsy_gas", "gadget3_gas",
+                                  "gadget2_gas_all_levels"])
 def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, case):
     """The particle mappers (OneLevel / nested TwoLevel ordering, per-level gadget types, the trimming of the zoom list
     to a user-placed window) and the tipsy / gadget writers: the files written from the device-evaluated particles are
     compared byte for byte with the files the reference binary writes for the same paramfile."""
     from genetic_b200 import mapper as PM, output as OUT
     fmt = {"tipsy": "tipsy", "gadget2": "gadget2", "gadget3": "gadget3"}[case.split("_")[0]]
-    pf = COSMO + "random_seed_real_space 90210\noutname t\noutdir ./\noutformat %s\n" % fmt
+    gas = "gas" in case
+    pf = ("Ob 0.04\n" if gas else "") + COSMO + "random_seed_real_space 90210\noutname t\noutdir ./\noutformat %s\n" % fmt
+    if "all_levels" in case:
+        pf += "baryons_all_levels\n"
     types, nfiles, corner, radius = [1, 1, 1], 1, None, 7
     if case == "gadget3_types_two_files":
         pf += "gadget_num_files 2\n"
@@ -112,7 +116,7 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     if three:
         pf += "centre 20 33 41\nselect_sphere 3\nzoomgrid 2 32\n"
     out = oracle.run_ref(pf + "done\n", str(tmp_path), [_camb_file(golden_dir)])
-    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99)
+    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99, OmegaBaryons0=0.04 if gas else 0.0)
     ctx = GM.MultiLevelGrid()
     ctx.addLevel(gb.Grid(60.0, 32))
     for s in ("dm", "all"):
@@ -127,8 +131,9 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     field = GM.draw(ctx, 90210)
     field.applyPowerSpectrumFor(GM.ALL)
     gen = GM.MultiLevelParticleGenerator(field)
-    mapper = PM.updateParticleMapper(ctx, types)
-    assert mapper.size() == int(re.search(r"number dm particles=(\d+)", out).group(1))
+    mapper = PM.updateParticleMapper(ctx, types, cos, "all_levels" in case, gasFirst=(fmt == "tipsy"))
+    assert mapper.size() - mapper.size_gas() == int(re.search(r"number dm particles=(\d+)", out).group(1))
+    assert mapper.size_gas() == int(re.search(r"number gas particles=(\d+)", out).group(1))
     ours = tmp_path / "ours"
     ours.mkdir()
     if fmt == "tipsy":
@@ -141,10 +146,42 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
         #  tipsy.hpp:129-134; ours lists all of them)
         light = np.loadtxt(str(ours / "photogenic.txt"), dtype=np.int64)
         assert set(np.loadtxt(str(tmp_path / "photogenic.txt"), dtype=np.int64).tolist()) <= set(light.tolist())
-        assert len(light) == np.count_nonzero(parts.level == ctx.getNumLevels() - 1)
+        assert len(light) == np.count_nonzero(parts.mass == parts.mass.min())
     else:
         parts = PM.MappedParticles(mapper, gen, cos, out_dtype=np.float32)
         files = OUT.saveGadget(str(ours / "t.gadget"), 60.0, parts, cos, int(fmt[-1]), nfiles)
         assert len(files) == nfiles
         for f in files:
             assert open(f, "rb").read() == (tmp_path / os.path.basename(f)).read_bytes()
+
+
+def test_example_paramfile_end_to_end_matches_the_reference_binary(tmp_path, golden_dir):
+    """BASELINE.json config 1: example/paramfile.txt as shipped (Planck 2018, Ob > 0 -> gas on the zoom level, base 128^3
+    over 50 Mpc/h, zoom x3 128^3 around (32.5, 32.5, 32.5), random_seed 8896131, gadget3), run by the reference binary and
+    through the device path + mappers + writer: the gadget3 file byte for byte except velocities to float32 rounding."""
+    from genetic_b200 import mapper as PM, output as OUT
+    pf = open(os.path.join(golden_dir, "example_paramfile.txt")).read()
+    pf = pf[:pf.index("done") + 5]                         # up to `done`: the dump_ps / dump_grid lines are diagnostics
+    out = oracle.run_ref(pf, str(tmp_path), [os.path.join(golden_dir, "planck_2018_transfer_out.dat")])
+    camb = os.path.join(golden_dir, "planck_2018_transfer_out.dat")
+    cos = gb.CosmologicalParameters(0.3158, 0.6842, 0.8117, 200, ns=0.9660, hubble=0.6732, OmegaBaryons0=0.0494)
+    ctx = GM.MultiLevelGrid()
+    ctx.addLevel(gb.Grid(50.0, 128))
+    ctx.setPowerspectrumGenerator("all", gb.CAMB(cos, camb, "all"))
+    Z.selectSphere(ctx, (32.5, 32.5, 32.5), 6)
+    Z.initZoomGrid(ctx, 3, 128)
+    field = GM.draw(ctx, 8896131, drawInFourierSpace=True, parallel=True)
+    field.applyPowerSpectrumFor(GM.ALL)
+    gen = GM.MultiLevelParticleGenerator(field)
+    mapper = PM.updateParticleMapper(ctx, None, cos)
+    assert mapper.size_dm() == int(re.search(r"number dm particles=(\d+)", out).group(1))
+    assert mapper.size_gas() == int(re.search(r"number gas particles=(\d+)", out).group(1))
+    parts = PM.MappedParticles(mapper, gen, cos, out_dtype=np.float32)
+    fn = OUT.saveGadget(str(tmp_path / "ours.gadget"), 50.0, parts, cos, 3)[0]
+    a, b = OUT.read_gadget(str(tmp_path / "test.gadget3")), OUT.read_gadget(fn)
+    assert a["header"] == b["header"]
+    assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["mass"], b["mass"]) and np.array_equal(a["u"], b["u"])
+    for k in ("pos", "vel"):
+        d = np.abs(a[k] - b[k])
+        assert np.all((d <= np.spacing(np.abs(a[k]))) | (d <= 1e-10 * np.abs(a[k]).max())), k
+        assert (d == 0).mean() > 0.999

@@ -49,3 +49,5 @@ test_zoom_particle_files_match_the_reference_binary = pytest.mark.skipif(
 
 _mapper_cases = _load("gx_mapper_cases", os.path.join(HERE, "test_gpu_mapper.py"))
 test_gadget_zoom_goldens_10b_10c = _mapper_cases.test_gadget_zoom_goldens_10b_10c
+test_example_paramfile_end_to_end_matches_the_reference_binary = pytest.mark.skipif(
+    _oracle.ref_binary() is None, reason="oracle/_ref/genetIC not built")(_ref_cases.test_example_paramfile_end_to_end_matches_the_reference_binary)
