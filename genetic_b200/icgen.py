@@ -1,0 +1,553 @@
+"""The paramfile command layer: `python -m genetic_b200 paramfile.txt` runs a genetIC parameter file on the device.
+
+Reference: ICGenerator (genetIC/src/ic.hpp) and the command routes of genetIC/src/main.cpp:22-172, dispatched line by line
+like tools::Dispatch::run_loop (tools/parser.hpp:156-207): first token = command (case-insensitive), `#` / `%` start a
+comment line, surplus tokens are ignored, an error aborts the run with the reference's message format.
+
+Everything numerical is sequencing over the C ABI (host.py / multilevel.py / zoom.py / mapper.py / output.py); this file
+holds only the state machine of ICGenerator. Commands outside the accelerated path raise "not supported" errors instead
+of being silently ignored: grafic / HDF5 / swift output, sub/supersampling, strays, autopad, adapt_mask, masks,
+mapper_relative_to, baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+
+from . import lib as L
+from .host import CosmologicalParameters, Grid, CAMB, PowerLawPowerSpectrum, RandomFieldGenerator
+from . import multilevel as GM, zoom as Z, mapper as PM, output as OUT
+
+
+class ICGenerator:
+    """ICGenerator<GridDataType> (ic.hpp:62-1762)."""
+
+    def __init__(self, dtype=np.float64, log=None):
+        self.dtype = np.dtype(dtype)
+        # ic.hpp:196-226
+        self.cosmology = CosmologicalParameters(OmegaM0=0.3, OmegaLambda0=None, sigma8=None, redshift=0.0, ns=0.96,
+                                                hubble=0.701, OmegaBaryons0=0.0, TCMB=2.725)
+        self.context = GM.MultiLevelGrid()
+        self.context.zoomParticleArray = []
+        self.spectrum_args = None
+        self.seed, self.drawInFourierSpace, self.parallel, self.reverseOrder = None, False, False, False
+        self.exactPowerSpectrum = False
+        self.haveInitialisedRandomComponent = False
+        self.outputField = None
+        self.modificationManager = None
+        self.pParticleGenerator = None
+        self.outputFolder, self.outputFilename, self.outputFormat = "./", "", None
+        self.nGadgetFiles = 1
+        self.mruGadgetType, self.gadgetTypesForLevels, self.usedGadgetParticleTypes = 1, [], [False] * 6
+        self.baryonsOnAllLevels = False
+        self.epsNorm = 0.01075
+        self.x0 = self.y0 = self.z0 = 0.0
+        self.variance_filterscale = -1.0
+        self.initial_number_steps, self.precision = 10, 0.001
+        self.velOffset = (0.0, 0.0, 0.0)
+        self.log = log if log is not None else (lambda msg: print(msg, flush=True))
+        GM.set_logger(self.log)
+        self.commands = self._routes()
+
+    # ---- command table (main.cpp:22-172) ---------------------------------------------------------------------------
+    def _routes(self):
+        f, i, s = float, int, str
+        r = {
+            "tcmb": (self.setTCMB, f), "om": (self.setOmegaM0, f), "ob": (self.setOmegaB0, f), "ol": (self.setOmegaLambda0, f),
+            "hubble": (self.setHubble, f), "s8": (self.setSigma8, f), "ns": (self.setns, f), "zin": (self.setZ0, f),
+            "z": (self.setZ0, f),
+            "seed": (self.setSeed, i), "random_seed_real_space": (self.setSeed, i),
+            "seedfourier": (self.setSeedFourier, i), "random_seed_serial": (self.setSeedFourier, i),
+            "seedfourier_reverse": (self.setSeedFourierReverseOrder, i),
+            "seedfourier_parallel": (self.setSeedFourierParallel, i), "random_seed": (self.setSeedFourierParallel, i),
+            "exact_power_spectrum_enforcement": (self.setExactPowerSpectrumEnforcement,),
+            "fix_power": (self.setExactPowerSpectrumEnforcement,),
+            "eps_norm": (self.setEpsNorm, f),
+            "gadget_particle_type": (self.setGadgetParticleType, i), "gadget_num_files": (self.setGadgetNumFiles, i),
+            "camb": (self.setCambDat, s), "powerlaw_amplitude": (self.setPowerLawAmplitude, f),
+            "outdir": (self.setOutDir, s), "outname": (self.setOutName, s), "outformat": (self.setOutputFormat, s),
+            "basegrid": (self.initBaseGrid, f, i), "base_grid": (self.initBaseGrid, f, i),
+            "zoomgrid": (self.initZoomGrid, i, i), "zoom_grid": (self.initZoomGrid, i, i),
+            "zoomgrid_with_origin_at": (self.initZoomGridWithLowLeftCornerAt, i, i, i, i, i),
+            "zoom_grid_with_origin_at": (self.initZoomGridWithLowLeftCornerAt, i, i, i, i, i),
+            "idfile": (self.loadID, s), "id_file": (self.loadID, s),
+            "append_idfile": (self.appendID, s), "merge_id_file": (self.appendID, s),
+            "dump_idfile": (self.dumpID, s), "dump_id_file": (self.dumpID, s),
+            "centre_on": (self.centreParticle, i), "center_on": (self.centreParticle, i),
+            "centre": (self.setCentre, f, f, f), "center": (self.setCentre, f, f, f),
+            "select_sphere": (self.selectSphere, f), "select_ellipse": (self.selectEllipse, f, f, f),
+            "select_cube": (self.selectCube, f), "select_nearest": (self.selectNearest,),
+            "expand_flagged_region": (self.expandFlaggedRegion, i),
+            "modify": (self.modify, s, s, f), "calculate": (self.calculate, s),
+            "filtering_scale": (self.setVarianceFilteringScale, f),
+            "clear_modifications": (self.clearModifications,), "done": (self.done,),
+            "apply_modifications": (self.applyModifications,), "chi2": (self.getFieldChi2,),
+            "reverse": (self.reverse,), "splice": (self.splice, i),
+            "dump_grid": (self.dumpGrid, i), "dump_vx": (self.dumpVelocityX, i), "dump_grid_fourier": (self.dumpGridFourier, i),
+            "dump_ps": (self.dumpPS, i), "dump_tipsy": (self.saveTipsyArray, s),
+            "zerolevel": (self.zeroLevel, i), "zero_level": (self.zeroLevel, i),
+            "baryons_all_levels": (self.setBaryonsOnAllLevels,),
+            "velocity_offset": (self.setOffset, f, f, f),
+        }
+        for name in ("strays_on", "supersample", "supersample_gas", "subsample", "num_neighbors", "num_neighbours", "pvar",
+                     "center_grafic_output", "centre_output", "center_output", "gadget_flagged_particle_type",
+                     "mapper_relative_to", "adapt_mask", "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
+                     "dump_ps_field", "dump_tipsy_field", "dump_mask", "import_level",
+                     "baryon_tf_on", "zero_level_field", "reverse_small_k"):
+            r[name] = (self._unsupported(name),)
+        return r
+
+    def _unsupported(self, name):
+        def fail(*_):
+            raise L.GxError("command %s is outside the accelerated path and not supported by genetic_b200" % name)
+        return fail
+
+    def run_line(self, line):
+        """Dispatch::run (parser.hpp:156-181)."""
+        tok = line.split()
+        if not tok or tok[0][0] in "#%":
+            return
+        name = tok[0].lower()
+        if name not in self.commands:
+            raise L.GxError("Unknown command " + tok[0])
+        fn, *types = self.commands[name]
+        if len(tok) - 1 < len(types) and fn.__name__ != "fail":
+            raise L.GxError("Insufficient arguments (expected %d)" % len(types))
+        try:
+            args = [t(v) for t, v in zip(types, tok[1:])]
+        except ValueError:
+            raise L.GxError("Error while parsing arguments")
+        fn(*args)
+
+    # ---- cosmology (ic.hpp:228-343) ----------------------------------------------------------------------------------
+    def setTCMB(self, v):
+        self.cosmology.TCMB = v
+
+    def setOmegaM0(self, v):
+        self.cosmology.OmegaM0 = v
+
+    def setOmegaB0(self, v):
+        self.cosmology.OmegaBaryons0 = v
+
+    def setOmegaLambda0(self, v):
+        self.cosmology.OmegaLambda0 = v
+
+    def setHubble(self, v):
+        self.cosmology.hubble = v
+
+    def setSigma8(self, v):
+        self.cosmology.sigma8 = v
+
+    def setns(self, v):
+        self.cosmology.ns = v
+
+    def setZ0(self, z):
+        self.cosmology.setRedshift(z)
+
+    def setEpsNorm(self, v):
+        self.epsNorm = v
+
+    def setBaryonsOnAllLevels(self):
+        self.baryonsOnAllLevels = True
+
+    def setOffset(self, vx, vy, vz):
+        """velocity_offset (ic.hpp:285-289): km/s -> km a^1/2 s^-1."""
+        T = self.dtype.type
+        conversion = T(math.pow(float(T(self.cosmology.scalefactor)), -0.5))
+        self.velOffset = tuple(T(T(v) * conversion) for v in (vx, vy, vz))
+
+    def setVarianceFilteringScale(self, v):
+        self.variance_filterscale = v
+
+    # ---- seeds (ic.hpp:615-660) --------------------------------------------------------------------------------------
+    def _seed(self, seed, fourier, parallel, reverse):
+        self.seed, self.drawInFourierSpace, self.parallel, self.reverseOrder = seed, fourier, parallel, reverse
+
+    def setSeed(self, seed):
+        self._seed(seed, False, False, False)
+
+    def setSeedFourier(self, seed):
+        self._seed(seed, True, False, False)
+
+    def setSeedFourierParallel(self, seed):
+        self._seed(seed, True, True, False)
+
+    def setSeedFourierReverseOrder(self, seed):
+        self.log("*** Warning: seed_field_fourier_reverse and seedfourier_reverse are deprecated commands and should be avoided.***")
+        self._seed(seed, True, False, True)
+
+    def setExactPowerSpectrumEnforcement(self):
+        self.exactPowerSpectrum = True
+
+    # ---- files and formats (ic.hpp:662-760) --------------------------------------------------------------------------
+    def setGadgetNumFiles(self, n):
+        self.nGadgetFiles = n
+
+    def setGadgetParticleType(self, t):
+        if t >= 6 or t < 0:
+            raise L.GxError("Gadget particle type must be between 0 and 5")
+        if t != self.mruGadgetType:
+            if self.usedGadgetParticleTypes[t]:
+                raise L.GxError("Cannot reuse a gadget particle type; this type was already used in a different section of the ICs")
+            self.mruGadgetType = t
+        if self.context.getNumLevels() == 0:
+            raise L.GxError("Can't set a gadget particle type until a level has been initialised to set it for")
+        self.gadgetTypesForLevels[-1] = t
+
+    def setCambDat(self, path):
+        self.spectrum_args = ("camb", path)
+        self._install_spectrum()
+
+    def setPowerLawAmplitude(self, amplitude):
+        self.spectrum_args = ("powerlaw", amplitude)
+        self._install_spectrum()
+
+    def _install_spectrum(self):
+        kind, arg = self.spectrum_args
+        c = self.cosmology
+        cos = CosmologicalParameters(c.OmegaM0, c.OmegaLambda0, c.sigma8, c.redshift, c.ns, c.hubble, c.OmegaBaryons0, c.TCMB)
+        for species in (GM.DM, GM.ALL):
+            spec = CAMB(cos, arg, species, self.dtype) if kind == "camb" else PowerLawPowerSpectrum(cos, arg, self.dtype)
+            self.context.setPowerspectrumGenerator(species, spec)
+
+    def setOutDir(self, path):
+        self.outputFolder = path
+
+    def setOutName(self, name):
+        self.outputFilename = name
+
+    def setOutputFormat(self, fmt):
+        """io::operator>>(OutputFormat) accepts a name or its number (io.hpp)."""
+        names = {"gadget2": "gadget2", "2": "gadget2", "gadget3": "gadget3", "3": "gadget3", "tipsy": "tipsy", "4": "tipsy"}
+        if fmt.lower() not in names:
+            if fmt.lower() in ("grafic", "5", "gadgethdf", "6", "swift", "7"):
+                raise L.GxError("output format %s is not supported by genetic_b200 (tipsy, gadget2, gadget3 are)" % fmt)
+            raise L.GxError("Unknown output format")
+        self.outputFormat = names[fmt.lower()]
+
+    def getOutputPath(self):
+        if not self.outputFilename:
+            name = "IC_%s_z%s_%d" % ("float" if self.dtype == np.float32 else "doub", "%g" % self.cosmology.redshift,
+                                     self.context.getGridForLevel(0).size)
+            return self.outputFolder + "/" + name
+        return self.outputFolder + "/" + self.outputFilename
+
+    # ---- grids (ic.hpp:365-612) --------------------------------------------------------------------------------------
+    def initBaseGrid(self, boxSize, n):
+        if self.context.getNumLevels() > 0:
+            raise L.GxError("Cannot re-initialize the base grid")
+        if self.haveInitialisedRandomComponent:
+            raise L.GxError("Trying to initialize a grid after the random field was already drawn")
+        self.log("Initialized the base grid:\n  Box length            = %g Mpc/h\n  n                     = %d\n"
+                 "  dx                    = %g" % (boxSize, n, boxSize / n))
+        self.context.addLevel(Grid(boxSize, n, dtype=self.dtype))
+        self._levelAdded()
+
+    def _levelAdded(self):
+        self.gadgetTypesForLevels.append(self.mruGadgetType)
+        if len(self.gadgetTypesForLevels) > 1:
+            self.usedGadgetParticleTypes[self.mruGadgetType] = True
+
+    def initZoomGrid(self, zoomfac, n):
+        self._zoom(zoomfac, n, None)
+
+    def initZoomGridWithLowLeftCornerAt(self, x0, y0, z0, zoomfac, n):
+        self._zoom(zoomfac, n, (x0, y0, z0))
+
+    def _zoom(self, zoomfac, n, corner):
+        if self.haveInitialisedRandomComponent:
+            raise L.GxError("Trying to initialize a grid after the random field was already drawn")
+        if self.context.getNumLevels() < 1:
+            raise L.GxError("Cannot initialise a zoom grid before initialising the base grid")
+        up = self.context.getGridForLevel(self.context.getNumLevels() - 1)
+        nflag = len(up.getFlaggedCells())
+        if nflag == 0:
+            raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
+        if corner is None:
+            corner = Z.zoomCorner(up, zoomfac)
+            if Z.flagsNearZoomBorder(up, corner, zoomfac):
+                self.log("WARNING: Opening a zoom where flagged particles are within 3 pixels of the edge. This is prone to "
+                         "numerical errors.")
+        g = Z.initZoomGrid(self.context, zoomfac, n, corner=corner)
+        self._levelAdded()
+        kept = len(self.context.zoomParticleArray[-1])
+        if kept < nflag:
+            self.log("WARNING: the requested zoom particles do not all fit in the requested zoom window\n"
+                     "         of %d particles, %d have been omitted\n         to make a new zoom flag list of %d"
+                     % (nflag, nflag - kept, kept))
+        self.log("Initialized a zoom region:\n  Subbox length         = %g Mpc/h\n  n                     = %d\n"
+                 "  dx                    = %g\n  Zoom factor           = %d\n  Num particles         = %d\n"
+                 "  Low-left corner in parent grid = (%d, %d, %d)\n"
+                 "  Low-left corner (h**-1 Mpc)    = %g, %g, %g\n  Total particles       = %d"
+                 % (float(g.thisGridSize), g.size, float(g.cellSize), zoomfac, nflag, *corner, *[float(v) for v in g.offsetLower],
+                    self._mapper().size()))
+
+    def _mapper(self, gasFirst=None):
+        if gasFirst is None:
+            gasFirst = self.outputFormat == "tipsy"
+        return PM.updateParticleMapper(self.context, self.gadgetTypesForLevels, self.cosmology, self.baryonsOnAllLevels,
+                                       gasFirst=gasFirst)
+
+    # ---- flags (ic.hpp:1236-1524) ------------------------------------------------------------------------------------
+    def _ids(self, filename):
+        with open(filename) as f:
+            return np.unique(np.array([int(t) for t in f.read().split()], dtype=np.int64))   # io::getBuffer + sortAndEraseDuplicate
+
+    def loadID(self, filename):
+        self._mapper().unflagAllParticles()
+        self.appendID(filename)
+
+    def appendID(self, filename):
+        self._mapper().flagParticles(self._ids(filename))
+        self._getCentre()
+
+    def dumpID(self, filename):
+        with open(filename, "w") as f:
+            for i in self._mapper().getFlaggedParticles():     # io::dumpBuffer: one id per line
+                f.write("%d\n" % i)
+
+    def _getCentre(self):
+        """ICGenerator::getCentre (ic.hpp:1372-1386): the centre of the flagged cells on the deepest level that has any."""
+        level = 0
+        for l in range(self.context.getNumLevels() - 1, -1, -1):      # deepestLevelwithFlaggedCells, multilevelgrid.hpp
+            if len(self.context.getGridForLevel(l).getFlaggedCells()) > 0:
+                level = l
+                break
+        g = self.context.getGridForLevel(level)
+        self.x0, self.y0, self.z0 = Z.getCentreWrapped(g, g.getFlaggedCells())
+        self.log("Centre of region is %.12g %.12g %.12g" % (self.x0, self.y0, self.z0))
+
+    def centreParticle(self, pid):
+        g = self.context.getGridForLevel(0)
+        c = np.unravel_index(int(pid), (g.size,) * 3)
+        T = g.dtype.type
+        self.x0, self.y0, self.z0 = (float(T(T(T(c[a]) * g.cellSize) + g.offsetLower[a]) + g.cellSize / T(2)) for a in range(3))
+
+    def setCentre(self, x, y, z):
+        self.x0, self.y0, self.z0 = x, y, z
+
+    def _centre(self):
+        return (self.x0, self.y0, self.z0)
+
+    def selectSphere(self, radius):
+        Z.selectSphere(self.context, self._centre(), radius)
+
+    def selectEllipse(self, a, b, c):
+        Z.selectEllipse(self.context, self._centre(), a, b, c)
+
+    def selectCube(self, side):
+        Z.selectCube(self.context, self._centre(), side)
+
+    def selectNearest(self):
+        Z.selectNearest(self.context, self._centre())
+
+    def expandFlaggedRegion(self, nCells):
+        """ic.hpp:1527-1543 over Grid::expandFlaggedRegion (grid.hpp:277-306): flags the +-1 neighbours along x, y, z in
+        turn, nCells times, with periodic wrapping of the cell coordinates."""
+        if self.context.getNumLevels() < 1:
+            raise L.GxError("No grid has yet been initialised")
+        self.log("Expand flagged region by %d cells" % nCells)
+        for level, g in enumerate(self.context.grids):
+            before = len(g.getFlaggedCells())
+            flags = g.getFlaggedCells()
+            n = g.size
+            for _ in range(nCells):
+                for axis in range(3):
+                    c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0)
+                    out = [flags]
+                    for step in (1, -1):
+                        d = c.copy()
+                        d[axis] = (d[axis] + step) % n
+                        out.append(np.ravel_multi_index(tuple(d), (n, n, n)))
+                    flags = np.unique(np.concatenate(out))
+            g.flagCells(flags)
+            self.log("  - level %d increased number of flagged cells by %d (now %d)" % (level, len(flags) - before, len(flags)))
+
+    # ---- random component, modifications (ic.hpp:1333-1346,1589-1745) ------------------------------------------------
+    def initialiseRandomComponentIfUninitialised(self):
+        if self.haveInitialisedRandomComponent:
+            return
+        if self.context.getNumLevels() == 0:
+            raise L.GxError("No grid has been initialised")
+        if self.seed is None:
+            raise L.GxError("No random seed has been specified")
+        self.log("Drawing random numbers")
+        self.outputField = GM.draw(self.context, self.seed, self.drawInFourierSpace, self.parallel, self.reverseOrder)
+        if self.exactPowerSpectrum:
+            self.outputField.enforceUnitVariance()
+        self.modificationManager = GM.ModificationManager(self.context, self.cosmology, self.outputField)
+        self.haveInitialisedRandomComponent = True
+
+    def getFieldChi2(self):
+        self.initialiseRandomComponentIfUninitialised()
+        self.log("Calculated chi^2 = %.10g (dof = %d)" % (self.outputField.getChi2(), self.context.getNumDof()))
+
+    def _modkw(self):
+        return dict(filterscale=self.variance_filterscale, initNumberSteps=self.initial_number_steps, precision=self.precision)
+
+    def calculate(self, name):
+        self.initialiseRandomComponentIfUninitialised()
+        self.log("%s: calculated value = %g" % (name, self.modificationManager.calculateCurrentValueByName(name, **self._modkw())))
+
+    def modify(self, name, type_, target):
+        self.initialiseRandomComponentIfUninitialised()
+        # ICGenerator::modify(string, string, float target): the target passes through a C float (ic.hpp:1606)
+        self.modificationManager.addModificationToList(name, type_, float(np.float32(target)), **self._modkw())
+
+    def clearModifications(self):
+        if self.modificationManager is not None:
+            self.modificationManager.clearModifications()
+
+    def applyModifications(self):
+        self.initialiseRandomComponentIfUninitialised()
+        self.modificationManager.applyModifications()
+
+    def reverse(self):
+        self.initialiseRandomComponentIfUninitialised()
+        self.outputField.reverse()
+
+    def splice(self, newSeed):
+        """ic.hpp:1706-1743."""
+        self.initialiseRandomComponentIfUninitialised()
+        if self.outputField.getTransferType() != GM.WHITENOISE:
+            raise L.GxError("It is too late in the IC generation process to perform splicing; try moving the splice command earlier")
+        if self.context.getNumLevels() > 1:
+            self.log("Splicing operations on multiple levels work, but may have edge artefacts. Use experimentally/at your own risk!")
+        self.log("Constructing new random field for exterior of splice")
+        newField = GM.draw(self.context, newSeed)           # a fresh RandomFieldGenerator: real space, serial (:1718-1727)
+        self.log("Finished constructing new random field. Beginning splice operation.")
+        for level in range(self.context.getNumLevels()):
+            orig = self.outputField.getFieldForLevel(level)
+            cov = self.context.getCovariance(level, GM.DM).getPowerSpectrumForGrid(orig.grid)
+            spliced = GM.spliceOneLevel(newField.getFieldForLevel(level), orig, cov)
+            spliced.toFourier()
+            self.outputField.fieldsOnLevels[level] = spliced
+
+    def zeroLevel(self, level):
+        self.log("*** Warning: your script calls zeroLevel(%d). This is intended for testing purposes only!" % level)
+        self.initialiseRandomComponentIfUninitialised()
+        if level > self.outputField.getNumLevels() - 1:
+            raise L.GxError("Specified level does not exist.")
+        f = self.outputField.getFieldForLevel(level)
+        f.lib.gx_memset_zero(f.ptr, f.nbytes, f.stream)
+
+    # ---- output (ic.hpp:820-900,1275-1331,1633-1648) -----------------------------------------------------------------
+    def done(self):
+        if self.outputFormat is None:
+            raise L.GxError("No output format specified!")
+        self.initialiseRandomComponentIfUninitialised()
+        if self.modificationManager.hasModifications():
+            self.applyModifications()
+        self.write()
+
+    def write(self):
+        self.initialiseRandomComponentIfUninitialised()
+        if self.outputField.getTransferType() == GM.WHITENOISE:
+            self.outputField.applyPowerSpectrumFor(GM.ALL)                      # applyPowerSpec (ic.hpp:802-818)
+        if self.pParticleGenerator is None:
+            self.log("Calculating particles from overdensity fields...")
+            self.pParticleGenerator = GM.MultiLevelParticleGenerator(self.outputField)
+        mapper = self._mapper()
+        self.log("Writing output; number dm particles=%d, number gas particles=%d" % (mapper.size() - mapper.size_gas(), mapper.size_gas()))
+        boxlen = float(self.context.getGridForLevel(0).periodicDomainSize)
+        offset = any(float(v) != 0.0 for v in self.velOffset)
+        if self.outputFormat == "tipsy" or offset:
+            parts = PM.MappedParticles(mapper, self.pParticleGenerator, self.cosmology, out_dtype=self.dtype, epsNorm=self.epsNorm)
+            if offset:                                                            # OffsetEvaluator (offsetgenerator.hpp:38-43)
+                parts.vel += np.array(self.velOffset, dtype=self.dtype)
+        else:
+            parts = PM.MappedParticles(mapper, self.pParticleGenerator, self.cosmology, out_dtype=np.float32, epsNorm=self.epsNorm)
+        if self.outputFormat == "tipsy":
+            OUT.saveTipsy(self.getOutputPath() + ".tipsy", boxlen, parts, self.cosmology, aux_dir=".")
+        else:
+            OUT.saveGadget(self.getOutputPath() + ".gadget", boxlen, parts, self.cosmology, int(self.outputFormat[-1]),
+                           self.nGadgetFiles)
+        self.log("Finished writing initial conditions")
+
+    def _dumpGridData(self, level, field, prefix="grid"):
+        """ic.hpp:822-851 (+ numpy.hpp): the n^3 array and the info text file."""
+        g = field.grid
+        name = "%s/%s-%d" % (self.outputFolder, prefix, level)
+        data = field.getDataVector()
+        np.save(name + ".npy", data)
+        with open("%s/%s-info-%d%s.txt" % (self.outputFolder, prefix, level, "-fourier" if field.isFourier() else ""), "w") as f:
+            f.write("%g %g %g %g\n" % (*[float(v) for v in g.offsetLower], float(g.thisGridSize)))
+            f.write("The line above contains information about grid level %d\n" % level)
+            f.write("It gives the x-offset, y-offset and z-offset of the low-left corner and also the box length\n")
+
+    def dumpGrid(self, level):
+        self.initialiseRandomComponentIfUninitialised()
+        self.outputField.toReal()
+        self._dumpGridData(level, self.outputField.getFieldForLevel(level))
+
+    def dumpGridFourier(self, level):
+        """ic.hpp:879-885 + getComplexFourierField (fourier.hpp:685-716): the full complex n^3 Fourier cube."""
+        self.initialiseRandomComponentIfUninitialised()
+        self.outputField.toFourier()
+        f = self.outputField.getFieldForLevel(level)
+        half = f.getDataVector()
+        n = f.grid.size
+        full = np.zeros((n, n, n), dtype=half.dtype)
+        full[:, :, :n // 2 + 1] = half
+        idx = (-np.arange(n)) % n
+        kz = np.arange(n // 2 + 1, n)
+        full[:, :, kz] = np.conj(half[idx][:, idx][:, :, n - kz])
+        np.save("%s/grid-%d.npy" % (self.outputFolder, level), full)
+
+    def dumpPS(self, level):
+        """ic.hpp:943-962: <outname>_<level>.ps, a host-side diagnostic of the level's Fourier field."""
+        self.initialiseRandomComponentIfUninitialised()
+        f = self.outputField.getFieldForLevel(level)
+        f.toFourier()
+        cov = self.context.getCovariance(level, GM.ALL).getPowerSpectrumForGrid(f.grid)
+        OUT.dumpPowerSpectrum(f.getDataVector(), cov.getDataVector(), f.grid, "%s_%d.ps" % (self.getOutputPath(), level))
+
+    def saveTipsyArray(self, filename):
+        """ic.hpp:853-862: the overdensity of every particle's cell in mapper order (`dump_tipsy`), a host-side diagnostic."""
+        self.initialiseRandomComponentIfUninitialised()
+        self.outputField.toReal()
+        OUT.saveFieldTipsyArray(filename, self._mapper(), [self.outputField.getFieldForLevel(l).getDataVector()
+                                                            for l in range(self.context.getNumLevels())])
+
+    def dumpVelocityX(self, level):
+        if self.pParticleGenerator is None:
+            raise L.GxError("dump_vx: the particle generator has not been initialised (call done first)")
+        self._dumpGridData(level, self.pParticleGenerator.getGeneratorForLevel(level).getGeneratedFields()[0], "vx")
+
+
+def run_paramfile(paramfile, dtype=np.float64, log=None):
+    """runGenetic (main.cpp:199-229): runs from the paramfile's directory, stops at the first error."""
+    paramfile = os.path.abspath(paramfile)
+    if not os.path.isfile(paramfile):
+        raise L.GxError("could not open parameter file " + paramfile)
+    gen = ICGenerator(dtype, log)
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(paramfile))
+    try:
+        with open(paramfile) as f:
+            for lineno, line in enumerate(f, 1):
+                line = line.rstrip("\n")
+                if not line.strip():
+                    continue
+                try:
+                    gen.run_line(line)
+                except (L.GxError, OSError, ValueError) as e:
+                    raise L.GxError('Error "%s" on line %d ("%s")' % (e, lineno, line)) from e
+    finally:
+        os.chdir(cwd)
+    return gen
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv or argv[0] in ("-h", "--help"):
+        print("Usage: python -m genetic_b200 paramfile [-f]\n\n The paramfile is a text file of genetIC commands.\n"
+              " If option -f is specified, float (32-bit) is used instead of double (64-bit) internally.")
+        return 0 if argv else 1
+    try:
+        run_paramfile(argv[0], np.float32 if "-f" in argv[1:] else np.float64)
+    except L.GxError as e:
+        print(str(e), file=sys.stderr)
+        return 1
+    return 0

@@ -26,6 +26,20 @@ FRACTIONAL_K_SPLIT = 0.3  # Makefile:23
 WHITENOISE, DM, BARYON, ALL = "whitenoise", "dm", "baryon", "all"  # particle::species (species.hpp)
 
 
+_log = [None]
+
+
+def set_logger(fn):
+    """Where the reference's classes write to logging::entry() (warnings of the modifications, the chi^2 lines of
+    ModificationManager::applyModifications); None = silent."""
+    _log[0] = fn
+
+
+def log(msg):
+    if _log[0] is not None:
+        _log[0](msg)
+
+
 class MultiLevelGrid:
     """multilevelgrid::MultiLevelGrid: the grids of all levels, their weights and the covariance provider."""
 
@@ -81,10 +95,17 @@ class MultiLevelGrid:
 
 
 class FilterFamily:
-    """filters::FilterFamily (filterfamily.hpp:86-143), levels not yet combined."""
+    """filters::FilterFamily (filterfamily.hpp:86-143). Once the levels have been combined (the fine fields carry the
+    low-frequency information too) every level but the finest gets the null filter and the finest the identity."""
 
     def __init__(self, context):
         ident = FilterProduct([])
+        if context.levelsAreCombined:
+            null = ident * 0.0
+            nl = context.getNumLevels()
+            self.filters = [null] * (nl - 1) + [ident]
+            self.lpFilters, self.hpFilters = list(self.filters), list(self.filters)
+            return
         self.filters, self.lpFilters, self.hpFilters = [ident], [ident], [ident]
         for level in range(context.getNumLevels() - 1):
             g = context.getGridForLevel(level)
@@ -335,12 +356,38 @@ def generateMultilevelCovectorFromHiresCovector(context, hires, transferType):
     return ret
 
 
+def _warnIfWholeZoomGridIsFlagged(context):
+    """Modification::Modification (modification.hpp:36-47)."""
+    for level in range(1, context.getNumLevels()):
+        g = context.getGridForLevel(level)
+        if len(g.flags) == g.size3:
+            log("WARNING: Region selected for modification is the entire zoom grid. This is likely because the cell "
+                "selection extends beyond the zoom boundaries.")
+            log("By design, modifications are meant to be defined inside a zoom region. Increase the size of your zoom grid "
+                "or decrease your selection to avoid nasty surprises.")
+
+
+def _flaggedCellsPhysicalSize(grid):
+    """Grid::getFlaggedCellsPhysicalSize (grid.hpp:318-334): the largest side of the periodic window holding the flags."""
+    from . import zoom as Z
+    flags = grid.getFlaggedCells()
+    if len(flags) == 0:
+        return 0.0
+    n = grid.size
+    coords = np.stack(np.unravel_index(flags, (n, n, n)), axis=1)
+    w = Z._Window(grid.simEquivalentSize, [int(v) for v in coords[0]])
+    for c in coords:
+        w.expandToInclude([int(v) for v in c])
+    return float(grid.dtype.type(max(w.sizes())) * grid.cellSize)
+
+
 class LinearModification:
     """modifications::LinearModification (linearmodification.hpp:24-107)."""
     order = 1
 
     def __init__(self, context, cosmology):
         self.context, self.cosmology = context, cosmology
+        _warnIfWholeZoomGridIsFlagged(context)
         g = context.getGridForLevel(context.getNumLevels() - 1)
         if len(g.flags) == 0:
             raise L.GxError("Linear modifications use exclusively information from the highest resolution grid "
@@ -496,6 +543,12 @@ class FilteredVarianceModification:
         fine = context.getGridForLevel(context.getNumLevels() - 1)
         if filterscale < float(fine.cellSize):
             raise L.GxError("Variance high-pass filtering scale is smaller than the smallest pixel size.")
+        _warnIfWholeZoomGridIsFlagged(context)
+        window_size = _flaggedCellsPhysicalSize(fine)
+        if filterscale > window_size:                       # checkFilterScale, quadraticmodification.hpp:128-149
+            log("WARNING: High-pass filtering scale: %g h**-1 Mpc is greater than the rough window size: %g h**-1 Mpc used "
+                "for modifications." % (filterscale, window_size))
+            log("This is prone to numerical errors when modifying the field. Decrease filtering scale to avoid it.")
         self.context, self.cosmology, self.scale = context, cosmology, float(filterscale)
         self.initNumberSteps, self.targetPrecision = initNumberSteps, targetPrecision
         self.flaggedCells = [g.flags.copy() for g in context.grids]
@@ -582,9 +635,23 @@ class ModificationManager:
         return bool(self.linearModificationList or self.quadraticModificationList)
 
     def clearModifications(self):
+        log("Clearing modification list")
         self.linearModificationList, self.quadraticModificationList = [], []
 
     def applyModifications(self):
+        logging = _log[0] is not None                # the chi^2 bookkeeping of modificationmanager.hpp:93-125 is log output only
+        pre = self.outputField.getChi2() if logging else None
+        log("")
+        log("Applying modifications")
+        self._applyModifications()
+        if logging:
+            post = self.outputField.getChi2()
+            log("   Post-modification chi^2 = %g" % post)
+            log("  Modification Delta chi^2 = %g" % (post - pre))
+            log("           d.o.f. in field = %d" % self.context.getNumDof())
+            log("")
+
+    def _applyModifications(self):
         covectors = [m.getCovector(self.outputField.getTransferType()) for m in self.linearModificationList]
         targets = [m.getTarget() for m in self.linearModificationList]
         self._orthonormalise(covectors, targets)

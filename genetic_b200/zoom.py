@@ -195,6 +195,21 @@ def zoomCorner(grid, zoomfac):
     return tuple(w.lo)
 
 
+def flagsNearZoomBorder(grid, corner, zoomfac, borderSafety=3):
+    """ICGenerator::initZoomGrid (ic.hpp:461-474): True when a flagged cell lies within `borderSafety` cells of the edge
+    of the zoom window placed at `corner` (Window<int>::containsWithBorderSafety, window.hpp:296-302)."""
+    n = grid.size
+    w = _Window(grid.simEquivalentSize, list(corner))
+    w.hi = [corner[a] + n // zoomfac for a in range(3)]
+    w.wrapCorners()
+    coords = np.unravel_index(grid.getFlaggedCells(), (n, n, n))
+    ok = np.ones(len(coords[0]), dtype=bool)
+    for a in range(3):
+        lo, hi = w.lo[a] + borderSafety, w.hi[a] - borderSafety
+        ok &= ((coords[a] < hi) & (coords[a] >= lo)) if hi >= lo else ((coords[a] < hi) | (coords[a] >= lo))
+    return not ok.all()
+
+
 def _trimToZoomWindow(up, flags, corner, nCoarse):
     """The trimming of initZoomGridWithLowLeftCornerAt (ic.hpp:531-554): flagged cells of the level above whose centroid
     lies outside the new window [centroid(corner) - eps, centroid(corner + nCoarse - 1) + eps] (Window<T>, periodic) are

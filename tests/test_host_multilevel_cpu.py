@@ -51,3 +51,18 @@ _mapper_cases = _load("gx_mapper_cases", os.path.join(HERE, "test_gpu_mapper.py"
 test_gadget_zoom_goldens_10b_10c = _mapper_cases.test_gadget_zoom_goldens_10b_10c
 test_example_paramfile_end_to_end_matches_the_reference_binary = pytest.mark.skipif(
     _oracle.ref_binary() is None, reason="oracle/_ref/genetIC not built")(_ref_cases.test_example_paramfile_end_to_end_matches_the_reference_binary)
+
+
+# the reference's own paramfiles through the command layer (genetic_b200/icgen.py), host logic on the mock device
+_pf = _load("gx_paramfile_cases", os.path.join(HERE, "test_gpu_paramfile.py"))
+
+
+@pytest.fixture(autouse=True)
+def _mock_spectrum_for_icgen(monkeypatch, mock_device):
+    import genetic_b200.icgen as I
+    monkeypatch.setattr(I, "CAMB", _mock.MockSpectrum)
+
+
+for _name in dir(_pf):
+    if _name.startswith("test_"):
+        globals()["test_paramfile_" + _name[5:]] = getattr(_pf, _name)
