@@ -12,6 +12,7 @@ mapper_relative_to, baryon_tf_on, import_level, reverse_small_k, dump_mask, cent
 import math
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -286,8 +287,16 @@ class ICGenerator:
     def _mapper(self, gasFirst=None):
         if gasFirst is None:
             gasFirst = self.outputFormat == "tipsy"
-        return PM.updateParticleMapper(self.context, self.gadgetTypesForLevels, self.cosmology, self.baryonsOnAllLevels,
-                                       gasFirst=gasFirst)
+        # the reference rebuilds the mapper whenever one of these changes (updateParticleMapper call sites); here it is
+        # rebuilt on demand and kept while they stay the same
+        key = (self.context.getNumLevels(), tuple(self.gadgetTypesForLevels), float(self.cosmology.OmegaBaryons0),
+               float(self.cosmology.OmegaM0), self.baryonsOnAllLevels, gasFirst,
+               tuple(id(z) for z in self.context.zoomParticleArray))
+        if getattr(self, "_mapper_key", None) != key:
+            self._mapper_cache = PM.updateParticleMapper(self.context, self.gadgetTypesForLevels, self.cosmology,
+                                                         self.baryonsOnAllLevels, gasFirst=gasFirst)
+            self._mapper_key = key
+        return self._mapper_cache
 
     # ---- flags (ic.hpp:1236-1524) ------------------------------------------------------------------------------------
     def _ids(self, filename):
@@ -448,7 +457,9 @@ class ICGenerator:
         if self.pParticleGenerator is None:
             self.log("Calculating particles from overdensity fields...")
             self.pParticleGenerator = GM.MultiLevelParticleGenerator(self.outputField)
+        t0 = time.perf_counter()
         mapper = self._mapper()
+        t1 = time.perf_counter()
         self.log("Writing output; number dm particles=%d, number gas particles=%d" % (mapper.size() - mapper.size_gas(), mapper.size_gas()))
         boxlen = float(self.context.getGridForLevel(0).periodicDomainSize)
         offset = any(float(v) != 0.0 for v in self.velOffset)
@@ -458,11 +469,15 @@ class ICGenerator:
                 parts.vel += np.array(self.velOffset, dtype=self.dtype)
         else:
             parts = PM.MappedParticles(mapper, self.pParticleGenerator, self.cosmology, out_dtype=np.float32, epsNorm=self.epsNorm)
+        t2 = time.perf_counter()
         if self.outputFormat == "tipsy":
             OUT.saveTipsy(self.getOutputPath() + ".tipsy", boxlen, parts, self.cosmology, aux_dir=".")
         else:
             OUT.saveGadget(self.getOutputPath() + ".gadget", boxlen, parts, self.cosmology, int(self.outputFormat[-1]),
                            self.nGadgetFiles)
+        if os.environ.get("GX_TIMING", "0") == "1":
+            self.log("[timing] mapper %.3f s, particle evaluation + copy %.3f s, file %.3f s"
+                     % (t1 - t0, t2 - t1, time.perf_counter() - t2))
         self.log("Finished writing initial conditions")
 
     def _dumpGridData(self, level, field, prefix="grid"):
@@ -522,6 +537,7 @@ def run_paramfile(paramfile, dtype=np.float64, log=None):
     if not os.path.isfile(paramfile):
         raise L.GxError("could not open parameter file " + paramfile)
     gen = ICGenerator(dtype, log)
+    timing = os.environ.get("GX_TIMING", "0") == "1"       # per-command wall clock in the log
     cwd = os.getcwd()
     os.chdir(os.path.dirname(paramfile))
     try:
@@ -531,7 +547,10 @@ def run_paramfile(paramfile, dtype=np.float64, log=None):
                 if not line.strip():
                     continue
                 try:
+                    t0 = time.perf_counter()
                     gen.run_line(line)
+                    if timing and time.perf_counter() - t0 > 0.01:
+                        gen.log("[timing] %-40s %.3f s" % (line.strip()[:40], time.perf_counter() - t0))
                 except (L.GxError, OSError, ValueError) as e:
                     raise L.GxError('Error "%s" on line %d ("%s")' % (e, lineno, line)) from e
     finally:

@@ -114,21 +114,25 @@ def saveGadget(name, boxLength, particles, cosmology, gadgetVersion=3, nFiles=1,
     types = particles.gadgetType[order]
     nPartPerType = [int(np.count_nonzero(types == t)) for t in range(6)]
     nTotal = len(order)
+    ordered = np.array_equal(order, np.arange(nTotal))    # already type-ordered (one type, or gas last): no gather
+    massT = particles.mass if ordered else particles.mass[order]
     masses = [0.0] * 6
     variableMass = False
     for t in range(6):
         if nPartPerType[t]:
-            m = particles.mass[order][types == t]
+            m = massT[types == t]
             if m.min() != m.max():
                 variableMass = True
             masses[t] = float(m.min())
     if variableMass:
         masses = [0.0] * 6
     nPartPerFile = [nTotal // nFiles] * (nFiles - 1) + [nTotal - (nTotal // nFiles) * (nFiles - 1)]
-    pos = particles.pos[order].astype(out_dtype)
-    vel = particles.vel[order].astype(out_dtype)
+    if ordered:
+        pos, vel = (np.asarray(a, dtype=out_dtype) for a in (particles.pos, particles.vel))
+    else:
+        pos, vel = (a[order].astype(out_dtype) for a in (particles.pos, particles.vel))
+    mass = massT.astype(out_dtype)
     ids = order.astype(np.uint64)
-    mass = particles.mass[order].astype(out_dtype)
     remainingPerType = list(nPartPerType)
     start = 0
     written = []
