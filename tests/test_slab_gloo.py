@@ -220,7 +220,7 @@ def _worker(rank, world, port, n, mode, outdir, overlap=False):
 
 
 @pytest.mark.parametrize("world,n,mode,overlap", [(2, 16, 2, False), (4, 16, 2, False), (2, 8, 0, False), (2, 8, 1, False),
-                                                  (2, 16, 2, True), (4, 16, 2, True)])
+                                                  (2, 16, 2, True), (4, 16, 2, True), (8, 16, 2, True), (8, 16, 1, False)])
 def test_slab_pipeline_matches_single_process_oracle(tmp_path, world, n, mode, overlap):
     """overlap=True: the double-buffered Zeldovich loop (exchange of one component in flight during the neighbouring
     components' passes) must give the same particles as the sequential one."""
