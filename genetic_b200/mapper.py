@@ -342,7 +342,7 @@ class MappedParticles:
     """All particles of a mapper, evaluated level by level on the device and placed in mapper order on the host:
     pos[N,3], vel[N,3] (out_dtype), mass[N], eps[N] (grid type), level[N], cell[N]."""
 
-    def __init__(self, mapper, particleGenerator, cosmology, out_dtype=np.float32, epsNorm=0.01075):
+    def __init__(self, mapper, particleGenerator, cosmology, out_dtype=np.float32, epsNorm=0.01075, chunk=1 << 25):
         lib = L.load()
         lev, cell = mapper.layout()
         scale, self.gadgetType = mapper.attrs()
@@ -360,38 +360,45 @@ class MappedParticles:
             where = np.flatnonzero(lev == level)
             self.mass[where] = particle_mass(grid, cosmology, scale[where])
             self.eps[where] = particle_eps(grid, epsNorm)
-            m = len(where)
-            if m == 0:
+            if len(where) == 0:
                 continue
-            cells = np.ascontiguousarray(cell[where])
             psis = particleGenerator.getGeneratorForLevel(level).getGeneratedFields()
+            for axis in range(3):
+                if psis[axis].isFourier():
+                    psis[axis].toReal()
             ratio = cosmology.zeldovichVelocityToOffsetRatio(grid.dtype)
-            dcells, dpos, dvel = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            lib.gx_malloc(C.byref(dcells), cells.nbytes)
-            lib.gx_malloc(C.byref(dpos), m * 3 * esz)
-            lib.gx_malloc(C.byref(dvel), m * 3 * esz)
-            try:
-                lib.gx_memcpy_h2d(dcells, cells.ctypes.data_as(C.c_void_p), cells.nbytes, None)
-                for axis in range(3):
-                    if psis[axis].isFourier():
-                        psis[axis].toReal()
-                    lib.gx_emit_cells(psis[axis].ptr, grid.size, psis[axis].dt, axis, float(grid.cellSize),
-                                      float(grid.offsetLower[axis]), float(grid.periodicDomainSize), ratio, dcells, m,
-                                      C.c_void_p(dpos.value + axis * esz), C.c_void_p(dvel.value + axis * esz), odt, 3,
-                                      None)
-                p = np.empty((m, 3), dtype=out_dtype)
-                v = np.empty((m, 3), dtype=out_dtype)
-                lib.gx_memcpy_d2h(p.ctypes.data_as(C.c_void_p), dpos, p.nbytes, None)
-                lib.gx_memcpy_d2h(v.ctypes.data_as(C.c_void_p), dvel, v.nbytes, None)
-                lib.gx_synchronize(None)
-            finally:
-                lib.gx_free(dcells)
-                lib.gx_free(dpos)
-                lib.gx_free(dvel)
-            # the mapper's levels are contiguous runs in practice; a general index assignment covers every case
-            if where[-1] - where[0] + 1 == m:
-                self.pos[where[0]:where[0] + m] = p
-                self.vel[where[0]:where[0] + m] = v
-            else:
-                self.pos[where] = p
-                self.vel[where] = v
+            contiguous_out = where[-1] - where[0] + 1 == len(where)     # the mapper's levels are runs in practice
+            for c0 in range(0, len(where), chunk):                       # bounded device staging
+                w = where[c0:c0 + chunk]
+                m = len(w)
+                cells = np.ascontiguousarray(cell[w])
+                is_range = int(cells[-1]) - int(cells[0]) + 1 == m and (m == 1 or bool(np.all(np.diff(cells) == 1)))
+                dcells, dpos, dvel = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                lib.gx_malloc(C.byref(dpos), m * 3 * esz)
+                lib.gx_malloc(C.byref(dvel), m * 3 * esz)
+                try:
+                    if not is_range:
+                        lib.gx_malloc(C.byref(dcells), cells.nbytes)
+                        lib.gx_memcpy_h2d(dcells, cells.ctypes.data_as(C.c_void_p), cells.nbytes, None)
+                    for axis in range(3):
+                        geo = (psis[axis].ptr, grid.size, psis[axis].dt, axis, float(grid.cellSize),
+                               float(grid.offsetLower[axis]), float(grid.periodicDomainSize), ratio)
+                        out = (C.c_void_p(dpos.value + axis * esz), C.c_void_p(dvel.value + axis * esz), odt, 3)
+                        if is_range:     # a whole level, or the unzoomed stretch of one: no cell list needed
+                            lib.gx_emit_component(*geo, *out, int(cells[0]), m, None)
+                        else:
+                            lib.gx_emit_cells(*geo, dcells, m, *out, None)
+                    if contiguous_out:
+                        p, v = self.pos[w[0]:w[0] + m], self.vel[w[0]:w[0] + m]
+                    else:
+                        p, v = np.empty((m, 3), dtype=out_dtype), np.empty((m, 3), dtype=out_dtype)
+                    lib.gx_memcpy_d2h(p.ctypes.data_as(C.c_void_p), dpos, p.nbytes, None)
+                    lib.gx_memcpy_d2h(v.ctypes.data_as(C.c_void_p), dvel, v.nbytes, None)
+                    lib.gx_synchronize(None)
+                    if not contiguous_out:
+                        self.pos[w], self.vel[w] = p, v
+                finally:
+                    if dcells.value:
+                        lib.gx_free(dcells)
+                    lib.gx_free(dpos)
+                    lib.gx_free(dvel)

@@ -47,3 +47,29 @@ def test_gadget_zoom_goldens_10b_10c(tmp_path, golden_dir, test, types):
         assert np.array_equal(ours["mass"][idx], gold["mass"])
     else:
         assert "mass" not in ours
+
+
+def test_chunked_evaluation_equals_one_shot(golden_dir):
+    """MappedParticles stages bounded chunks on the device (id ranges through gx_emit_component, scattered cells through
+    gx_emit_cells): any chunk size gives the same particles, also for an interleaved (non-contiguous) layout."""
+    camb = os.path.join(golden_dir, "camb_transfer_kmax40_z0.dat")
+    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99, OmegaBaryons0=0.04)
+    ctx = GM.MultiLevelGrid()
+    ctx.addLevel(gb.Grid(40.0, 16))
+    ctx.setPowerspectrumGenerator("all", gb.CAMB(cos, camb, "all"))
+    Z.selectSphere(ctx, (20, 21, 19), 6)
+    Z.initZoomGrid(ctx, 2, 16)
+    field = GM.draw(ctx, 77)
+    field.applyPowerSpectrumFor(GM.ALL)
+    gen = GM.MultiLevelParticleGenerator(field)
+    mapper = PM.updateParticleMapper(ctx, None, cos, baryonsOnAllLevels=True, gasFirst=True)
+    a = PM.MappedParticles(mapper, gen, cos, out_dtype=np.float64)
+    b = PM.MappedParticles(mapper, gen, cos, out_dtype=np.float64, chunk=777)
+    for k in ("pos", "vel", "mass", "eps", "gadgetType", "isGas"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    # gas first on all levels: level 0 appears twice in the layout (gas, then dark matter) -> not one contiguous run
+    lev = a.level
+    assert np.count_nonzero(np.diff(lev) != 0) >= 3
+    n0 = 16 ** 3 - len(ctx.zoomParticleArray[0])
+    assert np.array_equal(a.pos[:n0], a.pos[mapper.size_gas():mapper.size_gas() + n0])   # same cells, two species
+    assert np.all(a.mass[:n0] < a.mass[mapper.size_gas():mapper.size_gas() + n0])

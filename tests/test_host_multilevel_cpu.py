@@ -66,3 +66,4 @@ def _mock_spectrum_for_icgen(monkeypatch, mock_device):
 for _name in dir(_pf):
     if _name.startswith("test_"):
         globals()["test_paramfile_" + _name[5:]] = getattr(_pf, _name)
+test_chunked_evaluation_equals_one_shot = _mapper_cases.test_chunked_evaluation_equals_one_shot
