@@ -309,7 +309,9 @@ static int run_gather(void *dst, int n_dst, const void *src, int n_src, const De
 
 static int check_desc(const gx_grid_desc *g, const char *who) {
   if (!g) return fail(std::string(who) + ": null grid descriptor");
-  if (g->n < 4 || g->n > 4096 || !is_pow2(g->n)) return fail(std::string(who) + ": grid size must be a power of two in [4,4096]");
+  // real-space gathers with per-axis tables: any even size (virtual super/subsampled grids of the particle mappers are
+  // e.g. 3 x 32 = 96 cells); only the transforms need powers of two
+  if (g->n < 4 || g->n > 4096 || (g->n & 1)) return fail(std::string(who) + ": grid size must be even and in [4,4096]");
   if (!(g->cell_size > 0) || !(g->domain_size > 0)) return fail(std::string(who) + ": cell and domain size must be positive");
   return 0;
 }

@@ -65,6 +65,19 @@ class Grid:
         self.simEquivalentSize = int(round(float(simsize) / float(self.cellSize)))  # grid.hpp:111
         self.flags = np.zeros(0, dtype=np.int64)  # sorted flagged cell indices (Grid::flagCells / getFlaggedCells)
         self._mask = None
+        self.cellMassFrac = T(math.pow(float(T(self.cellSize / T(simsize))), 3.0))   # grid.hpp:112
+        self.cellSofteningScale = T(1.0)
+        self.base = self                          # the stored grid a virtual grid is a view of
+
+    # virtual views used by the particle mappers (virtualgrid.hpp): same cells at another resolution / mass
+    def makeSupersampled(self, ratio):
+        return VirtualGrid(self, "super", int(ratio))
+
+    def makeSubsampled(self, ratio):
+        return VirtualGrid(self, "sub", int(ratio))
+
+    def makeScaledMassVersion(self, massScale):
+        return VirtualGrid(self, "mass", massScale)
 
     def getFourierKmin(self):
         return self.kMin
@@ -107,6 +120,95 @@ class Grid:
 
     def coversFullSimulation(self):
         return self.periodicDomainSize == self.thisGridSize
+
+
+class VirtualGrid(Grid):
+    """grids::SuperSampleGrid / SubSampleGrid / MassScaledGrid (virtualgrid.hpp:125-182, 520-616, 657-676): metadata of a
+    view of `underlying`; flags are proxied to the stored grid (scaled up or down), fields are evaluated by tricubic
+    interpolation (super) or sub-cell averaging (sub) of the stored grid's field."""
+
+    def __init__(self, underlying, kind, arg):
+        T = underlying.dtype.type
+        u = underlying
+        if kind == "super":
+            n, dx = u.size * arg, T(u.cellSize / T(arg))
+            frac, soft = T(u.cellMassFrac / T(arg * arg * arg)), T(arg)      # (sic: the factor is passed as softening scale)
+        elif kind == "sub":
+            if u.size % arg:
+                raise L.GxError("subsampling factor does not divide the grid size")
+            n, dx = u.size // arg, T(u.cellSize * T(arg))
+            frac, soft = T(u.cellMassFrac * T(math.pow(float(arg), 3.0))), u.cellSofteningScale
+        elif kind == "mass":
+            n, dx = u.size, u.cellSize
+            frac, soft = T(T(arg) * u.cellMassFrac), u.cellSofteningScale
+        else:
+            raise ValueError(kind)
+        Grid.__init__(self, u.periodicDomainSize, n, dx=dx, x0=u.offsetLower[0], y0=u.offsetLower[1], z0=u.offsetLower[2],
+                      dtype=u.dtype)
+        self.underlying, self.kind, self.arg, self.base = u, kind, arg, u.base
+        self.cellMassFrac, self.cellSofteningScale = frac, soft
+
+    # resolution of this view relative to the stored grid, as (up, down) integer factors
+    def resolution(self):
+        up, down = self.underlying.resolution() if isinstance(self.underlying, VirtualGrid) else (1, 1)
+        if self.kind == "super":
+            up *= self.arg
+        elif self.kind == "sub":
+            down *= self.arg
+        return up, down
+
+    def makeSupersampled(self, ratio):
+        if self.kind == "super":
+            return self.underlying.makeSupersampled(ratio * self.arg)
+        if self.kind == "sub":
+            if ratio > self.arg:
+                return self.underlying.makeSupersampled(_int_ratio(ratio, self.arg))
+            if ratio == self.arg:
+                return self.underlying
+            return self.underlying.makeSubsampled(_int_ratio(self.arg, ratio))
+        return VirtualGrid(self, "super", int(ratio))
+
+    def makeSubsampled(self, ratio):
+        if self.kind == "sub":
+            return self.underlying.makeSubsampled(ratio * self.arg)
+        if self.kind == "super":
+            if ratio > self.arg:
+                return self.underlying.makeSubsampled(_int_ratio(ratio, self.arg))
+            if ratio == self.arg:
+                return self.underlying
+            return self.underlying.makeSupersampled(_int_ratio(self.arg, ratio))
+        return VirtualGrid(self, "sub", int(ratio))
+
+    def _scale(self, cells, src_n, dst_n):
+        """Grid::upscaleCellFlagVector / downscaleCellFlagVector (grid.hpp:384-436)."""
+        cells = np.asarray(cells, dtype=np.int64)
+        c = np.stack(np.unravel_index(cells, (src_n,) * 3), axis=0)
+        if dst_n >= src_n:
+            f = dst_n // src_n
+            o = np.arange(f, dtype=np.int64)
+            x = c[0][:, None, None, None] * f + o[None, :, None, None]
+            y = c[1][:, None, None, None] * f + o[None, None, :, None]
+            z = c[2][:, None, None, None] * f + o[None, None, None, :]
+            return ((x * dst_n + y) * dst_n + z).reshape(-1)
+        f = src_n // dst_n
+        return np.unique(((c[0] // f) * dst_n + (c[1] // f)) * dst_n + (c[2] // f))
+
+    def getFlaggedCells(self):
+        u = self.underlying.getFlaggedCells()
+        return u if self.kind == "mass" else self._scale(u, self.underlying.size, self.size)
+
+    def flagCells(self, indices, append=False):
+        ids = np.asarray(indices, dtype=np.int64).reshape(-1)
+        self.underlying.flagCells(ids if self.kind == "mass" else self._scale(ids, self.size, self.underlying.size), append)
+
+    def unflagAllCells(self):
+        self.underlying.unflagAllCells()
+
+
+def _int_ratio(a, b):
+    if a % b:
+        raise L.GxError("The ratio of sub/supersampling factors is not an integer")
+    return a // b
 
 
 class Field:

@@ -6,7 +6,7 @@ comment line, surplus tokens are ignored, an error aborts the run with the refer
 
 Everything numerical is sequencing over the C ABI (host.py / multilevel.py / zoom.py / mapper.py / output.py); this file
 holds only the state machine of ICGenerator. Commands outside the accelerated path raise "not supported" errors instead
-of being silently ignored: grafic / HDF5 / swift output, sub/supersampling, strays, autopad, adapt_mask, masks,
+of being silently ignored: grafic / HDF5 / swift output, strays, autopad, masks,
 mapper_relative_to, baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
 """
 import math
@@ -42,6 +42,8 @@ class ICGenerator:
         self.nGadgetFiles = 1
         self.mruGadgetType, self.gadgetTypesForLevels, self.usedGadgetParticleTypes = 1, [], [False] * 6
         self.baryonsOnAllLevels = False
+        self.supersample = self.subsample = self.supersampleGas = 1
+        self.flaggedGadgetParticleType, self._flaggedCellsForType = None, None
         self.epsNorm = 0.01075
         self.x0 = self.y0 = self.z0 = 0.0
         self.variance_filterscale = -1.0
@@ -91,9 +93,12 @@ class ICGenerator:
             "baryons_all_levels": (self.setBaryonsOnAllLevels,),
             "velocity_offset": (self.setOffset, f, f, f),
         }
-        for name in ("strays_on", "supersample", "supersample_gas", "subsample", "num_neighbors", "num_neighbours", "pvar",
-                     "center_grafic_output", "centre_output", "center_output", "gadget_flagged_particle_type",
-                     "mapper_relative_to", "adapt_mask", "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
+        r.update({"adapt_mask": (self.adaptMask, i), "gadget_flagged_particle_type": (self.setFlaggedGadgetParticleType, i),
+                  "supersample": (self.setSupersample, i), "subsample": (self.setSubsample, i),
+                  "supersample_gas": (self.setSupersampleGas, i)})
+        for name in ("strays_on", "num_neighbors", "num_neighbours", "pvar",
+                     "center_grafic_output", "centre_output", "center_output",
+                     "mapper_relative_to", "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
                      "dump_ps_field", "dump_tipsy_field", "dump_mask", "import_level",
                      "baryon_tf_on", "zero_level_field", "reverse_small_k"):
             r[name] = (self._unsupported(name),)
@@ -148,6 +153,21 @@ class ICGenerator:
 
     def setEpsNorm(self, v):
         self.epsNorm = v
+
+    def setSupersample(self, factor):
+        if factor <= 1:
+            raise L.GxError("Supersampling factor must be greater then one")
+        self.supersample = factor
+
+    def setSupersampleGas(self, factor):
+        if factor <= 1:
+            raise L.GxError("Supersampling factor must be greater then one")
+        self.supersampleGas = factor
+
+    def setSubsample(self, factor):
+        if factor <= 0:
+            raise L.GxError("Subsampling factor must be greater then zero")
+        self.subsample = factor
 
     def setBaryonsOnAllLevels(self):
         self.baryonsOnAllLevels = True
@@ -290,11 +310,15 @@ class ICGenerator:
         # the reference rebuilds the mapper whenever one of these changes (updateParticleMapper call sites); here it is
         # rebuilt on demand and kept while they stay the same
         key = (self.context.getNumLevels(), tuple(self.gadgetTypesForLevels), float(self.cosmology.OmegaBaryons0),
-               float(self.cosmology.OmegaM0), self.baryonsOnAllLevels, gasFirst,
-               tuple(id(z) for z in self.context.zoomParticleArray))
+               float(self.cosmology.OmegaM0), self.baryonsOnAllLevels, gasFirst, self.supersample, self.subsample,
+               self.supersampleGas, self.flaggedGadgetParticleType, tuple(id(z) for z in self.context.zoomParticleArray))
         if getattr(self, "_mapper_key", None) != key:
             self._mapper_cache = PM.updateParticleMapper(self.context, self.gadgetTypesForLevels, self.cosmology,
-                                                         self.baryonsOnAllLevels, gasFirst=gasFirst)
+                                                         self.baryonsOnAllLevels, gasFirst=gasFirst,
+                                                         supersample=self.supersample, subsample=self.subsample,
+                                                         supersampleGas=self.supersampleGas,
+                                                         flaggedGadgetParticleType=self.flaggedGadgetParticleType,
+                                                         flaggedCells=self._flaggedCellsForType)
             self._mapper_key = key
         return self._mapper_cache
 
@@ -352,26 +376,56 @@ class ICGenerator:
         Z.selectNearest(self.context, self._centre())
 
     def expandFlaggedRegion(self, nCells):
-        """ic.hpp:1527-1543 over Grid::expandFlaggedRegion (grid.hpp:277-306): flags the +-1 neighbours along x, y, z in
-        turn, nCells times, with periodic wrapping of the cell coordinates."""
+        """ic.hpp:1527-1543."""
         if self.context.getNumLevels() < 1:
             raise L.GxError("No grid has yet been initialised")
         self.log("Expand flagged region by %d cells" % nCells)
         for level, g in enumerate(self.context.grids):
             before = len(g.getFlaggedCells())
-            flags = g.getFlaggedCells()
-            n = g.size
-            for _ in range(nCells):
-                for axis in range(3):
-                    c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0)
-                    out = [flags]
-                    for step in (1, -1):
-                        d = c.copy()
-                        d[axis] = (d[axis] + step) % n
-                        out.append(np.ravel_multi_index(tuple(d), (n, n, n)))
-                    flags = np.unique(np.concatenate(out))
+            flags = self._expanded(g.getFlaggedCells(), g.size, nCells)
             g.flagCells(flags)
             self.log("  - level %d increased number of flagged cells by %d (now %d)" % (level, len(flags) - before, len(flags)))
+
+    @staticmethod
+    def _expanded(flags, n, nCells):
+        """Grid::expandFlaggedRegion (grid.hpp:277-306): the +-1 neighbours along each axis, nCells times."""
+        flags = np.asarray(flags, dtype=np.int64)
+        for _ in range(nCells):
+            for axis in range(3):
+                c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0)
+                out = [flags]
+                for step in (1, -1):
+                    d = c.copy()
+                    d[axis] = (d[axis] + step) % n
+                    out.append(np.ravel_multi_index(tuple(d), (n, n, n)))
+                flags = np.unique(np.concatenate(out))
+        return flags
+
+    def adaptMask(self, nPadCells):
+        """ic.hpp:1545-1575: working up from the deepest zoom, the cells each level replaces become the footprint of the
+        level below's zoom cells on it, padded by nPadCells."""
+        nl = self.context.getNumLevels()
+        if nl < 3:
+            raise L.GxError("Adapting the mask requires there to be more than one zoom level")
+        z = self.context.zoomParticleArray
+        for level in range(nl - 2, 0, -1):
+            this, above = self.context.getGridForLevel(level), self.context.getGridForLevel(level - 1)
+            ratio = int(round(float(above.cellSize) / float(this.cellSize)))
+            corner = [int(round(float(this.offsetLower[a] - above.offsetLower[a]) / float(above.cellSize))) for a in range(3)]
+            c = np.unravel_index(np.asarray(z[level], dtype=np.int64), (this.size,) * 3)
+            up = [corner[a] + c[a] // ratio for a in range(3)]               # makeProxyGridToMatch: section + subsample
+            cells = np.unique((up[0] * above.size + up[1]) * above.size + up[2])
+            z[level - 1] = self._expanded(cells, above.size, nPadCells)
+
+    def setFlaggedGadgetParticleType(self, t):
+        """ic.hpp:703-714: the flagged cells of the finest level become a separate gadget particle type."""
+        if t >= 6 or t < 0:
+            raise L.GxError("Gadget particle type must be between 0 and 5")
+        if self.usedGadgetParticleTypes[t]:
+            raise L.GxError("Cannot reuse a gadget particle type; this type was already used in a different section of the ICs")
+        self.flaggedGadgetParticleType = t
+        self.usedGadgetParticleTypes[t] = True
+        self._flaggedCellsForType = self.context.getGridForLevel(self.context.getNumLevels() - 1).getFlaggedCells().copy()
 
     # ---- random component, modifications (ic.hpp:1333-1346,1589-1745) ------------------------------------------------
     def initialiseRandomComponentIfUninitialised(self):

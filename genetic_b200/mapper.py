@@ -16,20 +16,25 @@ component (gx_emit_cells). Gas: AddGasMapper over splitMass (gasmapper.hpp). Not
 stray particles, the grafic mapper.
 """
 import ctypes as C
+import itertools
 import math
 
 import numpy as np
 
 from . import lib as L
-from .host import _dt
+from .host import _dt, Field
+
+
+_layer_ids = itertools.count()
 
 
 class OneLevelParticleMapper:
-    """onelevelmapper.hpp: every cell of one grid, in cell-index order."""
+    """onelevelmapper.hpp: every cell of one grid, in cell-index order. `grid` may be a virtual view (host.VirtualGrid:
+    super/subsampled or mass-scaled) of the stored grid of `level`; every instance is one *layer* of a layout."""
 
-    def __init__(self, grid, level, gadgetParticleType=1, massScale=None):
-        # massScale: the MassScaledGrid view of `grid` (virtualgrid.hpp:657-676) that splitMass creates for gas / dark matter
-        self.grid, self.level, self.gadgetParticleType, self.massScale = grid, level, gadgetParticleType, massScale
+    def __init__(self, grid, level, gadgetParticleType=1):
+        self.grid, self.level, self.gadgetParticleType = grid, level, gadgetParticleType
+        self.layer = next(_layer_ids)
 
     def size(self):
         return self.grid.size3
@@ -40,31 +45,40 @@ class OneLevelParticleMapper:
     def getCoarsestGrid(self):
         return self.grid
 
-    def getFinestLevel(self):
-        return self.level
+    def getFinestLayer(self):
+        return self.layer
+
+    def layers(self):
+        return {self.layer: self}
 
     def grids(self):
-        return {self.level: self.grid}
+        return {self.layer: self.grid}
 
     def layout(self):
-        return (np.full(self.grid.size3, self.level, dtype=np.int32), np.arange(self.grid.size3, dtype=np.int64))
+        return (np.full(self.grid.size3, self.layer, dtype=np.int32), np.arange(self.grid.size3, dtype=np.int64))
 
     def attrs(self):
-        """Per particle: the mass scale of its (virtual) grid and its gadget type."""
-        T = self.grid.dtype.type
-        return (np.full(self.grid.size3, T(1) if self.massScale is None else T(self.massScale), dtype=self.grid.dtype),
-                np.full(self.grid.size3, self.gadgetParticleType, dtype=np.int32))
+        """Per particle: its gadget type."""
+        return (np.full(self.grid.size3, self.gadgetParticleType, dtype=np.int32),)
 
     def size_gas(self):
         return 0
 
-    def splitMass(self, massRatio, toLevels):
-        """onelevelmapper.hpp:155-173: (gas mapper or None, dark-matter mapper)."""
+    def splitMass(self, massRatio, toGrids):
+        """onelevelmapper.hpp:155-173: (gas mapper or None, dark-matter mapper) on mass-scaled views of the grid."""
         T = self.grid.dtype.type
-        if self.level in toLevels:
-            return (OneLevelParticleMapper(self.grid, self.level, 0, T(massRatio)),
-                    OneLevelParticleMapper(self.grid, self.level, self.gadgetParticleType, T(T(1.0) - T(massRatio))))
-        return None, OneLevelParticleMapper(self.grid, self.level, self.gadgetParticleType, self.massScale)
+        if any(self.grid.base is g for g in toGrids):
+            return (OneLevelParticleMapper(self.grid.makeScaledMassVersion(T(massRatio)), self.level, 0),
+                    OneLevelParticleMapper(self.grid.makeScaledMassVersion(T(T(1.0) - T(massRatio))), self.level,
+                                           self.gadgetParticleType))
+        return None, OneLevelParticleMapper(self.grid, self.level, self.gadgetParticleType)
+
+    def superOrSubSample(self, ratio, toGrids, super_):
+        """onelevelmapper.hpp:179-195."""
+        g = self.grid
+        if any(g.base is t for t in toGrids):
+            g = g.makeSupersampled(ratio) if super_ else g.makeSubsampled(ratio)
+        return OneLevelParticleMapper(g, self.level, self.gadgetParticleType)
 
     def unflagAllParticles(self):
         self.grid.unflagAllCells()
@@ -126,7 +140,7 @@ class TwoLevelParticleMapper:
         if len(self.level1CellsToReplace) == 0:
             raise L.GxError("TwoLevelParticleMapper: no cells to replace")
         lev, cell = pLevel1.layout()
-        on_finest = np.flatnonzero(lev == pLevel1.getFinestLevel())
+        on_finest = np.flatnonzero(lev == pLevel1.getFinestLayer())
         hit = np.isin(cell[on_finest], self.level1CellsToReplace)
         self.level1ParticlesToReplace = on_finest[hit]           # ascending particle ids of level 1
         if len(self.level1ParticlesToReplace) != len(self.level1CellsToReplace):
@@ -151,7 +165,7 @@ class TwoLevelParticleMapper:
         if skipLevel1:
             keep[:] = False
         self._keep = keep
-        self._layout = (np.concatenate([lev[keep], np.full(len(self.zoomParticleArrayHiresUnsorted), pLevel2.level, np.int32)]),
+        self._layout = (np.concatenate([lev[keep], np.full(len(self.zoomParticleArrayHiresUnsorted), pLevel2.layer, np.int32)]),
                         np.concatenate([cell[keep], self.zoomParticleArrayHiresUnsorted]))
 
     def size(self):
@@ -163,13 +177,16 @@ class TwoLevelParticleMapper:
     def getCoarsestGrid(self):
         return self.pLevel1.getCoarsestGrid()
 
-    def getFinestLevel(self):
-        return self.pLevel2.level
+    def getFinestLayer(self):
+        return self.pLevel2.layer
+
+    def layers(self):
+        g = dict(self.pLevel1.layers())
+        g.update(self.pLevel2.layers())
+        return g
 
     def grids(self):
-        g = dict(self.pLevel1.grids())
-        g.update(self.pLevel2.grids())
-        return g
+        return {k: m.grid for k, m in self.layers().items()}
 
     def layout(self):
         return self._layout
@@ -181,11 +198,27 @@ class TwoLevelParticleMapper:
     def size_gas(self):
         return 0
 
-    def splitMass(self, massRatio, toLevels):
+    def superOrSubSample(self, ratio, toGrids, super_):
+        """twolevelmapper.hpp:568-591: both sub-mappers are resampled and the cells to replace are re-expressed on the new
+        finest level-1 grid through the flags (virtual grids scale them), which leaves exactly those cells flagged."""
+        subLR = self.pLevel1.superOrSubSample(ratio, toGrids, super_)
+        subHR = self.pLevel2.superOrSubSample(ratio, toGrids, super_)
+        subLR.unflagAllParticles()
+        self.pLevel1.flagParticles(self.level1ParticlesToReplace)
+        newCells = subLR.getFinestGrid().getFlaggedCells()
+        try:
+            return TwoLevelParticleMapper(subLR, subHR, newCells, self.skipLevel1)
+        except L.GxError as e:
+            if "outside high resolution grid" in str(e):
+                raise L.GxError("Following sub/super-sampling, the zoom particles no longer fit fully on their grids. Try "
+                                "rerunning with strays_on, or (better) increase the size of the zoom region.") from e
+            raise
+
+    def splitMass(self, massRatio, toGrids):
         """twolevelmapper.hpp:519-553: gas exists only where level 2 (and possibly level 1) was asked to carry it; a level
         1 without gas is kept as the notional (skipped) low-resolution part of the gas mapper."""
-        gas1, dm1 = self.pLevel1.splitMass(massRatio, toLevels)
-        gas2, dm2 = self.pLevel2.splitMass(massRatio, toLevels)
+        gas1, dm1 = self.pLevel1.splitMass(massRatio, toGrids)
+        gas2, dm2 = self.pLevel2.splitMass(massRatio, toGrids)
         newskip = self.skipLevel1
         if gas1 is None:
             gas1, newskip = self.pLevel1, True
@@ -243,9 +276,9 @@ class AddGasMapper:
         self.nFirst, self.nSecond = pFirst.size(), pSecond.size()
         gas, dm = (pFirst, pSecond) if gasFirst else (pSecond, pFirst)
         self.gasMap, self.dmMap = gas, dm
-        if (gas.attrs()[1] != 0).any():
+        if (gas.attrs()[0] != 0).any():
             raise L.GxError("AddGasMapper: the gas mapper holds particles of a gadget type other than 0")
-        if (dm.attrs()[1] == 0).any():
+        if (dm.attrs()[0] == 0).any():
             raise L.GxError("You have asked for some gadget DM particles to be output with type 0, but have also set "
                             "non-zero baryon density. Type 0 is reserved for gas particles in hydro simulations, and "
                             "genetIC particle types refer only to the dark matter part of the output.")
@@ -265,10 +298,13 @@ class AddGasMapper:
     def getCoarsestGrid(self):
         return self.dmMap.getCoarsestGrid()
 
-    def grids(self):
-        g = dict(self.firstMap.grids())
-        g.update(self.secondMap.grids())
+    def layers(self):
+        g = dict(self.firstMap.layers())
+        g.update(self.secondMap.layers())
         return g
+
+    def grids(self):
+        return {k: m.grid for k, m in self.layers().items()}
 
     def layout(self):
         return tuple(np.concatenate([a, b]) for a, b in zip(self.firstMap.layout(), self.secondMap.layout()))
@@ -301,41 +337,51 @@ class AddGasMapper:
         return self.firstMap.getFlaggedParticles()
 
 
-def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, baryonsOnAllLevels=False, gasFirst=False):
-    """ICGenerator::updateParticleMapper (ic.hpp:1129-1221) without sub/supersampling and padding: the one-level mapper of
-    the base grid, wrapped once per zoom level with that level's zoomParticleArray (stored on the context by
-    zoom.initZoomGrid); with OmegaBaryons0 > 0 the mass is split into a gas mapper (deepest level only unless
-    baryonsOnAllLevels) and a dark-matter mapper, gas first for tipsy and last for gadget."""
+def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, baryonsOnAllLevels=False, gasFirst=False,
+                         supersample=1, subsample=1, supersampleGas=1, flaggedGadgetParticleType=None, flaggedCells=None):
+    """ICGenerator::updateParticleMapper (ic.hpp:1129-1236) without padding and strays: the one-level mapper of the base
+    grid, wrapped once per zoom level with that level's zoomParticleArray (stored on the context by zoom.initZoomGrid);
+    with OmegaBaryons0 > 0 the mass is split into a gas mapper (deepest level only unless baryonsOnAllLevels) and a
+    dark-matter mapper, gas first for tipsy and last for gadget; `supersample` refines the deepest level, `subsample`
+    coarsens the base level (superOrSubSample, ic.hpp:1223-1234)."""
     nl = context.getNumLevels()
     types = list(gadgetTypesForLevels) if gadgetTypesForLevels is not None else [1] * nl
     m = OneLevelParticleMapper(context.getGridForLevel(0), 0, types[0])
     for level in range(1, nl):
         fine = OneLevelParticleMapper(context.getGridForLevel(level), level, types[level])
         m = TwoLevelParticleMapper(m, fine, context.zoomParticleArray[level - 1])
+    if flaggedGadgetParticleType is not None:       # ic.hpp:1176-1186: the flagged cells of the finest grid, retyped
+        flagged = OneLevelParticleMapper(context.getGridForLevel(nl - 1), nl - 1, flaggedGadgetParticleType)
+        m = TwoLevelParticleMapper(m, flagged, flaggedCells)
+
+    def resample(mp, sup, sub):
+        if sup > 1:
+            mp = mp.superOrSubSample(sup, [context.getGridForLevel(nl - 1)], True)
+        if sub > 1:
+            mp = mp.superOrSubSample(sub, [context.getGridForLevel(0)], False)
+        return mp
+
     if cosmology is not None and cosmology.OmegaBaryons0 > 0:
         T = context.getGridForLevel(0).dtype.type
         gas, dm = m.splitMass(T(T(cosmology.OmegaBaryons0) / T(cosmology.OmegaM0)),
-                              list(range(nl)) if baryonsOnAllLevels else [nl - 1])
-        m = AddGasMapper(gas, dm, True) if gasFirst else AddGasMapper(dm, gas, False)
-    return m
+                              list(context.grids) if baryonsOnAllLevels else [context.getGridForLevel(nl - 1)])
+        gas, dm = resample(gas, supersampleGas, 1), resample(dm, supersample, subsample)
+        return AddGasMapper(gas, dm, True) if gasFirst else AddGasMapper(dm, gas, False)
+    return resample(m, supersample, subsample)
 
 
-def particle_mass(grid, cosmology, massScale=None):
-    """ZeldovichParticleEvaluator::getMass (zeldovich.hpp:55-62,108-110): boxMass * cellMassFrac, cellMassFrac =
-    pow(dx / simsize, 3) (grid.hpp:112), times the mass scale of a MassScaledGrid (virtualgrid.hpp:672), in the grid's type.
-    massScale may be an array (one entry per particle)."""
+def particle_mass(grid, cosmology):
+    """ZeldovichParticleEvaluator::getMass (zeldovich.hpp:55-62,108-110): boxMass * cellMassFrac; cellMassFrac =
+    pow(dx / simsize, 3) for a stored grid (grid.hpp:112), rescaled by the virtual views (virtualgrid.hpp:145,544,672)."""
     T = grid.dtype.type
     boxMass = T(T(27.744948) * T(cosmology.OmegaM0)) * T(math.pow(float(grid.periodicDomainSize), 3.0))
-    frac = T(math.pow(float(T(grid.cellSize / grid.periodicDomainSize)), 3.0))
-    if massScale is None:
-        return T(boxMass * frac)
-    return boxMass * (np.asarray(massScale, dtype=grid.dtype) * frac)
+    return T(boxMass * grid.cellMassFrac)
 
 
 def particle_eps(grid, epsNorm=0.01075):
-    """getEps (zeldovich.hpp:113-115): cellSize * cellSofteningScale(=1) * epsNorm."""
+    """getEps (zeldovich.hpp:113-115): cellSize * cellSofteningScale * epsNorm."""
     T = grid.dtype.type
-    return T(T(grid.cellSize * T(1.0)) * T(epsNorm))
+    return T(T(grid.cellSize * grid.cellSofteningScale) * T(epsNorm))
 
 
 class MappedParticles:
@@ -345,27 +391,45 @@ class MappedParticles:
     def __init__(self, mapper, particleGenerator, cosmology, out_dtype=np.float32, epsNorm=0.01075, chunk=1 << 25):
         lib = L.load()
         lev, cell = mapper.layout()
-        scale, self.gadgetType = mapper.attrs()
+        (self.gadgetType,) = mapper.attrs()
         N = len(lev)
-        self.level, self.cell = lev, cell
+        self.layer, self.cell = lev, cell
+        self.level = np.empty(N, dtype=np.int32)             # the stored level each particle's fields come from
         self.isGas = mapper.isGas() if hasattr(mapper, "isGas") else np.zeros(N, dtype=bool)
         self.pos = np.empty((N, 3), dtype=out_dtype)
         self.vel = np.empty((N, 3), dtype=out_dtype)
-        grids = mapper.grids()
-        T = next(iter(grids.values())).dtype.type
+        layers = mapper.layers()
+        T = next(iter(layers.values())).grid.dtype.type
         self.mass = np.empty(N, dtype=T)
         self.eps = np.empty(N, dtype=T)
         odt, esz = _dt(out_dtype), np.dtype(out_dtype).itemsize
-        for level, grid in grids.items():
-            where = np.flatnonzero(lev == level)
-            self.mass[where] = particle_mass(grid, cosmology, scale[where])
+        resampled = {}
+        for layer, onelevel in layers.items():
+            grid, level = onelevel.grid, onelevel.level
+            where = np.flatnonzero(lev == layer)
+            self.mass[where] = particle_mass(grid, cosmology)
             self.eps[where] = particle_eps(grid, epsNorm)
+            self.level[where] = level
             if len(where) == 0:
                 continue
             psis = particleGenerator.getGeneratorForLevel(level).getGeneratedFields()
             for axis in range(3):
                 if psis[axis].isFourier():
                     psis[axis].toReal()
+            res = grid.resolution() if hasattr(grid, "resolution") else (1, 1)
+            if res != (1, 1):
+                # Super/SubSampleEvaluator (evaluator.hpp:96-205): the stored offsets interpolated tricubically at the
+                # centres of a finer virtual grid, or averaged over the sub-cells of a coarser one -- the same cross-grid
+                # kernels that combine the levels, writing a field on the virtual grid
+                key = (level,) + res
+                if key not in resampled:
+                    out = []
+                    for axis in range(3):
+                        v = Field(grid, fourier=False, stream=psis[axis].stream)
+                        v.addFieldFromDifferentGrid(psis[axis])
+                        out.append(v)
+                    resampled[key] = out
+                psis = resampled[key]
             ratio = cosmology.zeldovichVelocityToOffsetRatio(grid.dtype)
             contiguous_out = where[-1] - where[0] + 1 == len(where)     # the mapper's levels are runs in practice
             for c0 in range(0, len(where), chunk):                       # bounded device staging

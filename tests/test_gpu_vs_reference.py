@@ -87,7 +87,8 @@ def test_zoom_with_modifications_matches_the_reference_binary(tmp_path, golden_d
 
 @pytest.mark.parametrize("case", ["tipsy_two_levels", "tipsy_three_levels", "gadget2_three_levels",
                                   "gadget3_types_two_files", "gadget3_trimmed_window", "tipsy_gas", "gadget3_gas",
-                                  "gadget2_gas_all_levels"])
+                                  "gadget2_gas_all_levels", "tipsy_supersample2", "gadget3_subsample2_supersample3",
+                                  "tipsy_gas_supersamplegas2_supersample3_three_levels"])
 def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, case):
     """The particle mappers (OneLevel / nested TwoLevel ordering, per-level gadget types, the trimming of the zoom list
     to a user-placed window) and the tipsy / gadget writers: the files written from the device-evaluated particles are
@@ -115,6 +116,10 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     three = "three" in case
     if three:
         pf += "centre 20 33 41\nselect_sphere 3\nzoomgrid 2 32\n"
+    import re as _re
+    resample = {k: int(v) for k, v in _re.findall(r"(supersamplegas|supersample|subsample)(\d)", case)}
+    for k, v in resample.items():
+        pf += "%s %d\n" % ({"supersamplegas": "supersample_gas"}.get(k, k), v)
     out = oracle.run_ref(pf + "done\n", str(tmp_path), [_camb_file(golden_dir)])
     cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99, OmegaBaryons0=0.04 if gas else 0.0)
     ctx = GM.MultiLevelGrid()
@@ -131,7 +136,9 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     field = GM.draw(ctx, 90210)
     field.applyPowerSpectrumFor(GM.ALL)
     gen = GM.MultiLevelParticleGenerator(field)
-    mapper = PM.updateParticleMapper(ctx, types, cos, "all_levels" in case, gasFirst=(fmt == "tipsy"))
+    mapper = PM.updateParticleMapper(ctx, types, cos, "all_levels" in case, gasFirst=(fmt == "tipsy"),
+                                     supersample=resample.get("supersample", 1), subsample=resample.get("subsample", 1),
+                                     supersampleGas=resample.get("supersamplegas", 1))
     assert mapper.size() - mapper.size_gas() == int(re.search(r"number dm particles=(\d+)", out).group(1))
     assert mapper.size_gas() == int(re.search(r"number gas particles=(\d+)", out).group(1))
     ours = tmp_path / "ours"

@@ -32,8 +32,9 @@ def test_idfile_round_trip_golden_mapper_test_01a(golden_dir):
     assert np.array_equal(mapper.getFlaggedParticles(), ref)
     # the special values the reference's paramfile comments on
     lev, cell = mapper.layout()
-    assert (lev[108381], cell[108381]) == (0, 108381) and (lev[108382], cell[108382]) == (0, 108386)
-    assert cell[200000] == 200000 + 1081 and lev[276828] == 1
+    base, zoom = mapper.pLevel1.layer, mapper.pLevel2.layer
+    assert (lev[108381], cell[108381]) == (base, 108381) and (lev[108382], cell[108382]) == (base, 108386)
+    assert cell[200000] == 200000 + 1081 and lev[276828] == zoom
 
 
 def test_mapper_errors():
