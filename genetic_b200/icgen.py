@@ -7,7 +7,7 @@ comment line, surplus tokens are ignored, an error aborts the run with the refer
 Everything numerical is sequencing over the C ABI (host.py / multilevel.py / zoom.py / mapper.py / output.py); this file
 holds only the state machine of ICGenerator. Commands outside the accelerated path raise "not supported" errors instead
 of being silently ignored: grafic / HDF5 / swift output, strays, autopad, masks,
-mapper_relative_to, baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
+baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
 """
 import math
 import os
@@ -24,8 +24,12 @@ from . import multilevel as GM, zoom as Z, mapper as PM, output as OUT
 class ICGenerator:
     """ICGenerator<GridDataType> (ic.hpp:62-1762)."""
 
-    def __init__(self, dtype=np.float64, log=None):
+    def __init__(self, dtype=np.float64, log=None, pUnderlying=None):
         self.dtype = np.dtype(dtype)
+        # DummyICGenerator (dummyic.hpp): run for `mapper_relative_to` to rebuild the geometry (grids, flags, mapper) of
+        # another parameter file; grids that this generator already has are shared, everything touching fields is a no-op
+        self.pUnderlying = pUnderlying
+        self.pInputMapper, self.pInputContext = None, None
         # ic.hpp:196-226
         self.cosmology = CosmologicalParameters(OmegaM0=0.3, OmegaLambda0=None, sigma8=None, redshift=0.0, ns=0.96,
                                                 hubble=0.701, OmegaBaryons0=0.0, TCMB=2.725)
@@ -50,8 +54,17 @@ class ICGenerator:
         self.initial_number_steps, self.precision = 10, 0.001
         self.velOffset = (0.0, 0.0, 0.0)
         self.log = log if log is not None else (lambda msg: print(msg, flush=True))
-        GM.set_logger(self.log)
+        if pUnderlying is None:
+            GM.set_logger(self.log)
         self.commands = self._routes()
+        if pUnderlying is not None:
+            noop = (lambda *a: None)
+            for name in ("zerolevel", "zero_level", "zero_level_field", "dump_grid", "dump_grid_for_field", "dump_ps",
+                         "dump_ps_field", "dump_mask", "dump_idfile", "dump_id_file", "modify", "done",
+                         "apply_modifications", "calculate", "chi2", "reverse", "reverse_small_k", "import_level",
+                         "dump_tipsy", "dump_tipsy_field", "dump_vx", "dump_grid_fourier", "splice"):
+                types = self.commands[name][1:] if name in self.commands and self.commands[name][0].__name__ != "fail" else ()
+                self.commands[name] = (noop,) + tuple(types)
 
     # ---- command table (main.cpp:22-172) ---------------------------------------------------------------------------
     def _routes(self):
@@ -93,12 +106,12 @@ class ICGenerator:
             "baryons_all_levels": (self.setBaryonsOnAllLevels,),
             "velocity_offset": (self.setOffset, f, f, f),
         }
-        r.update({"adapt_mask": (self.adaptMask, i), "gadget_flagged_particle_type": (self.setFlaggedGadgetParticleType, i),
+        r.update({"mapper_relative_to": (self.setInputMapper, s), "adapt_mask": (self.adaptMask, i), "gadget_flagged_particle_type": (self.setFlaggedGadgetParticleType, i),
                   "supersample": (self.setSupersample, i), "subsample": (self.setSubsample, i),
                   "supersample_gas": (self.setSupersampleGas, i)})
         for name in ("strays_on", "num_neighbors", "num_neighbours", "pvar",
                      "center_grafic_output", "centre_output", "center_output",
-                     "mapper_relative_to", "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
+                     "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
                      "dump_ps_field", "dump_tipsy_field", "dump_mask", "import_level",
                      "baryon_tf_on", "zero_level_field", "reverse_small_k"):
             r[name] = (self._unsupported(name),)
@@ -266,6 +279,23 @@ class ICGenerator:
         self._levelAdded()
 
     def _levelAdded(self):
+        if self.pUnderlying is not None:
+            # DummyICGenerator::addLevelToContext (dummyic.hpp:28-58): share the grid object of the underlying generator
+            level = self.context.getNumLevels() - 1
+            mine = self.context.grids[level]
+            uctx = self.pUnderlying.context
+            if uctx.getNumLevels() > level:
+                shared = uctx.getGridForLevel(level)
+                if shared.size != mine.size:
+                    raise L.GxError("Trying to match particles between incompatible simulation setups (wrong grid n)")
+                if shared.thisGridSize != mine.thisGridSize:
+                    raise L.GxError("Trying to match particles between incompatible simulation setups (wrong grid size)")
+                if any(abs(float(a) - float(b)) > 1e-12 * max(1.0, abs(float(a))) for a, b in zip(shared.offsetLower, mine.offsetLower)):
+                    raise L.GxError("Trying to match particles between incompatible simulation setups (wrong grid origin)")
+                shared.flagCells(mine.getFlaggedCells(), append=True)
+                self.context.grids[level] = shared
+            self.gadgetTypesForLevels.append(1)
+            return
         self.gadgetTypesForLevels.append(self.mruGadgetType)
         if len(self.gadgetTypesForLevels) > 1:
             self.usedGadgetParticleTypes[self.mruGadgetType] = True
@@ -328,12 +358,47 @@ class ICGenerator:
             return np.unique(np.array([int(t) for t in f.read().split()], dtype=np.int64))   # io::getBuffer + sortAndEraseDuplicate
 
     def loadID(self, filename):
-        self._mapper().unflagAllParticles()
+        self._mapper().unflagAllParticles()                # clearCellFlags (ic.hpp:1238-1245)
+        if self.pInputMapper is not None:
+            self.pInputMapper.unflagAllParticles()
         self.appendID(filename)
 
     def appendID(self, filename):
-        self._mapper().flagParticles(self._ids(filename))
+        ids = self._ids(filename)
+        if self.pInputMapper is not None:
+            # flagCellsCorrespondingToParticles (ic.hpp:1247-1261): ids refer to the other setup; flag there, then carry the
+            # flags onto the grids only this setup has, and back
+            self.pInputMapper.flagParticles(ids)
+            PM.extendParticleListToUnreferencedGrids(self.pInputMapper, self.context)
+            PM.extendParticleListToUnreferencedGrids(self._mapper(), self.pInputContext)
+        else:
+            self._mapper().flagParticles(ids)
         self._getCentre()
+
+    def setInputMapper(self, fname):
+        """mapper_relative_to (ic.hpp:1077-1112): the particle ids of later id files refer to the setup of another
+        parameter file, whose geometry is rebuilt here by a field-less run of its commands."""
+        if self.context.getNumLevels() == 0:
+            raise L.GxError("Mapper relative command cannot be used before a basegrid has been initialised.")
+        if not os.path.isfile(fname):
+            raise L.GxError("Cannot open IC paramfile for relative_to command")
+        self.log("")
+        self.log("+ Input mapper: computing geometry from " + fname)
+        pseudo = ICGenerator(self.dtype, lambda msg: self.log("\n".join("| " + l for l in (str(msg).splitlines() or [""]))),
+                             pUnderlying=self)                       # logging::IndentWhileInScope
+        pseudo.log("")
+        cwd = os.getcwd()
+        fname = os.path.abspath(fname)
+        os.chdir(os.path.dirname(fname))
+        try:
+            with open(fname) as f:
+                for line in f:
+                    if line.strip():
+                        pseudo.run_line(line.rstrip("\n"))
+        finally:
+            os.chdir(cwd)
+        self.log("")
+        self.pInputMapper, self.pInputContext = pseudo._mapper(), pseudo.context
 
     def dumpID(self, filename):
         with open(filename, "w") as f:
@@ -461,6 +526,8 @@ class ICGenerator:
     def clearModifications(self):
         if self.modificationManager is not None:
             self.modificationManager.clearModifications()
+        else:
+            self.log("Clearing modification list")
 
     def applyModifications(self):
         self.initialiseRandomComponentIfUninitialised()

@@ -337,6 +337,21 @@ class AddGasMapper:
         return self.firstMap.getFlaggedParticles()
 
 
+def references(mapper, grid):
+    """ParticleMapper::references: does the mapper use (a view of) this stored grid?"""
+    return any(m.grid.base is grid for m in mapper.layers().values())
+
+
+def extendParticleListToUnreferencedGrids(mapper, context):
+    """mapper.hpp:183-196: every grid of `context` the mapper does not use receives the flags of the mapper's finest
+    grid, re-expressed on it (zoom.proxyFlags)."""
+    from . import zoom as Z
+    for level in range(context.getNumLevels()):
+        g = context.getGridForLevel(level)
+        if not references(mapper, g):
+            g.flagCells(Z.proxyFlags(mapper.getFinestGrid(), g), append=True)
+
+
 def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, baryonsOnAllLevels=False, gasFirst=False,
                          supersample=1, subsample=1, supersampleGas=1, flaggedGadgetParticleType=None, flaggedCells=None):
     """ICGenerator::updateParticleMapper (ic.hpp:1129-1236) without padding and strays: the one-level mapper of the base

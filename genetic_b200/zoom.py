@@ -272,3 +272,47 @@ def initZoomGrid(context, zoomfac, n, corner=None):
     sub &= inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :]
     g.flagCells(np.flatnonzero(sub.reshape(-1)))
     return g
+
+
+def proxyFlags(source, target):
+    """Grid::makeProxyGridToMatch(target)->getFlaggedCells (grid.hpp:195-228; SuperSampleGrid / SectionOfGrid /
+    SubSampleGrid flag proxies, virtualgrid.hpp): the flagged cells of `source` expressed as cells of `target` -- refined
+    first if the target is finer, shifted into the target's frame (periodic in units of the simulation box, cells outside
+    the target dropped), coarsened last if the target is coarser."""
+    flags = np.asarray(source.getFlaggedCells(), dtype=np.int64)
+    n, dx = source.size, float(source.cellSize)
+    c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0) if len(flags) else np.zeros((3, 0), dtype=np.int64)
+    if float(target.cellSize) < dx:
+        r = _ratio(dx, float(target.cellSize))
+        o = np.arange(r, dtype=np.int64)
+        c = np.stack([(c[0][:, None, None, None] * r + o[None, :, None, None]) + 0 * o[None, None, :, None] + 0 * o[None, None, None, :],
+                      (c[1][:, None, None, None] * r + o[None, None, :, None]) + 0 * o[None, :, None, None] + 0 * o[None, None, None, :],
+                      (c[2][:, None, None, None] * r + o[None, None, None, :]) + 0 * o[None, :, None, None] + 0 * o[None, None, :, None]],
+                     axis=0).reshape(3, -1)
+        dx /= r
+        n *= r
+    sub = _ratio(float(target.cellSize), dx)
+    pre = target.size * sub
+    off = [_ratio_signed(float(target.offsetLower[a]) - float(source.offsetLower[a]), dx) for a in range(3)]
+    if any(off) or pre != n:
+        wrap = int(round(float(source.periodicDomainSize) / dx))
+        c = np.stack([(c[a] - off[a]) % wrap for a in range(3)], axis=0)
+        keep = np.all((c >= 0) & (c < pre), axis=0)
+        c = c[:, keep]
+    c = c // sub
+    m = target.size
+    return np.unique((c[0] * m + c[1]) * m + c[2])
+
+
+def _ratio(a, b):
+    r = a / b
+    if abs(r - round(r)) > 1e-8 * max(1.0, abs(r)) or round(r) < 1:
+        raise L.GxError("The ratio of cell sizes is not a positive integer")
+    return int(round(r))
+
+
+def _ratio_signed(a, b):
+    r = a / b
+    if abs(r - round(r)) > 1e-6 * max(1.0, abs(r)):
+        raise L.GxError("Grid offsets do not differ by a whole number of cells")
+    return int(round(r))

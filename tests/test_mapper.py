@@ -78,3 +78,31 @@ def test_idfile_round_trip_three_levels_vs_reference_binary(tmp_path, golden_dir
     mapper.unflagAllParticles()
     mapper.flagParticles(ids)
     assert np.array_equal(mapper.getFlaggedParticles(), _ids(str(tmp_path / "out_ids.txt")))
+
+
+@pytest.mark.parametrize("test", ["mapper_test_01a_zoom", "mapper_test_01b_zoom_gas", "mapper_test_03a_zoom_linkage",
+                                  "mapper_test_03b_zoom_to_coarse", "mapper_test_05_gadget_ptype",
+                                  "mapper_test_07_ids_from_two_inputs"])
+def test_reference_mapper_tests_through_the_command_layer(golden_dir, tmp_path, monkeypatch, test):
+    """The reference's mapper_test_* directories (run_mapper_tests.sh: run the paramfile, `diff reference.txt output.txt`)
+    through genetic_b200.icgen: zoom mappers with and without gas, per-type gadget ordering, sub-sampled inputs, and
+    `mapper_relative_to` (ids of another setup, rebuilt by a field-less run of its paramfile). Pure host logic: the
+    commands that need the device (`camb`, `done`) are not reached."""
+    import shutil
+    from genetic_b200 import icgen
+    for d in os.listdir(golden_dir):
+        if d.startswith("mapper_test_"):
+            shutil.copytree(os.path.join(golden_dir, d), tmp_path / d)
+    monkeypatch.setattr(icgen.ICGenerator, "setCambDat", lambda self, path: None)     # also in the field-less sub-runs
+    gen = icgen.ICGenerator(log=lambda s: None)
+    gen.commands["camb"] = (lambda path: None, str)
+    gen.commands["done"] = (lambda: None,)
+    cwd = os.getcwd()
+    os.chdir(tmp_path / test)
+    try:
+        for line in open("paramfile.txt"):
+            if line.strip():
+                gen.run_line(line.rstrip("\n"))
+        assert open("reference.txt").read().split() == open("output.txt").read().split()
+    finally:
+        os.chdir(cwd)
