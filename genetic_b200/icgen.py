@@ -31,8 +31,10 @@ class ICGenerator:
         self.pUnderlying = pUnderlying
         self.pInputMapper, self.pInputContext = None, None
         # ic.hpp:196-226
-        self.cosmology = CosmologicalParameters(OmegaM0=0.3, OmegaLambda0=None, sigma8=None, redshift=0.0, ns=0.96,
-                                                hubble=0.701, OmegaBaryons0=0.0, TCMB=2.725)
+        T = self.dtype.type
+        self.cosmology = CosmologicalParameters(OmegaM0=float(T(0.3)), OmegaLambda0=None, sigma8=None, redshift=0.0,
+                                                ns=float(T(0.96)), hubble=float(T(0.701)), OmegaBaryons0=0.0,
+                                                TCMB=float(T(2.725)))
         self.context = GM.MultiLevelGrid()
         self.context.zoomParticleArray = []
         self.spectrum_args = None
@@ -140,29 +142,35 @@ class ICGenerator:
         fn(*args)
 
     # ---- cosmology (ic.hpp:228-343) ----------------------------------------------------------------------------------
+    def _T(self, v):
+        """CosmologicalParameters<T> holds its members in the field type: `-f` rounds them to float32."""
+        return float(self.dtype.type(v))
+
     def setTCMB(self, v):
-        self.cosmology.TCMB = v
+        self.cosmology.TCMB = self._T(v)
 
     def setOmegaM0(self, v):
-        self.cosmology.OmegaM0 = v
+        self.cosmology.OmegaM0 = self._T(v)
 
     def setOmegaB0(self, v):
-        self.cosmology.OmegaBaryons0 = v
+        self.cosmology.OmegaBaryons0 = self._T(v)
 
     def setOmegaLambda0(self, v):
-        self.cosmology.OmegaLambda0 = v
+        self.cosmology.OmegaLambda0 = self._T(v)
 
     def setHubble(self, v):
-        self.cosmology.hubble = v
+        self.cosmology.hubble = self._T(v)
 
     def setSigma8(self, v):
-        self.cosmology.sigma8 = v
+        self.cosmology.sigma8 = self._T(v)
 
     def setns(self, v):
-        self.cosmology.ns = v
+        self.cosmology.ns = self._T(v)
 
     def setZ0(self, z):
-        self.cosmology.setRedshift(z)
+        """ic.hpp:339-342: redshift = z; scalefactor = 1. / (redshift + 1.), each stored in T."""
+        self.cosmology.setRedshift(self._T(z))
+        self.cosmology.scalefactor = self._T(1. / (self.cosmology.redshift + 1.))
 
     def setEpsNorm(self, v):
         self.epsNorm = v

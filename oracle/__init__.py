@@ -59,7 +59,7 @@ def ref_binary():
     return REF_BINARY if os.access(REF_BINARY, os.X_OK) else None
 
 
-def run_ref(paramfile_text, workdir, files=(), timeout=3600):
+def run_ref(paramfile_text, workdir, files=(), timeout=3600, args=()):
     """Runs the compiled reference on a paramfile written into `workdir` (extra input files are copied next to it).
     Returns its combined stdout/stderr. Raises if the binary is missing or exits non-zero."""
     import shutil
@@ -71,7 +71,7 @@ def run_ref(paramfile_text, workdir, files=(), timeout=3600):
         shutil.copy(f, os.path.join(workdir, os.path.basename(f)))
     with open(os.path.join(workdir, "paramfile.txt"), "w") as fh:
         fh.write(paramfile_text)
-    r = subprocess.run([exe, "paramfile.txt"], cwd=workdir, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run([exe, "paramfile.txt"] + list(args), cwd=workdir, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError("reference binary failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
     return r.stdout + r.stderr

@@ -192,3 +192,30 @@ def test_example_paramfile_end_to_end_matches_the_reference_binary(tmp_path, gol
         d = np.abs(a[k] - b[k])
         assert np.all((d <= np.spacing(np.abs(a[k]))) | (d <= 1e-10 * np.abs(a[k]).max())), k
         assert (d == 0).mean() > 0.999
+
+
+@pytest.mark.parametrize("zoom", [False, True])
+def test_float_mode_through_the_command_layer_matches_the_reference_binary(tmp_path, golden_dir, zoom):
+    """`genetIC paramfile.txt -f` (float32 fields, ICf in main.cpp:283-287) against `python -m genetic_b200 paramfile.txt -f`:
+    the draws are the same GSL stream cast to float, so positions / velocities agree to the float32 tolerance of the north
+    star (1e-5 of the field's scale); ids, counts and masses exactly."""
+    import shutil
+    from genetic_b200 import icgen, output as OUT
+    pf = COSMO + "random_seed_real_space 5150\noutname t\noutdir ./\noutformat gadget3\nbasegrid 80.0 32\n"
+    if zoom:
+        pf += "centre 40 41 39\nselect_sphere 9\nzoomgrid 2 32\n"
+    pf += "done\n"
+    ref = tmp_path / "ref"
+    oracle.run_ref(pf, str(ref), [_camb_file(golden_dir)], args=["-f"])
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    shutil.copy(_camb_file(golden_dir), ours)
+    (ours / "paramfile.txt").write_text(pf)
+    icgen.run_paramfile(str(ours / "paramfile.txt"), dtype=np.float32, log=lambda s: None)
+    a, b = OUT.read_gadget(str(ref / "t.gadget3")), OUT.read_gadget(str(ours / "t.gadget3"))
+    assert a["header"] == b["header"] and np.array_equal(a["ids"], b["ids"])
+    if "mass" in a:
+        assert np.array_equal(a["mass"], b["mass"])
+    d = np.abs(a["pos"] - b["pos"])
+    assert np.minimum(d, 80.0 - d).max() < 1e-5 * 80.0
+    assert np.abs(a["vel"] - b["vel"]).max() < 1e-4 * np.abs(a["vel"]).max()
