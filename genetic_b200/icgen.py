@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from . import lib as L
-from .host import CosmologicalParameters, Grid, CAMB, PowerLawPowerSpectrum, RandomFieldGenerator
+from .host import CosmologicalParameters, Grid, CAMB, PowerLawPowerSpectrum
 from . import multilevel as GM, zoom as Z, mapper as PM, output as OUT
 
 
@@ -651,8 +651,7 @@ class ICGenerator:
         """ic.hpp:853-862: the overdensity of every particle's cell in mapper order (`dump_tipsy`), a host-side diagnostic."""
         self.initialiseRandomComponentIfUninitialised()
         self.outputField.toReal()
-        OUT.saveFieldTipsyArray(filename, self._mapper(), [self.outputField.getFieldForLevel(l).getDataVector()
-                                                            for l in range(self.context.getNumLevels())])
+        OUT.saveFieldTipsyArray(filename, PM.field_on_mapper(self._mapper(), self.outputField.fieldsOnLevels))
 
     def dumpVelocityX(self, level):
         if self.pParticleGenerator is None:

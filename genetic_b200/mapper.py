@@ -481,3 +481,28 @@ class MappedParticles:
                         lib.gx_free(dcells)
                     lib.gx_free(dpos)
                     lib.gx_free(dvel)
+
+
+def field_on_mapper(mapper, fieldsOnLevels):
+    """MapperIterator::getField (mapperiterator.hpp:188-197) for every particle: the value of a multi-level real-space
+    field in the cell each particle comes from; virtual layers are resampled on the device like the particle offsets
+    (makeEvaluator, evaluator.hpp:271-318). Returns a host array in mapper order (diagnostic output, `dump_tipsy`)."""
+    lev, cell = mapper.layout()
+    out = np.empty(len(lev), dtype=fieldsOnLevels[0].grid.dtype)
+    for layer, onelevel in mapper.layers().items():
+        w = np.flatnonzero(lev == layer)
+        if len(w):
+            out[w] = _grid_values(onelevel.grid, fieldsOnLevels, cell[w])
+    return out
+
+
+def _grid_values(grid, fieldsOnLevels, cells):
+    src = fieldsOnLevels[grid.base.levelIndex]
+    if src.isFourier():
+        src.toReal()
+    res = grid.resolution() if hasattr(grid, "resolution") else (1, 1)
+    if res != (1, 1):
+        v = Field(grid, fourier=False, stream=src.stream)
+        v.addFieldFromDifferentGrid(src)
+        src = v
+    return src.getDataVector().reshape(-1)[cells]

@@ -52,6 +52,7 @@ class MultiLevelGrid:
     def addLevel(self, grid):
         """multilevelgrid.hpp:112-137: weight = (cellSize / cellSize_0)^3."""
         self.weights.append(1.0 if not self.grids else float(grid.cellSize / self.grids[0].cellSize) ** 3.0)
+        grid.levelIndex = len(self.grids)         # which level's fields a (view of this) grid's particles come from
         self.grids.append(grid)
 
     def addZoomLevel(self, zoomfac, n, corner):

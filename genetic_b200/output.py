@@ -236,14 +236,10 @@ def _mirrored(F, n):
     return F
 
 
-def saveFieldTipsyArray(filename, mapper, levelData):
-    """io::tipsy::saveFieldTipsyArray (tipsy.hpp:38-54), `dump_tipsy`: a 4-byte count, then the real-space field value
-    of every particle's cell in mapper order as float32 (a diagnostic; levelData[level] = host n^3 array)."""
-    lev, cell = mapper.layout()
-    out = np.empty(len(lev), dtype=np.float32)
-    for level, data in enumerate(levelData):
-        w = lev == level
-        out[w] = np.asarray(data).reshape(-1)[cell[w]]
+def saveFieldTipsyArray(filename, values):
+    """io::tipsy::saveFieldTipsyArray (tipsy.hpp:38-54), `dump_tipsy`: a 4-byte count, then the field value of every
+    particle's cell in mapper order as float32 (mapper.field_on_mapper)."""
+    out = np.asarray(values).astype(np.float32)
     with open(filename, "wb") as f:
-        f.write(struct.pack("<I", len(lev) & 0xffffffff))
+        f.write(struct.pack("<I", len(out) & 0xffffffff))
         out.tofile(f)

@@ -22,7 +22,6 @@ REF = "/root/reference/genetIC/tests"
 
 
 def read_particles(fn):
-    from oracle import model as M
     from genetic_b200 import output as OUT
     raw = open(fn, "rb").read(8)
     if raw[:4] == b"\x00\x01\x00\x00":
@@ -85,6 +84,14 @@ def compare_dir(d, log):
             err = np.abs(a[k].astype(np.float64) - b[k].astype(np.float64)).max() if a[k].size else 0
             assert err <= tol, "%s differs by %g" % (k, err)
         msgs.append("particles")
+        ro = os.path.join(d, "reference_output.overdensity")
+        if os.path.exists(ro):
+            mine = glob.glob(d + "/*.overdensity") + glob.glob(d + "/*.overden")
+            mine = [m for m in mine if not m.endswith("reference_output.overdensity")]
+            assert len(mine) == 1, "expected one dump_tipsy array"
+            x, y = np.fromfile(ro, dtype=np.float32, offset=4), np.fromfile(mine[0], dtype=np.float32, offset=4)
+            assert x.shape == y.shape and np.abs(x - y).max() < 1e-5 * max(1.0, np.abs(x).max()), "overdensity array differs"
+            msgs.append("overdensity")
     rg = os.path.join(d, "reference_grid")
     if os.path.isdir(rg):
         for f in sorted(glob.glob(rg + "/grid-?.npy")):
