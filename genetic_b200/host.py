@@ -205,6 +205,71 @@ class VirtualGrid(Grid):
         self.underlying.unflagAllCells()
 
 
+class ResolutionMatchingGrid(Grid):
+    """grids::ResolutionMatchingGrid (virtualgrid.hpp:183-360), the output grid of a zoom level when stray particles are
+    allowed: the whole extent of the low-resolution grid at the cell size of the high-resolution one. Inside the
+    high-resolution window a cell is a cell of `hi`; outside it is a cell of `lo` super-sampled (tricubic interpolation of
+    the low-resolution fields). Flags live on `hi` and, for the interpolated part, in an independent list."""
+
+    def __init__(self, hi, lo):
+        T = hi.dtype.type
+        r = float(lo.cellSize) / float(hi.cellSize)
+        if abs(r - round(r)) > 1e-8 or round(r) < 1:
+            raise L.GxError("ResolutionMatchingGrid: the cell size ratio is not a positive integer")
+        self.ratio = int(round(r))
+        Grid.__init__(self, lo.periodicDomainSize, lo.size * self.ratio, dx=hi.cellSize, x0=lo.offsetLower[0],
+                      y0=lo.offsetLower[1], z0=lo.offsetLower[2], dtype=hi.dtype)
+        self.cellMassFrac, self.cellSofteningScale = hi.cellMassFrac, hi.cellSofteningScale
+        self.hi, self.lo, self.base = hi, lo, hi.base
+        self.loInterp = lo.makeSupersampled(self.ratio)          # withIndependentFlags(): its flags are self.interpFlags
+        self.interpFlags = np.zeros(0, dtype=np.int64)
+        self.corner = [int(round(float(T(hi.offsetLower[a] - lo.offsetLower[a])) / float(self.cellSize))) for a in range(3)]
+        W = self.simEquivalentSize
+        self.win_lo = [c % W for c in self.corner]
+        self.win_hi = [((c + hi.size - 1) % W) + 1 for c in self.corner]
+
+    def inHiResWindow(self, coords):
+        ok = np.ones(len(coords[0]), dtype=bool)
+        for a in range(3):
+            lo, hi, c = self.win_lo[a], self.win_hi[a], coords[a]
+            ok &= ((c < hi) & (c >= lo)) if hi >= lo else ((c < hi) | (c >= lo))
+        return ok
+
+    def split(self, cells):
+        """cells of this grid -> (mask of those in the high-resolution window, their cell ids on `hi`)."""
+        n = self.size
+        c = np.unravel_index(np.asarray(cells, dtype=np.int64), (n, n, n))
+        m = self.inHiResWindow(c)
+        W, h = self.simEquivalentSize, self.hi.size
+        ch = [((c[a][m] - self.corner[a]) % W) for a in range(3)]
+        return m, (ch[0] * h + ch[1]) * h + ch[2]
+
+    def getFlaggedCells(self):
+        h, n, W = self.hi.size, self.size, self.simEquivalentSize
+        hf = np.asarray(self.hi.getFlaggedCells(), dtype=np.int64)
+        c = np.unravel_index(hf, (h, h, h))
+        up = [(c[a] + self.corner[a]) % W for a in range(3)]
+        mapped = (up[0] * n + up[1]) * n + up[2]
+        m, _ = self.split(self.interpFlags)
+        return np.unique(np.concatenate([mapped, self.interpFlags[~m]]))
+
+    def flagCells(self, indices, append=False):
+        ids = np.asarray(indices, dtype=np.int64).reshape(-1)
+        m, hi_cells = self.split(ids)
+        self.hi.flagCells(hi_cells, append)
+        self.interpFlags = np.unique(np.concatenate([self.interpFlags, ids[~m]]) if append else ids[~m])
+
+    def unflagAllCells(self):
+        self.hi.unflagAllCells()
+        self.interpFlags = np.zeros(0, dtype=np.int64)
+
+    def makeSupersampled(self, ratio):
+        return ResolutionMatchingGrid(self.hi.makeSupersampled(ratio), self.lo.makeSupersampled(ratio))
+
+    def makeSubsampled(self, ratio):
+        return ResolutionMatchingGrid(self.hi.makeSubsampled(ratio), self.lo.makeSubsampled(ratio))
+
+
 def _int_ratio(a, b):
     if a % b:
         raise L.GxError("The ratio of sub/supersampling factors is not an integer")

@@ -6,7 +6,7 @@ comment line, surplus tokens are ignored, an error aborts the run with the refer
 
 Everything numerical is sequencing over the C ABI (host.py / multilevel.py / zoom.py / mapper.py / output.py); this file
 holds only the state machine of ICGenerator. Commands outside the accelerated path raise "not supported" errors instead
-of being silently ignored: grafic / HDF5 / swift output, strays, autopad, masks,
+of being silently ignored: grafic / HDF5 / swift output, autopad, masks,
 baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
 """
 import math
@@ -111,7 +111,8 @@ class ICGenerator:
         r.update({"mapper_relative_to": (self.setInputMapper, s), "adapt_mask": (self.adaptMask, i), "gadget_flagged_particle_type": (self.setFlaggedGadgetParticleType, i),
                   "supersample": (self.setSupersample, i), "subsample": (self.setSubsample, i),
                   "supersample_gas": (self.setSupersampleGas, i)})
-        for name in ("strays_on", "num_neighbors", "num_neighbours", "pvar",
+        r["strays_on"] = (self.setStraysOn,)
+        for name in ("num_neighbors", "num_neighbours", "pvar",
                      "center_grafic_output", "centre_output", "center_output",
                      "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
                      "dump_ps_field", "dump_tipsy_field", "dump_mask", "import_level",
@@ -174,6 +175,11 @@ class ICGenerator:
 
     def setEpsNorm(self, v):
         self.epsNorm = v
+
+    def setStraysOn(self):
+        """ic.hpp:256-260: zoom levels opened from now on keep flagged cells that fall outside their window (the
+        particles are interpolated from the level above)."""
+        self.context.allowStrays = True
 
     def setSupersample(self, factor):
         if factor <= 1:
@@ -301,6 +307,9 @@ class ICGenerator:
                 if any(abs(float(a) - float(b)) > 1e-12 * max(1.0, abs(float(a))) for a, b in zip(shared.offsetLower, mine.offsetLower)):
                     raise L.GxError("Trying to match particles between incompatible simulation setups (wrong grid origin)")
                 shared.flagCells(mine.getFlaggedCells(), append=True)
+                shared.levelIndex = level
+                if self.context.outputGrids[level] is mine:
+                    self.context.outputGrids[level] = shared
                 self.context.grids[level] = shared
             self.gadgetTypesForLevels.append(1)
             return
@@ -324,17 +333,21 @@ class ICGenerator:
         if nflag == 0:
             raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
         if corner is None:
-            corner = Z.zoomCorner(up, zoomfac)
+            corner = Z.zoomCorner(up, zoomfac, self.context.allowStrays)
             if Z.flagsNearZoomBorder(up, corner, zoomfac):
                 self.log("WARNING: Opening a zoom where flagged particles are within 3 pixels of the edge. This is prone to "
                          "numerical errors.")
         g = Z.initZoomGrid(self.context, zoomfac, n, corner=corner)
         self._levelAdded()
         kept = len(self.context.zoomParticleArray[-1])
-        if kept < nflag:
-            self.log("WARNING: the requested zoom particles do not all fit in the requested zoom window\n"
-                     "         of %d particles, %d have been omitted\n         to make a new zoom flag list of %d"
-                     % (nflag, nflag - kept, kept))
+        missed = self.context.zoomMissedParticles
+        if missed > 0:
+            self.log("WARNING: the requested zoom particles do not all fit in the requested zoom window")
+            if self.context.allowStrays:
+                self.log("         of %d particles, %d will be interpolated from LR grid (stray particle mode)" % (nflag, missed))
+            else:
+                self.log("         of %d particles, %d have been omitted" % (nflag, missed))
+            self.log("         to make a new zoom flag list of %d" % kept)
         self.log("Initialized a zoom region:\n  Subbox length         = %g Mpc/h\n  n                     = %d\n"
                  "  dx                    = %g\n  Zoom factor           = %d\n  Num particles         = %d\n"
                  "  Low-left corner in parent grid = (%d, %d, %d)\n"

@@ -13,7 +13,7 @@ The reference walks these with iterators that dereference one particle at a time
 mapper is resolved once into its *layout* -- two arrays (level, cell index) in output order, pure index arithmetic on the
 host -- and the particles of each level are then evaluated on the device at that level's cell list in one launch per
 component (gx_emit_cells). Gas: AddGasMapper over splitMass (gasmapper.hpp). Not covered: sub/supersampling, intermediate-resolution padding,
-stray particles, the grafic mapper.
+the grafic mapper. Stray particles (ResolutionMatchingGrid output grids) for one zoom level.
 """
 import ctypes as C
 import itertools
@@ -361,12 +361,12 @@ def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, bar
     coarsens the base level (superOrSubSample, ic.hpp:1223-1234)."""
     nl = context.getNumLevels()
     types = list(gadgetTypesForLevels) if gadgetTypesForLevels is not None else [1] * nl
-    m = OneLevelParticleMapper(context.getGridForLevel(0), 0, types[0])
+    m = OneLevelParticleMapper(context.getOutputGridForLevel(0), 0, types[0])
     for level in range(1, nl):
-        fine = OneLevelParticleMapper(context.getGridForLevel(level), level, types[level])
+        fine = OneLevelParticleMapper(context.getOutputGridForLevel(level), level, types[level])
         m = TwoLevelParticleMapper(m, fine, context.zoomParticleArray[level - 1])
     if flaggedGadgetParticleType is not None:       # ic.hpp:1176-1186: the flagged cells of the finest grid, retyped
-        flagged = OneLevelParticleMapper(context.getGridForLevel(nl - 1), nl - 1, flaggedGadgetParticleType)
+        flagged = OneLevelParticleMapper(context.getOutputGridForLevel(nl - 1), nl - 1, flaggedGadgetParticleType)
         m = TwoLevelParticleMapper(m, flagged, flaggedCells)
 
     def resample(mp, sup, sub):
@@ -418,70 +418,88 @@ class MappedParticles:
         self.mass = np.empty(N, dtype=T)
         self.eps = np.empty(N, dtype=T)
         odt, esz = _dt(out_dtype), np.dtype(out_dtype).itemsize
-        resampled = {}
+        self._lib, self._gen, self._cos, self._chunk = lib, particleGenerator, cosmology, chunk
+        self._odt, self._esz, self._out_dtype, self._resampled = odt, esz, out_dtype, {}
         for layer, onelevel in layers.items():
-            grid, level = onelevel.grid, onelevel.level
+            grid = onelevel.grid
             where = np.flatnonzero(lev == layer)
             self.mass[where] = particle_mass(grid, cosmology)
             self.eps[where] = particle_eps(grid, epsNorm)
-            self.level[where] = level
-            if len(where) == 0:
-                continue
-            psis = particleGenerator.getGeneratorForLevel(level).getGeneratedFields()
-            for axis in range(3):
-                if psis[axis].isFourier():
-                    psis[axis].toReal()
-            res = grid.resolution() if hasattr(grid, "resolution") else (1, 1)
-            if res != (1, 1):
-                # Super/SubSampleEvaluator (evaluator.hpp:96-205): the stored offsets interpolated tricubically at the
-                # centres of a finer virtual grid, or averaged over the sub-cells of a coarser one -- the same cross-grid
-                # kernels that combine the levels, writing a field on the virtual grid
-                key = (level,) + res
-                if key not in resampled:
-                    out = []
-                    for axis in range(3):
-                        v = Field(grid, fourier=False, stream=psis[axis].stream)
-                        v.addFieldFromDifferentGrid(psis[axis])
-                        out.append(v)
-                    resampled[key] = out
-                psis = resampled[key]
-            ratio = cosmology.zeldovichVelocityToOffsetRatio(grid.dtype)
-            contiguous_out = where[-1] - where[0] + 1 == len(where)     # the mapper's levels are runs in practice
-            for c0 in range(0, len(where), chunk):                       # bounded device staging
-                w = where[c0:c0 + chunk]
-                m = len(w)
-                cells = np.ascontiguousarray(cell[w])
-                is_range = int(cells[-1]) - int(cells[0]) + 1 == m and (m == 1 or bool(np.all(np.diff(cells) == 1)))
-                dcells, dpos, dvel = C.c_void_p(), C.c_void_p(), C.c_void_p()
-                lib.gx_malloc(C.byref(dpos), m * 3 * esz)
-                lib.gx_malloc(C.byref(dvel), m * 3 * esz)
-                try:
-                    if not is_range:
-                        lib.gx_malloc(C.byref(dcells), cells.nbytes)
-                        lib.gx_memcpy_h2d(dcells, cells.ctypes.data_as(C.c_void_p), cells.nbytes, None)
-                    for axis in range(3):
-                        geo = (psis[axis].ptr, grid.size, psis[axis].dt, axis, float(grid.cellSize),
-                               float(grid.offsetLower[axis]), float(grid.periodicDomainSize), ratio)
-                        out = (C.c_void_p(dpos.value + axis * esz), C.c_void_p(dvel.value + axis * esz), odt, 3)
-                        if is_range:     # a whole level, or the unzoomed stretch of one: no cell list needed
-                            lib.gx_emit_component(*geo, *out, int(cells[0]), m, None)
-                        else:
-                            lib.gx_emit_cells(*geo, dcells, m, *out, None)
-                    if contiguous_out:
-                        p, v = self.pos[w[0]:w[0] + m], self.vel[w[0]:w[0] + m]
-                    else:
-                        p, v = np.empty((m, 3), dtype=out_dtype), np.empty((m, 3), dtype=out_dtype)
-                    lib.gx_memcpy_d2h(p.ctypes.data_as(C.c_void_p), dpos, p.nbytes, None)
-                    lib.gx_memcpy_d2h(v.ctypes.data_as(C.c_void_p), dvel, v.nbytes, None)
-                    lib.gx_synchronize(None)
-                    if not contiguous_out:
-                        self.pos[w], self.vel[w] = p, v
-                finally:
-                    if dcells.value:
-                        lib.gx_free(dcells)
-                    lib.gx_free(dpos)
-                    lib.gx_free(dvel)
+            self.level[where] = onelevel.level
+            if len(where):
+                self._evaluate(grid, cell[where], where)
+        del self._resampled
 
+    def _evaluate(self, grid, cells, where):
+        """Particles of `cells` of `grid` into rows `where` of pos / vel."""
+        if len(cells) == 0:
+            return
+        inner = grid
+        while getattr(inner, "kind", None) == "mass":      # MassScaledGrid: same cells, same fields (evaluator.hpp:311-315)
+            inner = inner.underlying
+        if hasattr(inner, "loInterp"):
+            # ResolutionMatchingEvaluator (evaluator.hpp:218-256): cells in the high-resolution window come from the
+            # zoom level's fields, stray cells from the level above interpolated at the fine cell centres
+            m, hi_cells = inner.split(cells)
+            self._evaluate(inner.hi, hi_cells, where[m])
+            self._evaluate(inner.loInterp, cells[~m], where[~m])
+            return
+        lib, cosmology, chunk, odt, esz, out_dtype = self._lib, self._cos, self._chunk, self._odt, self._esz, self._out_dtype
+        level = grid.base.levelIndex
+        psis = self._gen.getGeneratorForLevel(level).getGeneratedFields()
+        for axis in range(3):
+            if psis[axis].isFourier():
+                psis[axis].toReal()
+        res = grid.resolution() if hasattr(grid, "resolution") else (1, 1)
+        if res != (1, 1):
+            # Super/SubSampleEvaluator (evaluator.hpp:96-205): the stored offsets interpolated tricubically at the
+            # centres of a finer virtual grid, or averaged over the sub-cells of a coarser one -- the same cross-grid
+            # kernels that combine the levels, writing a field on the virtual grid
+            key = (level,) + res
+            if key not in self._resampled:
+                out = []
+                for axis in range(3):
+                    v = Field(grid, fourier=False, stream=psis[axis].stream)
+                    v.addFieldFromDifferentGrid(psis[axis])
+                    out.append(v)
+                self._resampled[key] = out
+            psis = self._resampled[key]
+        ratio = cosmology.zeldovichVelocityToOffsetRatio(grid.dtype)
+        contiguous_out = where[-1] - where[0] + 1 == len(where) and (len(where) == 1 or bool(np.all(np.diff(where) == 1)))
+        for c0 in range(0, len(where), chunk):                       # bounded device staging
+            w = where[c0:c0 + chunk]
+            m = len(w)
+            cc = np.ascontiguousarray(cells[c0:c0 + chunk])
+            is_range = int(cc[-1]) - int(cc[0]) + 1 == m and (m == 1 or bool(np.all(np.diff(cc) == 1)))
+            dcells, dpos, dvel = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            lib.gx_malloc(C.byref(dpos), m * 3 * esz)
+            lib.gx_malloc(C.byref(dvel), m * 3 * esz)
+            try:
+                if not is_range:
+                    lib.gx_malloc(C.byref(dcells), cc.nbytes)
+                    lib.gx_memcpy_h2d(dcells, cc.ctypes.data_as(C.c_void_p), cc.nbytes, None)
+                for axis in range(3):
+                    geo = (psis[axis].ptr, grid.size, psis[axis].dt, axis, float(grid.cellSize),
+                           float(grid.offsetLower[axis]), float(grid.periodicDomainSize), ratio)
+                    out = (C.c_void_p(dpos.value + axis * esz), C.c_void_p(dvel.value + axis * esz), odt, 3)
+                    if is_range:     # a whole level, or the unzoomed stretch of one: no cell list needed
+                        lib.gx_emit_component(*geo, *out, int(cc[0]), m, None)
+                    else:
+                        lib.gx_emit_cells(*geo, dcells, m, *out, None)
+                if contiguous_out:
+                    p, v = self.pos[w[0]:w[0] + m], self.vel[w[0]:w[0] + m]
+                else:
+                    p, v = np.empty((m, 3), dtype=out_dtype), np.empty((m, 3), dtype=out_dtype)
+                lib.gx_memcpy_d2h(p.ctypes.data_as(C.c_void_p), dpos, p.nbytes, None)
+                lib.gx_memcpy_d2h(v.ctypes.data_as(C.c_void_p), dvel, v.nbytes, None)
+                lib.gx_synchronize(None)
+                if not contiguous_out:
+                    self.pos[w], self.vel[w] = p, v
+            finally:
+                if dcells.value:
+                    lib.gx_free(dcells)
+                lib.gx_free(dpos)
+                lib.gx_free(dvel)
 
 def field_on_mapper(mapper, fieldsOnLevels):
     """MapperIterator::getField (mapperiterator.hpp:188-197) for every particle: the value of a multi-level real-space
@@ -497,6 +515,14 @@ def field_on_mapper(mapper, fieldsOnLevels):
 
 
 def _grid_values(grid, fieldsOnLevels, cells):
+    while getattr(grid, "kind", None) == "mass":
+        grid = grid.underlying
+    if hasattr(grid, "loInterp"):                      # ResolutionMatchingEvaluator
+        m, hi_cells = grid.split(cells)
+        out = np.empty(len(cells), dtype=grid.dtype)
+        out[m] = _grid_values(grid.hi, fieldsOnLevels, hi_cells)
+        out[~m] = _grid_values(grid.loInterp, fieldsOnLevels, np.asarray(cells)[~m])
+        return out
     src = fieldsOnLevels[grid.base.levelIndex]
     if src.isFourier():
         src.toReal()

@@ -47,12 +47,19 @@ class MultiLevelGrid:
         self.grids = []
         self.weights = []
         self.levelsAreCombined = False
+        self.allowStrays = False     # strays_on: output grids of later zoom levels become ResolutionMatchingGrids
+        self.outputGrids = []
         self.spectra = {}     # species -> PowerSpectrum (cosmology::CAMB); evaluated in-kernel per grid
 
     def addLevel(self, grid):
         """multilevelgrid.hpp:112-137: weight = (cellSize / cellSize_0)^3."""
         self.weights.append(1.0 if not self.grids else float(grid.cellSize / self.grids[0].cellSize) ** 3.0)
         grid.levelIndex = len(self.grids)         # which level's fields a (view of this) grid's particles come from
+        if self.allowStrays and self.grids:        # multilevelgrid.hpp:131-137
+            from .host import ResolutionMatchingGrid
+            self.outputGrids.append(ResolutionMatchingGrid(grid, self.outputGrids[-1]))
+        else:
+            self.outputGrids.append(grid)
         self.grids.append(grid)
 
     def addZoomLevel(self, zoomfac, n, corner):
@@ -74,6 +81,10 @@ class MultiLevelGrid:
 
     def getGridForLevel(self, level):
         return self.grids[level]
+
+    def getOutputGridForLevel(self, level):
+        """The grid particles are output from (multilevelgrid.hpp:190-197): the stored grid unless strays are allowed."""
+        return self.outputGrids[level]
 
     def getWeightForLevel(self, level):
         return self.weights[level]

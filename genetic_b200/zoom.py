@@ -32,7 +32,10 @@ def select(context, centre, inclusion):
     """ICGenerator::select (ic.hpp:1458-1484): on every level flag the cells whose centroid offset from `centre`
     satisfies inclusion(dx, dy, dz)."""
     base = context.getGridForLevel(0)
-    for g in context.grids:
+    outputGrids = [context.getOutputGridForLevel(l) for l in range(context.getNumLevels())]
+    for g in outputGrids:
+        g.unflagAllCells()
+    for g in outputGrids:
         d = [_wrapped_offset(base, _centroids(g, a), g.dtype.type(centre[a])) for a in range(3)]
         m = inclusion(d[0][:, None, None], d[1][None, :, None], d[2][None, None, :])
         g.flagCells(np.flatnonzero(np.broadcast_to(m, (g.size,) * 3).reshape(-1)))
@@ -82,8 +85,9 @@ def getCentreWrapped(grid, flags):
 def selectNearest(context, centre):
     """ICGenerator::selectNearest (ic.hpp:1447-1455): the cell of the deepest level that holds `centre`
     (Grid::getIndexFromPoint, grid.hpp:672-677)."""
-    for g in context.grids:
-        g.flagCells([])
+    for l in range(context.getNumLevels()):
+        context.getOutputGridForLevel(l).unflagAllCells()
+        context.getGridForLevel(l).unflagAllCells()
     g = context.grids[-1]
     c = []
     for a in range(3):
@@ -161,7 +165,7 @@ class _Window:
         return d
 
 
-def zoomCorner(grid, zoomfac):
+def zoomCorner(grid, zoomfac, allowStrays=False):
     """ICGenerator::initZoomGrid (ic.hpp:398-479) without stray particles: the lower-left corner, in cells of `grid`, of
     the zoom window of grid.size / zoomfac cells that holds the flagged cells."""
     n = grid.size
@@ -175,7 +179,7 @@ def zoomCorner(grid, zoomfac):
         w.expandToInclude([int(v) for v in c])
     n_user = n // zoomfac
     n_required = max(w.sizes())
-    if n_required > n_user:
+    if n_required > n_user and not allowStrays:
         raise L.GxError("Zoom particles do not fit in specified sub-box. Decrease zoom, or choose different particles")
     if n_required < n_user:
         w.expandSymmetricallyToSize(n_user)
@@ -253,14 +257,20 @@ def initZoomGrid(context, zoomfac, n, corner=None):
     up = context.grids[-1]
     if len(up.getFlaggedCells()) == 0:
         raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
+    strays = getattr(context, "allowStrays", False)
+    if strays and context.getOutputGridForLevel(len(context.grids) - 1) is not up:
+        raise L.GxError("stray particles are supported for a single zoom level only")
     if corner is None:
-        corner = zoomCorner(up, zoomfac)
+        corner = zoomCorner(up, zoomfac, strays)
     if min(corner) < 0:
         raise L.GxError("The newly initialised zoom level is not fully contained within the previous level")
     if not hasattr(context, "zoomParticleArray"):
         context.zoomParticleArray = []
     del context.zoomParticleArray[len(context.grids) - 1:]
-    context.zoomParticleArray.append(_trimToZoomWindow(up, up.getFlaggedCells(), corner, up.size // zoomfac))
+    trimmed = _trimToZoomWindow(up, up.getFlaggedCells(), corner, up.size // zoomfac)
+    context.zoomMissedParticles = len(up.getFlaggedCells()) - len(trimmed)
+    # with strays the cells outside the window stay in the list: their particles are interpolated from the level above
+    context.zoomParticleArray.append(np.asarray(up.getFlaggedCells(), dtype=np.int64).copy() if strays else trimmed)
     g = context.addZoomLevel(zoomfac, n, corner)
     ratio = int(round(float(up.cellSize) / float(g.cellSize)))
     pm = np.zeros(up.size3, dtype=bool)

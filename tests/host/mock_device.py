@@ -93,7 +93,7 @@ class MockLib:
         a = _addr(p)
         if a in self.mem:
             return a, 0
-        base = max(h for h in self.mem if h <= a)
+        base = max(h for h in list(self.mem) if h <= a)    # (a Field finaliser may free a buffer meanwhile)
         assert a - base < len(self.mem[base])
         return base, a - base
 

@@ -88,7 +88,8 @@ def test_zoom_with_modifications_matches_the_reference_binary(tmp_path, golden_d
 @pytest.mark.parametrize("case", ["tipsy_two_levels", "tipsy_three_levels", "gadget2_three_levels",
                                   "gadget3_types_two_files", "gadget3_trimmed_window", "tipsy_gas", "gadget3_gas",
                                   "gadget2_gas_all_levels", "tipsy_supersample2", "gadget3_subsample2_supersample3",
-                                  "tipsy_gas_supersamplegas2_supersample3_three_levels"])
+                                  "tipsy_gas_supersamplegas2_supersample3_three_levels", "tipsy_strays",
+                                  "gadget3_strays_supersample2"])
 def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, case):
     """The particle mappers (OneLevel / nested TwoLevel ordering, per-level gadget types, the trimming of the zoom list
     to a user-placed window) and the tipsy / gadget writers: the files written from the device-evaluated particles are
@@ -106,7 +107,9 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     pf += "basegrid 60.0 32\n"
     if case == "gadget3_types_two_files":
         pf += "gadget_particle_type 2\n"
-    if case == "gadget3_trimmed_window":
+    if "strays" in case:
+        pf += "strays_on\n"
+    if case == "gadget3_trimmed_window" or "strays" in case:
         corner, radius = (6, 9, 13), 12
         pf += "centre 20 33 41\nselect_sphere 12\nzoomgrid_with_origin_at 6 9 13 2 32\n"
     else:
@@ -126,8 +129,11 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     ctx.addLevel(gb.Grid(60.0, 32))
     for s in ("dm", "all"):
         ctx.setPowerspectrumGenerator(s, gb.CAMB(cos, _camb_file(golden_dir), s))
+    ctx.allowStrays = "strays" in case
     Z.selectSphere(ctx, (20, 33, 41), radius)
     Z.initZoomGrid(ctx, 2, 32, corner=corner)
+    if "strays" in case:
+        assert "stray particle mode" in out and len(ctx.zoomParticleArray[0]) == len(ctx.getGridForLevel(0).getFlaggedCells())
     if case == "gadget3_trimmed_window":
         assert "have been omitted" in out and len(ctx.zoomParticleArray[0]) < len(ctx.getGridForLevel(0).getFlaggedCells())
     if three:
