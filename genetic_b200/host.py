@@ -180,18 +180,7 @@ class VirtualGrid(Grid):
         return VirtualGrid(self, "sub", int(ratio))
 
     def _scale(self, cells, src_n, dst_n):
-        """Grid::upscaleCellFlagVector / downscaleCellFlagVector (grid.hpp:384-436)."""
-        cells = np.asarray(cells, dtype=np.int64)
-        c = np.stack(np.unravel_index(cells, (src_n,) * 3), axis=0)
-        if dst_n >= src_n:
-            f = dst_n // src_n
-            o = np.arange(f, dtype=np.int64)
-            x = c[0][:, None, None, None] * f + o[None, :, None, None]
-            y = c[1][:, None, None, None] * f + o[None, None, :, None]
-            z = c[2][:, None, None, None] * f + o[None, None, None, :]
-            return ((x * dst_n + y) * dst_n + z).reshape(-1)
-        f = src_n // dst_n
-        return np.unique(((c[0] // f) * dst_n + (c[1] // f)) * dst_n + (c[2] // f))
+        return scale_cells(cells, src_n, dst_n)
 
     def getFlaggedCells(self):
         u = self.underlying.getFlaggedCells()
@@ -268,6 +257,23 @@ class ResolutionMatchingGrid(Grid):
 
     def makeSubsampled(self, ratio):
         return ResolutionMatchingGrid(self.hi.makeSubsampled(ratio), self.lo.makeSubsampled(ratio))
+
+
+def scale_cells(cells, src_n, dst_n):
+    """Grid::upscaleCellFlagVector / downscaleCellFlagVector (grid.hpp:384-436): cell ids of a grid of side src_n as ids
+    of the same volume at side dst_n (all sub-cells when refining, the unique parents when coarsening)."""
+    cells = np.asarray(cells, dtype=np.int64)
+
+    c = np.stack(np.unravel_index(cells, (src_n,) * 3), axis=0)
+    if dst_n >= src_n:
+        f = dst_n // src_n
+        o = np.arange(f, dtype=np.int64)
+        x = c[0][:, None, None, None] * f + o[None, :, None, None]
+        y = c[1][:, None, None, None] * f + o[None, None, :, None]
+        z = c[2][:, None, None, None] * f + o[None, None, None, :]
+        return ((x * dst_n + y) * dst_n + z).reshape(-1)
+    f = src_n // dst_n
+    return np.unique(((c[0] // f) * dst_n + (c[1] // f)) * dst_n + (c[2] // f))
 
 
 def _int_ratio(a, b):

@@ -6,7 +6,7 @@ comment line, surplus tokens are ignored, an error aborts the run with the refer
 
 Everything numerical is sequencing over the C ABI (host.py / multilevel.py / zoom.py / mapper.py / output.py); this file
 holds only the state machine of ICGenerator. Commands outside the accelerated path raise "not supported" errors instead
-of being silently ignored: grafic / HDF5 / swift output, autopad, masks,
+of being silently ignored: grafic / HDF5 / swift output, masks,
 baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
 """
 import math
@@ -50,6 +50,7 @@ class ICGenerator:
         self.baryonsOnAllLevels = False
         self.supersample = self.subsample = self.supersampleGas = 1
         self.flaggedGadgetParticleType, self._flaggedCellsForType = None, None
+        self.autopad = 0
         self.epsNorm = 0.01075
         self.x0 = self.y0 = self.z0 = 0.0
         self.variance_filterscale = -1.0
@@ -112,9 +113,10 @@ class ICGenerator:
                   "supersample": (self.setSupersample, i), "subsample": (self.setSubsample, i),
                   "supersample_gas": (self.setSupersampleGas, i)})
         r["strays_on"] = (self.setStraysOn,)
+        r["autopad"] = (self.setAutopad, i)
         for name in ("num_neighbors", "num_neighbours", "pvar",
                      "center_grafic_output", "centre_output", "center_output",
-                     "autopad", "dump_grid_for_field", "dump_grid_fourier_for_field",
+                     "dump_grid_for_field", "dump_grid_fourier_for_field",
                      "dump_ps_field", "dump_tipsy_field", "dump_mask", "import_level",
                      "baryon_tf_on", "zero_level_field", "reverse_small_k"):
             r[name] = (self._unsupported(name),)
@@ -175,6 +177,9 @@ class ICGenerator:
 
     def setEpsNorm(self, v):
         self.epsNorm = v
+
+    def setAutopad(self, nCells):
+        self.autopad = nCells
 
     def setStraysOn(self):
         """ic.hpp:256-260: zoom levels opened from now on keep flagged cells that fall outside their window (the
@@ -362,14 +367,14 @@ class ICGenerator:
         # rebuilt on demand and kept while they stay the same
         key = (self.context.getNumLevels(), tuple(self.gadgetTypesForLevels), float(self.cosmology.OmegaBaryons0),
                float(self.cosmology.OmegaM0), self.baryonsOnAllLevels, gasFirst, self.supersample, self.subsample,
-               self.supersampleGas, self.flaggedGadgetParticleType, tuple(id(z) for z in self.context.zoomParticleArray))
+               self.supersampleGas, self.flaggedGadgetParticleType, self.autopad, tuple(id(z) for z in self.context.zoomParticleArray))
         if getattr(self, "_mapper_key", None) != key:
             self._mapper_cache = PM.updateParticleMapper(self.context, self.gadgetTypesForLevels, self.cosmology,
                                                          self.baryonsOnAllLevels, gasFirst=gasFirst,
                                                          supersample=self.supersample, subsample=self.subsample,
                                                          supersampleGas=self.supersampleGas,
                                                          flaggedGadgetParticleType=self.flaggedGadgetParticleType,
-                                                         flaggedCells=self._flaggedCellsForType)
+                                                         flaggedCells=self._flaggedCellsForType, autopad=self.autopad)
             self._mapper_key = key
         return self._mapper_cache
 
@@ -474,18 +479,7 @@ class ICGenerator:
 
     @staticmethod
     def _expanded(flags, n, nCells):
-        """Grid::expandFlaggedRegion (grid.hpp:277-306): the +-1 neighbours along each axis, nCells times."""
-        flags = np.asarray(flags, dtype=np.int64)
-        for _ in range(nCells):
-            for axis in range(3):
-                c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0)
-                out = [flags]
-                for step in (1, -1):
-                    d = c.copy()
-                    d[axis] = (d[axis] + step) % n
-                    out.append(np.ravel_multi_index(tuple(d), (n, n, n)))
-                flags = np.unique(np.concatenate(out))
-        return flags
+        return PM._expandFlaggedRegion(flags, n, nCells)
 
     def adaptMask(self, nPadCells):
         """ic.hpp:1545-1575: working up from the deepest zoom, the cells each level replaces become the footprint of the

@@ -22,7 +22,7 @@ import math
 import numpy as np
 
 from . import lib as L
-from .host import _dt, Field
+from .host import _dt, Field, scale_cells
 
 
 _layer_ids = itertools.count()
@@ -72,6 +72,12 @@ class OneLevelParticleMapper:
                     OneLevelParticleMapper(self.grid.makeScaledMassVersion(T(T(1.0) - T(massRatio))), self.level,
                                            self.gadgetParticleType))
         return None, OneLevelParticleMapper(self.grid, self.level, self.gadgetParticleType)
+
+    def insertIntermediateResolutionPadding(self, ratio, padCells):
+        return self
+
+    def getGadgetParticleTypeForFinestGrid(self):
+        return self.gadgetParticleType
 
     def superOrSubSample(self, ratio, toGrids, super_):
         """onelevelmapper.hpp:179-195."""
@@ -197,6 +203,38 @@ class TwoLevelParticleMapper:
 
     def size_gas(self):
         return 0
+
+    def getGadgetParticleTypeForFinestGrid(self):
+        return self.pLevel2.getGadgetParticleTypeForFinestGrid()
+
+    def insertIntermediateResolutionPadding(self, ratio, padCells):
+        """twolevelmapper.hpp:603-690 (`autopad`): where the zoom is more than `ratio` times finer than its surroundings, a
+        shell of padCells cells around the zoomed cells is replaced by particles of intermediate resolution interpolated from
+        the level above, recursively until the jump is at most `ratio`."""
+        mapperLR = self.pLevel1.insertIntermediateResolutionPadding(ratio, padCells)
+        cells = self.level1CellsToReplace
+        finestLR = mapperLR.getFinestGrid()
+        r = float(finestLR.cellSize) / float(self.pGrid2.cellSize)
+        if abs(r - round(r)) > 1e-8:
+            raise L.GxError("autopad: the cell size ratio is not an integer")
+        newRatio = int(round(r))
+        if newRatio <= ratio:
+            return TwoLevelParticleMapper(mapperLR, self.pLevel2, cells, self.skipLevel1)
+        if newRatio % ratio:
+            raise L.GxError("autopad: the zoom factor is not a multiple of the padding ratio")
+        supersampledCells = scale_cells(cells, finestLR.size, finestLR.size * ratio)
+        expanded = _expandFlaggedRegion(cells, finestLR.size, padCells)
+        if isinstance(mapperLR, TwoLevelParticleMapper):       # only cells the level-1 mapper can reach stay flagged
+            expanded = np.intersect1d(expanded, mapperLR.zoomParticleArrayHiresUnsorted)
+        # The reference builds a ResolutionMatchingGrid(zoom grid subsampled, finestLR) here (twolevelmapper.hpp:655-657), but
+        # its compiled binary evaluates every padding particle from the level above (tricubic interpolation, mass of a
+        # level-above cell / ratio^3, also where the zoom level's fields exist): measured against oracle/_ref/genetIC and
+        # the goldens of test_10i / test_18, which is what a super-sampled view of finestLR gives.
+        padGrid = finestLR.makeSupersampled(ratio)
+        padMapper = OneLevelParticleMapper(padGrid, self.pLevel2.level, mapperLR.getGadgetParticleTypeForFinestGrid())
+        lowAndPad = TwoLevelParticleMapper(mapperLR, padMapper, expanded, self.skipLevel1)
+        everything = TwoLevelParticleMapper(lowAndPad, self.pLevel2, supersampledCells, self.skipLevel1)
+        return everything.insertIntermediateResolutionPadding(ratio, padCells)
 
     def superOrSubSample(self, ratio, toGrids, super_):
         """twolevelmapper.hpp:568-591: both sub-mappers are resampled and the cells to replace are re-expressed on the new
@@ -336,6 +374,27 @@ class AddGasMapper:
             return self.secondMap.getFlaggedParticles() + self.nFirst
         return self.firstMap.getFlaggedParticles()
 
+    def insertIntermediateResolutionPadding(self, ratio, padCells):
+        """gasmapper.hpp:299-310: padding goes around the dark-matter map only."""
+        if self.gasFirst:
+            return AddGasMapper(self.firstMap, self.secondMap.insertIntermediateResolutionPadding(ratio, padCells), True)
+        return AddGasMapper(self.firstMap.insertIntermediateResolutionPadding(ratio, padCells), self.secondMap, False)
+
+
+def _expandFlaggedRegion(flags, n, nCells):
+    """Grid::expandFlaggedRegion (grid.hpp:277-306): the +-1 neighbours along each axis, nCells times (periodic)."""
+    flags = np.asarray(flags, dtype=np.int64)
+    for _ in range(nCells):
+        for axis in range(3):
+            c = np.stack(np.unravel_index(flags, (n, n, n)), axis=0)
+            out = [flags]
+            for step in (1, -1):
+                d = c.copy()
+                d[axis] = (d[axis] + step) % n
+                out.append(np.ravel_multi_index(tuple(d), (n, n, n)))
+            flags = np.unique(np.concatenate(out))
+    return flags
+
 
 def references(mapper, grid):
     """ParticleMapper::references: does the mapper use (a view of) this stored grid?"""
@@ -353,7 +412,8 @@ def extendParticleListToUnreferencedGrids(mapper, context):
 
 
 def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, baryonsOnAllLevels=False, gasFirst=False,
-                         supersample=1, subsample=1, supersampleGas=1, flaggedGadgetParticleType=None, flaggedCells=None):
+                         supersample=1, subsample=1, supersampleGas=1, flaggedGadgetParticleType=None, flaggedCells=None,
+                         autopad=0):
     """ICGenerator::updateParticleMapper (ic.hpp:1129-1236) without padding and strays: the one-level mapper of the base
     grid, wrapped once per zoom level with that level's zoomParticleArray (stored on the context by zoom.initZoomGrid);
     with OmegaBaryons0 > 0 the mass is split into a gas mapper (deepest level only unless baryonsOnAllLevels) and a
@@ -381,8 +441,12 @@ def updateParticleMapper(context, gadgetTypesForLevels=None, cosmology=None, bar
         gas, dm = m.splitMass(T(T(cosmology.OmegaBaryons0) / T(cosmology.OmegaM0)),
                               list(context.grids) if baryonsOnAllLevels else [context.getGridForLevel(nl - 1)])
         gas, dm = resample(gas, supersampleGas, 1), resample(dm, supersample, subsample)
-        return AddGasMapper(gas, dm, True) if gasFirst else AddGasMapper(dm, gas, False)
-    return resample(m, supersample, subsample)
+        m = AddGasMapper(gas, dm, True) if gasFirst else AddGasMapper(dm, gas, False)
+    else:
+        m = resample(m, supersample, subsample)
+    if autopad > 0:
+        m = m.insertIntermediateResolutionPadding(2, autopad)      # ic.hpp:1216-1218
+    return m
 
 
 def particle_mass(grid, cosmology):

@@ -114,7 +114,7 @@ def test_errors_abort_with_the_reference_message_format(tmp_path):
     p.write_text("Om 0.3\n# comment\nzoomgrid 2 64\n")
     with pytest.raises(icgen.L.GxError, match=r'Error ".*base grid" on line 3 \("zoomgrid 2 64"\)'):
         icgen.run_paramfile(str(p), log=lambda s: None)
-    p.write_text("base_grid 50 16\nautopad 2\n")
+    p.write_text("base_grid 50 16\noutformat grafic\n")
     with pytest.raises(icgen.L.GxError, match="not supported"):
         icgen.run_paramfile(str(p), log=lambda s: None)
     p.write_text("no_such_command 1\n")

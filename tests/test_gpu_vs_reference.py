@@ -89,7 +89,7 @@ def test_zoom_with_modifications_matches_the_reference_binary(tmp_path, golden_d
                                   "gadget3_types_two_files", "gadget3_trimmed_window", "tipsy_gas", "gadget3_gas",
                                   "gadget2_gas_all_levels", "tipsy_supersample2", "gadget3_subsample2_supersample3",
                                   "tipsy_gas_supersamplegas2_supersample3_three_levels", "tipsy_strays",
-                                  "gadget3_strays_supersample2"])
+                                  "gadget3_strays_supersample2", "gadget3_gas_autopad2"])
 def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, case):
     """The particle mappers (OneLevel / nested TwoLevel ordering, per-level gadget types, the trimming of the zoom list
     to a user-placed window) and the tipsy / gadget writers: the files written from the device-evaluated particles are
@@ -119,6 +119,8 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     three = "three" in case
     if three:
         pf += "centre 20 33 41\nselect_sphere 3\nzoomgrid 2 32\n"
+    if "autopad" in case:                 # a x4 zoom in one step, padded with a shell of x2 particles
+        pf = pf.replace("zoomgrid 2 32", "zoomgrid 4 32").replace("select_sphere 7", "select_sphere 3") + "autopad 2\n"
     import re as _re
     resample = {k: int(v) for k, v in _re.findall(r"(supersamplegas|supersample|subsample)(\d)", case)}
     for k, v in resample.items():
@@ -130,8 +132,10 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     for s in ("dm", "all"):
         ctx.setPowerspectrumGenerator(s, gb.CAMB(cos, _camb_file(golden_dir), s))
     ctx.allowStrays = "strays" in case
+    if "autopad" in case:
+        radius = 3
     Z.selectSphere(ctx, (20, 33, 41), radius)
-    Z.initZoomGrid(ctx, 2, 32, corner=corner)
+    Z.initZoomGrid(ctx, 4 if "autopad" in case else 2, 32, corner=corner)
     if "strays" in case:
         assert "stray particle mode" in out and len(ctx.zoomParticleArray[0]) == len(ctx.getGridForLevel(0).getFlaggedCells())
     if case == "gadget3_trimmed_window":
@@ -144,7 +148,7 @@ def test_zoom_particle_files_match_the_reference_binary(tmp_path, golden_dir, ca
     gen = GM.MultiLevelParticleGenerator(field)
     mapper = PM.updateParticleMapper(ctx, types, cos, "all_levels" in case, gasFirst=(fmt == "tipsy"),
                                      supersample=resample.get("supersample", 1), subsample=resample.get("subsample", 1),
-                                     supersampleGas=resample.get("supersamplegas", 1))
+                                     supersampleGas=resample.get("supersamplegas", 1), autopad=2 if "autopad" in case else 0)
     assert mapper.size() - mapper.size_gas() == int(re.search(r"number dm particles=(\d+)", out).group(1))
     assert mapper.size_gas() == int(re.search(r"number gas particles=(\d+)", out).group(1))
     ours = tmp_path / "ours"
