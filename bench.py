@@ -4,7 +4,7 @@
 One "step" = the whole hot path for one IC: draw white noise from the seed (GSL-exact, parallel Fourier order)
 -> delta_k = sqrt(C(k)) * noise -> psi_xyz = c2r(i k_j delta_k / k^2) -> particle positions and velocities.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n GRID] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n GRID] [--impl ours|reference|reference-cufft]
 
   value : N^3 / step time, device timed (CUDA events), results left in HBM (staging buffer)
   e2e   : the same through the C-ABI call with HOST buffers: the transfer table is uploaded and the particles are
@@ -117,14 +117,14 @@ def cpu_port_step(n, threads):
     return time.perf_counter() - t0
 
 
-def reference_binary_step(n, workdir=None):
+def reference_binary_step(n, workdir=None, cufft=False):
     """One IC of the same workload through the reference ITSELF (oracle/_ref/genetIC: the unmodified sources compiled
     against the stand-in FFTW3/GSL/HDF5 headers of oracle/shims/): whole-process wall clock, including the tipsy file it
     has to write (the reference has no output-less mode). Returns (seconds, threads) or None if the binary is absent."""
     import shutil
     import tempfile
     import oracle
-    if oracle.ref_binary() is None:
+    if oracle.ref_binary(cufft) is None:
         return None
     d = tempfile.mkdtemp(prefix="gx_ref_", dir=workdir)
     try:
@@ -132,7 +132,7 @@ def reference_binary_step(n, workdir=None):
               "camb %s\nrandom_seed %d\noutname bench\noutdir ./\noutformat tipsy\nbase_grid %r %d\ndone\n"
               % (os.path.basename(CAMB_FILE), SEED, box_for(n), n))
         t0 = time.perf_counter()
-        oracle.run_ref(pf, d, [CAMB_FILE])
+        oracle.run_ref(pf, d, [CAMB_FILE], cufft=cufft)
         return time.perf_counter() - t0, os.cpu_count() or 1
     finally:
         shutil.rmtree(d, ignore_errors=True)
@@ -150,11 +150,23 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n = args.cpu_n
     kind = "port"
-    first = reference_binary_step(min(n, 64))  # warm-up (page cache, OpenMP pool) and the availability check
+    cufft = args.impl == "reference-cufft"   # the reference's own GPU path (USE_CUFFT=1: FFTs through cuFFTW, rest on the host)
+    try:
+        first = reference_binary_step(min(n, 64), cufft=cufft)  # warm-up (page cache, OpenMP pool) and the availability check
+    except RuntimeError as e:
+        if not cufft:
+            raise
+        first = None
+        print("reference-cufft failed: %s" % str(e).strip().splitlines()[-1], file=sys.stderr)
+    if cufft and first is None:
+        print(json.dumps({"impl": "reference-cufft", "unavailable": "oracle/_ref/genetIC_cufft not built, or no GPU for cuFFTW"}))
+        return 0
     if first is not None:
         kind = "reference"
-        times = [reference_binary_step(n)[0] for _ in range(max(1, min(args.steps, 3)))]
+        times = [reference_binary_step(n, cufft=cufft)[0] for _ in range(max(1, min(args.steps, 3)))]
         sample = REF_SAMPLE % (n, threads) + " (the %d^3 workload does not fit the CPU time budget)" % args.n
+        if cufft:
+            sample = sample.replace("radix-2 OpenMP FFT instead of FFTW", "USE_CUFFT=1: FFTs through the toolkit's cuFFTW on the GPU")
     else:
         for _ in range(max(0, min(args.warmup, 1))):
             cpu_port_step(min(n, 128), threads)
@@ -164,7 +176,7 @@ def run_reference(args):
                      n, args.n, threads)
     t = statistics.mean(times)
     v = n ** 3 / t
-    line = {"impl": "reference", "metric": "IC particles/sec (Zeldovich %d^3)" % args.n, "value": v,
+    line = {"impl": args.impl, "metric": "IC particles/sec (Zeldovich %d^3)" % args.n, "value": v,
             "unit": "particles/s", "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n, "f64"), "sample": sample},
@@ -359,13 +371,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cufft"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "2048")))
     ap.add_argument("--cpu-n", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-cufft"):
         return run_reference(args)
     return run_ours(args)
 

@@ -49,21 +49,27 @@ def build_ref(force=False):
     if os.path.isdir(os.path.join(REF_ROOT, "genetIC", "src")):
         srcs = [os.path.join(_HERE, "build_ref.sh"), os.path.join(_HERE, "gx_oracle.c")] + \
                [os.path.join(_HERE, "shims", f) for f in ("fft_shim.cpp", "gsl_shim.cpp", "fftw3.h", "highfive/highfive.hpp")]
-        if force or not os.path.exists(REF_BINARY) or os.path.getmtime(REF_BINARY) < max(os.path.getmtime(f) for f in srcs):
+        newest = max(os.path.getmtime(f) for f in srcs)
+        have_cufft = os.path.exists("/usr/local/cuda/include/cufftw.h")
+        stale = not os.path.exists(REF_BINARY) or os.path.getmtime(REF_BINARY) < newest or \
+            (have_cufft and (not os.path.exists(REF_BINARY + "_cufft") or os.path.getmtime(REF_BINARY + "_cufft") < newest))
+        if force or stale:
             subprocess.check_call(["/bin/sh", os.path.join(_HERE, "build_ref.sh"), REF_ROOT], stdout=subprocess.DEVNULL)
     return ref_binary()
 
 
-def ref_binary():
-    """Path of the compiled reference (oracle/_ref/genetIC) if it exists and is executable, else None."""
-    return REF_BINARY if os.access(REF_BINARY, os.X_OK) else None
+def ref_binary(cufft=False):
+    """Path of the compiled reference (oracle/_ref/genetIC; cufft=True: oracle/_ref/genetIC_cufft, the reference's own
+    USE_CUFFT=1 GPU path through the toolkit's cuFFTW) if it exists and is executable, else None."""
+    exe = REF_BINARY + ("_cufft" if cufft else "")
+    return exe if os.access(exe, os.X_OK) else None
 
 
-def run_ref(paramfile_text, workdir, files=(), timeout=3600, args=()):
+def run_ref(paramfile_text, workdir, files=(), timeout=3600, args=(), cufft=False):
     """Runs the compiled reference on a paramfile written into `workdir` (extra input files are copied next to it).
     Returns its combined stdout/stderr. Raises if the binary is missing or exits non-zero."""
     import shutil
-    exe = ref_binary()
+    exe = ref_binary(cufft)
     if exe is None:
         raise RuntimeError("oracle/_ref/genetIC has not been built (needs /root/reference: oracle.build_ref())")
     os.makedirs(workdir, exist_ok=True)

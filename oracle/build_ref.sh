@@ -24,3 +24,12 @@ wait
 $CXX -fopenmp -o "$OUT/genetIC" "$OUT"/main.o "$OUT"/tools_logging.o "$OUT"/tools_progress_progress.o "$OUT"/tools_filesystem.o \
   "$OUT/fft_shim.o" "$OUT/gsl_shim.o" "$OUT/gx_oracle.o" -lm -lpthread
 echo "$OUT/genetIC"
+# The only GPU path the reference ships: USE_CUFFT=1 (genetIC/Makefile:59-70, fourier.hpp:6-8), its FFTs through cuFFTW.
+# Same unmodified sources, the real cuFFTW of the CUDA toolkit instead of the FFT stand-in (GSL / HDF5 stand-ins as above).
+CUDA=${CUDA_HOME:-/usr/local/cuda}
+if [ -f "$CUDA/include/cufftw.h" ] && [ -f "$CUDA/lib64/libcufftw.so" ]; then
+  $CXX $CFLAGS $CODEOPTIONS -DUSE_CUFFT -I"$CUDA/include" -c "$REF/src/main.cpp" -o "$OUT/main_cufft.o"
+  $CXX -fopenmp -o "$OUT/genetIC_cufft" "$OUT"/main_cufft.o "$OUT"/tools_logging.o "$OUT"/tools_progress_progress.o \
+    "$OUT"/tools_filesystem.o "$OUT/gsl_shim.o" "$OUT/gx_oracle.o" -L"$CUDA/lib64" -Wl,-rpath,"$CUDA/lib64" -lcufftw -lcufft -lcudart -lm -lpthread
+  echo "$OUT/genetIC_cufft"
+fi
