@@ -16,7 +16,8 @@ tests use the committed copies.
   * particle mappers / writers: test_10b (zoom x3, variable-mass gadget3) and test_10c (zoom with gadget particle types
     1 and 0) reference_output -> header[:208] + every 53rd particle (pos, vel, ids, mass) and the per-type counts;
     mapper_test_01a_zoom (id file round trip through a two-level mapper) paramfile, zoomtest.txt, reference.txt;
-    mapper_test_01b / 03a / 03b / 05 / 07 (ids of one setup re-expressed in another, `mapper_relative_to`), text files
+    mapper_test_01b / 03a / 03b / 05 / 07 (ids of one setup re-expressed in another, `mapper_relative_to`), 04a-c (stray
+    particles), 06 (sub-sampling + adapt_mask + autopad in the input setup): text files
 """
 import os
 import shutil
@@ -117,7 +118,8 @@ for f in ("paramfile.txt", "unzoomed_paramfile.txt", "zoomtest.txt", "reference.
     cp(f"{REF}/mapper_test_01a_zoom/{f}", f"{HERE}/mapper_test_01a_zoom/{f}")
 # id files through `mapper_relative_to` (ids of one setup re-expressed in another): whole directories, text only
 for t in ("mapper_test_01b_zoom_gas", "mapper_test_03a_zoom_linkage", "mapper_test_03b_zoom_to_coarse",
-          "mapper_test_05_gadget_ptype", "mapper_test_07_ids_from_two_inputs"):
+          "mapper_test_05_gadget_ptype", "mapper_test_07_ids_from_two_inputs", "mapper_test_04a_stray",
+          "mapper_test_04b_stray_linkage", "mapper_test_04c_stray_wrapping", "mapper_test_06_intermediate_levels"):
     for f in os.listdir(f"{REF}/{t}"):
         cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
 print("ok")

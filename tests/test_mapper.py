@@ -82,11 +82,14 @@ def test_idfile_round_trip_three_levels_vs_reference_binary(tmp_path, golden_dir
 
 @pytest.mark.parametrize("test", ["mapper_test_01a_zoom", "mapper_test_01b_zoom_gas", "mapper_test_03a_zoom_linkage",
                                   "mapper_test_03b_zoom_to_coarse", "mapper_test_05_gadget_ptype",
-                                  "mapper_test_07_ids_from_two_inputs"])
+                                  "mapper_test_07_ids_from_two_inputs", "mapper_test_04a_stray",
+                                  "mapper_test_04b_stray_linkage", "mapper_test_04c_stray_wrapping",
+                                  "mapper_test_06_intermediate_levels"])
 def test_reference_mapper_tests_through_the_command_layer(golden_dir, tmp_path, monkeypatch, test):
     """The reference's mapper_test_* directories (run_mapper_tests.sh: run the paramfile, `diff reference.txt output.txt`)
     through genetic_b200.icgen: zoom mappers with and without gas, per-type gadget ordering, sub-sampled inputs, and
-    `mapper_relative_to` (ids of another setup, rebuilt by a field-less run of its paramfile). Pure host logic: the
+    `mapper_relative_to` (ids of another setup, rebuilt by a field-less run of its paramfile), stray particles, adapt_mask
+    and autopad. Pure host logic: the
     commands that need the device (`camb`, `done`) are not reached."""
     import shutil
     from genetic_b200 import icgen
