@@ -243,3 +243,21 @@ def saveFieldTipsyArray(filename, values):
     with open(filename, "wb") as f:
         f.write(struct.pack("<I", len(out) & 0xffffffff))
         out.tofile(f)
+
+
+def read_particles(filename):
+    """Reader for the files written above (tests and tools): tipsy (gas + dark records) or a single gadget2/3 file, as a
+    dict of arrays (pos, vel, mass, and ids / u for gadget, eps and the counts for tipsy)."""
+    with open(filename, "rb") as f:
+        head = f.read(4)
+    if head == b"\x00\x01\x00\x00":
+        g = read_gadget(filename)
+        return {k: g[k] for k in ("pos", "vel", "ids", "mass", "u") if k in g}
+    with open(filename, "rb") as f:
+        b = f.read()
+    a, n, ndim, ngas, ndark, nstar = struct.unpack("<diiiii", b[:28])
+    gas = np.frombuffer(b, dtype=np.float32, count=ngas * 12, offset=32).reshape(ngas, 12)
+    dark = np.frombuffer(b, dtype=np.float32, count=ndark * 9, offset=32 + ngas * 48).reshape(ndark, 9)
+    return {"a": np.array([a]), "pos": np.concatenate([gas[:, 1:4], dark[:, 1:4]]), "vel": np.concatenate([gas[:, 4:7], dark[:, 4:7]]),
+            "mass": np.concatenate([gas[:, 0], dark[:, 0]]), "eps": np.concatenate([gas[:, 9], dark[:, 7]]),
+            "n": np.array([ngas, ndark])}

@@ -18,10 +18,13 @@ tests use the committed copies.
     mapper_test_01a_zoom (id file round trip through a two-level mapper) paramfile, zoomtest.txt, reference.txt;
     mapper_test_01b / 03a / 03b / 05 / 07 (ids of one setup re-expressed in another, `mapper_relative_to`), 04a-c (stray
     particles), 06 (sub-sampling + adapt_mask + autopad in the input setup): text files
+  * mapper / writer feature tests 04a-d, 06a-d, 10d, 10e, 10h, 10i, 18, 01f, 01g, 03a, 17: paramfile and ~4000 evenly spaced
+    particles of reference_output (particles_sample.npz)
 """
 import os
 import shutil
 import struct
+import sys
 import numpy as np
 
 REF = "/root/reference/genetIC/tests"
@@ -122,4 +125,27 @@ for t in ("mapper_test_01b_zoom_gas", "mapper_test_03a_zoom_linkage", "mapper_te
           "mapper_test_04b_stray_linkage", "mapper_test_04c_stray_wrapping", "mapper_test_06_intermediate_levels"):
     for f in os.listdir(f"{REF}/{t}"):
         cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
+
+# particle goldens of the mapper / writer features (sub/supersampling, gas, strays, flagged and per-level gadget types,
+# autopad, adapt_mask, velocity offset, reversal): paramfile (+ id file) and every k-th particle of reference_output
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from genetic_b200 import output as OUT  # noqa: E402  (reader only)
+for t in ("test_04a_supersampling", "test_04b_subsampling", "test_04c_doublezoom_supersampling", "test_04d_gas_supersampling",
+          "test_06a_stray_particles", "test_06b_stray_supersample", "test_06c_stray_subsampling", "test_06d_stray_wrapping_zoom",
+          "test_10d_gadget_flagged_particles", "test_10e_gadget_zoom_ptype_resample", "test_10i_gadget_zoom_ptype_autopad",
+          "test_18_intermediate_levels", "test_01f_two_zooms_adapt_mask", "test_03a_baryons_basegrid",
+          "test_10h_gadget_zoom_ptype_gas", "test_01g_zoom_grid_vel_offset", "test_17_reversal"):
+    cp(f"{REF}/{t}/paramfile.txt", f"{HERE}/{t}/paramfile.txt")
+    if os.path.exists(f"{REF}/{t}/zoomtest.txt"):
+        cp(f"{REF}/{t}/zoomtest.txt", f"{HERE}/{t}/zoomtest.txt")
+    d = OUT.read_particles(f"{REF}/{t}/reference_output")
+    n = len(d["pos"])
+    idx = np.arange(0, n, max(1, n // 4000))
+    arrays = {"index": idx, "count": np.array([n])}
+    for k in ("pos", "vel", "mass", "eps", "ids", "u"):
+        if k in d:
+            arrays[k] = d[k][idx] if len(d[k]) == n else d[k][:1]
+    if "n" in d:
+        arrays["n"] = d["n"]
+    np.savez_compressed(f"{HERE}/{t}/particles_sample.npz", **arrays)
 print("ok")

@@ -23,18 +23,7 @@ REF = "/root/reference/genetIC/tests"
 
 def read_particles(fn):
     from genetic_b200 import output as OUT
-    raw = open(fn, "rb").read(8)
-    if raw[:4] == b"\x00\x01\x00\x00":
-        g = OUT.read_gadget(fn)
-        return {k: g[k] for k in ("pos", "vel", "ids", "mass", "u") if k in g}
-    import struct
-    b = open(fn, "rb").read()
-    a, n, ndim, ngas, ndark, nstar = struct.unpack("<diiiii", b[:28])
-    gas = np.frombuffer(b, dtype=np.float32, count=ngas * 12, offset=32).reshape(ngas, 12)
-    dark = np.frombuffer(b, dtype=np.float32, count=ndark * 9, offset=32 + ngas * 48).reshape(ndark, 9)
-    return {"a": np.array([a]), "pos": np.concatenate([gas[:, 1:4], dark[:, 1:4]]), "vel": np.concatenate([gas[:, 4:7], dark[:, 4:7]]),
-            "mass": np.concatenate([gas[:, 0], dark[:, 0]]), "eps": np.concatenate([gas[:, 9], dark[:, 7]]),
-            "n": np.array([ngas, ndark])}
+    return OUT.read_particles(fn)
 
 
 def read_multifile(first):
