@@ -1,0 +1,59 @@
+"""Mapper / writer features of the reference through the command layer, against subsampled reference_output goldens
+(tests/golden/*/particles_sample.npz, make_golden.py). Kept in its own file, collected after the other GPU files: these
+cases were added after round 1's GPU minutes were spent (host logic verified on the mock device and against the reference
+binary; the kernels they use are covered by the earlier files)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from genetic_b200 import output as OUT
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("gx_paramfile_helpers", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_paramfile.py"))
+_pf = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_pf)
+_run = _pf._run
+
+_spec2 = importlib.util.spec_from_file_location("gx_reference_helpers", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_vs_reference.py"))
+_vr = importlib.util.module_from_spec(_spec2)
+_spec2.loader.exec_module(_vr)
+
+
+@pytest.mark.skipif(_vr.oracle.ref_binary() is None, reason="oracle/_ref/genetIC not built")
+@pytest.mark.parametrize("case", _vr.ADDED_LATER)
+def test_stray_and_autopad_particle_files_match_the_reference_binary(tmp_path, golden_dir, case):
+    """Stray particles (with and without supersampling) and autopad with gas: files byte-identical to the reference binary's."""
+    _vr.zoom_particle_files_case(tmp_path, golden_dir, case)
+
+
+@pytest.mark.parametrize("test", [
+    "test_04a_supersampling", "test_04b_subsampling", "test_04c_doublezoom_supersampling", "test_04d_gas_supersampling",
+    "test_06a_stray_particles", "test_06b_stray_supersample", "test_06c_stray_subsampling", "test_06d_stray_wrapping_zoom",
+    "test_10d_gadget_flagged_particles", "test_10e_gadget_zoom_ptype_resample", "test_10i_gadget_zoom_ptype_autopad",
+    "test_18_intermediate_levels", "test_01f_two_zooms_adapt_mask", "test_03a_baryons_basegrid",
+    "test_10h_gadget_zoom_ptype_gas", "test_01g_zoom_grid_vel_offset", "test_17_reversal"])
+def test_mapper_and_writer_feature_goldens(golden_dir, tmp_path, test):
+    """Sub/supersampling (dark matter and gas), stray particles, flagged and per-level gadget types, autopad, adapt_mask,
+    velocity offset and field reversal: the reference's paramfiles against ~4000 evenly spaced particles of its
+    reference_output files, with the tolerances of its tools/compare.py (1e-4 on float32 positions / velocities, 1e-6
+    on masses)."""
+    d, _ = _run(golden_dir, tmp_path, test)
+    out = [f for f in os.listdir(d) if f.endswith(".tipsy") or f.endswith(".gadget2") or f.endswith(".gadget3")]
+    assert len(out) == 1
+    ours = OUT.read_particles(str(d / out[0]))
+    gold = np.load(str(d / "particles_sample.npz"))
+    assert len(ours["pos"]) == int(gold["count"][0])
+    idx = gold["index"]
+    if "n" in gold.files:
+        assert np.array_equal(ours["n"], gold["n"])              # gas / dark counts
+    if "ids" in gold.files:
+        assert np.array_equal(ours["ids"][idx], gold["ids"])
+    assert np.abs(ours["pos"][idx] - gold["pos"]).max() < 1e-4
+    assert np.abs(ours["vel"][idx] - gold["vel"]).max() < 1e-4 * max(1.0, np.abs(gold["vel"]).max() / 10)
+    if "mass" in gold.files and len(gold["mass"]) == len(idx):
+        assert np.abs(ours["mass"][idx] - gold["mass"]).max() < 1e-6 * max(1.0, np.abs(gold["mass"]).max())
+    if "eps" in gold.files:
+        assert np.abs(ours["eps"][idx] - gold["eps"]).max() < 1e-6

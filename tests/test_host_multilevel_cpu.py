@@ -67,3 +67,8 @@ for _name in dir(_pf):
     if _name.startswith("test_"):
         globals()["test_paramfile_" + _name[5:]] = getattr(_pf, _name)
 test_chunked_evaluation_equals_one_shot = _mapper_cases.test_chunked_evaluation_equals_one_shot
+
+
+_fg = _load("gx_feature_golden_cases", os.path.join(HERE, "test_gpu_zz_feature_goldens.py"))
+test_paramfile_mapper_and_writer_feature_goldens = _fg.test_mapper_and_writer_feature_goldens
+test_stray_and_autopad_particle_files_match_the_reference_binary = _fg.test_stray_and_autopad_particle_files_match_the_reference_binary
