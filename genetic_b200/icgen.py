@@ -590,6 +590,8 @@ class ICGenerator:
         self.initialiseRandomComponentIfUninitialised()
         if self.outputField.getTransferType() == GM.WHITENOISE:
             self.outputField.applyPowerSpectrumFor(GM.ALL)                      # applyPowerSpec (ic.hpp:802-818)
+        if self._streamableUnigrid():
+            return self._writeUnigridStreaming()
         if self.pParticleGenerator is None:
             self.log("Calculating particles from overdensity fields...")
             self.pParticleGenerator = GM.MultiLevelParticleGenerator(self.outputField)
@@ -614,6 +616,117 @@ class ICGenerator:
         if os.environ.get("GX_TIMING", "0") == "1":
             self.log("[timing] mapper %.3f s, particle evaluation + copy %.3f s, file %.3f s"
                      % (t1 - t0, t2 - t1, time.perf_counter() - t2))
+        self.log("Finished writing initial conditions")
+
+    # ---- large single-level ICs: two fields on the device, particles streamed into the memory-mapped output file --------
+    def _streamableUnigrid(self):
+        """One level, dark matter only, no resampling or retyping: particle id = cell index, so the offsets can be formed
+        one component at a time (the fused transform of gx_zeldovich_offset) and evaluated by id range straight into the
+        file -- delta + one psi field on the device instead of delta + three, nothing of size n^3 on the host. Used from
+        512^3 upwards (GX_STREAM_UNIGRID=1/0 forces it on / off); a 2048^3 f64 IC needs 2 x 68.8 GB of the 180 GB."""
+        env = os.environ.get("GX_STREAM_UNIGRID", "")
+        if env == "0" or self.context.getNumLevels() != 1 or self.pParticleGenerator is not None:
+            return False
+        if float(self.cosmology.OmegaBaryons0) > 0 or self.supersample > 1 or self.subsample > 1 or \
+                self.flaggedGadgetParticleType is not None or self.nGadgetFiles != 1:
+            return False
+        return env == "1" or self.context.getGridForLevel(0).size >= 512
+
+    def _writeUnigridStreaming(self, chunk=1 << 24):
+        import ctypes as C
+        from .host import Field, _dt
+        lib = L.load()
+        grid = self.context.getGridForLevel(0)
+        delta = self.outputField.getFieldForLevel(0)
+        delta.toFourier()
+        n, n3 = grid.size, grid.size3
+        T = self.dtype.type
+        boxlen = float(grid.periodicDomainSize)
+        mass, eps = PM.particle_mass(grid, self.cosmology), PM.particle_eps(grid, self.epsNorm)
+        self.log("Writing output; number dm particles=%d, number gas particles=0" % n3)
+        tipsy = self.outputFormat == "tipsy"
+        offset = any(float(v) != 0.0 for v in self.velOffset)
+        wide = tipsy or offset                       # unit conversions / the offset are applied in T before the float32 store
+        out_dtype = self.dtype if wide else np.dtype(np.float32)
+        esz, odt = out_dtype.itemsize, _dt(out_dtype)
+        if tipsy:
+            # TipsyOutput::operator() (tipsy.hpp:207-271); the mass sum over identical particles, sequentially in double
+            tot, m = 0.0, float(mass)
+            for c0 in range(0, n3, 1 << 22):            # tot_mass += mass, one particle after the other (tipsy.hpp:217-223)
+                tot = float(np.cumsum(np.concatenate([[tot], np.full(min(1 << 22, n3 - c0), m)]))[-1])
+            mass_factor = float(self.cosmology.OmegaM0) / tot
+            pos_factor = 1. / boxlen
+            dKpcUnit = boxlen * 1000 / float(self.cosmology.hubble)
+            dMsolUnit = 1e10 / float(self.cosmology.hubble) / mass_factor
+            dKmsUnit = float(np.sqrt(4.3022682e-6 * dMsolUnit / dKpcUnit))
+            vel_factor = float(self.cosmology.scalefactor) ** -0.5 / dKmsUnit
+            fn = self.getOutputPath() + ".tipsy"
+            with open(fn, "wb") as f:
+                f.write(OUT.struct.pack("<diiiii4x", float(self.cosmology.scalefactor), n3, 3, 0, n3, 0))
+                f.truncate(32 + n3 * 36)
+            rec = np.memmap(fn, dtype=np.float32, mode="r+", offset=32, shape=(n3, 9))
+            with open("tipsy.param", "w") as f:
+                f.write("dKpcUnit = %g\ndMsolUnit = %g\ndHubble0 = %g\nbComove = 1 \n"
+                        % (dKpcUnit, dMsolUnit, 0.1 * float(self.cosmology.hubble) * dKpcUnit / dKmsUnit))
+            for c0 in range(0, n3, chunk):
+                rec[c0:c0 + chunk, 0] = np.float32(float(mass) * mass_factor)
+                rec[c0:c0 + chunk, 7] = np.float32(float(eps) * pos_factor)
+                rec[c0:c0 + chunk, 8] = 0.0
+        else:
+            version = int(self.outputFormat[-1])
+            fn = self.getOutputPath() + ".gadget" + str(version)
+            counts = [0] * 6
+            counts[self.gadgetTypesForLevels[0]] = n3
+            masses = [0.0] * 6
+            masses[self.gadgetTypesForLevels[0]] = float(mass)
+            header = OUT._gadget_header(version, masses, counts, counts, 1, boxlen, self.cosmology, False)
+            blocks = [("pos", 12), ("vel", 12), ("ids", 8)]
+            with open(fn, "wb") as f:
+                OUT._fortran(f, header)
+                where = {}
+                for name, width in blocks:
+                    nbytes = n3 * width
+                    marker = OUT.struct.pack("<i", nbytes if nbytes <= 0x7fffffff else 0x7fffffff)
+                    f.write(marker)
+                    where[name] = f.tell()
+                    f.seek(nbytes, 1)
+                    f.write(marker)
+            posm = np.memmap(fn, dtype=np.float32, mode="r+", offset=where["pos"], shape=(n3, 3))
+            velm = np.memmap(fn, dtype=np.float32, mode="r+", offset=where["vel"], shape=(n3, 3))
+            idm = np.memmap(fn, dtype=np.uint64, mode="r+", offset=where["ids"], shape=(n3,))
+            for c0 in range(0, n3, chunk):
+                idm[c0:c0 + chunk] = np.arange(c0, min(n3, c0 + chunk), dtype=np.uint64)
+        ratio = self.cosmology.zeldovichVelocityToOffsetRatio(grid.dtype)
+        m = min(chunk, n3)
+        dpos, dvel = C.c_void_p(), C.c_void_p()
+        lib.gx_malloc(C.byref(dpos), m * esz)
+        lib.gx_malloc(C.byref(dvel), m * esz)
+        hp, hv = np.empty(m, dtype=out_dtype), np.empty(m, dtype=out_dtype)
+        psi = Field(grid, fourier=True, stream=delta.stream)
+        try:
+            for axis in range(3):
+                lib.gx_zeldovich_offset(delta.ptr, psi.ptr, n, delta.dt, float(grid.thisGridSize), axis, delta.stream)
+                for c0 in range(0, n3, chunk):
+                    cnt = min(chunk, n3 - c0)
+                    lib.gx_emit_component(psi.ptr, n, psi.dt, axis, float(grid.cellSize), float(grid.offsetLower[axis]),
+                                          float(grid.periodicDomainSize), ratio, dpos, dvel, odt, 1, c0, cnt, delta.stream)
+                    lib.gx_memcpy_d2h(hp.ctypes.data_as(C.c_void_p), dpos, cnt * esz, delta.stream)
+                    lib.gx_memcpy_d2h(hv.ctypes.data_as(C.c_void_p), dvel, cnt * esz, delta.stream)
+                    lib.gx_synchronize(delta.stream)
+                    p, v = hp[:cnt], hv[:cnt]
+                    if offset:
+                        v = v + T(self.velOffset[axis])
+                    if tipsy:
+                        rec[c0:c0 + cnt, 1 + axis] = p.astype(np.float64) * pos_factor - 0.5
+                        rec[c0:c0 + cnt, 4 + axis] = v.astype(np.float64) * vel_factor
+                    else:
+                        posm[c0:c0 + cnt, axis] = p
+                        velm[c0:c0 + cnt, axis] = v
+        finally:
+            lib.gx_free(dpos)
+            lib.gx_free(dvel)
+        for mm in ((rec,) if tipsy else (posm, velm, idm)):
+            mm.flush()
         self.log("Finished writing initial conditions")
 
     def _dumpGridData(self, level, field, prefix="grid"):

@@ -221,6 +221,11 @@ class MockLib:
         self.F(psi, n)[:] = M.zeldovich_offsets_fourier(self.F(d, n), L)[axis]
         return 0
 
+    def gx_zeldovich_offset(self, d, psi, n, dt, L, axis, st):
+        """The fused form: psi <- c2r(i k_axis delta / k^2), real space."""
+        self.R(psi, n)[:] = M.to_real(M.zeldovich_offsets_fourier(self.F(d, n), L)[axis])
+        return 0
+
     def gx_scale_inv_k2(self, p, n, dt, L, scale, potential_form, st):
         g = ML.Grid(L, n)
         k2 = ML.k_magnitude(g) ** 2

@@ -121,3 +121,4 @@ def test_errors_abort_with_the_reference_message_format(tmp_path):
     with pytest.raises(icgen.L.GxError, match="Unknown command no_such_command"):
         icgen.run_paramfile(str(p), log=lambda s: None)
 
+

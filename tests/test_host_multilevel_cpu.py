@@ -72,3 +72,4 @@ test_chunked_evaluation_equals_one_shot = _mapper_cases.test_chunked_evaluation_
 _fg = _load("gx_feature_golden_cases", os.path.join(HERE, "test_gpu_zz_feature_goldens.py"))
 test_paramfile_mapper_and_writer_feature_goldens = _fg.test_mapper_and_writer_feature_goldens
 test_stray_and_autopad_particle_files_match_the_reference_binary = _fg.test_stray_and_autopad_particle_files_match_the_reference_binary
+test_streaming_unigrid_writer_equals_the_mapped_path = _fg.test_streaming_unigrid_writer_equals_the_mapped_path
