@@ -11,8 +11,9 @@
 //
 // Status: the host logic (selection, window placement, layouts, id flagging, masses) is checked on CPU against the Python
 // layer by tests/test_cpp_zoom.py through `host/genetic_b200_zoom --layout-only`; on the B200 the driver's gadget3 file of a
-// two-level zoom is byte-identical to the reference binary's (profiles/r1s25_*, tests/test_cpp_zoom.py -m gpu). The tipsy
-// and gas branches of the writers have so far only been compiled.
+// two-level zoom is byte-identical to the reference binary's (profiles/r1s25_*, tests/test_cpp_zoom.py -m gpu). The writers
+// (tipsy with gas records, gadget2/3 with gas, per-level types, variable masses, multi-file) are checked on CPU byte for
+// byte against the Python writers through `--particles-from`.
 #ifndef GENETIC_B200_ZOOM_HPP
 #define GENETIC_B200_ZOOM_HPP
 
@@ -670,6 +671,7 @@ public:
   int noiseMode = -1, nGadgetFiles = 1;
   bool reverse = false, fixPower = false, baryonsOnAllLevels = false;
   bool layoutOnly = false;               // stop before anything touches the device (CPU check of the host logic)
+  std::string particlesFile;             // CPU check of the writers: positions / velocities [N][3] doubles each, in mapper order
   std::array<T, 3> centre{0, 0, 0};
   typename particle::mapper::ParticleMapper<T>::Ptr pMapper;
 
@@ -810,6 +812,28 @@ public:
     if (context.getNumLevels() == 0) throw std::runtime_error("No grid has been initialised");
     pMapper = mapper();
     if (layoutOnly) return;
+    const double boxlen0 = (double) context.getGridForLevel(0).periodicDomainSize;
+    if (!particlesFile.empty()) {  // writers only: the particles come from a file instead of the device
+      std::ifstream pf(particlesFile, std::ios::binary);
+      if (!pf.is_open()) throw std::runtime_error("Could not open " + particlesFile);
+      const size_t N = pMapper->size();
+      std::vector<double> buf(6 * N);
+      pf.read(reinterpret_cast<char *>(buf.data()), (std::streamsize) (buf.size() * sizeof(double)));
+      if ((size_t) pf.gcount() != buf.size() * sizeof(double)) throw std::runtime_error("particle file has the wrong size");
+      const std::string out = outputFolder + "/" + outputFilename;
+      if (outputFormat == "tipsy") {
+        particle::MappedParticles<T, T> P(*pMapper, nullptr, cosmo);
+        P.pos.assign(buf.begin(), buf.begin() + 3 * N);
+        P.vel.assign(buf.begin() + 3 * N, buf.end());
+        io::tipsy::saveMapped<T>(out + ".tipsy", boxlen0, P, cosmo);
+      } else {
+        particle::MappedParticles<T, float> P(*pMapper, nullptr, cosmo);
+        P.pos.resize(3 * N); P.vel.resize(3 * N);
+        for (size_t i = 0; i < 3 * N; ++i) { P.pos[i] = (float) T(buf[i]); P.vel[i] = (float) T(buf[3 * N + i]); }
+        io::gadget::save<T>(out + ".gadget", boxlen0, P, cosmo, outputFormat == "gadget2" ? 2 : 3, nGadgetFiles);
+      }
+      return;
+    }
     if (noiseMode < 0) throw std::runtime_error("The random number generator has not been seeded");
     const size_t nl = context.getNumLevels();
     std::vector<std::shared_ptr<fields::Field<T>>> delta;
