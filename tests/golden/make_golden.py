@@ -20,6 +20,7 @@ tests use the committed copies.
     particles), 06 (sub-sampling + adapt_mask + autopad in the input setup): text files
   * mapper / writer feature tests 04a-d, 06a-d, 10d, 10e, 10h, 10i, 18, 01f, 01g, 03a, 17: paramfile and ~4000 evenly spaced
     particles of reference_output (particles_sample.npz)
+  * profiler_test_config3: SURVEY 8(d) config 3 run through the reference binary built here (oracle/_ref/genetIC), sampled
 """
 import os
 import shutil
@@ -148,4 +149,19 @@ for t in ("test_04a_supersampling", "test_04b_subsampling", "test_04c_doublezoom
     if "n" in d:
         arrays["n"] = d["n"]
     np.savez_compressed(f"{HERE}/{t}/particles_sample.npz", **arrays)
+
+# SURVEY 8(d) config 3 (profiler_test, modernised): ~6000 evenly spaced particles of the output of the reference BINARY
+# (oracle/_ref/genetIC; 36 minutes on 8 threads, so only regenerated on request: GX_GOLDEN_SLOW=1)
+cfg3 = f"{HERE}/profiler_test_config3"
+cp(os.path.join(os.path.dirname(os.path.dirname(HERE)), "tools", "paramfiles", "profiler_test_modernised.txt"), f"{cfg3}/paramfile.txt")
+if os.environ.get("GX_GOLDEN_SLOW") == "1":
+    import tempfile
+    import oracle
+    with tempfile.TemporaryDirectory() as tmp:
+        oracle.run_ref(open(f"{cfg3}/paramfile.txt").read(), tmp, [f"{HERE}/camb_transfer_kmax40_z0.dat"], timeout=4 * 3600)
+        d = OUT.read_particles(os.path.join(tmp, "test_9.tipsy"))
+    n = len(d["pos"])
+    idx = np.arange(0, n, n // 6000)
+    np.savez_compressed(f"{cfg3}/particles_sample.npz", index=idx, count=np.array([n]), pos=d["pos"][idx], vel=d["vel"][idx],
+                        mass=d["mass"][idx], eps=d["eps"][idx], n=d["n"])
 print("ok")
