@@ -27,7 +27,10 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
     // (L2 resident), the product is the one Field::applyTransferFunction would form, and the transfer sweep (2 B) is gone
     const void *table = nullptr;
     if ((rc = build_transfer_table(n, dt, p->grid_length, spectrum, 0.5, 1, st, &table))) return rc;
-    if ((rc = noise_draw_scaled(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, st, table))) return rc;
+    // (the work field is idle until the first transform: it holds the staged draws of the noise generator)
+    if ((rc = noise_draw_scaled(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, st, table, psi_field,
+                                gx_field_bytes(n, dt))))
+      return rc;
   } else {
     if ((rc = gx_noise_draw(delta_field, n, dt, p->seed, p->noise_mode, p->reverse_order, &off, stream))) return rc;
     if (p->fix_power && (rc = gx_unit_variance(delta_field, n, dt, stream))) return rc;

@@ -23,6 +23,7 @@
 //      the field is bit-identical to what the reference produces on the same machine.
 #include "../../include/genetic_b200.h"
 #include "rng_core.cuh"
+#include "rng_staged_core.cuh"
 #include "zig_tables.h"  // generated constant tables (GSL's published 128-level ziggurat)
 #include <cmath>
 #include <vector>
@@ -38,35 +39,12 @@ namespace fft { template <typename T> int fft3d(T *data, int n, int dir, cudaStr
 
 namespace rng {
 
-constexpr int kBc = 64;                 // increments per chunk
-constexpr int kChunkLen = kBc * 24;     // raw outputs per chunk
 constexpr int kThreads = 128;
-constexpr int kJumpBits = 40;
+constexpr int kJumpDigits = 3, kJumpRadix = 512;   // chunk index -> jump: three base-512 digits, one table product each
 
 __device__ unsigned int d_zig_ktab[128];
 __device__ double d_zig_wtab[128];
 __device__ double d_zig_ytab[128];
-
-struct StreamDesc {
-  State s0;              // seed state (used when the stream starts at block 0)
-  Big xs;                // X at block b0 (start block of the stream's first chunk)
-  long long b0;          // first block index of the stream's first chunk
-  int entry0;            // position of the first attempt inside the first chunk
-  int first_chunk;       // index of the stream's first chunk in the global chunk list
-  long long n_gauss;     // gaussians wanted from this stream
-  int shell;             // ks for per-shell streams, 0 otherwise
-};
-
-struct ChunkFn {
-  long long count[4];
-  unsigned char exit[4];
-  unsigned char reset;
-};
-
-struct ScanState {
-  long long base;
-  int entry;
-};
 
 struct TailEvent {
   long long g;       // stream-local gaussian index
@@ -92,25 +70,6 @@ template <typename T> struct Dest {
   // folded into the delivery -- the same rounded product per component as the separate sweep, one field sweep less
   const T *wtab;
 };
-
-__device__ __forceinline__ ChunkFn compose(const ChunkFn &f, const ChunkFn &g) {  // f first, then g
-  if (g.reset) return g;
-  ChunkFn h;
-  h.reset = f.reset;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    h.exit[e] = g.exit[f.exit[e]];
-    h.count[e] = f.count[e] + g.count[f.exit[e]];
-  }
-  return h;
-}
-
-__device__ __forceinline__ ScanState apply_fn(const ChunkFn &f, const ScanState &s) {
-  ScanState o;
-  if (f.reset) { o.entry = f.exit[0]; o.base = f.count[0]; }
-  else { o.entry = f.exit[s.entry]; o.base = s.base + f.count[s.entry]; }
-  return o;
-}
 
 // ---- delivery of gaussian g of a stream to its destination ---------------------------------------------------
 // calls before shell ks in the serial order: sum_{j<ks} 3 (2j)^2 = 2 (ks-1) ks (2ks-1)
@@ -288,7 +247,7 @@ struct ChunkParams {
   const StreamDesc *streams;
   int n_streams;
   int n_chunks;
-  const Big *jump;            // jump[j] = a^(397 * kBc * 2^j)
+  const Big *jump;            // jump[d * 512 + i] = a^(397 * kBc * i * 512^d)
   ChunkFn *fn;                // pass A output
   const ScanState *scan;      // pass B input
   unsigned long long *stream_end;  // pass B: raw position after the last wanted gaussian (per stream)
@@ -301,11 +260,16 @@ struct ChunkParams {
   ChunkFn *fn_out;            // pass A writes fn_out[chunk - first]
 };
 
+// jump[d][i] = J^(i * 512^d), J = a^(397 * kBc): at most three 576-bit products per chunk start (the bitwise table of
+// round 1 cost ~7.5 at 2048^3, a quarter of the chunk's generator work)
 __device__ __forceinline__ State chunk_start_state(const StreamDesc &sd, int q, const Big *jump) {
   if (sd.b0 == 0 && q == 0) return sd.s0;
   Big X = sd.xs;
-  for (int j = 0; j < kJumpBits; ++j)
-    if ((q >> j) & 1) X = modmul(X, jump[j]);
+#pragma unroll 1
+  for (int d = 0; d < kJumpDigits; ++d) {
+    const int digit = (q >> (9 * d)) & (kJumpRadix - 1);
+    if (digit) X = modmul(X, jump[d * kJumpRadix + digit]);
+  }
   return big_to_state(X);
 }
 
@@ -537,19 +501,48 @@ __global__ void raw_chunks_kernel(StreamDesc sd, const Big *jump, long long q0, 
 
 template <typename T> __global__ void zero_dc_real_kernel(T *field) { field[0] = (T) 0; }
 
+// accepted tail draws: x = R - log(U1) / R with the C library's log() -- the call gsl_ran_gaussian_ziggurat makes. ~6e-4 of
+// all draws (5 million at 2048^3): spread over the host threads.
+struct TailEvent;
+static void host_tail_values(const TailEvent *ev, double *val, unsigned int ntail);
 // ---- host driver ------------------------------------------------------------------------------------------------------
 static Big *g_jump = nullptr;
 static int ensure_jump_table() {
   if (g_jump) return 0;
-  std::vector<Big> h(kJumpBits);
+  std::vector<Big> h((size_t) kJumpDigits * kJumpRadix);
   Big base = modpow(big_a(), 397ull * kBc);
-  for (int j = 0; j < kJumpBits; ++j) { h[j] = base; base = modmul(base, base); }
+  for (int d = 0; d < kJumpDigits; ++d) {
+    Big acc = big_one();
+    for (int i = 0; i < kJumpRadix; ++i) { h[(size_t) d * kJumpRadix + i] = acc; acc = modmul(acc, base); }
+    base = acc;  // base^512
+  }
   GX_CUDA_CHECK(cudaMemcpyToSymbol(d_zig_ktab, gx_zig_ktab, sizeof(gx_zig_ktab)));
   GX_CUDA_CHECK(cudaMemcpyToSymbol(d_zig_wtab, gx_zig_wtab, sizeof(gx_zig_wtab)));
   GX_CUDA_CHECK(cudaMemcpyToSymbol(d_zig_ytab, gx_zig_ytab, sizeof(gx_zig_ytab)));
-  GX_CUDA_CHECK(cudaMalloc(&g_jump, sizeof(Big) * kJumpBits));
-  GX_CUDA_CHECK(cudaMemcpy(g_jump, h.data(), sizeof(Big) * kJumpBits, cudaMemcpyHostToDevice));
+  GX_CUDA_CHECK(cudaMalloc(&g_jump, sizeof(Big) * h.size()));
+  GX_CUDA_CHECK(cudaMemcpy(g_jump, h.data(), sizeof(Big) * h.size(), cudaMemcpyHostToDevice));
   return 0;
+}
+
+static void host_tail_values(const TailEvent *ev, double *val, unsigned int ntail) {
+  const double R = GX_ZIG_R;
+  auto work = [&](unsigned int i0, unsigned int i1) {
+    for (unsigned int i = i0; i < i1; ++i) {
+      const double U1 = 1.0 - (double) ev[i].u1 / 16777216.0;
+      const double x = R - std::log(U1) / R;
+      val[i] = ev[i].positive ? x : -x;
+    }
+  };
+  unsigned int nt = std::thread::hardware_concurrency();
+  if (nt > 32) nt = 32;
+  if (nt < 2 || ntail < 65536) { work(0, ntail); return; }
+  std::vector<std::thread> pool;
+  const unsigned int per = (ntail + nt - 1) / nt;
+  for (unsigned int t = 0; t < nt; ++t) {
+    const unsigned int i0 = t * per, i1 = std::min(ntail, i0 + per);
+    if (i0 < i1) pool.emplace_back(work, i0, i1);
+  }
+  for (auto &th : pool) th.join();
 }
 
 static long long calls_before_shell_host(long long ks) { return 2 * (ks - 1) * ks * (2 * ks - 1); }
@@ -757,29 +750,7 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
     double *val = (double *) pin_val;
     GX_CUDA_CHECK(cudaMemcpyAsync(ev, d_tails, sizeof(TailEvent) * ntail, cudaMemcpyDeviceToHost, cs));
     GX_CUDA_CHECK(cudaStreamSynchronize(cs));
-    // ~6e-4 of all draws: 5 million log() calls at 2048^3 -- on one core that was ~60 ms of idle GPU per draw
-    {
-      const double R = GX_ZIG_R;
-      auto work = [&](unsigned int i0, unsigned int i1) {
-        for (unsigned int i = i0; i < i1; ++i) {
-          const double U1 = 1.0 - (double) ev[i].u1 / 16777216.0;
-          const double x = R - std::log(U1) / R;
-          val[i] = ev[i].positive ? x : -x;
-        }
-      };
-      unsigned int nt = std::thread::hardware_concurrency();
-      if (nt > 32) nt = 32;
-      if (nt < 2 || ntail < 65536) work(0, ntail);
-      else {
-        std::vector<std::thread> pool;
-        const unsigned int per = (ntail + nt - 1) / nt;
-        for (unsigned int t = 0; t < nt; ++t) {
-          const unsigned int i0 = t * per, i1 = std::min(ntail, i0 + per);
-          if (i0 < i1) pool.emplace_back(work, i0, i1);
-        }
-        for (auto &th : pool) th.join();
-      }
-    }
+    host_tail_values(ev, val, ntail);
     GX_CUDA_CHECK(cudaMemcpyAsync(p_val, val, sizeof(double) * ntail, cudaMemcpyHostToDevice, cs));
     GX_TIMED("rng_tail_patch", cs);
     tail_patch_kernel<T><<<(ntail + 127) / 128, 128, 0, cs>>>(d_tails, (const double *) p_val, ntail, d_streams, dest);
@@ -791,12 +762,456 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
   return 0;
 }
 
+// ==== staged path for the parallel Fourier order (rng_staged_core.cuh) ====================================================
+// Owner table: slot (ix, iy, iz) of the field lives on the rank that holds ky row iy, in a [n][nyl][n/2+1] slab. One GPU:
+// world = 1, nyl = n, base[0] = the field. Several GPUs: base[r] are peer-mapped slab pointers (cudaIpc), so the delivery
+// kernel of the rank that generated a shell stores every mode straight into its owner's memory over NVLink.
+constexpr int kMaxPeers = 8;
+template <typename T> struct Owners {
+  T *base[kMaxPeers];
+  int n, nc, nyl;
+  __device__ __forceinline__ cplx<T> *slot(int a, int b, int c) const {
+    const int ix = a < 0 ? a + n : a, iy = b < 0 ? b + n : b;
+    const int o = iy / nyl, iyl = iy - o * nyl;
+    return reinterpret_cast<cplx<T> *>(base[o]) + ((size_t) c + (size_t) nc * ((size_t) iyl + (size_t) nyl * (size_t) ix));
+  }
+};
+
+struct GenParams {
+  const StreamDesc *streams;
+  int n_streams;
+  int first, count;        // global chunk range of the batch
+  const Big *jump;
+  ChunkFn *fn;             // per batch chunk
+  ListMeta *meta;
+  uint32_t *stage;         // kChunkStage words per batch chunk
+  StagedTail *tails;
+  unsigned int *tail_count;
+  unsigned int tail_cap;
+};
+
+struct SmemColumn {  // column tx of a [slots][kThreads] shared array: conflict-free per-thread storage
+  uint32_t (*r)[kThreads];
+  int tx;
+  __device__ __forceinline__ uint32_t &at(int s) const { return r[s][tx]; }
+};
+
+struct DevTailSink {
+  StagedTail *tails;
+  unsigned int *count;
+  unsigned int cap;
+  int chunk;
+  GX_HD void push(int list, int idx, unsigned int u1, bool positive) {
+#ifdef __CUDA_ARCH__
+    const unsigned int s = atomicAdd(count, 1u);
+    if (s < cap) {
+      StagedTail t;
+      t.chunk = chunk; t.u1 = u1; t.idx = (unsigned short) idx; t.list = (unsigned char) list; t.positive = positive ? 1 : 0;
+      tails[s] = t;
+    }
+#endif
+  }
+};
+
+__device__ __forceinline__ int stream_of_chunk(const StreamDesc *streams, int n_streams, int chunk) {
+  int lo = 0, hi = n_streams - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (streams[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) rng_gen_kernel(GenParams P) {
+  __shared__ unsigned int s_k[128];
+  __shared__ double s_w[128], s_y[128];
+  __shared__ uint32_t ring[kRing][kThreads];
+  __shared__ uint32_t sbuf[4][kThreads];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_k[i] = d_zig_ktab[i]; s_w[i] = d_zig_wtab[i]; s_y[i] = d_zig_ytab[i]; }
+  __syncthreads();
+  const int rel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rel >= P.count) return;  // exited lanes do not take part in the __syncwarp of gen_chunk
+  const int chunk = P.first + rel;
+  const StreamDesc &sd = P.streams[stream_of_chunk(P.streams, P.n_streams, chunk)];
+  const int q = chunk - sd.first_chunk;
+  const State st = chunk_start_state(sd, q, P.jump);
+  DevTailSink sink{P.tails, P.tail_count, P.tail_cap, rel};
+  ChunkFn f;
+  ListMeta m;
+  gen_chunk(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x}, s_k, s_w, s_y,
+            P.stage + (size_t) rel * kChunkStage, f, m, sink);
+  P.fn[rel] = f;
+  P.meta[rel] = m;
+}
+
+__global__ void resolve_kernel(const ChunkFn *fn, const ScanState *scan, const ListMeta *meta, uint32_t *stage, ChunkLoc *loc,
+                               int count) {
+  const int rel = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rel >= count) return;
+  const bool first = fn[rel].reset != 0;
+  const ScanState ss = scan[rel];
+  loc[rel] = resolve_chunk(meta[rel], first ? 0 : ss.entry, first ? 0 : ss.base, stage + (size_t) rel * kChunkStage);
+}
+
+// staged tails of a batch -> (stream, gaussian index) events of the draws that lie on the chunk's true path
+__global__ void tail_resolve_kernel(const StagedTail *st, const unsigned int *count, unsigned int cap, const ChunkFn *fn,
+                                    const ScanState *scan, const ListMeta *meta, const ChunkLoc *loc, const StreamDesc *streams,
+                                    int n_streams, int first_chunk, TailEvent *out, unsigned int *out_count, unsigned int out_cap,
+                                    unsigned int *overflow) {
+  if (*count > cap && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u;
+  const unsigned int n = min(*count, cap);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const StagedTail t = st[i];
+    const bool first = fn[t.chunk].reset != 0;
+    const int pi = path_index(meta[t.chunk], first ? 0 : scan[t.chunk].entry, t.list, t.idx);
+    if (pi < 0) continue;
+    const int sid = stream_of_chunk(streams, n_streams, first_chunk + t.chunk);
+    const long long g = loc[t.chunk].base + pi;
+    if (g >= streams[sid].n_gauss) continue;
+    const unsigned int s = atomicAdd(out_count, 1u);
+    if (s < out_cap) { TailEvent ev; ev.g = g; ev.stream = sid; ev.u1 = t.u1; ev.positive = t.positive; out[s] = ev; }
+  }
+}
+
+template <typename T> struct DeliverParams {
+  Owners<T> own;
+  int reverse;
+  double sigma;
+  const T *wtab;
+  const int *shell_first;  // [n/2 + 1]: global index of the first chunk of shell ks (entry ks + 1: its end)
+  int chunk0;              // global index of the batch's first chunk
+  const ChunkLoc *loc;     // per batch chunk
+  const uint32_t *stage;
+  int sa, sb;              // shells [sa, sb) of the batch
+  int p_origin, q_origin;  // (p, q) of block (0, 0), lane 0
+};
+
+// CTA = one k1 value p and 32 consecutive k2 values (lanes); the 8 warps take 8 consecutive shells per iteration.
+template <typename T>
+__global__ void __launch_bounds__(256) deliver_kernel(DeliverParams<T> P) {
+  __shared__ cplx<T> tile[32][9];
+  __shared__ unsigned int vmask[8];
+  __shared__ double s_w[128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 128) s_w[tid] = d_zig_wtab[tid];
+  __syncthreads();
+  const int p = P.p_origin + (int) blockIdx.y;
+  const int q0 = P.q_origin + 32 * (int) blockIdx.x;
+  const int q = q0 + lane;
+  const int need_p = max(-p, p + 1), need_q = max(-q, q + 1);      // first shell whose loops reach p / q
+  const int need_blk = max(need_p, q0 >= 0 ? q0 + 1 : -(q0 + 31));  // ... reach any lane of this block
+  const int start = max(P.sa, need_blk) & ~7;
+  for (int ks0 = start; ks0 < P.sb; ks0 += 8) {
+    const int ks = ks0 + warp;
+    const bool valid = ks >= P.sa && ks < P.sb && ks >= need_p && ks >= need_q;
+    bool w2 = false;
+    if (valid) {
+      const int c0 = ((p + ks) * 2 * ks + (q + ks)) * 3;
+      const long long g0 = 2ll * c0;
+      const int fc = P.shell_first[ks] - P.chunk0, nch = P.shell_first[ks + 1] - P.shell_first[ks];
+      int ci = locate_chunk(P.loc, fc, nch, g0);
+      ChunkLoc L = P.loc[ci];
+      long long hi = (ci + 1 < fc + nch) ? P.loc[ci + 1].base : 0x7fffffffffffffffll;
+      double d[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const long long g = g0 + k;
+        if (g >= hi) {  // the triple straddles a chunk boundary
+          ++ci;
+          L = P.loc[ci];
+          hi = (ci + 1 < fc + nch) ? P.loc[ci + 1].base : 0x7fffffffffffffffll;
+        }
+        d[k] = unpack_draw(fetch_draw(L, P.stage + (size_t) ci * kChunkStage, (int) (g - L.base)), s_w);
+      }
+#pragma unroll
+      for (int face = 0; face < 3; ++face) {
+        const FaceSlot fs = face_slot(ks, p, q, face);
+        if (!fs.write) continue;
+        T re, im;
+        call_value<T>(d[2 * face], d[2 * face + 1], P.sigma, P.wtab, fs.m, P.reverse, re, im);
+        if (face < 2) {  // kz = +-q: the warp's stores are one contiguous run of a row
+          *P.own.slot(fs.a, fs.b, fs.c) = mk<T>(re, fs.neg ? -im : im);
+          if (fs.second) *P.own.slot(-fs.a, -fs.b, 0) = mk<T>(re, -im);
+        } else {         // kz = ks: 32 different rows -- through the tile, 8 shells side by side
+          tile[lane][warp] = mk<T>(re, im);
+          w2 = true;
+        }
+      }
+    }
+    const unsigned int wm = __ballot_sync(0xffffffffu, w2);
+    if (lane == 0) vmask[warp] = wm;
+    __syncthreads();
+    {
+      const int qq = tid >> 3, kk = tid & 7;
+      if ((vmask[kk] >> qq) & 1u) *P.own.slot(p, q0 + qq, ks0 + kk) = tile[qq][kk];
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void staged_patch_kernel(const TailEvent *ev, const double *values, unsigned int n, const StreamDesc *streams,
+                                    Owners<T> own, int reverse, double sigma, const T *wtab) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long g = ev[i].g;
+  const int ks = streams[ev[i].stream].shell;
+  const long long c = g >> 1;
+  const int comp = (int) (g & 1), face = (int) (c % 3);
+  const long long t = c / 3;
+  const int p = (int) (t / (2 * ks)) - ks, q = (int) (t % (2 * ks)) - ks;
+  const FaceSlot fs = face_slot(ks, p, q, face);
+  if (!fs.write) return;
+  T v = (T) GX_DMUL(sigma, values[i]);
+  if (wtab) v = (T) GX_DMUL(v, __ldg(wtab + fs.m));
+  const int part = reverse ? 1 - comp : comp;
+  const T vconj = part == 1 ? -v : v;
+  reinterpret_cast<T *>(own.slot(fs.a, fs.b, fs.c))[part] = fs.neg ? vconj : v;
+  if (fs.second) reinterpret_cast<T *>(own.slot(-fs.a, -fs.b, 0))[part] = vconj;
+}
+
+// the slots no call writes, in this rank's rows [iy0, iy0 + nyl): one thread per (kx, ky) row
+template <typename T> __global__ void zero_undrawn_kernel(cplx<T> *slab, int n, int iy0, int nyl) {
+  const long row = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (row >= (long) n * nyl) return;
+  const int h = n >> 1, nc = h + 1;
+  const int ix = (int) (row / nyl), iy = iy0 + (int) (row % nyl);
+  cplx<T> *r = slab + (size_t) row * nc;
+  const cplx<T> z = mk<T>((T) 0, (T) 0);
+  if (ix == h || iy == h) { for (int c = 0; c < nc; ++c) r[c] = z; return; }
+  r[h] = z;
+  const int a = ix <= h ? ix : ix - n, b = iy <= h ? iy : iy - n;
+  const int A = max(abs(a), abs(b));
+  if (never_drawn(n, ix, iy, A)) r[A] = z;
+  if (A > 0 && never_drawn(n, ix, iy, 0)) for (int c = 0; c < A; ++c) r[c] = z;  // kz < A: the same status along the row
+}
+
+struct Shard { int world = 1, rank = 0; void *peers[kMaxPeers] = {nullptr}; };
+
+static int staged_minb() {
+  static int minb = -1;
+  if (minb < 0) { const char *e = getenv("GX_RNG_GEN_MINB"); minb = e ? atoi(e) : 6; }
+  return minb;
+}
+
+// Parallel Fourier order through the staged path. `field`: the whole field (world 1) or this rank's ky-slab; `scratch`:
+// device memory for the staged draws (any size from one shell's worth up; nullptr: allocated here for the call).
+template <typename T>
+static int noise_parallel_staged(T *field, int n, unsigned long seed, int reverse, const T *wtab, void *scratch,
+                                 size_t scratch_bytes, cudaStream_t cs, const Shard &shard) {
+  if (ensure_jump_table()) return 1;
+  if (ws_bind_device()) return 1;
+  const int h = n / 2, ns = h - 1;
+  const int world = shard.world, rank = shard.rank, nyl = n / world;
+  Owners<T> own;
+  own.n = n; own.nc = h + 1; own.nyl = nyl;
+  for (int r = 0; r < kMaxPeers; ++r) own.base[r] = nullptr;
+  if (world == 1) own.base[0] = field;
+  else for (int r = 0; r < world; ++r) own.base[r] = (T *) (r == rank ? (void *) field : shard.peers[r]);
+  {
+    const long rows = (long) n * nyl;
+    zero_undrawn_kernel<T><<<(unsigned) ((rows + 255) / 256), 256, 0, cs>>>(reinterpret_cast<cplx<T> *>(field), n, rank * nyl, nyl);
+    count_launch();
+    GX_LAUNCH_CHECK();
+  }
+  if (ns <= 0) return 0;
+  // streams: one per shell, seed + ks (randomfieldgenerator.hpp:228-229), 24 ks^2 gaussians each
+  void *pin0 = nullptr;
+  if (ws_pin(0, sizeof(StreamDesc) * ns + sizeof(int) * (h + 2) + 64, &pin0)) return 1;
+  StreamDesc *sd = (StreamDesc *) pin0;
+  int *shell_first = (int *) ((char *) pin0 + sizeof(StreamDesc) * ns);  // [ks], ks = 0..h
+  unsigned int *h_ntail = (unsigned int *) (shell_first + h + 1);  // 3 words
+  long long n_chunks = 0, total_gauss = 0;
+  shell_first[0] = 0;
+  for (int s = 0; s < ns; ++s) {
+    StreamDesc &d = sd[s];
+    const int ks = s + 1;
+    d.s0 = seed_state(seed + (unsigned long) ks);
+    d.b0 = 0; d.entry0 = 0; d.n_gauss = 24ll * ks * ks; d.shell = ks;
+    d.xs = state_to_big(d.s0);
+    d.first_chunk = (int) n_chunks;
+    shell_first[ks] = (int) n_chunks;
+    n_chunks += (raw_budget(d.n_gauss) + kChunkLen - 1) / kChunkLen;
+    total_gauss += d.n_gauss;
+  }
+  shell_first[h] = (int) n_chunks;
+  // this rank's shells: contiguous, balanced by chunk count (generator work)
+  int s_lo = 1, s_hi = h;
+  if (world > 1) {
+    auto cut = [&](int r) {
+      const long long target = n_chunks * r / world;
+      int ks = 1;
+      while (ks < h && shell_first[ks] < target) ++ks;
+      return ks;
+    };
+    s_lo = cut(rank);
+    s_hi = rank + 1 == world ? h : cut(rank + 1);
+  }
+  if (s_lo >= s_hi) return 0;
+  const long long my_chunks = shell_first[s_hi] - shell_first[s_lo];
+  const long long largest = shell_first[s_hi] - shell_first[s_hi - 1];
+  const size_t per_chunk = (size_t) kChunkStage * sizeof(uint32_t);
+  void *own_scratch = nullptr;
+  if (!scratch || scratch_bytes < (size_t) largest * per_chunk) {
+    size_t free_b = 0, total_b = 0;
+    GX_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t want = (size_t) my_chunks * per_chunk;
+    size_t cap = free_b / 2;
+    if (const char *e = getenv("GX_NOISE_STAGE_BYTES")) cap = (size_t) atoll(e);  // test hook: forces several batches
+    cap = std::max((size_t) largest * per_chunk, cap);
+    if (want > cap) want = cap;
+    GX_CUDA_CHECK(cudaMalloc(&own_scratch, want));
+    scratch = own_scratch; scratch_bytes = want;
+  }
+  const long long cap_chunks = (long long) (scratch_bytes / per_chunk);
+  // batches of whole shells
+  std::vector<std::pair<int, int>> batches;
+  long long max_batch = 0, max_batch_gauss = 0;
+  for (int a = s_lo; a < s_hi;) {
+    int b = a + 1;
+    while (b < s_hi && shell_first[b + 1] - shell_first[a] <= cap_chunks) ++b;
+    batches.push_back({a, b});
+    max_batch = std::max<long long>(max_batch, shell_first[b] - shell_first[a]);
+    long long gsum = 0;
+    for (int ks = a; ks < b; ++ks) gsum += 24ll * ks * ks;
+    max_batch_gauss = std::max(max_batch_gauss, gsum);
+    a = b;
+  }
+  // per-batch arrays
+  std::vector<int> level_n;
+  level_n.push_back((int) max_batch);
+  while (level_n.back() > 4096) level_n.push_back((level_n.back() + 63) / 64);
+  size_t fn_total = 0;
+  for (int v : level_n) fn_total += (size_t) v;
+  long long my_gauss = 0;
+  for (int ks = s_lo; ks < s_hi; ++ks) my_gauss += 24ll * ks * ks;
+  const unsigned int staged_cap = (unsigned int) std::min<long long>((long long) (max_batch_gauss * 1.5e-3) + 8192, 600000000ll);
+  const unsigned int tail_cap = (unsigned int) std::min<long long>((long long) (my_gauss * 8e-4) + 4096, 400000000ll);
+  void *p_streams, *p_misc, *p_tails, *p_fn, *p_st, *p_meta, *p_staged;
+  if (ws_dev(0, sizeof(StreamDesc) * ns + sizeof(int) * (h + 1), &p_streams)) return 1;
+  if (ws_dev(1, 64, &p_misc)) return 1;
+  if (ws_dev(2, sizeof(TailEvent) * (size_t) tail_cap, &p_tails)) return 1;
+  if (ws_dev(3, sizeof(ChunkFn) * fn_total, &p_fn)) return 1;
+  if (ws_dev(4, sizeof(ScanState) * fn_total, &p_st)) return 1;
+  if (ws_dev(6, (sizeof(ListMeta) + sizeof(ChunkLoc)) * (size_t) max_batch + 64, &p_meta)) return 1;
+  if (ws_dev(7, sizeof(StagedTail) * (size_t) staged_cap, &p_staged)) return 1;
+  StreamDesc *d_streams = (StreamDesc *) p_streams;
+  int *d_shell_first = (int *) ((char *) p_streams + sizeof(StreamDesc) * ns);
+  unsigned int *d_staged_count = (unsigned int *) p_misc, *d_tail_count = d_staged_count + 1;
+  ChunkLoc *d_loc = (ChunkLoc *) p_meta;
+  ListMeta *d_meta = (ListMeta *) ((char *) p_meta + sizeof(ChunkLoc) * (size_t) max_batch);
+  GX_CUDA_CHECK(cudaMemcpyAsync(d_streams, sd, sizeof(StreamDesc) * ns + sizeof(int) * (h + 1), cudaMemcpyHostToDevice, cs));
+  GX_CUDA_CHECK(cudaMemsetAsync(d_tail_count, 0, 2 * sizeof(unsigned int), cs));  // final tail count, staged-overflow flag
+  const int nl = (int) level_n.size();
+  std::vector<ChunkFn *> d_fn(nl);
+  std::vector<ScanState *> d_st(nl);
+  const double sigma = (double) (T) (1.0 / sqrt(2.0));
+
+  for (const auto &bt : batches) {
+    const int sa = bt.first, sb = bt.second;
+    const int c0 = shell_first[sa], cnt = shell_first[sb] - c0;
+    std::vector<int> ln;
+    ln.push_back(cnt);
+    while (ln.back() > 4096) ln.push_back((ln.back() + 63) / 64);
+    const int bl = (int) ln.size();
+    {
+      size_t off = 0;
+      for (int l = 0; l < bl; ++l) { d_fn[l] = (ChunkFn *) p_fn + off; d_st[l] = (ScanState *) p_st + off; off += (size_t) ln[l]; }
+    }
+    GX_CUDA_CHECK(cudaMemsetAsync(d_staged_count, 0, sizeof(unsigned int), cs));
+    GenParams G;
+    G.streams = d_streams; G.n_streams = ns; G.first = c0; G.count = cnt; G.jump = g_jump; G.fn = d_fn[0]; G.meta = d_meta;
+    G.stage = (uint32_t *) scratch; G.tails = (StagedTail *) p_staged; G.tail_count = d_staged_count; G.tail_cap = staged_cap;
+    {
+      GX_TIMED("rng_gen", cs);
+      const int grid = (cnt + kThreads - 1) / kThreads;
+      const int mb = staged_minb();
+      if (mb == 4) rng_gen_kernel<4><<<grid, kThreads, 0, cs>>>(G);
+      else if (mb == 5) rng_gen_kernel<5><<<grid, kThreads, 0, cs>>>(G);
+      else if (mb == 8) rng_gen_kernel<8><<<grid, kThreads, 0, cs>>>(G);
+      else rng_gen_kernel<6><<<grid, kThreads, 0, cs>>>(G);
+      count_launch();
+    }
+    GX_LAUNCH_CHECK();
+    {
+      GX_TIMED("rng_scan", cs);
+      for (int l = 1; l < bl; ++l) {
+        scan_up_kernel<<<(ln[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], ln[l - 1], d_fn[l], ln[l]);
+        count_launch();
+      }
+      scan_top_kernel<<<1, 32, 0, cs>>>(d_fn[bl - 1], ln[bl - 1], d_st[bl - 1]);
+      count_launch();
+      for (int l = bl - 1; l >= 1; --l) {
+        scan_down_kernel<<<(ln[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], ln[l - 1], d_st[l], ln[l], d_st[l - 1]);
+        count_launch();
+      }
+      resolve_kernel<<<(cnt + 127) / 128, 128, 0, cs>>>(d_fn[0], d_st[0], d_meta, (uint32_t *) scratch, d_loc, cnt);
+      count_launch();
+      tail_resolve_kernel<<<128, 256, 0, cs>>>((const StagedTail *) p_staged, d_staged_count, staged_cap, d_fn[0], d_st[0], d_meta,
+                                               d_loc, d_streams, ns, c0, (TailEvent *) p_tails, d_tail_count, tail_cap,
+                                               d_tail_count + 1);
+      count_launch();
+    }
+    GX_LAUNCH_CHECK();
+    DeliverParams<T> D;
+    D.own = own; D.reverse = reverse; D.sigma = sigma; D.wtab = wtab; D.shell_first = d_shell_first; D.chunk0 = c0;
+    D.loc = d_loc; D.stage = (const uint32_t *) scratch; D.sa = sa; D.sb = sb;
+    const int top = sb - 1;                       // p, q in [-top, top)
+    D.p_origin = -top;
+    D.q_origin = -((top + 31) / 32) * 32;
+    const dim3 grid((unsigned) ((top - D.q_origin + 31) / 32), (unsigned) (2 * top));
+    {
+      GX_TIMED("rng_deliver", cs);
+      deliver_kernel<T><<<grid, 256, 0, cs>>>(D);
+      count_launch();
+    }
+    GX_LAUNCH_CHECK();
+  }
+
+  // tails: host libm recomputation (the reference's own arithmetic for these draws), then patched over the delivered values
+  GX_CUDA_CHECK(cudaMemcpyAsync(h_ntail, d_staged_count, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
+  GX_CUDA_CHECK(cudaStreamSynchronize(cs));
+  if (own_scratch) GX_CUDA_CHECK(cudaFree(own_scratch));
+  if (h_ntail[2]) return fail("gx_noise_draw: staged tail list overflow");
+  const unsigned int ntail = h_ntail[1];
+  if (ntail > tail_cap) return fail("gx_noise_draw: tail list overflow");
+  if (ntail > 0) {
+    void *pin_ev = nullptr, *pin_val = nullptr, *p_val = nullptr;
+    if (ws_pin(1, sizeof(TailEvent) * (size_t) ntail, &pin_ev)) return 1;
+    if (ws_pin(2, sizeof(double) * (size_t) ntail, &pin_val)) return 1;
+    if (ws_dev(5, sizeof(double) * (size_t) ntail, &p_val)) return 1;
+    TailEvent *ev = (TailEvent *) pin_ev;
+    double *val = (double *) pin_val;
+    GX_CUDA_CHECK(cudaMemcpyAsync(ev, p_tails, sizeof(TailEvent) * ntail, cudaMemcpyDeviceToHost, cs));
+    GX_CUDA_CHECK(cudaStreamSynchronize(cs));
+    host_tail_values(ev, val, ntail);
+    GX_CUDA_CHECK(cudaMemcpyAsync(p_val, val, sizeof(double) * ntail, cudaMemcpyHostToDevice, cs));
+    GX_TIMED("rng_tail_patch", cs);
+    staged_patch_kernel<T><<<(ntail + 127) / 128, 128, 0, cs>>>((const TailEvent *) p_tails, (const double *) p_val, ntail, d_streams,
+                                                             own, reverse, sigma, wtab);
+    count_launch();
+    GX_LAUNCH_CHECK();
+    GX_CUDA_CHECK(cudaStreamSynchronize(cs));  // the pinned staging buffers are reused by the next draw
+  }
+  return 0;
+}
+
 // world == 1: the whole field. world > 1: rank's slab only -- Fourier orders fill the ky-slab [n][n/world][nc] (every
 // rank walks every stream and keeps the draws it owns), the real order fills the x-slab and stays in real space (the
 // caller runs the slab-decomposed r2c and zeroes Re(DC)).
+static bool staged_enabled() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("GX_NOISE_STAGED"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 template <typename T>
 static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int reverse, unsigned long long *offset_io,
-                        cudaStream_t cs, int world = 1, int rank = 0, Phase phase = Phase(), const void *wtab = nullptr) {
+                        cudaStream_t cs, int world = 1, int rank = 0, Phase phase = Phase(), const void *wtab = nullptr,
+                        void *scratch = nullptr, size_t scratch_bytes = 0) {
+  if (mode == GX_NOISE_FOURIER_PARALLEL && world == 1 && phase.which == 0 && staged_enabled())
+    return noise_parallel_staged<T>((T *) field, n, seed, reverse, (const T *) wtab, scratch, scratch_bytes, cs, Shard());
   const size_t bytes = (size_t) 2 * n * n * (n / 2 + 1) * sizeof(T) / (size_t) world;
   if (phase.which != 1) GX_CUDA_CHECK(cudaMemsetAsync(field, 0, bytes, cs));
   Dest<T> dest;
@@ -840,10 +1255,11 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
 }  // namespace rng
 
 int noise_draw_scaled(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
-                      unsigned long long *stream_offset_io, cudaStream_t st, const void *table) {
+                      unsigned long long *stream_offset_io, cudaStream_t st, const void *table, void *scratch,
+                      size_t scratch_bytes) {
   if (!is_pow2(n) || n < 4 || n > 4096) return fail("grid size must be a power of two in [4,4096]");
-  if (dtype == GX_F64) return rng::noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table);
-  if (dtype == GX_F32) return rng::noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table);
+  if (dtype == GX_F64) return rng::noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table, scratch, scratch_bytes);
+  if (dtype == GX_F32) return rng::noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table, scratch, scratch_bytes);
   return fail("bad dtype");
 }
 }  // namespace gx

@@ -1,0 +1,296 @@
+// Staged white noise: every chunk of a ranlxs2 stream is generated ONCE.
+//
+// The two-pass scheme of round 1 (rng.cu: pass A parses each chunk from its 4 possible entry positions, a scan resolves
+// the true one, pass B regenerates the chunk and scatters every draw to its slot) ran the 397-step generator advance
+// twice per chunk and wrote the field as isolated 16-byte stores. Here the chunk's accepted ziggurat draws are kept:
+//   gen      one thread per chunk: jump, generate, parse the (up to) 4 entry hypotheses, and APPEND each accepted draw
+//            as 32 bits -- (sign | level i) in the low byte, the 24-bit j above it; x = j * wtab[i] is re-formed exactly
+//            on delivery -- to the list of the hypothesis it belongs to. Hypotheses merge after a few attempts (same
+//            parity) or ~80 attempts (opposite parity), after which only list 0 grows: ~1.1 lists' worth per chunk.
+//   scan     the chunk transfer functions (unchanged) give every chunk its true entry position and first gaussian index;
+//   resolve  the true path of a chunk is  list_e[0, len1) ++ list_0[join, ...)  (chains through a second alt list are
+//            spliced once), recorded as 16 bytes per chunk;
+//   deliver  CALL-driven: a thread owns one (shell, k1, k2) position of drawRandomForSpecifiedGridFourier's loops
+//            (randomfieldgenerator.hpp:226-243), i.e. three drawOneFourierMode calls = 6 consecutive gaussians = 24
+//            contiguous staged bytes, and stores the three modes with the reference's overwrite rule resolved
+//            analytically (a mode and its conjugate partner can both be drawn in a shell: the later call wins,
+//            :144-171). Lanes run along k2, so the two faces with kz = k2 store whole contiguous row segments and the
+//            face with kz = ks goes through a shared-memory transpose over 8 shells (128-byte row segments).
+// Never-drawn slots (DC, the Nyquist planes and the shell edges (A, A, c <= A), (-A, -A, c < A)) are zeroed by a small
+// kernel instead of a memset of the whole field.
+//
+// Everything here is __host__ __device__: tests/host/rng_staged_host.cu runs the same code on the CPU against the oracle.
+#pragma once
+#include "rng_core.cuh"
+
+namespace gx {
+namespace rng {
+
+constexpr int kBc = 64;               // increments per chunk
+constexpr int kChunkLen = kBc * 24;   // raw outputs per chunk
+constexpr int kCap = 772;             // list capacity: a chunk holds at most (1536 + 3) / 2 accepted draws
+constexpr int kChunkStage = 4 * kCap; // 32-bit words of staging per chunk (4 hypothesis lists)
+constexpr int kRing = 32;             // raw outputs kept per thread (the parse looks back < 28)
+
+struct StreamDesc {
+  State s0;              // seed state (used when the stream starts at block 0)
+  Big xs;                // X at block b0 (start block of the stream's first chunk)
+  long long b0;          // first block index of the stream's first chunk
+  int entry0;            // position of the first attempt inside the first chunk
+  int first_chunk;       // index of the stream's first chunk in the global chunk list
+  long long n_gauss;     // gaussians wanted from this stream
+  int shell;             // ks for per-shell streams, 0 otherwise
+};
+
+struct ChunkFn {
+  long long count[4];
+  unsigned char exit[4];
+  unsigned char reset;
+};
+
+struct ScanState {
+  long long base;
+  int entry;
+};
+
+GX_HD ChunkFn compose(const ChunkFn &f, const ChunkFn &g) {  // f first, then g
+  if (g.reset) return g;
+  ChunkFn h;
+  h.reset = f.reset;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h.exit[e] = g.exit[f.exit[e]];
+    h.count[e] = f.count[e] + g.count[f.exit[e]];
+  }
+  return h;
+}
+
+GX_HD ScanState apply_fn(const ChunkFn &f, const ScanState &s) {
+  ScanState o;
+  if (f.reset) { o.entry = f.exit[0]; o.base = f.count[0]; }
+  else { o.entry = f.exit[s.entry]; o.base = s.base + f.count[s.entry]; }
+  return o;
+}
+
+// ---- gen -----------------------------------------------------------------------------------------------------------
+struct ListMeta {          // how the 4 hypothesis lists of a chunk hang together
+  unsigned short len[4];   // draws appended to list e before it merged into list rep[e] (list 0: all of its draws)
+  unsigned short join[4];  // index in list rep[e] at which path e continues
+  signed char rep[4];      // -1: never merged
+};
+
+struct StagedTail {        // an accepted tail draw seen by hypothesis `list` (value needs the host's log())
+  int chunk;               // batch-relative chunk index
+  unsigned int u1;
+  unsigned short idx;      // position in that list
+  unsigned char list, positive;
+};
+
+#ifdef __CUDA_ARCH__
+#define GX_SYNCWARP() __syncwarp()
+#else
+#define GX_SYNCWARP()
+#endif
+
+GX_HD uint32_t pack_draw(uint32_t r0, uint32_t r1) { return (r0 & 0xFFu) | (r1 << 8); }
+
+// x = j * wtab[i], value = sign * x: the products gsl_ran_gaussian_ziggurat forms (zig_attempt in rng_core.cuh)
+GX_HD double unpack_draw(uint32_t e, const double *wtab) {
+  const double x = GX_DMUL((double) (e >> 8), wtab[e & 0x7Fu]);
+  const double sign = (e & 0x80u) ? 1.0 : -1.0;
+  return GX_DMUL(GX_DMUL(sign, 1.0), x);
+}
+
+// One chunk: `st` is the generator state at the chunk's first block. Ring::at(slot) / Buf::at(k) are the thread's raw-output
+// ring (kRing slots) and its 4-entry store buffer (shared memory on the device, plain arrays on the host); `stage` is the
+// chunk's kChunkStage words; sink.push(list, idx, u1, positive) records accepted tail draws.
+template <class Ring, class Buf, class Sink>
+GX_HD void gen_chunk(const StreamDesc &sd, bool first, State st, Ring ring, Buf buf, const unsigned int *ktab,
+                     const double *wtab, const double *ytab, uint32_t *stage, ChunkFn &f, ListMeta &meta, Sink &sink) {
+  int pos[4], cnt[4], rep[4], joinv[4];
+  int ncur;
+  if (first) { ncur = 1; pos[0] = sd.entry0; pos[1] = pos[2] = pos[3] = 0; }
+  else { ncur = 4; for (int e = 0; e < 4; ++e) pos[e] = e; }
+  for (int e = 0; e < 4; ++e) { cnt[e] = 0; rep[e] = -1; joinv[e] = 0; }
+
+  for (int bi = 0; bi <= kBc; ++bi) {
+    GX_SYNCWARP();  // the 397-step advance runs with the warp converged
+    advance_block(st);
+    const int rbase = 24 * bi;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) ring.at((rbase + j) & (kRing - 1)) = block_output(st, j);
+    const int avail = 24 * (bi + 1);
+    const int limit = avail - 3 < kChunkLen ? avail - 3 : kChunkLen;
+    for (int e = 0; e < ncur; ++e) {
+      if (rep[e] >= 0) continue;
+      int p = pos[e];
+      while (p < limit) {
+        const uint32_t r0 = ring.at(p & (kRing - 1)), r1 = ring.at((p + 1) & (kRing - 1));
+        const Attempt a = zig_attempt(r0, r1, ring.at((p + 2) & (kRing - 1)), ring.at((p + 3) & (kRing - 1)), ktab, wtab, ytab);
+        p += a.consumed;
+        if (a.accepted) {
+          const uint32_t d = pack_draw(r0, r1);
+          const int c = cnt[e];
+          if (a.tail) sink.push(e, c, a.tail_u1, a.value > 0);
+          if (e == 0) {  // the long list leaves as 16-byte stores
+            buf.at(c & 3) = d;
+            if ((c & 3) == 3) {
+#ifdef __CUDA_ARCH__
+              *reinterpret_cast<uint4 *>(stage + (c - 3)) = make_uint4(buf.at(0), buf.at(1), buf.at(2), d);
+#else
+              for (int k = 0; k < 4; ++k) stage[c - 3 + k] = buf.at(k);
+#endif
+            }
+          } else {
+            stage[e * kCap + c] = d;
+          }
+          cnt[e] = c + 1;
+        }
+      }
+      pos[e] = p;
+    }
+    if (ncur == 4) {  // merge hypotheses that have reached the same position
+      for (int e = 1; e < 4; ++e) {
+        if (rep[e] >= 0) continue;
+        for (int r = 0; r < e; ++r)
+          if (rep[r] < 0 && pos[r] == pos[e]) { rep[e] = r; joinv[e] = cnt[r]; break; }
+      }
+    }
+  }
+  for (int k = cnt[0] & ~3; k < cnt[0]; ++k) stage[k] = buf.at(k & 3);
+
+  f.reset = first ? 1 : 0;
+  for (int e = 0; e < 4; ++e) {
+    int r = first ? 0 : e;
+    long long total = 0;
+    int start = 0;
+    while (rep[r] >= 0) { total += cnt[r] - start; start = joinv[r]; r = rep[r]; }  // merges can chain (3 -> 1 -> 0)
+    total += cnt[r] - start;
+    f.exit[e] = (unsigned char) (pos[r] - kChunkLen);
+    f.count[e] = total;
+    meta.len[e] = (unsigned short) cnt[e];
+    meta.join[e] = (unsigned short) joinv[e];
+    meta.rep[e] = (signed char) rep[e];
+  }
+  if (first) for (int e = 1; e < 4; ++e) { meta.len[e] = 0; meta.join[e] = 0; meta.rep[e] = 0; }
+}
+
+// ---- resolve -------------------------------------------------------------------------------------------------------
+struct ChunkLoc {
+  long long base;            // stream-local index of the chunk's first gaussian
+  unsigned short len1, join; // gaussian i of the chunk: i < len1 ? list_e[i] : list_0[i - len1 + join]
+  unsigned char e, pad[3];
+};
+
+GX_HD ChunkLoc resolve_chunk(const ListMeta &m, int entry, long long base, uint32_t *stage) {
+  ChunkLoc L;
+  L.base = base; L.pad[0] = L.pad[1] = L.pad[2] = 0;
+  const int e = entry;
+  if (e == 0) { L.e = 0; L.len1 = 0; L.join = 0; return L; }
+  int len = m.len[e], r = m.rep[e], j = m.join[e];
+  while (r > 0) {  // the path runs through another alt list before it reaches list 0: splice that stretch onto ours
+    const int lr = m.len[r];
+    for (int k = j; k < lr; ++k) stage[e * kCap + len++] = stage[r * kCap + k];
+    j = m.join[r];
+    r = m.rep[r];
+  }
+  L.e = (unsigned char) e; L.len1 = (unsigned short) len; L.join = (unsigned short) (r == 0 ? j : 0);
+  return L;
+}
+
+GX_HD uint32_t fetch_draw(const ChunkLoc &L, const uint32_t *stage, int i) {
+  return i < (int) L.len1 ? stage[(int) L.e * kCap + i] : stage[i - (int) L.len1 + (int) L.join];
+}
+
+// index in the chunk's true path of the draw that hypothesis `list` stored at position idx, or -1 if it is not on the path
+GX_HD int path_index(const ListMeta &m, int entry, int list, int idx) {
+  int cur = entry, start = 0, off = 0;
+  for (int hop = 0; hop < 4 && cur >= 0; ++hop) {
+    if (cur == list) return (idx >= start && idx < (int) m.len[cur]) ? off + idx - start : -1;
+    off += (int) m.len[cur] - start;
+    start = m.join[cur];
+    cur = m.rep[cur];
+  }
+  return -1;
+}
+
+// the chunk of a stream (chunks [fc, fc + nch) of `loc`) that holds gaussian g
+GX_HD int locate_chunk(const ChunkLoc *loc, int fc, int nch, long long g) {
+  int k = 0;
+  if (nch > 1) {
+    const long long last = loc[fc + nch - 1].base;
+    k = (int) ((double) g * (double) (nch - 1) / (double) last);
+    if (k > nch - 1) k = nch - 1;
+  }
+  while (k > 0 && loc[fc + k].base > g) --k;
+  while (k + 1 < nch && loc[fc + k + 1].base <= g) ++k;
+  return fc + k;
+}
+
+// ---- deliver -------------------------------------------------------------------------------------------------------
+// drawOneFourierMode call `face` at loop position (ks; p, q): the mode (k1, k2, k3), whether this call is the last writer
+// of its slot, and where setFourierCoefficient stores it.
+struct FaceSlot {
+  int a, b, c;       // signed coordinates of the stored representative (c >= 0)
+  bool neg;          // the representative is -k: the imaginary part is stored negated
+  bool write;        // this call is the last writer (its conjugate partner is not drawn later in the shell)
+  bool second;       // k3 == 0: drawOneFourierMode's explicit second write lands on a different slot, (-k1, -k2, 0)
+  int m;             // k1^2 + k2^2 + k3^2
+};
+
+GX_HD FaceSlot face_slot(int ks, int p, int q, int face) {
+  const int k1 = (face == 0) ? ks : p;
+  const int k2 = (face == 0) ? p : ((face == 1) ? ks : q);
+  const int k3 = (face == 2) ? ks : q;
+  // the partner -k is drawn in the same shell iff exactly one of its coordinates equals +ks and the others lie in [-ks, ks-1]
+  const int a = -k1, b = -k2, c3 = -k3;
+  const int np = (a == ks) + (b == ks) + (c3 == ks);
+  const int pface = (a == ks) ? 0 : ((b == ks) ? 1 : 2);
+  const int pp = (pface == 0) ? b : a;
+  const int pq = (pface == 2) ? b : c3;
+  const bool partner_drawn = (np == 1) && (pp >= -ks) && (pp < ks) && (pq >= -ks) && (pq < ks);
+  const int twoks = 2 * ks;
+  const int c_self = ((p + ks) * twoks + (q + ks)) * 3 + face;
+  const int c_partner = ((pp + ks) * twoks + (pq + ks)) * 3 + pface;
+  FaceSlot s;
+  s.write = !(partner_drawn && c_partner > c_self);
+  s.m = k1 * k1 + k2 * k2 + k3 * k3;
+  s.neg = k3 < 0;
+  s.a = s.neg ? -k1 : k1; s.b = s.neg ? -k2 : k2; s.c = s.neg ? -k3 : k3;
+  s.second = (k3 == 0);
+  return s;
+}
+
+// the two draws of a call in the field's type: norm * gaussian with norm = FloatType(1/sqrt(2)) (randomfieldgenerator.hpp:213),
+// times the optional per-mode factor (Field::applyTransferFunction folded in), re/im swapped for the reverse order
+template <typename T>
+GX_HD void call_value(double first, double second, double sigma, const T *wtab, int m, int reverse, T &re, T &im) {
+  T a = (T) GX_DMUL(sigma, first), b = (T) GX_DMUL(sigma, second);
+  if (wtab) {
+#ifdef __CUDA_ARCH__
+    const T w = __ldg(wtab + m);
+#else
+    const T w = wtab[m];
+#endif
+    a = (T) GX_DMUL(a, w); b = (T) GX_DMUL(b, w);
+  }
+  re = reverse ? b : a;
+  im = reverse ? a : b;
+}
+
+// slots of the parallel Fourier order that no call ever writes (they keep the zero of the freshly constructed field)
+GX_HD bool never_drawn(int n, int ix, int iy, int iz) {
+  const int h = n >> 1;
+  if (ix == h || iy == h || iz == h) return true;
+  const int a = ix <= h ? ix : ix - n, b = iy <= h ? iy : iy - n, c = iz;
+  const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
+  int M = aa > ab ? aa : ab;
+  if (c > M) M = c;
+  if (M == 0) return true;  // DC
+  // k is drawn (in shell M) iff exactly one coordinate equals +M; -k iff exactly one coordinate of k equals -M
+  const int plus = (a == M) + (b == M) + (c == M), minus = (a == -M) + (b == -M);
+  return plus != 1 && minus != 1;
+}
+
+}  // namespace rng
+}  // namespace gx

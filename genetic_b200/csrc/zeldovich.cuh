@@ -22,7 +22,8 @@ int build_transfer_table(int n, int dtype, double grid_length, const gx_spectrum
                          cudaStream_t st, const void **table);
 // gx_noise_draw with every mode multiplied by table[kx^2 + ky^2 + kz^2] as it is written (Fourier orders only)
 int noise_draw_scaled(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
-                      unsigned long long *stream_offset_io, cudaStream_t st, const void *table);
+                      unsigned long long *stream_offset_io, cudaStream_t st, const void *table, void *scratch = nullptr,
+                      size_t scratch_bytes = 0);  // scratch: device memory the staged draw may use (e.g. the idle work field)
 int unit_variance_slab(void *field, int n, int dtype, int iy0, int ny, cudaStream_t st);
 // last pass: c2r along z of rows [row0, row0+nrows) of `work`, scaled by n^-1.5, written back in place (real space)
 int zeldovich_z_real(void *work, int n, int dtype, long row0, long nrows, cudaStream_t st);

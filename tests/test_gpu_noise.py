@@ -127,3 +127,38 @@ def test_unigrid_128_vs_oracle():
     d = np.minimum(d, box - d)
     assert d.max() < 1e-10 * box
     assert mass == omass and eps == oeps
+
+
+# ---- staged single-generation path (csrc/rng_staged_core.cuh) at sizes where streams span many chunks ----------------
+@pytest.mark.parametrize("n,dtype", [(128, np.float64), (128, np.float32), (256, np.float64)])
+def test_parallel_draw_bit_exact_many_chunks(n, dtype):
+    seed = 1512351
+    W = _draw(n, seed, "fourier_parallel", dtype).getDataVector()
+    Wo = crng.draw_fourier(crng.Stream(seed), n, True, False, dtype == np.float32)
+    assert np.array_equal(W, Wo.astype(W.dtype))
+
+
+def test_parallel_draw_in_several_batches(monkeypatch):
+    """The staged draws of a batch of shells live in a bounded scratch buffer: with a tiny one every few shells are a batch."""
+    n, seed = 128, 8896131
+    monkeypatch.setenv("GX_NOISE_STAGE_BYTES", str(1 << 20))
+    W = _draw(n, seed, "fourier_parallel", np.float64).getDataVector()
+    monkeypatch.delenv("GX_NOISE_STAGE_BYTES")
+    assert np.array_equal(W, crng.draw_fourier(crng.Stream(seed), n, True, False, False))
+
+
+def test_outer_shells_of_1024_bit_exact():
+    """Long streams: the outermost shells of a 1024^3 parallel draw (25 million gaussians per stream, ~8000 chunks, skip-ahead
+    over 5e5 generator increments) against the oracle's sequential draw of those shells only (per-shell streams make this
+    cheap on the CPU). bench.py's 2048^3 workload is checked the same way by tools/noise_shell_check.py (profiles/)."""
+    n, seed, ks0 = 1024, 8896131, 508
+    W = _draw(n, seed, "fourier_parallel", np.float64).getDataVector()
+    ref = crng.draw_fourier_parallel_shells(seed, n, ks0, n // 2).view(np.complex128).reshape(n, n, n // 2 + 1)
+    sm = np.abs(M.signed_modes(n))
+    for kz in range(ks0, n // 2):          # face kz = ks: whole planes of the half-space
+        assert np.array_equal(W[:, :, kz], ref[:, :, kz])
+    for k in range(ks0, n // 2):            # faces kx = +-ks, ky = +-ks: inside the shell's cube
+        for idx in (k, n - k):
+            inside = (sm[:, None] <= k) & (np.arange(n // 2 + 1)[None, :] <= k)
+            assert np.array_equal(W[idx][inside], ref[idx][inside])
+            assert np.array_equal(W[:, idx][inside], ref[:, idx][inside])

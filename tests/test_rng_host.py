@@ -53,3 +53,30 @@ def test_ziggurat_parse_matches_gsl(hostlib):
     assert used > 0
     ref = crng.Stream(seed).gaussians(ng)
     assert np.array_equal(out, ref)  # host build: same libm, so even the tail values agree bit for bit
+
+
+@pytest.fixture(scope="module")
+def stagedlib():
+    src = os.path.join(HERE, "host", "rng_staged_host.cu")
+    so = os.path.join(HERE, "host", "_rng_staged_host.so")
+    hdrs = [os.path.join(HERE, "..", "genetic_b200", "csrc", h) for h in ("rng_core.cuh", "rng_staged_core.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-shared", "-Xcompiler", "-fPIC", "-ccbin",
+                               "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so, src],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("n,seed,reverse", [(8, 42, 0), (16, 8896131, 0), (32, 8896131, 1), (64, 1512351, 0)])
+def test_staged_noise_path_on_the_host(stagedlib, n, seed, reverse):
+    """The staged single-generation noise path (rng_staged_core.cuh: hypothesis lists, resolve, call-driven delivery with
+    the analytic overwrite rule, never-drawn set) run on the CPU: bit-exact against the oracle's sequential draw."""
+    nc = n // 2 + 1
+    out = np.zeros((n, n, nc), dtype=np.complex128)
+    written = np.zeros((n, n, nc), dtype=np.uint8)
+    stats = np.zeros(8, dtype=np.int64)
+    rc = stagedlib.host_staged_noise(n, ctypes.c_ulong(seed), reverse, out.ctypes.data_as(ctypes.c_void_p),
+                                     written.ctypes.data_as(ctypes.c_void_p), stats.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    ref = crng.draw_fourier(crng.Stream(seed), n, True, bool(reverse), False)   # parallel order, optionally reversed draws
+    assert np.array_equal(out, ref)
