@@ -769,11 +769,11 @@ static int run_streams(const std::vector<StreamReq> &reqs, Dest<T> dest, std::ve
 constexpr int kMaxPeers = 8;
 template <typename T> struct Owners {
   T *base[kMaxPeers];
-  int n, nc, nyl;
+  int n, nc, nyl, ny_shift;  // nyl = n / world = 1 << ny_shift
   __device__ __forceinline__ cplx<T> *slot(int a, int b, int c) const {
-    const int ix = a < 0 ? a + n : a, iy = b < 0 ? b + n : b;
-    const int o = iy / nyl, iyl = iy - o * nyl;
-    return reinterpret_cast<cplx<T> *>(base[o]) + ((size_t) c + (size_t) nc * ((size_t) iyl + (size_t) nyl * (size_t) ix));
+    const unsigned int ix = (unsigned int) (a < 0 ? a + n : a), iy = (unsigned int) (b < 0 ? b + n : b);
+    const unsigned int row = (iy & (unsigned int) (nyl - 1)) + ((ix << ny_shift));   // < 2^24
+    return reinterpret_cast<cplx<T> *>(base[iy >> ny_shift]) + ((size_t) row * (unsigned int) nc + (unsigned int) c);
   }
 };
 
@@ -803,6 +803,7 @@ struct DevTailSink {
   int chunk;
   GX_HD void push(int list, int idx, unsigned int u1, bool positive) {
 #ifdef __CUDA_ARCH__
+    if (cap == 0) return;
     const unsigned int s = atomicAdd(count, 1u);
     if (s < cap) {
       StagedTail t;
@@ -822,7 +823,7 @@ __device__ __forceinline__ int stream_of_chunk(const StreamDesc *streams, int n_
   return lo;
 }
 
-template <int MINB>
+template <int MINB, bool FMA>
 __global__ void __launch_bounds__(kThreads, MINB) rng_gen_kernel(GenParams P) {
   __shared__ unsigned int s_k[128];
   __shared__ double s_w[128], s_y[128];
@@ -830,19 +831,20 @@ __global__ void __launch_bounds__(kThreads, MINB) rng_gen_kernel(GenParams P) {
   __shared__ uint32_t sbuf[4][kThreads];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_k[i] = d_zig_ktab[i]; s_w[i] = d_zig_wtab[i]; s_y[i] = d_zig_ytab[i]; }
   __syncthreads();
-  const int rel = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rel >= P.count) return;  // exited lanes do not take part in the __syncwarp of gen_chunk
+  // gen_chunk is warp-collective: the lanes past the end of the batch redo its last chunk (identical stores) and report nothing
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = slot < P.count;
+  const int rel = in_range ? slot : P.count - 1;
   const int chunk = P.first + rel;
   const StreamDesc &sd = P.streams[stream_of_chunk(P.streams, P.n_streams, chunk)];
   const int q = chunk - sd.first_chunk;
   const State st = chunk_start_state(sd, q, P.jump);
-  DevTailSink sink{P.tails, P.tail_count, P.tail_cap, rel};
+  DevTailSink sink{P.tails, P.tail_count, in_range ? P.tail_cap : 0u, rel};
   ChunkFn f;
   ListMeta m;
-  gen_chunk(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x}, s_k, s_w, s_y,
-            P.stage + (size_t) rel * kChunkStage, f, m, sink);
-  P.fn[rel] = f;
-  P.meta[rel] = m;
+  gen_chunk<FMA>(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x}, s_k, s_w, s_y,
+                 P.stage + (size_t) rel * kChunkStage, f, m, sink);
+  if (in_range) { P.fn[rel] = f; P.meta[rel] = m; }
 }
 
 __global__ void resolve_kernel(const ChunkFn *fn, const ScanState *scan, const ListMeta *meta, uint32_t *stage, ChunkLoc *loc,
@@ -874,12 +876,19 @@ __global__ void tail_resolve_kernel(const StagedTail *st, const unsigned int *co
   }
 }
 
+__global__ void shell_scale_kernel(const ChunkLoc *loc, const int *shell_first, int chunk0, int sa, int sb, float *scale) {
+  const int ks = sa + blockIdx.x * blockDim.x + threadIdx.x;
+  if (ks >= sb) return;
+  scale[ks] = locate_scale(loc, shell_first[ks] - chunk0, shell_first[ks + 1] - shell_first[ks]);
+}
+
 template <typename T> struct DeliverParams {
   Owners<T> own;
   int reverse;
   double sigma;
   const T *wtab;
   const int *shell_first;  // [n/2 + 1]: global index of the first chunk of shell ks (entry ks + 1: its end)
+  const float *shell_scale; // [n/2]: locate_scale of shell ks (valid for the batch's shells)
   int chunk0;              // global index of the batch's first chunk
   const ChunkLoc *loc;     // per batch chunk
   const uint32_t *stage;
@@ -910,7 +919,7 @@ __global__ void __launch_bounds__(256) deliver_kernel(DeliverParams<T> P) {
       const int c0 = ((p + ks) * 2 * ks + (q + ks)) * 3;
       const long long g0 = 2ll * c0;
       const int fc = P.shell_first[ks] - P.chunk0, nch = P.shell_first[ks + 1] - P.shell_first[ks];
-      int ci = locate_chunk(P.loc, fc, nch, g0);
+      int ci = locate_chunk(P.loc, fc, nch, g0, P.shell_scale[ks]);
       ChunkLoc L = P.loc[ci];
       long long hi = (ci + 1 < fc + nch) ? P.loc[ci + 1].base : 0x7fffffffffffffffll;
       double d[6];
@@ -991,7 +1000,7 @@ struct Shard { int world = 1, rank = 0; void *peers[kMaxPeers] = {nullptr}; };
 
 static int staged_minb() {
   static int minb = -1;
-  if (minb < 0) { const char *e = getenv("GX_RNG_GEN_MINB"); minb = e ? atoi(e) : 6; }
+  if (minb < 0) { const char *e = getenv("GX_RNG_GEN_MINB"); minb = e ? atoi(e) : 5; }
   return minb;
 }
 
@@ -1005,7 +1014,9 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
   const int h = n / 2, ns = h - 1;
   const int world = shard.world, rank = shard.rank, nyl = n / world;
   Owners<T> own;
-  own.n = n; own.nc = h + 1; own.nyl = nyl;
+  own.n = n; own.nc = h + 1; own.nyl = nyl; own.ny_shift = 0;
+  while ((1 << own.ny_shift) < nyl) ++own.ny_shift;
+  if ((1 << own.ny_shift) != nyl) return fail("gx_noise_draw: n / world must be a power of two");
   for (int r = 0; r < kMaxPeers; ++r) own.base[r] = nullptr;
   if (world == 1) own.base[0] = field;
   else for (int r = 0; r < world; ++r) own.base[r] = (T *) (r == rank ? (void *) field : shard.peers[r]);
@@ -1089,7 +1100,7 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
   const unsigned int staged_cap = (unsigned int) std::min<long long>((long long) (max_batch_gauss * 1.5e-3) + 8192, 600000000ll);
   const unsigned int tail_cap = (unsigned int) std::min<long long>((long long) (my_gauss * 8e-4) + 4096, 400000000ll);
   void *p_streams, *p_misc, *p_tails, *p_fn, *p_st, *p_meta, *p_staged;
-  if (ws_dev(0, sizeof(StreamDesc) * ns + sizeof(int) * (h + 1), &p_streams)) return 1;
+  if (ws_dev(0, sizeof(StreamDesc) * ns + sizeof(int) * (h + 1) + sizeof(float) * (h + 1), &p_streams)) return 1;
   if (ws_dev(1, 64, &p_misc)) return 1;
   if (ws_dev(2, sizeof(TailEvent) * (size_t) tail_cap, &p_tails)) return 1;
   if (ws_dev(3, sizeof(ChunkFn) * fn_total, &p_fn)) return 1;
@@ -1098,6 +1109,7 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
   if (ws_dev(7, sizeof(StagedTail) * (size_t) staged_cap, &p_staged)) return 1;
   StreamDesc *d_streams = (StreamDesc *) p_streams;
   int *d_shell_first = (int *) ((char *) p_streams + sizeof(StreamDesc) * ns);
+  float *d_shell_scale = (float *) (d_shell_first + h + 1);
   unsigned int *d_staged_count = (unsigned int *) p_misc, *d_tail_count = d_staged_count + 1;
   ChunkLoc *d_loc = (ChunkLoc *) p_meta;
   ListMeta *d_meta = (ListMeta *) ((char *) p_meta + sizeof(ChunkLoc) * (size_t) max_batch);
@@ -1127,10 +1139,19 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
       GX_TIMED("rng_gen", cs);
       const int grid = (cnt + kThreads - 1) / kThreads;
       const int mb = staged_minb();
-      if (mb == 4) rng_gen_kernel<4><<<grid, kThreads, 0, cs>>>(G);
-      else if (mb == 5) rng_gen_kernel<5><<<grid, kThreads, 0, cs>>>(G);
-      else if (mb == 8) rng_gen_kernel<8><<<grid, kThreads, 0, cs>>>(G);
-      else rng_gen_kernel<6><<<grid, kThreads, 0, cs>>>(G);
+      // mask of the SWB step on the fma pipe (IMAD.HI + IMAD) instead of the alu pipe: measured SLOWER at 2048^3
+      // (100 against 87 ms, profiles/r2s4_*): off unless GX_RNG_FMA_MASK=1
+      static int fma = -1;
+      if (fma < 0) { const char *e = getenv("GX_RNG_FMA_MASK"); fma = (e && e[0] == '1') ? 1 : 0; }
+      if (fma) {
+        if (mb == 5) rng_gen_kernel<5, true><<<grid, kThreads, 0, cs>>>(G);
+        else if (mb == 8) rng_gen_kernel<8, true><<<grid, kThreads, 0, cs>>>(G);
+        else rng_gen_kernel<6, true><<<grid, kThreads, 0, cs>>>(G);
+      } else {
+        if (mb == 5) rng_gen_kernel<5, false><<<grid, kThreads, 0, cs>>>(G);
+        else if (mb == 8) rng_gen_kernel<8, false><<<grid, kThreads, 0, cs>>>(G);
+        else rng_gen_kernel<6, false><<<grid, kThreads, 0, cs>>>(G);
+      }
       count_launch();
     }
     GX_LAUNCH_CHECK();
@@ -1148,6 +1169,8 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
       }
       resolve_kernel<<<(cnt + 127) / 128, 128, 0, cs>>>(d_fn[0], d_st[0], d_meta, (uint32_t *) scratch, d_loc, cnt);
       count_launch();
+      shell_scale_kernel<<<(sb - sa + 127) / 128, 128, 0, cs>>>(d_loc, d_shell_first, c0, sa, sb, d_shell_scale);
+      count_launch();
       tail_resolve_kernel<<<128, 256, 0, cs>>>((const StagedTail *) p_staged, d_staged_count, staged_cap, d_fn[0], d_st[0], d_meta,
                                                d_loc, d_streams, ns, c0, (TailEvent *) p_tails, d_tail_count, tail_cap,
                                                d_tail_count + 1);
@@ -1155,7 +1178,7 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
     }
     GX_LAUNCH_CHECK();
     DeliverParams<T> D;
-    D.own = own; D.reverse = reverse; D.sigma = sigma; D.wtab = wtab; D.shell_first = d_shell_first; D.chunk0 = c0;
+    D.own = own; D.reverse = reverse; D.sigma = sigma; D.wtab = wtab; D.shell_first = d_shell_first; D.shell_scale = d_shell_scale; D.chunk0 = c0;
     D.loc = d_loc; D.stage = (const uint32_t *) scratch; D.sa = sa; D.sb = sb;
     const int top = sb - 1;                       // p, q in [-top, top)
     D.p_origin = -top;

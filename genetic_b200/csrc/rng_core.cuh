@@ -231,6 +231,54 @@ __device__ __forceinline__ void swb_round_cc(uint32_t (&lo)[12], uint32_t (&hi)[
         "+r"(hi[4]), "+r"(hi[5]), "+r"(hi[6]), "+r"(hi[7]), "+r"(hi[8]), "+r"(hi[9]), "+r"(hi[10]), "+r"(hi[11]),
         "+r"(c));
 }
+// The same round with the mask on the FMA pipe: x & 0xFFFF0000 as (x * 2^16 >> 32) * 2^16 = IMAD.HI + IMAD. The alu pipe
+// (IADD3.X, LOP3) issues one warp instruction every 2 cycles per scheduler and the generator is nothing but alu work, so
+// the noise kernels were bound by that pipe (ncu: alu 71 %, fma idle); this leaves 2 alu + 2 fma instructions per word step.
+__device__ __forceinline__ void swb_round_cc_fma(uint32_t (&lo)[12], uint32_t (&hi)[12], uint32_t &c) {
+#define GX_SWB_STEP(I, J, HI, HJ) \
+  "subc.cc.u32 %" #I ", %" #J ", %" #I ";\n\t subc.cc.u32 %" #HI ", %" #HJ ", %" #HI ";\n\t" \
+  "mul.hi.u32 u, %" #I ", 0x10000;\n\t mul.lo.u32 %" #I ", u, 0x10000;\n\t"
+  asm volatile(
+      "{\n\t.reg .u32 t, u;\n\t"
+      "sub.cc.u32 t, 0, %24;\n\t"
+      GX_SWB_STEP(0, 7, 12, 19) GX_SWB_STEP(1, 8, 13, 20) GX_SWB_STEP(2, 9, 14, 21) GX_SWB_STEP(3, 10, 15, 22)
+      GX_SWB_STEP(4, 11, 16, 23) GX_SWB_STEP(5, 0, 17, 12) GX_SWB_STEP(6, 1, 18, 13) GX_SWB_STEP(7, 2, 19, 14)
+      GX_SWB_STEP(8, 3, 20, 15) GX_SWB_STEP(9, 4, 21, 16) GX_SWB_STEP(10, 5, 22, 17) GX_SWB_STEP(11, 6, 23, 18)
+      "subc.u32 %24, 0, 0;\n\t"
+      "}"
+      : "+r"(lo[0]), "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]), "+r"(lo[4]), "+r"(lo[5]), "+r"(lo[6]), "+r"(lo[7]),
+        "+r"(lo[8]), "+r"(lo[9]), "+r"(lo[10]), "+r"(lo[11]), "+r"(hi[0]), "+r"(hi[1]), "+r"(hi[2]), "+r"(hi[3]),
+        "+r"(hi[4]), "+r"(hi[5]), "+r"(hi[6]), "+r"(hi[7]), "+r"(hi[8]), "+r"(hi[9]), "+r"(hi[10]), "+r"(hi[11]),
+        "+r"(c));
+#undef GX_SWB_STEP
+}
+
+// Generator state kept in the (lo, hi) form across increments (no 64-bit repacking per block).
+struct StateCC {
+  uint32_t lo[12], hi[12], c;
+  __device__ __forceinline__ void load(const uint64_t (&x)[12], uint32_t carry) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { lo[i] = (uint32_t) (x[i] << 16); hi[i] = (uint32_t) (x[i] >> 16); }
+    c = carry;
+  }
+  // increment_state: 33 rounds + 1 word step, then rotate so that word 0 is the oldest again
+  template <bool FMA> __device__ __forceinline__ void advance() {
+#pragma unroll 3
+    for (int r = 0; r < 33; ++r) { if (FMA) swb_round_cc_fma(lo, hi, c); else swb_round_cc(lo, hi, c); }
+    uint32_t l0 = lo[0], h0 = hi[0];
+    asm volatile("{\n\t.reg .u32 t;\n\t sub.cc.u32 t, 0, %2;\n\t subc.cc.u32 %0, %3, %0;\n\t subc.cc.u32 %1, %4, %1;\n\t"
+                 "and.b32 %0, %0, 0xFFFF0000;\n\t subc.u32 %2, 0, 0;\n\t}"
+                 : "+r"(l0), "+r"(h0), "+r"(c) : "r"(lo[7]), "r"(hi[7]));
+#pragma unroll
+    for (int i = 0; i < 11; ++i) { lo[i] = lo[i + 1]; hi[i] = hi[i + 1]; }
+    lo[11] = l0; hi[11] = h0;
+  }
+  // out[2i] = low 24 bits of word i, out[2i+1] = high 24 bits
+  __device__ __forceinline__ uint32_t out(int j) const {
+    const int i = j >> 1;
+    return (j & 1) ? (hi[i] >> 8) : (((hi[i] & 0xFFu) << 16) | (lo[i] >> 16));
+  }
+};
 #endif
 
 // increment_state of ranlxs2: 397 = 33*12 + 1 word steps, then rotate so x[0] is the oldest again.

@@ -101,78 +101,138 @@ GX_HD double unpack_draw(uint32_t e, const double *wtab) {
   return GX_DMUL(GX_DMUL(sign, 1.0), x);
 }
 
-// One chunk: `st` is the generator state at the chunk's first block. Ring::at(slot) / Buf::at(k) are the thread's raw-output
-// ring (kRing slots) and its 4-entry store buffer (shared memory on the device, plain arrays on the host); `stage` is the
-// chunk's kChunkStage words; sink.push(list, idx, u1, positive) records accepted tail draws.
-template <class Ring, class Buf, class Sink>
-GX_HD void gen_chunk(const StreamDesc &sd, bool first, State st, Ring ring, Buf buf, const unsigned int *ktab,
-                     const double *wtab, const double *ytab, uint32_t *stage, ChunkFn &f, ListMeta &meta, Sink &sink) {
-  int pos[4], cnt[4], rep[4], joinv[4];
-  int ncur;
-  if (first) { ncur = 1; pos[0] = sd.entry0; pos[1] = pos[2] = pos[3] = 0; }
-  else { ncur = 4; for (int e = 0; e < 4; ++e) pos[e] = e; }
-  for (int e = 0; e < 4; ++e) { cnt[e] = 0; rep[e] = -1; joinv[e] = 0; }
-
-  for (int bi = 0; bi <= kBc; ++bi) {
-    GX_SYNCWARP();  // the 397-step advance runs with the warp converged
-    advance_block(st);
-    const int rbase = 24 * bi;
-#pragma unroll
-    for (int j = 0; j < 24; ++j) ring.at((rbase + j) & (kRing - 1)) = block_output(st, j);
-    const int avail = 24 * (bi + 1);
-    const int limit = avail - 3 < kChunkLen ? avail - 3 : kChunkLen;
-    for (int e = 0; e < ncur; ++e) {
-      if (rep[e] >= 0) continue;
-      int p = pos[e];
-      while (p < limit) {
-        const uint32_t r0 = ring.at(p & (kRing - 1)), r1 = ring.at((p + 1) & (kRing - 1));
-        const Attempt a = zig_attempt(r0, r1, ring.at((p + 2) & (kRing - 1)), ring.at((p + 3) & (kRing - 1)), ktab, wtab, ytab);
-        p += a.consumed;
-        if (a.accepted) {
-          const uint32_t d = pack_draw(r0, r1);
-          const int c = cnt[e];
-          if (a.tail) sink.push(e, c, a.tail_u1, a.value > 0);
-          if (e == 0) {  // the long list leaves as 16-byte stores
-            buf.at(c & 3) = d;
-            if ((c & 3) == 3) {
 #ifdef __CUDA_ARCH__
-              *reinterpret_cast<uint4 *>(stage + (c - 3)) = make_uint4(buf.at(0), buf.at(1), buf.at(2), d);
+#define GX_ANY(x) __any_sync(0xffffffffu, (x))
 #else
-              for (int k = 0; k < 4; ++k) stage[c - 3 + k] = buf.at(k);
+#define GX_ANY(x) (x)
 #endif
-            }
-          } else {
-            stage[e * kCap + c] = d;
-          }
-          cnt[e] = c + 1;
-        }
-      }
-      pos[e] = p;
+
+// generator state of a chunk thread: (lo, hi) register form on the device, the plain words on the host
+template <bool FMA> struct GenState {
+#ifdef __CUDA_ARCH__
+  StateCC s;
+  GX_HD void load(const State &st) { s.load(st.x, st.c); }
+  GX_HD void advance() { s.template advance<FMA>(); }
+  GX_HD uint32_t out(int j) const { return s.out(j); }
+#else
+  State s;
+  GX_HD void load(const State &st) { s = st; }
+  GX_HD void advance() { advance_block(s); }
+  GX_HD uint32_t out(int j) const { return block_output(s, j); }
+#endif
+};
+
+template <int E, class Buf> GX_HD void append_draw(uint32_t d, int c, Buf buf, uint32_t *stage) {
+  if (E == 0) {  // the long list leaves as 16-byte stores
+    buf.at(c & 3) = d;
+    if ((c & 3) == 3) {
+#ifdef __CUDA_ARCH__
+      *reinterpret_cast<uint4 *>(stage + (c - 3)) = make_uint4(buf.at(0), buf.at(1), buf.at(2), d);
+#else
+      for (int k = 0; k < 4; ++k) stage[c - 3 + k] = buf.at(k);
+#endif
     }
-    if (ncur == 4) {  // merge hypotheses that have reached the same position
-      for (int e = 1; e < 4; ++e) {
-        if (rep[e] >= 0) continue;
-        for (int r = 0; r < e; ++r)
-          if (rep[r] < 0 && pos[r] == pos[e]) { rep[e] = r; joinv[e] = cnt[r]; break; }
+  } else {
+    stage[E * kCap + c] = d;
+  }
+}
+
+// Hypothesis E of a chunk parsed up to raw position `limit`. ALL lanes of the warp call this together (`live` says whether
+// the lane has work): 98.8 % of the attempts are the integer fast path (j < ktab[i]); the others need exp() (wedge) or
+// log() and exp() (tail), ~150 instructions that used to run for one or two lanes at a time at every loop iteration in
+// which any lane needed them (ncu: 21 % of the kernel's instructions at 12.7 of 32 lanes). Here a lane that meets a slow
+// attempt waits; when every lane has either finished or waits, the waiting lanes evaluate theirs together.
+template <int E, class Ring, class Buf, class Sink>
+GX_HD void parse_hypothesis(bool live, int &p, int &c, int limit, Ring ring, Buf buf, const unsigned int *ktab,
+                            const double *wtab, const double *ytab, uint32_t *stage, Sink &sink) {
+  bool more = live && p < limit;
+  while (GX_ANY(more)) {
+    bool slow = false;
+    uint32_t r0 = 0, r1 = 0;
+    while (more) {
+      r0 = ring.at(p & (kRing - 1));
+      r1 = ring.at((p + 1) & (kRing - 1));
+      if (r1 < ktab[r0 & 0x7Fu]) {
+        append_draw<E>(pack_draw(r0, r1), c, buf, stage);
+        ++c;
+        p += 2;
+        more = p < limit;
+      } else {
+        slow = true;
+        more = false;
       }
+    }
+    GX_SYNCWARP();
+    if (slow) {
+      const Attempt a = zig_attempt(r0, r1, ring.at((p + 2) & (kRing - 1)), ring.at((p + 3) & (kRing - 1)), ktab, wtab, ytab);
+      if (a.accepted) {
+        if (a.tail) sink.push(E, c, a.tail_u1, a.value > 0);
+        append_draw<E>(pack_draw(r0, r1), c, buf, stage);
+        ++c;
+      }
+      p += a.consumed;
+      more = p < limit;
     }
   }
-  for (int k = cnt[0] & ~3; k < cnt[0]; ++k) stage[k] = buf.at(k & 3);
+}
 
+// One chunk: `st` is the generator state at the chunk's first block. Ring::at(slot) / Buf::at(k) are the thread's raw-output
+// ring (kRing slots) and its 4-entry store buffer (shared memory on the device, plain arrays on the host); `stage` is the
+// chunk's kChunkStage words; sink.push(list, idx, u1, positive) records accepted tail draws. Warp-collective on the
+// device: every lane of the warp must call it.
+template <bool FMA, class Ring, class Buf, class Sink>
+GX_HD void gen_chunk(const StreamDesc &sd, bool first, const State &st0, Ring ring, Buf buf, const unsigned int *ktab,
+                     const double *wtab, const double *ytab, uint32_t *stage, ChunkFn &f, ListMeta &meta, Sink &sink) {
+  int p0, p1 = 1, p2 = 2, p3 = 3;          // positions of the four entry hypotheses
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // draws appended to their lists
+  int rep1 = -1, rep2 = -1, rep3 = -1;     // list a hypothesis merged into (a lower one), -1 while it is on its own
+  int j1 = 0, j2 = 0, j3 = 0;              // index in that list at which its path continues
+  p0 = first ? sd.entry0 : 0;
+  if (first) rep1 = rep2 = rep3 = 0;       // a stream's first chunk starts at a known position: one hypothesis
+  GenState<FMA> gs;
+  gs.load(st0);
+
+  for (int bi = 0; bi <= kBc; ++bi) {
+    GX_SYNCWARP();
+    gs.advance();
+    const int rbase = 24 * bi;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) ring.at((rbase + j) & (kRing - 1)) = gs.out(j);
+    const int avail = 24 * (bi + 1);
+    const int limit = avail - 3 < kChunkLen ? avail - 3 : kChunkLen;
+    parse_hypothesis<0>(true, p0, c0, limit, ring, buf, ktab, wtab, ytab, stage, sink);
+    if (GX_ANY(rep1 < 0)) parse_hypothesis<1>(rep1 < 0, p1, c1, limit, ring, buf, ktab, wtab, ytab, stage, sink);
+    if (GX_ANY(rep2 < 0)) parse_hypothesis<2>(rep2 < 0, p2, c2, limit, ring, buf, ktab, wtab, ytab, stage, sink);
+    if (GX_ANY(rep3 < 0)) parse_hypothesis<3>(rep3 < 0, p3, c3, limit, ring, buf, ktab, wtab, ytab, stage, sink);
+    // merge hypotheses that have reached the same position (into the lowest one)
+    if (rep1 < 0 && p1 == p0) { rep1 = 0; j1 = c0; }
+    if (rep2 < 0) {
+      if (p2 == p0) { rep2 = 0; j2 = c0; }
+      else if (rep1 < 0 && p2 == p1) { rep2 = 1; j2 = c1; }
+    }
+    if (rep3 < 0) {
+      if (p3 == p0) { rep3 = 0; j3 = c0; }
+      else if (rep1 < 0 && p3 == p1) { rep3 = 1; j3 = c1; }
+      else if (rep2 < 0 && p3 == p2) { rep3 = 2; j3 = c2; }
+    }
+  }
+  for (int k = c0 & ~3; k < c0; ++k) stage[k] = buf.at(k & 3);
+
+  const int pos[4] = {p0, p1, p2, p3}, cnt[4] = {c0, c1, c2, c3}, rep[4] = {-1, rep1, rep2, rep3}, joinv[4] = {0, j1, j2, j3};
   f.reset = first ? 1 : 0;
+#pragma unroll
   for (int e = 0; e < 4; ++e) {
     int r = first ? 0 : e;
     long long total = 0;
     int start = 0;
-    while (rep[r] >= 0) { total += cnt[r] - start; start = joinv[r]; r = rep[r]; }  // merges can chain (3 -> 1 -> 0)
+    for (int hop = 0; hop < 3 && rep[r] >= 0; ++hop) { total += cnt[r] - start; start = joinv[r]; r = rep[r]; }  // 3 -> 1 -> 0
     total += cnt[r] - start;
     f.exit[e] = (unsigned char) (pos[r] - kChunkLen);
     f.count[e] = total;
-    meta.len[e] = (unsigned short) cnt[e];
-    meta.join[e] = (unsigned short) joinv[e];
-    meta.rep[e] = (signed char) rep[e];
+    meta.len[e] = (unsigned short) (first && e > 0 ? 0 : cnt[e]);
+    meta.join[e] = (unsigned short) (first ? 0 : joinv[e]);
+    meta.rep[e] = (signed char) (first && e > 0 ? 0 : rep[e]);
   }
-  if (first) for (int e = 1; e < 4; ++e) { meta.len[e] = 0; meta.join[e] = 0; meta.rep[e] = 0; }
 }
 
 // ---- resolve -------------------------------------------------------------------------------------------------------
@@ -214,17 +274,19 @@ GX_HD int path_index(const ListMeta &m, int entry, int list, int idx) {
   return -1;
 }
 
-// the chunk of a stream (chunks [fc, fc + nch) of `loc`) that holds gaussian g
-GX_HD int locate_chunk(const ChunkLoc *loc, int fc, int nch, long long g) {
-  int k = 0;
-  if (nch > 1) {
-    const long long last = loc[fc + nch - 1].base;
-    k = (int) ((double) g * (double) (nch - 1) / (double) last);
-    if (k > nch - 1) k = nch - 1;
-  }
+// the chunk of a stream (chunks [fc, fc + nch) of `loc`) that holds gaussian g; `guess_scale` ~ chunks per gaussian of this
+// stream ((nch - 1) / base of its last chunk): the counts per chunk scatter by a few draws, so the guess is off by a
+// chunk or two at most and the probes below finish it
+GX_HD int locate_chunk(const ChunkLoc *loc, int fc, int nch, long long g, float guess_scale) {
+  int k = (int) ((float) g * guess_scale);
+  if (k > nch - 1) k = nch - 1;
   while (k > 0 && loc[fc + k].base > g) --k;
   while (k + 1 < nch && loc[fc + k + 1].base <= g) ++k;
   return fc + k;
+}
+
+GX_HD float locate_scale(const ChunkLoc *loc, int fc, int nch) {
+  return nch > 1 ? (float) ((double) (nch - 1) / (double) loc[fc + nch - 1].base) : 0.0f;
 }
 
 // ---- deliver -------------------------------------------------------------------------------------------------------

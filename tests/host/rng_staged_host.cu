@@ -60,7 +60,7 @@ int host_staged_noise(int n, unsigned long seed, int reverse, double *out, unsig
       X = modmul(X, jump);
       uint32_t ring[kRing], buf[4];
       HostSink sink{&tails, chunk};
-      gen_chunk(sd[s], q == 0, st, HostRing{ring}, HostRing{buf}, gx_zig_ktab, gx_zig_wtab, gx_zig_ytab,
+      gen_chunk<false>(sd[s], q == 0, st, HostRing{ring}, HostRing{buf}, gx_zig_ktab, gx_zig_wtab, gx_zig_ytab,
                 stage.data() + (size_t) chunk * kChunkStage, fn[chunk], meta[chunk], sink);
       for (int e = 1; e < 4; ++e) {
         if (q > 0 && meta[chunk].rep[e] > 0) ++multi_hop;
@@ -103,7 +103,7 @@ int host_staged_noise(int n, unsigned long seed, int reverse, double *out, unsig
   auto draw = [&](int s, long long g) -> double {
     for (const Patch &p : patches) if (p.stream == s && p.g == g) return p.v;
     const int nch = (s + 1 < (int) sd.size() ? sd[s + 1].first_chunk : n_chunks) - sd[s].first_chunk;
-    const int c = locate_chunk(loc.data(), sd[s].first_chunk, nch, g);
+    const int c = locate_chunk(loc.data(), sd[s].first_chunk, nch, g, locate_scale(loc.data(), sd[s].first_chunk, nch));
     const int i = (int) (g - loc[c].base);
     return unpack_draw(fetch_draw(loc[c], stage.data() + (size_t) c * kChunkStage, i), gx_zig_wtab);
   };
