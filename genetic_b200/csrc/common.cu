@@ -51,4 +51,24 @@ int gx_timing_report(char *buf, int buflen) {
   if (buflen > 0) { memcpy(buf, out.c_str(), out.size()); buf[out.size()] = 0; }
   return (int) acc.size();
 }
+
+// ---- peer memory between the ranks of one node (one process per GPU): CUDA IPC over a cudaMalloc'ed allocation ----------
+// handle_out: 64 bytes (cudaIpcMemHandle_t). ptr must be the base of an allocation made by gx_malloc.
+int gx_ipc_get_handle(void *ptr, void *handle_out) {
+  cudaIpcMemHandle_t h;
+  GX_CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+int gx_ipc_open(const void *handle, void **ptr_out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  GX_CUDA_CHECK(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int gx_ipc_close(void *ptr) {
+  GX_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
 }

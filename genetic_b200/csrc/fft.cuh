@@ -43,6 +43,24 @@ template <typename T> struct OpScale {
   __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int, int) const { return mk<T>(v.x * s, v.y * s); }
 };
 
+// Store-side redirect (slab path, several GPUs): the inverse x-pass writes every element straight into the exchange buffer
+// of the rank that owns its x plane -- peer-mapped memory, NVLink stores of whole TC-column row segments -- so the FFT
+// transpose needs no send buffer, no all-to-all kernel and no second sweep: compute and collective are one kernel.
+// Element (ix, ky_local, kz) of rank r lands in peer (ix / P) at [r][ix % P][ky_local][kz].
+template <typename T> struct OpPushX {
+  cplx<T> *peer[8];
+  int pshift, pmask;       // P = n / world = 1 << pshift
+  long self_off;           // r * P * P * nc: this rank's block in every peer's buffer
+  long line_stride;        // P * nc: one x plane of a block
+  static constexpr bool kPush = true;
+  __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int, int) const { return v; }
+  __device__ __forceinline__ cplx<T> *addr(int row, long col) const {
+    return peer[row >> pshift] + (self_off + (long) (row & pmask) * line_stride + col);
+  }
+};
+template <class S, class = void> struct is_push : std::false_type {};
+template <class S> struct is_push<S, std::void_t<decltype(S::kPush)>> : std::true_type {};
+
 // ---- which axis a column pass transforms ---------------------------------------------------------
 // PassY: batch = i0, line index = i1, column = i2            (line stride nc,   batch stride n1*nc)
 // PassX: one batch, line index = i0, column = i1*nc + i2     (line stride n1*nc)
@@ -142,7 +160,7 @@ __device__ __forceinline__ void cluster_arrive_relaxed_after(float dep) {
 template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
 __global__ void __launch_bounds__(ColsCfg<T, N, CL, TC, SEL>::threads, MINB)
 fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int nclusters, const cplx<T> *__restrict__ twR,
-                const cplx<T> *__restrict__ twN, LoadOp lop, StoreOp sop) {
+                const cplx<T> *__restrict__ twN, LoadOp lop, const __grid_constant__ StoreOp sop) {
   using C = cplx<T>;
   using Cfg = ColsCfg<T, N, CL, TC, SEL>;
   using B = BlockFFT<T, Cfg::R, DIR, TC, Cfg::SEL>;
@@ -202,7 +220,8 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
     auto store = [&](int row, C val) {
       if (active) {
         C y = std::is_same<Pass, PassY>::value ? sop(val, batch, row, c2) : sop(val, row, c1, c2);
-        dst[base + g.dst.off(row)] = y;
+        if constexpr (is_push<StoreOp>::value) *sop.addr(row, base) = y;
+        else dst[base + g.dst.off(row)] = y;
       }
     };
 

@@ -25,6 +25,7 @@
 #include "rng_core.cuh"
 #include "rng_staged_core.cuh"
 #include "zig_tables.h"  // generated constant tables (GSL's published 128-level ziggurat)
+#include "zeldovich.cuh"   // build_transfer_table
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -1333,6 +1334,33 @@ int gx_slab_noise_finish(void *slab, const void *fn_all, int n, int dtype, int w
   Phase ph; ph.which = 2; ph.world = world; ph.rank = rank; ph.fn_io = const_cast<void *>(fn_all);
   if (dtype == GX_F64) return noise_draw_t<double>(slab, n, seed, GX_NOISE_FOURIER_PARALLEL, reverse_order, nullptr, (cudaStream_t) stream, world, rank, ph);
   if (dtype == GX_F32) return noise_draw_t<float>(slab, n, seed, GX_NOISE_FOURIER_PARALLEL, reverse_order, nullptr, (cudaStream_t) stream, world, rank, ph);
+  return gx::fail("bad dtype");
+}
+
+// Parallel Fourier order on G ranks through the staged path: this rank generates its share of the shells (balanced by
+// generator work) ONCE and stores every mode straight into the slab of the rank that owns its ky row -- peer_slabs[r] are
+// peer-mapped pointers (gx_ipc_open) to the ranks' ky-slabs, peer_slabs[rank] == slab. With `spectrum` the factor
+// sqrt(C(k)) / k^2 is applied as the modes are stored (the slab then holds delta_k / k^2, as after gx_slab_apply_transfer
+// with divide_k2). The caller brackets the call with barriers across the ranks: nobody may still read the slabs when the
+// first rank starts, and all ranks must have finished before anybody reads its slab.
+int gx_slab_noise_staged(void *slab, int n, int dtype, int world, int rank, unsigned long seed, int reverse_order,
+                         void *const *peer_slabs, const gx_spectrum *spectrum, double grid_length, void *scratch,
+                         size_t scratch_bytes, void *stream) {
+  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (world < 1 || world > kMaxPeers || !gx::is_pow2(world) || n % world != 0 || rank < 0 || rank >= world)
+    return gx::fail("gx_slab_noise_staged: bad world/rank (at most 8 ranks, powers of two)");
+  Shard sh;
+  sh.world = world; sh.rank = rank;
+  for (int r = 0; r < world; ++r) {
+    sh.peers[r] = r == rank ? slab : (peer_slabs ? peer_slabs[r] : nullptr);
+    if (!sh.peers[r]) return gx::fail("gx_slab_noise_staged: null peer pointer");
+  }
+  cudaStream_t cs = (cudaStream_t) stream;
+  const void *table = nullptr;
+  if (spectrum)
+    if (int rc = gx::build_transfer_table(n, dtype, grid_length, spectrum, 0.5, 1, cs, &table)) return rc;
+  if (dtype == GX_F64) return noise_parallel_staged<double>((double *) slab, n, seed, reverse_order, (const double *) table, scratch, scratch_bytes, cs, sh);
+  if (dtype == GX_F32) return noise_parallel_staged<float>((float *) slab, n, seed, reverse_order, (const float *) table, scratch, scratch_bytes, cs, sh);
   return gx::fail("bad dtype");
 }
 

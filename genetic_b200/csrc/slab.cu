@@ -18,6 +18,7 @@
 #include "spectral.cuh"
 #include "fft.cuh"
 #include "zeldovich.cuh"
+#include "zeldovich_ops.cuh"
 #include <algorithm>
 
 namespace gx {
@@ -88,6 +89,24 @@ static int slab_x_mirror_t(const void *src, const void *planes, void *dst, int n
   GX_N_SWITCH(n, (slab_x_n<T, N, 1>(src, dst, P, op, fft::OpIdentity<T>(), st)));
 }
 
+// the same pass with the exchange fused into its store: every element goes straight to its owner's exchange buffer
+template <typename T, int MODE>
+static int slab_x_push_t(const void *src, const void *planes, void *const *peer_bufs, int n, int world, int rank, double L,
+                         int axis, cudaStream_t st) {
+  OpSlabMirror<T, MODE> op;
+  op.planes = (const cplx<T> *) planes; op.n = n; op.axis = axis; op.P = n / world; op.iy0 = rank * op.P;
+  op.pshift = 0; while ((1 << op.pshift) < op.P) ++op.pshift;
+  op.kmin = (T) (2. * M_PI / (double) (T) L);
+  const int P = op.P;
+  const long nc = n / 2 + 1;
+  fft::OpPushX<T> push;
+  for (int r = 0; r < 8; ++r) push.peer[r] = (cplx<T> *) (r < world ? peer_bufs[r] : nullptr);
+  push.pshift = op.pshift; push.pmask = P - 1;
+  push.self_off = (long) rank * P * P * nc;
+  push.line_stride = (long) P * nc;
+  GX_N_SWITCH(n, (slab_x_n<T, N, 1>(src, nullptr, P, op, push, st)));
+}
+
 template <typename T> static int slab_x_plain_t(void *data, int n, int world, int dir, int scale, cudaStream_t st) {
   const int P = n / world;
   const T s = scale ? (T) (1.0 / pow((double) n, 1.5)) : (T) 1;
@@ -109,6 +128,33 @@ static int slab_y_n(const void *src, void *dst, int P, int src_blocked, int dst_
   g.dst = dst_blocked ? blocked : plain;
   return launch_cols_cfg<T, N, PL::CL, PL::TC, PL::MINB, PL::SEL, DIR, PassY>((const cplx<T> *) src, (cplx<T> *) dst, g, P,
                                                                              OpIdentity<T>(), OpIdentity<T>(), st);
+}
+
+// inverse y-pass out of the exchange layout with i k_axis applied as the elements are loaded (axis 1 or 2)
+template <typename T, int N, class LoadOp>
+static int slab_y_op_n(const void *src, void *dst, int P, int src_blocked, LoadOp lop, cudaStream_t st) {
+  using namespace fft;
+  using PL = ColsPlan<T, N>;
+  const int nc = N / 2 + 1;
+  ColGeo g;
+  g.nc = nc; g.tiles_per_batch = 0; g.ncols = nc;
+  const LineMap plain = plain_map(nc, (long) N * nc);
+  const LineMap blocked = blocked_map(nc, (long) P * nc, P, (long) P * P * nc);
+  g.src = src_blocked ? blocked : plain;
+  g.dst = plain;
+  return launch_cols_cfg<T, N, PL::CL, PL::TC, PL::MINB, PL::SEL, 1, PassY>((const cplx<T> *) src, (cplx<T> *) dst, g, P, lop,
+                                                                           OpIdentity<T>(), st);
+}
+template <typename T>
+static int slab_y_op_t(const void *src, void *dst, int n, int world, int sb, double L, int axis, cudaStream_t st) {
+  const int P = n / world;
+  const T kmin = (T) (2. * M_PI / (double) (T) L);
+  if (axis == 1) {
+    OpIKy<T> op; op.n = n; op.kmin = kmin;
+    GX_N_SWITCH(n, (slab_y_op_n<T, N>(src, dst, P, sb, op, st)));
+  }
+  OpIKz<T> op; op.n = n; op.kmin = kmin;
+  GX_N_SWITCH(n, (slab_y_op_n<T, N>(src, dst, P, sb, op, st)));
 }
 
 template <typename T>
@@ -178,6 +224,39 @@ int gx_slab_fft_x_mirror(const void *slab, const void *planes_all, void *out, in
   if (dtype == GX_F64) { GX_SLAB_X(double) }
   if (dtype == GX_F32) { GX_SLAB_X(float) }
 #undef GX_SLAB_X
+  return fail("bad dtype");
+}
+
+int gx_slab_fft_x_mirror_push(const void *slab, const void *planes_all, void *const *peer_exchange, int n, int dtype,
+                              int world, int rank, double grid_length, int op, int axis, void *stream) {
+  if (check_slab(n, world, rank)) return 1;
+  if (world > 8) return fail("gx_slab_fft_x_mirror_push: at most 8 ranks");
+  if (op < 0 || op > 2) return fail("gx_slab_fft_x_mirror_push: op must be 0 (mirror), 1 (i k_axis) or 2 (i k_axis / k^2)");
+  if (op != 0 && (axis < 0 || axis > 2)) return fail("axis must be 0, 1 or 2");
+  if (!peer_exchange) return fail("gx_slab_fft_x_mirror_push: null peer table");
+  for (int r = 0; r < world; ++r) if (!peer_exchange[r]) return fail("gx_slab_fft_x_mirror_push: null peer pointer");
+  if (int rc = fft::ensure_twiddles()) return rc;
+  cudaStream_t st = (cudaStream_t) stream;
+#define GX_SLAB_XP(T)                                                                                              \
+  switch (op) {                                                                                                   \
+    case 0: return slab_x_push_t<T, 0>(slab, planes_all, peer_exchange, n, world, rank, grid_length, axis, st);    \
+    case 1: return slab_x_push_t<T, 1>(slab, planes_all, peer_exchange, n, world, rank, grid_length, axis, st);    \
+    default: return slab_x_push_t<T, 2>(slab, planes_all, peer_exchange, n, world, rank, grid_length, axis, st);   \
+  }
+  if (dtype == GX_F64) { GX_SLAB_XP(double) }
+  if (dtype == GX_F32) { GX_SLAB_XP(float) }
+#undef GX_SLAB_XP
+  return fail("bad dtype");
+}
+
+int gx_slab_fft_y_op(const void *src, void *dst, int n, int dtype, int world, int src_exchange_layout, double grid_length,
+                     int axis, void *stream) {
+  if (check_slab(n, world, 0)) return 1;
+  if (axis != 1 && axis != 2) return fail("gx_slab_fft_y_op: axis must be 1 (i k_y) or 2 (i k_z)");
+  if (src == dst && src_exchange_layout) return fail("gx_slab_fft_y_op: in-place needs the plain layout on both sides");
+  if (int rc = fft::ensure_twiddles()) return rc;
+  if (dtype == GX_F64) return slab_y_op_t<double>(src, dst, n, world, src_exchange_layout, grid_length, axis, (cudaStream_t) stream);
+  if (dtype == GX_F32) return slab_y_op_t<float>(src, dst, n, world, src_exchange_layout, grid_length, axis, (cudaStream_t) stream);
   return fail("bad dtype");
 }
 

@@ -16,6 +16,7 @@
 #include "spectral.cuh"
 #include "fft.cuh"
 #include "zeldovich.cuh"
+#include "zeldovich_ops.cuh"
 
 namespace gx {
 
@@ -61,25 +62,6 @@ template <typename T, bool PREDIV> struct OpZeldovichMirror {
 // (x-passes in place, the out-of-place ones along y). The Hermitian mirror commutes with the diagonal operators on the
 // dependent slots (mirror(i k G) = i k mirror(G)), and the imaginary parts it leaves on self-conjugate entries are dropped
 // by the c2r pass either way, so G's two planes are mirrored once, explicitly, before the shared x-pass.
-template <typename T> struct OpIKy {  // load side of a y-pass: (value, ix, iy, iz)
-  int n;
-  T kmin;
-  __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int iy, int) const {
-    if (iy == (n >> 1)) return mk<T>(0, 0);  // zeldovich.hpp:170-176: zero on the Nyquist plane of the component's axis
-    const T ka = mul_rn((T) signed_mode(iy, n), kmin);
-    return mk<T>(mul_rn(-v.y, ka), mul_rn(v.x, ka));
-  }
-};
-template <typename T> struct OpIKz {  // store side of a y-pass
-  int n;
-  T kmin;
-  __device__ __forceinline__ cplx<T> operator()(cplx<T> v, int, int, int iz) const {
-    if (iz == (n >> 1)) return mk<T>(0, 0);
-    const T ka = mul_rn((T) iz, kmin);
-    return mk<T>(mul_rn(-v.y, ka), mul_rn(v.x, ka));
-  }
-};
-
 template <typename O> struct Pair;
 template <> struct Pair<float> { using type = float2; };
 template <> struct Pair<double> { using type = double2; };

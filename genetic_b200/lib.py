@@ -48,6 +48,9 @@ PROTOTYPES = {
     "gx_memset_zero": (ci, [vp, csz, vp]),
     "gx_host_alloc_pinned": (ci, [P(vp), csz]),
     "gx_host_free_pinned": (ci, [vp]),
+    "gx_ipc_get_handle": (ci, [vp, vp]),
+    "gx_ipc_open": (ci, [vp, P(vp)]),
+    "gx_ipc_close": (ci, [vp]),
     "gx_memcpy_d2d": (ci, [vp, vp, csz, vp]),
     "gx_memcpy_h2d": (ci, [vp, vp, csz, vp]),
     "gx_memcpy_d2h": (ci, [vp, vp, csz, vp]),
@@ -93,11 +96,14 @@ PROTOTYPES = {
     "gx_slab_noise_fn_bytes": (csz, [ci, ci]),
     "gx_slab_noise_pass_a": (ci, [vp, ci, ci, ci, ci, cul, vp]),
     "gx_slab_noise_finish": (ci, [vp, vp, ci, ci, ci, ci, cul, ci, vp]),
+    "gx_slab_noise_staged": (ci, [vp, ci, ci, ci, ci, cul, ci, P(vp), vp, cd, vp, csz, vp]),
     "gx_slab_zero_dc": (ci, [vp, ci, vp]),
     "gx_slab_unit_variance": (ci, [vp, ci, ci, ci, ci, vp]),
     "gx_slab_apply_transfer": (ci, [vp, ci, ci, ci, ci, cd, vp, cd, ci, vp]),
     "gx_slab_extract_planes": (ci, [vp, vp, ci, ci, ci, vp]),
     "gx_slab_fft_x_mirror": (ci, [vp, vp, vp, ci, ci, ci, ci, cd, ci, ci, vp]),
+    "gx_slab_fft_x_mirror_push": (ci, [vp, vp, P(vp), ci, ci, ci, ci, cd, ci, ci, vp]),
+    "gx_slab_fft_y_op": (ci, [vp, vp, ci, ci, ci, ci, cd, ci, vp]),
     "gx_slab_fft_x": (ci, [vp, ci, ci, ci, ci, ci, vp]),
     "gx_slab_fft_y": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "gx_slab_fft_z_r2c": (ci, [vp, ci, ci, ci, vp]),

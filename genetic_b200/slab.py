@@ -81,6 +81,56 @@ class TorchComm:
         if self.world > 1:
             self.dist.barrier(group=self.group)
 
+    def stream_barrier(self):
+        """Barrier in stream order: work enqueued after it on the current stream starts only when every rank's stream has
+        reached the same point (a one-element all-reduce; the kernels that store into peer memory need nothing else)."""
+        if self.world == 1:
+            return
+        import torch
+        if getattr(self, "_token", None) is None:
+            self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.dist.all_reduce(self._token, group=self.group)
+
+    def peer_pointers(self, buf):
+        """Device pointers, valid in THIS process, to the same buffer on every rank (buf from CudaSlabOps.alloc_shared):
+        CUDA IPC handles exchanged once; the own entry is the local pointer."""
+        import torch
+        lib = L.load()
+        if self.world == 1:
+            return [buf.data_ptr()]
+        h = C.create_string_buffer(64)
+        lib.gx_ipc_get_handle(C.c_void_p(buf.data_ptr()), h)
+        mine = torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).cuda()
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device="cuda")
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(buf.data_ptr())
+                continue
+            out = C.c_void_p()
+            lib.gx_ipc_open(C.create_string_buffer(raw[64 * r:64 * (r + 1)], 64), C.byref(out))
+            ptrs.append(out.value)
+        return ptrs
+
+
+class _RawCuda:
+    """A gx_malloc allocation seen by torch (torch.as_tensor reads __cuda_array_interface__): CUDA IPC needs the base of a
+    cudaMalloc allocation, which a tensor from torch's caching allocator is not."""
+
+    def __init__(self, lib, nbytes):
+        self.lib, self.ptr = lib, C.c_void_p()
+        lib.gx_malloc(C.byref(self.ptr), int(nbytes))
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (self.ptr.value, False),
+                                         "version": 2}
+
+    def __del__(self):
+        try:
+            self.lib.gx_free(self.ptr)
+        except Exception:
+            pass
+
 
 class CudaSlabOps:
     """Per-rank passes through the C ABI (include/genetic_b200.h, 'slab decomposition'). Buffers are torch CUDA
@@ -97,8 +147,37 @@ class CudaSlabOps:
     def alloc(self, nbytes):
         return self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
 
+    def alloc_shared(self, nbytes):
+        """A buffer the other ranks' kernels may store into (peer-mapped through CUDA IPC)."""
+        raw = _RawCuda(self.lib, nbytes)
+        t = self.torch.as_tensor(raw, device=self.device)
+        t._gx_raw = raw  # keeps the allocation alive as long as the tensor
+        return t
+
     def _st(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _ptr_table(ptrs):
+        return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+
+    def noise_staged(self, slab, peer_slabs, seed, reverse, spectrum, grid_length, scratch):
+        """Parallel Fourier order, every shell generated on one rank, modes stored straight into their owners' slabs."""
+        g = self.geo
+        self.lib.gx_slab_noise_staged(self._p(slab), g.n, self.dt, g.world, g.rank, seed, int(reverse),
+                                      self._ptr_table(peer_slabs), spectrum.handle if spectrum is not None else None,
+                                      float(grid_length), self._p(scratch) if scratch is not None else None,
+                                      int(scratch.numel()) if scratch is not None else 0, self._st())
+
+    def x_inverse_mirror_push(self, slab, planes_all, peer_exchange, grid_length, op, axis):
+        g = self.geo
+        self.lib.gx_slab_fft_x_mirror_push(self._p(slab), self._p(planes_all), self._ptr_table(peer_exchange), g.n, self.dt,
+                                           g.world, g.rank, float(grid_length), op, axis, self._st())
+
+    def y_pass_op(self, src, dst, src_exchange, grid_length, axis):
+        g = self.geo
+        self.lib.gx_slab_fft_y_op(self._p(src), self._p(dst), g.n, self.dt, g.world, int(src_exchange), float(grid_length),
+                                  axis, self._st())
 
     @staticmethod
     def _p(t):
@@ -175,11 +254,12 @@ class CudaSlabOps:
 class SlabPipeline:
     """Sequencing of the slab path for one rank. All tensors are flat uint8 buffers of geo.slab_bytes."""
 
-    def __init__(self, geo, ops, comm, overlap=False):
+    def __init__(self, geo, ops, comm, overlap=False, lean=False):
         self.geo, self.ops, self.comm = geo, ops, comm
         g = geo
         self.bufA = ops.alloc(g.slab_bytes)
-        self.bufB = ops.alloc(g.slab_bytes)
+        # lean: peer-memory mode only (enable_push) -- the receive buffer of the all-to-all path is never allocated
+        self.bufB = ops.alloc(g.slab_bytes) if not lean else None
         # overlap: a second pair of buffers so that the all-to-all of one displacement component runs while the next
         # component's x-pass and the previous component's y/z-passes compute (5 slab-sized buffers in total with delta)
         self.overlap = bool(overlap) and g.world > 1 and hasattr(comm, "all_to_all_async")
@@ -188,6 +268,38 @@ class SlabPipeline:
         self.planes_local = ops.alloc(2 * g.planes_local_complex * g.itemsize)
         self.planes_all = ops.alloc(2 * g.planes_local_complex * g.itemsize * g.world)
         self.fn_local = self.fn_all = None
+        self.push = None
+
+    def enable_push(self, delta):
+        """Peer-memory mode (several GPUs of one node): the noise delivery and the inverse x-pass store straight into the
+        owners' buffers over NVLink, so an IC needs no all-to-all at all. `delta` and the two exchange buffers must come
+        from ops.alloc_shared. Returns False (and changes nothing) when ops / comm cannot do it (CPU stand-ins)."""
+        ops, comm, g = self.ops, self.comm, self.geo
+        if g.world == 1 or g.world > 8 or not (hasattr(ops, "x_inverse_mirror_push") and hasattr(comm, "peer_pointers")):
+            return False
+        ex0, ex1 = ops.alloc_shared(g.slab_bytes), ops.alloc_shared(g.slab_bytes)
+        self.push = {"delta": delta, "ex": (ex0, ex1), "delta_peers": comm.peer_pointers(delta),
+                     "ex_peers": (comm.peer_pointers(ex0), comm.peer_pointers(ex1))}
+        return True
+
+    def ic_push(self, seed, reverse, grid_length, spectrum, emit):
+        """One IC in peer-memory mode: parallel Fourier noise with the transfer folded in, then the shared-transform
+        Zeldovich schedule -- 2 x-passes (each one IS its FFT transpose), 3 y-passes, 3 z-passes, 3 barriers."""
+        ops, comm, p = self.ops, self.comm, self.push
+        delta, (ex0, ex1) = p["delta"], p["ex"]
+        comm.stream_barrier()                      # nobody reads delta / the exchange buffers of the previous IC any more
+        ops.noise_staged(delta, p["delta_peers"], seed, reverse, spectrum, grid_length, ex0)   # ex0 idle: staged draws
+        comm.stream_barrier()                      # every rank's modes have landed
+        self.gather_mirror_planes(delta)
+        ops.x_inverse_mirror_push(delta, self.planes_all, p["ex_peers"][0], grid_length, 1, 0)   # i k_x G -> owners
+        ops.x_inverse_mirror_push(delta, self.planes_all, p["ex_peers"][1], grid_length, 0, 0)   # G (mirrored) -> owners
+        comm.stream_barrier()
+        ops.y_pass(ex0, self.bufA, +1, True, False)
+        emit(0, self.bufA)
+        ops.y_pass_op(ex1, self.bufA, True, grid_length, 1)                                    # i k_y on load
+        emit(1, self.bufA)
+        ops.y_pass_op(ex1, self.bufA, True, grid_length, 2)                                    # i k_z on load
+        emit(2, self.bufA)
 
     # ---- general transforms (Field::toReal / toFourier on a slab) ---------------------------------------------
     def gather_mirror_planes(self, slab):
@@ -323,7 +435,6 @@ def unigrid_ic_slab(geo, ops, comm, seed, mode, reverse, fix_power, grid, spectr
     """One IC for this rank's x-slab. Either out_pos/out_vel are [3][particles] (component-major) device tensors that
     receive every particle, or `stager` streams them through bounded staging (and to pinned host memory if to_host)."""
     g = geo
-    pipe.draw_delta(delta, seed, mode, reverse, fix_power, float(grid.thisGridSize), spectrum)
     osz = np.dtype(out_dtype).itemsize
 
     def emit(axis, work):
@@ -333,7 +444,11 @@ def unigrid_ic_slab(geo, ops, comm, seed, mode, reverse, fix_power, grid, spectr
         ops.z_emit(work, axis, float(grid.cellSize), float(grid.offsetLower[axis]), float(grid.periodicDomainSize),
                    vel_ratio, 0, g.P, out_pos[axis * g.particles * osz:], out_vel[axis * g.particles * osz:], out_dtype)
 
-    pipe.zeldovich(delta, float(grid.thisGridSize), emit)
+    if pipe.push is not None and mode == L.NOISE_FOURIER_PARALLEL and not fix_power and pipe.push["delta"] is delta:
+        pipe.ic_push(seed, reverse, float(grid.thisGridSize), spectrum, emit)
+    else:
+        pipe.draw_delta(delta, seed, mode, reverse, fix_power, float(grid.thisGridSize), spectrum)
+        pipe.zeldovich(delta, float(grid.thisGridSize), emit)
     if stager is not None and to_host:
         stager.finish()
 
@@ -357,9 +472,16 @@ def bench_main(args, lib, world, rank, local_rank):
     comm = TorchComm()
     # the overlapped exchange needs 5 slab-sized buffers (+ staging): use it when they fit
     free_b, _ = torch.cuda.mem_get_info()
-    overlap = os.environ.get("GX_SLAB_OVERLAP", "1") != "0" and free_b > 5 * geo.slab_bytes + (12 << 30)
-    pipe = SlabPipeline(geo, ops, comm, overlap=overlap)
-    delta = ops.alloc(geo.slab_bytes)
+    push = os.environ.get("GX_SLAB_PUSH", "1") != "0" and world <= 8
+    if push:
+        # peer-memory mode: delta, two exchange buffers (stored into by the peers) and one work buffer
+        pipe = SlabPipeline(geo, ops, comm, overlap=False, lean=True)
+        delta = ops.alloc_shared(geo.slab_bytes)
+        push = pipe.enable_push(delta)
+    if not push:
+        overlap = os.environ.get("GX_SLAB_OVERLAP", "1") != "0" and free_b > 5 * geo.slab_bytes + (12 << 30)
+        pipe = SlabPipeline(geo, ops, comm, overlap=overlap)
+        delta = ops.alloc(geo.slab_bytes)
     osz = 4
     vel_ratio = cos.zeldovichVelocityToOffsetRatio(dtype)
     stager = EmitStager(ops, geo, out_dtype)   # particles leave through bounded staging, as in gx_unigrid_ic
@@ -435,7 +557,10 @@ def bench_main(args, lib, world, rank, local_rank):
         roof = None
         if dom:
             # class bytes per step on this rank; a class may be several launches per step
-            class_bytes = {"fft_cols_x": 3 * 2 * geo.slab_bytes, "fft_cols_y": 3 * 2 * geo.slab_bytes,
+            def n_launch(k):
+                return classes[k][0] / args.steps if k in classes else 0
+            class_bytes = {"fft_cols_x": n_launch("fft_cols_x") * 2 * geo.slab_bytes,
+                           "fft_cols_y": n_launch("fft_cols_y") * 2 * geo.slab_bytes,
                            "fft_rows_c2r": 3 * (geo.slab_bytes + 2 * osz * geo.particles)}
             cnt, tot = classes[dom]
             avg_ms = tot / cnt
@@ -450,20 +575,41 @@ def bench_main(args, lib, world, rank, local_rank):
                     "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                     "per_class_ms_per_step_rank0": {k: v[1] / args.steps for k, v in sorted(classes.items())},
                     "passes": passes, "share_of_step": tot / args.steps / ms}
-        a2a_bytes = 3 * geo.slab_bytes * (world - 1) // world
+        if pipe.push is not None:
+            # peer-memory mode: the two inverse x-passes store (world-1)/world of their output into the peers' exchange buffers
+            # (that IS the FFT transpose), the noise delivery the same share of the field; the x-pass is timed by CUDA events
+            # on this rank, so bytes / time is the NVLink rate its stores sustained
+            nx = classes["fft_cols_x"][0] / args.steps if "fft_cols_x" in classes else 0
+            push_bytes = geo.slab_bytes * (world - 1) // world
+            x_ms = classes["fft_cols_x"][1] / classes["fft_cols_x"][0] if nx else float("nan")
+            gbs = push_bytes / (x_ms * 1e-3) / 1e9
+            nvlink = {"mode": "peer stores fused into the inverse x-pass and the noise delivery (no all-to-all)",
+                      "x_pass_push_bytes_per_gpu_per_launch": push_bytes, "x_pass_launches_per_step": nx,
+                      "x_pass_ms_per_launch_rank0": x_ms, "GB/s_per_direction": gbs, "frac_of_900": gbs / 900.0,
+                      "frac_of_measured_770_peer_copy": gbs / 770.0,
+                      "noise_delivery_push_bytes_per_gpu_per_step": push_bytes,
+                      "bytes_sent_per_gpu_per_step": int(push_bytes * (nx + 1))}
+        else:
+            a2a_bytes = 3 * geo.slab_bytes * (world - 1) // world
+            nvlink = {"mode": "NCCL all_to_all_single per inverse transform",
+                      "all_to_all_bytes_sent_per_gpu_per_step": a2a_bytes}
         line = {"metric": "IC particles/sec (Zeldovich %d^3)" % n, "value": n3 / (ms * 1e-3), "unit": "particles/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": B.workload_name(n, "f64"), "output": "float32 pos+vel, component-major, x-slab per rank",
-                           "parallelism": "slab%d: ky-slabs in Fourier space, x-slabs in real space, one NCCL all-to-all "
-                                          "per inverse transform%s" % (world, ", overlapped with the neighbouring components' "
-                                                                              "passes" if pipe.overlap else ""),
+                           "parallelism": ("slab%d: ky-slabs in Fourier space, x-slabs in real space; peer-memory mode: noise "
+                                           "delivery and inverse x-passes store straight into the owners' buffers over NVLink "
+                                           "(CUDA IPC), 2 transposes per IC, 3 stream-ordered barriers" % world)
+                           if pipe.push is not None else
+                           "slab%d: ky-slabs in Fourier space, x-slabs in real space, one NCCL all-to-all "
+                           "per inverse transform%s" % (world, ", overlapped with the neighbouring components' "
+                                                               "passes" if pipe.overlap else ""),
                            "l2": "inputs larger than L2 (each slab %.2f GB)" % (geo.slab_bytes / 1e9)},
                 "clocks": clocks,
                 "e2e": {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": 3 * 8 * 213 * world,
                         "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches) * world,
-                "nvlink": {"all_to_all_bytes_sent_per_gpu_per_step": a2a_bytes},
+                "nvlink": nvlink,
                 "roofline": roof, "cpu_baseline": None}
         print(json.dumps(line))
     dist.barrier()

@@ -57,6 +57,12 @@ int gx_malloc(void **ptr, size_t bytes);
 int gx_free(void *ptr);
 int gx_memset_zero(void *ptr, size_t bytes, void *stream);
 int gx_host_alloc_pinned(void **ptr, size_t bytes);
+/* Peer memory between the ranks of one node (one process per GPU; no reference counterpart -- the reference is a single
+   process): CUDA IPC handle (64 bytes) of an allocation made by gx_malloc, opened by the other ranks as a device pointer
+   their kernels can store through (NVLink). Used by gx_slab_noise_staged and gx_slab_fft_x_mirror_push. */
+int gx_ipc_get_handle(void *ptr, void *handle_out_64_bytes);
+int gx_ipc_open(const void *handle_64_bytes, void **ptr_out);
+int gx_ipc_close(void *ptr);
 int gx_host_free_pinned(void *ptr);
 int gx_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int gx_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
@@ -239,6 +245,14 @@ size_t gx_slab_noise_fn_bytes(int n, int world);
 int gx_slab_noise_pass_a(void *fn_local, int n, int dtype, int world, int rank, unsigned long seed, void *stream);
 int gx_slab_noise_finish(void *slab, const void *fn_all, int n, int dtype, int world, int rank, unsigned long seed,
                          int reverse_order, void *stream);
+/* The same draw with every chunk generated on exactly ONE rank (shells split by generator work) and every mode stored
+   straight into its owner's slab through peer-mapped pointers (peer_slabs[r], from gx_ipc_open; peer_slabs[rank] == slab):
+   the delivery kernel is the routing step, over NVLink. spectrum != NULL folds Field::applyTransferFunction(0.5) and the
+   division by k^2 into the stores (as gx_unigrid_ic does). scratch: idle device memory for the staged draws (>= one
+   shell's worth; NULL: allocated for the call). Bracket with barriers across the ranks. Bit-identical to gx_noise_draw. */
+int gx_slab_noise_staged(void *slab, int n, int dtype, int world, int rank, unsigned long seed, int reverse_order,
+                         void *const *peer_slabs, const gx_spectrum *spectrum, double grid_length, void *scratch,
+                         size_t scratch_bytes, void *stream);
 int gx_slab_zero_dc(void *slab, int dtype, void *stream);
 int gx_slab_unit_variance(void *slab, int n, int dtype, int world, int rank, void *stream);
 /* Field::applyTransferFunction on the ky-slab; divide_k2 != 0 leaves delta_k / k^2 (see gx_unigrid_ic) */
@@ -251,6 +265,16 @@ int gx_slab_extract_planes(const void *slab, void *planes_local, int n, int dtyp
    delta_k/k^2), 2: times i k_axis / k^2 (zeldovich.hpp:170-176). out may not alias slab. */
 int gx_slab_fft_x_mirror(const void *slab, const void *planes_all, void *out, int n, int dtype, int world, int rank,
                          double grid_length, int op, int axis, void *stream);
+/* gx_slab_fft_x_mirror with the FFT transpose fused into the pass: every output element is stored straight into the
+   exchange buffer of the rank that owns its x plane (peer_exchange[r]: peer-mapped buffers of gx_slab_bytes each, laid out
+   [source rank][x_local][ky_local][kz]; peer_exchange[rank] is this rank's own) -- no send buffer, no all-to-all.
+   Bracket with barriers across the ranks; follow with gx_slab_fft_y / gx_slab_fft_y_op reading the exchange layout. */
+int gx_slab_fft_x_mirror_push(const void *slab, const void *planes_all, void *const *peer_exchange, int n, int dtype,
+                              int world, int rank, double grid_length, int op, int axis, void *stream);
+/* inverse y-pass with i k_axis (axis 1 or 2) applied on load: psi_y and psi_z from ONE x-transformed, exchanged
+   G = delta_k / k^2 (zeldovich.hpp:152-181; neither factor depends on kx) */
+int gx_slab_fft_y_op(const void *src, void *dst, int n, int dtype, int world, int src_exchange_layout, double grid_length,
+                     int axis, void *stream);
 int gx_slab_fft_x(void *slab, int n, int dtype, int world, int dir, int scale, void *stream); /* plain x-pass, in place; scale: / n^1.5 */
 /* y-pass over the P local x-planes; either side may be the exchange layout instead of [x_local][y][kz] */
 int gx_slab_fft_y(const void *src, void *dst, int n, int dtype, int world, int dir, int src_exchange_layout,

@@ -59,6 +59,17 @@ class LocalComm:
     def barrier(self):
         self.sh.barrier.wait()
 
+    def stream_barrier(self):
+        self.torch.cuda.synchronize()
+        self.sh.barrier.wait()
+
+    def peer_pointers(self, buf):
+        """In one process every rank's buffer is directly addressable: the product path gets these through CUDA IPC."""
+        self._publish(buf)
+        ptrs = [t.data_ptr() for t in self.sh.slots]
+        self.sh.barrier.wait()
+        return ptrs
+
 
 class LockedOps:
     """The library keeps per-process scratch state (noise workspace): emulated ranks take turns."""
@@ -182,3 +193,66 @@ def test_slab_noise_bit_exact_and_transform_roundtrip(world, n, mode, reverse):
     f2.toFourier()
     ref_back = f2.getDataVector()
     assert np.abs(back - ref_back).max() <= 1e-13 * np.abs(ref_back).max()
+
+
+@pytest.mark.parametrize("world,n,reverse", [(2, 32, 0), (4, 64, 0), (8, 64, 1), (8, 256, 0)])
+def test_slab_noise_staged_peer_delivery_bit_exact(world, n, reverse):
+    """gx_slab_noise_staged: every shell generated on one rank, every mode stored through the owner table into the slab of
+    the rank that holds its ky row -- identical to the single-GPU draw slot for slot."""
+    import torch
+    import genetic_b200 as gb
+    from genetic_b200 import lib as L, slab as SL
+    lib = L.load()
+    full = gb.Field(gb.Grid(50.0, n), fourier=True)
+    lib.gx_noise_draw(full.ptr, n, L.F64, 4321, L.NOISE_FOURIER_PARALLEL, reverse, None, None)
+    W = full.getDataVector()
+
+    def body(rank, comm):
+        geo = SL.SlabGeometry(n, world, rank, 8)
+        ops = LockedOps(SL.CudaSlabOps(geo, np.float64))
+        slab = ops.alloc_shared(geo.slab_bytes)
+        slab.fill_(0x7f)                        # stale contents: every slot must be written or zeroed by the draw
+        peers = comm.peer_pointers(slab)
+        comm.stream_barrier()
+        ops.noise_staged(slab, peers, 4321, reverse, None, 50.0, None)
+        comm.stream_barrier()
+        return slab.cpu().numpy().view(np.complex128).reshape(n, geo.P, geo.nc).copy()
+
+    res = _run_ranks(world, body)
+    noise = np.concatenate(res, axis=1)
+    assert np.array_equal(noise.view(np.float64), W.view(np.float64))
+
+
+@pytest.mark.parametrize("world,n", [(2, 32), (4, 64), (8, 64), (8, 256), (2, 512)])
+def test_slab_ic_peer_memory_mode_matches_single_gpu(world, n):
+    """Peer-memory mode (SlabPipeline.ic_push): staged noise with the transfer folded in, inverse x-passes that store
+    straight into the owners' exchange buffers, psi_y and psi_z from one exchanged x-transform."""
+    import torch
+    import genetic_b200 as gb
+    from genetic_b200 import lib as L, slab as SL
+    box, seed = 50.0 * n / 32, 8896131
+    cos = gb.CosmologicalParameters(0.279, 0.721, 0.817, 99)
+    pos1, vel1, _, _ = gb.generate_unigrid_ic(n, box, seed, cos, CAMB_FILE, out_dtype=np.float64)
+    spectrum = gb.CAMB(cos, CAMB_FILE, "all", np.float64)
+    grid = gb.Grid(box, n)
+    ratio = cos.zeldovichVelocityToOffsetRatio(np.float64)
+
+    def body(rank, comm):
+        geo = SL.SlabGeometry(n, world, rank, 8)
+        ops = LockedOps(SL.CudaSlabOps(geo, np.float64))
+        pipe = SL.SlabPipeline(geo, ops, comm, lean=True)
+        delta = ops.alloc_shared(geo.slab_bytes)
+        assert pipe.enable_push(delta)
+        out_pos, out_vel = ops.alloc(3 * geo.particles * 8), ops.alloc(3 * geo.particles * 8)
+        for _ in range(2):   # twice: the second IC reuses every buffer the peers stored into
+            SL.unigrid_ic_slab(geo, ops, comm, seed, L.NOISE_FOURIER_PARALLEL, 0, 0, grid, spectrum, ratio, np.float64, delta,
+                               pipe, out_pos, out_vel)
+        torch.cuda.synchronize()
+        return (out_pos.cpu().numpy().view(np.float64).reshape(3, -1), out_vel.cpu().numpy().view(np.float64).reshape(3, -1))
+
+    res = _run_ranks(world, body)
+    pos = np.concatenate([r[0] for r in res], axis=1).T
+    vel = np.concatenate([r[1] for r in res], axis=1).T
+    assert np.abs(vel - vel1).max() <= 1e-12 * np.abs(vel1).max()
+    d = np.abs(pos - pos1)
+    assert np.minimum(d, box - d).max() <= 1e-12 * box
