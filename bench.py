@@ -34,7 +34,8 @@ COSMO = dict(Om=0.3158, Ol=0.6842, s8=0.8117, z=200.0, ns=0.9660, hubble=0.6732)
 
 
 def box_for(n):
-    return 200.0 * n / 512.0  # 512^3 -> L=200, 2048^3 -> L=1000 (k_Nyq stays inside the CAMB table)
+    """512^3 -> L = 200, 2048^3 -> L = 1000, 4096^3 -> L = 2000 Mpc/h (k_Nyq stays inside the CAMB table)."""
+    return 1000.0 * n / 2048.0 if n >= 2048 else 200.0 * n / 512.0
 
 
 def workload_name(n, dtype):
@@ -117,6 +118,14 @@ def cpu_port_step(n, threads):
     return time.perf_counter() - t0
 
 
+def host_threads():
+    """Threads given to the reference: every host core of the box, set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def reference_binary_step(n, workdir=None, cufft=False):
     """One IC of the same workload through the reference ITSELF (oracle/_ref/genetIC: the unmodified sources compiled
     against the stand-in FFTW3/GSL/HDF5 headers of oracle/shims/): whole-process wall clock, including the tipsy file it
@@ -131,9 +140,10 @@ def reference_binary_step(n, workdir=None, cufft=False):
         pf = ("Om %(Om)r\nOl %(Ol)r\ns8 %(s8)r\nns %(ns)r\nhubble %(hubble)r\nz %(z)r\n" % COSMO +
               "camb %s\nrandom_seed %d\noutname bench\noutdir ./\noutformat tipsy\nbase_grid %r %d\ndone\n"
               % (os.path.basename(CAMB_FILE), SEED, box_for(n), n))
+        threads = host_threads()
         t0 = time.perf_counter()
-        oracle.run_ref(pf, d, [CAMB_FILE], cufft=cufft)
-        return time.perf_counter() - t0, os.cpu_count() or 1
+        oracle.run_ref(pf, d, [CAMB_FILE], cufft=cufft, threads=threads)
+        return time.perf_counter() - t0, threads
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -147,7 +157,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     n = args.cpu_n
     kind = "port"
     cufft = args.impl == "reference-cufft"   # the reference's own GPU path (USE_CUFFT=1: FFTs through cuFFTW, rest on the host)
@@ -163,8 +173,10 @@ def run_reference(args):
         return 0
     if first is not None:
         kind = "reference"
-        times = [reference_binary_step(n, cufft=cufft)[0] for _ in range(max(1, min(args.steps, 3)))]
-        sample = REF_SAMPLE % (n, threads) + " (the %d^3 workload does not fit the CPU time budget)" % args.n
+        times = [reference_binary_step(n, cufft=cufft)[0] for _ in range(max(1, min(args.steps, 2)))]
+        sample = REF_SAMPLE % (n, threads) + (" (OMP_NUM_THREADS=%d set for the subprocess; the %d^3 workload needs ~0.4 TB of "
+                                              "host memory in the reference's allocation pattern and hours of CPU time)"
+                                              % (threads, args.n))
         if cufft:
             sample = sample.replace("radix-2 OpenMP FFT instead of FFTW", "USE_CUFFT=1: FFTs through the toolkit's cuFFTW on the GPU")
     else:
@@ -178,6 +190,7 @@ def run_reference(args):
     v = n ** 3 / t
     line = {"impl": args.impl, "metric": "IC particles/sec (Zeldovich %d^3)" % args.n, "value": v,
             "unit": "particles/s", "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
+            "sample_n": n, "omp_num_threads": threads,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.n, "f64"), "sample": sample},
             "cpu_baseline": {"value": v, "unit": "particles/s", "cores": threads, "kind": kind, "sample": sample},
@@ -187,6 +200,61 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def particle_checksum(lib, torch, step, dist=None):
+    """One extra IC (outside every timed region) with the emit hook on: per axis sum(pos), sum(vel), sum(vel^2) over all
+    particles, summed over the ranks. The N-rank and the 1-rank run of the same workload must agree to rounding."""
+    acc = torch.zeros(9, dtype=torch.float64, device="cuda")
+    lib.gx_emit_checksum(C.c_void_p(acc.data_ptr()))
+    try:
+        step()
+        torch.cuda.synchronize()
+    finally:
+        lib.gx_emit_checksum(None)
+    if dist is not None:
+        dist.all_reduce(acc)
+    a = acc.cpu().numpy().reshape(3, 3)
+    return {"pos_sum": [float("%.13e" % v) for v in a[:, 0]], "vel_sum": [float("%.13e" % v) for v in a[:, 1]],
+            "vel_sumsq": [float("%.13e" % v) for v in a[:, 2]],
+            "note": "per axis, double accumulation over every emitted particle of one extra IC; compare across n_gpus"}
+
+
+def cufft_crosscheck(lib, torch, n, dt, planes=8):
+    """The three hand-written pass kinds at the bench's line length against cuFFT (torch.fft on the same device) on a thin
+    slab of `planes` planes of random data, outside the timed loop (the north star allows cuFFT for exactly this)."""
+    if dt != 1:   # F64 only: the comparison is at 1e-13
+        cdt, rdt, tol = torch.complex64, torch.float32, 2e-5
+    else:
+        cdt, rdt, tol = torch.complex128, torch.float64, 1e-12
+    nc, P = n // 2 + 1, min(planes, n)
+    world = n // P
+    g = torch.Generator(device="cuda").manual_seed(7)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max())
+
+    out = {"n": n, "planes": P, "tolerance": tol}
+    # y-pass: x-slab [P][n][nc], inverse along axis 1
+    x = torch.randn(P, n, nc, 2, dtype=rdt, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    lib.gx_slab_fft_y(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), n, dt, world, 1, 0, 0, st)
+    ref = torch.fft.ifft(torch.view_as_complex(x), dim=1, norm="forward")
+    out["y_pass_rel_err"] = rel(torch.view_as_complex(y), ref)
+    # z-pass: c2r rows scaled by n^-1.5, in place, padded pitch n + 2
+    z = x.clone()
+    lib.gx_slab_fft_z_c2r(C.c_void_p(z.data_ptr()), n, dt, world, st)
+    ref = torch.fft.irfft(torch.view_as_complex(x), n=n, dim=2, norm="forward") / float(n) ** 1.5
+    out["z_pass_rel_err"] = rel(z.view(P, n, n + 2)[:, :, :n], ref)
+    # x-pass: ky-slab [n][P][nc], inverse along axis 0, in place, unscaled
+    w = torch.randn(n, P, nc, 2, dtype=rdt, device="cuda", generator=g)
+    ref = torch.fft.ifft(torch.view_as_complex(w), dim=0, norm="forward")
+    lib.gx_slab_fft_x(C.c_void_p(w.data_ptr()), n, dt, world, 1, 0, st)
+    out["x_pass_rel_err"] = rel(torch.view_as_complex(w), ref)
+    torch.cuda.synchronize()
+    out["ok"] = all(out[k] < tol for k in ("x_pass_rel_err", "y_pass_rel_err", "z_pass_rel_err"))
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -293,6 +361,8 @@ def run_ours(args):
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
     tab_bytes = 3 * 8 * 213
+    checksum = particle_checksum(lib, torch, device_step)
+    crosscheck = cufft_crosscheck(lib, torch, n, dt)
 
     # roofline of the dominant kernel class
     peaks = {}
@@ -310,29 +380,40 @@ def run_ours(args):
         return classes[k][0] / args.steps if k in classes else 0
 
     # (a column pass is one launch: the shared-transform schedule runs 3 x-passes and 2 y-passes per IC)
+    n_gauss = 8 * sum(3 * ks * ks for ks in range(1, n // 2))   # 24 ks^2 gaussians per shell
     class_bytes = {"fft_cols_x": n_launch("fft_cols_x") * 2 * fbytes, "fft_cols_y": n_launch("fft_cols_y") * 2 * fbytes,
                    "fft_rows_c2r": 3 * (fbytes + 2 * osz * n3), "apply_transfer": 2 * fbytes,
-                   "rng_pass_b": fbytes}
+                   "rng_pass_b": fbytes,
+                   # staged noise: gen writes 4 bytes per accepted draw (it is instruction-bound: ~1250 integer instructions
+                   # of ranlxs2 per 24 raw outputs); deliver reads them once and writes every mode of the field once
+                   "rng_gen": 4 * n_gauss, "rng_deliver": 4 * n_gauss + fbytes}
     passes = {}
     for k, (cnt, tot) in classes.items():
         if k in class_bytes and tot > 0:
             gbs = class_bytes[k] / (tot / args.steps * 1e-3) / 1e9
             passes[k] = {"GB/s": gbs, "frac": gbs / peak, "ms_per_step": tot / args.steps,
                          "launches_per_step": cnt / args.steps}
-    fft_classes = {k: v for k, v in classes.items() if k.startswith("fft_")}
-    dom = max(fft_classes, key=lambda k: fft_classes[k][1]) if fft_classes else None
+    # the dominant kernel class: the largest share of the step among ALL classes (noise included)
+    cand = {k: v for k, v in classes.items() if k in class_bytes and class_bytes[k] > 0}
+    dom = max(cand, key=lambda k: cand[k][1]) if cand else None
     roof = None
     if dom:
         cnt, tot = classes[dom]
         avg_ms = tot / cnt
         bytes_per_launch = class_bytes[dom] * args.steps / cnt
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        traffic = None  # dram bytes of the same kernel from the ncu --set full capture (profiles/), per launch
+        # dram bytes per launch of the same kernel from ncu (profiles/r2_ncu_dram_2048.json, written by
+        # tools/ncu_dram_summary.py from a dram__bytes_{read,write}.sum pass over this very command), if committed
+        traffic, traffic_note = None, "no ncu capture committed for this kernel at this size"
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_dram_%d.json" % n)))
+            if dom in tr:
+                traffic = tr[dom]["dram_bytes_per_launch"]
+                traffic_note = tr[dom].get("note", "")
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "ncu --set full of this kernel at 1024^3: dram read+write = 1.00 x algorithmic bytes "
-                                "(profiles/r1s8_ncu_full_1024_summary.txt); at 2048^3 ncu would have to save and restore "
-                                "~150 GB of device memory per replay pass, so no capture exists at the bench size",
+                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "per_class_ms_per_step": {k: v[1] / args.steps for k, v in sorted(classes.items())},
@@ -356,12 +437,15 @@ def run_ours(args):
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, "f64"), "output": "float32 pos+vel, component-major",
-                       "l2": "inputs larger than L2 (each field %.2f GB)" % (fbytes / 1e9)},
+                       "l2": "inputs larger than L2 (each field %.2f GB)" % (fbytes / 1e9),
+                       "e2e_host_buffers": "full component-major arrays" if cap == n3 else
+                       "pinned RING of %d particles per component (6 x n^3 x 4 bytes = %.0f GB does not fit the pinned "
+                       "budget): every byte is copied, the IC is not retained" % (cap, 6 * n3 * osz / 1e9)},
             "clocks": clocks,
             "e2e": None if args.no_e2e else {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": tab_bytes,
                                              "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "cpu_baseline": cpu, "checksum": checksum, "cufft_crosscheck": crosscheck}
     print(json.dumps(line))
     return 0
 
@@ -373,7 +457,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cufft"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "2048")))
-    ap.add_argument("--cpu-n", type=int, default=256)
+    ap.add_argument("--cpu-n", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -201,13 +201,41 @@ int zeldovich_z_real(void *work, int n, int dtype, long row0, long nrows, cudaSt
   return fail("bad dtype");
 }
 
+// ---- verification hook: sums over everything the emit writes ----------------------------------------------------------
+// bench.py prints them (one extra IC outside the timed loop) so that the particles of an N-rank run can be compared with the
+// 1-rank run of the same workload: per axis sum(pos), sum(vel), sum(vel^2), accumulated in double.
+static double *g_emit_checksum = nullptr;  // device, 9 doubles: [axis][pos_sum, vel_sum, vel_sumsq]
+
+template <typename O> __global__ void emit_checksum_kernel(const O *pos, const O *vel, long long count, double *acc) {
+  double sp = 0, sv = 0, sq = 0;
+  for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < count; i += (long long) gridDim.x * blockDim.x) {
+    if (pos) sp += (double) pos[i];
+    if (vel) { const double v = (double) vel[i]; sv += v; sq += v * v; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sp += __shfl_down_sync(0xffffffffu, sp, o);
+    sv += __shfl_down_sync(0xffffffffu, sv, o);
+    sq += __shfl_down_sync(0xffffffffu, sq, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(acc, sp); atomicAdd(acc + 1, sv); atomicAdd(acc + 2, sq); }
+}
+
 int zeldovich_z_emit(const void *work, int n, int dtype, int axis, const EmitGeo &geo, long row0, long nrows,
                      void *out_pos, void *out_vel, int out_dtype, cudaStream_t st) {
-  if (dtype == GX_F64 && out_dtype == GX_F32) return z_emit_t<double, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
-  if (dtype == GX_F64 && out_dtype == GX_F64) return z_emit_t<double, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
-  if (dtype == GX_F32 && out_dtype == GX_F32) return z_emit_t<float, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
-  if (dtype == GX_F32 && out_dtype == GX_F64) return z_emit_t<float, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
-  return fail("bad dtype");
+  int rc;
+  if (dtype == GX_F64 && out_dtype == GX_F32) rc = z_emit_t<double, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  else if (dtype == GX_F64 && out_dtype == GX_F64) rc = z_emit_t<double, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  else if (dtype == GX_F32 && out_dtype == GX_F32) rc = z_emit_t<float, float>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  else if (dtype == GX_F32 && out_dtype == GX_F64) rc = z_emit_t<float, double>(work, n, axis, geo, row0, nrows, out_pos, out_vel, st);
+  else return fail("bad dtype");
+  if (rc || !g_emit_checksum) return rc;
+  const long long count = (long long) nrows * n;
+  if (out_dtype == GX_F32)
+    emit_checksum_kernel<float><<<148 * 8, 256, 0, st>>>((const float *) out_pos, (const float *) out_vel, count, g_emit_checksum + 3 * axis);
+  else
+    emit_checksum_kernel<double><<<148 * 8, 256, 0, st>>>((const double *) out_pos, (const double *) out_vel, count, g_emit_checksum + 3 * axis);
+  GX_LAUNCH_CHECK();
+  return 0;
 }
 
 int zeldovich_shared_x(void *g, int n, int dtype, cudaStream_t st) {
@@ -235,4 +263,11 @@ extern "C" int gx_zeldovich_offset(const void *delta_k, void *psi, int n, int dt
   int rc = gx::zeldovich_xy(delta_k, psi, n, dtype, grid_length, axis, 0, st);
   if (rc) return rc;
   return gx::zeldovich_z_real(psi, n, dtype, 0, (long) n * n, st);
+}
+
+// device_accum9 != NULL: every particle emit that follows (gx_unigrid_ic, gx_slab_z_emit) also adds sum(pos), sum(vel),
+// sum(vel^2) of what it wrote to device_accum9[3 * axis + 0..2] (zero it first); NULL switches the hook off.
+extern "C" int gx_emit_checksum(double *device_accum9) {
+  gx::g_emit_checksum = device_accum9;
+  return 0;
 }

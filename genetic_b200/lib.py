@@ -98,6 +98,7 @@ PROTOTYPES = {
     "gx_slab_noise_finish": (ci, [vp, vp, ci, ci, ci, ci, cul, ci, vp]),
     "gx_slab_noise_staged": (ci, [vp, ci, ci, ci, ci, cul, ci, P(vp), vp, cd, vp, csz, vp]),
     "gx_slab_zero_dc": (ci, [vp, ci, vp]),
+    "gx_emit_checksum": (ci, [vp]),
     "gx_slab_unit_variance": (ci, [vp, ci, ci, ci, ci, vp]),
     "gx_slab_apply_transfer": (ci, [vp, ci, ci, ci, ci, cd, vp, cd, ci, vp]),
     "gx_slab_extract_planes": (ci, [vp, vp, ci, ci, ci, vp]),

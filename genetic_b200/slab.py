@@ -545,6 +545,7 @@ def bench_main(args, lib, world, rank, local_rank):
             nm, cnt, tot = line.split()
             classes[nm] = (int(cnt), float(tot))
     n3 = n ** 3
+    checksum = B.particle_checksum(lib, torch, device_step, dist)
     if rank == 0:
         peaks = {}
         try:
@@ -552,16 +553,18 @@ def bench_main(args, lib, world, rank, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        fft_classes = {k: v for k, v in classes.items() if k.startswith("fft_")}
-        dom = max(fft_classes, key=lambda k: fft_classes[k][1]) if fft_classes else None
+        def n_launch(k):
+            return classes[k][0] / args.steps if k in classes else 0
+        # class bytes per step on this rank; a class may be several launches per step
+        n_gauss_rank = 8 * sum(3 * ks * ks for ks in range(1, n // 2)) // world
+        class_bytes = {"fft_cols_x": n_launch("fft_cols_x") * 2 * geo.slab_bytes,
+                       "fft_cols_y": n_launch("fft_cols_y") * 2 * geo.slab_bytes,
+                       "fft_rows_c2r": 3 * (geo.slab_bytes + 2 * osz * geo.particles),
+                       "rng_gen": 4 * n_gauss_rank, "rng_deliver": 4 * n_gauss_rank + geo.slab_bytes}
+        cand = {k: v for k, v in classes.items() if k in class_bytes and class_bytes[k] > 0}
+        dom = max(cand, key=lambda k: cand[k][1]) if cand else None
         roof = None
         if dom:
-            # class bytes per step on this rank; a class may be several launches per step
-            def n_launch(k):
-                return classes[k][0] / args.steps if k in classes else 0
-            class_bytes = {"fft_cols_x": n_launch("fft_cols_x") * 2 * geo.slab_bytes,
-                           "fft_cols_y": n_launch("fft_cols_y") * 2 * geo.slab_bytes,
-                           "fft_rows_c2r": 3 * (geo.slab_bytes + 2 * osz * geo.particles)}
             cnt, tot = classes[dom]
             avg_ms = tot / cnt
             per_launch = class_bytes[dom] * args.steps / cnt
@@ -610,7 +613,7 @@ def bench_main(args, lib, world, rank, local_rank):
                         "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches) * world,
                 "nvlink": nvlink,
-                "roofline": roof, "cpu_baseline": None}
+                "roofline": roof, "cpu_baseline": None, "checksum": checksum}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

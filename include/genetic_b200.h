@@ -254,6 +254,11 @@ int gx_slab_noise_staged(void *slab, int n, int dtype, int world, int rank, unsi
                          void *const *peer_slabs, const gx_spectrum *spectrum, double grid_length, void *scratch,
                          size_t scratch_bytes, void *stream);
 int gx_slab_zero_dc(void *slab, int dtype, void *stream);
+/* Verification hook (no reference counterpart): device_accum9 != NULL makes every particle emit that follows
+   (gx_unigrid_ic, gx_slab_z_emit) add sum(pos), sum(vel), sum(vel^2) of what it wrote to device_accum9[3*axis + 0..2]
+   (9 doubles on the device, zeroed by the caller); NULL switches it off. bench.py prints the sums of one extra IC outside
+   the timed loop, so an N-rank run can be compared with the 1-rank run of the same workload. */
+int gx_emit_checksum(double *device_accum9);
 int gx_slab_unit_variance(void *slab, int n, int dtype, int world, int rank, void *stream);
 /* Field::applyTransferFunction on the ky-slab; divide_k2 != 0 leaves delta_k / k^2 (see gx_unigrid_ic) */
 int gx_slab_apply_transfer(void *slab, int n, int dtype, int world, int rank, double grid_length, const gx_spectrum *s,

@@ -65,7 +65,7 @@ def ref_binary(cufft=False):
     return exe if os.access(exe, os.X_OK) else None
 
 
-def run_ref(paramfile_text, workdir, files=(), timeout=3600, args=(), cufft=False):
+def run_ref(paramfile_text, workdir, files=(), timeout=3600, args=(), cufft=False, threads=None):
     """Runs the compiled reference on a paramfile written into `workdir` (extra input files are copied next to it).
     Returns its combined stdout/stderr. Raises if the binary is missing or exits non-zero."""
     import shutil
@@ -77,7 +77,11 @@ def run_ref(paramfile_text, workdir, files=(), timeout=3600, args=(), cufft=Fals
         shutil.copy(f, os.path.join(workdir, os.path.basename(f)))
     with open(os.path.join(workdir, "paramfile.txt"), "w") as fh:
         fh.write(paramfile_text)
-    r = subprocess.run([exe, "paramfile.txt"] + list(args), cwd=workdir, capture_output=True, text=True, timeout=timeout)
+    env = dict(os.environ)
+    if threads is not None:  # torchrun exports OMP_NUM_THREADS=1: the reference's thread count is set, not inherited
+        env["OMP_NUM_THREADS"] = str(int(threads))
+    r = subprocess.run([exe, "paramfile.txt"] + list(args), cwd=workdir, capture_output=True, text=True, timeout=timeout,
+                       env=env)
     if r.returncode != 0:
         raise RuntimeError("reference binary failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
     return r.stdout + r.stderr
