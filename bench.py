@@ -457,6 +457,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cufft"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("GX_BENCH_N", "2048")))
+    ap.add_argument("--dtype", default=os.environ.get("GX_BENCH_DTYPE", "f64"), choices=["f64", "f32"],
+                    help="field precision: f64 (default) or f32 = the reference's -f build (BASELINE config 5: 4096^3 on 8 GPUs)")
     ap.add_argument("--cpu-n", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

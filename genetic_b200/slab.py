@@ -270,7 +270,7 @@ class SlabPipeline:
         self.fn_local = self.fn_all = None
         self.push = None
 
-    def enable_push(self, delta):
+    def enable_push(self, delta, overlap=False):
         """Peer-memory mode (several GPUs of one node): the noise delivery and the inverse x-pass store straight into the
         owners' buffers over NVLink, so an IC needs no all-to-all at all. `delta` and the two exchange buffers must come
         from ops.alloc_shared. Returns False (and changes nothing) when ops / comm cannot do it (CPU stand-ins)."""
@@ -279,8 +279,14 @@ class SlabPipeline:
             return False
         ex0, ex1 = ops.alloc_shared(g.slab_bytes), ops.alloc_shared(g.slab_bytes)
         self.push = {"delta": delta, "ex": (ex0, ex1), "delta_peers": comm.peer_pointers(delta),
-                     "ex_peers": (comm.peer_pointers(ex0), comm.peer_pointers(ex1))}
+                     "ex_peers": (comm.peer_pointers(ex0), comm.peer_pointers(ex1)),
+                     "overlap": bool(overlap) and hasattr(ops, "torch")}
         return True
+
+    def _aux_stream(self):
+        if getattr(self, "_aux", None) is None:
+            self._aux = self.ops.torch.cuda.Stream()
+        return self._aux
 
     def ic_push(self, seed, reverse, grid_length, spectrum, emit):
         """One IC in peer-memory mode: parallel Fourier noise with the transfer folded in, then the shared-transform
@@ -292,10 +298,28 @@ class SlabPipeline:
         comm.stream_barrier()                      # every rank's modes have landed
         self.gather_mirror_planes(delta)
         ops.x_inverse_mirror_push(delta, self.planes_all, p["ex_peers"][0], grid_length, 1, 0)   # i k_x G -> owners
-        ops.x_inverse_mirror_push(delta, self.planes_all, p["ex_peers"][1], grid_length, 0, 0)   # G (mirrored) -> owners
-        comm.stream_barrier()
-        ops.y_pass(ex0, self.bufA, +1, True, False)
-        emit(0, self.bufA)
+        aux = self._aux_stream() if p.get("overlap") else None
+        if aux is None:
+            ops.x_inverse_mirror_push(delta, self.planes_all, p["ex_peers"][1], grid_length, 0, 0)   # G (mirrored) -> owners
+            comm.stream_barrier()
+            ops.y_pass(ex0, self.bufA, +1, True, False)
+            emit(0, self.bufA)
+        else:
+            # the second push is NVLink-bound: it runs on a side stream under psi_x's y- and z-passes (HBM-bound)
+            torch = ops.torch
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            aux.wait_event(ev)
+            with torch.cuda.stream(aux):
+                ops.x_inverse_mirror_push(delta, self.planes_all, p["ex_peers"][1], grid_length, 0, 0)
+                ev2 = torch.cuda.Event()
+                ev2.record(aux)
+            comm.stream_barrier()                  # exchange buffer 0 is complete on every rank
+            ops.y_pass(ex0, self.bufA, +1, True, False)
+            emit(0, self.bufA)
+            main.wait_event(ev2)
+            comm.stream_barrier()                  # exchange buffer 1 is complete on every rank
         ops.y_pass_op(ex1, self.bufA, True, grid_length, 1)                                    # i k_y on load
         emit(1, self.bufA)
         ops.y_pass_op(ex1, self.bufA, True, grid_length, 2)                                    # i k_z on load
@@ -461,13 +485,15 @@ def bench_main(args, lib, world, rank, local_rank):
     import bench as B
 
     n = args.n
-    dtype, out_dtype = np.float64, np.float32
+    dtype = np.float32 if getattr(args, "dtype", "f64") == "f32" else np.float64   # f32: the reference's -f build (config 5)
+    out_dtype = np.float32
+    dname = "f32" if dtype == np.float32 else "f64"
     box = B.box_for(n)
     cos = gb.CosmologicalParameters(B.COSMO["Om"], B.COSMO["Ol"], B.COSMO["s8"], B.COSMO["z"], ns=B.COSMO["ns"],
                                     hubble=B.COSMO["hubble"])
     grid = gb.Grid(box, n, dtype=dtype)
     spectrum = gb.CAMB(cos, B.CAMB_FILE, "all", dtype)
-    geo = SlabGeometry(n, world, rank, 8)
+    geo = SlabGeometry(n, world, rank, np.dtype(dtype).itemsize)
     ops = CudaSlabOps(geo, dtype)
     comm = TorchComm()
     # the overlapped exchange needs 5 slab-sized buffers (+ staging): use it when they fit
@@ -477,7 +503,7 @@ def bench_main(args, lib, world, rank, local_rank):
         # peer-memory mode: delta, two exchange buffers (stored into by the peers) and one work buffer
         pipe = SlabPipeline(geo, ops, comm, overlap=False, lean=True)
         delta = ops.alloc_shared(geo.slab_bytes)
-        push = pipe.enable_push(delta)
+        push = pipe.enable_push(delta, overlap=os.environ.get("GX_SLAB_PUSH_OVERLAP", "1") != "0")
     if not push:
         overlap = os.environ.get("GX_SLAB_OVERLAP", "1") != "0" and free_b > 5 * geo.slab_bytes + (12 << 30)
         pipe = SlabPipeline(geo, ops, comm, overlap=overlap)
@@ -598,8 +624,8 @@ def bench_main(args, lib, world, rank, local_rank):
                       "all_to_all_bytes_sent_per_gpu_per_step": a2a_bytes}
         line = {"metric": "IC particles/sec (Zeldovich %d^3)" % n, "value": n3 / (ms * 1e-3), "unit": "particles/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": B.workload_name(n, "f64"), "output": "float32 pos+vel, component-major, x-slab per rank",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dname, "data": "synthetic",
+                "config": {"workload": B.workload_name(n, dname), "output": "float32 pos+vel, component-major, x-slab per rank",
                            "parallelism": ("slab%d: ky-slabs in Fourier space, x-slabs in real space; peer-memory mode: noise "
                                            "delivery and inverse x-passes store straight into the owners' buffers over NVLink "
                                            "(CUDA IPC), 2 transposes per IC, 3 stream-ordered barriers" % world)
