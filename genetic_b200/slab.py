@@ -503,7 +503,7 @@ def bench_main(args, lib, world, rank, local_rank):
         # peer-memory mode: delta, two exchange buffers (stored into by the peers) and one work buffer
         pipe = SlabPipeline(geo, ops, comm, overlap=False, lean=True)
         delta = ops.alloc_shared(geo.slab_bytes)
-        push = pipe.enable_push(delta, overlap=os.environ.get("GX_SLAB_PUSH_OVERLAP", "1") != "0")
+        push = pipe.enable_push(delta, overlap=os.environ.get("GX_SLAB_PUSH_OVERLAP", "0") == "1")
     if not push:
         overlap = os.environ.get("GX_SLAB_OVERLAP", "1") != "0" and free_b > 5 * geo.slab_bytes + (12 << 30)
         pipe = SlabPipeline(geo, ops, comm, overlap=overlap)
@@ -553,14 +553,16 @@ def bench_main(args, lib, world, rank, local_rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
-    for _ in range(min(args.warmup, 2)):
+    # (config 5 moves 1.65 TB to the host per IC: GX_BENCH_E2E_STEPS / GX_BENCH_E2E_WARMUP bound that leg)
+    e2e_steps = int(os.environ.get("GX_BENCH_E2E_STEPS", args.steps))
+    for _ in range(int(os.environ.get("GX_BENCH_E2E_WARMUP", min(args.warmup, 2)))):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_local = (time.perf_counter() - t0) / args.steps
+    e2e_local = (time.perf_counter() - t0) / max(e2e_steps, 1)
     t = torch.tensor([e2e_local], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
@@ -636,7 +638,7 @@ def bench_main(args, lib, world, rank, local_rank):
                            "l2": "inputs larger than L2 (each slab %.2f GB)" % (geo.slab_bytes / 1e9)},
                 "clocks": clocks,
                 "e2e": {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": 3 * 8 * 213 * world,
-                        "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},
+                        "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
                 "gpu_launches": int(launches) * world,
                 "nvlink": nvlink,
                 "roofline": roof, "cpu_baseline": None, "checksum": checksum}
