@@ -466,6 +466,64 @@ fft_rows_c2r_kernel(const T *data, long row0, long nrows, const cplx<T> *__restr
   B::run(v, t, line, twM, [&](int k, C val) { if (active) store.put(ctx, k, val); });
 }
 
+// The same pass with its last stage decimation in time (fft_core.cuh DitRows): thread t emits k = t + (M/16) u, so the lanes
+// of a warp store CONSECUTIVE results -- for the fused particle emit 256 contiguous bytes of pos and of vel per instruction
+// instead of 32 scattered 8-byte stores.
+template <typename T, int N> struct RowsDitCfg {
+  static constexpr int M = N / 2;
+  using D = DitRows<T, M, 1>;
+  static constexpr int P = D::P;
+  static constexpr int pitch = (M + 16 + 1 + 1) & ~1;  // raw row (M + 1 entries) and the 16 sub-transform rows (M + 16)
+  static constexpr size_t per_row = (size_t) pitch * sizeof(cplx<T>);
+  static constexpr int LR = (128 / P) > 0 ? (128 / P) : 1;
+  static constexpr int threads = LR * P;
+  static constexpr int MINB = (threads <= 128 && sizeof(T) == 8) ? 5 : (threads <= 128 ? 6 : 1);
+  static constexpr size_t smem = (size_t) LR * per_row;
+};
+
+template <typename T, int N, class Store>
+__global__ void __launch_bounds__(RowsDitCfg<T, N>::threads, RowsDitCfg<T, N>::MINB)
+fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__restrict__ twM,
+                        const cplx<T> *__restrict__ twN, Store store) {
+  using C = cplx<T>;
+  using Cfg = RowsDitCfg<T, N>;
+  using D = typename Cfg::D;
+  constexpr int M = Cfg::M, P = Cfg::P;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C *smem = reinterpret_cast<C *>(smem_raw);
+  const int l = threadIdx.x / P, t = threadIdx.x % P;
+  const long row = row0 + (long) blockIdx.x * Cfg::LR + l;
+  const bool active = row < row0 + nrows;
+  const C *rowp = reinterpret_cast<const C *>(data + row * (long) (N + 2));
+  C *line = smem + (size_t) l * Cfg::pitch;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) line[t + i * P] = active ? rowp[t + i * P] : mk<T>(0, 0);
+  if (t == 0) line[M] = active ? rowp[M] : mk<T>(0, 0);
+  __syncthreads();
+  C v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int k = D::input_index(t, e);
+    C xk = line[k];
+    C xm = cconj(line[M - k]);
+    if (k == 0) { xk.y = 0; xm.y = 0; }
+    const C s = cadd(xk, xm);
+    const C d = csub(xk, xm);
+    const C w = cconj(__ldg(twN + k));
+    const C wd = cmul(w, d);
+    v[e] = mk<T>(s.x - wd.y, s.y + wd.x);  // s + i*wd
+  }
+  __syncthreads();  // everyone has consumed the inputs before the buffer is reused for the stage exchanges
+  D::stage_a(v, t, line, twM);
+  __syncthreads();
+  if constexpr (D::RB > 1) {
+    D::stage_b(t, line);
+    __syncthreads();
+  }
+  const auto ctx = store.begin(active ? row : row0);
+  D::stage_final(t, line, twM, [&](int k, C val) { if (active) store.put(ctx, k, val); });
+}
+
 // (Also measured and dropped, profiles/r1s5_bench2048_rows_{single,pipelined}.json: a persistent form of this kernel with
 // the next group of rows prefetched by cp.async into a second shared-memory buffer -- 3 CTAs of 128 threads per SM instead
 // of 5 -- took 203 ms per step at 2048^3 against 174 ms: the pass is bound by how many warps an SM has to cover the
@@ -486,8 +544,29 @@ template <typename T, int N> int launch_rows_r2c(T *data, long nrows, cudaStream
 }
 
 // rows [row0, row0 + nrows) of `data` (pitch N+2 reals) -> store functor
+inline bool rows_dit_enabled() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("GX_ROWS_DIT"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 template <typename T, int N, class Store>
 int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStream_t st) {
+  if constexpr (N >= 512 && N <= 4096) {
+    if (rows_dit_enabled()) {
+      using Cfg = RowsDitCfg<T, N>;
+      auto kern = fft_rows_c2r_dit_kernel<T, N, Store>;
+      if (Cfg::smem > 48 * 1024)
+        GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
+      const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
+      if (grid <= 0) return 0;
+      GX_TIMED("fft_rows_c2r", st);
+      kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store);
+      count_launch();
+      GX_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   using Cfg = RowsCfg<T, N>;
   auto kern = fft_rows_c2r_kernel<T, N, Store>;
   if (Cfg::smem > 48 * 1024)

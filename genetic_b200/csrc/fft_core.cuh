@@ -328,5 +328,93 @@ template <typename T, int NC, int DIR, int LS = 0, int SEL = 0> struct BlockFFT 
 #endif
 };
 
+// ---- row transform with its outputs in NATURAL order ----------------------------------------------------------------------
+// BlockFFT is decimation in frequency: its last stage leaves frequency freq_of_pos(p) at position p, so the lanes of a warp
+// emit digit-reversed indices and the c2r pass, which stores straight from that stage, issues 8..16-byte stores to 32
+// different sectors per instruction (ncu, z-pass at 1024^3: L1 data pipe 89 %, more than half of it those stores). Here the
+// LAST stage is decimation in time instead:
+//     X[k1 + M' u] = sum_r W_16^(r u) * ( W_M^(r k1) * Y_r[k1] ),   M' = M / 16,  u = 0..15,
+// where Y_r is the M'-point transform of the inputs n = r (mod 16). Thread t owns k1 = t, so for every u the lanes of a warp
+// emit consecutive k: 256 contiguous bytes per store instruction. The 16 sub-transforms are decimation in frequency in one
+// or two stages (radices RA, RB; RB == 1: one stage), in place in shared memory:
+//     stage A   butterfly (r, j):  a_q = sum_i x[r + 16 (j + RB i)] W_RA^(i q),  a_q *= W_M'^(j q)   -> S[r][q + RA j]
+//     stage B   butterfly (r, q):  Y_r[q + RA p] = sum_j S[r][q + RA j] W_RB^(j p)                    -> S[r][q + RA p]
+//     final     thread k1: the formula above, reading S[r][k1] for r = 0..15.
+// S[r][.] has pitch M' + 1 elements, which keeps the 16 sub-transforms of a butterfly column on different banks.
+template <typename T, int M, int DIR> struct DitRows {
+  using C = cplx<T>;
+  static_assert(M >= 256 && M <= 2048, "DitRows: 256 <= M <= 2048");
+  static constexpr int MP = M / 16;                                  // length of a sub-transform, threads per row
+  static constexpr int RA = (MP == 16 || MP == 128) ? 16 : 8;
+  static constexpr int RB = MP / RA;                                 // 1, 4, 8, 8
+  static constexpr int P = MP;
+  static constexpr int E = 16;
+  static constexpr int NA = 16 / RA;                                 // stage-A butterflies per thread
+  static constexpr int NB = (RB > 1) ? 16 / RB : 0;                  // stage-B butterflies per thread
+  static constexpr int PITCH = MP + 1;
+  static constexpr int smem_elems = 16 * PITCH;
+
+  // input n (0 <= n < M) that thread t holds as element e = c * RA + i of its 16 (stage-A butterfly c, leg i)
+  GX_HD static int input_index(int t, int e) {
+    const int c = e / RA, i = e % RA;
+    const int b = t + P * c, r = b % 16, j = b / 16;
+    return r + 16 * (j + RB * i);
+  }
+
+  GX_HD static C tw_at(const C *__restrict__ twM, int idx) {          // W_M^idx, conjugated for the inverse
+    C w = twM[idx];
+    if (DIR > 0) w.y = -w.y;
+    return w;
+  }
+
+  // v[e]: the 16 inputs of thread t in input_index order
+  GX_HD static void stage_a(C (&v)[16], int t, C *S, const C *__restrict__ twM) {
+#pragma unroll
+    for (int c = 0; c < NA; ++c) {
+      const int b = t + P * c, r = b % 16, j = b / 16;
+      C *a = v + c * RA;
+      butterfly<RA, DIR, T>(a);
+      if (RB > 1) {
+        // W_M'^(j q) = W_M^(16 j q)
+        if (sizeof(T) == 8) BlockFFT<T, M, DIR>::template apply_twiddle_powers<RA>(tw_at(twM, 16 * j), a);
+        else {
+#pragma unroll
+          for (int q = 1; q < RA; ++q) a[q] = cmul(a[q], tw_at(twM, 16 * j * q));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RA; ++q) S[r * PITCH + q + RA * j] = a[q];
+    }
+  }
+
+  GX_HD static void stage_b(int t, C *S) {
+    if (RB == 1) return;
+#pragma unroll
+    for (int c = 0; c < (NB > 0 ? NB : 1); ++c) {
+      const int b = t + P * c, q = b % RA, r = b / RA;
+      C a[RB > 1 ? RB : 2];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) a[j] = S[r * PITCH + q + RA * j];
+      butterfly<RB, DIR, T>(a);
+#pragma unroll
+      for (int p2 = 0; p2 < RB; ++p2) S[r * PITCH + q + RA * p2] = a[p2];
+    }
+  }
+
+  template <class Emit> GX_HD static void stage_final(int t, const C *S, const C *__restrict__ twM, Emit &&emit) {
+    C y[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) y[r] = S[r * PITCH + t];
+    if (sizeof(T) == 8) BlockFFT<T, M, DIR>::template apply_twiddle_powers<16>(tw_at(twM, t), y);
+    else {
+#pragma unroll
+      for (int r = 1; r < 16; ++r) y[r] = cmul(y[r], tw_at(twM, t * r));
+    }
+    butterfly<16, DIR, T>(y);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) emit(t + MP * u, y[u]);
+  }
+};
+
 }  // namespace fft
 }  // namespace gx
