@@ -282,6 +282,11 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
   }
 }
 
+// Upper bound on the clusters a column pass launches (0: one per tile). A pass that is bound by NVLink rather than HBM (the
+// slab x-pass that stores into its peers, OpPushX) needs only a few KB in flight per SM: launched as a small persistent grid on
+// a side stream it leaves the SMs to the HBM-bound passes of the previous component running beside it.
+inline int &cols_cluster_limit() { static int v = 0; return v; }
+
 template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
 int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, LoadOp lop, StoreOp sop, cudaStream_t st) {
   using Cfg = ColsCfg<T, N, CL, TC, SEL>;
@@ -325,7 +330,8 @@ int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, Load
       fprintf(stderr, "[gx] fft_cols<N=%d,CL=%d,TC=%d,%zu-byte elems>: %d resident clusters, %zu KB smem/CTA, %d threads\n", N, CL,
               TC, sizeof(cplx<T>), max_clusters, Cfg::smem / 1024, Cfg::threads);
   }
-  const int nclusters = (int) ((ntiles < max_clusters || Cfg::NBUF == 1) ? ntiles : max_clusters);
+  int nclusters = (int) ((ntiles < max_clusters || Cfg::NBUF == 1) ? ntiles : max_clusters);
+  if (cols_cluster_limit() > 0 && nclusters > cols_cluster_limit()) nclusters = cols_cluster_limit();
   cfg.gridDim = dim3((unsigned) nclusters * CL);
   const char *tname = std::is_same<Pass, PassY>::value ? "fft_cols_y" : "fft_cols_x";
   GX_TIMED(tname, st);
@@ -481,7 +487,10 @@ template <typename T, int N> struct RowsDitCfg {
   static constexpr size_t smem = (size_t) LR * per_row;
 };
 
-template <typename T, int N, class Store>
+// TMA: a row of the padded field is (M + 1) complex = one contiguous, 16-byte aligned run in double precision (16400 bytes at
+// 2048^3), so ONE thread stages the CTA's rows with cp.async.bulk (TMA bulk engine, UBLKCP in SASS) completing on an mbarrier,
+// instead of 16 LDG + 16 STS per thread. (Single precision rows are 8-byte aligned only: they keep the register path.)
+template <typename T, int N, class Store, bool TMA>
 __global__ void __launch_bounds__(RowsDitCfg<T, N>::threads, RowsDitCfg<T, N>::MINB)
 fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__restrict__ twM,
                         const cplx<T> *__restrict__ twN, Store store) {
@@ -492,14 +501,47 @@ fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__r
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
   const int l = threadIdx.x / P, t = threadIdx.x % P;
-  const long row = row0 + (long) blockIdx.x * Cfg::LR + l;
+  const long first = row0 + (long) blockIdx.x * Cfg::LR;
+  const long row = first + l;
   const bool active = row < row0 + nrows;
   const C *rowp = reinterpret_cast<const C *>(data + row * (long) (N + 2));
   C *line = smem + (size_t) l * Cfg::pitch;
+  if constexpr (TMA) {
+    __shared__ __align__(8) unsigned long long mbar;
+    const unsigned mb = smem_addr_u32(&mbar);
+    constexpr unsigned row_bytes = (unsigned) ((M + 1) * sizeof(C));
+    static_assert(row_bytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long left = row0 + nrows - first;
+      const int nact = (int) (left < (long) Cfg::LR ? left : (long) Cfg::LR);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(row_bytes * (unsigned) nact) : "memory");
+      for (int r = 0; r < nact; ++r)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr_u32(smem + (size_t) r * Cfg::pitch)),
+                     "l"(data + (first + r) * (long) (N + 2)), "r"(row_bytes), "r"(mb)
+                     : "memory");
+    }
+    if (!active) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) line[t + i * P] = active ? rowp[t + i * P] : mk<T>(0, 0);
-  if (t == 0) line[M] = active ? rowp[M] : mk<T>(0, 0);
-  __syncthreads();
+      for (int i = 0; i < 16; ++i) line[t + i * P] = mk<T>(0, 0);
+      if (t == 0) line[M] = mk<T>(0, 0);
+    }
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(mb), "r"(0) : "memory");
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) line[t + i * P] = active ? rowp[t + i * P] : mk<T>(0, 0);
+    if (t == 0) line[M] = active ? rowp[M] : mk<T>(0, 0);
+    __syncthreads();
+  }
   C v[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
@@ -555,12 +597,26 @@ int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStrea
   if constexpr (N >= 512 && N <= 4096) {
     if (rows_dit_enabled()) {
       using Cfg = RowsDitCfg<T, N>;
-      auto kern = fft_rows_c2r_dit_kernel<T, N, Store>;
-      if (Cfg::smem > 48 * 1024)
-        GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
+      static int tma = -1;  // GX_ROWS_TMA=0: stage the rows through registers (A/B switch)
+      if (tma < 0) { const char *e = getenv("GX_ROWS_TMA"); tma = (e && e[0] == '0') ? 0 : 1; }
+      const bool use_tma = sizeof(T) == 8 && tma && ((size_t) data % 16 == 0);
       const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
       if (grid <= 0) return 0;
       GX_TIMED("fft_rows_c2r", st);
+      if constexpr (sizeof(T) == 8) {
+        if (use_tma) {
+          auto kern = fft_rows_c2r_dit_kernel<T, N, Store, true>;
+          if (Cfg::smem > 48 * 1024)
+            GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
+          kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store);
+          count_launch();
+          GX_LAUNCH_CHECK();
+          return 0;
+        }
+      }
+      auto kern = fft_rows_c2r_dit_kernel<T, N, Store, false>;
+      if (Cfg::smem > 48 * 1024)
+        GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
       kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store);
       count_launch();
       GX_LAUNCH_CHECK();

@@ -894,7 +894,8 @@ template <typename T> struct DeliverParams {
   const ChunkLoc *loc;     // per batch chunk
   const uint32_t *stage;
   int sa, sb;              // shells [sa, sb) of the batch
-  int p_origin, q_origin;  // (p, q) of block (0, 0), lane 0
+  int p_origin, q_origin;  // (p, q) of item 0, lane 0
+  int n_qblocks, n_items;  // items = (p, block of 32 q values), q-block fastest
 };
 
 // CTA = one k1 value p and 32 consecutive k2 values (lanes); the 8 warps take 8 consecutive shells per iteration.
@@ -906,8 +907,11 @@ __global__ void __launch_bounds__(256) deliver_kernel(DeliverParams<T> P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 128) s_w[tid] = d_zig_wtab[tid];
   __syncthreads();
-  const int p = P.p_origin + (int) blockIdx.y;
-  const int q0 = P.q_origin + 32 * (int) blockIdx.x;
+  // work items (p, q-block): one CTA each, or -- when the grid is smaller than the item count (several GPUs: the kernel is
+  // NVLink-bound and leaves most of every SM to the generation of the next batch) -- a grid-stride walk over them
+  for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+  const int p = P.p_origin + item / P.n_qblocks;
+  const int q0 = P.q_origin + 32 * (item % P.n_qblocks);
   const int q = q0 + lane;
   const int need_p = max(-p, p + 1), need_q = max(-q, q + 1);      // first shell whose loops reach p / q
   const int need_blk = max(need_p, q0 >= 0 ? q0 + 1 : -(q0 + 31));  // ... reach any lane of this block
@@ -957,6 +961,7 @@ __global__ void __launch_bounds__(256) deliver_kernel(DeliverParams<T> P) {
       if ((vmask[kk] >> qq) & 1u) *P.own.slot(p, q0 + qq, ks0 + kk) = tile[qq][kk];
     }
     __syncthreads();
+  }
   }
 }
 
@@ -1076,7 +1081,14 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
     GX_CUDA_CHECK(cudaMalloc(&own_scratch, want));
     scratch = own_scratch; scratch_bytes = want;
   }
-  const long long cap_chunks = (long long) (scratch_bytes / per_chunk);
+  // Several ranks: the delivery stores over NVLink and is bound by it, the generation is pure integer work. With two halves of
+  // the scratch buffer and of the per-batch arrays, batch b + 1 is generated (stream s_gen) while batch b is delivered (s_del).
+  static int pipe_env = -1;
+  if (pipe_env < 0) { const char *e = getenv("GX_NOISE_PIPELINE"); pipe_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool pipelined = world > 1 && pipe_env && scratch_bytes / 2 >= (size_t) largest * per_chunk;
+  const int nslots = pipelined ? 2 : 1;
+  const size_t slot_bytes = (scratch_bytes / nslots) & ~(size_t) 255;
+  const long long cap_chunks = (long long) (slot_bytes / per_chunk);
   // batches of whole shells
   std::vector<std::pair<int, int>> batches;
   long long max_batch = 0, max_batch_gauss = 0;
@@ -1102,26 +1114,61 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
   const unsigned int tail_cap = (unsigned int) std::min<long long>((long long) (my_gauss * 8e-4) + 4096, 400000000ll);
   void *p_streams, *p_misc, *p_tails, *p_fn, *p_st, *p_meta, *p_staged;
   if (ws_dev(0, sizeof(StreamDesc) * ns + sizeof(int) * (h + 1) + sizeof(float) * (h + 1), &p_streams)) return 1;
+  const size_t meta_bytes = ((sizeof(ListMeta) + sizeof(ChunkLoc)) * (size_t) max_batch + 255) & ~(size_t) 255;
   if (ws_dev(1, 64, &p_misc)) return 1;
   if (ws_dev(2, sizeof(TailEvent) * (size_t) tail_cap, &p_tails)) return 1;
-  if (ws_dev(3, sizeof(ChunkFn) * fn_total, &p_fn)) return 1;
-  if (ws_dev(4, sizeof(ScanState) * fn_total, &p_st)) return 1;
-  if (ws_dev(6, (sizeof(ListMeta) + sizeof(ChunkLoc)) * (size_t) max_batch + 64, &p_meta)) return 1;
-  if (ws_dev(7, sizeof(StagedTail) * (size_t) staged_cap, &p_staged)) return 1;
+  if (ws_dev(3, sizeof(ChunkFn) * fn_total * nslots, &p_fn)) return 1;
+  if (ws_dev(4, sizeof(ScanState) * fn_total * nslots, &p_st)) return 1;
+  if (ws_dev(6, meta_bytes * nslots, &p_meta)) return 1;
+  if (ws_dev(7, sizeof(StagedTail) * (size_t) staged_cap * nslots, &p_staged)) return 1;
   StreamDesc *d_streams = (StreamDesc *) p_streams;
   int *d_shell_first = (int *) ((char *) p_streams + sizeof(StreamDesc) * ns);
   float *d_shell_scale = (float *) (d_shell_first + h + 1);
-  unsigned int *d_staged_count = (unsigned int *) p_misc, *d_tail_count = d_staged_count + 1;
-  ChunkLoc *d_loc = (ChunkLoc *) p_meta;
-  ListMeta *d_meta = (ListMeta *) ((char *) p_meta + sizeof(ChunkLoc) * (size_t) max_batch);
+  // p_misc: [0] final tail count, [1] staged-overflow flag, [2], [3] staged tail counts of the two slots
+  unsigned int *d_tail_count = (unsigned int *) p_misc, *d_staged_counts = d_tail_count + 2;
   GX_CUDA_CHECK(cudaMemcpyAsync(d_streams, sd, sizeof(StreamDesc) * ns + sizeof(int) * (h + 1), cudaMemcpyHostToDevice, cs));
-  GX_CUDA_CHECK(cudaMemsetAsync(d_tail_count, 0, 2 * sizeof(unsigned int), cs));  // final tail count, staged-overflow flag
+  GX_CUDA_CHECK(cudaMemsetAsync(d_tail_count, 0, 4 * sizeof(unsigned int), cs));
   const int nl = (int) level_n.size();
   std::vector<ChunkFn *> d_fn(nl);
   std::vector<ScanState *> d_st(nl);
   const double sigma = (double) (T) (1.0 / sqrt(2.0));
 
-  for (const auto &bt : batches) {
+  static cudaStream_t s_gen = nullptr, s_del = nullptr;
+  static cudaEvent_t ev_ready[2], ev_free[2], ev_fork, ev_join[2];
+  static int s_dev = -1;
+  if (pipelined) {
+    int dev = 0;
+    GX_CUDA_CHECK(cudaGetDevice(&dev));
+    if (s_dev != dev) {
+      GX_CUDA_CHECK(cudaStreamCreateWithFlags(&s_gen, cudaStreamNonBlocking));
+      GX_CUDA_CHECK(cudaStreamCreateWithFlags(&s_del, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming));
+        GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+        GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+      }
+      GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      s_dev = dev;
+    }
+    GX_CUDA_CHECK(cudaEventRecord(ev_fork, cs));
+    GX_CUDA_CHECK(cudaStreamWaitEvent(s_gen, ev_fork, 0));
+    GX_CUDA_CHECK(cudaStreamWaitEvent(s_del, ev_fork, 0));
+  }
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+
+  for (size_t bi = 0; bi < batches.size(); ++bi) {
+    const auto &bt = batches[bi];
+    const int slot = pipelined ? (int) (bi & 1) : 0;
+    const cudaStream_t cg = pipelined ? s_gen : cs, cd = pipelined ? s_del : cs;
+    void *const scratch_b = (char *) scratch + (size_t) slot * slot_bytes;
+    ChunkFn *const fn_b = (ChunkFn *) p_fn + (size_t) slot * fn_total;
+    ScanState *const st_b = (ScanState *) p_st + (size_t) slot * fn_total;
+    ChunkLoc *const d_loc = (ChunkLoc *) ((char *) p_meta + (size_t) slot * meta_bytes);
+    ListMeta *const d_meta = (ListMeta *) ((char *) d_loc + sizeof(ChunkLoc) * (size_t) max_batch);
+    StagedTail *const staged_b = (StagedTail *) p_staged + (size_t) slot * staged_cap;
+    unsigned int *const d_staged_count = d_staged_counts + slot;
+    if (pipelined && bi >= 2) GX_CUDA_CHECK(cudaStreamWaitEvent(cg, ev_free[slot], 0));  // the slot's previous batch is delivered
     const int sa = bt.first, sb = bt.second;
     const int c0 = shell_first[sa], cnt = shell_first[sb] - c0;
     std::vector<int> ln;
@@ -1130,14 +1177,14 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
     const int bl = (int) ln.size();
     {
       size_t off = 0;
-      for (int l = 0; l < bl; ++l) { d_fn[l] = (ChunkFn *) p_fn + off; d_st[l] = (ScanState *) p_st + off; off += (size_t) ln[l]; }
+      for (int l = 0; l < bl; ++l) { d_fn[l] = fn_b + off; d_st[l] = st_b + off; off += (size_t) ln[l]; }
     }
-    GX_CUDA_CHECK(cudaMemsetAsync(d_staged_count, 0, sizeof(unsigned int), cs));
+    GX_CUDA_CHECK(cudaMemsetAsync(d_staged_count, 0, sizeof(unsigned int), cg));
     GenParams G;
     G.streams = d_streams; G.n_streams = ns; G.first = c0; G.count = cnt; G.jump = g_jump; G.fn = d_fn[0]; G.meta = d_meta;
-    G.stage = (uint32_t *) scratch; G.tails = (StagedTail *) p_staged; G.tail_count = d_staged_count; G.tail_cap = staged_cap;
+    G.stage = (uint32_t *) scratch_b; G.tails = staged_b; G.tail_count = d_staged_count; G.tail_cap = staged_cap;
     {
-      GX_TIMED("rng_gen", cs);
+      GX_TIMED("rng_gen", cg);
       const int grid = (cnt + kThreads - 1) / kThreads;
       const int mb = staged_minb();
       // mask of the SWB step on the fma pipe (IMAD.HI + IMAD) instead of the alu pipe: measured SLOWER at 2048^3
@@ -1145,34 +1192,34 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
       static int fma = -1;
       if (fma < 0) { const char *e = getenv("GX_RNG_FMA_MASK"); fma = (e && e[0] == '1') ? 1 : 0; }
       if (fma) {
-        if (mb == 5) rng_gen_kernel<5, true><<<grid, kThreads, 0, cs>>>(G);
-        else if (mb == 8) rng_gen_kernel<8, true><<<grid, kThreads, 0, cs>>>(G);
-        else rng_gen_kernel<6, true><<<grid, kThreads, 0, cs>>>(G);
+        if (mb == 5) rng_gen_kernel<5, true><<<grid, kThreads, 0, cg>>>(G);
+        else if (mb == 8) rng_gen_kernel<8, true><<<grid, kThreads, 0, cg>>>(G);
+        else rng_gen_kernel<6, true><<<grid, kThreads, 0, cg>>>(G);
       } else {
-        if (mb == 5) rng_gen_kernel<5, false><<<grid, kThreads, 0, cs>>>(G);
-        else if (mb == 8) rng_gen_kernel<8, false><<<grid, kThreads, 0, cs>>>(G);
-        else rng_gen_kernel<6, false><<<grid, kThreads, 0, cs>>>(G);
+        if (mb == 5) rng_gen_kernel<5, false><<<grid, kThreads, 0, cg>>>(G);
+        else if (mb == 8) rng_gen_kernel<8, false><<<grid, kThreads, 0, cg>>>(G);
+        else rng_gen_kernel<6, false><<<grid, kThreads, 0, cg>>>(G);
       }
       count_launch();
     }
     GX_LAUNCH_CHECK();
     {
-      GX_TIMED("rng_scan", cs);
+      GX_TIMED("rng_scan", cg);
       for (int l = 1; l < bl; ++l) {
-        scan_up_kernel<<<(ln[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], ln[l - 1], d_fn[l], ln[l]);
+        scan_up_kernel<<<(ln[l] + 127) / 128, 128, 0, cg>>>(d_fn[l - 1], ln[l - 1], d_fn[l], ln[l]);
         count_launch();
       }
-      scan_top_kernel<<<1, 32, 0, cs>>>(d_fn[bl - 1], ln[bl - 1], d_st[bl - 1]);
+      scan_top_kernel<<<1, 32, 0, cg>>>(d_fn[bl - 1], ln[bl - 1], d_st[bl - 1]);
       count_launch();
       for (int l = bl - 1; l >= 1; --l) {
-        scan_down_kernel<<<(ln[l] + 127) / 128, 128, 0, cs>>>(d_fn[l - 1], ln[l - 1], d_st[l], ln[l], d_st[l - 1]);
+        scan_down_kernel<<<(ln[l] + 127) / 128, 128, 0, cg>>>(d_fn[l - 1], ln[l - 1], d_st[l], ln[l], d_st[l - 1]);
         count_launch();
       }
-      resolve_kernel<<<(cnt + 127) / 128, 128, 0, cs>>>(d_fn[0], d_st[0], d_meta, (uint32_t *) scratch, d_loc, cnt);
+      resolve_kernel<<<(cnt + 127) / 128, 128, 0, cg>>>(d_fn[0], d_st[0], d_meta, (uint32_t *) scratch_b, d_loc, cnt);
       count_launch();
-      shell_scale_kernel<<<(sb - sa + 127) / 128, 128, 0, cs>>>(d_loc, d_shell_first, c0, sa, sb, d_shell_scale);
+      shell_scale_kernel<<<(sb - sa + 127) / 128, 128, 0, cg>>>(d_loc, d_shell_first, c0, sa, sb, d_shell_scale);
       count_launch();
-      tail_resolve_kernel<<<128, 256, 0, cs>>>((const StagedTail *) p_staged, d_staged_count, staged_cap, d_fn[0], d_st[0], d_meta,
+      tail_resolve_kernel<<<128, 256, 0, cg>>>((const StagedTail *) staged_b, d_staged_count, staged_cap, d_fn[0], d_st[0], d_meta,
                                                d_loc, d_streams, ns, c0, (TailEvent *) p_tails, d_tail_count, tail_cap,
                                                d_tail_count + 1);
       count_launch();
@@ -1180,25 +1227,40 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
     GX_LAUNCH_CHECK();
     DeliverParams<T> D;
     D.own = own; D.reverse = reverse; D.sigma = sigma; D.wtab = wtab; D.shell_first = d_shell_first; D.shell_scale = d_shell_scale; D.chunk0 = c0;
-    D.loc = d_loc; D.stage = (const uint32_t *) scratch; D.sa = sa; D.sb = sb;
+    D.loc = d_loc; D.stage = (const uint32_t *) scratch_b; D.sa = sa; D.sb = sb;
     const int top = sb - 1;                       // p, q in [-top, top)
     D.p_origin = -top;
     D.q_origin = -((top + 31) / 32) * 32;
-    const dim3 grid((unsigned) ((top - D.q_origin + 31) / 32), (unsigned) (2 * top));
+    D.n_qblocks = (top - D.q_origin + 31) / 32;
+    D.n_items = D.n_qblocks * 2 * top;
+    if (pipelined) {
+      GX_CUDA_CHECK(cudaEventRecord(ev_ready[slot], cg));
+      GX_CUDA_CHECK(cudaStreamWaitEvent(cd, ev_ready[slot], 0));
+    }
     {
-      GX_TIMED("rng_deliver", cs);
-      deliver_kernel<T><<<grid, 256, 0, cs>>>(D);
+      static int per_sm = -1;  // CTAs per SM of the NVLink-bound delivery when it shares the GPU with the generation
+      if (per_sm < 0) { const char *e = getenv("GX_DELIVER_CTAS_PER_SM"); per_sm = e ? atoi(e) : 1; }
+      const int grid = pipelined ? std::min(D.n_items, std::max(1, per_sm) * sms) : D.n_items;
+      GX_TIMED("rng_deliver", cd);
+      deliver_kernel<T><<<grid, 256, 0, cd>>>(D);
       count_launch();
     }
     GX_LAUNCH_CHECK();
+    if (pipelined) GX_CUDA_CHECK(cudaEventRecord(ev_free[slot], cd));
+  }
+  if (pipelined) {
+    GX_CUDA_CHECK(cudaEventRecord(ev_join[0], s_gen));
+    GX_CUDA_CHECK(cudaEventRecord(ev_join[1], s_del));
+    GX_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_join[0], 0));
+    GX_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_join[1], 0));
   }
 
   // tails: host libm recomputation (the reference's own arithmetic for these draws), then patched over the delivered values
-  GX_CUDA_CHECK(cudaMemcpyAsync(h_ntail, d_staged_count, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h_ntail, d_tail_count, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, cs));
   GX_CUDA_CHECK(cudaStreamSynchronize(cs));
   if (own_scratch) GX_CUDA_CHECK(cudaFree(own_scratch));
-  if (h_ntail[2]) return fail("gx_noise_draw: staged tail list overflow");
-  const unsigned int ntail = h_ntail[1];
+  if (h_ntail[1]) return fail("gx_noise_draw: staged tail list overflow");
+  const unsigned int ntail = h_ntail[0];
   if (ntail > tail_cap) return fail("gx_noise_draw: tail list overflow");
   if (ntail > 0) {
     void *pin_ev = nullptr, *pin_val = nullptr, *p_val = nullptr;

@@ -104,6 +104,18 @@ static int slab_x_push_t(const void *src, const void *planes, void *const *peer_
   push.pshift = op.pshift; push.pmask = P - 1;
   push.self_off = (long) rank * P * P * nc;
   push.line_stride = (long) P * nc;
+  struct Limit {  // GX_PUSH_CTAS_PER_SM > 0: a persistent grid of that many CTAs per SM (see cols_cluster_limit)
+    explicit Limit(int v) { fft::cols_cluster_limit() = v; }
+    ~Limit() { fft::cols_cluster_limit() = 0; }
+  };
+  static int per_sm = -1;
+  if (per_sm < 0) { const char *e = getenv("GX_PUSH_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; }
+  int clusters = 0;
+  if (per_sm > 0) {
+    const int cl = n > 256 ? std::min(8, n / 256) : 1;
+    clusters = std::max(1, per_sm * 148 / cl);
+  }
+  Limit guard(clusters);
   GX_N_SWITCH(n, (slab_x_n<T, N, 1>(src, nullptr, P, op, push, st)));
 }
 
