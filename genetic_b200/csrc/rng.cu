@@ -1084,7 +1084,9 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
   // Several ranks: the delivery stores over NVLink and is bound by it, the generation is pure integer work. With two halves of
   // the scratch buffer and of the per-batch arrays, batch b + 1 is generated (stream s_gen) while batch b is delivered (s_del).
   static int pipe_env = -1;
-  if (pipe_env < 0) { const char *e = getenv("GX_NOISE_PIPELINE"); pipe_env = (e && e[0] == '0') ? 0 : 1; }
+  // (measured on 2 B200s at 2048^3, profiles/r2s10_*: no gain -- the delivery needs most of the GPU's warps to keep NVLink busy,
+  // with 1-2 CTAs per SM it drops from 32 to 48-76 ms -- so this is off unless GX_NOISE_PIPELINE=1)
+  if (pipe_env < 0) { const char *e = getenv("GX_NOISE_PIPELINE"); pipe_env = (e && e[0] == '1') ? 1 : 0; }
   const bool pipelined = world > 1 && pipe_env && scratch_bytes / 2 >= (size_t) largest * per_chunk;
   const int nslots = pipelined ? 2 : 1;
   const size_t slot_bytes = (scratch_bytes / nslots) & ~(size_t) 255;
