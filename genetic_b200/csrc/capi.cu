@@ -25,8 +25,19 @@ int gx_device_count(int *count) {
   return 0;
 }
 
+// The library keeps grow-only workspaces (noise staging lists, |k|^2 table, partial sums, cross-grid tables, twiddles) on the
+// device that was current when they were created, and is driven by ONE host thread per process (as the reference is:
+// every call comes from its main thread). Binding another device drops them; they are rebuilt there on demand.
 int gx_set_device(int device) {
+  int cur = -1;
+  const bool had = cudaGetDevice(&cur) == cudaSuccess;
+  static int bound = -1;
+  if (bound >= 0 && bound != device) {
+    if (had && cur != bound) GX_CUDA_CHECK(cudaSetDevice(bound));
+    gx_workspace_release();
+  }
   GX_CUDA_CHECK(cudaSetDevice(device));
+  bound = device;
   return gx::fft::ensure_twiddles();
 }
 

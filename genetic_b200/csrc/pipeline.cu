@@ -49,7 +49,11 @@ extern "C" int gx_unigrid_ic(const gx_ic_params *p, const gx_spectrum *spectrum,
   if (to_host && host_capacity_particles == 0) return fail("gx_unigrid_ic: host_capacity_particles == 0");
   static cudaStream_t copy_stream = nullptr;
   static cudaEvent_t ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-  if (to_host && !copy_stream) {
+  static int copy_device = -1;
+  int cur_device = 0;
+  GX_CUDA_CHECK(cudaGetDevice(&cur_device));
+  if (to_host && (!copy_stream || copy_device != cur_device)) {
+    copy_device = cur_device;
     GX_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       GX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_emit[i], cudaEventDisableTiming));

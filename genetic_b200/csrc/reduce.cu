@@ -117,9 +117,17 @@ static int ensure_partials() {
   GX_CUDA_CHECK(cudaMalloc(&g_partials, (kMaxPartials + 1) * sizeof(double)));
   return 0;
 }
+void release_reduce_workspace() {  // gx_workspace_release / gx_set_device(another device)
+  if (g_partials) { cudaDeviceSynchronize(); cudaFree(g_partials); }
+  g_partials = nullptr;
+}
+static int check_n_reduce(int n) {  // the partials hold 64 blocks x n planes: n <= 4096
+  if (!is_pow2(n) || n < 4 || n > 4096) return fail("grid size must be a power of two in [4,4096]");
+  return 0;
+}
 
 template <typename T> static int dot_fourier_t(const void *a, const void *b, int n, double *host_out, cudaStream_t st) {
-  if (ensure_partials()) return 1;
+  if (check_n_reduce(n) || ensure_partials()) return 1;
   const int nc = n / 2 + 1, plane = n * nc;
   int bx = (plane + 255) / 256; if (bx > 64) bx = 64;
   dot_fourier_kernel<T><<<dim3(bx, n), 256, 0, st>>>((const cplx<T> *) a, (const cplx<T> *) b, n, nc, g_partials);
@@ -132,7 +140,7 @@ template <typename T> static int dot_fourier_t(const void *a, const void *b, int
 }
 
 template <typename T> static int dot_real_t(const void *a, const void *b, int n, double *host_out, cudaStream_t st) {
-  if (ensure_partials()) return 1;
+  if (check_n_reduce(n) || ensure_partials()) return 1;
   long nrows = (long) n * n;
   int grid = (int) (nrows < 148 * 16 ? nrows : 148 * 16);
   dot_real_kernel<T><<<grid, 256, 0, st>>>((const T *) a, (const T *) b, n, g_partials);
@@ -156,6 +164,7 @@ using namespace gx;
   } while (0)
 
 template <typename T> static int scale_t(void *f, int n, double a, cudaStream_t st) {
+  if (n < 1 || n > 4096) return gx::fail("grid size out of range");
   const size_t len = (size_t) 2 * n * n * (n / 2 + 1);
   scale_kernel<T><<<148 * 8, 256, 0, st>>>((T *) f, len, (T) a);
   count_launch();

@@ -34,6 +34,7 @@
 
 namespace gx {
 void release_spectral_workspace();   // spectral.cu: the |k|^2 table
+void release_reduce_workspace();     // reduce.cu: partial sums
 void release_multigrid_workspace();  // multigrid.cu: cached cross-grid tables
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
 namespace fft { template <typename T> int fft3d(T *data, int n, int dir, cudaStream_t st); }
@@ -508,8 +509,13 @@ struct TailEvent;
 static void host_tail_values(const TailEvent *ev, double *val, unsigned int ntail);
 // ---- host driver ------------------------------------------------------------------------------------------------------
 static Big *g_jump = nullptr;
+static int g_jump_device = -1;
 static int ensure_jump_table() {
-  if (g_jump) return 0;
+  int dev = 0;
+  GX_CUDA_CHECK(cudaGetDevice(&dev));
+  if (g_jump && dev == g_jump_device) return 0;
+  g_jump = nullptr;  // (a table on another device stays allocated there until that device is reset)
+  g_jump_device = dev;
   std::vector<Big> h((size_t) kJumpDigits * kJumpRadix);
   Big base = modpow(big_a(), 397ull * kBc);
   for (int d = 0; d < kJumpDigits; ++d) {
@@ -1432,6 +1438,7 @@ int gx_workspace_release(void) {
   gx::rng::ws_release();
   gx::release_spectral_workspace();
   gx::release_multigrid_workspace();
+  gx::release_reduce_workspace();
   return 0;
 }
 

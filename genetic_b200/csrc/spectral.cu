@@ -254,7 +254,12 @@ static int build_transfer_table_t(int n, double L, const gx_spectrum *s, double 
     GX_TIMED("transfer_table", st);
     long blocks = (mcount + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    transfer_table_kernel<T><<<(unsigned) blocks, 256, 3 * tf.sp.m * sizeof(double), st>>>(tf);
+    const size_t smem = 3 * tf.sp.m * sizeof(double);
+    if (smem > 48 * 1024) {
+      if (smem > 200 * 1024) return fail("transfer-function table too long for the in-kernel spline (more than ~8500 rows)");
+      GX_CUDA_CHECK(cudaFuncSetAttribute(transfer_table_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    }
+    transfer_table_kernel<T><<<(unsigned) blocks, 256, smem, st>>>(tf);
     count_launch();
   }
   GX_LAUNCH_CHECK();

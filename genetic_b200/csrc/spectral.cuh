@@ -122,6 +122,11 @@ int launch_slot_sweep(int n, F f, cudaStream_t st, size_t smem = 0, const char *
   int bx = (plane + 255) / 256;
   if (bx > 64) bx = 64;  // 64 x n CTAs: >= 4 waves of 148 SMs from n = 16 upward
   dim3 grid(bx, n);
+  // a CAMB table with more than ~2000 usable rows needs more than the default 48 KB of dynamic shared memory for its spline
+  if (smem > 48 * 1024) {
+    if (smem > 200 * 1024) return fail("transfer-function table too long for the in-kernel spline (more than ~8500 rows)");
+    GX_CUDA_CHECK(cudaFuncSetAttribute(slot_sweep_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  }
   slot_sweep_kernel<F><<<grid, 256, smem, st>>>(n, nc, iy0, ny, f);
   count_launch();
   GX_LAUNCH_CHECK();

@@ -651,9 +651,11 @@ class ICGenerator:
         esz, odt = out_dtype.itemsize, _dt(out_dtype)
         if tipsy:
             # TipsyOutput::operator() (tipsy.hpp:207-271); the mass sum over identical particles, sequentially in double
-            tot, m = 0.0, float(mass)
-            for c0 in range(0, n3, 1 << 22):            # tot_mass += mass, one particle after the other (tipsy.hpp:217-223)
-                tot = float(np.cumsum(np.concatenate([[tot], np.full(min(1 << 22, n3 - c0), m)]))[-1])
+            ft = np.dtype(self.dtype).type               # FloatType tot_mass: float under -f (tipsy.hpp:218)
+            tot, m = ft(0.0), ft(mass)
+            for c0 in range(0, n3, 1 << 22):            # tot_mass += mass, one particle after the other (tipsy.hpp:217-225)
+                tot = np.cumsum(np.concatenate([[tot], np.full(min(1 << 22, n3 - c0), m, dtype=ft)]).astype(ft), dtype=ft)[-1]
+            tot = float(tot)
             mass_factor = float(self.cosmology.OmegaM0) / tot
             pos_factor = 1. / boxlen
             dKpcUnit = boxlen * 1000 / float(self.cosmology.hubble)
@@ -662,7 +664,8 @@ class ICGenerator:
             vel_factor = float(self.cosmology.scalefactor) ** -0.5 / dKmsUnit
             fn = self.getOutputPath() + ".tipsy"
             with open(fn, "wb") as f:
-                f.write(OUT.struct.pack("<diiiii4x", float(self.cosmology.scalefactor), n3, 3, 0, n3, 0))
+                f.write(OUT.struct.pack("<diiiii4x", float(self.cosmology.scalefactor), OUT._wrap_int32(n3), 3, 0,
+                                        OUT._wrap_int32(n3), 0))
                 f.truncate(32 + n3 * 36)
             rec = np.memmap(fn, dtype=np.float32, mode="r+", offset=32, shape=(n3, 9))
             with open("tipsy.param", "w") as f:

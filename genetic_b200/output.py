@@ -16,18 +16,26 @@ import struct
 import numpy as np
 
 
-def _sequential_sum(values):
-    """tot_mass += mass in mapper order, in double (tipsy.hpp:217-223): sequential, not pairwise."""
-    return float(np.cumsum(np.asarray(values, dtype=np.float64))[-1])
+def _sequential_sum(values, dtype=np.float64):
+    """tot_mass += mass in mapper order (tipsy.hpp:217-225): sequential, not pairwise, and in the generator's FloatType --
+    `FloatType mass, tot_mass` is float under genetIC -f."""
+    return float(np.cumsum(np.asarray(values, dtype=dtype), dtype=dtype)[-1])
+
+
+def _wrap_int32(v):
+    """A particle count as the reference's `int npart[6]` holds it (gadget.hpp:28,122-127): the low 32 bits, signed."""
+    v = int(v) & 0xffffffff
+    return v - (1 << 32) if v >= (1 << 31) else v
 
 
 def saveTipsy(filename, boxLength, particles, cosmology, aux_dir=None):
     """tipsy::save. `particles` must hold positions/velocities in the grid's floating type (the conversions below are
     done in double before the float32 store, like the reference). Writes tipsy.param and, when masses differ,
     photogenic.txt next to the file (the reference writes them into its working directory)."""
+    ftype = np.float32 if np.asarray(particles.mass).dtype == np.float32 else np.float64
     mass = particles.mass.astype(np.float64)
     min_mass, max_mass = float(mass.min()), float(mass.max())
-    mass_factor = float(cosmology.OmegaM0) / _sequential_sum(mass)
+    mass_factor = float(cosmology.OmegaM0) / _sequential_sum(particles.mass, ftype)
     pos_factor = 1. / float(boxLength)
     dKpcUnit = float(boxLength) * 1000 / float(cosmology.hubble)
     dMsolUnit = 1e10 / float(cosmology.hubble) / mass_factor
@@ -60,7 +68,9 @@ def saveTipsy(filename, boxLength, particles, cosmology, aux_dir=None):
         f.write("dKpcUnit = %s\ndMsolUnit = %s\ndHubble0 = %s\nbComove = 1 \n"
                 % (_g6(dKpcUnit), _g6(dMsolUnit), _g6(0.1 * float(cosmology.hubble) * dKpcUnit / dKmsUnit)))
     with open(filename, "wb") as f:
-        f.write(struct.pack("<diiiii4x", float(cosmology.scalefactor), N, 3, ngas, N - ngas, 0))
+        # (int n, ngas, ndark in the reference's header struct: counts beyond 2^31 wrap, tipsy.hpp:20-27)
+        f.write(struct.pack("<diiiii4x", float(cosmology.scalefactor), _wrap_int32(N), 3, _wrap_int32(ngas),
+                            _wrap_int32(N - ngas), 0))
         grec.tofile(f)
         rec.tofile(f)
 
@@ -88,7 +98,7 @@ def _fortran(f, payload):
 
 def _gadget_header(version, masses, npart, npartTotal, nFiles, boxLength, cosmology, doubleprecision):
     h = bytearray(256)
-    struct.pack_into("<6i", h, 0, *[int(v) for v in npart])
+    struct.pack_into("<6i", h, 0, *[_wrap_int32(v) for v in npart])
     struct.pack_into("<6d", h, 24, *[float(m) for m in masses])
     struct.pack_into("<dd", h, 72, float(cosmology.scalefactor), float(cosmology.redshift))
     baryons = 1 if npartTotal[0] > 0 else 0
