@@ -174,6 +174,103 @@ class NumpyOps:
         slab.numpy().view(np.float64)[0] = 0.0
 
 
+class PushNumpyOps(NumpyOps):
+    """Stand-in for the peer-memory entry points of CudaSlabOps (gx_slab_noise_staged, gx_slab_fft_x_mirror_push,
+    gx_slab_fft_y_op): processes on a CPU cannot store into each other's buffers, so the "push" is the local x-pass followed
+    by the same block exchange through gloo; the sequencing under test (SlabPipeline.ic_push: transfer folded into the noise,
+    ONE exchanged x-transform of G shared by psi_y and psi_z) is the product's."""
+
+    def __init__(self, geo, box, cosmo, comm):
+        super().__init__(geo, box, cosmo)
+        self.comm = comm
+
+    def alloc_shared(self, nbytes):
+        return self.alloc(nbytes)
+
+    def noise_staged(self, slab, peer_slabs, seed, reverse, spectrum, grid_length, scratch):
+        self.noise_draw(slab, seed, 2, reverse)
+        if spectrum is not None:
+            self.apply_transfer(slab, grid_length, spectrum, 0.5, 1)
+
+    def x_inverse_mirror_push(self, slab, planes_all, peer_exchange, grid_length, op, axis):
+        send = self.alloc(self.geo.slab_bytes)
+        self.x_inverse_mirror(slab, planes_all, send, grid_length, op, axis)
+        self.comm.all_to_all(self.comm.registered[peer_exchange[self.geo.rank]], send)
+
+    def y_pass_op(self, src, dst, src_exchange, grid_length, axis):
+        g, M = self.geo, self.M
+        X = self._plain(src, src_exchange).copy()
+        kmin = 2.0 * np.pi / grid_length
+        if axis == 1:
+            k = M.signed_modes(g.n).astype(np.float64) * kmin
+            k[g.n // 2] = 0.0                      # zero on the Nyquist plane of the component's axis
+            X = 1j * k[None, :, None] * X
+        else:
+            k = np.arange(g.nc) * kmin
+            k[g.n // 2] = 0.0
+            X = 1j * k[None, None, :] * X
+        self._c(dst, (g.P, g.n, g.nc))[:] = np.fft.ifft(X, axis=1) * g.n
+
+
+def _push_worker(rank, world, port, n, outdir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from genetic_b200 import slab as SL
+    from genetic_b200 import host as H
+    from oracle import model as M
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        class Comm(SL.TorchComm):
+            registered = {}
+
+            def stream_barrier(self):
+                self.barrier()
+
+            def peer_pointers(self, buf):          # a handle per buffer; the stand-in ops resolve their own entry
+                key = len(self.registered) + 1
+                self.registered[key] = buf
+                return [key] * self.world
+
+        box, seed = 50.0, 8896131
+        ocos = M.Cosmology(0.279, 0.721, 0.817, 99)
+        camb = M.CAMB(CAMB_FILE, ocos)
+        geo = SL.SlabGeometry(n, world, rank, 8)
+        comm = Comm()
+        ops = PushNumpyOps(geo, box, ocos, comm)
+        pipe = SL.SlabPipeline(geo, ops, comm, lean=True)
+        delta = ops.alloc_shared(geo.slab_bytes)
+        assert pipe.enable_push(delta) and pipe.bufB is None
+        grid = H.Grid(box, n)
+        ratio = M.velocity_to_offset_ratio(ocos)
+        out_pos = ops.alloc(3 * geo.particles * 8)
+        out_vel = ops.alloc(3 * geo.particles * 8)
+        for _ in range(2):
+            SL.unigrid_ic_slab(geo, ops, comm, seed, 2, 0, 0, grid, camb, ratio, np.float64, delta, pipe, out_pos, out_vel)
+        np.savez(os.path.join(outdir, "rank%d.npz" % rank), pos=out_pos.numpy().view(np.float64).reshape(3, -1),
+                 vel=out_vel.numpy().view(np.float64).reshape(3, -1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 16), (4, 16)])
+def test_peer_memory_schedule_matches_single_process_oracle(tmp_path, world, n):
+    """SlabPipeline.ic_push over gloo: noise with the transfer folded in, two pushed x-passes, psi_y / psi_z from the one
+    exchanged x-transform of G with i k_y / i k_z applied on the load side of their y-passes, three barriers."""
+    import torch.multiprocessing as mp
+    from oracle import model as M
+    port = _free_port()
+    mp.spawn(_push_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    box, seed = 50.0, 8896131
+    ocos = M.Cosmology(0.279, 0.721, 0.817, 99)
+    opos, ovel, _, _ = M.unigrid_ic(n, box, seed, "fourier_parallel", CAMB_FILE, ocos)
+    pos = np.concatenate([np.load(tmp_path / ("rank%d.npz" % r))["pos"] for r in range(world)], axis=1).T
+    vel = np.concatenate([np.load(tmp_path / ("rank%d.npz" % r))["vel"] for r in range(world)], axis=1).T
+    assert np.abs(vel - ovel).max() <= 1e-11 * np.abs(ovel).max()
+    d = np.abs(pos - opos)
+    assert np.minimum(d, box - d).max() <= 1e-11 * box
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
