@@ -902,6 +902,7 @@ template <typename T> struct DeliverParams {
   int sa, sb;              // shells [sa, sb) of the batch
   int p_origin, q_origin;  // (p, q) of item 0, lane 0
   int n_qblocks, n_items;  // items = (p, block of 32 q values), q-block fastest
+  int item_shift;          // rotation of the item order (rank * n_items / world)
 };
 
 // CTA = one k1 value p and 32 consecutive k2 values (lanes); the 8 warps take 8 consecutive shells per iteration.
@@ -915,7 +916,10 @@ __global__ void __launch_bounds__(256) deliver_kernel(DeliverParams<T> P) {
   __syncthreads();
   // work items (p, q-block): one CTA each, or -- when the grid is smaller than the item count (several GPUs: the kernel is
   // NVLink-bound and leaves most of every SM to the generation of the next batch) -- a grid-stride walk over them
-  for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+  for (int it0 = blockIdx.x; it0 < P.n_items; it0 += gridDim.x) {
+  // (several ranks: each starts its sweep over k1 at a different place, so that at any moment the ranks store into
+  // different owners -- the face with ky = k1 sends a whole CTA's output to one rank)
+  const int item = it0 + P.item_shift < P.n_items ? it0 + P.item_shift : it0 + P.item_shift - P.n_items;
   const int p = P.p_origin + item / P.n_qblocks;
   const int q0 = P.q_origin + 32 * (item % P.n_qblocks);
   const int q = q0 + lane;
@@ -1241,6 +1245,7 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
     D.q_origin = -((top + 31) / 32) * 32;
     D.n_qblocks = (top - D.q_origin + 31) / 32;
     D.n_items = D.n_qblocks * 2 * top;
+    D.item_shift = world > 1 ? (int) ((long long) D.n_items * rank / world) : 0;
     if (pipelined) {
       GX_CUDA_CHECK(cudaEventRecord(ev_ready[slot], cg));
       GX_CUDA_CHECK(cudaStreamWaitEvent(cd, ev_ready[slot], 0));

@@ -105,3 +105,40 @@ def test_profiler_test_config3_against_the_reference_binary_sample(golden_dir, t
     assert np.array_equal(ours["mass"][idx], gold["mass"]) and np.array_equal(ours["eps"][idx], gold["eps"])
     assert np.abs(ours["pos"][idx] - gold["pos"]).max() < 1e-5
     assert np.abs(ours["vel"][idx] - gold["vel"]).max() < 1e-4 * np.abs(gold["vel"]).max()
+
+
+def test_config2_512_unigrid_whole_chain_against_the_reference_binary(tmp_path, golden_dir):
+    """BASELINE config 2 / SURVEY 8(d) item 2: single-level 512^3, double precision, Fourier-space (parallel) seed, Zeldovich
+    displacement + velocity, L = 200 Mpc/h, Planck-2018 transfer -- the paramfile run through the command layer on the GPU
+    (streaming writer: staged noise, shared-transform Zeldovich, natural-order c2r with the particle emit) and through the
+    reference binary on the host cores (~20 s); the two tipsy files are compared particle by particle."""
+    import oracle
+    from genetic_b200 import icgen
+    if oracle.ref_binary() is None:
+        pytest.skip("oracle/_ref/genetIC not built")
+    n, box, seed = 512, 200.0, 8896131
+    camb = os.path.join(golden_dir, "planck_2018_transfer_out.dat")
+    pf = ("Om 0.3158\nOl 0.6842\ns8 0.8117\nns 0.9660\nhubble 0.6732\nz 200\ncamb %s\nrandom_seed %d\noutname c2\noutdir ./\n"
+          "outformat tipsy\nbase_grid %r %d\ndone\n" % (os.path.basename(camb), seed, box, n))
+    ref_dir, our_dir = tmp_path / "ref", tmp_path / "ours"
+    oracle.run_ref(pf, str(ref_dir), [camb], threads=len(os.sched_getaffinity(0)))
+    os.makedirs(our_dir)
+    shutil.copy(camb, our_dir)
+    (our_dir / "paramfile.txt").write_text(pf)
+    icgen.run_paramfile(str(our_dir / "paramfile.txt"), log=lambda s: None)
+    hdr = 32
+    a = np.memmap(str(ref_dir / "c2.tipsy"), dtype=np.float32, mode="r", offset=hdr).reshape(n ** 3, 9)
+    b = np.memmap(str(our_dir / "c2.tipsy"), dtype=np.float32, mode="r", offset=hdr).reshape(n ** 3, 9)
+    assert open(str(ref_dir / "c2.tipsy"), "rb").read(hdr) == open(str(our_dir / "c2.tipsy"), "rb").read(hdr)
+    worst_pos = worst_vel = 0.0
+    exact = 0
+    vmax = float(np.abs(a[::997, 4:7]).max())
+    for c0 in range(0, n ** 3, 1 << 24):
+        x, y = np.asarray(a[c0:c0 + (1 << 24)]), np.asarray(b[c0:c0 + (1 << 24)])
+        assert np.array_equal(x[:, 0], y[:, 0]) and np.array_equal(x[:, 7], y[:, 7])       # mass, softening
+        worst_pos = max(worst_pos, float(np.abs(x[:, 1:4] - y[:, 1:4]).max()))
+        worst_vel = max(worst_vel, float(np.abs(x[:, 4:7] - y[:, 4:7]).max()))
+        exact += int(np.count_nonzero(np.all(x == y, axis=1)))
+    # float32 file: positions in box units (|pos| <= 0.5), f64 fields behind them agree to ~1e-13
+    assert worst_pos <= np.spacing(np.float32(0.5)) and worst_vel <= 2 * np.spacing(np.float32(vmax))
+    assert exact > 0.98 * n ** 3
