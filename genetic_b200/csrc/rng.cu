@@ -836,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rng_gen_kernel(GenParams P) {
   __shared__ double s_w[128], s_y[128];
   __shared__ uint32_t ring[kRing][kThreads];
   __shared__ uint32_t sbuf[4][kThreads];
+  __shared__ uint32_t sinc[kIncCap][kThreads];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_k[i] = d_zig_ktab[i]; s_w[i] = d_zig_wtab[i]; s_y[i] = d_zig_ytab[i]; }
   __syncthreads();
   // gen_chunk is warp-collective: the lanes past the end of the batch redo its last chunk (identical stores) and report nothing
@@ -849,7 +850,8 @@ __global__ void __launch_bounds__(kThreads, MINB) rng_gen_kernel(GenParams P) {
   DevTailSink sink{P.tails, P.tail_count, in_range ? P.tail_cap : 0u, rel};
   ChunkFn f;
   ListMeta m;
-  gen_chunk<FMA>(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x}, s_k, s_w, s_y,
+  gen_chunk<FMA>(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x},
+                 SmemColumn{sinc, (int) threadIdx.x}, s_k, s_w, s_y,
                  P.stage + (size_t) rel * kChunkStage, f, m, sink);
   if (in_range) { P.fn[rel] = f; P.meta[rel] = m; }
 }

@@ -138,50 +138,72 @@ template <int E, class Buf> GX_HD void append_draw(uint32_t d, int c, Buf buf, u
 }
 
 // Hypothesis E of a chunk parsed up to raw position `limit`. ALL lanes of the warp call this together (`live` says whether
-// the lane has work): 98.8 % of the attempts are the integer fast path (j < ktab[i]); the others need exp() (wedge) or
-// log() and exp() (tail), ~150 instructions that used to run for one or two lanes at a time at every loop iteration in
-// which any lane needed them (ncu: 21 % of the kernel's instructions at 12.7 of 32 lanes). Here a lane that meets a slow
-// attempt waits; when every lane has either finished or waits, the waiting lanes evaluate theirs together.
-template <int E, class Ring, class Buf, class Sink>
-GX_HD void parse_hypothesis(bool live, int &p, int &c, int limit, Ring ring, Buf buf, const unsigned int *ktab,
+// the lane has work). 98.8 % of the attempts are the integer fast path (j < ktab[i]); the others need exp() (wedge) or log()
+// and exp() (tail), ~130 instructions. How far an attempt advances the parse does NOT depend on whether it is accepted
+// (2 raw outputs on the fast path, 3 in a wedge, 4 in the tail), only the list of accepted draws does. So the lane walks
+// its ~12 attempts of the increment in one loop of uniform length, collecting the draws in a small buffer `inc` with the
+// slow attempts entered TENTATIVELY; then the pending slow attempts of all lanes are evaluated together (one convergent
+// pass, two for a lane with two of them), rejected ones are taken out of the buffer, and the buffer is appended to the list.
+// (Before: a lane that met a slow attempt waited for the others -- 24 loop iterations per increment at 15 of 32 lanes, ncu.)
+constexpr int kIncCap = 16;   // draws of one increment per hypothesis: at most (24 + 3) / 2 = 13
+
+template <int E, class Ring, class Buf, class Inc, class Sink>
+GX_HD void parse_hypothesis(bool live, int &p, int &c, int limit, Ring ring, Buf buf, Inc inc, const unsigned int *ktab,
                             const double *wtab, const double *ytab, uint32_t *stage, Sink &sink) {
   bool more = live && p < limit;
-  while (GX_ANY(more)) {
-    bool slow = false;
-    uint32_t r0 = 0, r1 = 0;
-    while (more) {
-      r0 = ring.at(p & (kRing - 1));
-      r1 = ring.at((p + 1) & (kRing - 1));
-      if (r1 < ktab[r0 & 0x7Fu]) {
-        append_draw<E>(pack_draw(r0, r1), c, buf, stage);
-        ++c;
-        p += 2;
-        more = p < limit;
-      } else {
-        slow = true;
-        more = false;
+  while (GX_ANY(more)) {           // one round, unless a lane meets a third slow attempt in the increment (~1e-4)
+    int m = 0, npend = 0;          // draws collected in inc; pending slow attempts (position in inc, raw position)
+    int pk0 = 0, pp0 = 0, pk1 = 0, pp1 = 0;
+    if (more) {
+      while (p < limit) {
+        const uint32_t r0 = ring.at(p & (kRing - 1)), r1 = ring.at((p + 1) & (kRing - 1));
+        const uint32_t i = r0 & 0x7Fu;
+        if (r1 < ktab[i]) {
+          inc.at(m++) = pack_draw(r0, r1);
+          p += 2;
+        } else if (npend < 2) {    // entered tentatively, decided after the loop
+          inc.at(m) = pack_draw(r0, r1);
+          if (npend == 0) { pk0 = m; pp0 = p; } else { pk1 = m; pp1 = p; }
+          ++npend;
+          ++m;
+          p += (i < 127u) ? 3 : 4;
+        } else {
+          break;
+        }
       }
     }
     GX_SYNCWARP();
-    if (slow) {
-      const Attempt a = zig_attempt(r0, r1, ring.at((p + 2) & (kRing - 1)), ring.at((p + 3) & (kRing - 1)), ktab, wtab, ytab);
-      if (a.accepted) {
-        if (a.tail) sink.push(E, c, a.tail_u1, a.value > 0);
-        append_draw<E>(pack_draw(r0, r1), c, buf, stage);
-        ++c;
+    int removed = 0;               // a rejected attempt leaves the buffer: later entries move down by one
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+      const bool have = round < npend;
+      if (!GX_ANY(have)) break;
+      if (have) {
+        const int pk = round == 0 ? pk0 : pk1, pp = round == 0 ? pp0 : pp1;
+        const Attempt a = zig_attempt(ring.at(pp & (kRing - 1)), ring.at((pp + 1) & (kRing - 1)),
+                                      ring.at((pp + 2) & (kRing - 1)), ring.at((pp + 3) & (kRing - 1)), ktab, wtab, ytab);
+        const int k = pk - removed;
+        if (a.accepted) {
+          if (a.tail) sink.push(E, c + k, a.tail_u1, a.value > 0);   // entries before k are final: so is this index
+        } else {
+          for (int q = k; q + 1 < m; ++q) inc.at(q) = inc.at(q + 1);
+          --m;
+          ++removed;
+        }
       }
-      p += a.consumed;
-      more = p < limit;
     }
+    for (int k = 0; k < m; ++k) { append_draw<E>(inc.at(k), c, buf, stage); ++c; }
+    more = live && p < limit;
   }
 }
 
 // One chunk: `st` is the generator state at the chunk's first block. Ring::at(slot) / Buf::at(k) are the thread's raw-output
-// ring (kRing slots) and its 4-entry store buffer (shared memory on the device, plain arrays on the host); `stage` is the
+// ring (kRing slots), its 4-entry store buffer and its per-increment draw buffer (kIncCap slots; shared memory on the device,
+// plain arrays on the host); `stage` is the
 // chunk's kChunkStage words; sink.push(list, idx, u1, positive) records accepted tail draws. Warp-collective on the
 // device: every lane of the warp must call it.
-template <bool FMA, class Ring, class Buf, class Sink>
-GX_HD void gen_chunk(const StreamDesc &sd, bool first, const State &st0, Ring ring, Buf buf, const unsigned int *ktab,
+template <bool FMA, class Ring, class Buf, class Inc, class Sink>
+GX_HD void gen_chunk(const StreamDesc &sd, bool first, const State &st0, Ring ring, Buf buf, Inc inc, const unsigned int *ktab,
                      const double *wtab, const double *ytab, uint32_t *stage, ChunkFn &f, ListMeta &meta, Sink &sink) {
   int p0, p1 = 1, p2 = 2, p3 = 3;          // positions of the four entry hypotheses
   int c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // draws appended to their lists
@@ -200,10 +222,10 @@ GX_HD void gen_chunk(const StreamDesc &sd, bool first, const State &st0, Ring ri
     for (int j = 0; j < 24; ++j) ring.at((rbase + j) & (kRing - 1)) = gs.out(j);
     const int avail = 24 * (bi + 1);
     const int limit = avail - 3 < kChunkLen ? avail - 3 : kChunkLen;
-    parse_hypothesis<0>(true, p0, c0, limit, ring, buf, ktab, wtab, ytab, stage, sink);
-    if (GX_ANY(rep1 < 0)) parse_hypothesis<1>(rep1 < 0, p1, c1, limit, ring, buf, ktab, wtab, ytab, stage, sink);
-    if (GX_ANY(rep2 < 0)) parse_hypothesis<2>(rep2 < 0, p2, c2, limit, ring, buf, ktab, wtab, ytab, stage, sink);
-    if (GX_ANY(rep3 < 0)) parse_hypothesis<3>(rep3 < 0, p3, c3, limit, ring, buf, ktab, wtab, ytab, stage, sink);
+    parse_hypothesis<0>(true, p0, c0, limit, ring, buf, inc, ktab, wtab, ytab, stage, sink);
+    if (GX_ANY(rep1 < 0)) parse_hypothesis<1>(rep1 < 0, p1, c1, limit, ring, buf, inc, ktab, wtab, ytab, stage, sink);
+    if (GX_ANY(rep2 < 0)) parse_hypothesis<2>(rep2 < 0, p2, c2, limit, ring, buf, inc, ktab, wtab, ytab, stage, sink);
+    if (GX_ANY(rep3 < 0)) parse_hypothesis<3>(rep3 < 0, p3, c3, limit, ring, buf, inc, ktab, wtab, ytab, stage, sink);
     // merge hypotheses that have reached the same position (into the lowest one)
     if (rep1 < 0 && p1 == p0) { rep1 = 0; j1 = c0; }
     if (rep2 < 0) {
@@ -304,6 +326,17 @@ GX_HD FaceSlot face_slot(int ks, int p, int q, int face) {
   const int k1 = (face == 0) ? ks : p;
   const int k2 = (face == 0) ? p : ((face == 1) ? ks : q);
   const int k3 = (face == 2) ? ks : q;
+  if (p != -ks && q != -ks) {
+    // no coordinate equals -ks: the conjugate partner has no coordinate equal to +ks, so it is not drawn in this shell and
+    // this call is the only writer of its slot (all but one lane per row and one row per shell take this path)
+    FaceSlot s;
+    s.write = true;
+    s.m = k1 * k1 + k2 * k2 + k3 * k3;
+    s.neg = k3 < 0;
+    s.a = s.neg ? -k1 : k1; s.b = s.neg ? -k2 : k2; s.c = s.neg ? -k3 : k3;
+    s.second = (k3 == 0);
+    return s;
+  }
   // the partner -k is drawn in the same shell iff exactly one of its coordinates equals +ks and the others lie in [-ks, ks-1]
   const int a = -k1, b = -k2, c3 = -k3;
   const int np = (a == ks) + (b == ks) + (c3 == ks);
