@@ -21,7 +21,9 @@
 #include <cmath>
 #include <type_traits>
 #include <cooperative_groups.h>
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstdlib>
+#include <cstring>
 #include "gx_common.cuh"
 #include "fft_core.cuh"
 
@@ -157,16 +159,31 @@ __device__ __forceinline__ void cluster_arrive_relaxed_after(float dep) {
 
 // Persistent: cluster `cid` of `nclusters` walks the tiles cid, cid + nclusters, ...; the loads of the next tile are in
 // flight (cp.async into the other half of shared memory) while the current one is transformed.
-template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
+// TMA = true: the CTA's tile -- R rows at stride CL lines x TC columns, 128-byte rows -- is fetched by ONE thread with a
+// tiled tensor-map copy (cp.async.bulk.tensor, UTMALDG in SASS) completing on an mbarrier, instead of E cp.async per thread
+// with their 64-bit address arithmetic. The tensor map views the matrix as [column][q = line mod CL][j = line / CL]([batch]), so
+// the strided row set of CTA q is the dense box {TC, 1, R} at (column, q, 0). Columns past the end are zero-filled by the
+// TMA unit. Used for plain (not exchange-layout) sources whose strides are multiples of 16 bytes.
+template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp, bool TMA = false>
 __global__ void __launch_bounds__(ColsCfg<T, N, CL, TC, SEL>::threads, MINB)
 fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int nclusters, const cplx<T> *__restrict__ twR,
-                const cplx<T> *__restrict__ twN, LoadOp lop, const __grid_constant__ StoreOp sop) {
+                const cplx<T> *__restrict__ twN, LoadOp lop, const __grid_constant__ StoreOp sop,
+                const __grid_constant__ CUtensorMap tmap) {
   using C = cplx<T>;
   using Cfg = ColsCfg<T, N, CL, TC, SEL>;
   using B = BlockFFT<T, Cfg::R, DIR, TC, Cfg::SEL>;
   constexpr int R = Cfg::R, E = B::E, P = B::P;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert(!TMA || Cfg::NBUF == 1, "the TMA form is single-buffered");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
+  __shared__ __align__(8) unsigned long long tma_bar;
+  unsigned tma_phase = 0;
+  if constexpr (TMA) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&tma_bar)), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
 
   const int c = threadIdx.x % TC;
   const int t = threadIdx.x / TC;
@@ -183,6 +200,26 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
 
   auto issue = [&](long tile, C *buf) {
     const int batch = (int) (tile / g.tiles_per_batch);
+    if constexpr (TMA) {
+      if (threadIdx.x == 0) {
+        constexpr int RB = R > 256 ? 256 : R;                       // a box dimension holds at most 256 elements
+        const unsigned mb = smem_addr_u32(&tma_bar);
+        const int c0 = (int) ((tile % g.tiles_per_batch) * TC) * 2;  // innermost dimension counts reals
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched through the generic proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned) (R * TC * sizeof(C))) : "memory");
+#pragma unroll
+        for (int j0 = 0; j0 < R; j0 += RB) {
+          const unsigned dstp = smem_addr_u32(buf + (size_t) j0 * TC);
+          if (std::is_same<Pass, PassY>::value)
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                         ::"r"(dstp), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(c0), "r"(q), "r"(j0), "r"(batch), "r"(mb) : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(dstp), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(c0), "r"(q), "r"(j0), "r"(mb) : "memory");
+        }
+      }
+      return;
+    }
     const long col = (tile % g.tiles_per_batch) * TC + c;
     const bool active = col < g.ncols;
     const C *p = src + ((long) batch * g.src.batch_stride + (active ? col : 0));
@@ -192,6 +229,17 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
       cp_async_elem<C>(buf + (t + i * P) * TC + c, p + g.src.off(row), active);
     }
     cp_async_commit();
+  };
+  auto wait_tile = [&]() {
+    if constexpr (TMA) {
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_addr_u32(&tma_bar)), "r"(tma_phase) : "memory");
+      tma_phase ^= 1u;
+    } else {
+      cp_async_wait<0>();
+    }
   };
 
   long tile = cid;
@@ -204,7 +252,7 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
       else cp_async_wait<0>();
     } else {
       issue(tile, buf);
-      cp_async_wait<0>();
+      wait_tile();
     }
 
     const int batch = (int) (tile / g.tiles_per_batch);
@@ -287,13 +335,57 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
 // a side stream it leaves the SMs to the HBM-bound passes of the previous component running beside it.
 inline int &cols_cluster_limit() { static int v = 0; return v; }
 
-template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
-int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, LoadOp lop, StoreOp sop, cudaStream_t st) {
+// ---- tensor maps for the TMA form of the column passes ---------------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (TensorMapEncodeFn) p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// [reals of a row of columns][q = line mod CL][j = line / CL]([batch]); false if the layout does not qualify
+template <typename T, class Pass>
+bool make_cols_tensor_map(CUtensorMap *tm, const cplx<T> *src, const ColGeo &g, int nbatch, int CL, int R, int TC) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc || g.src.blk_shift != 30 || ((size_t) src & 15)) return false;
+  const size_t esz = sizeof(cplx<T>);
+  const cuuint64_t line_b = (cuuint64_t) g.src.line_stride * esz, batch_b = (cuuint64_t) g.src.batch_stride * esz;
+  if ((line_b & 15) || (std::is_same<Pass, PassY>::value && (batch_b & 15))) return false;
+  const cuuint32_t rb = R > 256 ? 256 : R;
+  cuuint64_t dims[4] = {(cuuint64_t) g.ncols * 2, (cuuint64_t) CL, (cuuint64_t) R, (cuuint64_t) nbatch};
+  cuuint64_t strides[3] = {line_b, line_b * (cuuint64_t) CL, batch_b};
+  cuuint32_t box[4] = {(cuuint32_t) TC * 2, 1, rb, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const int rank = std::is_same<Pass, PassY>::value ? 4 : 3;
+  const CUresult rc = enc(tm, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t) rank,
+                          (void *) src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
+inline bool cols_tma_enabled() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("GX_COLS_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
+template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp, bool TMA>
+int launch_cols_variant(const cplx<T> *src, cplx<T> *dst, const ColGeo &g, long ntiles, LoadOp lop, StoreOp sop,
+                        const CUtensorMap &tmap, cudaStream_t st) {
   using Cfg = ColsCfg<T, N, CL, TC, SEL>;
-  g.tiles_per_batch = (int) ((g.ncols + TC - 1) / TC);
-  const long ntiles = (long) g.tiles_per_batch * nbatch;
-  if (ntiles <= 0) return 0;
-  auto kern = fft_cols_kernel<T, N, CL, TC, MINB, SEL, DIR, Pass, LoadOp, StoreOp>;
+  auto kern = fft_cols_kernel<T, N, CL, TC, MINB, SEL, DIR, Pass, LoadOp, StoreOp, TMA>;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(Cfg::threads);
   cfg.dynamicSmemBytes = Cfg::smem;
@@ -327,8 +419,8 @@ int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, Load
     if (max_clusters < 1) return fail("fft_cols: kernel cannot be resident (cluster occupancy query returned 0)");
     max_clusters_dev = dev;
     if (getenv("GX_DEBUG"))
-      fprintf(stderr, "[gx] fft_cols<N=%d,CL=%d,TC=%d,%zu-byte elems>: %d resident clusters, %zu KB smem/CTA, %d threads\n", N, CL,
-              TC, sizeof(cplx<T>), max_clusters, Cfg::smem / 1024, Cfg::threads);
+      fprintf(stderr, "[gx] fft_cols<N=%d,CL=%d,TC=%d,%zu-byte elems,tma=%d>: %d resident clusters, %zu KB smem/CTA, %d threads\n", N,
+              CL, TC, sizeof(cplx<T>), (int) TMA, max_clusters, Cfg::smem / 1024, Cfg::threads);
   }
   int nclusters = (int) ((ntiles < max_clusters || Cfg::NBUF == 1) ? ntiles : max_clusters);
   if (cols_cluster_limit() > 0 && nclusters > cols_cluster_limit()) nclusters = cols_cluster_limit();
@@ -336,10 +428,25 @@ int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, Load
   const char *tname = std::is_same<Pass, PassY>::value ? "fft_cols_y" : "fft_cols_x";
   GX_TIMED(tname, st);
   const cplx<T> *twR = twiddle_table<T>(Cfg::R), *twN = twiddle_table<T>(N);
-  GX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, src, dst, g, ntiles, nclusters, twR, twN, lop, sop));
+  GX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, src, dst, g, ntiles, nclusters, twR, twN, lop, sop, tmap));
   count_launch();
   GX_LAUNCH_CHECK();
   return 0;
+}
+
+template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
+int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, LoadOp lop, StoreOp sop, cudaStream_t st) {
+  using Cfg = ColsCfg<T, N, CL, TC, SEL>;
+  g.tiles_per_batch = (int) ((g.ncols + TC - 1) / TC);
+  const long ntiles = (long) g.tiles_per_batch * nbatch;
+  if (ntiles <= 0) return 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if constexpr (N >= 512 && Cfg::NBUF == 1) {
+    if (cols_tma_enabled() && make_cols_tensor_map<T, Pass>(&tmap, src, g, nbatch, CL, Cfg::R, TC))
+      return launch_cols_variant<T, N, CL, TC, MINB, SEL, DIR, Pass, LoadOp, StoreOp, true>(src, dst, g, ntiles, lop, sop, tmap, st);
+  }
+  return launch_cols_variant<T, N, CL, TC, MINB, SEL, DIR, Pass, LoadOp, StoreOp, false>(src, dst, g, ntiles, lop, sop, tmap, st);
 }
 
 template <class Pass> inline ColGeo make_col_geo(int n0, int n1, int nc, int &nbatch) {
@@ -386,7 +493,7 @@ fft_rows_r2c_kernel(T *data, long nrows, const cplx<T> *__restrict__ twM, const 
   using Cfg = RowsCfg<T, N>;
   using B = BlockFFT<T, Cfg::M, -1>;
   constexpr int M = Cfg::M, E = B::E, P = B::P;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
   const int l = threadIdx.x / P, t = threadIdx.x % P;
   const long row = (long) blockIdx.x * Cfg::LR + l;
@@ -443,7 +550,7 @@ fft_rows_c2r_kernel(const T *data, long row0, long nrows, const cplx<T> *__restr
   using Cfg = RowsCfg<T, N>;
   using B = BlockFFT<T, Cfg::M, 1>;
   constexpr int M = Cfg::M, E = B::E, P = B::P;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
   const int l = threadIdx.x / P, t = threadIdx.x % P;
   const long row = row0 + (long) blockIdx.x * Cfg::LR + l;
@@ -498,7 +605,7 @@ fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__r
   using Cfg = RowsDitCfg<T, N>;
   using D = typename Cfg::D;
   constexpr int M = Cfg::M, P = Cfg::P;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   C *smem = reinterpret_cast<C *>(smem_raw);
   const int l = threadIdx.x / P, t = threadIdx.x % P;
   const long first = row0 + (long) blockIdx.x * Cfg::LR;
