@@ -375,9 +375,12 @@ bool make_cols_tensor_map(CUtensorMap *tm, const cplx<T> *src, const ColGeo &g, 
   return rc == CUDA_SUCCESS;
 }
 
+// Measured at 2048^3 f64 (profiles/r2s13_cols_tma.txt): x-pass 85.2 ms against 78.7 with cp.async, y-pass 133.9 against 126.7 --
+// a box of 256 rows of 128 bytes is 256 short row fetches for the TMA unit, the same finding as round 1's per-row bulk copies.
+// Correct (the GPU suite and the cuFFT cross-check pass with it), kept for wider tiles, off unless GX_COLS_TMA=1.
 inline bool cols_tma_enabled() {
   static int on = -1;
-  if (on < 0) { const char *e = getenv("GX_COLS_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
+  if (on < 0) { const char *e = getenv("GX_COLS_TMA"); on = (e && e[0] == '1') ? 1 : 0; }
   return on != 0;
 }
 
