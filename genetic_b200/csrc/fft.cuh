@@ -93,6 +93,7 @@ inline LineMap blocked_map(long line_stride, long batch_stride, int rows_per_blo
 }
 
 struct ColGeo {
+  int prefetch_tiles;  // > 0: every CTA also prefetches its rows of tile (tile + prefetch_tiles) into L2
   long ncols;          // columns per batch
   LineMap src, dst;
   int tiles_per_batch;
@@ -252,6 +253,22 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
       else cp_async_wait<0>();
     } else {
       issue(tile, buf);
+      if (g.prefetch_tiles > 0) {
+        // L2 prefetch of the rows this CTA position will load one wave of clusters later: a CTA keeps 32 KB in flight only
+        // while it waits for its tile (about a third of its life), and a second shared-memory buffer costs residency
+        // (measured slower, round 1); a prefetch costs nothing but the instruction and turns the later tile's DRAM latency
+        // into an L2 hit. The bytes still cross the DRAM interface once.
+        const long ptile = tile + g.prefetch_tiles;
+        if (ptile < ntiles) {
+          const int pbatch = (int) (ptile / g.tiles_per_batch);
+          const long pcol = (ptile % g.tiles_per_batch) * TC;
+          const C *pp = src + ((long) pbatch * g.src.batch_stride + pcol);
+          for (int r = threadIdx.x; r < R; r += Cfg::threads) {
+            const int row = (CL > 1) ? q + CL * r : r;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + g.src.off(row)));
+          }
+        }
+      }
       wait_tile();
     }
 
@@ -443,6 +460,11 @@ int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, Load
   g.tiles_per_batch = (int) ((g.ncols + TC - 1) / TC);
   const long ntiles = (long) g.tiles_per_batch * nbatch;
   if (ntiles <= 0) return 0;
+  {
+    static int dist = -2;  // GX_COLS_PREFETCH: prefetch distance in tiles (0: off)
+    if (dist == -2) { const char *e = getenv("GX_COLS_PREFETCH"); dist = e ? atoi(e) : 0; }
+    g.prefetch_tiles = (N >= 512 && g.src.blk_shift == 30) ? dist : 0;
+  }
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if constexpr (N >= 512 && Cfg::NBUF == 1) {
@@ -603,7 +625,7 @@ template <typename T, int N> struct RowsDitCfg {
 template <typename T, int N, class Store, bool TMA>
 __global__ void __launch_bounds__(RowsDitCfg<T, N>::threads, RowsDitCfg<T, N>::MINB)
 fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__restrict__ twM,
-                        const cplx<T> *__restrict__ twN, Store store) {
+                        const cplx<T> *__restrict__ twN, Store store, int prefetch_ctas) {
   using C = cplx<T>;
   using Cfg = RowsDitCfg<T, N>;
   using D = typename Cfg::D;
@@ -635,6 +657,12 @@ fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__r
                          smem_addr_u32(smem + (size_t) r * Cfg::pitch)),
                      "l"(data + (first + r) * (long) (N + 2)), "r"(row_bytes), "r"(mb)
                      : "memory");
+      if (prefetch_ctas > 0) {  // the rows of the CTA that will run about one wave later, into L2
+        const long pf = first + (long) prefetch_ctas * Cfg::LR;
+        for (int r = 0; r < Cfg::LR; ++r)
+          if (pf + r < row0 + nrows)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(data + (pf + r) * (long) (N + 2)), "r"(row_bytes) : "memory");
+      }
     }
     if (!active) {
 #pragma unroll
@@ -710,6 +738,8 @@ int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStrea
       static int tma = -1;  // GX_ROWS_TMA=0: stage the rows through registers (A/B switch)
       if (tma < 0) { const char *e = getenv("GX_ROWS_TMA"); tma = (e && e[0] == '0') ? 0 : 1; }
       const bool use_tma = sizeof(T) == 8 && tma && ((size_t) data % 16 == 0);
+      static int pf = -2;   // GX_ROWS_PREFETCH: L2 prefetch distance in CTAs (0: off)
+      if (pf == -2) { const char *e = getenv("GX_ROWS_PREFETCH"); pf = e ? atoi(e) : 0; }
       const long grid = (nrows + Cfg::LR - 1) / Cfg::LR;
       if (grid <= 0) return 0;
       GX_TIMED("fft_rows_c2r", st);
@@ -718,7 +748,7 @@ int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStrea
           auto kern = fft_rows_c2r_dit_kernel<T, N, Store, true>;
           if (Cfg::smem > 48 * 1024)
             GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
-          kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store);
+          kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store, pf);
           count_launch();
           GX_LAUNCH_CHECK();
           return 0;
@@ -727,7 +757,7 @@ int launch_rows_c2r(const T *data, long row0, long nrows, Store store, cudaStrea
       auto kern = fft_rows_c2r_dit_kernel<T, N, Store, false>;
       if (Cfg::smem > 48 * 1024)
         GX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::smem));
-      kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store);
+      kern<<<(unsigned) grid, Cfg::threads, Cfg::smem, st>>>(data, row0, nrows, twiddle_table<T>(N / 2), twiddle_table<T>(N), store, 0);
       count_launch();
       GX_LAUNCH_CHECK();
       return 0;
