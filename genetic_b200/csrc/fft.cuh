@@ -193,11 +193,16 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
   const long cid = blockIdx.x / CL;
   C *twl = smem + Cfg::NBUF * (R * TC);  // W_R^j
   C *twc = twl + R;              // W_N^(q j)
-  for (int i = threadIdx.x; i < R; i += blockDim.x) {
-    twl[i] = twR[i];
-    if constexpr (CL > 1) twc[i] = twN[q * i];
-  }
-  __syncthreads();
+  // (the private twiddle copies are filled AFTER the first tile's loads have been issued, further down: the fill is an L2
+  // round trip plus a CTA barrier, and with one tile per CTA it used to sit in front of every tile's DRAM latency)
+  auto fill_twiddles = [&]() {
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+      twl[i] = twR[i];
+      if constexpr (CL > 1) twc[i] = twN[q * i];
+    }
+    __syncthreads();
+  };
+  if constexpr (TMA) __syncthreads();  // the mbarrier initialisation above must be visible before its first use
 
   auto issue = [&](long tile, C *buf) {
     const int batch = (int) (tile / g.tiles_per_batch);
@@ -244,7 +249,8 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
   };
 
   long tile = cid;
-  if (Cfg::NBUF == 2 && tile < ntiles) issue(tile, smem);
+  if (tile < ntiles) issue(tile, smem);  // first tile: in flight while the twiddle copies are filled
+  fill_twiddles();
   for (int it = 0; tile < ntiles; tile += nclusters, ++it) {
     C *buf = smem + (size_t) (Cfg::NBUF == 2 ? (it & 1) : 0) * (R * TC);
     if constexpr (Cfg::NBUF == 2) {
@@ -252,12 +258,11 @@ fft_cols_kernel(const cplx<T> *src, cplx<T> *dst, ColGeo g, long ntiles, int ncl
       if (next < ntiles) { issue(next, smem + (size_t) ((it + 1) & 1) * (R * TC)); cp_async_wait<1>(); }
       else cp_async_wait<0>();
     } else {
-      issue(tile, buf);
+      if (it > 0) issue(tile, buf);
       if (g.prefetch_tiles > 0) {
-        // L2 prefetch of the rows this CTA position will load one wave of clusters later: a CTA keeps 32 KB in flight only
-        // while it waits for its tile (about a third of its life), and a second shared-memory buffer costs residency
-        // (measured slower, round 1); a prefetch costs nothing but the instruction and turns the later tile's DRAM latency
-        // into an L2 hit. The bytes still cross the DRAM interface once.
+        // L2 prefetch of the rows this CTA position will load one wave of clusters later (GX_COLS_PREFETCH=<tiles>). Measured
+        // at 2048^3 (profiles/r2s15_prefetch.txt): the x-pass goes from 76 to 92 ms and the y-pass from 124 to 128 at any
+        // distance -- the hint competes with the demand loads instead of hiding their latency. Off by default.
         const long ptile = tile + g.prefetch_tiles;
         if (ptile < ntiles) {
           const int pbatch = (int) (ptile / g.tiles_per_batch);
@@ -643,12 +648,9 @@ fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__r
     const unsigned mb = smem_addr_u32(&mbar);
     constexpr unsigned row_bytes = (unsigned) ((M + 1) * sizeof(C));
     static_assert(row_bytes % 16 == 0, "bulk copies move multiples of 16 bytes");
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {  // initialise and issue at once: the other threads only need the barrier when they wait on it
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
       const long left = row0 + nrows - first;
       const int nact = (int) (left < (long) Cfg::LR ? left : (long) Cfg::LR);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(row_bytes * (unsigned) nact) : "memory");
@@ -669,6 +671,7 @@ fft_rows_c2r_dit_kernel(const T *data, long row0, long nrows, const cplx<T> *__r
       for (int i = 0; i < 16; ++i) line[t + i * P] = mk<T>(0, 0);
       if (t == 0) line[M] = mk<T>(0, 0);
     }
+    __syncthreads();  // the initialised barrier is visible to every thread
     unsigned done = 0;
     while (!done)
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
