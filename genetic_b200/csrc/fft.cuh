@@ -458,6 +458,14 @@ int launch_cols_variant(const cplx<T> *src, cplx<T> *dst, const ColGeo &g, long 
 template <typename T, int N, int CL, int TC, int MINB, int SEL, int DIR, class Pass, class LoadOp, class StoreOp>
 int launch_cols_cfg(const cplx<T> *src, cplx<T> *dst, ColGeo g, int nbatch, LoadOp lop, StoreOp sop, cudaStream_t st) {
   using Cfg = ColsCfg<T, N, CL, TC, SEL>;
+  if constexpr (N == 4096 && CL == 8) {
+    // 4096-point lines: the portable cluster size 8 means 512 rows per CTA -- 64 KB tiles, up to 1024 threads, one CTA per SM.
+    // A (non-portable) cluster of 16 keeps the 2048^3 shape: 256 rows, 32 KB tiles, 4-5 CTAs per SM. GX_COLS4096_CL8=1: old form.
+    static int cl16 = -1;
+    if (cl16 < 0) { const char *e = getenv("GX_COLS4096_CL8"); cl16 = (e && e[0] == '1') ? 0 : 1; }
+    if (cl16)
+      return launch_cols_cfg<T, N, 16, TC, (sizeof(T) == 8 ? 5 : 4), SEL, DIR, Pass, LoadOp, StoreOp>(src, dst, g, nbatch, lop, sop, st);
+  }
   g.tiles_per_batch = (int) ((g.ncols + TC - 1) / TC);
   const long ntiles = (long) g.tiles_per_batch * nbatch;
   if (ntiles <= 0) return 0;

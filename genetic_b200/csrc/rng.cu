@@ -1102,7 +1102,14 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
   const bool pipelined = world > 1 && pipe_env && scratch_bytes / 2 >= (size_t) largest * per_chunk;
   const int nslots = pipelined ? 2 : 1;
   const size_t slot_bytes = (scratch_bytes / nslots) & ~(size_t) 255;
-  const long long cap_chunks = (long long) (slot_bytes / per_chunk);
+  long long cap_chunks = (long long) (slot_bytes / per_chunk);
+  {
+    // equal batches: with the capacity as the only limit a 2048^3 draw was two full batches and a 2 % one, whose kernels ran
+    // on a nearly empty GPU
+    const long long nb = (my_chunks + cap_chunks - 1) / cap_chunks;
+    const long long even = (my_chunks + nb - 1) / nb + largest;   // whole shells: allow one shell of slack
+    if (even < cap_chunks) cap_chunks = even;
+  }
   // batches of whole shells
   std::vector<std::pair<int, int>> batches;
   long long max_batch = 0, max_batch_gauss = 0;
