@@ -26,7 +26,9 @@ def _deps():
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    # (fft_variants.cu is a development sweep harness, not part of the C ABI: only built with GX_DEV=1)
+    dev = os.environ.get("GX_DEV", "0") == "1"
+    srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and (dev or f != "fft_variants.cu"))
     hdr_m = _deps()
     jobs = []
     objs = []

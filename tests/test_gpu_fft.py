@@ -128,7 +128,8 @@ def test_transfer_zeldovich_emit_vs_oracle(dtype):
     spec = gb.CAMB(cos, camb_file, "all", dtype)
     assert abs(spec.amplitude / r["camb"].amplitude - 1) < (1e-13 if dtype == np.float64 else 1e-5)
     cov = spec.getPowerSpectrumForGrid(g).getDataVector()
-    assert _rel(cov.real, r["cov"]) < 100 * _tol(dtype) and np.all(cov.imag == 0)
+    # (the spline, exp, log and pow behind C(k) are the device's libm against the host's: measured agreement ~1e-13 in double)
+    assert _rel(cov.real, r["cov"]) < (_tol(dtype) if dtype == np.float64 else 10 * _tol(dtype)) and np.all(cov.imag == 0)
     f = gb.Field(g, r["white"], fourier=True)
     f.applyTransferFunction(spec, 0.5)
     D = f.getDataVector()
@@ -192,6 +193,15 @@ def test_filters_and_unit_variance():
     f = gb.Field(g, A)
     f.enforceUnitVariance()
     assert np.allclose(np.abs(f.getDataVector()[ind]), 1.0, rtol=1e-14)
+    # against the oracle's statement of MultiLevelField::enforceUnitVariance (multilevelfield.hpp:498-510): delta_k / |delta_k|
+    U = f.getDataVector()
+    ref = A / np.abs(A)
+    assert np.abs(U[ind] - ref[ind]).max() <= 4 * np.finfo(np.float64).eps
+    Z = A.copy()
+    Z[3, 5, 2] = 0.0                                    # 0 stays 0
+    f = gb.Field(g, Z)
+    f.enforceUnitVariance()
+    assert f.getDataVector()[3, 5, 2] == 0
 
 
 def test_errors_are_raised():
