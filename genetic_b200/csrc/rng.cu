@@ -795,6 +795,7 @@ struct GenParams {
   StagedTail *tails;
   unsigned int *tail_count;
   unsigned int tail_cap;
+  int f64_share;           // of every 8 consecutive CTAs, this many run the generator on the FP64 pipe (rng_core.cuh StateF64)
 };
 
 struct SmemColumn {  // column tx of a [slots][kThreads] shared array: conflict-free per-thread storage
@@ -850,9 +851,12 @@ __global__ void __launch_bounds__(kThreads, MINB) rng_gen_kernel(GenParams P) {
   DevTailSink sink{P.tails, P.tail_count, in_range ? P.tail_cap : 0u, rel};
   ChunkFn f;
   ListMeta m;
-  gen_chunk<FMA>(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x},
-                 SmemColumn{sinc, (int) threadIdx.x}, s_k, s_w, s_y,
-                 P.stage + (size_t) rel * kChunkStage, f, m, sink);
+  if ((int) (blockIdx.x & 7u) < P.f64_share)
+    gen_chunk<2>(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x},
+                 SmemColumn{sinc, (int) threadIdx.x}, s_k, s_w, s_y, P.stage + (size_t) rel * kChunkStage, f, m, sink);
+  else
+    gen_chunk<FMA ? 1 : 0>(sd, q == 0, st, SmemColumn{ring, (int) threadIdx.x}, SmemColumn{sbuf, (int) threadIdx.x},
+                           SmemColumn{sinc, (int) threadIdx.x}, s_k, s_w, s_y, P.stage + (size_t) rel * kChunkStage, f, m, sink);
   if (in_range) { P.fn[rel] = f; P.meta[rel] = m; }
 }
 
@@ -1206,6 +1210,11 @@ static int noise_parallel_staged(T *field, int n, unsigned long seed, int revers
     GenParams G;
     G.streams = d_streams; G.n_streams = ns; G.first = c0; G.count = cnt; G.jump = g_jump; G.fn = d_fn[0]; G.meta = d_meta;
     G.stage = (uint32_t *) scratch_b; G.tails = staged_b; G.tail_count = d_staged_count; G.tail_cap = staged_cap;
+    {
+      static int share = -1;
+      if (share < 0) { const char *e = getenv("GX_RNG_F64_SHARE"); share = e ? atoi(e) : 0; }
+      G.f64_share = share;
+    }
     {
       GX_TIMED("rng_gen", cg);
       const int grid = (cnt + kThreads - 1) / kThreads;

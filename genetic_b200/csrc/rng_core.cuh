@@ -279,6 +279,42 @@ struct StateCC {
     return (j & 1) ? (hi[i] >> 8) : (((hi[i] & 0xFFu) << 16) | (lo[i] >> 16));
   }
 };
+// The same generator on the FP64 pipe. B200's integer (alu) pipe and its FP64 pipe are equally wide (64 lanes per SM; DFMA
+// peak measured 63.7 per clock per SM, profiles/r2s19_fp64_peak.txt) and the noise generation is bound by the alu pipe alone
+// (ncu: alu 78 %, fp64 3 %). GSL itself runs ranlxs in doubles; a word is an integer below 2^48 held exactly in a double:
+//     y = (x_j - x_i) - c;   c' = (y < 0) ? 1.0 : 0.0;   x_i = c' * 2^48 + y
+// = 3 DADD/DFMA + 1 DSETP on the FP64 pipe and ONE alu instruction (the select that forms the high word of c') per word
+// step, against 3 alu instructions in the carry-flag form. A fraction of the kernel's CTAs runs this form so that both pipes
+// work (rng.cu GenParams::f64_share).
+struct StateF64 {
+  double x[12], c;
+  __device__ __forceinline__ void load(const uint64_t (&w)[12], uint32_t carry) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = (double) w[i];
+    c = carry ? 1.0 : 0.0;
+  }
+  __device__ __forceinline__ static void step(double &xi, double xj, double &c) {
+    const double y = (xj - xi) - c;
+    c = __hiloint2double((y < 0.0) ? 0x3FF00000 : 0, 0);
+    xi = fma(c, 281474976710656.0, y);
+  }
+  __device__ __forceinline__ void advance() {
+#pragma unroll 3
+    for (int r = 0; r < 33; ++r) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) step(x[i], x[(i + 7) % 12], c);
+    }
+    double x0 = x[0];
+    step(x0, x[7], c);
+#pragma unroll
+    for (int i = 0; i < 11; ++i) x[i] = x[i + 1];
+    x[11] = x0;
+  }
+  __device__ __forceinline__ uint32_t out(int j) const {
+    const unsigned long long u = (unsigned long long) x[j >> 1];
+    return (j & 1) ? (uint32_t) (u >> 24) : (uint32_t) (u & 0xFFFFFFull);
+  }
+};
 #endif
 
 // increment_state of ranlxs2: 397 = 33*12 + 1 word steps, then rotate so x[0] is the oldest again.

@@ -22,6 +22,7 @@
 // Everything here is __host__ __device__: tests/host/rng_staged_host.cu runs the same code on the CPU against the oracle.
 #pragma once
 #include "rng_core.cuh"
+#include <type_traits>
 
 namespace gx {
 namespace rng {
@@ -107,12 +108,16 @@ GX_HD double unpack_draw(uint32_t e, const double *wtab) {
 #define GX_ANY(x) (x)
 #endif
 
-// generator state of a chunk thread: (lo, hi) register form on the device, the plain words on the host
-template <bool FMA> struct GenState {
+// generator state of a chunk thread. Device: MODE 0 / 1 the (lo, hi) carry-flag form (mask on the alu / fma pipe), MODE 2 the
+// FP64 form; host: the plain words
+template <int MODE> struct GenState {
 #ifdef __CUDA_ARCH__
-  StateCC s;
+  typename std::conditional<MODE == 2, StateF64, StateCC>::type s;
   GX_HD void load(const State &st) { s.load(st.x, st.c); }
-  GX_HD void advance() { s.template advance<FMA>(); }
+  GX_HD void advance() {
+    if constexpr (MODE == 2) s.advance();
+    else s.template advance<MODE == 1>();
+  }
   GX_HD uint32_t out(int j) const { return s.out(j); }
 #else
   State s;
@@ -202,7 +207,7 @@ GX_HD void parse_hypothesis(bool live, int &p, int &c, int limit, Ring ring, Buf
 // plain arrays on the host); `stage` is the
 // chunk's kChunkStage words; sink.push(list, idx, u1, positive) records accepted tail draws. Warp-collective on the
 // device: every lane of the warp must call it.
-template <bool FMA, class Ring, class Buf, class Inc, class Sink>
+template <int MODE, class Ring, class Buf, class Inc, class Sink>
 GX_HD void gen_chunk(const StreamDesc &sd, bool first, const State &st0, Ring ring, Buf buf, Inc inc, const unsigned int *ktab,
                      const double *wtab, const double *ytab, uint32_t *stage, ChunkFn &f, ListMeta &meta, Sink &sink) {
   int p0, p1 = 1, p2 = 2, p3 = 3;          // positions of the four entry hypotheses
@@ -211,7 +216,7 @@ GX_HD void gen_chunk(const StreamDesc &sd, bool first, const State &st0, Ring ri
   int j1 = 0, j2 = 0, j3 = 0;              // index in that list at which its path continues
   p0 = first ? sd.entry0 : 0;
   if (first) rep1 = rep2 = rep3 = 0;       // a stream's first chunk starts at a known position: one hypothesis
-  GenState<FMA> gs;
+  GenState<MODE> gs;
   gs.load(st0);
 
   for (int bi = 0; bi <= kBc; ++bi) {

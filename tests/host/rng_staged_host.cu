@@ -60,7 +60,7 @@ int host_staged_noise(int n, unsigned long seed, int reverse, double *out, unsig
       X = modmul(X, jump);
       uint32_t ring[kRing], buf[4], inc[kIncCap];
       HostSink sink{&tails, chunk};
-      gen_chunk<false>(sd[s], q == 0, st, HostRing{ring}, HostRing{buf}, HostRing{inc}, gx_zig_ktab, gx_zig_wtab, gx_zig_ytab,
+      gen_chunk<0>(sd[s], q == 0, st, HostRing{ring}, HostRing{buf}, HostRing{inc}, gx_zig_ktab, gx_zig_wtab, gx_zig_ytab,
                 stage.data() + (size_t) chunk * kChunkStage, fn[chunk], meta[chunk], sink);
       for (int e = 1; e < 4; ++e) {
         if (q > 0 && meta[chunk].rep[e] > 0) ++multi_hop;
