@@ -313,6 +313,70 @@ static int zeldovich_fourier_t(const void *delta, void *psi, int n, double L, in
 }
 
 namespace gx {
+// ---- cosmology::dumpPowerSpectrum (cosmology/parameters.hpp:112-205): the binning reduction on the device ------------------
+// The reference visits every (ix, iy, iz) in [-n/2, n/2]^3 through getFourierCoefficient -- each stored slot (a, b, c >= 0)
+// once for +iz and once (as the conjugate, same modulus) for -iz, and twice more per index that sits on the Nyquist plane
+// (ix = -n/2 and +n/2 are the same slot) -- and adds |delta_k|^2, Re C(k), k and 1 to the logarithmic bin of
+// k = sqrt(ix^2 + iy^2 + iz^2) * 2 pi / L if kmin <= k < kmax. Here: one thread per stored slot with that multiplicity as its
+// weight, bins in shared memory per CTA, double atomics into the result. bins[4][nbins] = count, sum k, sum |delta|^2, sum C.
+template <typename T>
+__global__ void ps_bins_kernel(const cplx<T> *f, const cplx<T> *cov, int n, T kw, T kmin, T kmax, T inv_dklog, int nbins,
+                               double *bins) {
+  extern __shared__ double sb[];  // [4][nbins]
+  for (int i = threadIdx.x; i < 4 * nbins; i += blockDim.x) sb[i] = 0.0;
+  __syncthreads();
+  const int h = n >> 1, nc = h + 1;
+  const long rows = (long) n * n;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int a = (int) (row / n), b = (int) (row % n);
+    const int sa = signed_mode(a, n), sb2 = signed_mode(b, n);
+    const int wab = (a == h ? 2 : 1) * (b == h ? 2 : 1);
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+      const int m = sa * sa + sb2 * sb2 + c * c;
+      const T kfft = (T) sqrt((double) m);
+      const T k = kfft * kw;
+      if (!(k >= kmin && k < kmax)) continue;
+      const int idx = (int) (inv_dklog * log10(k / kmin));
+      if (idx < 0 || idx >= nbins) continue;
+      const double w = (double) (wab * (c == 0 ? 1 : 2));
+      const cplx<T> v = f[row * nc + c];
+      T vabs = (T) hypot((double) v.x, (double) v.y);  // std::abs(complex)
+      vabs *= vabs;
+      atomicAdd(&sb[idx], w);
+      atomicAdd(&sb[nbins + idx], w * (double) k);
+      atomicAdd(&sb[2 * nbins + idx], w * (double) vabs);
+      if (cov) atomicAdd(&sb[3 * nbins + idx], w * (double) cov[row * nc + c].x);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * nbins; i += blockDim.x)
+    if (sb[i] != 0.0) atomicAdd(&bins[i], sb[i]);
+}
+
+template <typename T>
+static int power_spectrum_bins_t(void *field, void *cov, int n, double L, int nbins, double *host_bins, cudaStream_t st) {
+  // field.ensureFourierModesAreMirrored(); P0.ensureFourierModesAreMirrored();  (:121-122)
+  if (int rc = mirror<T>((T *) field, n, st)) return rc;
+  if (cov) if (int rc = mirror<T>((T *) cov, n, st)) return rc;
+  const T boxLength = (T) L;
+  const T kmax = (T) M_PI / boxLength * (T) n, kmin = 2.0f * (T) M_PI / boxLength;
+  const T dklog = (T) log10((double) (kmax / kmin)) / (T) nbins, kw = 2.0f * (T) M_PI / boxLength;
+  double *d_bins = nullptr;
+  GX_CUDA_CHECK(cudaMalloc(&d_bins, sizeof(double) * 4 * nbins));
+  GX_CUDA_CHECK(cudaMemsetAsync(d_bins, 0, sizeof(double) * 4 * nbins, st));
+  const long rows = (long) n * n;
+  const int grid = (int) (rows < 148 * 8 ? rows : 148 * 8);
+  ps_bins_kernel<T><<<grid, 256, sizeof(double) * 4 * nbins, st>>>((const cplx<T> *) field, (const cplx<T> *) cov, n, kw, kmin, kmax,
+                                                                 (T) (1.0f / dklog), nbins, d_bins);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_bins, d_bins, sizeof(double) * 4 * nbins, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_bins);
+  if (e != cudaSuccess) return fail(std::string("gx_power_spectrum_bins: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 void release_spectral_workspace() {
   if (g_transfer_tab) { cudaDeviceSynchronize(); cudaFree(g_transfer_tab); }
   g_transfer_tab = nullptr; g_transfer_tab_bytes = 0;
@@ -352,6 +416,14 @@ extern "C" {
 int gx_mirror(void *field, int n, int dtype, void *stream) {
   if (check_n(n)) return 1;
   GX_DISPATCH(dtype, gx::mirror<T>((T *) field, n, (cudaStream_t) stream));
+}
+
+int gx_power_spectrum_bins(void *field, void *cov_field, int n, int dtype, double grid_length, int nbins, double *host_bins,
+                           void *stream) {
+  if (check_n(n)) return 1;
+  if (nbins < 1 || nbins > 256) return fail("gx_power_spectrum_bins: 1 <= nbins <= 256");
+  if (!field || !host_bins) return fail("gx_power_spectrum_bins: null argument");
+  GX_DISPATCH(dtype, power_spectrum_bins_t<T>(field, cov_field, n, grid_length, nbins, host_bins, (cudaStream_t) stream));
 }
 
 int gx_covariance_field(void *out_field, int n, int dtype, double grid_length, const gx_spectrum *s, void *stream) {

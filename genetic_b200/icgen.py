@@ -9,6 +9,7 @@ holds only the state machine of ICGenerator. Commands outside the accelerated pa
 of being silently ignored: grafic / HDF5 / swift output, masks,
 baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
 """
+import ctypes as C
 import math
 import os
 import sys
@@ -768,7 +769,10 @@ class ICGenerator:
         f = self.outputField.getFieldForLevel(level)
         f.toFourier()
         cov = self.context.getCovariance(level, GM.ALL).getPowerSpectrumForGrid(f.grid)
-        OUT.dumpPowerSpectrum(f.getDataVector(), cov.getDataVector(), f.grid, "%s_%d.ps" % (self.getOutputPath(), level))
+        bins = np.zeros((4, 100), dtype=np.float64)        # the binning reduction runs on the device
+        f.lib.gx_power_spectrum_bins(f.ptr, cov.ptr, f.grid.size, f.dt, float(f.grid.thisGridSize), 100,
+                                     bins.ctypes.data_as(C.c_void_p), None)
+        OUT.writePowerSpectrum(bins, f.grid, "%s_%d.ps" % (self.getOutputPath(), level))
 
     def saveTipsyArray(self, filename):
         """ic.hpp:853-862: the overdensity of every particle's cell in mapper order (`dump_tipsy`), a host-side diagnostic."""

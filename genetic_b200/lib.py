@@ -68,6 +68,7 @@ PROTOTYPES = {
     "gx_spectrum_amplitude": (cd, [vp]),
     "gx_spectrum_eval": (cd, [vp, cd]),
     "gx_covariance_field": (ci, [vp, ci, ci, cd, vp, vp]),
+    "gx_power_spectrum_bins": (ci, [vp, vp, ci, ci, cd, ci, vp, vp]),
     "gx_apply_transfer": (ci, [vp, ci, ci, cd, vp, cd, vp]),
     "gx_apply_transfer_field": (ci, [vp, vp, ci, ci, cd, vp]),
     "gx_apply_filter": (ci, [vp, ci, ci, cd, P(FilterFactor), ci, vp]),

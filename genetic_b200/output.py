@@ -200,31 +200,15 @@ def read_gadget(filename):
     return out
 
 
-def dumpPowerSpectrum(field, P0, grid, filename):
-    """cosmology::dumpPowerSpectrum (cosmology/parameters.hpp:112-170), a diagnostic written from the host mirrors of a
-    Fourier-space field and of its covariance C(k) (both [n][n][n/2+1] complex): 100 logarithmic bins between the
-    fundamental and the Nyquist wavenumber, every (ix, iy, iz) in [-n/2, n/2]^3 visited (the +-Nyquist planes twice, as the
-    reference does); columns: bin centre, mean k, mean theory P, mean |delta_k|^2 / norm, count."""
+def writePowerSpectrum(bins, grid, filename, nBins=100):
+    """The text file of cosmology::dumpPowerSpectrum (cosmology/parameters.hpp:172-205) from the per-bin sums the device
+    reduction returns (gx_power_spectrum_bins: count, sum k, sum |delta_k|^2, sum C(k) for 100 logarithmic bins between the
+    fundamental and the Nyquist wavenumber); columns: bin centre, mean k, mean theory P, mean |delta_k|^2 / norm, count."""
     n = grid.size
-    field, P0 = _mirrored(np.asarray(field), n), _mirrored(np.asarray(P0), n)
-    nBins = 100
+    inBin, kbin, Gx, Px = (np.asarray(bins[i], dtype=np.float64) for i in range(4))
     boxLength = float(grid.thisGridSize)
     kmax, kmin = math.pi / boxLength * n, 2.0 * math.pi / boxLength
     dklog, kw = math.log10(kmax / kmin) / nBins, 2.0 * math.pi / boxLength
-    i1 = np.arange(-(n // 2), n // 2 + 1)
-    ix, iy, iz = np.meshgrid(i1, i1, i1, indexing="ij")
-    neg = iz < 0
-    a = np.where(neg, (-ix) % n, ix % n)
-    b = np.where(neg, (-iy) % n, iy % n)
-    c = np.abs(iz)
-    k = np.sqrt((ix * ix + iy * iy + iz * iz).astype(np.float64)) * kw
-    ok = (k >= kmin) & (k < kmax)
-    idx = (1.0 / dklog * np.log10(k[ok] / kmin)).astype(np.int64)
-    vabs = np.abs(np.asarray(field)[a[ok], b[ok], c[ok]]) ** 2
-    Gx = np.bincount(idx, weights=vabs, minlength=nBins)
-    Px = np.bincount(idx, weights=np.asarray(P0)[a[ok], b[ok], c[ok]].real, minlength=nBins)
-    kbin = np.bincount(idx, weights=k[ok], minlength=nBins)
-    inBin = np.bincount(idx, minlength=nBins).astype(np.float64)
     psnorm = 1.0 / ((kw * kw * kw / float(np.float32(2.0 * np.float32(math.pi)) ** np.float32(3.0))) * float(n) ** 3)
     with open(filename, "w") as f:
         for i in range(nBins):
@@ -233,17 +217,6 @@ def dumpPowerSpectrum(field, P0, grid, filename):
                     10. ** (math.log10(kmin) + dklog * (i + 0.5)), kbin[i] / inBin[i], Px[i] / inBin[i] * psnorm,
                     Gx[i] / inBin[i] * psnorm, inBin[i])) + "\n")
 
-
-def _mirrored(F, n):
-    """Field::ensureFourierModesAreMirrored (fourier.hpp:331-357) on a host copy: on the planes kz = 0 and kz = n/2 the
-    slots with kx < 0 (or kx in {0, n/2} and ky < 0) become the conjugates of their partners."""
-    F = F.copy()
-    a = np.arange(n)
-    dep = (a[:, None] > n // 2) | (((a[:, None] == 0) | (a[:, None] == n // 2)) & (a[None, :] > n // 2))
-    ia, ib = np.nonzero(dep)
-    for kz in (0, n // 2):
-        F[ia, ib, kz] = np.conj(F[(-ia) % n, (-ib) % n, kz])
-    return F
 
 
 def saveFieldTipsyArray(filename, values):

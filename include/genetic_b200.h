@@ -101,6 +101,13 @@ int gx_spectrum_create_powerlaw(double amplitude, double ns, int dtype, gx_spect
 int gx_spectrum_destroy(gx_spectrum *s);
 double gx_spectrum_amplitude(const gx_spectrum *s);
 double gx_spectrum_eval(const gx_spectrum *s, double k); /* CAMB::operator()(k), host evaluation */
+/* cosmology::dumpPowerSpectrum (cosmology/parameters.hpp:112-205), the binning reduction of `dump_ps` on the device: both
+   fields are mirrored in place (ensureFourierModesAreMirrored, :121-122), every (ix, iy, iz) in [-n/2, n/2]^3 of the reference's
+   loop is accounted for through the multiplicity of its storage slot, and host_bins[4][nbins] receives per logarithmic k bin:
+   the count, the sum of k, the sum of |delta_k|^2 and the sum of Re C(k) (cov_field may be NULL: zeros). The caller divides
+   by the count and by the grid's power-spectrum normalisation and writes the text file. */
+int gx_power_spectrum_bins(void *field, void *cov_field, int n, int dtype, double grid_length, int nbins, double *host_bins,
+                           void *stream);
 /* getPowerSpectrumForGridUncached (camb.hpp:101-119): materialise C(k) = P(k) * n^3 / L^3 as a Fourier field */
 int gx_covariance_field(void *out_field, int n, int dtype, double grid_length, const gx_spectrum *s, void *stream);
 /* Field::applyTransferFunction (field.hpp:394-412) with the covariance evaluated in-kernel (nothing materialised) */

@@ -205,6 +205,43 @@ class MockLib:
         self.R(p, n)[:] *= self.mem[_addr(mask)][: n ** 3].reshape(n, n, n)
         return 0
 
+    def gx_power_spectrum_bins(self, p, cov, n, dt, L, nbins, out, st):
+        """cosmology::dumpPowerSpectrum's binning (parameters.hpp:112-170) on the host mirrors: every (ix, iy, iz) in
+        [-n/2, n/2]^3 visited as the reference does (the +-Nyquist planes twice)."""
+        import ctypes as C
+        import math
+
+        def mirrored(F):
+            F = F.copy()
+            a = np.arange(n)
+            dep = (a[:, None] > n // 2) | (((a[:, None] == 0) | (a[:, None] == n // 2)) & (a[None, :] > n // 2))
+            ia, ib = np.nonzero(dep)
+            for kz in (0, n // 2):
+                F[ia, ib, kz] = np.conj(F[(-ia) % n, (-ib) % n, kz])
+            return F
+
+        field = mirrored(self.F(p, n))
+        P0 = mirrored(self.F(cov, n)) if cov else np.zeros_like(field)
+        kmax, kmin = math.pi / L * n, 2.0 * math.pi / L
+        dklog, kw = math.log10(kmax / kmin) / nbins, 2.0 * math.pi / L
+        i1 = np.arange(-(n // 2), n // 2 + 1)
+        ix, iy, iz = np.meshgrid(i1, i1, i1, indexing="ij")
+        neg = iz < 0
+        a = np.where(neg, (-ix) % n, ix % n)
+        b = np.where(neg, (-iy) % n, iy % n)
+        c = np.abs(iz)
+        k = np.sqrt((ix * ix + iy * iy + iz * iz).astype(np.float64)) * kw
+        ok = (k >= kmin) & (k < kmax)
+        idx = (1.0 / dklog * np.log10(k[ok] / kmin)).astype(np.int64)
+        bins = np.zeros((4, nbins))
+        bins[0] = np.bincount(idx, minlength=nbins)
+        bins[1] = np.bincount(idx, weights=k[ok], minlength=nbins)
+        bins[2] = np.bincount(idx, weights=np.abs(field[a[ok], b[ok], c[ok]]) ** 2, minlength=nbins)
+        bins[3] = np.bincount(idx, weights=P0[a[ok], b[ok], c[ok]].real, minlength=nbins)
+        dst = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(4 * nbins,))
+        dst[:] = bins.reshape(-1)
+        return 0
+
     def gx_dot_fourier(self, a, b, n, dt, out, st):
         out._obj.value = float(np.sum(M.mode_weights(n) * (np.conj(self.F(a, n)) * self.F(b, n)).real))
         return 0

@@ -209,3 +209,39 @@ def test_errors_are_raised():
     with pytest.raises(gb.GxError):
         f = gb.Field(g, fourier=False)
         f.toFourier()
+
+
+@pytest.mark.parametrize("n,dtype", [(16, np.float64), (32, np.float64), (32, np.float32)])
+def test_power_spectrum_bins_on_device(n, dtype):
+    """gx_power_spectrum_bins (the reduction behind `dump_ps`, cosmology/parameters.hpp:112-205) against the reference's
+    triple loop over [-n/2, n/2]^3 restated in numpy (tests/host/mock_device.py): counts exact, sums to rounding."""
+    import ctypes as C
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gx_mock_device", os.path.join(os.path.dirname(__file__), "host", "mock_device.py"))
+    mock = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mock)
+    box = 37.0
+    rng = np.random.default_rng(n)
+    ct = np.complex128 if dtype == np.float64 else np.complex64
+    A = (rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))).astype(ct)
+    P = (rng.random((n, n, n // 2 + 1)) + 0.5).astype(ct)
+    g = gb.Grid(box, n, dtype=dtype)
+    f, cov = gb.Field(g, A, fourier=True), gb.Field(g, P, fourier=True)
+    bins = np.zeros((4, 100))
+    f.lib.gx_power_spectrum_bins(f.ptr, cov.ptr, n, f.dt, box, 100, bins.ctypes.data_as(C.c_void_p), None)
+    m = mock.MockLib()
+    hp, hc = C.c_void_p(), C.c_void_p()
+    m.gx_malloc(C.byref(hp), m.gx_field_bytes(n, 1))
+    m.gx_malloc(C.byref(hc), m.gx_field_bytes(n, 1))
+    m.F(hp, n)[:] = A.astype(np.complex128)
+    m.F(hc, n)[:] = P.astype(np.complex128)
+    ref = np.zeros((4, 100))
+    m.gx_power_spectrum_bins(hp, hc, n, 1, box, 100, ref.ctypes.data_as(C.c_void_p), None)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    if dtype == np.float64:
+        assert np.array_equal(bins[0], ref[0])
+    else:   # single precision: a mode within rounding of a bin edge may fall on the other side
+        assert np.abs(bins[0] - ref[0]).sum() <= 8 and bins[0].sum() == ref[0].sum()
+        return
+    for i in (1, 2, 3):
+        assert np.allclose(bins[i], ref[i], rtol=tol, atol=0)
