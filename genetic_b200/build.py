@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
 
 
 HOST_DIR = os.path.join(os.path.dirname(HERE), "host")
-HOST_PROGRAMS = ("genetic_b200_ic", "genetic_b200_chi2", "genetic_b200_zoom")
+HOST_PROGRAMS = ("genetic_b200_ic", "genetic_b200_chi2", "genetic_b200_zoom", "genetic_b200_modify")
 HOST_BIN = os.path.join(HOST_DIR, "genetic_b200_ic")
 
 
@@ -67,7 +67,8 @@ def build_host(force=False, program="genetic_b200_ic"):
     for prog in HOST_PROGRAMS:
         src, exe = os.path.join(HOST_DIR, prog + ".cpp"), os.path.join(HOST_DIR, prog)
         newest = max(os.path.getmtime(p) for p in (src, os.path.join(inc, "genetic_b200.hpp"), os.path.join(inc, "genetic_b200.h"),
-                                                   os.path.join(inc, "genetic_b200_zoom.hpp")))
+                                                   os.path.join(inc, "genetic_b200_zoom.hpp"),
+                                                   os.path.join(inc, "genetic_b200_modif.hpp")))
         if force or not os.path.exists(exe) or os.path.getmtime(exe) < newest:
             cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I", inc, src, "-L", HERE, "-lgenetic_b200",
                    "-Wl,-rpath,$ORIGIN/../genetic_b200", "-o", exe]

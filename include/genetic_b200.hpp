@@ -192,7 +192,18 @@ public:
     const_cast<Field<T> &>(o).toDevice();
     check(gx_memcpy_d2d(dev, o.dev, bytes(), nullptr));
   }
-  Field<T> &operator=(const Field<T> &) = delete;
+  Field<T> &operator=(const Field<T> &o) {  // deep copy into the existing buffer (reallocated if the grids differ in size)
+    if (this == &o) return *this;
+    const size_t have = bytes();
+    pGrid = o.pGrid;
+    fourier_ = o.fourier_;
+    if (have != bytes()) { if (dev) gx_free(dev); dev = nullptr; allocate(); }
+    const_cast<Field<T> &>(o).toDevice();
+    check(gx_memcpy_d2d(dev, o.dev, bytes(), nullptr));
+    hostValid = false;
+    devValid = true;
+    return *this;
+  }
   ~Field() { if (dev) gx_free(dev); }
 
   const TGrid &getGrid() const { return *pGrid; }
@@ -365,6 +376,9 @@ public:
     }
     return dof;
   }
+  // set once the particle generator has folded the coarse levels into the fine ones (multilevelgrid.hpp:82-95)
+  bool levelsAreCombined = false;
+  void setLevelsAreCombined() { levelsAreCombined = true; }
 private:
   std::vector<std::shared_ptr<grids::Grid<T>>> pGrids;
   std::vector<T> weights;
@@ -373,9 +387,15 @@ private:
 }  // namespace multilevelgrid
 
 namespace filters {
-template <typename T> class FilterFamily {  // filterfamily.hpp:86-143, levels not yet combined; FRACTIONAL_K_SPLIT = 0.3
+template <typename T> class FilterFamily {  // filterfamily.hpp:86-143; FRACTIONAL_K_SPLIT = 0.3
 public:
   explicit FilterFamily(const multilevelgrid::MultiLevelGrid<T> &ctx) {
+    if (ctx.levelsAreCombined) {  // the fine fields carry the low frequencies too: null filter everywhere but on the finest level
+      const Filter<T> null = Filter<T>() * T(0);
+      for (size_t level = 0; level + 1 < ctx.getNumLevels(); ++level) { fs.push_back(null); lp.push_back(null); hp.push_back(null); }
+      fs.emplace_back(); lp.emplace_back(); hp.emplace_back();
+      return;
+    }
     fs.emplace_back(); lp.emplace_back(); hp.emplace_back();
     for (size_t level = 0; level + 1 < ctx.getNumLevels(); ++level) {
       const auto &g = ctx.getGridForLevel(level);

@@ -492,6 +492,7 @@ public:
         overdensity[l]->addFieldFromDifferentGridWithFilter(*overdensity[l - 1], lp);
         for (int a = 0; a < 3; ++a) pOff[l][a]->addFieldFromDifferentGridWithFilter(*pOff[l - 1][a], lp);
       }
+      ctx.setLevelsAreCombined();
     }
     for (auto &lev : pOff) for (auto &p : lev) p->toReal();
   }
@@ -737,7 +738,6 @@ public:
     std::ifstream f(filename);
     if (!f.is_open()) throw std::runtime_error("Paramfile " + filename + " not found");
     dir = filename.find('/') == std::string::npos ? "." : filename.substr(0, filename.rfind('/'));
-    auto path = [this](const std::string &p) { return p[0] == '/' ? p : dir + "/" + p; };
     std::string line;
     int lineno = 0;
     while (std::getline(f, line)) {
@@ -746,9 +746,21 @@ public:
       std::string cmd;
       if (!(ss >> cmd) || cmd[0] == '#' || cmd[0] == '%') continue;
       for (auto &c : cmd) c = (char) std::tolower(c);
-      auto num = [&]() { double v; if (!(ss >> v)) throw std::runtime_error("Insufficient arguments for command " + cmd); return v; };
-      auto str = [&]() { std::string v; if (!(ss >> v)) throw std::runtime_error("Insufficient arguments for command " + cmd); return v; };
       try {
+        runCommand(cmd, ss);
+      } catch (std::exception &e) {
+        throw std::runtime_error("Error \"" + std::string(e.what()) + "\" on line " + std::to_string(lineno) + " (\"" + line + "\")");
+      }
+    }
+  }
+
+  // one command of a paramfile (lower-cased name, the rest of the line)
+  void runCommand(const std::string &cmd, std::istringstream &ss) {
+    auto path = [this](const std::string &p) { return p[0] == '/' ? p : dir + "/" + p; };
+    auto num = [&]() { double v; if (!(ss >> v)) throw std::runtime_error("Insufficient arguments for command " + cmd); return v; };
+    auto str = [&]() { std::string v; if (!(ss >> v)) throw std::runtime_error("Insufficient arguments for command " + cmd); return v; };
+    {
+      {
         if (cmd == "om") cosmo.OmegaM0 = (T) num();
         else if (cmd == "ol") cosmo.OmegaLambda0 = (T) num();
         else if (cmd == "ob") cosmo.OmegaBaryons0 = (T) num();
@@ -800,8 +812,6 @@ public:
         }
         else if (cmd == "done") done();
         else throw std::runtime_error("Unknown command " + cmd);
-      } catch (std::exception &e) {
-        throw std::runtime_error("Error \"" + std::string(e.what()) + "\" on line " + std::to_string(lineno) + " (\"" + line + "\")");
       }
     }
   }

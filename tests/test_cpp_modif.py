@@ -1,0 +1,93 @@
+"""The C++ host layer for modifications and splicing (include/genetic_b200_modif.hpp, host/genetic_b200_modify.cpp): the
+reference's own test paramfiles run unmodified through the C++ driver on the device and compared with the reference's
+goldens (tests/golden/, made by make_golden.py from genetIC/tests/*) -- dumped grids, log lines, particle files, the
+power-spectrum dump. Same fixtures and tolerances as the Python command layer's tests (tests/test_gpu_paramfile.py)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from genetic_b200 import build as gbuild, output as OUT
+
+
+def _run(golden_dir, tmp_path, test, expect=0):
+    exe = gbuild.build_host(program="genetic_b200_modify")
+    d = tmp_path / test
+    shutil.copytree(os.path.join(golden_dir, test), d)
+    for f in os.listdir(golden_dir):
+        if f.endswith(".dat"):
+            shutil.copy(os.path.join(golden_dir, f), tmp_path / f)
+    r = subprocess.run([exe, str(d / "paramfile.txt")], capture_output=True, text=True, cwd=str(d))
+    assert r.returncode == expect, r.stderr
+    return d, [l.strip() for l in r.stdout.splitlines()], r.stderr
+
+
+def test_cpp_modify_driver_errors_before_the_device(tmp_path):
+    exe = gbuild.build_host(program="genetic_b200_modify")
+    p = tmp_path / "paramfile.txt"
+    p.write_text("Om 0.3\nbasegrid 50 16\ncalculate overdensity\n")
+    r = subprocess.run([exe, str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and 'on line 3 ("calculate overdensity")' in r.stderr and "has not been seeded" in r.stderr
+    p.write_text("basegrid 50 16\nmodify overdensity relative\n")
+    r = subprocess.run([exe, str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and "Insufficient arguments for command modify" in r.stderr
+    p.write_text("basegrid 50 16\nreverse_small_k 0.1\n")
+    r = subprocess.run([exe, str(p)], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown command reverse_small_k" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("test", ["test_02k_chisquare_onelevel", "test_02m_chisquare_twolevels", "test_02f_onelevelvariance",
+                                  "test_02g_multilevelvariance"])
+def test_cpp_log_line_goldens(golden_dir, tmp_path, test):
+    """chi^2 of one and two levels, filtered variance / overdensity values before and after `done`, and the warnings about
+    the filtering scale and the flagged region: every line of the reference's reference.txt appears in the output."""
+    d, log, _ = _run(golden_dir, tmp_path, test)
+    for line in open(str(d / "reference.txt")).read().splitlines():
+        assert line.strip() in log, (line, log)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("test", ["test_01c_zoom_grid", "test_02c_two_modifs", "test_02i_multilevel_algorithm"])
+def test_cpp_zoom_grid_goldens(golden_dir, tmp_path, test):
+    """Two linear modifications on a zoom (02c), overdensity + variance modification on two levels (02i), and the plain zoom
+    (01c, with dump_ps): the dumped grids of both levels against the reference's."""
+    d, _, _ = _run(golden_dir, tmp_path, test)
+    gold = np.load(str(d / "grids_every4.npz"))
+    for l in (0, 1):
+        g = np.load(str(d / ("grid-%d.npy" % l)))[::4, ::4, ::4]
+        assert np.abs(g - gold["grid%d" % l]).max() < 1e-6 * max(1.0, np.abs(gold["grid%d" % l]).max())
+
+
+@pytest.mark.gpu
+def test_cpp_splicing_golden_and_power_spectrum_dump(golden_dir, tmp_path):
+    """test_24: two white-noise fields spliced by conjugate gradient on the device, then dump_ps / dump_grid. The grid
+    against the reference's; the .ps file against the one the Python layer writes for the same paramfile."""
+    from genetic_b200 import icgen
+    d, _, _ = _run(golden_dir, tmp_path, "test_24_splicing")
+    gold = np.load(str(d / "grid0.npz"))["grid0"]
+    assert np.abs(np.load(str(d / "grid-0.npy")) - gold).max() < 1e-4     # CG stops at rtol 1e-6 (cg.hpp)
+    ours = np.loadtxt(str(d / "test_22_0.ps"))
+    py = tmp_path / "py"
+    shutil.copytree(os.path.join(golden_dir, "test_24_splicing"), py / "test_24_splicing")
+    shutil.copy(os.path.join(golden_dir, "camb_transfer_kmax40_z0.dat"), py)
+    icgen.run_paramfile(str(py / "test_24_splicing" / "paramfile.txt"), log=lambda s: None)
+    ref = np.loadtxt(str(py / "test_24_splicing" / "test_22_0.ps"))
+    assert ours.shape == ref.shape and ours.shape[1] == 5
+    assert np.array_equal(ours[:, [0, 1, 4]], ref[:, [0, 1, 4]])
+    assert np.allclose(ours[:, 2:4], ref[:, 2:4], rtol=1e-4)              # %g keeps 6 digits; the spliced field is CG-limited
+
+
+@pytest.mark.gpu
+def test_cpp_velocity_modification_golden(golden_dir, tmp_path):
+    d, log, _ = _run(golden_dir, tmp_path, "test_14_velocity_modif")
+    files = [f for f in os.listdir(d) if f.endswith(".gadget3")]
+    assert len(files) == 1
+    ours = OUT.read_gadget(str(d / files[0]))
+    gold = np.load(str(d / "particles.npz"))
+    assert np.abs(ours["pos"] - gold["pos"]).max() < 1e-4
+    assert np.abs(ours["vel"] - gold["vel"]).max() < 1e-4 * max(1.0, np.abs(gold["vel"]).max())
+    values = [float(l.split("=")[1]) for l in log if l.startswith("vx: calculated value")]
+    assert len(values) == 2 and abs(values[1]) < 1e-6 * max(1.0, abs(values[0]))   # `modify vx absolute 0` holds after done
