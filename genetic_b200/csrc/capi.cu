@@ -5,6 +5,8 @@
 namespace gx {
 const char *last_error_cstr();
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
+int pool_malloc(void **ptr, size_t bytes);  // mempool.cu
+int pool_free(void *ptr);
 }
 
 using namespace gx;
@@ -50,14 +52,8 @@ unsigned long long gx_launch_count(void) { return gx::g_launch_count; }
 
 size_t gx_field_bytes(int n, int dtype) { return (size_t) 2 * n * n * (n / 2 + 1) * esize(dtype); }
 
-int gx_malloc(void **ptr, size_t bytes) {
-  GX_CUDA_CHECK(cudaMalloc(ptr, bytes));
-  return 0;
-}
-int gx_free(void *ptr) {
-  GX_CUDA_CHECK(cudaFree(ptr));
-  return 0;
-}
+int gx_malloc(void **ptr, size_t bytes) { return gx::pool_malloc(ptr, bytes); }
+int gx_free(void *ptr) { return gx::pool_free(ptr); }
 int gx_memset_zero(void *ptr, size_t bytes, void *stream) {
   GX_CUDA_CHECK(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t) stream));
   return 0;

@@ -38,43 +38,53 @@ template <typename T> struct AxisTab {
 
 // mode 0: weighted sum, cell contained when bit 0 is set on all three axes
 // mode 1: mean over the gathered cells, contained when bit 0 is set on all axes or bit 1 is set on all axes
+// One CTA makes `group` consecutive destination lines of one x-plane: their source lines (cx * cy each, 4 x 4 for the tricubic
+// transfer) overlap, and the CTA's later lines find them in L1 instead of L2.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 axis_gather_add_kernel(T *__restrict__ dst, int n_dst, const T *__restrict__ src, int n_src, AxisTab<T> tx, AxisTab<T> ty,
-                       AxisTab<T> tz, T scale) {
+                       AxisTab<T> tz, T scale, int group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *row = reinterpret_cast<T *>(smem_raw);
-  const int A = blockIdx.y, B = blockIdx.x;
-  const int cx = tx.cnt[A], cy = ty.cnt[B];
-  if (cx == 0 || cy == 0) return;
-  const unsigned fxy = tx.flag[A] & ty.flag[B];
-  if (fxy == 0) return;
+  const int A = blockIdx.y;
+  const int cx = tx.cnt[A];
+  if (cx == 0) return;
   const long ps = n_src + 2, pd = n_dst + 2;
-  const int *ix = tx.idx + (long) A * tx.K, *iy = ty.idx + (long) B * ty.K;
-  const T *wx = tx.w + (long) A * tx.K, *wy = ty.w + (long) B * ty.K;
-  for (int z = threadIdx.x; z < n_src; z += blockDim.x) {
-    T acc = 0;
-    for (int i = 0; i < cx; ++i) {
-      const T *plane = src + (long) ix[i] * n_src * ps + z;
-      T a = 0;
-      for (int j = 0; j < cy; ++j) a += wy[j] * plane[(long) iy[j] * ps];
-      acc += wx[i] * a;
+  const int *ix = tx.idx + (long) A * tx.K;
+  const T *wx = tx.w + (long) A * tx.K;
+  const int B1 = min(n_dst, (int) (blockIdx.x + 1) * group);
+  for (int B = blockIdx.x * group; B < B1; ++B) {  // every condition below is uniform over the CTA
+    const int cy = ty.cnt[B];
+    if (cy == 0) continue;
+    const unsigned fxy = tx.flag[A] & ty.flag[B];
+    if (fxy == 0) continue;
+    const int *iy = ty.idx + (long) B * ty.K;
+    const T *wy = ty.w + (long) B * ty.K;
+    for (int z = threadIdx.x; z < n_src; z += blockDim.x) {
+      T acc = 0;
+      for (int i = 0; i < cx; ++i) {
+        const T *plane = src + (long) ix[i] * n_src * ps + z;
+        T a = 0;
+        for (int j = 0; j < cy; ++j) a += wy[j] * plane[(long) iy[j] * ps];
+        acc += wx[i] * a;
+      }
+      row[z] = acc;
     }
-    row[z] = acc;
-  }
-  __syncthreads();
-  T *out = dst + ((long) A * n_dst + B) * pd;
-  for (int C = threadIdx.x; C < n_dst; C += blockDim.x) {
-    const int cz = tz.cnt[C];
-    if (cz == 0) continue;
-    const unsigned f = fxy & tz.flag[C];
-    if (MODE == 0 ? !(f & 1u) : f == 0) continue;
-    const int *iz = tz.idx + (long) C * tz.K;
-    const T *wz = tz.w + (long) C * tz.K;
-    T s = 0;
-    for (int k = 0; k < cz; ++k) s += wz[k] * row[iz[k]];
-    if (MODE == 1) s /= (T) (cx * cy * cz);
-    out[C] += scale * s;
+    __syncthreads();
+    T *out = dst + ((long) A * n_dst + B) * pd;
+    for (int C = threadIdx.x; C < n_dst; C += blockDim.x) {
+      const int cz = tz.cnt[C];
+      if (cz == 0) continue;
+      const unsigned f = fxy & tz.flag[C];
+      if (MODE == 0 ? !(f & 1u) : f == 0) continue;
+      const int *iz = tz.idx + (long) C * tz.K;
+      const T *wz = tz.w + (long) C * tz.K;
+      T s = 0;
+      for (int k = 0; k < cz; ++k) s += wz[k] * row[iz[k]];
+      if (MODE == 1) s /= (T) (cx * cy * cz);
+      out[C] += scale * s;
+    }
+    __syncthreads();
   }
 }
 
@@ -300,8 +310,9 @@ template <typename T, int MODE>
 static int run_gather(void *dst, int n_dst, const void *src, int n_src, const DevTabs<T> &d, T scale, const char *name,
                       cudaStream_t st) {
   GX_TIMED(name, st);
-  axis_gather_add_kernel<T, MODE><<<dim3(n_dst, n_dst), 256, (size_t) n_src * sizeof(T), st>>>(
-      (T *) dst, n_dst, (const T *) src, n_src, d.tab[0], d.tab[1], d.tab[2], scale);
+  static const int group = [] { const char *e = getenv("GX_GATHER_GROUP"); const int g = e ? atoi(e) : 8; return g < 1 ? 1 : g; }();
+  axis_gather_add_kernel<T, MODE><<<dim3((n_dst + group - 1) / group, n_dst), 256, (size_t) n_src * sizeof(T), st>>>(
+      (T *) dst, n_dst, (const T *) src, n_src, d.tab[0], d.tab[1], d.tab[2], scale, group);
   count_launch();
   GX_LAUNCH_CHECK();
   return 0;

@@ -35,6 +35,7 @@
 namespace gx {
 void release_spectral_workspace();   // spectral.cu: the |k|^2 table
 void release_reduce_workspace();     // reduce.cu: partial sums
+void pool_release();                 // mempool.cu: idle field buffers
 void release_multigrid_workspace();  // multigrid.cu: cached cross-grid tables
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
 namespace fft { template <typename T> int fft3d(T *data, int n, int dir, cudaStream_t st); }
@@ -1478,6 +1479,7 @@ int gx_workspace_release(void) {
   gx::release_spectral_workspace();
   gx::release_multigrid_workspace();
   gx::release_reduce_workspace();
+  gx::pool_release();
   return 0;
 }
 

@@ -237,15 +237,20 @@ template <typename T> static int covariance_field_t(void *out, int n, double L, 
 static void *g_transfer_tab = nullptr;   // grow-only workspace for the |k|^2 table (values are rebuilt by every call)
 static size_t g_transfer_tab_bytes = 0;
 
+static int ensure_transfer_tab(size_t bytes) {
+  if (g_transfer_tab_bytes < bytes) {
+    if (g_transfer_tab) { GX_CUDA_CHECK(cudaDeviceSynchronize()); GX_CUDA_CHECK(cudaFree(g_transfer_tab)); g_transfer_tab = nullptr; }
+    GX_CUDA_CHECK(cudaMalloc(&g_transfer_tab, bytes));
+    g_transfer_tab_bytes = bytes;
+  }
+  return 0;
+}
+
 // table[m] = C(k)^power [/ k^2] for m = ix^2 + iy^2 + iz^2; rebuilt by every call, only the allocation is kept
 template <typename T>
 static int build_transfer_table_t(int n, double L, const gx_spectrum *s, double power, int divide_k2, cudaStream_t st) {
   const long h = n / 2, mcount = 3 * h * h + 1;
-  if (g_transfer_tab_bytes < mcount * sizeof(T)) {
-    if (g_transfer_tab) { GX_CUDA_CHECK(cudaDeviceSynchronize()); GX_CUDA_CHECK(cudaFree(g_transfer_tab)); g_transfer_tab = nullptr; }
-    GX_CUDA_CHECK(cudaMalloc(&g_transfer_tab, mcount * sizeof(T)));
-    g_transfer_tab_bytes = mcount * sizeof(T);
-  }
+  if (int rc = ensure_transfer_tab(mcount * sizeof(T))) return rc;
   TransferTableF<T> tf;
   tf.sp = gx_spectrum_device_view(s);
   tf.tab = (T *) g_transfer_tab; tf.mcount = mcount; tf.kmin = kmin_of<T>(L); tf.norm = (T) gx_spectrum_grid_norm(s, L, n);
@@ -290,9 +295,41 @@ template <typename T> static int apply_transfer_field_t(void *field, const void 
   return launch_slot_sweep(n, f, st);
 }
 
+// table[m] = f(|k|) for m = ix^2 + iy^2 + iz^2 (|k| = sqrt(m kMin^2)): the exponentials of the Fermi factors are evaluated
+// once per distinct |k|^2 (3 (n/2)^2 + 1 values) instead of once per mode, and the sweep becomes a pure HBM pass
+template <typename T> struct FilterTableF {
+  T *tab; long mcount; T kmin; FilterDesc d;
+};
+template <typename T> __global__ void __launch_bounds__(256) filter_table_kernel(FilterTableF<T> f) {
+  for (long m = (long) blockIdx.x * blockDim.x + threadIdx.x; m < f.mcount; m += (long) gridDim.x * blockDim.x) {
+    const T k2 = mul_rn((T) m, mul_rn(f.kmin, f.kmin));
+    f.tab[m] = filter_eval<T>(f.d, (T) sqrt((double) k2));
+  }
+}
+
 template <typename T>
 static int apply_filter_t(void *field, int n, double L, const gx_filter_factor *fac, int nf, cudaStream_t st) {
   if (nf < 0 || nf > 16) return gx::fail("gx_apply_filter: at most 16 factors");
+  static int use_table = -1;
+  if (use_table < 0) { const char *e = getenv("GX_FILTER_TABLE"); use_table = (e && e[0] == '0') ? 0 : 1; }
+  if (use_table) {
+    const long h = n / 2, mcount = 3 * h * h + 1;
+    if (int rc = ensure_transfer_tab(mcount * sizeof(T))) return rc;
+    FilterTableF<T> tf;
+    tf.tab = (T *) g_transfer_tab; tf.mcount = mcount; tf.kmin = kmin_of<T>(L); tf.d.nf = nf;
+    for (int i = 0; i < nf; ++i) tf.d.f[i] = fac[i];
+    {
+      GX_TIMED("filter_table", st);
+      long blocks = (mcount + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      filter_table_kernel<T><<<(unsigned) blocks, 256, 0, st>>>(tf);
+      count_launch();
+    }
+    GX_LAUNCH_CHECK();
+    ApplyTableF<T> f;
+    f.f = (cplx<T> *) field; f.tab = (const T *) g_transfer_tab; f.n = n;
+    return launch_slot_sweep(n, f, st, 0, "apply_filter");
+  }
   ApplyFilterF<T> f;
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.d.nf = nf;
   for (int i = 0; i < nf; ++i) f.d.f[i] = fac[i];

@@ -388,8 +388,7 @@ def _flaggedCellsPhysicalSize(grid):
     n = grid.size
     coords = np.stack(np.unravel_index(flags, (n, n, n)), axis=1)
     w = Z._Window(grid.simEquivalentSize, [int(v) for v in coords[0]])
-    for c in coords:
-        w.expandToInclude([int(v) for v in c])
+    w.expandToIncludeAll(coords)
     return float(grid.dtype.type(max(w.sizes())) * grid.cellSize)
 
 
@@ -696,17 +695,22 @@ class ModificationManager:
 
     @staticmethod
     def _performIterations(field, alphas, q, n_steps):
-        start = q.calculateCurrentValue(field)
-        end = q.getTarget()
+        # The reference evaluates the current value (a push through the matrix + an inner product) and then pushes the same
+        # field again (modificationmanager.hpp:309-323); the second push repeats the first bit for bit, so one is kept.
+        def push_and_value():
+            p = q.pushMultiLevelFieldThroughMatrix(field)
+            p.toFourier()
+            return p, p.innerProduct(field)
+        pushed, cur = push_and_value()
+        start, end = cur, q.getTarget()
         if n_steps in (0, 1) or start == end:          # tools::linspace (util_functions.hpp:78-92)
             targets = [end]
         else:
             step = (end - start) / n_steps
             targets = [start + c * step for c in range(n_steps + 1)]
         for i in range(n_steps):
-            cur = q.calculateCurrentValue(field)
-            pushed = q.pushMultiLevelFieldThroughMatrix(field)
-            pushed.toFourier()
+            if i > 0:
+                pushed, cur = push_and_value()
             norm = math.sqrt(pushed.innerProduct(pushed))
             for a in alphas:                             # addToOrthonormalFamily (:306-319); the alphas are vectors by now
                 r = pushed.innerProduct(a)

@@ -127,6 +127,8 @@ class _RawCuda:
 
     def __del__(self):
         try:
+            import torch
+            torch.cuda.synchronize()    # the buffer was used on non-blocking streams (and by peers): gx_free pools it unsynchronised
             self.lib.gx_free(self.ptr)
         except Exception:
             pass

@@ -115,19 +115,39 @@ class _Window:
     def _within(lo, hi, v):
         return (lo <= v < hi) if hi >= lo else (v < hi or v >= lo)
 
+    def _expandAxis(self, a, v):
+        lo, hi = self.lo[a], self.hi[a]
+        if self._within(lo, hi, v):
+            return
+        sizeLower = self._w(hi - v - 1) + 1
+        sizeUpper = self._w(v - lo) + 1
+        canLower = self._within(v, hi, lo)
+        canUpper = self._within(lo, v + 1, hi - 1)
+        if canLower and (sizeLower < sizeUpper or not canUpper):
+            self.lo[a] = v
+        else:
+            self.hi[a] = v + 1
+
     def expandToInclude(self, p):
         for a in range(3):
-            lo, hi, v = self.lo[a], self.hi[a], p[a]
-            if self._within(lo, hi, v):
-                continue
-            sizeLower = self._w(hi - v - 1) + 1
-            sizeUpper = self._w(v - lo) + 1
-            canLower = self._within(v, hi, lo)
-            canUpper = self._within(lo, v + 1, hi - 1)
-            if canLower and (sizeLower < sizeUpper or not canUpper):
-                self.lo[a] = v
-            else:
-                self.hi[a] = v + 1
+            self._expandAxis(a, p[a])
+
+    def expandToIncludeAll(self, coords):
+        """expandToInclude over the rows of an (m, 3) array, in order. The axes are independent, and while the window is a
+        proper arc of the period it only grows, so a value that has been seen changes nothing when it comes again: per axis
+        only the first occurrence of each distinct value is visited. If the arc ever closes on itself (flags spanning the
+        whole period: [lo, hi) with hi == lo reads as empty) that argument fails and the rows are replayed one by one."""
+        coords = np.asarray(coords)
+        lo0, hi0 = list(self.lo), list(self.hi)
+        for a in range(3):
+            vals, first = np.unique(coords[:, a], return_index=True)
+            for v in vals[np.argsort(first, kind="stable")]:
+                self._expandAxis(a, int(v))
+                if (self.hi[a] - self.lo[a]) % self.wrap == 0:
+                    self.lo, self.hi = lo0, hi0
+                    for c in coords:
+                        self.expandToInclude([int(x) for x in c])
+                    return
 
     def sizes(self):
         return [self._w(self.hi[a] - self.lo[a] - 1) + 1 for a in range(3)]
@@ -175,8 +195,7 @@ def zoomCorner(grid, zoomfac, allowStrays=False):
     coords = np.stack(np.unravel_index(flags, (n, n, n)), axis=1)
     wrap = grid.simEquivalentSize
     w = _Window(wrap, [int(v) for v in coords[0]])
-    for c in coords:
-        w.expandToInclude([int(v) for v in c])
+    w.expandToIncludeAll(coords)
     n_user = n // zoomfac
     n_required = max(w.sizes())
     if n_required > n_user and not allowStrays:

@@ -48,11 +48,16 @@ int gx_version(void);
 int gx_device_count(int *count);
 int gx_set_device(int device);           /* fourier::initialise() analogue, fourier.hpp:36-81 */
 int gx_synchronize(void *stream);
-int gx_workspace_release(void);          /* frees the grow-only scratch the library keeps between calls (noise workspace, |k|^2 table, cross-grid tables) */
+int gx_workspace_release(void);          /* frees the grow-only scratch the library keeps between calls (noise workspace, |k|^2 table, cross-grid
+                                            tables) and the idle field buffers of the gx_malloc pool */
 unsigned long long gx_launch_count(void); /* kernels launched by this library so far (bench bookkeeping) */
 
 /* ---- memory ----------------------------------------------------------------------------------- */
 size_t gx_field_bytes(int n, int dtype); /* FieldFourierManager::getRequiredDataSize, fourier.hpp:471-476 */
+/* Field buffers (the reference: std::vector inside fields::Field, copied freely). Freed blocks up to GX_POOL_MAX_BLOCK bytes
+   (default 1.5 GiB) are pooled by exact size, at most GX_POOL_BYTES (default 8 GiB) in total, and handed out again once the
+   work issued before the free (legacy default stream and blocking streams) has completed; GX_POOL=0 maps and unmaps every
+   block (cudaMalloc / cudaFree). A buffer used on a non-blocking stream is synchronised by its owner before gx_free. */
 int gx_malloc(void **ptr, size_t bytes);
 int gx_free(void *ptr);
 int gx_memset_zero(void *ptr, size_t bytes, void *stream);

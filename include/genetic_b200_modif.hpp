@@ -395,7 +395,12 @@ private:
   }
   static void performIterations(TypedField<T> &field, std::vector<TypedField<T>> &alphas, FilteredVarianceModification<T> &q,
                                 int nSteps) {  // :306-331
-    const T start = q.calculateCurrentValue(field), end = q.getTarget();
+    // The reference evaluates the current value (a push through the matrix + an inner product) and then pushes the same
+    // field again (:309-323); the second push repeats the first bit for bit, so one is kept.
+    TypedField<T> pushed = q.pushMultiLevelFieldThroughMatrix(field);
+    pushed.toFourier();
+    T cur = pushed.innerProduct(field);
+    const T start = cur, end = q.getTarget();
     std::vector<T> targets;  // tools::linspace (util_functions.hpp:78-92)
     if (nSteps == 0 || nSteps == 1 || start == end) targets.push_back(end);
     else {
@@ -403,9 +408,11 @@ private:
       for (int c = 0; c <= nSteps; ++c) targets.push_back(start + T(c) * step);
     }
     for (int i = 0; i < nSteps; ++i) {
-      const T cur = q.calculateCurrentValue(field);
-      TypedField<T> pushed = q.pushMultiLevelFieldThroughMatrix(field);
-      pushed.toFourier();
+      if (i > 0) {
+        pushed = q.pushMultiLevelFieldThroughMatrix(field);
+        pushed.toFourier();
+        cur = pushed.innerProduct(field);
+      }
       const T norm = std::sqrt(pushed.innerProduct(pushed));
       for (auto &a : alphas) {  // addToOrthonormalFamily: the alphas are vectors by now
         const T r = pushed.innerProduct(a);

@@ -23,7 +23,7 @@ CAMB_FILE = os.path.join(ROOT, "tests", "golden", "planck_2018_transfer_out.dat"
 COSMO = dict(Om=0.3158, Ol=0.6842, s8=0.8117, z=200.0, ns=0.9660, hubble=0.6732)
 
 
-def run_device(n, seed):
+def run_device(n, seed, timing=False):
     import genetic_b200 as gb
     from genetic_b200 import multilevel as GM, zoom as Z, lib as L
     lib = L.load()
@@ -58,11 +58,32 @@ def run_device(n, seed):
         lib.gx_synchronize(None)
         t["total"] = time.perf_counter() - t0
         t["combine"] = t["total"] - t["draw"] - t["modifications"]
+        sums = []
+        for l in range(ctx.getNumLevels()):      # outside the timed region: a value to compare runs by
+            d = field.getFieldForLevel(l)
+            d.toReal()
+            sums.append(float((d.getDataVector().astype("float64") ** 2).sum()))
+        t["sumsq"] = sums
         return t
     once()
     l0 = lib.gx_launch_count()
     t = once()
     t["launches"] = int(lib.gx_launch_count() - l0)
+    if os.environ.get("GX_ZOOM_CPROFILE"):       # host-side profile of one more run (development)
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        once()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(35)
+    if timing:                                   # a third run with the library's per-class CUDA-event timing on
+        import ctypes as C
+        lib.gx_timing_enable(1)
+        once()
+        buf = C.create_string_buffer(1 << 16)
+        lib.gx_timing_report(buf, len(buf))
+        lib.gx_timing_enable(0)
+        t["classes_ms"] = {a: (int(b), round(float(c), 2)) for a, b, c in (ln.split() for ln in buf.value.decode().splitlines())}
     return t
 
 
@@ -95,12 +116,16 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64)
     ap.add_argument("--seed", type=int, default=1512351)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--timing", action="store_true", help="add per-kernel-class device time of one more run")
     a = ap.parse_args()
-    t = run_device(a.n, a.seed)
+    t = run_device(a.n, a.seed, a.timing)
     cells = 3 * a.n ** 3
     line = {"workload": "three-level zoom %d^3 x 3, overdensity + variance modification, random_seed_serial %d" % (a.n, a.seed),
             "seconds": t["total"], "cells_per_s": cells / t["total"], "breakdown_s": {k: t[k] for k in ("draw", "modifications", "combine")},
-            "gpu_launches": t["launches"]}
+            "gpu_launches": t["launches"], "sumsq_per_level": t["sumsq"]}
+    if "classes_ms" in t:
+        line["classes_ms"] = t["classes_ms"]
+        line["device_ms"] = round(sum(v[1] for v in t["classes_ms"].values()), 1)
     if not a.no_cpu:
         tc = run_oracle(a.cpu_n, a.seed)
         line["cpu_oracle"] = {"n": a.cpu_n, "seconds": tc, "cells_per_s": 3 * a.cpu_n ** 3 / tc, "cores": os.cpu_count(),
