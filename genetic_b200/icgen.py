@@ -19,7 +19,7 @@ import numpy as np
 
 from . import lib as L
 from .host import CosmologicalParameters, Grid, CAMB, PowerLawPowerSpectrum
-from . import multilevel as GM, zoom as Z, mapper as PM, output as OUT
+from . import multilevel as GM, zoom as Z, mapper as PM, output as OUT, grafic as GF
 
 
 class ICGenerator:
@@ -57,6 +57,7 @@ class ICGenerator:
         self.variance_filterscale = -1.0
         self.initial_number_steps, self.precision = 10, 0.001
         self.velOffset = (0.0, 0.0, 0.0)
+        self.pvarValue, self.centerOnTargetRegion = 1.0, False       # grafic output (ic.hpp:126,148)
         self.log = log if log is not None else (lambda msg: print(msg, flush=True))
         if pUnderlying is None:
             GM.set_logger(self.log)
@@ -115,10 +116,12 @@ class ICGenerator:
                   "supersample_gas": (self.setSupersampleGas, i)})
         r["strays_on"] = (self.setStraysOn,)
         r["autopad"] = (self.setAutopad, i)
-        for name in ("num_neighbors", "num_neighbours", "pvar",
-                     "center_grafic_output", "centre_output", "center_output",
+        r.update({"pvar": (self.setpvarValue, f), "center_grafic_output": (self.setCenteringOnRegion,),
+                  "centre_output": (self.setCenteringOnRegion,), "center_output": (self.setCenteringOnRegion,),
+                  "dump_mask": (self.dumpMask,), "import_level": (self.importLevel, i, s)})
+        for name in ("num_neighbors", "num_neighbours",
                      "dump_grid_for_field", "dump_grid_fourier_for_field",
-                     "dump_ps_field", "dump_tipsy_field", "dump_mask", "import_level",
+                     "dump_ps_field", "dump_tipsy_field",
                      "baryon_tf_on", "zero_level_field", "reverse_small_k"):
             r[name] = (self._unsupported(name),)
         return r
@@ -202,6 +205,52 @@ class ICGenerator:
             raise L.GxError("Subsampling factor must be greater then zero")
         self.subsample = factor
 
+    def setpvarValue(self, value):
+        """ic.hpp:344-347: the value of the passive variable written where the grafic mask is set."""
+        self.pvarValue = value
+
+    def setCenteringOnRegion(self):
+        """ic.hpp:349-353 (`center_output`): output centred on the point selected at `done` time."""
+        self.centerOnTargetRegion = True
+
+    def getBoxCentre(self):
+        """ic.hpp:1585-1589"""
+        half = float(self.context.getGridForLevel(0).thisGridSize) / 2.0
+        return (half, half, half)
+
+    def _graficCentre(self):
+        return (self.x0, self.y0, self.z0) if self.centerOnTargetRegion else self.getBoxCentre()
+
+    def dumpMask(self):
+        """ic.hpp:973-994: mask-<level>.npy for every level of the centred grafic stack, virtual levels included."""
+        gctx = GF.GraficContext(self.context, self._graficCentre(), self.subsample, self.supersample)
+        mask = GF.GraficMask(gctx, self.context.zoomParticleArray, self.log)
+        mask.calculateMask()
+        for level, lv in enumerate(gctx.levels):
+            g = lv.grid
+            np.save("%s/mask-%d.npy" % (self.outputFolder, level), mask.cube(level).astype(g.dtype))
+            with open("%s/mask-info-%d.txt" % (self.outputFolder, level), "w") as fh:
+                fh.write("%g %g %g %g\n" % (*[float(v) for v in lv.offsetLower], float(g.thisGridSize)))
+                fh.write("The line above contains information about grid level %d\n" % level)
+                fh.write("It gives the x-offset, y-offset and z-offset of the low-left corner and also the box length\n")
+
+    def importLevel(self, level, filename):
+        """ic.hpp:809-821 + Field::loadGridData (field.hpp:868-891): the real-space field of one level read from a .npy file."""
+        self.initialiseRandomComponentIfUninitialised()
+        self.log("Importing random field on level %d from %s" % (level, filename))
+        fld = self.outputField.getFieldForLevel(level)
+        data = np.load(filename)
+        n = fld.grid.size
+        if data.shape != (n, n, n):
+            raise L.GxError("Incorrect size for imported numpy array")
+        if data.dtype != self.dtype:
+            raise L.GxError("Incorrect data type for imported numpy array")
+        fld.setFourier(False)
+        fld.setDataVector(data)
+        fld.toFourier()
+        fld.applyTransferFunction(self.context.getCovariance(level, GM.DM), -0.5)   # back to white noise
+        self.log("... success!")
+
     def setBaryonsOnAllLevels(self):
         self.baryonsOnAllLevels = True
 
@@ -273,10 +322,11 @@ class ICGenerator:
 
     def setOutputFormat(self, fmt):
         """io::operator>>(OutputFormat) accepts a name or its number (io.hpp)."""
-        names = {"gadget2": "gadget2", "2": "gadget2", "gadget3": "gadget3", "3": "gadget3", "tipsy": "tipsy", "4": "tipsy"}
+        names = {"gadget2": "gadget2", "2": "gadget2", "gadget3": "gadget3", "3": "gadget3", "tipsy": "tipsy", "4": "tipsy",
+                 "grafic": "grafic", "5": "grafic"}
         if fmt.lower() not in names:
-            if fmt.lower() in ("grafic", "5", "gadgethdf", "6", "swift", "7"):
-                raise L.GxError("output format %s is not supported by genetic_b200 (tipsy, gadget2, gadget3 are)" % fmt)
+            if fmt.lower() in ("gadgethdf", "6", "swift", "7"):
+                raise L.GxError("output format %s is not supported by genetic_b200 (tipsy, gadget2, gadget3, grafic are)" % fmt)
             raise L.GxError("Unknown output format")
         self.outputFormat = names[fmt.lower()]
 
@@ -362,6 +412,14 @@ class ICGenerator:
                     self._mapper().size()))
 
     def _mapper(self, gasFirst=None):
+        if self.outputFormat == "grafic":
+            # ensureParticleGeneratorInitialised (ic.hpp:1140-1147): grafic writes the grids in turn; ids are their cells
+            key = ("grafic", self.context.getNumLevels(), self.subsample, self.supersample)
+            if getattr(self, "_mapper_key", None) != key:
+                self._mapper_cache = GF.GraficMapper(self.context, (self.x0, self.y0, self.z0), self.subsample,
+                                                     self.supersample, self.log)
+                self._mapper_key = key
+            return self._mapper_cache
         if gasFirst is None:
             gasFirst = self.outputFormat == "tipsy"
         # the reference rebuilds the mapper whenever one of these changes (updateParticleMapper call sites); here it is
@@ -596,6 +654,14 @@ class ICGenerator:
         if self.pParticleGenerator is None:
             self.log("Calculating particles from overdensity fields...")
             self.pParticleGenerator = GM.MultiLevelParticleGenerator(self.outputField)
+        if self.outputFormat == "grafic":
+            # ic.hpp:1312-1324: the grids in turn, centred on the selected point with `center_output`
+            self.outputField.toReal()
+            GF.save(self.getOutputPath() + ".grafic", self.context, self.pParticleGenerator, self.outputField, None,
+                    self.cosmology, self.pvarValue, self._graficCentre(), self.subsample, self.supersample,
+                    self.context.zoomParticleArray, self.log)
+            self.log("Finished writing initial conditions")
+            return
         t0 = time.perf_counter()
         mapper = self._mapper()
         t1 = time.perf_counter()
@@ -626,7 +692,7 @@ class ICGenerator:
         file -- delta + one psi field on the device instead of delta + three, nothing of size n^3 on the host. Used from
         512^3 upwards (GX_STREAM_UNIGRID=1/0 forces it on / off); a 2048^3 f64 IC needs 2 x 68.8 GB of the 180 GB."""
         env = os.environ.get("GX_STREAM_UNIGRID", "")
-        if env == "0" or self.context.getNumLevels() != 1 or self.pParticleGenerator is not None:
+        if env == "0" or self.context.getNumLevels() != 1 or self.pParticleGenerator is not None or self.outputFormat == "grafic":
             return False
         if float(self.cosmology.OmegaBaryons0) > 0 or self.supersample > 1 or self.subsample > 1 or \
                 self.flaggedGadgetParticleType is not None or self.nGadgetFiles != 1:

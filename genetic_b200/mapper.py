@@ -398,6 +398,8 @@ def _expandFlaggedRegion(flags, n, nCells):
 
 def references(mapper, grid):
     """ParticleMapper::references: does the mapper use (a view of) this stored grid?"""
+    if hasattr(mapper, "references"):
+        return mapper.references(grid)
     return any(m.grid.base is grid for m in mapper.layers().values())
 
 

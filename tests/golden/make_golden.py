@@ -165,3 +165,46 @@ if os.environ.get("GX_GOLDEN_SLOW") == "1":
     np.savez_compressed(f"{cfg3}/particles_sample.npz", index=idx, count=np.array([n]), pos=d["pos"][idx], vel=d["vel"][idx],
                         mass=d["mass"][idx], eps=d["eps"][idx], n=d["n"])
 print("ok")
+
+
+# ---- grafic output, grafic mapper ids, refinement masks, import_level (round 2) ---------------------------------------------
+def read_grafic_dir(path):
+    """The ten Fortran-record files of one level directory of the reference's grafic output."""
+    out = {}
+    for name in sorted(os.listdir(path)):
+        raw = open(os.path.join(path, name), "rb").read()
+        hdr = struct.unpack("<iiiffffffff", raw[4:48])
+        n = hdr[0]
+        dtype = np.uint64 if name == "ic_particle_ids" else np.float32
+        plane = n * n * np.dtype(dtype).itemsize
+        body = np.frombuffer(raw, dtype=np.uint8, offset=52).reshape(n, plane + 8)
+        out[name] = np.ascontiguousarray(body[:, 4:4 + plane]).view(dtype).reshape(n, n, n)
+        out["header"] = np.array(hdr, dtype=np.float64)
+    return out
+
+
+cp(f"{REF}/camb_transfer_kmax40_z0_post2015.dat", f"{HERE}/camb_transfer_kmax40_z0_post2015.dat")
+for t in ("test_12_grafic", "test_08e_mask_multiple_virtual_grids", "test_08f_mask_multiple_supersample"):
+    cp(f"{REF}/{t}/paramfile.txt", f"{HERE}/{t}/paramfile.txt")
+    packed = {}
+    for d in sorted(os.listdir(f"{REF}/{t}/reference_grafic")):
+        res = d.rsplit("_", 1)[1]
+        for k, v in read_grafic_dir(f"{REF}/{t}/reference_grafic/{d}").items():
+            packed["%s/%s" % (res, k)] = v
+    np.savez_compressed(f"{HERE}/{t}/reference_grafic.npz", **packed)
+for t, extra in {"test_08a_mask_lagrange_volume": ("lagrange.txt",), "test_08b_mask_virtual_architecture": (),
+                 "test_08c_centering_masks": (), "test_08d_mask_flag_interaction": ("lagrange.txt",),
+                 "test_08e_mask_multiple_virtual_grids": (), "test_08f_mask_multiple_supersample": ()}.items():
+    for f in ("paramfile.txt",) + extra:
+        cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
+    masks = {os.path.basename(f)[:-4]: np.load(f"{REF}/{t}/reference_mask/{f}").astype(np.uint8)
+             for f in sorted(os.listdir(f"{REF}/{t}/reference_mask")) if f.endswith(".npy")}
+    np.savez_compressed(f"{HERE}/{t}/reference_mask.npz", **masks)
+for t, files in {"mapper_test_02a_grafic": ("paramfile.txt", "test_ids.txt", "reference.txt"),
+                 "mapper_test_02b_grafic_zoom_to_coarse": ("paramfile.txt", "test_ids.txt", "reference.txt"),
+                 "mapper_test_02c_grafic_relative": ("paramfile.txt", "test_ids.txt", "reference.txt", "morezoomed.txt"),
+                 "mapper_test_02d_grafic_rel_subsupersample": ("paramfile.txt", "test_ids.txt", "reference.txt", "morezoomed.txt"),
+                 "test_01h_zoom_grid_pos_offset": ("paramfile.txt",), "test_01i_zoom_pos_offset_wrap": ("paramfile.txt",),
+                 "test_11_import": ("paramfile.txt", "reference_grid/grid-0.npy")}.items():
+    for f in files:
+        cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
