@@ -7,12 +7,14 @@ const char *last_error_cstr();
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
 int pool_malloc(void **ptr, size_t bytes);  // mempool.cu
 int pool_free(void *ptr);
+namespace fft { template <typename T> int fft3d_any(T *field, int n, int dir, cudaStream_t st); }  // fft_generic.cu
 }
 
 using namespace gx;
 
+// even sizes: powers of two take the tuned passes, the rest the mixed-radix passes (fft_generic.cu)
 static int check_n(int n) {
-  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (n < 4 || n > 4096 || (n & 1)) return gx::fail("grid size must be even and in [4,4096]");
   return 0;
 }
 static size_t esize(int dtype) { return dtype == GX_F64 ? 8 : 4; }
@@ -110,8 +112,8 @@ int gx_field_download(void *host, const void *dev_field, int n, int dtype, int l
 
 int gx_fft_forward(void *field, int n, int dtype, void *stream) {
   if (check_n(n)) return 1;
-  if (dtype == GX_F64) return gx::fft::fft3d<double>((double *) field, n, -1, (cudaStream_t) stream);
-  if (dtype == GX_F32) return gx::fft::fft3d<float>((float *) field, n, -1, (cudaStream_t) stream);
+  if (dtype == GX_F64) return gx::fft::fft3d_any<double>((double *) field, n, -1, (cudaStream_t) stream);
+  if (dtype == GX_F32) return gx::fft::fft3d_any<float>((float *) field, n, -1, (cudaStream_t) stream);
   return gx::fail("bad dtype");
 }
 
@@ -120,11 +122,11 @@ int gx_fft_inverse(void *field, int n, int dtype, void *stream) {
   int rc;
   if (dtype == GX_F64) {
     rc = gx::mirror<double>((double *) field, n, (cudaStream_t) stream);
-    return rc ? rc : gx::fft::fft3d<double>((double *) field, n, 1, (cudaStream_t) stream);
+    return rc ? rc : gx::fft::fft3d_any<double>((double *) field, n, 1, (cudaStream_t) stream);
   }
   if (dtype == GX_F32) {
     rc = gx::mirror<float>((float *) field, n, (cudaStream_t) stream);
-    return rc ? rc : gx::fft::fft3d<float>((float *) field, n, 1, (cudaStream_t) stream);
+    return rc ? rc : gx::fft::fft3d_any<float>((float *) field, n, 1, (cudaStream_t) stream);
   }
   return gx::fail("bad dtype");
 }

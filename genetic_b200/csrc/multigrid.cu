@@ -542,7 +542,7 @@ int gx_masked_shift_scale(void *field, const unsigned char *mask_n3, int n, int 
 }
 
 int gx_scale_inv_k2(void *field, int n, int dtype, double grid_length, double scale, int potential_form, void *stream) {
-  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (n < 4 || n > 4096 || (n & 1)) return gx::fail("grid size must be even and in [4,4096]");
   GX_DISPATCH(dtype, scale_inv_k2_t<T>(field, n, grid_length, scale, potential_form, (cudaStream_t) stream));
 }
 

@@ -122,7 +122,7 @@ void release_reduce_workspace() {  // gx_workspace_release / gx_set_device(anoth
   g_partials = nullptr;
 }
 static int check_n_reduce(int n) {  // the partials hold 64 blocks x n planes: n <= 4096
-  if (!is_pow2(n) || n < 4 || n > 4096) return fail("grid size must be a power of two in [4,4096]");
+  if (n < 4 || n > 4096 || (n & 1)) return fail("grid size must be even and in [4,4096]");
   return 0;
 }
 

@@ -36,6 +36,8 @@ namespace gx {
 void release_spectral_workspace();   // spectral.cu: the |k|^2 table
 void release_reduce_workspace();     // reduce.cu: partial sums
 void pool_release();                 // mempool.cu: idle field buffers
+namespace fftgen { void release_workspace(); }                                              // fft_generic.cu: twiddle tables
+namespace fft { template <typename T> int fft3d_any(T *field, int n, int dir, cudaStream_t st); }
 void release_multigrid_workspace();  // multigrid.cu: cached cross-grid tables
 template <typename T> int mirror(T *field, int n, cudaStream_t st);
 namespace fft { template <typename T> int fft3d(T *data, int n, int dir, cudaStream_t st); }
@@ -1376,7 +1378,7 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
   if (rc) return rc;
   if (phase.which == 1) return 0;
   if (mode == GX_NOISE_REAL && world == 1) {
-    rc = fft::fft3d<T>((T *) field, n, -1, cs);
+    rc = fft::fft3d_any<T>((T *) field, n, -1, cs);
     if (rc) return rc;
     zero_dc_real_kernel<T><<<1, 1, 0, cs>>>((T *) field);  // tools::set_zero(fieldData[0]) :195
     count_launch();
@@ -1388,10 +1390,18 @@ static int noise_draw_t(void *field, int n, unsigned long seed, int mode, int re
 
 }  // namespace rng
 
+// the real-space order (N^3 sequential draws, then the r2c) takes any even size; the Fourier-space orders are built on
+// power-of-two shells
+static int check_noise_n(int n, int mode) {
+  if (n < 4 || n > 4096 || (n & 1)) return fail("grid size must be even and in [4,4096]");
+  if (!is_pow2(n) && mode != GX_NOISE_REAL) return fail("the Fourier-space draw orders need a power-of-two grid size");
+  return 0;
+}
+
 int noise_draw_scaled(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
                       unsigned long long *stream_offset_io, cudaStream_t st, const void *table, void *scratch,
                       size_t scratch_bytes) {
-  if (!is_pow2(n) || n < 4 || n > 4096) return fail("grid size must be a power of two in [4,4096]");
+  if (check_noise_n(n, mode)) return 1;
   if (dtype == GX_F64) return rng::noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table, scratch, scratch_bytes);
   if (dtype == GX_F32) return rng::noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, st, 1, 0, rng::Phase(), table, scratch, scratch_bytes);
   return fail("bad dtype");
@@ -1405,7 +1415,7 @@ extern "C" {
 
 int gx_noise_draw(void *field, int n, int dtype, unsigned long seed, int mode, int reverse_order,
                   unsigned long long *stream_offset_io, void *stream) {
-  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (gx::check_noise_n(n, mode)) return 1;
   if (dtype == GX_F64) return noise_draw_t<double>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
   if (dtype == GX_F32) return noise_draw_t<float>(field, n, seed, mode, reverse_order, stream_offset_io, (cudaStream_t) stream);
   return gx::fail("bad dtype");
@@ -1480,6 +1490,7 @@ int gx_workspace_release(void) {
   gx::release_multigrid_workspace();
   gx::release_reduce_workspace();
   gx::pool_release();
+  gx::fftgen::release_workspace();
   return 0;
 }
 

@@ -170,6 +170,20 @@ template <typename T> struct ApplyFilterF : NoInit {
   }
 };
 
+// ---- ICGenerator::reverseSmallK (ic.hpp:1690-1708): delta_k <- -delta_k where 0 < k^2 < kmax^2 ---------------------------
+template <typename T> struct ReverseSmallKF : NoInit {
+  cplx<T> *f; int n; T kmin, k2max;
+  __device__ __forceinline__ void operator()(int ix, int iy, int iz, size_t s) const {
+    if (!slot_is_independent(n, ix, iy, iz)) return;
+    T kx, ky, kz, k2;
+    slot_k<T>(n, ix, iy, iz, kmin, kx, ky, kz, k2);
+    if (k2 < k2max && k2 != (T) 0) {
+      const cplx<T> v = f[s];
+      f[s] = mk<T>(-v.x, -v.y);
+    }
+  }
+};
+
 // ---- enforceUnitVariance (multilevelfield.hpp:498-510) ---------------------------------------------------
 template <typename T> struct UnitVarianceF : NoInit {
   cplx<T> *f; int n;
@@ -217,7 +231,7 @@ using namespace gx;
   } while (0)
 
 static int check_n(int n) {
-  if (!gx::is_pow2(n) || n < 4 || n > 4096) return gx::fail("grid size must be a power of two in [4,4096]");
+  if (n < 4 || n > 4096 || (n & 1)) return gx::fail("grid size must be even and in [4,4096]");  // sweeps: any even size
   return 0;
 }
 
@@ -334,6 +348,12 @@ static int apply_filter_t(void *field, int n, double L, const gx_filter_factor *
   f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.d.nf = nf;
   for (int i = 0; i < nf; ++i) f.d.f[i] = fac[i];
   return launch_slot_sweep(n, f, st);
+}
+
+template <typename T> static int reverse_small_k_t(void *field, int n, double L, double kmax, cudaStream_t st) {
+  ReverseSmallKF<T> f;
+  f.f = (cplx<T> *) field; f.n = n; f.kmin = kmin_of<T>(L); f.k2max = (T) kmax * (T) kmax;
+  return launch_slot_sweep(n, f, st, 0, "reverse_small_k");
 }
 
 template <typename T> static int unit_variance_t(void *field, int n, cudaStream_t st) {
@@ -483,6 +503,11 @@ int gx_apply_filter(void *field, int n, int dtype, double grid_length, const gx_
                     void *stream) {
   if (check_n(n)) return 1;
   GX_DISPATCH(dtype, apply_filter_t<T>(field, n, grid_length, factors, nfactors, (cudaStream_t) stream));
+}
+
+int gx_reverse_small_k(void *field, int n, int dtype, double grid_length, double kmax, void *stream) {
+  if (check_n(n)) return 1;
+  GX_DISPATCH(dtype, reverse_small_k_t<T>(field, n, grid_length, kmax, (cudaStream_t) stream));
 }
 
 int gx_unit_variance(void *field, int n, int dtype, void *stream) {

@@ -260,6 +260,10 @@ int zeldovich_shared_y(void *g, void *work, int n, int dtype, double grid_length
 extern "C" int gx_zeldovich_offset(const void *delta_k, void *psi, int n, int dtype, double grid_length, int axis,
                                    void *stream) {
   cudaStream_t st = (cudaStream_t) stream;
+  if (!gx::is_pow2(n)) {  // mixed-radix sizes: the operator as a sweep, then the plain inverse transform
+    if (int rc0 = gx_zeldovich_fourier(delta_k, psi, n, dtype, grid_length, axis, stream)) return rc0;
+    return gx_fft_inverse(psi, n, dtype, stream);
+  }
   int rc = gx::zeldovich_xy(delta_k, psi, n, dtype, grid_length, axis, 0, st);
   if (rc) return rc;
   return gx::zeldovich_z_real(psi, n, dtype, 0, (long) n * n, st);

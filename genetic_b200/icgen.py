@@ -6,8 +6,7 @@ comment line, surplus tokens are ignored, an error aborts the run with the refer
 
 Everything numerical is sequencing over the C ABI (host.py / multilevel.py / zoom.py / mapper.py / output.py); this file
 holds only the state machine of ICGenerator. Commands outside the accelerated path raise "not supported" errors instead
-of being silently ignored: grafic / HDF5 / swift output, masks,
-baryon_tf_on, import_level, reverse_small_k, dump_mask, center_output.
+of being silently ignored: HDF5 / swift output, baryon_tf_on, the *_field variants of the dump commands.
 """
 import ctypes as C
 import math
@@ -118,11 +117,12 @@ class ICGenerator:
         r["autopad"] = (self.setAutopad, i)
         r.update({"pvar": (self.setpvarValue, f), "center_grafic_output": (self.setCenteringOnRegion,),
                   "centre_output": (self.setCenteringOnRegion,), "center_output": (self.setCenteringOnRegion,),
-                  "dump_mask": (self.dumpMask,), "import_level": (self.importLevel, i, s)})
+                  "dump_mask": (self.dumpMask,), "import_level": (self.importLevel, i, s),
+                  "reverse_small_k": (self.reverseSmallK, f)})
         for name in ("num_neighbors", "num_neighbours",
                      "dump_grid_for_field", "dump_grid_fourier_for_field",
                      "dump_ps_field", "dump_tipsy_field",
-                     "baryon_tf_on", "zero_level_field", "reverse_small_k"):
+                     "baryon_tf_on", "zero_level_field"):
             r[name] = (self._unsupported(name),)
         return r
 
@@ -610,6 +610,14 @@ class ICGenerator:
     def reverse(self):
         self.initialiseRandomComponentIfUninitialised()
         self.outputField.reverse()
+
+    def reverseSmallK(self, kmax):
+        """ic.hpp:1690-1708: the sign of the modes below kmax reversed on every level."""
+        self.initialiseRandomComponentIfUninitialised()
+        for level in range(self.context.getNumLevels()):
+            fld = self.outputField.getFieldForLevel(level)
+            fld.toFourier()
+            fld.lib.gx_reverse_small_k(fld.ptr, fld.n, fld.dt, float(fld.grid.thisGridSize), float(kmax), fld.stream)
 
     def splice(self, newSeed):
         """ic.hpp:1706-1743."""

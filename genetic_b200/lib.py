@@ -73,6 +73,7 @@ PROTOTYPES = {
     "gx_apply_transfer_field": (ci, [vp, vp, ci, ci, cd, vp]),
     "gx_apply_filter": (ci, [vp, ci, ci, cd, P(FilterFactor), ci, vp]),
     "gx_unit_variance": (ci, [vp, ci, ci, vp]),
+    "gx_reverse_small_k": (ci, [vp, ci, ci, cd, cd, vp]),
     "gx_scale": (ci, [vp, ci, ci, cd, vp]),
     "gx_axpy": (ci, [vp, vp, ci, ci, cd, vp]),
     "gx_axpy_fourier": (ci, [vp, vp, ci, ci, cd, vp]),

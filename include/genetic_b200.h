@@ -18,7 +18,9 @@
  *    gx_field_download).
  *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
  *    asynchronous with respect to the host unless documented otherwise.
- *  - n must be a power of two in [4, 4096].
+ *  - n must be even and in [4, 4096]. Powers of two take the tuned passes; other even sizes the mixed-radix passes
+ *    (fft_generic.cu) -- every element-wise entry point and the real-space draw order accept them, while the Fourier-space
+ *    draw orders, gx_unigrid_ic and the gx_slab_* entry points need a power of two and fail with a message otherwise.
  */
 #ifndef GENETIC_B200_H
 #define GENETIC_B200_H
@@ -137,6 +139,8 @@ int gx_apply_filter(void *field, int n, int dtype, double grid_length, const gx_
 
 /* ---- element-wise and reductions ------------------------------------------------------------------- */
 int gx_unit_variance(void *field, int n, int dtype, void *stream); /* enforceUnitVariance, multilevelfield.hpp:498-510 */
+/* ICGenerator::reverseSmallK (ic.hpp:1690-1708): the sign of every mode with 0 < k^2 < kmax^2 reversed (Fourier space) */
+int gx_reverse_small_k(void *field, int n, int dtype, double grid_length, double kmax, void *stream);
 int gx_scale(void *field, int n, int dtype, double a, void *stream);                   /* Field::operator*=(value) */
 int gx_axpy(void *y, const void *x, int n, int dtype, double a, void *stream);         /* Field::addScaled :355-362 */
 int gx_axpy_fourier(void *y, const void *x, int n, int dtype, double a, void *stream); /* MultiLevelField::addScaled :194-212 */

@@ -188,6 +188,13 @@ class MockLib:
         F[ind & (a > 0)] /= a[ind & (a > 0)]
         return 0
 
+    def gx_reverse_small_k(self, p, n, dt, L, kmax, st):
+        k2 = ML.k_magnitude(ML.Grid(L, n)) ** 2
+        F = self.F(p, n)
+        sel = M.independent_mask(n) & (k2 < kmax * kmax) & (k2 != 0)
+        F[sel] = -F[sel]
+        return 0
+
     def gx_scale(self, p, n, dt, a, st):
         self.mem[_addr(p)].view(np.float64)[:] *= a
         return 0

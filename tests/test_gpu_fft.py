@@ -205,7 +205,7 @@ def test_filters_and_unit_variance():
 
 
 def test_errors_are_raised():
-    g = gb.Grid(10.0, 12)
+    g = gb.Grid(10.0, 9)                                # odd sizes are refused (even sizes: powers of two or mixed radix)
     with pytest.raises(gb.GxError):
         f = gb.Field(g, fourier=False)
         f.toFourier()
@@ -245,3 +245,47 @@ def test_power_spectrum_bins_on_device(n, dtype):
         return
     for i in (1, 2, 3):
         assert np.allclose(bins[i], ref[i], rtol=tol, atol=0)
+
+
+# ---- grid sizes that are not powers of two: the mixed-radix passes (csrc/fft_generic.cu) ---------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [6, 12, 20, 24, 48, 60, 66, 96, 100, 144])
+def test_mixed_radix_fft_vs_oracle(n, dtype):
+    """The reference takes any N through FFTW (fourier.hpp:521-563): radices 4, 2, 3, 5 and larger primes (66 = 2 * 3 * 11)."""
+    test_fft_forward_inverse_vs_oracle(n, dtype)
+
+
+@pytest.mark.parametrize("n", [12, 36])
+def test_mixed_radix_inverse_mirrors_first(n):
+    rng = np.random.default_rng(n)
+    F = rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))
+    g = gb.Grid(100.0, n)
+    f = gb.Field(g, F, fourier=True)
+    f.toReal()
+    assert _rel(f.getDataVector(), M.to_real(F)) < 1e-10
+
+
+def test_unigrid_48_real_space_seed_vs_oracle():
+    """Whole chain at 48^3 (real-space draw order, transfer, Zeldovich operator as a sweep + the mixed-radix inverse, particle
+    evaluation) against the oracle on the same seed."""
+    n, box, seed = 48, 100.0, 8896131
+    camb = os.path.join(GOLD, "planck_2018_transfer_out.dat")
+    cos = gb.CosmologicalParameters(0.3158, 0.6842, 0.8117, 200, ns=0.9660, hubble=0.6732)
+    pos, vel, mass, eps = gb.generate_unigrid_ic(n, box, seed, cos, camb, mode="real", out_dtype=np.float64)
+    ocos = M.Cosmology(0.3158, 0.6842, 0.8117, 200, ns=0.9660, hubble=0.6732)
+    opos, ovel, omass, oeps = M.unigrid_ic(n, box, seed, "real", camb, ocos)
+    assert np.abs(vel - ovel).max() < 1e-10 * np.abs(ovel).max()
+    d = np.abs(pos - opos)
+    d = np.minimum(d, box - d)
+    assert d.max() < 1e-10 * box
+    assert mass == omass and eps == oeps
+
+
+def test_fourier_draw_orders_refuse_mixed_radix_sizes():
+    g = gb.Grid(100.0, 48)
+    f = gb.Field(g, fourier=True)
+    rfg = gb.RandomFieldGenerator(f)
+    rfg.seed(1)
+    rfg.setDrawInFourierSpace(True)
+    with pytest.raises(gb.GxError, match="power-of-two"):
+        rfg.draw()

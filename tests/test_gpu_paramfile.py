@@ -114,7 +114,7 @@ def test_errors_abort_with_the_reference_message_format(tmp_path):
     p.write_text("Om 0.3\n# comment\nzoomgrid 2 64\n")
     with pytest.raises(icgen.L.GxError, match=r'Error ".*base grid" on line 3 \("zoomgrid 2 64"\)'):
         icgen.run_paramfile(str(p), log=lambda s: None)
-    p.write_text("base_grid 50 16\noutformat grafic\n")
+    p.write_text("base_grid 50 16\noutformat gadgethdf\n")
     with pytest.raises(icgen.L.GxError, match="not supported"):
         icgen.run_paramfile(str(p), log=lambda s: None)
     p.write_text("no_such_command 1\n")
@@ -122,3 +122,27 @@ def test_errors_abort_with_the_reference_message_format(tmp_path):
         icgen.run_paramfile(str(p), log=lambda s: None)
 
 
+
+
+def test_reverse_small_k_command(golden_dir, tmp_path):
+    """`reverse_small_k kmax` (ic.hpp:1690-1708): modes with 0 < k^2 < kmax^2 change sign, all others are untouched."""
+    shutil.copy(os.path.join(golden_dir, "camb_transfer_kmax40_z0.dat"), tmp_path)
+    base = ("Om 0.279\nOl 0.721\ns8 0.817\nzin 99\ncamb %s\nrandom_seed_real_space 8896131\noutformat tipsy\nbasegrid 50.0 32\n"
+            % str(tmp_path / "camb_transfer_kmax40_z0.dat"))
+    fields = []
+    for extra in ("", "reverse_small_k 0.9\n"):
+        gen = icgen.ICGenerator(log=lambda s: None)
+        for line in (base + extra).splitlines():
+            gen.run_line(line)
+        gen.initialiseRandomComponentIfUninitialised()
+        f = gen.outputField.getFieldForLevel(0)
+        f.toFourier()
+        fields.append(f.getDataVector().copy())
+    n, L = 32, 50.0
+    kmin = 2 * np.pi / L
+    idx = np.fft.fftfreq(n, 1.0 / n)
+    k2 = ((idx[:, None, None] * kmin) ** 2 + (idx[None, :, None] * kmin) ** 2) + (np.arange(n // 2 + 1)[None, None, :] * kmin) ** 2
+    flip = (k2 < 0.9 * 0.9) & (k2 != 0) & M.independent_mask(n)
+    assert 100 < flip.sum() < flip.size // 2
+    assert np.array_equal(fields[1][flip], -fields[0][flip])
+    assert np.array_equal(fields[1][~flip], fields[0][~flip])
