@@ -14,6 +14,7 @@
 #ifndef GENETIC_B200_MODIF_HPP
 #define GENETIC_B200_MODIF_HPP
 #include "genetic_b200_zoom.hpp"
+#include "genetic_b200_grafic.hpp"
 #include <cmath>
 #include <cstdio>
 #include <functional>
@@ -508,7 +509,53 @@ public:
   std::unique_ptr<modifications::TypedField<T>> outputField;
   std::unique_ptr<modifications::ModificationManager<T>> manager;
   T variance_filterscale = T(-1);
+  size_t subsample = 1, supersample = 1;      // grafic output only in this layer (virtual levels of the centred stack)
+  T pvarValue = T(1);                         // ic.hpp:148
+  bool centerOnTargetRegion = false;          // ic.hpp:126, `center_output`
   static void log(const std::string &s) { modifications::logger()(s); }
+
+  std::array<T, 3> graficCentre() {           // ic.hpp:1313-1319
+    if (centerOnTargetRegion) return this->centre;
+    const T half = this->context.getGridForLevel(0).thisGridSize / T(2);
+    return {half, half, half};
+  }
+  // ICGenerator::getCentre (ic.hpp:1372-1386) + Grid::getCentreWrapped (grid.hpp:466-494): after an id file has been loaded
+  // the current point is the centre of the flagged cells of the deepest level that has any
+  void updateCentreFromFlags() {
+    size_t level = 0;
+    std::vector<size_t> flags;
+    for (size_t l = this->context.getNumLevels(); l-- > 0;) {
+      flags.clear();
+      this->context.getGridForLevel(l).getFlaggedCells(flags);
+      if (!flags.empty()) { level = l; break; }
+    }
+    if (flags.empty()) throw std::runtime_error("Cannot calculate the center of an empty region");
+    std::sort(flags.begin(), flags.end());
+    const auto &g = this->context.getGridForLevel(level);
+    const size_t n = g.size;
+    const double Lbox = (double) g.periodicDomainSize, dx = (double) g.cellSize;
+    for (int a = 0; a < 3; ++a) {
+      auto pos = [&](size_t id) {
+        const size_t c = a == 0 ? id / (n * n) : (a == 1 ? (id / n) % n : id % n);
+        return ((double) c * dx + (double) g.offsetLower[a]) + dx / 2;
+      };
+      const double p0 = pos(flags[0]);
+      double run = 0;
+      for (size_t i = 1; i < flags.size(); ++i) {
+        double d = pos(flags[i]) - p0;
+        if (d > Lbox / 2) d -= Lbox;
+        if (d < -Lbox / 2) d += Lbox;
+        run += d;
+      }
+      run /= (double) flags.size();
+      double x = std::fmod(run + p0, Lbox);
+      if (x < 0) x += Lbox;
+      this->centre[a] = (T) x;
+    }
+    char buf[160];
+    snprintf(buf, sizeof buf, "Centre of region is %.12g %.12g %.12g", (double) this->centre[0], (double) this->centre[1], (double) this->centre[2]);
+    log(buf);
+  }
 
   void initialiseRandomComponentIfUninitialised() {  // ic.hpp:1238-1259
     if (outputField) return;
@@ -533,7 +580,41 @@ public:
     auto num = [&]() { double v; if (!(ss >> v)) throw std::runtime_error("Insufficient arguments for command " + cmd); return v; };
     auto str = [&]() { std::string v; if (!(ss >> v)) throw std::runtime_error("Insufficient arguments for command " + cmd); return v; };
     char buf[256];
-    if (cmd == "filtering_scale") { variance_filterscale = (T) num(); if (manager) manager->variance_filterscale = variance_filterscale; }
+    auto path = [this](const std::string &p) { return p[0] == '/' ? p : this->dir + "/" + p; };
+    const bool isGrafic = this->outputFormat == "grafic";
+    if (cmd == "outformat") {
+      std::string f = str();
+      for (auto &c : f) c = (char) std::tolower(c);
+      if (f == "grafic" || f == "5") this->outputFormat = "grafic";
+      else { std::istringstream again(f); Base::runCommand(cmd, again); }
+    }
+    else if (cmd == "subsample") subsample = (size_t) num();
+    else if (cmd == "supersample") supersample = (size_t) num();
+    else if (cmd == "pvar") pvarValue = (T) num();
+    else if (cmd == "center_output" || cmd == "centre_output" || cmd == "center_grafic_output") centerOnTargetRegion = true;
+    else if (cmd == "dump_mask")
+      grafic::dumpMask<T>(this->context, graficCentre(), subsample, supersample, this->zoomParticleArray, this->outputFolder);
+    else if (cmd == "idfile" || cmd == "id_file" || cmd == "append_idfile" || cmd == "merge_id_file") {
+      const bool replace = cmd == "idfile" || cmd == "id_file";
+      const std::vector<size_t> ids = Base::readIds(path(str()));
+      if (isGrafic) {  // ensureParticleGeneratorInitialised (ic.hpp:1140-1147): ids are the cells of the grafic levels in turn
+        grafic::GraficMapper<T> m(this->context, this->centre, subsample, supersample);
+        if (replace) m.unflagAllParticles();
+        m.flagParticles(ids);
+      } else {
+        auto m = this->mapper();
+        if (replace) m->unflagAllParticles();
+        m->flagParticles(ids);
+      }
+      updateCentreFromFlags();
+    }
+    else if ((cmd == "dump_idfile" || cmd == "dump_id_file") && isGrafic) {
+      std::vector<size_t> ids;
+      grafic::GraficMapper<T>(this->context, this->centre, subsample, supersample).getFlaggedParticles(ids);
+      std::ofstream o(path(str()));
+      for (size_t i : ids) o << i << std::endl;
+    }
+    else if (cmd == "filtering_scale") { variance_filterscale = (T) num(); if (manager) manager->variance_filterscale = variance_filterscale; }
     else if (cmd == "calculate") {
       const std::string name = str();
       initialiseRandomComponentIfUninitialised();
@@ -587,6 +668,16 @@ public:
     if (manager->hasModifications()) manager->applyModifications();
     if (outputField->getTransferType() == modifications::TransferType::whitenoise)
       outputField->applyPowerSpectrumFor(modifications::TransferType::all);
+    const std::string base0 = this->outputFolder + "/" + this->outputFilename;
+    if (this->outputFormat == "grafic") {  // ic.hpp:1312-1324: the grids in turn, no particle mapper
+      particle::MultiLevelParticleGenerator<T> ggen(this->context, outputField->getFields());
+      outputField->toReal();
+      grafic::save<T>(base0 + ".grafic", this->context, ggen, outputField->getFields(), this->cosmo, pvarValue, graficCentre(),
+                      subsample, supersample, this->zoomParticleArray);
+      return;
+    }
+    if (subsample != 1 || supersample != 1)
+      throw std::runtime_error("subsample / supersample are implemented for grafic output only in the C++ layer");
     this->pMapper = this->mapper();
     particle::MultiLevelParticleGenerator<T> gen(this->context, outputField->getFields());
     const double boxlen = (double) this->context.getGridForLevel(0).periodicDomainSize;

@@ -91,3 +91,58 @@ def test_cpp_velocity_modification_golden(golden_dir, tmp_path):
     assert np.abs(ours["vel"] - gold["vel"]).max() < 1e-4 * max(1.0, np.abs(gold["vel"]).max())
     values = [float(l.split("=")[1]) for l in log if l.startswith("vx: calculated value")]
     assert len(values) == 2 and abs(values[1]) < 1e-6 * max(1.0, abs(values[0]))   # `modify vx absolute 0` holds after done
+
+
+# ---- grafic output, grafic mapper, masks in C++ (include/genetic_b200_grafic.hpp) ------------------------------------------
+def _run_without_done(golden_dir, tmp_path, test):
+    """The geometry commands of a golden paramfile through the C++ driver with the `done` line removed: id files and
+    masks depend on the grids and flags only, so these run without a device."""
+    exe = gbuild.build_host(program="genetic_b200_modify")
+    d = tmp_path / test
+    shutil.copytree(os.path.join(golden_dir, test), d)
+    text = [l for l in open(d / "paramfile.txt").read().splitlines() if l.strip().lower() != "done"]
+    (d / "paramfile.txt").write_text("\n".join(text) + "\n")
+    r = subprocess.run([exe, str(d / "paramfile.txt")], capture_output=True, text=True, cwd=str(d))
+    assert r.returncode == 0, r.stderr
+    return d
+
+
+@pytest.mark.parametrize("test", ["mapper_test_02a_grafic", "mapper_test_02b_grafic_zoom_to_coarse"])
+def test_cpp_grafic_mapper_id_goldens(golden_dir, tmp_path, test):
+    d = _run_without_done(golden_dir, tmp_path, test)
+    assert open(str(d / "reference.txt")).read().split() == open(str(d / "output.txt")).read().split()
+
+
+@pytest.mark.parametrize("test", ["test_08a_mask_lagrange_volume", "test_08b_mask_virtual_architecture", "test_08c_centering_masks",
+                                  "test_08d_mask_flag_interaction", "test_08e_mask_multiple_virtual_grids",
+                                  "test_08f_mask_multiple_supersample"])
+def test_cpp_refinement_mask_goldens(golden_dir, tmp_path, test):
+    d = _run_without_done(golden_dir, tmp_path, test)
+    gold = np.load(str(d / "reference_mask.npz"))
+    assert len(gold.files) > 0
+    for k in gold.files:
+        m = np.load(str(d / (k + ".npy")))
+        assert m.shape == gold[k].shape and np.array_equal(m, gold[k].astype(m.dtype)), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("test", ["test_12_grafic", "test_08e_mask_multiple_virtual_grids", "test_08f_mask_multiple_supersample"])
+def test_cpp_grafic_output_goldens(golden_dir, tmp_path, test):
+    """All ten files of every level (real and virtual) of the reference's grafic goldens through the C++ writer."""
+    from genetic_b200 import grafic as GF
+    d, _, _ = _run(golden_dir, tmp_path, test)
+    gold = np.load(str(d / "reference_grafic.npz"))
+    resolutions = sorted({k.split("/")[0] for k in gold.files}, key=int)
+    mine = sorted((p for p in os.listdir(d) if ".grafic_" in p), key=lambda p: int(p.rsplit("_", 1)[1]))
+    assert [p.rsplit("_", 1)[1] for p in mine] == resolutions
+    for res, p in zip(resolutions, mine):
+        lvl = GF.read_grafic_level(str(d / p))
+        np.testing.assert_allclose(np.array(lvl["header"], dtype=np.float64), gold[res + "/header"], rtol=2e-7)
+        for k in lvl:
+            if k == "header":
+                continue
+            ref = gold["%s/%s" % (res, k)]
+            if k in ("ic_particle_ids", "ic_refmap", "ic_pvar_00001"):
+                assert np.array_equal(lvl[k], ref), (res, k)
+            else:
+                assert np.abs(lvl[k].astype(np.float64) - ref).max() < 1e-4 * max(1.0, np.abs(ref).max() / 10), (res, k)
