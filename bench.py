@@ -302,8 +302,10 @@ def run_ours(args):
     # host arrays: full component-major arrays if they fit 24 GiB, else a ring
     cap = n3 if 6 * n3 * osz <= (24 << 30) else (8 << 30) // (3 * osz)
     hpos, hvel = C.c_void_p(), C.c_void_p()
-    lib.gx_host_alloc_pinned(C.byref(hpos), 3 * cap * osz)
-    lib.gx_host_alloc_pinned(C.byref(hvel), 3 * cap * osz)
+    with L.numa_local(torch.cuda.current_device()) as numa:      # pinned pages on the GPU's NUMA node
+        lib.gx_host_alloc_pinned(C.byref(hpos), 3 * cap * osz)
+        lib.gx_host_alloc_pinned(C.byref(hvel), 3 * cap * osz)
+    pinned_cpus = numa.cpus
 
     prm = L.IcParams()
     prm.n, prm.dtype, prm.out_dtype = n, dt, L.F32
@@ -443,7 +445,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (each field %.2f GB)" % (fbytes / 1e9),
                        "e2e_host_buffers": "full component-major arrays" if cap == n3 else
                        "pinned RING of %d particles per component (6 x n^3 x 4 bytes = %.0f GB does not fit the pinned "
-                       "budget): every byte is copied, the IC is not retained" % (cap, 6 * n3 * osz / 1e9)},
+                       "budget): every byte is copied, the IC is not retained" % (cap, 6 * n3 * osz / 1e9),
+                       "e2e_pinned_on_cpus": ("%d-%d (GPU-local NUMA node, NVML)" % (pinned_cpus[0], pinned_cpus[-1])) if pinned_cpus else "default"},
             "clocks": clocks,
             "e2e": None if args.no_e2e else {"value": n3 / e2e_s, "unit": "particles/s", "h2d_bytes_per_step": tab_bytes,
                                              "d2h_bytes_per_step": 6 * n3 * osz, "ms_per_step": e2e_s * 1e3},

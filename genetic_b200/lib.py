@@ -154,3 +154,42 @@ def load():
                           "(there is no CPU fallback)" % LIBPATH)
         _lib = _Lib(C.CDLL(LIBPATH))
     return _lib
+
+
+class numa_local:
+    """Context manager: run the body on the CPUs NVML reports as local to CUDA device `device`, then restore the affinity.
+    Pinned host buffers allocated inside land on the GPU's NUMA node (first touch), which is what the PCIe copies of the
+    end-to-end path want; outside, host work keeps all the cores. A box without NVML or with one NUMA node is left alone."""
+
+    def __init__(self, device=0):
+        self.device, self.saved, self.cpus = device, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.device
+            if vis:
+                tok = vis.split(",")[self.device].strip()
+                index = int(tok) if tok.isdigit() else self.device
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            have = os.sched_getaffinity(0)
+            use = local & have
+            if use and use != have:
+                self.saved = have
+                os.sched_setaffinity(0, use)
+            self.cpus = sorted(use) if use else None
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False

@@ -425,8 +425,9 @@ class EmitStager:
     def enable_host(self):
         if self.host is None:
             half = self.dev[0][0].numel()
-            self.host = [(self.torch.empty(half, dtype=self.torch.uint8, pin_memory=True),
-                          self.torch.empty(half, dtype=self.torch.uint8, pin_memory=True)) for _ in range(2)]
+            with L.numa_local(self.torch.cuda.current_device()):           # pinned pages on this GPU's NUMA node
+                self.host = [(self.torch.empty(half, dtype=self.torch.uint8, pin_memory=True),
+                              self.torch.empty(half, dtype=self.torch.uint8, pin_memory=True)) for _ in range(2)]
 
     def emit(self, work, axis, grid, vel_ratio, out_dtype, to_host):
         torch, g = self.torch, self.geo
