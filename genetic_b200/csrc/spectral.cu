@@ -377,7 +377,7 @@ namespace gx {
 // k = sqrt(ix^2 + iy^2 + iz^2) * 2 pi / L if kmin <= k < kmax. Here: one thread per stored slot with that multiplicity as its
 // weight, bins in shared memory per CTA, double atomics into the result. bins[4][nbins] = count, sum k, sum |delta|^2, sum C.
 template <typename T>
-__global__ void ps_bins_kernel(const cplx<T> *f, const cplx<T> *cov, int n, T kw, T kmin, T kmax, T inv_dklog, int nbins,
+__global__ void ps_bins_kernel(const cplx<T> *f, const cplx<T> *cov, int n, T kw, const int *__restrict__ bin_of_m, int nbins,
                                double *bins) {
   extern __shared__ double sb[];  // [4][nbins]
   for (int i = threadIdx.x; i < 4 * nbins; i += blockDim.x) sb[i] = 0.0;
@@ -390,11 +390,10 @@ __global__ void ps_bins_kernel(const cplx<T> *f, const cplx<T> *cov, int n, T kw
     const int wab = (a == h ? 2 : 1) * (b == h ? 2 : 1);
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const int m = sa * sa + sb2 * sb2 + c * c;
+      const int idx = bin_of_m[m];  // host-made with the C library's log10: a bin edge is one ulp of log10 wide (below)
+      if (idx < 0) continue;
       const T kfft = (T) sqrt((double) m);
       const T k = kfft * kw;
-      if (!(k >= kmin && k < kmax)) continue;
-      const int idx = (int) (inv_dklog * log10(k / kmin));
-      if (idx < 0 || idx >= nbins) continue;
       const double w = (double) (wab * (c == 0 ? 1 : 2));
       const cplx<T> v = f[row * nc + c];
       T vabs = (T) hypot((double) v.x, (double) v.y);  // std::abs(complex)
@@ -418,18 +417,36 @@ static int power_spectrum_bins_t(void *field, void *cov, int n, double L, int nb
   const T boxLength = (T) L;
   const T kmax = (T) M_PI / boxLength * (T) n, kmin = 2.0f * (T) M_PI / boxLength;
   const T dklog = (T) log10((double) (kmax / kmin)) / (T) nbins, kw = 2.0f * (T) M_PI / boxLength;
+  // The bin of a mode depends on m = ix^2 + iy^2 + iz^2 only. Modes sit exactly on bin edges (k / kmin = 2 when (n/2)^(j/100) = 2),
+  // where the truncation of log10(k / kmin) / dklog turns on the last bit of log10: the table is made on the host with the C
+  // library's log10, the one the reference calls, instead of the device's (1 ulp) -- found by the reference's test_01d on the
+  // B200, whose power-spectrum file moved 12 modes between two bins.
+  const long h = n / 2, mcount = 3 * h * h + 1;
+  std::vector<int> bin_of_m((size_t) mcount, -1);
+  const T inv_dklog = (T) (1.0f / dklog);
+  for (long m = 0; m < mcount; ++m) {
+    const T kfft = (T) std::sqrt((double) m);
+    const T k = kfft * kw;
+    if (!(k >= kmin && k < kmax)) continue;
+    const int idx = (int) (inv_dklog * std::log10(k / kmin));
+    if (idx >= 0 && idx < nbins) bin_of_m[(size_t) m] = idx;
+  }
+  int *d_bin_of_m = nullptr;
+  GX_CUDA_CHECK(cudaMalloc(&d_bin_of_m, sizeof(int) * mcount));
+  GX_CUDA_CHECK(cudaMemcpyAsync(d_bin_of_m, bin_of_m.data(), sizeof(int) * mcount, cudaMemcpyHostToDevice, st));
   double *d_bins = nullptr;
   GX_CUDA_CHECK(cudaMalloc(&d_bins, sizeof(double) * 4 * nbins));
   GX_CUDA_CHECK(cudaMemsetAsync(d_bins, 0, sizeof(double) * 4 * nbins, st));
   const long rows = (long) n * n;
   const int grid = (int) (rows < 148 * 8 ? rows : 148 * 8);
-  ps_bins_kernel<T><<<grid, 256, sizeof(double) * 4 * nbins, st>>>((const cplx<T> *) field, (const cplx<T> *) cov, n, kw, kmin, kmax,
-                                                                 (T) (1.0f / dklog), nbins, d_bins);
+  ps_bins_kernel<T><<<grid, 256, sizeof(double) * 4 * nbins, st>>>((const cplx<T> *) field, (const cplx<T> *) cov, n, kw, d_bin_of_m,
+                                                                 nbins, d_bins);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_bins, d_bins, sizeof(double) * 4 * nbins, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_bins);
+  cudaFree(d_bin_of_m);
   if (e != cudaSuccess) return fail(std::string("gx_power_spectrum_bins: ") + cudaGetErrorString(e));
   return 0;
 }

@@ -208,3 +208,8 @@ for t, files in {"mapper_test_02a_grafic": ("paramfile.txt", "test_ids.txt", "re
                  "test_11_import": ("paramfile.txt", "reference_grid/grid-0.npy")}.items():
     for f in files:
         cp(f"{REF}/{t}/{f}", f"{HERE}/{t}/{f}")
+
+# test_01d (two nested zooms): the three power-spectrum dumps -- modes sit exactly on bin edges there (found on the B200)
+cp(f"{REF}/test_01d_two_zooms/paramfile.txt", f"{HERE}/test_01d_two_zooms/paramfile.txt")
+for l in (0, 1, 2):
+    cp(f"{REF}/test_01d_two_zooms/reference_ps/test_01d_{l}.ps", f"{HERE}/test_01d_two_zooms/reference_ps/test_01d_{l}.ps")

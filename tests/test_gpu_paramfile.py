@@ -146,3 +146,14 @@ def test_reverse_small_k_command(golden_dir, tmp_path):
     assert 100 < flip.sum() < flip.size // 2
     assert np.array_equal(fields[1][flip], -fields[0][flip])
     assert np.array_equal(fields[1][~flip], fields[0][~flip])
+
+
+def test_power_spectrum_dumps_of_two_nested_zooms_golden_01d(golden_dir, tmp_path):
+    """dump_ps on three levels against the reference's files (compare.py: rtol 1e-4 on every column, the mode counts included).
+    Modes sit exactly on the edges of the logarithmic bins here (k / kmin = 2 is the edge of bin 20 when n / 2 = 32), so the
+    bin a mode falls into turns on the last bit of log10: the device path takes its bin table from the host's C library."""
+    d, _ = _run(golden_dir, tmp_path, "test_01d_two_zooms")
+    for level in (0, 1, 2):
+        ref = np.loadtxt(str(d / "reference_ps" / ("test_01d_%d.ps" % level)))
+        mine = np.loadtxt(str(d / ("test_1_%d.ps" % level)))
+        np.testing.assert_allclose(mine, ref, rtol=1e-4)

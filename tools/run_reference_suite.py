@@ -18,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-REF = "/root/reference/genetIC/tests"
+REF = os.environ.get("GX_REFERENCE_TESTS", "/root/reference/genetIC/tests")   # a copy of the test DATA on a GPU box
 
 
 def read_particles(fn):
