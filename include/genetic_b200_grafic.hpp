@@ -255,6 +255,27 @@ template <typename T> void saveNpy(const std::string &fn, const std::vector<T> &
   o.write(reinterpret_cast<const char *>(data.data()), (std::streamsize) (n * n * n * sizeof(T)));
 }
 
+// io::numpy::LoadArrayFromNumpy for the files saveNpy / numpy.save write: version 1.0 header, C order, '<f8' or '<f4'
+template <typename T> std::vector<T> loadNpy(const std::string &fn, size_t n) {
+  std::ifstream f(fn, std::ios::binary);
+  if (!f.is_open()) throw std::runtime_error("File " + fn + " not found");
+  char magic[10];
+  f.read(magic, 10);
+  if (std::memcmp(magic, "\x93NUMPY", 6) != 0) throw std::runtime_error("Not a numpy file: " + fn);
+  const size_t hl = (unsigned char) magic[8] | ((size_t) (unsigned char) magic[9] << 8);
+  std::string h(hl, ' ');
+  f.read(&h[0], (std::streamsize) hl);
+  char shape[64];
+  snprintf(shape, sizeof shape, "(%zu, %zu, %zu)", n, n, n);
+  if (h.find(shape) == std::string::npos) throw std::runtime_error("Incorrect size for imported numpy array");
+  if (h.find(sizeof(T) == 8 ? "<f8" : "<f4") == std::string::npos) throw std::runtime_error("Incorrect data type for imported numpy array");
+  if (h.find("'fortran_order': False") == std::string::npos) throw std::runtime_error("Imported numpy array must be in C order");
+  std::vector<T> data(n * n * n);
+  f.read((char *) data.data(), (std::streamsize) (data.size() * sizeof(T)));
+  if (!f) throw std::runtime_error("Imported numpy array is truncated");
+  return data;
+}
+
 // ICGenerator::dumpMask (ic.hpp:973-994): mask-<level>.npy in the coordinates of the centred grids
 template <typename T>
 void dumpMask(multilevelgrid::MultiLevelGrid<T> &context, const std::array<T, 3> &centre, size_t subsample, size_t supersample,

@@ -242,6 +242,72 @@ protected:
   int direction;
 };
 
+// linearmodification.hpp:288-411: specific angular momentum of the flagged Lagrangian patch about its centre,
+// -(q - q_c) x grad(Phi) with the 4th-order real-space stencil
+template <typename T> class AngMomentumModification : public OverdensityModification<T> {
+public:
+  AngMomentumModification(Context<T> &c, const cosmology::CosmologicalParameters<T> &cos, int direction_)
+      : OverdensityModification<T>(c, cos), direction(direction_) {
+    if (direction < 0 || direction > 2) throw std::runtime_error("Angular momentum direction must be 0 (x), 1 (y) or 2 (z)");
+  }
+protected:
+  std::shared_ptr<fields::Field<T>> calculateLocalisationCovector(const grids::Grid<T> &g) override {
+    const long n = (long) g.size, S = (long) g.simEquivalentSize;
+    const auto &flags = this->flaggedCellsFinestGrid;
+    const double dx = (double) g.cellSize, Lbox = (double) g.periodicDomainSize;
+    auto coordOf = [n](size_t id) { return std::array<long, 3>{(long) (id / (size_t) (n * n)), (long) ((id / (size_t) n) % (size_t) n), (long) (id % (size_t) n)}; };
+    auto pos = [&](long c, int a) { return ((double) c * dx + (double) g.offsetLower[a]) + dx / 2; };
+    auto wrapped = [Lbox](double d) { if (d > Lbox / 2) d -= Lbox; if (d < -Lbox / 2) d += Lbox; return d; };
+    double qc[3];  // Grid::getCentreWrapped (grid.hpp:466-494)
+    {
+      const auto c0 = coordOf(flags[0]);
+      for (int a = 0; a < 3; ++a) {
+        const double p0 = pos(c0[a], a);
+        double run = 0;
+        for (size_t i = 1; i < flags.size(); ++i) run += wrapped(pos(coordOf(flags[i])[a], a) - p0);
+        run /= (double) flags.size();
+        double x = std::fmod(run + p0, Lbox);
+        qc[a] = x < 0 ? x + Lbox : x;
+      }
+    }
+    const double norm = (double) flags.size() * dx, ca = 1. / 12. / norm, cb = -2. / 3. / norm;
+    const int d = direction, d1 = (direction + 1) % 3, d2 = (direction + 2) % 3;
+    std::vector<T> data(g.size3, T(0));
+    auto step = [S](std::array<long, 3> c, int ax, long s) {
+      long v = c[ax] + s;
+      if (v > S - 1) v -= S;
+      if (v < 0) v += S;
+      c[ax] = v;
+      return c;
+    };
+    auto add = [&](const std::array<long, 3> &c, double v) { data[(size_t) ((c[0] * n + c[1]) * n + c[2])] += (T) v; };
+    for (int ax = 0; ax < 3; ++ax) {
+      if (ax == d) continue;
+      for (size_t id : flags) {
+        const auto c = coordOf(id);
+        double dq[3];
+        for (int a = 0; a < 3; ++a) dq[a] = wrapped(qc[a] - pos(c[a], a));
+        const double coeff = ax == d2 ? dq[d1] : -dq[d2];
+        const auto m1 = step(c, ax, -1), p1 = step(c, ax, 1), m2 = step(m1, ax, -1), p2 = step(p1, ax, 1);
+        add(m2, coeff * ca); add(m1, coeff * cb); add(p1, -coeff * cb); add(p2, -coeff * ca);
+      }
+    }
+    auto f = std::make_shared<fields::Field<T>>(g, data, false);
+    f->toFourier();
+    return f;
+  }
+  void turnLocalisationCovectorIntoModificationCovector(TypedField<T> &field) override {
+    OverdensityModification<T>::turnLocalisationCovectorIntoModificationCovector(field);
+    const double scale = (double) cosmology::zeldovichVelocityToOffsetRatio<T>(this->cosmo);
+    for (size_t l = 0; l < field.getNumLevels(); ++l) {
+      auto &f = field.getFieldForLevel(l);
+      f.toFourier();
+      check(gx_scale_inv_k2(f.devicePointer(), (int) f.getGrid().size, dtype_of<T>(), (double) f.getGrid().thisGridSize, -scale, 0, nullptr));
+    }
+  }
+  int direction;
+};
+
 // ---- quadratic modification: variance of the high-pass filtered field inside the flagged region -------------------------
 template <typename T> class FilteredVarianceModification {
 public:
@@ -367,6 +433,8 @@ private:
     if (nm == "potential") return std::unique_ptr<LinearModification<T>>(new PotentialModification<T>(*ctx, cosmo));
     if (nm == "vx" || nm == "vy" || nm == "vz")
       return std::unique_ptr<LinearModification<T>>(new VelocityModification<T>(*ctx, cosmo, nm[1] - 'x'));
+    if (nm == "lx" || nm == "ly" || nm == "lz")
+      return std::unique_ptr<LinearModification<T>>(new AngMomentumModification<T>(*ctx, cosmo, nm[1] - 'x'));
     throw std::runtime_error(nm + " is an unknown modification name");
   }
   std::unique_ptr<FilteredVarianceModification<T>> makeVariance() {
@@ -588,6 +656,47 @@ public:
       if (f == "grafic" || f == "5") this->outputFormat = "grafic";
       else { std::istringstream again(f); Base::runCommand(cmd, again); }
     }
+    else if (cmd == "zerolevel" || cmd == "zero_level") {  // ic.hpp:1650-1670, for tests
+      const size_t level = (size_t) num();
+      snprintf(buf, sizeof buf, "*** Warning: your script calls zeroLevel(%zu). This is intended for testing purposes only!", level);
+      log(buf);
+      initialiseRandomComponentIfUninitialised();
+      if (level + 1 > outputField->getNumLevels()) throw std::runtime_error("Specified level does not exist.");
+      auto &f = outputField->getFieldForLevel(level);
+      check(gx_memset_zero(f.devicePointer(), gx_field_bytes((int) f.getGrid().size, dtype_of<T>()), nullptr));
+    }
+    else if (cmd == "reverse") {  // MultiLevelField::reverse, multilevelfield.hpp:182-191
+      initialiseRandomComponentIfUninitialised();
+      for (size_t l = 0; l < outputField->getNumLevels(); ++l) outputField->getFieldForLevel(l) *= T(-1);
+    }
+    else if (cmd == "reverse_small_k") {  // ic.hpp:1690-1708
+      const double kmax = num();
+      initialiseRandomComponentIfUninitialised();
+      for (size_t l = 0; l < outputField->getNumLevels(); ++l) {
+        auto &f = outputField->getFieldForLevel(l);
+        f.toFourier();
+        check(gx_reverse_small_k(f.devicePointer(), (int) f.getGrid().size, dtype_of<T>(), (double) f.getGrid().thisGridSize, kmax, nullptr));
+      }
+    }
+    else if (cmd == "velocity_offset") {  // ic.hpp:285-289: km/s -> km a^1/2 s^-1
+      const T conversion = (T) std::pow((double) this->cosmo.scalefactor, -0.5);
+      for (int a = 0; a < 3; ++a) this->velOffset[a] = (T) num() * conversion;
+    }
+    else if (cmd == "import_level") {  // ic.hpp:809-821 + Field::loadGridData
+      const size_t level = (size_t) num();
+      const std::string fn = path(str());
+      initialiseRandomComponentIfUninitialised();
+      log("Importing random field on level " + std::to_string(level) + " from " + fn);
+      auto &f = outputField->getFieldForLevel(level);
+      std::vector<T> data = grafic::loadNpy<T>(fn, f.getGrid().size);
+      f.setFourier(false);
+      f.getDataVector() = data;
+      f.toFourier();
+      f.applyTransferFunction(*specDM, -0.5);  // back to white noise
+      log("... success!");
+    }
+    else if (cmd == "dump_tipsy") dumpTipsy(str());
+    else if (cmd == "adapt_mask") adaptMask((size_t) num());
     else if (cmd == "subsample") subsample = (size_t) num();
     else if (cmd == "supersample") supersample = (size_t) num();
     else if (cmd == "pvar") pvarValue = (T) num();
@@ -628,7 +737,7 @@ public:
       manager->addModificationToList(name, type, (T) target);
     }
     else if (cmd == "clear_modifications") { if (manager) manager->clearModifications(); }
-    else if (cmd == "apply_modifications") { initialiseRandomComponentIfUninitialised(); manager->applyModifications(); }
+    else if (cmd == "apply_modifications") { initialiseRandomComponentIfUninitialised(); applyModificationsLogged(); }
     else if (cmd == "chi2") {
       initialiseRandomComponentIfUninitialised();
       snprintf(buf, sizeof buf, "Calculated chi^2 = %.10g (dof = %zu)", (double) outputField->getChi2(), this->context.getNumDof());
@@ -662,10 +771,80 @@ public:
     }
   }
 
+  // ModificationManager::applyModifications with its chi^2 bookkeeping (modificationmanager.hpp:93-125)
+  void applyModificationsLogged() {
+    const T pre = outputField->getChi2();
+    log("");
+    log("Applying modifications");
+    manager->applyModifications();
+    const T post = outputField->getChi2();
+    char buf[160];
+    snprintf(buf, sizeof buf, "   Post-modification chi^2 = %g", (double) post); log(buf);
+    snprintf(buf, sizeof buf, "  Modification Delta chi^2 = %g", (double) (post - pre)); log(buf);
+    snprintf(buf, sizeof buf, "           d.o.f. in field = %zu", this->context.getNumDof()); log(buf);
+    log("");
+  }
+
+  // ICGenerator::adaptMask (ic.hpp:1545-1575): working up from the deepest zoom, the cells each level replaces become the
+  // footprint of the level below's zoom cells on it, padded by nPadCells (Grid::expandFlaggedRegion, grid.hpp:277-306)
+  void adaptMask(size_t nPadCells) {
+    const size_t nl = this->context.getNumLevels();
+    if (nl < 3) throw std::runtime_error("Adapting the mask requires there to be more than one zoom level");
+    auto &z = this->zoomParticleArray;
+    for (size_t level = nl - 2; level >= 1; --level) {
+      const auto &cur = this->context.getGridForLevel(level);
+      const auto &above = this->context.getGridForLevel(level - 1);
+      const long ratio = std::lround((double) above.cellSize / (double) cur.cellSize), n = (long) cur.size, na = (long) above.size;
+      long corner[3];
+      for (int a = 0; a < 3; ++a) corner[a] = std::lround((double) (cur.offsetLower[a] - above.offsetLower[a]) / (double) above.cellSize);
+      std::vector<size_t> cells;
+      for (size_t id : z[level]) {
+        const long c[3] = {(long) (id / (size_t) (n * n)), (long) ((id / (size_t) n) % (size_t) n), (long) (id % (size_t) n)};
+        cells.push_back((size_t) (((corner[0] + c[0] / ratio) * na + (corner[1] + c[1] / ratio)) * na + (corner[2] + c[2] / ratio)));
+      }
+      auto uniq = [](std::vector<size_t> &v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+      uniq(cells);
+      for (size_t it = 0; it < nPadCells; ++it)
+        for (int axis = 0; axis < 3; ++axis) {
+          const size_t have = cells.size();
+          for (size_t k = 0; k < have; ++k) {
+            long c[3] = {(long) (cells[k] / (size_t) (na * na)), (long) ((cells[k] / (size_t) na) % (size_t) na), (long) (cells[k] % (size_t) na)};
+            for (long stepv : {1L, -1L}) {
+              long d[3] = {c[0], c[1], c[2]};
+              d[axis] = ((d[axis] + stepv) % na + na) % na;
+              cells.push_back((size_t) ((d[0] * na + d[1]) * na + d[2]));
+            }
+          }
+          uniq(cells);
+        }
+      z[level - 1] = cells;
+      if (level == 1) break;
+    }
+  }
+
+  // ic.hpp:853-862 + io::tipsy::saveFieldTipsyArray (tipsy.hpp:38-54): the overdensity of every particle's cell in mapper order
+  void dumpTipsy(const std::string &filename) {
+    initialiseRandomComponentIfUninitialised();
+    auto m = this->mapper();
+    const particle::mapper::Layout &lay = m->layout();
+    std::vector<float> out(lay.size());
+    for (auto &kv : m->layers()) {
+      auto &f = outputField->getFieldForLevel(kv.second->level);
+      f.toReal();
+      const std::vector<T> &data = f.getDataVector();
+      for (size_t i = 0; i < lay.size(); ++i)
+        if (lay.layer[i] == kv.first) out[i] = (float) data[(size_t) lay.cell[i]];
+    }
+    std::ofstream o(this->outputFolder + "/" + filename, std::ios::binary);
+    const unsigned n = (unsigned) out.size();
+    o.write((const char *) &n, 4);
+    o.write((const char *) out.data(), (std::streamsize) (out.size() * sizeof(float)));
+  }
+
   void doneWithModifications() {  // ICGenerator::done, ic.hpp:1633-1648
     if (this->outputFormat.empty()) throw std::runtime_error("No output format specified!");
     initialiseRandomComponentIfUninitialised();
-    if (manager->hasModifications()) manager->applyModifications();
+    if (manager->hasModifications()) applyModificationsLogged();
     if (outputField->getTransferType() == modifications::TransferType::whitenoise)
       outputField->applyPowerSpectrumFor(modifications::TransferType::all);
     const std::string base0 = this->outputFolder + "/" + this->outputFilename;
@@ -682,10 +861,14 @@ public:
     particle::MultiLevelParticleGenerator<T> gen(this->context, outputField->getFields());
     const double boxlen = (double) this->context.getGridForLevel(0).periodicDomainSize;
     const std::string base = this->outputFolder + "/" + this->outputFilename;
+    const bool offset = this->velOffset[0] != T(0) || this->velOffset[1] != T(0) || this->velOffset[2] != T(0);
     if (this->outputFormat == "tipsy") {
       particle::MappedParticles<T, T> P(*this->pMapper, &gen, this->cosmo);
+      if (offset)  // OffsetEvaluator (offsetgenerator.hpp:38-43)
+        for (size_t i = 0; i < P.vel.size(); ++i) P.vel[i] += this->velOffset[i % 3];
       io::tipsy::saveMapped<T>(base + ".tipsy", boxlen, P, this->cosmo);
     } else {
+      if (offset) throw std::runtime_error("velocity_offset is implemented for tipsy output only in the C++ layer");
       particle::MappedParticles<T, float> P(*this->pMapper, &gen, this->cosmo);
       io::gadget::save<T>(base + ".gadget", boxlen, P, this->cosmo, this->outputFormat == "gadget2" ? 2 : 3, this->nGadgetFiles);
     }

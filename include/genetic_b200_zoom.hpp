@@ -20,6 +20,7 @@
 #include "genetic_b200.hpp"
 
 #include <algorithm>
+#include <iostream>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -74,6 +75,10 @@ template <typename T> void selectSphere(multilevelgrid::MultiLevelGrid<T> &ctx, 
 template <typename T> void selectCube(multilevelgrid::MultiLevelGrid<T> &ctx, const std::array<T, 3> &c, float side) {
   const T h = T(side / 2);  // ic.hpp:1519-1524
   select<T>(ctx, c, [h](T x, T y, T z) { return std::abs(x) < h && std::abs(y) < h && std::abs(z) < h; });
+}
+template <typename T> void selectEllipse(multilevelgrid::MultiLevelGrid<T> &ctx, const std::array<T, 3> &c, float a, float b, float cc) {
+  const T a2 = T(a * a), b2 = T(b * b), c2 = T(cc * cc);  // selectEllipse(float a, b, c), ic.hpp:1503-1513
+  select<T>(ctx, c, [a2, b2, c2](T x, T y, T z) { return x * x / a2 + y * y / b2 + z * z / c2 < T(1.); });
 }
 template <typename T> void selectNearest(multilevelgrid::MultiLevelGrid<T> &ctx, const std::array<T, 3> &centre) {  // ic.hpp:1447-1455
   for (size_t l = 0; l < ctx.getNumLevels(); ++l) ctx.getGridForLevel(l).flagCells({});
@@ -150,6 +155,26 @@ template <typename T> Int3 zoomCorner(const grids::Grid<T> &grid, size_t zoomfac
   win.shift(move);
   win.shift({-above.lo[0], -above.lo[1], -above.lo[2]});
   return win.lo;
+}
+
+// ICGenerator::initZoomGrid (ic.hpp:461-474): a flagged cell within `borderSafety` cells of the edge of the zoom window placed at
+// `corner` (Window<int>::containsWithBorderSafety, window.hpp:296-302)
+template <typename T> bool flagsNearZoomBorder(const grids::Grid<T> &grid, const Int3 &corner, size_t zoomfac, long borderSafety = 3) {
+  const long n = (long) grid.size;
+  IntWindow w((long) grid.simEquivalentSize, corner);
+  w.hi = {corner[0] + n / (long) zoomfac, corner[1] + n / (long) zoomfac, corner[2] + n / (long) zoomfac};
+  w.wrapCorners();
+  std::vector<size_t> flags;
+  grid.getFlaggedCells(flags);
+  for (size_t id : flags) {
+    const Int3 c = coordinateFromIndex(grid, id);
+    for (int a = 0; a < 3; ++a) {
+      const long lo = w.lo[a] + borderSafety, hi = w.hi[a] - borderSafety;
+      const bool ok = hi >= lo ? (c[a] < hi && c[a] >= lo) : (c[a] < hi || c[a] >= lo);
+      if (!ok) return true;
+    }
+  }
+  return false;
 }
 
 // the trimming of initZoomGridWithLowLeftCornerAt (ic.hpp:531-554): flagged cells whose centroid lies outside the new window
@@ -667,6 +692,8 @@ public:
   std::vector<std::vector<size_t>> zoomParticleArray;
   std::vector<unsigned> gadgetTypesForLevels;
   unsigned mruGadgetType = 1;
+  bool usedGadgetParticleTypes[6] = {false, false, false, false, false, false};
+  std::array<T, 3> velOffset{0, 0, 0};   // velocity_offset (ic.hpp:285-289), km a^1/2 s^-1
   std::string cambFile, outputFolder = ".", outputFilename = "IC", outputFormat, dir = ".";
   unsigned long seed = 0;
   int noiseMode = -1, nGadgetFiles = 1;
@@ -685,7 +712,7 @@ public:
   void initBaseGrid(T boxSize, size_t n) {
     if (context.getNumLevels() > 0) throw std::runtime_error("Cannot re-initialize the base grid");
     context.addLevel(boxSize, n);
-    gadgetTypesForLevels.push_back(mruGadgetType);
+    gadgetTypesForLevels.push_back(mruGadgetType);   // (the type of the base level is only reserved once a zoom is opened, ic.hpp:611-613)
   }
 
   void initZoomGrid(size_t zoomfac, size_t n, const zoom::Int3 *userCorner = nullptr) {  // ic.hpp:398-598
@@ -695,14 +722,27 @@ public:
     up.getFlaggedCells(flags);
     if (flags.empty()) throw std::runtime_error("Cannot initialise zoom without marking particles to be replaced");
     const zoom::Int3 corner = userCorner ? *userCorner : zoom::zoomCorner(up, zoomfac);
+    if (!userCorner && zoom::flagsNearZoomBorder(up, corner, zoomfac))
+      std::cout << "WARNING: Opening a zoom where flagged particles are within 3 pixels of the edge. This is prone to numerical errors."
+                << std::endl;
     if (std::min(corner[0], std::min(corner[1], corner[2])) < 0)
       throw std::runtime_error("The newly initialised zoom level is not fully contained within the previous level");
     zoomParticleArray.push_back(zoom::trimToZoomWindow(up, flags, corner, (long) (up.size / zoomfac)));
     context.addLevel(up.thisGridSize / T(zoomfac), n, up.offsetLower[0] + T(corner[0]) * up.cellSize,
                      up.offsetLower[1] + T(corner[1]) * up.cellSize, up.offsetLower[2] + T(corner[2]) * up.cellSize);
     gadgetTypesForLevels.push_back(mruGadgetType);
+    usedGadgetParticleTypes[mruGadgetType] = true;
     // flags of the level above carried onto the new grid (makeProxyGridToMatch, grid.hpp:195-228)
     auto &g = context.getGridForLevel(context.getNumLevels() - 1);
+    {
+      char buf[512];
+      snprintf(buf, sizeof buf, "Initialized a zoom region:\n  Subbox length         = %g Mpc/h\n  n                     = %zu\n"
+               "  dx                    = %g\n  Zoom factor           = %zu\n  Num particles         = %zu\n"
+               "  Low-left corner in parent grid = (%ld, %ld, %ld)\n  Low-left corner (h**-1 Mpc)    = %g, %g, %g",
+               (double) g.thisGridSize, g.size, (double) g.cellSize, zoomfac, flags.size(), corner[0], corner[1], corner[2],
+               (double) g.offsetLower[0], (double) g.offsetLower[1], (double) g.offsetLower[2]);
+      std::cout << buf << std::endl;
+    }
     const long ratio = std::lround((double) up.cellSize / (double) g.cellSize), nu = (long) up.size, nf = (long) g.size;
     const long W = (long) up.simEquivalentSize;
     std::vector<char> mask(up.size3, 0);
@@ -780,6 +820,7 @@ public:
         else if (cmd == "centre" || cmd == "center") { centre[0] = (T) num(); centre[1] = (T) num(); centre[2] = (T) num(); }
         else if (cmd == "select_sphere") zoom::selectSphere<T>(context, centre, (float) num());
         else if (cmd == "select_cube") zoom::selectCube<T>(context, centre, (float) num());
+        else if (cmd == "select_ellipse") { const float a = (float) num(), b = (float) num(); zoom::selectEllipse<T>(context, centre, a, b, (float) num()); }
         else if (cmd == "select_nearest") zoom::selectNearest<T>(context, centre);
         else if (cmd == "idfile" || cmd == "id_file") { auto m = mapper(); m->unflagAllParticles(); m->flagParticles(readIds(path(str()))); }
         else if (cmd == "append_idfile" || cmd == "merge_id_file") mapper()->flagParticles(readIds(path(str())));
@@ -792,8 +833,12 @@ public:
         else if (cmd == "gadget_particle_type") {
           const unsigned t = (unsigned) num();
           if (t >= 6) throw std::runtime_error("Gadget particle type must be between 0 and 5");
+          if (t != mruGadgetType) {  // ic.hpp:690-703
+            if (usedGadgetParticleTypes[t])
+              throw std::runtime_error("Cannot reuse a gadget particle type; this type was already used in a different section of the ICs");
+            mruGadgetType = t;
+          }
           if (gadgetTypesForLevels.empty()) throw std::runtime_error("Can't set a gadget particle type until a level has been initialised to set it for");
-          mruGadgetType = t;
           gadgetTypesForLevels.back() = t;
         }
         else if (cmd == "gadget_num_files") nGadgetFiles = (int) num();

@@ -33,9 +33,9 @@ def test_cpp_modify_driver_errors_before_the_device(tmp_path):
     p.write_text("basegrid 50 16\nmodify overdensity relative\n")
     r = subprocess.run([exe, str(p)], capture_output=True, text=True)
     assert r.returncode == 1 and "Insufficient arguments for command modify" in r.stderr
-    p.write_text("basegrid 50 16\nreverse_small_k 0.1\n")
+    p.write_text("basegrid 50 16\nstrays_on\n")
     r = subprocess.run([exe, str(p)], capture_output=True, text=True)
-    assert r.returncode == 1 and "Unknown command reverse_small_k" in r.stderr
+    assert r.returncode == 1 and "Unknown command strays_on" in r.stderr
 
 
 @pytest.mark.gpu

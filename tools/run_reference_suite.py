@@ -131,7 +131,8 @@ def compare_dir(d, log):
 def main():
     args = sys.argv[1:]
     mock = "--mock" in args
-    args = [a for a in args if a != "--mock"]
+    cpp = "--cpp" in args          # through the C++ driver host/genetic_b200_modify instead of the Python command layer
+    args = [a for a in args if a not in ("--mock", "--cpp")]
     if mock:
         import importlib.util
         spec = importlib.util.spec_from_file_location("gx_mock_device", os.path.join(ROOT, "tests", "host", "mock_device.py"))
@@ -158,13 +159,22 @@ def main():
         log = []
         t0 = time.time()
         try:
-            icgen.run_paramfile(os.path.join(d, "paramfile.txt"), log=lambda s: log.extend(str(s).splitlines() or [""]))
+            if cpp:
+                import subprocess
+                from genetic_b200 import build as gbuild
+                r = subprocess.run([gbuild.build_host(program="genetic_b200_modify"), os.path.join(d, "paramfile.txt")],
+                                   capture_output=True, text=True, cwd=d, timeout=600)
+                log.extend(r.stdout.splitlines())
+                if r.returncode != 0:
+                    raise L.GxError((r.stderr.strip().splitlines() or ["exit %d" % r.returncode])[-1])
+            else:
+                icgen.run_paramfile(os.path.join(d, "paramfile.txt"), log=lambda s: log.extend(str(s).splitlines() or [""]))
             status = "PASS " + compare_dir(d, log)
         except L.GxError as e:
             msg = str(e)
             if "error" in t and "Error" in msg:
                 status = "PASS (expected error)"
-            elif "not supported" in msg or "Unknown output format" in msg:
+            elif "not supported" in msg or "Unknown output format" in msg or (cpp and ("Unknown command" in msg or "only in the C++ layer" in msg)):
                 status = "SKIP " + msg[:110]
             else:
                 status = "FAIL " + msg[:160]
