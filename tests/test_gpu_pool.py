@@ -51,7 +51,7 @@ def test_a_block_in_use_is_not_handed_out():
     nbytes = lib.gx_field_bytes(n, L.F64)
     a = _malloc(lib, nbytes)
     lib.gx_memset_zero(a, nbytes, None)
-    for _ in range(40):                          # ~7 ms of queued device work on the block
+    for _ in range(120):                         # ~40 ms of queued device work on the block
         lib.gx_fft_forward(a, n, L.F64, None)
         lib.gx_fft_inverse(a, n, L.F64, None)
     addr = a.value
