@@ -745,6 +745,7 @@ public:
     }
     else if (cmd == "dump_grid") { dumpGrid((size_t) num()); }
     else if (cmd == "dump_ps") { dumpPS((size_t) num()); }
+    else if (cmd == "dump_grid_fourier") { dumpGridFourier((size_t) num()); }
     else if (cmd == "splice") { splice((unsigned long) num()); }
     else if (cmd == "done") { doneWithModifications(); }
     else return false;
@@ -896,6 +897,44 @@ public:
     fields::Field<T> spliced = modifications::spliceOneLevel<T>(other, orig, cov);
     spliced.toFourier();
     outputField->getFields()[0] = std::make_shared<fields::Field<T>>(spliced);
+  }
+
+  // ic.hpp:879-885 + getComplexFourierField (fourier.hpp:685-716): the full complex n^3 Fourier cube as .npy ('<c16' / '<c8')
+  void dumpGridFourier(size_t level) {
+    initialiseRandomComponentIfUninitialised();
+    auto &f = outputField->getFieldForLevel(level);
+    f.toFourier();
+    const auto &g = f.getGrid();
+    const size_t n = g.size, nc = n / 2 + 1;
+    const std::vector<T> &half = f.getDataVector();  // [n][n][nc] complex, interleaved
+    std::vector<T> full(2 * n * n * n);
+    for (size_t x = 0; x < n; ++x)
+      for (size_t y = 0; y < n; ++y)
+        for (size_t z = 0; z < n; ++z) {
+          const bool neg = z >= nc;  // kz < 0: the conjugate of the mode (-kx, -ky, -kz)
+          const size_t sx = neg ? (n - x) % n : x, sy = neg ? (n - y) % n : y, sz = neg ? n - z : z;
+          const size_t s = 2 * ((sx * n + sy) * nc + sz), d = 2 * ((x * n + y) * n + z);
+          full[d] = half[s];
+          full[d + 1] = neg ? -half[s + 1] : half[s + 1];
+        }
+    const std::string base = this->outputFolder + "/grid-" + std::to_string(level);
+    std::ofstream o(base + ".npy", std::ios::binary);
+    char dict[128];
+    snprintf(dict, sizeof dict, "{'descr': '<c%d', 'fortran_order': False, 'shape': (%zu, %zu, %zu), }", (int) (2 * sizeof(T)), n, n, n);
+    std::string h(dict);
+    const size_t total = 10 + h.size() + 1;
+    h.append((64 - total % 64) % 64, ' ');
+    h.push_back('\n');
+    const unsigned short hl = (unsigned short) h.size();
+    o.write("\x93NUMPY\x01\x00", 8);
+    o.write(reinterpret_cast<const char *>(&hl), 2);
+    o.write(h.data(), (std::streamsize) h.size());
+    o.write(reinterpret_cast<const char *>(full.data()), (std::streamsize) (full.size() * sizeof(T)));
+    std::ofstream t(this->outputFolder + "/grid-info-" + std::to_string(level) + "-fourier.txt");
+    char buf[256];
+    snprintf(buf, sizeof buf, "%g %g %g %g\n", (double) g.offsetLower[0], (double) g.offsetLower[1], (double) g.offsetLower[2], (double) g.thisGridSize);
+    t << buf << "The line above contains information about grid level " << level << "\n"
+      << "It gives the x-offset, y-offset and z-offset of the low-left corner and also the box length\n";
   }
 
   void dumpPS(size_t level, int nBins = 100) {  // ic.hpp:943-962 + cosmology::dumpPowerSpectrum, parameters.hpp:172-205

@@ -464,16 +464,21 @@ private:
   Layout lay;
 };
 
-// ICGenerator::updateParticleMapper (ic.hpp:1129-1221) without sub/supersampling, flagged types and padding
+// ICGenerator::updateParticleMapper (ic.hpp:1129-1221) without sub/supersampling and padding
 template <typename T>
 typename ParticleMapper<T>::Ptr updateParticleMapper(multilevelgrid::MultiLevelGrid<T> &ctx, const std::vector<std::vector<size_t>> &zoomParticleArray,
                                                     const std::vector<unsigned> &gadgetTypes, const cosmology::CosmologicalParameters<T> &cosmo,
-                                                    bool baryonsOnAllLevels, bool gasFirst) {
+                                                    bool baryonsOnAllLevels, bool gasFirst, int flaggedGadgetParticleType = -1,
+                                                    const std::vector<size_t> *flaggedCells = nullptr) {
   const size_t nl = ctx.getNumLevels();
   typename ParticleMapper<T>::Ptr m = std::make_shared<OneLevelParticleMapper<T>>(ctx.getGridForLevel(0), 0, gadgetTypes[0]);
   for (size_t level = 1; level < nl; ++level) {
     auto fine = std::make_shared<OneLevelParticleMapper<T>>(ctx.getGridForLevel(level), level, gadgetTypes[level]);
     m = std::make_shared<TwoLevelParticleMapper<T>>(m, fine, zoomParticleArray[level - 1]);
+  }
+  if (flaggedGadgetParticleType >= 0 && flaggedCells) {  // ic.hpp:1176-1186: the flagged cells of the finest grid, retyped
+    auto flagged = std::make_shared<OneLevelParticleMapper<T>>(ctx.getGridForLevel(nl - 1), nl - 1, (unsigned) flaggedGadgetParticleType);
+    m = std::make_shared<TwoLevelParticleMapper<T>>(m, flagged, *flaggedCells);
   }
   if (cosmo.OmegaBaryons0 > 0) {
     std::vector<const grids::Grid<T> *> to;
@@ -693,6 +698,8 @@ public:
   std::vector<unsigned> gadgetTypesForLevels;
   unsigned mruGadgetType = 1;
   bool usedGadgetParticleTypes[6] = {false, false, false, false, false, false};
+  int flaggedGadgetParticleType = -1;          // gadget_flagged_particle_type (ic.hpp:703-714)
+  std::vector<size_t> flaggedCellsForType;
   std::array<T, 3> velOffset{0, 0, 0};   // velocity_offset (ic.hpp:285-289), km a^1/2 s^-1
   std::string cambFile, outputFolder = ".", outputFilename = "IC", outputFormat, dir = ".";
   unsigned long seed = 0;
@@ -706,7 +713,8 @@ public:
   void setRedshift(T z) { cosmo.redshift = z; cosmo.scalefactor = T(1.) / (z + T(1.)); }
 
   typename particle::mapper::ParticleMapper<T>::Ptr mapper() {
-    return particle::mapper::updateParticleMapper<T>(context, zoomParticleArray, gadgetTypesForLevels, cosmo, baryonsOnAllLevels, outputFormat == "tipsy");
+    return particle::mapper::updateParticleMapper<T>(context, zoomParticleArray, gadgetTypesForLevels, cosmo, baryonsOnAllLevels, outputFormat == "tipsy",
+                                                     flaggedGadgetParticleType, &flaggedCellsForType);
   }
 
   void initBaseGrid(T boxSize, size_t n) {
@@ -840,6 +848,16 @@ public:
           }
           if (gadgetTypesForLevels.empty()) throw std::runtime_error("Can't set a gadget particle type until a level has been initialised to set it for");
           gadgetTypesForLevels.back() = t;
+        }
+        else if (cmd == "gadget_flagged_particle_type") {  // ic.hpp:703-714: the flagged cells of the finest level as a separate type
+          const unsigned t = (unsigned) num();
+          if (t >= 6) throw std::runtime_error("Gadget particle type must be between 0 and 5");
+          if (usedGadgetParticleTypes[t])
+            throw std::runtime_error("Cannot reuse a gadget particle type; this type was already used in a different section of the ICs");
+          flaggedGadgetParticleType = (int) t;
+          usedGadgetParticleTypes[t] = true;
+          flaggedCellsForType.clear();
+          context.getGridForLevel(context.getNumLevels() - 1).getFlaggedCells(flaggedCellsForType);
         }
         else if (cmd == "gadget_num_files") nGadgetFiles = (int) num();
         else if (cmd == "baryons_all_levels") baryonsOnAllLevels = true;

@@ -23,6 +23,8 @@ CASES = {
     "gas_gadget": "Ob 0.04\noutformat gadget3\nbasegrid 60.0 32\ncentre 20 33 41\nselect_sphere 7\nzoomgrid 2 32\n",
     "gas_tipsy_all_levels": ("Ob 0.04\noutformat tipsy\nbaryons_all_levels\nbasegrid 60.0 32\ncentre 20 33 41\nselect_sphere 7\n"
                              "zoomgrid 2 32\n"),
+    "flagged_particle_type": ("outformat gadget3\nbasegrid 60.0 32\ncentre 20 33 41\nselect_sphere 7\nzoomgrid 2 32\n"
+                              "centre 20 33 41\nselect_sphere 2\ngadget_flagged_particle_type 3\n"),
     "nearest_then_ids": ("outformat tipsy\nbasegrid 50.0 32\ncentre 24.219 24.219 24.219\nselect_nearest\nzoomgrid 4 32\n"
                          "idfile ids.txt\ndump_idfile out_ids.txt\n"),
 }
