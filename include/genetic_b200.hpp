@@ -376,6 +376,8 @@ public:
     }
     return dof;
   }
+  std::shared_ptr<grids::Grid<T>> getGridPtr(size_t level) { return pGrids[level]; }
+  void replaceGrid(size_t level, std::shared_ptr<grids::Grid<T>> g) { pGrids[level] = std::move(g); }  // DummyICGenerator: shared grids
   // set once the particle generator has folded the coarse levels into the fine ones (multilevelgrid.hpp:82-95)
   bool levelsAreCombined = false;
   void setLevelsAreCombined() { levelsAreCombined = true; }

@@ -25,7 +25,7 @@ namespace modifications {
 
 // where the warnings and the "calculated value" lines go (the reference's logging::entry())
 inline std::function<void(const std::string &)> &logger() {
-  static std::function<void(const std::string &)> f = [](const std::string &s) { std::cout << s << std::endl; };
+  static std::function<void(const std::string &)> f = [](const std::string &s) { logLine(s); };
   return f;
 }
 
@@ -577,6 +577,10 @@ public:
   std::unique_ptr<modifications::TypedField<T>> outputField;
   std::unique_ptr<modifications::ModificationManager<T>> manager;
   T variance_filterscale = T(-1);
+  // mapper_relative_to (ic.hpp:1077-1112, dummyic.hpp): the ids of later id files refer to the setup of another parameter file,
+  // whose geometry is rebuilt by a field-less run of its commands on shared grid objects
+  std::unique_ptr<ModifICGenerator<T>> pInput;
+  typename particle::mapper::ParticleMapper<T>::Ptr pInputMapper;
   size_t subsample = 1, supersample = 1;      // grafic output only in this layer (virtual levels of the centred stack)
   T pvarValue = T(1);                         // ic.hpp:148
   bool centerOnTargetRegion = false;          // ic.hpp:126, `center_output`
@@ -587,6 +591,24 @@ public:
     const T half = this->context.getGridForLevel(0).thisGridSize / T(2);
     return {half, half, half};
   }
+  // ParticleMapper::extendParticleListToUnreferencedGrids (mapper.hpp:183-196): every grid of `ctx` the mapper does not use
+  // receives the flags of the mapper's finest grid, re-expressed on it
+  static void extendParticleListToUnreferencedGrids(particle::mapper::ParticleMapper<T> &m, multilevelgrid::MultiLevelGrid<T> &ctx) {
+    const auto layers = m.layers();
+    for (size_t level = 0; level < ctx.getNumLevels(); ++level) {
+      auto &g = ctx.getGridForLevel(level);
+      bool referenced = false;
+      for (auto &kv : layers) referenced = referenced || kv.second->grid == &g;
+      if (referenced) continue;
+      std::vector<size_t> add = zoom::proxyFlags<T>(m.getFinestGrid(), g), have;
+      g.getFlaggedCells(have);
+      have.insert(have.end(), add.begin(), add.end());
+      std::sort(have.begin(), have.end());
+      have.erase(std::unique(have.begin(), have.end()), have.end());
+      g.flagCells(have);
+    }
+  }
+
   // ICGenerator::getCentre (ic.hpp:1372-1386) + Grid::getCentreWrapped (grid.hpp:466-494): after an id file has been loaded
   // the current point is the centre of the flagged cells of the deepest level that has any
   void updateCentreFromFlags() {
@@ -650,6 +672,34 @@ public:
     char buf[256];
     auto path = [this](const std::string &p) { return p[0] == '/' ? p : this->dir + "/" + p; };
     const bool isGrafic = this->outputFormat == "grafic";
+    if (this->pUnderlying) {  // DummyICGenerator (dummyic.hpp:60-120): everything that touches fields or writes output is a no-op
+      static const char *noop[] = {"zerolevel", "zero_level", "dump_grid", "dump_ps", "dump_mask", "dump_idfile", "dump_id_file", "modify",
+                                   "done", "apply_modifications", "calculate", "chi2", "reverse", "reverse_small_k", "import_level",
+                                   "dump_tipsy", "dump_grid_fourier", "splice", "dump_vx"};
+      for (const char *c : noop) if (cmd == c) return true;
+    }
+    if (cmd == "mapper_relative_to") {
+      const std::string given = str(), fname = path(given);
+      if (this->context.getNumLevels() == 0) throw std::runtime_error("Mapper relative command cannot be used before a basegrid has been initialised.");
+      { std::ifstream probe(fname); if (!probe.is_open()) throw std::runtime_error("Cannot open IC paramfile for relative_to command"); }
+      log("");
+      log("+ Input mapper: computing geometry from " + given);
+      pInput.reset(new ModifICGenerator<T>());
+      pInput->pUnderlying = this;
+      {
+        const std::string saved = logIndent();
+        logIndent() = saved + "| ";
+        log("");
+        try { pInput->runParamFile(fname); } catch (...) { logIndent() = saved; throw; }
+        logIndent() = saved;
+      }
+      log("");
+      if (pInput->outputFormat == "grafic") throw std::runtime_error("mapper_relative_to a grafic setup is not implemented in the C++ layer");
+      if (pInput->subsample != 1 || pInput->supersample != 1)
+        throw std::runtime_error("mapper_relative_to a sub/supersampled setup is not implemented in the C++ layer");
+      pInputMapper = pInput->mapper();
+      return true;
+    }
     if (cmd == "outformat") {
       std::string f = str();
       for (auto &c : f) c = (char) std::tolower(c);
@@ -710,6 +760,16 @@ public:
         grafic::GraficMapper<T> m(this->context, this->centre, subsample, supersample);
         if (replace) m.unflagAllParticles();
         m.flagParticles(ids);
+      } else if (subsample != 1 || supersample != 1) {
+        throw std::runtime_error("subsample / supersample are implemented for grafic output only in the C++ layer");
+      } else if (pInputMapper) {
+        // flagCellsCorrespondingToParticles (ic.hpp:1247-1261): the ids refer to the other setup; flag there, then carry the
+        // flags onto the grids only this setup has, and back
+        auto mine = this->mapper();
+        if (replace) { mine->unflagAllParticles(); pInputMapper->unflagAllParticles(); }
+        pInputMapper->flagParticles(ids);
+        extendParticleListToUnreferencedGrids(*pInputMapper, this->context);
+        extendParticleListToUnreferencedGrids(*mine, pInput->context);
       } else {
         auto m = this->mapper();
         if (replace) m->unflagAllParticles();
@@ -736,7 +796,7 @@ public:
       initialiseRandomComponentIfUninitialised();
       manager->addModificationToList(name, type, (T) target);
     }
-    else if (cmd == "clear_modifications") { if (manager) manager->clearModifications(); }
+    else if (cmd == "clear_modifications") { log("Clearing modification list"); if (manager) manager->clearModifications(); }
     else if (cmd == "apply_modifications") { initialiseRandomComponentIfUninitialised(); applyModificationsLogged(); }
     else if (cmd == "chi2") {
       initialiseRandomComponentIfUninitialised();

@@ -177,6 +177,60 @@ template <typename T> bool flagsNearZoomBorder(const grids::Grid<T> &grid, const
   return false;
 }
 
+// Grid::makeProxyGridToMatch(target)->getFlaggedCells (grid.hpp:195-228; SuperSampleGrid / SectionOfGrid / SubSampleGrid flag
+// proxies, virtualgrid.hpp): the flagged cells of `source` as cells of `target` -- refined first if the target is finer,
+// shifted into the target's frame (periodic in the simulation box, cells outside the target dropped), coarsened last
+template <typename T> std::vector<size_t> proxyFlags(const grids::Grid<T> &source, const grids::Grid<T> &target) {
+  auto ratio = [](double a, double b) {
+    const double r = a / b;
+    if (std::fabs(r - std::round(r)) > 1e-8 * std::max(1.0, std::fabs(r)) || std::round(r) < 1)
+      throw std::runtime_error("The ratio of cell sizes is not a positive integer");
+    return (long) std::lround(r);
+  };
+  std::vector<size_t> flags;
+  source.getFlaggedCells(flags);
+  long n = (long) source.size;
+  double dx = (double) source.cellSize;
+  std::vector<std::array<long, 3>> c;
+  c.reserve(flags.size());
+  for (size_t id : flags) c.push_back({(long) (id / (size_t) (n * n)), (long) ((id / (size_t) n) % (size_t) n), (long) (id % (size_t) n)});
+  if ((double) target.cellSize < dx) {
+    const long r = ratio(dx, (double) target.cellSize);
+    std::vector<std::array<long, 3>> fine;
+    fine.reserve(c.size() * (size_t) (r * r * r));
+    for (auto &q : c)
+      for (long a = 0; a < r; ++a)
+        for (long b = 0; b < r; ++b)
+          for (long d = 0; d < r; ++d) fine.push_back({q[0] * r + a, q[1] * r + b, q[2] * r + d});
+    c.swap(fine);
+    dx /= (double) r;
+    n *= r;
+  }
+  const long sub = ratio((double) target.cellSize, dx), pre = (long) target.size * sub;
+  long off[3];
+  bool shifted = false;
+  for (int a = 0; a < 3; ++a) {
+    const double r = ((double) target.offsetLower[a] - (double) source.offsetLower[a]) / dx;
+    if (std::fabs(r - std::round(r)) > 1e-6 * std::max(1.0, std::fabs(r))) throw std::runtime_error("Grid offsets do not differ by a whole number of cells");
+    off[a] = (long) std::lround(r);
+    shifted = shifted || off[a] != 0;
+  }
+  const long wrap = std::lround((double) source.periodicDomainSize / dx), m = (long) target.size;
+  std::vector<size_t> out;
+  for (auto q : c) {
+    bool keep = true;
+    if (shifted || pre != n)
+      for (int a = 0; a < 3; ++a) {
+        q[a] = ((q[a] - off[a]) % wrap + wrap) % wrap;
+        keep = keep && q[a] < pre;
+      }
+    if (keep) out.push_back((size_t) (((q[0] / sub) * m + (q[1] / sub)) * m + (q[2] / sub)));
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+  return out;
+}
+
 // the trimming of initZoomGridWithLowLeftCornerAt (ic.hpp:531-554): flagged cells whose centroid lies outside the new window
 template <typename T>
 std::vector<size_t> trimToZoomWindow(const grids::Grid<T> &up, const std::vector<size_t> &flags, const Int3 &corner, long nCoarse) {
@@ -208,6 +262,18 @@ std::vector<size_t> trimToZoomWindow(const grids::Grid<T> &up, const std::vector
 }  // namespace zoom
 
 // ---------------------------------------------------------------------------------------------------------------------
+// log output with the indentation of logging::IndentWhileInScope (the geometry run of `mapper_relative_to` is shown as "| ...")
+inline std::string &logIndent() { static std::string s; return s; }
+inline void logLine(const std::string &text) {
+  size_t a = 0;
+  while (true) {
+    const size_t b = text.find('\n', a);
+    std::cout << logIndent() << text.substr(a, b == std::string::npos ? std::string::npos : b - a) << std::endl;
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+}
+
 namespace particle { namespace mapper {
 
 template <typename T> class OneLevelParticleMapper;
@@ -698,6 +764,7 @@ public:
   std::vector<unsigned> gadgetTypesForLevels;
   unsigned mruGadgetType = 1;
   bool usedGadgetParticleTypes[6] = {false, false, false, false, false, false};
+  ZoomICGenerator<T> *pUnderlying = nullptr;   // DummyICGenerator (dummyic.hpp): geometry only, grids shared with this generator
   int flaggedGadgetParticleType = -1;          // gadget_flagged_particle_type (ic.hpp:703-714)
   std::vector<size_t> flaggedCellsForType;
   std::array<T, 3> velOffset{0, 0, 0};   // velocity_offset (ic.hpp:285-289), km a^1/2 s^-1
@@ -717,10 +784,44 @@ public:
                                                      flaggedGadgetParticleType, &flaggedCellsForType);
   }
 
+  // DummyICGenerator::addLevelToContext (dummyic.hpp:28-58): a level the underlying generator also has is the same Grid object,
+  // so that flags set through either setup are seen by both
+  void levelAdded() {
+    if (!pUnderlying) return;
+    const size_t level = context.getNumLevels() - 1;
+    gadgetTypesForLevels.back() = 1;
+    if (pUnderlying->context.getNumLevels() <= level) return;
+    auto shared = pUnderlying->context.getGridPtr(level);
+    const auto &mine = context.getGridForLevel(level);
+    if (shared->size != mine.size) throw std::runtime_error("Trying to match particles between incompatible simulation setups (wrong grid n)");
+    if (shared->thisGridSize != mine.thisGridSize)
+      throw std::runtime_error("Trying to match particles between incompatible simulation setups (wrong grid size)");
+    for (int a = 0; a < 3; ++a)
+      if (std::fabs((double) shared->offsetLower[a] - (double) mine.offsetLower[a]) > 1e-12 * std::max(1.0, std::fabs((double) shared->offsetLower[a])))
+        throw std::runtime_error("Trying to match particles between incompatible simulation setups (wrong grid origin)");
+    {  // the flags this setup put on its own copy of the level are kept (dummyic.hpp:50-52)
+      std::vector<size_t> have, add;
+      shared->getFlaggedCells(have);
+      mine.getFlaggedCells(add);
+      have.insert(have.end(), add.begin(), add.end());
+      std::sort(have.begin(), have.end());
+      have.erase(std::unique(have.begin(), have.end()), have.end());
+      shared->flagCells(have);
+    }
+    context.replaceGrid(level, shared);
+  }
+
   void initBaseGrid(T boxSize, size_t n) {
     if (context.getNumLevels() > 0) throw std::runtime_error("Cannot re-initialize the base grid");
+    {
+      char buf[256];
+      snprintf(buf, sizeof buf, "Initialized the base grid:\n  Box length            = %g Mpc/h\n  n                     = %zu\n"
+               "  dx                    = %g", (double) boxSize, n, (double) boxSize / (double) n);
+      logLine(buf);
+    }
     context.addLevel(boxSize, n);
     gadgetTypesForLevels.push_back(mruGadgetType);   // (the type of the base level is only reserved once a zoom is opened, ic.hpp:611-613)
+    levelAdded();
   }
 
   void initZoomGrid(size_t zoomfac, size_t n, const zoom::Int3 *userCorner = nullptr) {  // ic.hpp:398-598
@@ -731,15 +832,14 @@ public:
     if (flags.empty()) throw std::runtime_error("Cannot initialise zoom without marking particles to be replaced");
     const zoom::Int3 corner = userCorner ? *userCorner : zoom::zoomCorner(up, zoomfac);
     if (!userCorner && zoom::flagsNearZoomBorder(up, corner, zoomfac))
-      std::cout << "WARNING: Opening a zoom where flagged particles are within 3 pixels of the edge. This is prone to numerical errors."
-                << std::endl;
+      logLine("WARNING: Opening a zoom where flagged particles are within 3 pixels of the edge. This is prone to numerical errors.");
     if (std::min(corner[0], std::min(corner[1], corner[2])) < 0)
       throw std::runtime_error("The newly initialised zoom level is not fully contained within the previous level");
     zoomParticleArray.push_back(zoom::trimToZoomWindow(up, flags, corner, (long) (up.size / zoomfac)));
     context.addLevel(up.thisGridSize / T(zoomfac), n, up.offsetLower[0] + T(corner[0]) * up.cellSize,
                      up.offsetLower[1] + T(corner[1]) * up.cellSize, up.offsetLower[2] + T(corner[2]) * up.cellSize);
     gadgetTypesForLevels.push_back(mruGadgetType);
-    usedGadgetParticleTypes[mruGadgetType] = true;
+    if (!pUnderlying) usedGadgetParticleTypes[mruGadgetType] = true;
     // flags of the level above carried onto the new grid (makeProxyGridToMatch, grid.hpp:195-228)
     auto &g = context.getGridForLevel(context.getNumLevels() - 1);
     {
@@ -749,7 +849,7 @@ public:
                "  Low-left corner in parent grid = (%ld, %ld, %ld)\n  Low-left corner (h**-1 Mpc)    = %g, %g, %g",
                (double) g.thisGridSize, g.size, (double) g.cellSize, zoomfac, flags.size(), corner[0], corner[1], corner[2],
                (double) g.offsetLower[0], (double) g.offsetLower[1], (double) g.offsetLower[2]);
-      std::cout << buf << std::endl;
+      zoomLogPending = buf;  // completed with the particle count once the flags of the new level are in place
     }
     const long ratio = std::lround((double) up.cellSize / (double) g.cellSize), nu = (long) up.size, nf = (long) g.size;
     const long W = (long) up.simEquivalentSize;
@@ -769,7 +869,11 @@ public:
       }
     }
     g.flagCells(fine);
+    levelAdded();
+    if (outputFormat != "grafic") zoomLogPending += "\n  Total particles       = " + std::to_string(mapper()->size());
+    logLine(zoomLogPending);
   }
+  std::string zoomLogPending;
 
   static std::vector<size_t> readIds(const std::string &fn) {
     std::ifstream f(fn);

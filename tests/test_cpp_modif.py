@@ -146,3 +146,21 @@ def test_cpp_grafic_output_goldens(golden_dir, tmp_path, test):
                 assert np.array_equal(lvl[k], ref), (res, k)
             else:
                 assert np.abs(lvl[k].astype(np.float64) - ref).max() < 1e-4 * max(1.0, np.abs(ref).max() / 10), (res, k)
+
+
+@pytest.mark.parametrize("test", ["mapper_test_01b_zoom_gas", "mapper_test_03a_zoom_linkage", "mapper_test_03b_zoom_to_coarse",
+                                  "mapper_test_05_gadget_ptype"])
+def test_cpp_mapper_relative_to_id_goldens(golden_dir, tmp_path, test):
+    """`mapper_relative_to` in the C++ driver: the ids of an id file refer to the setup of another parameter file (rebuilt by a
+    field-less run on shared grids); flags travel between the two setups through the grids. The reference's id-list goldens,
+    without a device (the `done` line of the test's own paramfile is removed)."""
+    exe = gbuild.build_host(program="genetic_b200_modify")
+    for d in os.listdir(golden_dir):
+        if d.startswith("mapper_test_") or d == "test_01a_basic_grid":
+            shutil.copytree(os.path.join(golden_dir, d), tmp_path / d)
+    d = tmp_path / test
+    text = [l for l in open(d / "paramfile.txt").read().splitlines() if l.strip().lower() != "done"]
+    (d / "paramfile.txt").write_text("\n".join(text) + "\n")
+    r = subprocess.run([exe, str(d / "paramfile.txt")], capture_output=True, text=True, cwd=str(d))
+    assert r.returncode == 0, r.stderr
+    assert open(str(d / "reference.txt")).read().split() == open(str(d / "output.txt")).read().split()

@@ -174,7 +174,7 @@ def main():
             msg = str(e)
             if "error" in t and "Error" in msg:
                 status = "PASS (expected error)"
-            elif "not supported" in msg or "Unknown output format" in msg or (cpp and ("Unknown command" in msg or "only in the C++ layer" in msg)):
+            elif "not supported" in msg or "Unknown output format" in msg or (cpp and ("Unknown command" in msg or "in the C++ layer" in msg)):
                 status = "SKIP " + msg[:110]
             else:
                 status = "FAIL " + msg[:160]
