@@ -55,12 +55,16 @@ def test_a_block_in_use_is_not_handed_out():
         lib.gx_fft_forward(a, n, L.F64, None)
         lib.gx_fft_inverse(a, n, L.F64, None)
     addr = a.value
+    import torch
+    done = torch.cuda.Event()
+    done.record()                                # torch's default stream is the legacy stream the transforms were queued on
     lib.gx_free(a)
     b = _malloc(lib, nbytes)                     # immediately: the transforms are still running
-    assert b.value != addr
+    if not done.query():                         # (queried after the allocation: still running now => running then)
+        assert b.value != addr
     lib.gx_synchronize(None)
     c = _malloc(lib, nbytes)                     # now the first block is idle
-    assert c.value == addr
+    assert c.value == addr or b.value == addr
     lib.gx_free(b)
     lib.gx_free(c)
 
