@@ -164,3 +164,37 @@ def test_cpp_mapper_relative_to_id_goldens(golden_dir, tmp_path, test):
     r = subprocess.run([exe, str(d / "paramfile.txt")], capture_output=True, text=True, cwd=str(d))
     assert r.returncode == 0, r.stderr
     assert open(str(d / "reference.txt")).read().split() == open(str(d / "output.txt")).read().split()
+
+
+def test_cpp_masks_match_the_reference_binary(golden_dir, tmp_path):
+    """dump_mask of the C++ driver against the reference binary itself on the cases of tests/test_grafic_vs_reference.py (a
+    centred zoom wrapping around the box, sub- and supersampled stacks, three levels, flags changed after the zoom was opened);
+    the C++ run has its `done` line removed, so no device is needed."""
+    import glob
+    import importlib.util
+    import oracle
+    if oracle.ref_binary() is None:
+        pytest.skip("oracle/_ref/genetIC not built")
+    spec = importlib.util.spec_from_file_location("gx_grafic_cases", os.path.join(os.path.dirname(__file__), "test_grafic_vs_reference.py"))
+    cases = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cases)
+    exe = gbuild.build_host(program="genetic_b200_modify")
+    camb = os.path.join(golden_dir, "camb_transfer_kmax40_z0.dat")
+    checked = 0
+    for name, body in sorted(cases.CASES.items()):
+        if "dump_mask" not in body:
+            continue
+        text = cases.HEAD + body
+        oracle.run_ref(text, str(tmp_path / name / "ref"), [camb])
+        ours = tmp_path / name / "ours"
+        ours.mkdir(parents=True)
+        shutil.copy(camb, ours)
+        (ours / "paramfile.txt").write_text("\n".join(l for l in text.splitlines() if l.strip() != "done") + "\n")
+        r = subprocess.run([exe, str(ours / "paramfile.txt")], capture_output=True, text=True, cwd=str(ours))
+        assert r.returncode == 0, (name, r.stderr)
+        masks = sorted(glob.glob(str(tmp_path / name / "ref" / "mask-?.npy")))
+        assert masks
+        for f in masks:
+            assert np.array_equal(np.load(f), np.load(str(ours / os.path.basename(f)))), (name, os.path.basename(f))
+            checked += 1
+    assert checked >= 15
