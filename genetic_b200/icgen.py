@@ -385,12 +385,13 @@ class ICGenerator:
         if self.context.getNumLevels() < 1:
             raise L.GxError("Cannot initialise a zoom grid before initialising the base grid")
         up = self.context.getGridForLevel(self.context.getNumLevels() - 1)
-        nflag = len(up.getFlaggedCells())
+        out = self.context.getOutputGridForLevel(self.context.getNumLevels() - 1)
+        nflag = len(out.getFlaggedCells())
         if nflag == 0:
             raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
         if corner is None:
-            corner = Z.zoomCorner(up, zoomfac, self.context.allowStrays)
-            if Z.flagsNearZoomBorder(up, corner, zoomfac):
+            corner = Z.zoomCorner(up, zoomfac, self.context.allowStrays, out)
+            if Z.flagsNearZoomBorder(up, corner, zoomfac, out=out):
                 self.log("WARNING: Opening a zoom where flagged particles are within 3 pixels of the edge. This is prone to "
                          "numerical errors.")
         g = Z.initZoomGrid(self.context, zoomfac, n, corner=corner)
@@ -548,12 +549,13 @@ class ICGenerator:
             raise L.GxError("Adapting the mask requires there to be more than one zoom level")
         z = self.context.zoomParticleArray
         for level in range(nl - 2, 0, -1):
-            this, above = self.context.getGridForLevel(level), self.context.getGridForLevel(level - 1)
-            ratio = int(round(float(above.cellSize) / float(this.cellSize)))
-            corner = [int(round(float(this.offsetLower[a] - above.offsetLower[a]) / float(above.cellSize))) for a in range(3)]
-            c = np.unravel_index(np.asarray(z[level], dtype=np.int64), (this.size,) * 3)
-            up = [corner[a] + c[a] // ratio for a in range(3)]               # makeProxyGridToMatch: section + subsample
-            cells = np.unique((up[0] * above.size + up[1]) * above.size + up[2])
+            # the output grids (the stored grids unless strays are on: then the whole extent of the level above at this
+            # level's resolution), with independent flags
+            this, above = self.context.getOutputGridForLevel(level), self.context.getOutputGridForLevel(level - 1)
+            src = Grid(this.periodicDomainSize, this.size, dx=this.cellSize, x0=this.offsetLower[0], y0=this.offsetLower[1],
+                       z0=this.offsetLower[2], dtype=this.dtype)
+            src.flagCells(z[level])
+            cells = Z.proxyFlags(src, above)                                 # makeProxyGridToMatch: section + subsample
             z[level - 1] = self._expanded(cells, above.size, nPadCells)
 
     def setFlaggedGadgetParticleType(self, t):
@@ -564,7 +566,8 @@ class ICGenerator:
             raise L.GxError("Cannot reuse a gadget particle type; this type was already used in a different section of the ICs")
         self.flaggedGadgetParticleType = t
         self.usedGadgetParticleTypes[t] = True
-        self._flaggedCellsForType = self.context.getGridForLevel(self.context.getNumLevels() - 1).getFlaggedCells().copy()
+        # cells of the mapper's finest grid, i.e. of the OUTPUT grid of the finest level (ic.hpp:1182-1183)
+        self._flaggedCellsForType = np.array(self.context.getOutputGridForLevel(self.context.getNumLevels() - 1).getFlaggedCells())
 
     # ---- random component, modifications (ic.hpp:1333-1346,1589-1745) ------------------------------------------------
     def initialiseRandomComponentIfUninitialised(self):

@@ -185,14 +185,18 @@ class _Window:
         return d
 
 
-def zoomCorner(grid, zoomfac, allowStrays=False):
-    """ICGenerator::initZoomGrid (ic.hpp:398-479) without stray particles: the lower-left corner, in cells of `grid`, of
-    the zoom window of grid.size / zoomfac cells that holds the flagged cells."""
+def zoomCorner(grid, zoomfac, allowStrays=False, out=None):
+    """ICGenerator::initZoomGrid (ic.hpp:398-479): the lower-left corner, in cells of `grid` (the grid the fields of the level
+    above live on), of the zoom window of grid.size / zoomfac cells that holds the flagged cells. `out` is the output grid of
+    the level above when it differs from `grid` (stray particles: a ResolutionMatchingGrid spanning the level above that
+    one): the flags are its cells, and the window found on it is moved into `grid`."""
     n = grid.size
-    flags = grid.getFlaggedCells()
+    out = grid if out is None else out
+    flags = out.getFlaggedCells()
     if len(flags) == 0:
         raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
-    coords = np.stack(np.unravel_index(flags, (n, n, n)), axis=1)
+    no = out.size
+    coords = np.stack(np.unravel_index(flags, (no, no, no)), axis=1)
     wrap = grid.simEquivalentSize
     w = _Window(wrap, [int(v) for v in coords[0]])
     w.expandToIncludeAll(coords)
@@ -202,8 +206,9 @@ def zoomCorner(grid, zoomfac, allowStrays=False):
         raise L.GxError("Zoom particles do not fit in specified sub-box. Decrease zoom, or choose different particles")
     if n_required < n_user:
         w.expandSymmetricallyToSize(n_user)
+    lo_out = [int(round(float(out.offsetLower[a]) / float(grid.cellSize))) for a in range(3)]
+    w.shift(lo_out)                         # relative to the origin of the simulation (outputWindowAbove's corner)
     lo = [int(round(float(grid.offsetLower[a]) / float(grid.cellSize))) for a in range(3)]
-    w.shift(lo)
     above = _Window(wrap, lo)
     above.hi = [lo[a] + n for a in range(3)]
     above.wrapCorners()
@@ -218,14 +223,18 @@ def zoomCorner(grid, zoomfac, allowStrays=False):
     return tuple(w.lo)
 
 
-def flagsNearZoomBorder(grid, corner, zoomfac, borderSafety=3):
+def flagsNearZoomBorder(grid, corner, zoomfac, borderSafety=3, out=None):
     """ICGenerator::initZoomGrid (ic.hpp:461-474): True when a flagged cell lies within `borderSafety` cells of the edge
     of the zoom window placed at `corner` (Window<int>::containsWithBorderSafety, window.hpp:296-302)."""
     n = grid.size
     w = _Window(grid.simEquivalentSize, list(corner))
     w.hi = [corner[a] + n // zoomfac for a in range(3)]
     w.wrapCorners()
-    coords = np.unravel_index(grid.getFlaggedCells(), (n, n, n))
+    out = grid if out is None else out
+    coords = list(np.unravel_index(out.getFlaggedCells(), (out.size,) * 3))
+    for a in range(3):                       # offsetBetweenOutputAndActualWindow (ic.hpp:463)
+        coords[a] = coords[a] - (int(round(float(grid.offsetLower[a]) / float(grid.cellSize)))
+                                 - int(round(float(out.offsetLower[a]) / float(grid.cellSize))))
     ok = np.ones(len(coords[0]), dtype=bool)
     for a in range(3):
         lo, hi = w.lo[a] + borderSafety, w.hi[a] - borderSafety
@@ -233,7 +242,7 @@ def flagsNearZoomBorder(grid, corner, zoomfac, borderSafety=3):
     return not ok.all()
 
 
-def _trimToZoomWindow(up, flags, corner, nCoarse):
+def _trimToZoomWindow(up, flags, corner, nCoarse, out=None):
     """The trimming of initZoomGridWithLowLeftCornerAt (ic.hpp:531-554): flagged cells of the level above whose centroid
     lies outside the new window [centroid(corner) - eps, centroid(corner + nCoarse - 1) + eps] (Window<T>, periodic) are
     dropped from the list of cells to replace."""
@@ -258,12 +267,13 @@ def _trimToZoomWindow(up, flags, corner, nCoarse):
         return T(T(T(T(c) * up.cellSize) + up.offsetLower[a]) + up.cellSize / T(2))
 
     keep = np.ones(len(flags), dtype=bool)
-    coords = np.unravel_index(np.asarray(flags, dtype=np.int64), (n, n, n))
+    out = up if out is None else out         # the flags are cells of the output grid above (ic.hpp:545)
+    coords = np.unravel_index(np.asarray(flags, dtype=np.int64), (out.size,) * 3)
     for a in range(3):
         lo = wrap(T(centroid(corner[a], a) - eps))
         hi = T(centroid(hi_cell[a] - 1, a) + eps)
         hi = np.nextafter(wrap(np.nextafter(hi, T(-np.inf))), T(np.inf))
-        cen = (coords[a].astype(up.dtype) * up.cellSize + up.offsetLower[a]) + up.cellSize / T(2)
+        cen = (coords[a].astype(up.dtype) * out.cellSize + out.offsetLower[a]) + out.cellSize / T(2)
         keep &= ((cen < hi) & (cen >= lo)) if hi >= lo else ((cen < hi) | (cen >= lo))
     return np.asarray(flags, dtype=np.int64)[keep]
 
@@ -274,22 +284,21 @@ def initZoomGrid(context, zoomfac, n, corner=None):
     the flags of the level above onto the new grid (the SuperSample + Section view of the parent, grid.hpp:195-228,
     virtualgrid.hpp:161-166,489-498)."""
     up = context.grids[-1]
-    if len(up.getFlaggedCells()) == 0:
+    out = context.getOutputGridForLevel(len(context.grids) - 1)   # differs from `up` below a zoom opened with strays_on
+    if len(out.getFlaggedCells()) == 0:
         raise L.GxError("Cannot initialise zoom without marking particles to be replaced")
     strays = getattr(context, "allowStrays", False)
-    if strays and context.getOutputGridForLevel(len(context.grids) - 1) is not up:
-        raise L.GxError("stray particles are supported for a single zoom level only")
     if corner is None:
-        corner = zoomCorner(up, zoomfac, strays)
+        corner = zoomCorner(up, zoomfac, strays, out)
     if min(corner) < 0:
         raise L.GxError("The newly initialised zoom level is not fully contained within the previous level")
     if not hasattr(context, "zoomParticleArray"):
         context.zoomParticleArray = []
     del context.zoomParticleArray[len(context.grids) - 1:]
-    trimmed = _trimToZoomWindow(up, up.getFlaggedCells(), corner, up.size // zoomfac)
-    context.zoomMissedParticles = len(up.getFlaggedCells()) - len(trimmed)
+    trimmed = _trimToZoomWindow(up, out.getFlaggedCells(), corner, up.size // zoomfac, out)
+    context.zoomMissedParticles = len(out.getFlaggedCells()) - len(trimmed)
     # with strays the cells outside the window stay in the list: their particles are interpolated from the level above
-    context.zoomParticleArray.append(np.asarray(up.getFlaggedCells(), dtype=np.int64).copy() if strays else trimmed)
+    context.zoomParticleArray.append(np.asarray(out.getFlaggedCells(), dtype=np.int64).copy() if strays else trimmed)
     g = context.addZoomLevel(zoomfac, n, corner)
     ratio = int(round(float(up.cellSize) / float(g.cellSize)))
     pm = np.zeros(up.size3, dtype=bool)

@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""Random paramfiles through the Python command layer (host logic on the numpy mock device, tests/host/mock_device.py) and
+through the reference binary itself (oracle/_ref/genetIC), particle files compared block by block: ids and counts exactly,
+masses / softenings to 1e-6, positions and velocities to 2e-4 of their range (mock FFT against the reference's).
+
+Geometry drawn at random: box, grid size, 0-2 zoom levels (spheres and cubes, nested), gas on one or all levels, gadget types
+per level, flagged particle type, sub/supersampling, supersampled gas, stray particles, autopad, adapt_mask, multi-file gadget,
+velocity offset, all three particle formats. Cases the reference itself refuses are skipped.
+
+  python tools/fuzz_vs_reference.py [seed] [cases] [--strays2]     # --strays2: stray particles below a second zoom, always
+Development tool for the build container (needs the reference binary); tests/test_mapper_fuzz_vs_reference.py runs a fixed set.
+"""
+import glob
+import importlib.util
+import os
+import random
+import shutil
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CAMB = os.path.join(ROOT, "tests", "golden", "camb_transfer_kmax40_z0.dat")
+HEAD = "Om 0.279\nOl 0.721\ns8 0.817\nzin 99\ncamb camb_transfer_kmax40_z0.dat\noutdir ./\noutname t\n"
+
+
+def make_case(rng, strays2=False):
+    L = rng.choice([40.0, 50.0, 64.0])
+    n = rng.choice([8, 16])
+    fmt = rng.choice(["tipsy", "gadget2", "gadget3"])
+    s = ""
+    if rng.random() < 0.4:
+        s += "Ob 0.04\n"
+    s += "random_seed_real_space %d\noutformat %s\n" % (rng.randrange(1, 10 ** 6), fmt)
+    if rng.random() < 0.25:
+        s += "baryons_all_levels\n"
+    if strays2 or rng.random() < 0.2:
+        s += "strays_on\n"
+    s += "basegrid %g %d\n" % (L, n)
+    if fmt != "tipsy" and rng.random() < 0.4:
+        s += "gadget_particle_type %d\n" % rng.choice([1, 2, 3])
+    nz = 2 if strays2 else rng.choice([0, 1, 1, 2])
+    size, prev = L, None
+    for z in range(nz):
+        c = prev if z == 1 else [rng.uniform(0, L) for _ in range(3)]
+        zf = rng.choice([2, 2, 4]) if n // 4 >= 2 else 2
+        sel = rng.choice(["sphere", "cube"])
+        r = size / zf * rng.uniform(0.15, 0.35)
+        s += "centre %g %g %g\nselect_%s %g\nzoomgrid %d %d\n" % (c[0], c[1], c[2], sel, r if sel == "sphere" else 1.5 * r, zf, n)
+        if fmt != "tipsy" and rng.random() < 0.4:
+            s += "gadget_particle_type %d\n" % ([0, 4, 5][z:z + 1] or [4])[0]
+        prev, size = c, size / zf
+    if nz == 2 and rng.random() < 0.3:
+        s += "adapt_mask %d\n" % rng.choice([1, 2])
+    if nz >= 1 and fmt != "tipsy" and rng.random() < 0.25:
+        s += "centre %g %g %g\nselect_sphere %g\ngadget_flagged_particle_type %d\n" % (prev[0], prev[1], prev[2], size * 0.2, rng.choice([1, 2, 3]))
+    if nz >= 1 and rng.random() < 0.2:
+        s += "autopad %d\n" % rng.choice([1, 2])
+    if "Ob" in s and rng.random() < 0.3:
+        s += "supersample_gas 2\n"
+    if rng.random() < 0.3:
+        s += "supersample 2\n"
+    if rng.random() < 0.3 and n >= 16:
+        s += "subsample 2\n"
+    if fmt != "tipsy" and rng.random() < 0.3:
+        s += "gadget_num_files 2\n"
+    if rng.random() < 0.3:
+        s += "velocity_offset 3.5 -2 1\n"
+    return s + "done\n"
+
+
+def install_mock():
+    spec = importlib.util.spec_from_file_location("gx_mock_device", os.path.join(ROOT, "tests", "host", "mock_device.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+
+    class MP:
+        def setattr(self, o, n, v):
+            setattr(o, n, v)
+    m.install(MP())
+    import genetic_b200.icgen as I
+    I.CAMB = m.MockSpectrum
+
+
+def particle_files(d):
+    return [f for f in sorted(glob.glob(os.path.join(d, "t.*"))) if not f.endswith((".param", ".txt"))]
+
+
+def compare(body, workdir):
+    """None if the reference refuses the case, else a list of differences (empty = identical within the tolerances)."""
+    import oracle
+    from genetic_b200 import icgen, output as OUT
+    shutil.rmtree(workdir, ignore_errors=True)
+    try:
+        oracle.run_ref(HEAD + body, os.path.join(workdir, "ref"), [CAMB])
+    except Exception:
+        return None
+    ours = os.path.join(workdir, "ours")
+    os.makedirs(ours)
+    shutil.copy(CAMB, ours)
+    with open(os.path.join(ours, "paramfile.txt"), "w") as f:
+        f.write(HEAD + body)
+    try:
+        icgen.run_paramfile(os.path.join(ours, "paramfile.txt"), log=lambda s: None)
+    except Exception as e:
+        return ["ours failed: " + "".join(traceback.format_exception_only(type(e), e)).strip()[:300]]
+    rf, of = particle_files(os.path.join(workdir, "ref")), particle_files(ours)
+    if [os.path.basename(f) for f in rf] != [os.path.basename(f) for f in of]:
+        return ["files %s vs %s" % (rf, of)]
+    diffs = []
+    for a, b in zip(rf, of):
+        x, y = OUT.read_particles(a), OUT.read_particles(b)
+        for k in x:
+            if x[k].shape != y[k].shape:
+                diffs.append("%s %s: shape %s vs %s" % (os.path.basename(a), k, x[k].shape, y[k].shape))
+            elif k in ("ids", "n"):
+                if not np.array_equal(x[k], y[k]):
+                    diffs.append("%s %s differs" % (os.path.basename(a), k))
+            elif k in ("mass", "eps", "a", "u"):
+                if not np.allclose(x[k], y[k], rtol=1e-6):
+                    diffs.append("%s %s differs" % (os.path.basename(a), k))
+            elif np.abs(x[k].astype(np.float64) - y[k]).max() >= 2e-4 * max(1.0, np.abs(x[k]).max()):
+                diffs.append("%s %s: max error %g" % (os.path.basename(a), k, np.abs(x[k].astype(np.float64) - y[k]).max()))
+    return diffs
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    strays2 = "--strays2" in sys.argv
+    rng = random.Random(int(args[0]) if args else 1)
+    cases = int(args[1]) if len(args) > 1 else 20
+    install_mock()
+    done = bad = 0
+    for it in range(cases):
+        body = make_case(rng, strays2)
+        d = compare(body, "/tmp/gx_fuzz/case%d" % it)
+        if d is None:
+            continue
+        done += 1
+        if d:
+            bad += 1
+            print("CASE %d: %s\n   %s" % (it, "; ".join(d[:4]), body.replace("\n", "; ")))
+    print("compared %d cases with the reference binary (%d refused by the reference itself), %d differ" % (done, cases - done, bad))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
