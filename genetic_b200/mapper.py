@@ -12,8 +12,10 @@ Reference (paths relative to genetIC/src/simulation/particles/mapper/):
 The reference walks these with iterators that dereference one particle at a time (mapperiterator.hpp:151-156). Here a
 mapper is resolved once into its *layout* -- two arrays (level, cell index) in output order, pure index arithmetic on the
 host -- and the particles of each level are then evaluated on the device at that level's cell list in one launch per
-component (gx_emit_cells). Gas: AddGasMapper over splitMass (gasmapper.hpp). Not covered: sub/supersampling, intermediate-resolution padding,
-the grafic mapper. Stray particles (ResolutionMatchingGrid output grids) for one zoom level.
+component (gx_emit_cells). Gas: AddGasMapper over splitMass (gasmapper.hpp). Sub/supersampling, intermediate-resolution
+padding (autopad), the flagged particle type and stray particles (ResolutionMatchingGrid output grids, nested for a second
+zoom level) are here as well; the grafic mapper lives in grafic.py. tools/fuzz_vs_reference.py compares the written files
+with the reference binary's on random paramfiles.
 """
 import ctypes as C
 import itertools
