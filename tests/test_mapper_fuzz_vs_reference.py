@@ -42,3 +42,17 @@ def test_random_paramfiles_match_the_reference_binary(tmp_path, seed, strays2, c
         compared += 1
         assert not diffs, (diffs[:4], body)
     assert compared >= at_least
+
+
+def test_random_grafic_paramfiles_match_the_reference_binary(tmp_path):
+    """Grafic output and dump_mask on random stacks (sub/supersampling, 0-2 zooms, pvar, centred output on a moved point)."""
+    rng = random.Random(3)
+    compared = 0
+    for it in range(24):
+        body = fuzz.make_grafic_case(rng)
+        diffs = fuzz.compare_grafic(body, str(tmp_path / ("g%d" % it)))
+        if diffs is None:
+            continue
+        compared += 1
+        assert not diffs, (diffs[:4], body)
+    assert compared >= 10

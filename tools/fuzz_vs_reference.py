@@ -8,6 +8,7 @@ per level, flagged particle type, sub/supersampling, supersampled gas, stray par
 velocity offset, all three particle formats. Cases the reference itself refuses are skipped.
 
   python tools/fuzz_vs_reference.py [seed] [cases] [--strays2]     # --strays2: stray particles below a second zoom, always
+  python tools/fuzz_vs_reference.py [seed] [cases] --grafic        # grafic output and dump_mask instead of particle files
 Development tool for the build container (needs the reference binary); tests/test_mapper_fuzz_vs_reference.py runs a fixed set.
 """
 import glob
@@ -71,6 +72,82 @@ def make_case(rng, strays2=False):
     return s + "done\n"
 
 
+def make_grafic_case(rng):
+    """Grafic output: sub/supersampled stacks, 0-2 zoom levels, a passive-scalar value, the current point moved after the last
+    zoom, centred output under its three command names, dump_mask."""
+    L = rng.choice([40.0, 50.0, 64.0])
+    n = rng.choice([8, 16])
+    s = "random_seed_real_space 8896131\noutformat %s\n" % rng.choice(["grafic", "5"])
+    if rng.random() < 0.3:
+        s += "Ob 0.04\n"
+    if rng.random() < 0.4:
+        s += "subsample %d\n" % rng.choice([2, 4] if n >= 16 else [2])
+    if rng.random() < 0.4:
+        s += "supersample %d\n" % rng.choice([2, 4])
+    if rng.random() < 0.4:
+        s += "pvar %g\n" % rng.choice([0.01, 0.5, 2.0])
+    s += "basegrid %g %d\n" % (L, n)
+    nz, size, prev = rng.choice([0, 1, 1, 2]), L, None
+    for z in range(nz):
+        c = prev if z == 1 else [rng.uniform(0, L) for _ in range(3)]
+        zf = rng.choice([2, 2, 4]) if n // 4 >= 2 else 2
+        sel = rng.choice(["sphere", "cube"])
+        r = size / zf * rng.uniform(0.15, 0.35)
+        s += "centre %g %g %g\nselect_%s %g\nzoomgrid %d %d\n" % (c[0], c[1], c[2], sel, r if sel == "sphere" else 1.5 * r, zf, n)
+        prev, size = c, size / zf
+    if rng.random() < 0.5:
+        s += "centre %g %g %g\n" % tuple(rng.uniform(0, L) for _ in range(3))
+    if rng.random() < 0.5:
+        s += rng.choice(["center_output", "centre_output", "center_grafic_output"]) + "\n"
+    return s + "done\ndump_mask\n"
+
+
+def compare_grafic(body, workdir):
+    """Like compare() for grafic output: the stack of levels, headers, ids, ic_refmap, ic_pvar and the dumped masks exactly, the
+    fields to 2e-5 of their range."""
+    import oracle
+    from genetic_b200 import icgen, grafic as GF
+    shutil.rmtree(workdir, ignore_errors=True)
+    try:
+        oracle.run_ref(HEAD + body, os.path.join(workdir, "ref"), [CAMB])
+    except Exception:
+        return None
+    ours = os.path.join(workdir, "ours")
+    os.makedirs(ours)
+    shutil.copy(CAMB, ours)
+    with open(os.path.join(ours, "paramfile.txt"), "w") as f:
+        f.write(HEAD + body)
+    try:
+        icgen.run_paramfile(os.path.join(ours, "paramfile.txt"), log=lambda s: None)
+    except Exception as e:
+        return ["ours failed: " + "".join(traceback.format_exception_only(type(e), e)).strip()[:300]]
+
+    def res(p):
+        return int(p.rsplit("_", 1)[1])
+    rl = sorted(glob.glob(os.path.join(workdir, "ref", "*.grafic_*")), key=res)
+    ol = sorted(glob.glob(os.path.join(ours, "*.grafic_*")), key=res)
+    diffs = []
+    if [res(p) for p in rl] != [res(p) for p in ol]:
+        diffs.append("levels %s vs %s" % ([res(p) for p in rl], [res(p) for p in ol]))
+    for a, b in zip(rl, ol):
+        x, y = GF.read_grafic_level(a), GF.read_grafic_level(b)
+        if not np.allclose(x["header"], y["header"], rtol=2e-7, atol=1e-6):
+            diffs.append("header of level %d: %s vs %s" % (res(a), x["header"], y["header"]))
+        for k in x:
+            if k == "header":
+                continue
+            if k in ("ic_particle_ids", "ic_refmap", "ic_pvar_00001"):
+                if not np.array_equal(x[k], y[k]):
+                    diffs.append("%d/%s differs in %d cells" % (res(a), k, int((x[k] != y[k]).sum())))
+            elif np.abs(x[k].astype(np.float64) - y[k]).max() > 2e-5 * max(1.0, np.abs(x[k]).max()):
+                diffs.append("%d/%s: max error %g" % (res(a), k, np.abs(x[k].astype(np.float64) - y[k]).max()))
+    for f in sorted(glob.glob(os.path.join(workdir, "ref", "mask-?.npy"))):
+        g = os.path.join(ours, os.path.basename(f))
+        if not os.path.exists(g) or not np.array_equal(np.load(f), np.load(g)):
+            diffs.append(os.path.basename(f) + " differs")
+    return diffs
+
+
 def install_mock():
     spec = importlib.util.spec_from_file_location("gx_mock_device", os.path.join(ROOT, "tests", "host", "mock_device.py"))
     m = importlib.util.module_from_spec(spec)
@@ -129,13 +206,14 @@ def compare(body, workdir):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     strays2 = "--strays2" in sys.argv
+    grafic = "--grafic" in sys.argv
     rng = random.Random(int(args[0]) if args else 1)
     cases = int(args[1]) if len(args) > 1 else 20
     install_mock()
     done = bad = 0
     for it in range(cases):
-        body = make_case(rng, strays2)
-        d = compare(body, "/tmp/gx_fuzz/case%d" % it)
+        body = make_grafic_case(rng) if grafic else make_case(rng, strays2)
+        d = (compare_grafic if grafic else compare)(body, "/tmp/gx_fuzz/case%d" % it)
         if d is None:
             continue
         done += 1
