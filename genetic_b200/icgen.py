@@ -60,6 +60,7 @@ class ICGenerator:
         self.log = log if log is not None else (lambda msg: print(msg, flush=True))
         if pUnderlying is None:
             GM.set_logger(self.log)
+            GM.set_log_precision(6)
         self.commands = self._routes()
         if pUnderlying is not None:
             noop = (lambda *a: None)
@@ -343,8 +344,8 @@ class ICGenerator:
             raise L.GxError("Cannot re-initialize the base grid")
         if self.haveInitialisedRandomComponent:
             raise L.GxError("Trying to initialize a grid after the random field was already drawn")
-        self.log("Initialized the base grid:\n  Box length            = %g Mpc/h\n  n                     = %d\n"
-                 "  dx                    = %g" % (boxSize, n, boxSize / n))
+        self.log("Initialized the base grid:\n  Box length            = %s Mpc/h\n  n                     = %d\n"
+                 "  dx                    = %s" % (GM.fmtg(boxSize), n, GM.fmtg(boxSize / n)))
         self.context.addLevel(Grid(boxSize, n, dtype=self.dtype))
         self._levelAdded()
 
@@ -405,11 +406,11 @@ class ICGenerator:
             else:
                 self.log("         of %d particles, %d have been omitted" % (nflag, missed))
             self.log("         to make a new zoom flag list of %d" % kept)
-        self.log("Initialized a zoom region:\n  Subbox length         = %g Mpc/h\n  n                     = %d\n"
-                 "  dx                    = %g\n  Zoom factor           = %d\n  Num particles         = %d\n"
+        self.log("Initialized a zoom region:\n  Subbox length         = %s Mpc/h\n  n                     = %d\n"
+                 "  dx                    = %s\n  Zoom factor           = %d\n  Num particles         = %d\n"
                  "  Low-left corner in parent grid = (%d, %d, %d)\n"
-                 "  Low-left corner (h**-1 Mpc)    = %g, %g, %g\n  Total particles       = %d"
-                 % (float(g.thisGridSize), g.size, float(g.cellSize), zoomfac, nflag, *corner, *[float(v) for v in g.offsetLower],
+                 "  Low-left corner (h**-1 Mpc)    = %s, %s, %s\n  Total particles       = %d"
+                 % (GM.fmtg(g.thisGridSize), g.size, GM.fmtg(g.cellSize), zoomfac, nflag, *corner, *[GM.fmtg(v) for v in g.offsetLower],
                     self._mapper().size()))
 
     def _mapper(self, gasFirst=None):
@@ -500,7 +501,8 @@ class ICGenerator:
                 break
         g = self.context.getGridForLevel(level)
         self.x0, self.y0, self.z0 = Z.getCentreWrapped(g, g.getFlaggedCells())
-        self.log("Centre of region is %.12g %.12g %.12g" % (self.x0, self.y0, self.z0))
+        GM.set_log_precision(12)          # setprecision(12), sticky (ic.hpp:1384)
+        self.log("Centre of region is %s %s %s" % (GM.fmtg(self.x0), GM.fmtg(self.y0), GM.fmtg(self.z0)))
 
     def centreParticle(self, pid):
         g = self.context.getGridForLevel(0)
@@ -586,14 +588,15 @@ class ICGenerator:
 
     def getFieldChi2(self):
         self.initialiseRandomComponentIfUninitialised()
-        self.log("Calculated chi^2 = %.10g (dof = %d)" % (self.outputField.getChi2(), self.context.getNumDof()))
+        GM.set_log_precision(10)          # std::setprecision(10), sticky on the reference's log stream (ic.hpp:1596)
+        self.log("Calculated chi^2 = %s (dof = %d)" % (GM.fmtg(self.outputField.getChi2()), self.context.getNumDof()))
 
     def _modkw(self):
         return dict(filterscale=self.variance_filterscale, initNumberSteps=self.initial_number_steps, precision=self.precision)
 
     def calculate(self, name):
         self.initialiseRandomComponentIfUninitialised()
-        self.log("%s: calculated value = %g" % (name, self.modificationManager.calculateCurrentValueByName(name, **self._modkw())))
+        self.log("%s: calculated value = %s" % (name, GM.fmtg(self.modificationManager.calculateCurrentValueByName(name, **self._modkw()))))
 
     def modify(self, name, type_, target):
         self.initialiseRandomComponentIfUninitialised()

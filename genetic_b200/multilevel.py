@@ -29,6 +29,19 @@ WHITENOISE, DM, BARYON, ALL = "whitenoise", "dm", "baryon", "all"  # particle::s
 _log = [None]
 
 
+# The reference's log is one ostream: `std::setprecision(10)` in ICGenerator::getChi2 (ic.hpp:1596) and `setprecision(12)` in
+# getCentre (ic.hpp:1384) stay in force for every number logged afterwards. fmtg() formats like that stream.
+_precision = [6]
+
+
+def set_log_precision(p):
+    _precision[0] = int(p)
+
+
+def fmtg(v):
+    return "%.*g" % (_precision[0], float(v))
+
+
 def set_logger(fn):
     """Where the reference's classes write to logging::entry() (warnings of the modifications, the chi^2 lines of
     ModificationManager::applyModifications); None = silent."""
@@ -557,8 +570,8 @@ class FilteredVarianceModification:
         _warnIfWholeZoomGridIsFlagged(context)
         window_size = _flaggedCellsPhysicalSize(fine)
         if filterscale > window_size:                       # checkFilterScale, quadraticmodification.hpp:128-149
-            log("WARNING: High-pass filtering scale: %g h**-1 Mpc is greater than the rough window size: %g h**-1 Mpc used "
-                "for modifications." % (filterscale, window_size))
+            log("WARNING: High-pass filtering scale: %s h**-1 Mpc is greater than the rough window size: %s h**-1 Mpc used "
+                "for modifications." % (fmtg(filterscale), fmtg(window_size)))
             log("This is prone to numerical errors when modifying the field. Decrease filtering scale to avoid it.")
         self.context, self.cosmology, self.scale = context, cosmology, float(filterscale)
         self.initNumberSteps, self.targetPrecision = initNumberSteps, targetPrecision
@@ -657,8 +670,8 @@ class ModificationManager:
         self._applyModifications()
         if logging:
             post = self.outputField.getChi2()
-            log("   Post-modification chi^2 = %g" % post)
-            log("  Modification Delta chi^2 = %g" % (post - pre))
+            log("   Post-modification chi^2 = %s" % fmtg(post))
+            log("  Modification Delta chi^2 = %s" % fmtg(post - pre))
             log("           d.o.f. in field = %d" % self.context.getNumDof())
             log("")
 

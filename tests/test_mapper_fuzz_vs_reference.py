@@ -56,3 +56,18 @@ def test_random_grafic_paramfiles_match_the_reference_binary(tmp_path):
         compared += 1
         assert not diffs, (diffs[:4], body)
     assert compared >= 10
+
+
+def test_random_modification_paramfiles_match_the_reference_binary(tmp_path):
+    """Linear modifications (overdensity, potential, velocity, angular momentum), splice, reversal, chi2, dump_grid, dump_ps on
+    one and two levels in the three draw orders (variance modifications are left to the tool: minutes on the mock device)."""
+    rng = random.Random(11)
+    compared = 0
+    for it in range(24):
+        body = fuzz.make_modification_case(rng, allow_variance=False)
+        diffs = fuzz.compare_modifications(body, str(tmp_path / ("m%d" % it)))
+        if diffs is None:
+            continue
+        compared += 1
+        assert not diffs, (diffs[:4], body)
+    assert compared >= 10
