@@ -855,14 +855,11 @@ public:
     for (size_t level = nl - 2; level >= 1; --level) {
       const auto &cur = this->context.getGridForLevel(level);
       const auto &above = this->context.getGridForLevel(level - 1);
-      const long ratio = std::lround((double) above.cellSize / (double) cur.cellSize), n = (long) cur.size, na = (long) above.size;
-      long corner[3];
-      for (int a = 0; a < 3; ++a) corner[a] = std::lround((double) (cur.offsetLower[a] - above.offsetLower[a]) / (double) above.cellSize);
-      std::vector<size_t> cells;
-      for (size_t id : z[level]) {
-        const long c[3] = {(long) (id / (size_t) (n * n)), (long) ((id / (size_t) n) % (size_t) n), (long) (id % (size_t) n)};
-        cells.push_back((size_t) (((corner[0] + c[0] / ratio) * na + (corner[1] + c[1] / ratio)) * na + (corner[2] + c[2] / ratio)));
-      }
+      const long na = (long) above.size;
+      // the parents of this level's zoom cells on the level above (makeProxyGridToMatch: periodic section + subsample)
+      grids::Grid<T> src(cur.periodicDomainSize, cur.size, cur.cellSize, cur.offsetLower[0], cur.offsetLower[1], cur.offsetLower[2]);
+      src.flagCells(z[level]);
+      std::vector<size_t> cells = zoom::proxyFlags<T>(src, above);
       auto uniq = [](std::vector<size_t> &v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
       uniq(cells);
       for (size_t it = 0; it < nPadCells; ++it)

@@ -198,3 +198,29 @@ def test_cpp_masks_match_the_reference_binary(golden_dir, tmp_path):
             assert np.array_equal(np.load(f), np.load(str(ours / os.path.basename(f)))), (name, os.path.basename(f))
             checked += 1
     assert checked >= 15
+
+
+def test_cpp_geometry_ids_match_the_reference_binary_on_random_paramfiles(tmp_path):
+    """Selection (sphere, cube, ellipse), zoom placement (also across the box edge), gas, adapt_mask and the flagged particle
+    type in the C++ driver: the id list of the final selection against the reference binary's on random geometry
+    (tools/fuzz_vs_reference.py; this comparison found a missing periodic wrap in the C++ adapt_mask)."""
+    import importlib.util
+    import random
+    import oracle
+    if oracle.ref_binary() is None:
+        pytest.skip("oracle/_ref/genetIC not built")
+    spec = importlib.util.spec_from_file_location("gx_fuzz", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_vs_reference.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    exe = gbuild.build_host(program="genetic_b200_modify")
+    compared = 0
+    for seed in (3, 4):
+        rng = random.Random(seed)
+        for it in range(30):
+            body = fuzz.make_geometry_case(rng)
+            diffs = fuzz.compare_cpp_ids(body, str(tmp_path / ("s%dc%d" % (seed, it))), exe)
+            if diffs is None:
+                continue
+            compared += 1
+            assert not diffs, (diffs, body)
+    assert compared >= 20

@@ -238,6 +238,55 @@ def compare_modifications(body, workdir):
     return diffs
 
 
+def make_geometry_case(rng):
+    """Geometry only (for the C++ driver without a device): 1-2 zooms selected by sphere / cube / ellipse, gas, adapt_mask, a
+    final selection, flagged particle type, then dump_idfile."""
+    L, n = rng.choice([40.0, 50.0, 64.0]), rng.choice([8, 16])
+    fmt = rng.choice(["tipsy", "gadget2", "gadget3"])
+    s = ("Ob 0.04\n" if rng.random() < 0.4 else "") + "random_seed_real_space 5\noutformat %s\n" % fmt
+    if rng.random() < 0.25:
+        s += "baryons_all_levels\n"
+    s += "basegrid %g %d\n" % (L, n)
+    nz, size, prev = rng.choice([1, 1, 2]), L, None
+    for z in range(nz):
+        c = prev if z == 1 else [rng.uniform(0, L) for _ in range(3)]
+        zf = rng.choice([2, 2, 4]) if n // 4 >= 2 else 2
+        sel = rng.choice(["sphere", "cube", "ellipse"])
+        r = size / zf * rng.uniform(0.15, 0.35)
+        arg = "%g" % r if sel == "sphere" else ("%g" % (1.5 * r) if sel == "cube" else "%g %g %g" % (r, 0.8 * r, 0.6 * r))
+        s += "centre %g %g %g\nselect_%s %s\nzoomgrid %d %d\n" % (c[0], c[1], c[2], sel, arg, zf, n)
+        prev, size = c, size / zf
+    if nz == 2 and rng.random() < 0.4:
+        s += "adapt_mask %d\n" % rng.choice([1, 2])
+    c = [prev[a] + rng.uniform(-0.1, 0.1) * size for a in range(3)]
+    s += "centre %g %g %g\nselect_%s %g\n" % (c[0], c[1], c[2], rng.choice(["sphere", "cube"]), size * rng.uniform(0.1, 0.3))
+    if fmt != "tipsy" and rng.random() < 0.3:
+        s += "gadget_flagged_particle_type %d\n" % rng.choice([2, 3])
+    return s + "dump_idfile ids_out.txt\n"
+
+
+def compare_cpp_ids(body, workdir, exe):
+    """The id list the C++ driver (host/genetic_b200_modify, no `done`: no device needed) dumps against the reference binary's."""
+    import subprocess
+    import oracle
+    shutil.rmtree(workdir, ignore_errors=True)
+    try:
+        oracle.run_ref(HEAD + body + "done\n", os.path.join(workdir, "ref"), [CAMB])
+    except Exception:
+        return None
+    ours = os.path.join(workdir, "ours")
+    os.makedirs(ours)
+    shutil.copy(CAMB, ours)
+    with open(os.path.join(ours, "paramfile.txt"), "w") as f:
+        f.write(HEAD + body)
+    r = subprocess.run([exe, "paramfile.txt"], cwd=ours, capture_output=True, text=True)
+    if r.returncode != 0:
+        return ["C++ driver failed: " + r.stderr.strip()[-200:]]
+    a = open(os.path.join(workdir, "ref", "ids_out.txt")).read().split()
+    b = open(os.path.join(ours, "ids_out.txt")).read().split()
+    return [] if a == b else ["ids differ (%d vs %d)" % (len(a), len(b))]
+
+
 def install_mock():
     spec = importlib.util.spec_from_file_location("gx_mock_device", os.path.join(ROOT, "tests", "host", "mock_device.py"))
     m = importlib.util.module_from_spec(spec)
