@@ -10,6 +10,7 @@ velocity offset, all three particle formats. Cases the reference itself refuses 
   python tools/fuzz_vs_reference.py [seed] [cases] [--strays2]     # --strays2: stray particles below a second zoom, always
   python tools/fuzz_vs_reference.py [seed] [cases] --grafic        # grafic output and dump_mask instead of particle files
   python tools/fuzz_vs_reference.py [seed] [cases] --modifications # modifications, splice, reversal, chi2, dump_grid, dump_ps
+  python tools/fuzz_vs_reference.py [seed] [cases] --relative      # ids of one random setup re-expressed in another (mapper_relative_to)
 Development tool for the build container (needs the reference binary); tests/test_mapper_fuzz_vs_reference.py runs a fixed set.
 """
 import glob
@@ -287,6 +288,60 @@ def compare_cpp_ids(body, workdir, exe):
     return [] if a == b else ["ids differ (%d vs %d)" % (len(a), len(b))]
 
 
+def make_relative_case(rng):
+    """`mapper_relative_to`: two independent random setups on the same base grid (0-2 zooms each, sub/supersampling, gas), a
+    random id list that refers to the other one, `idfile` then `dump_idfile`. Returns (main paramfile, other paramfile, ids)."""
+    L, n, fmt = rng.choice([40.0, 50.0]), rng.choice([8, 16]), rng.choice(["tipsy", "gadget3"])
+    head = ("Ob 0.04\n" if rng.random() < 0.3 else "") + "random_seed_real_space 5\noutformat %s\n" % fmt
+
+    def geometry():
+        s = "basegrid %g %d\n" % (L, n)
+        nz, size, prev = rng.choice([0, 1, 1, 2]), L, None
+        for z in range(nz):
+            c = prev if z == 1 else [rng.uniform(0, L) for _ in range(3)]
+            zf = rng.choice([2, 2, 4]) if n // 4 >= 2 else 2
+            s += "centre %g %g %g\nselect_%s %g\nzoomgrid %d %d\n" % (c[0], c[1], c[2], rng.choice(["sphere", "cube"]),
+                                                                     size / zf * rng.uniform(0.15, 0.35), zf, n)
+            prev, size = c, size / zf
+        if rng.random() < 0.3:
+            s += "supersample 2\n"
+        if rng.random() < 0.3 and n >= 16:
+            s += "subsample 2\n"
+        return s
+    other = HEAD + head + geometry() + "done\n"
+    ids = sorted(rng.sample(range(0, n ** 3 // 2), rng.choice([1, 5, 40])))
+    main = head + geometry() + "mapper_relative_to other.txt\n%s ids.txt\ndump_idfile ids_out.txt\n" % rng.choice(["idfile", "IDfile", "id_file"])
+    return main, other, ids
+
+
+def compare_relative_ids(case, workdir):
+    import oracle
+    from genetic_b200 import icgen
+    main, other, ids = case
+    shutil.rmtree(workdir, ignore_errors=True)
+    for side in ("ref", "ours"):
+        d = os.path.join(workdir, side)
+        os.makedirs(d)
+        with open(os.path.join(d, "other.txt"), "w") as f:
+            f.write(other)
+        with open(os.path.join(d, "ids.txt"), "w") as f:
+            f.write("\n".join(map(str, ids)) + "\n")
+        shutil.copy(CAMB, d)
+    try:
+        oracle.run_ref(HEAD + main + "done\n", os.path.join(workdir, "ref"), [])
+    except Exception:
+        return None
+    with open(os.path.join(workdir, "ours", "paramfile.txt"), "w") as f:
+        f.write(HEAD + main)
+    try:
+        icgen.run_paramfile(os.path.join(workdir, "ours", "paramfile.txt"), log=lambda t: None)
+    except Exception as e:
+        return ["ours failed: " + "".join(traceback.format_exception_only(type(e), e)).strip()[:300]]
+    a = open(os.path.join(workdir, "ref", "ids_out.txt")).read().split()
+    b = open(os.path.join(workdir, "ours", "ids_out.txt")).read().split()
+    return [] if a == b else ["ids differ (%d vs %d)" % (len(a), len(b))]
+
+
 def install_mock():
     spec = importlib.util.spec_from_file_location("gx_mock_device", os.path.join(ROOT, "tests", "host", "mock_device.py"))
     m = importlib.util.module_from_spec(spec)
@@ -347,13 +402,18 @@ def main():
     strays2 = "--strays2" in sys.argv
     grafic = "--grafic" in sys.argv
     modif = "--modifications" in sys.argv
+    relative = "--relative" in sys.argv
     rng = random.Random(int(args[0]) if args else 1)
     cases = int(args[1]) if len(args) > 1 else 20
     install_mock()
     done = bad = 0
     for it in range(cases):
-        body = make_modification_case(rng) if modif else (make_grafic_case(rng) if grafic else make_case(rng, strays2))
-        d = (compare_modifications if modif else (compare_grafic if grafic else compare))(body, "/tmp/gx_fuzz/case%d" % it)
+        if relative:
+            case = make_relative_case(rng)
+            body, d = case[0] + "  [other: " + case[1][len(HEAD):] + "]", compare_relative_ids(case, "/tmp/gx_fuzz/case%d" % it)
+        else:
+            body = make_modification_case(rng) if modif else (make_grafic_case(rng) if grafic else make_case(rng, strays2))
+            d = (compare_modifications if modif else (compare_grafic if grafic else compare))(body, "/tmp/gx_fuzz/case%d" % it)
         if d is None:
             continue
         done += 1
